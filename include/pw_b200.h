@@ -1,0 +1,178 @@
+/*
+ * pw_b200.h -- C ABI of libpwb200.so: the B200 (sm_100a) drop-in for the
+ * array-only seam of tqsd/photon_weave (photon_weave/core/adapters.py).
+ *
+ * The reference has no FFI of its own (it is pure Python on JAX); the seam a
+ * replacement must bind is the function set of photon_weave/core/adapters.py
+ * (SURVEY.md section 8b).  Each entry point below names the reference function
+ * (file:line under /root/reference) whose arithmetic it replaces.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no framework types.
+ *  - All state/operator pointers are DEVICE pointers unless the function name
+ *    ends in _host.  Every device entry point only ENQUEUES work on `stream`
+ *    (a cudaStream_t passed as void*; NULL = legacy default stream): it never
+ *    synchronises and never throws.  Return value: PW_OK or a PW_ERR_* code.
+ *  - Layout: flat row-major tensor, subsystem 0 most significant; a state vector
+ *    has prod(dims) elements, a density matrix prod(dims)^2 (row index = ket).
+ *    Elements are interleaved complex: PW_C64 = 2 x float, PW_C128 = 2 x double.
+ *  - `targets` are subsystem indices in the ORDER the operator's indices are
+ *    factored (photon_weave/core/adapters.py:53 `perm = list(target_indices)+rest`);
+ *    the tensor order of the state is never changed by apply/Kraus.
+ *  - Operators are dense row-major (t x t), t = prod(dims[targets]), in the SAME
+ *    dtype as the state (the Python host promotes, as JAX does).
+ *  - `out` may alias the input state for pw_apply_vec / pw_apply_mat /
+ *    pw_kraus_mat (in-place update); otherwise buffers must not overlap.
+ *  - Probabilities are real arrays in the state's real dtype (float for PW_C64,
+ *    double for PW_C128), normalised to sum 1, indexed in target-given order.
+ */
+#ifndef PW_B200_H
+#define PW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PW_B200_VERSION 100 /* major*10000 + minor*100 + patch */
+
+enum { PW_C64 = 0, PW_C128 = 1 };
+
+enum {
+  PW_OK = 0,
+  PW_ERR_INVALID = 1,     /* bad dims/targets/null pointer                      */
+  PW_ERR_UNSUPPORTED = 2, /* shape outside what the kernels cover               */
+  PW_ERR_CUDA = 3,        /* a CUDA runtime call failed (pw_last_cuda_error())  */
+  PW_ERR_WORKSPACE = 4    /* stream-ordered workspace allocation failed         */
+};
+
+#define PW_MAX_SUBSYSTEMS 32
+#define PW_MAX_TARGETS 8
+
+int pw_version(void);
+const char* pw_status_string(int status);
+/* cudaError_t of the last failing CUDA call on this host thread (0 if none). */
+int pw_last_cuda_error(void);
+/* Number of kernels this library has launched since load (bench "gpu_launches"). */
+uint64_t pw_launch_count(void);
+
+/* ---- apply ------------------------------------------------------------------ */
+
+/* psi' = (O on targets) psi.
+ * Replaces kernels.apply_op_vector_ordered (core/kernels.py:62-98) and the
+ * reorder/einsum/restore around it in adapters.apply_operation_vector
+ * (core/adapters.py:299-345), both use_contraction routes. */
+int pw_apply_vec(const void* psi, void* out, const void* op, const int64_t* dims, int n,
+                 const int32_t* targets, int nt, int dtype, void* stream);
+
+/* rho' = (O x I) rho (O x I)^dagger.
+ * Replaces kernels.apply_op_matrix_ordered (core/kernels.py:101-145) and
+ * adapters.apply_operation_matrix (core/adapters.py:348-393). */
+int pw_apply_mat(const void* rho, void* out, const void* op, const int64_t* dims, int n,
+                 const int32_t* targets, int nt, int dtype, void* stream);
+
+/* rho' = sum_k (K_k x I) rho (K_k x I)^dagger, ops stacked (K, t, t).
+ * Replaces kernels.apply_kraus_matrix_ordered (core/kernels.py:148-186),
+ * adapters.apply_kraus_matrix (core/adapters.py:396-466) and the un-embedded
+ * _math/ops.apply_kraus (_math/ops.py:371-403, dims = (d,)). */
+int pw_kraus_mat(const void* rho, void* out, const void* ops, int K, const int64_t* dims,
+                 int n, const int32_t* targets, int nt, int dtype, void* stream);
+
+/* ---- reductions ---------------------------------------------------------------- */
+
+/* out (t x t) = Tr_rest rho, kept subsystems ordered as listed in `keep`.
+ * Replaces kernels.trace_out_matrix_ordered (core/kernels.py:301-319) and
+ * adapters.trace_out_matrix (core/adapters.py:696-733): pass `keep` as given for
+ * the ordered route (:720,732), sorted ascending for the contraction route (:80-81). */
+int pw_trace_out_mat(const void* rho, void* out, const int64_t* dims, int n,
+                     const int32_t* keep, int nkeep, int dtype, void* stream);
+
+/* out (t x t) = Tr_rest |psi><psi| without materialising psi psi^dagger.
+ * Replaces state/utils/trace_out.trace_out_vector (state/utils/trace_out.py:17-25)
+ * and the second output of kernels.measure_vector_expectation_ordered
+ * (core/kernels.py:266-283) when `keep` is the unmeasured subsystems. */
+int pw_reduced_from_vec(const void* psi, void* out, const int64_t* dims, int n,
+                        const int32_t* keep, int nkeep, int dtype, void* stream);
+
+/* probs[j] = sum_rest |psi[j,rest]|^2 / sum_all.
+ * Replaces kernels._measurement_probs_vector (core/kernels.py:28-41). */
+int pw_probs_vec(const void* psi, void* probs, const int64_t* dims, int n,
+                 const int32_t* targets, int nt, int dtype, void* stream);
+
+/* probs[j] = real(sum_rest rho[(j,rest),(j,rest)]) / sum_all (reads only the diagonal).
+ * Replaces kernels._measurement_probs_matrix (core/kernels.py:44-59). */
+int pw_probs_mat(const void* rho, void* probs, const int64_t* dims, int n,
+                 const int32_t* targets, int nt, int dtype, void* stream);
+
+/* ---- sampling + collapse ---------------------------------------------------- */
+
+/* *outcome = jax.random.choice(key, a=t, p=probs): threefry2x32 bits of the
+ * scalar draw, cumsum, searchsorted-left; computed on the device, no host sync.
+ * Replaces the jax.random.choice call sites core/kernels.py:204,224,243,261,341. */
+int pw_draw(const void* probs, int64_t t, uint32_t key0, uint32_t key1, int dtype,
+            int64_t* outcome, void* stream);
+
+/* post (r) = psi[outcome, :] / sqrt(probs[outcome] + 1e-18); rest in tensor order.
+ * `outcome` and `probs` are device pointers (outputs of pw_draw / pw_probs_vec).
+ * Replaces core/kernels.py:205 (and :244). */
+int pw_collapse_vec(const void* psi, void* post, const int64_t* outcome, const void* probs,
+                    const int64_t* dims, int n, const int32_t* targets, int nt, int dtype,
+                    void* stream);
+
+/* post (r x r) = rho[outcome, :, outcome, :] / (probs[outcome] + 1e-18).
+ * Replaces core/kernels.py:225-226 (and :262). */
+int pw_collapse_mat(const void* rho, void* post, const int64_t* outcome, const void* probs,
+                    const int64_t* dims, int n, const int32_t* targets, int nt, int dtype,
+                    void* stream);
+
+/* POVM probabilities from the reduced state of the targets:
+ * probs[k] = real Tr(E_k rho_T E_k^dagger) / sum, traces[k] = un-normalised value.
+ * rho_T is (t x t) (pw_trace_out_mat with keep = targets), ops (K, t, t).
+ * Replaces the K full-size projections + traces of
+ * kernels.measure_povm_matrix_ordered (core/kernels.py:331-339). */
+int pw_povm_probs(const void* rho_t, const void* ops, int K, int64_t t, void* probs,
+                  void* traces, int dtype, void* stream);
+
+/* op_out (t x t) = ops[*outcome] / sqrt(traces[*outcome] + 1e-18), so that
+ * pw_apply_mat(rho, op_out) is the POVM post state of core/kernels.py:342-343. */
+int pw_povm_select(const void* ops, int64_t t, const int64_t* outcome, const void* traces,
+                   void* op_out, int dtype, void* stream);
+
+/* ---- bookkeeping reductions the callers need ------- */
+
+/* stats[0] = sum |x|^2, stats[1] = max |x|^2 over `count` complex elements (doubles). */
+int pw_norm_stats(const void* x, int64_t count, int dtype, double* stats, void* stream);
+
+/* x *= *scale_dev (a device double); e.g. 1/sqrt(norm) for Operation.renormalize
+ * (state/composite_envelope.py:685-686). */
+int pw_scale(void* x, int64_t count, const double* scale_dev, int dtype, void* stream);
+
+/* ---- host-side PRNG key management (pure integer, no device) --------------- */
+
+/* out[i] = jax.random.split(key, num)[i] (partitionable threefry2x32).
+ * Replaces jax.random.split at core/rng.py:37, photon_weave.py:47. */
+int pw_rng_split(const uint32_t key[2], int num, uint32_t* out /* num x 2 */);
+
+/* ---- host-buffer entry points (end-to-end path: H2D + kernels + D2H) -------- */
+
+typedef struct {
+  int kind;          /* 0 = operator on a state vector, 1 = operator on a density
+                        matrix, 2 = Kraus channel on a density matrix              */
+  int nt;            /* number of target subsystems                               */
+  int32_t targets[PW_MAX_TARGETS];
+  int K;             /* number of Kraus operators (kind 2), else 1                */
+  const void* op;    /* HOST pointer, (K,) t x t row-major, state dtype           */
+} pw_host_op;
+
+/* Upload h_state (pageable or pinned host memory), run `nops` operations in
+ * order on the device, download into h_out (may alias h_state).  is_matrix
+ * selects vector / density-matrix layout.  Synchronises before returning. */
+int pw_circuit_host(const void* h_state, void* h_out, int is_matrix, const int64_t* dims,
+                    int n, const pw_host_op* ops, int nops, int dtype, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PW_B200_H */

@@ -1,0 +1,211 @@
+"""
+Tensor-level wrappers over the C ABI (include/pw_b200.h): each function takes
+CUDA ``torch.Tensor`` buffers, passes raw device pointers + the current stream to
+libpwb200 and returns freshly allocated outputs.  No arithmetic happens here.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from .. import _lib
+from . import _arrays as A
+
+
+def _common(dims: Sequence[int], idx: Sequence[int]):
+    return _lib.i64_array(dims), len(dims), _lib.i32_array(idx), len(idx)
+
+
+def apply_vec(psi: torch.Tensor, op: torch.Tensor, dims, targets, out: Optional[torch.Tensor] = None):
+    lib = _lib.load()
+    out = torch.empty_like(psi) if out is None else out
+    d, n, t, nt = _common(dims, targets)
+    _lib.check(
+        lib.pw_apply_vec(psi.data_ptr(), out.data_ptr(), op.data_ptr(), d, n, t, nt,
+                         A.code(psi.dtype), A.stream_ptr()),
+        "pw_apply_vec",
+    )
+    return out
+
+
+def apply_mat(rho: torch.Tensor, op: torch.Tensor, dims, targets, out: Optional[torch.Tensor] = None):
+    lib = _lib.load()
+    out = torch.empty_like(rho) if out is None else out
+    d, n, t, nt = _common(dims, targets)
+    _lib.check(
+        lib.pw_apply_mat(rho.data_ptr(), out.data_ptr(), op.data_ptr(), d, n, t, nt,
+                         A.code(rho.dtype), A.stream_ptr()),
+        "pw_apply_mat",
+    )
+    return out
+
+
+def kraus_mat(rho: torch.Tensor, ops: torch.Tensor, dims, targets, out: Optional[torch.Tensor] = None):
+    lib = _lib.load()
+    out = torch.empty_like(rho) if out is None else out
+    d, n, t, nt = _common(dims, targets)
+    _lib.check(
+        lib.pw_kraus_mat(rho.data_ptr(), out.data_ptr(), ops.data_ptr(), int(ops.shape[0]), d, n,
+                         t, nt, A.code(rho.dtype), A.stream_ptr()),
+        "pw_kraus_mat",
+    )
+    return out
+
+
+def trace_out_mat(rho: torch.Tensor, dims, keep):
+    lib = _lib.load()
+    t = math.prod(dims[i] for i in keep)
+    out = torch.empty((t, t), dtype=rho.dtype, device=rho.device)
+    d, n, k, nk = _common(dims, keep)
+    _lib.check(
+        lib.pw_trace_out_mat(rho.data_ptr(), out.data_ptr(), d, n, k, nk, A.code(rho.dtype),
+                             A.stream_ptr()),
+        "pw_trace_out_mat",
+    )
+    return out
+
+
+def reduced_from_vec(psi: torch.Tensor, dims, keep):
+    lib = _lib.load()
+    t = math.prod(dims[i] for i in keep)
+    out = torch.empty((t, t), dtype=psi.dtype, device=psi.device)
+    d, n, k, nk = _common(dims, keep)
+    _lib.check(
+        lib.pw_reduced_from_vec(psi.data_ptr(), out.data_ptr(), d, n, k, nk, A.code(psi.dtype),
+                                A.stream_ptr()),
+        "pw_reduced_from_vec",
+    )
+    return out
+
+
+def probs(state: torch.Tensor, dims, targets, is_matrix: bool):
+    lib = _lib.load()
+    t = math.prod(dims[i] for i in targets)
+    out = torch.empty((t,), dtype=A.real_dtype(state.dtype), device=state.device)
+    d, n, tg, nt = _common(dims, targets)
+    fn = lib.pw_probs_mat if is_matrix else lib.pw_probs_vec
+    _lib.check(
+        fn(state.data_ptr(), out.data_ptr(), d, n, tg, nt, A.code(state.dtype), A.stream_ptr()),
+        "pw_probs_mat" if is_matrix else "pw_probs_vec",
+    )
+    return out
+
+
+def draw(probs_t: torch.Tensor, key, cdtype: torch.dtype):
+    lib = _lib.load()
+    k0, k1 = A.key_words(key)
+    outcome = torch.empty((), dtype=torch.int64, device=probs_t.device)
+    _lib.check(
+        lib.pw_draw(probs_t.data_ptr(), int(probs_t.numel()), k0, k1, A.code(cdtype),
+                    outcome.data_ptr(), A.stream_ptr()),
+        "pw_draw",
+    )
+    return outcome
+
+
+def collapse(state: torch.Tensor, outcome: torch.Tensor, probs_t: torch.Tensor, dims, targets,
+             is_matrix: bool):
+    lib = _lib.load()
+    r = math.prod(dims) // math.prod(dims[i] for i in targets)
+    shape = (r, r) if is_matrix else (r, 1)
+    post = torch.empty(shape, dtype=state.dtype, device=state.device)
+    d, n, tg, nt = _common(dims, targets)
+    fn = lib.pw_collapse_mat if is_matrix else lib.pw_collapse_vec
+    _lib.check(
+        fn(state.data_ptr(), post.data_ptr(), outcome.data_ptr(), probs_t.data_ptr(), d, n, tg,
+           nt, A.code(state.dtype), A.stream_ptr()),
+        "pw_collapse_mat" if is_matrix else "pw_collapse_vec",
+    )
+    return post
+
+
+def povm_probs(rho_t: torch.Tensor, ops: torch.Tensor):
+    lib = _lib.load()
+    K, t = int(ops.shape[0]), int(rho_t.shape[0])
+    rdt = A.real_dtype(rho_t.dtype)
+    p = torch.empty((K,), dtype=rdt, device=rho_t.device)
+    tr = torch.empty((K,), dtype=rdt, device=rho_t.device)
+    _lib.check(
+        lib.pw_povm_probs(rho_t.data_ptr(), ops.data_ptr(), K, t, p.data_ptr(), tr.data_ptr(),
+                          A.code(rho_t.dtype), A.stream_ptr()),
+        "pw_povm_probs",
+    )
+    return p, tr
+
+
+def povm_select(ops: torch.Tensor, outcome: torch.Tensor, traces: torch.Tensor):
+    lib = _lib.load()
+    t = int(ops.shape[-1])
+    out = torch.empty((t, t), dtype=ops.dtype, device=ops.device)
+    _lib.check(
+        lib.pw_povm_select(ops.data_ptr(), t, outcome.data_ptr(), traces.data_ptr(),
+                           out.data_ptr(), A.code(ops.dtype), A.stream_ptr()),
+        "pw_povm_select",
+    )
+    return out
+
+
+def norm_stats(x: torch.Tensor):
+    """Device tensor [sum |x|^2, max |x|^2] (float64), no host sync."""
+    lib = _lib.load()
+    stats = torch.empty((2,), dtype=torch.float64, device=x.device)
+    _lib.check(
+        lib.pw_norm_stats(x.data_ptr(), int(x.numel()), A.code(x.dtype), stats.data_ptr(),
+                          A.stream_ptr()),
+        "pw_norm_stats",
+    )
+    return stats
+
+
+def scale_(x: torch.Tensor, scale_dev: torch.Tensor):
+    lib = _lib.load()
+    _lib.check(
+        lib.pw_scale(x.data_ptr(), int(x.numel()), scale_dev.data_ptr(), A.code(x.dtype),
+                     A.stream_ptr()),
+        "pw_scale",
+    )
+    return x
+
+
+def rng_split(key, num: int = 2) -> np.ndarray:
+    lib = _lib.load()
+    k0, k1 = A.key_words(key)
+    kin = (C.c_uint32 * 2)(k0, k1)
+    out = (C.c_uint32 * (2 * num))()
+    _lib.check(lib.pw_rng_split(kin, num, out), "pw_rng_split")
+    return np.frombuffer(out, dtype=np.uint32).reshape(num, 2).copy()
+
+
+def circuit_host(h_state: np.ndarray, is_matrix: bool, dims, ops_list, device: int = 0,
+                 out: Optional[np.ndarray] = None) -> np.ndarray:
+    """
+    End-to-end host-buffer path (pw_circuit_host): ops_list holds
+    (kind, targets, operator ndarray) with kind 0 vector-op, 1 matrix-op, 2 Kraus.
+    """
+    lib = _lib.load()
+    cdt = np.complex128 if h_state.dtype == np.complex128 else np.complex64
+    h_state = np.ascontiguousarray(h_state, dtype=cdt)
+    out = np.empty_like(h_state) if out is None else out
+    arr = (_lib.pw_host_op * max(len(ops_list), 1))()
+    keep = []
+    for i, (kind, targets, op) in enumerate(ops_list):
+        op = np.ascontiguousarray(op, dtype=cdt)
+        keep.append(op)
+        arr[i].kind = int(kind)
+        arr[i].nt = len(targets)
+        for k, tg in enumerate(targets):
+            arr[i].targets[k] = int(tg)
+        arr[i].K = int(op.shape[0]) if kind == 2 else 1
+        arr[i].op = op.ctypes.data
+    _lib.check(
+        lib.pw_circuit_host(h_state.ctypes.data, out.ctypes.data, int(is_matrix),
+                            _lib.i64_array(dims), len(dims), arr, len(ops_list),
+                            _lib.PW_C128 if cdt == np.complex128 else _lib.PW_C64, device),
+        "pw_circuit_host",
+    )
+    return out

@@ -1,0 +1,76 @@
+// Host-buffer entry point: the end-to-end path a caller with NumPy/host arrays
+// takes (H2D upload, the operation list on the device, D2H download).
+#include <vector>
+
+#include "pw_internal.cuh"
+
+using namespace pw;
+
+namespace {
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+};
+struct Stream {
+  cudaStream_t s = nullptr;
+  ~Stream() { if (s) cudaStreamDestroy(s); }
+};
+}  // namespace
+
+extern "C" int pw_circuit_host(const void* h_state, void* h_out, int is_matrix,
+                               const int64_t* dims, int n, const pw_host_op* ops, int nops,
+                               int dtype, int device) {
+  if (!h_state || !h_out || !dims || n < 1 || n > PW_MAX_SUBSYSTEMS || nops < 0 || (nops && !ops))
+    return PW_ERR_INVALID;
+  if (dtype != PW_C64 && dtype != PW_C128) return PW_ERR_INVALID;
+  PW_CUDA(cudaSetDevice(device));
+  const size_t es = dtype == PW_C128 ? 16 : 8;
+  uint64_t N = 1;
+  for (int i = 0; i < n; ++i) {
+    if (dims[i] < 1) return PW_ERR_INVALID;
+    N *= (uint64_t)dims[i];
+  }
+  const uint64_t count = is_matrix ? N * N : N;
+  const size_t bytes = count * es;
+
+  Stream st;
+  PW_CUDA(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
+  DevBuf state;
+  PW_CUDA(cudaMalloc(&state.p, bytes));
+
+  // operators: one small upload each, queued ahead of the state so they overlap it
+  std::vector<DevBuf> dops(nops);
+  for (int i = 0; i < nops; ++i) {
+    const pw_host_op& o = ops[i];
+    if (o.nt < 1 || o.nt > PW_MAX_TARGETS || !o.op) return PW_ERR_INVALID;
+    if ((o.kind != 0) != (is_matrix != 0)) return PW_ERR_INVALID;
+    uint64_t t = 1;
+    for (int k = 0; k < o.nt; ++k) {
+      if (o.targets[k] < 0 || o.targets[k] >= n) return PW_ERR_INVALID;
+      t *= (uint64_t)dims[o.targets[k]];
+    }
+    const int K = o.kind == 2 ? o.K : 1;
+    if (K < 1) return PW_ERR_INVALID;
+    const size_t ob = (size_t)K * t * t * es;
+    PW_CUDA(cudaMalloc(&dops[i].p, ob));
+    PW_CUDA(cudaMemcpyAsync(dops[i].p, o.op, ob, cudaMemcpyHostToDevice, st.s));
+  }
+  PW_CUDA(cudaMemcpyAsync(state.p, h_state, bytes, cudaMemcpyHostToDevice, st.s));
+  for (int i = 0; i < nops; ++i) {
+    const pw_host_op& o = ops[i];
+    int rc;
+    if (o.kind == 0)
+      rc = pw_apply_vec(state.p, state.p, dops[i].p, dims, n, o.targets, o.nt, dtype, st.s);
+    else if (o.kind == 1)
+      rc = pw_apply_mat(state.p, state.p, dops[i].p, dims, n, o.targets, o.nt, dtype, st.s);
+    else
+      rc = pw_kraus_mat(state.p, state.p, dops[i].p, o.K, dims, n, o.targets, o.nt, dtype, st.s);
+    if (rc != PW_OK) {
+      cudaStreamSynchronize(st.s);
+      return rc;
+    }
+  }
+  PW_CUDA(cudaMemcpyAsync(h_out, state.p, bytes, cudaMemcpyDeviceToHost, st.s));
+  PW_CUDA(cudaStreamSynchronize(st.s));
+  return PW_OK;
+}

@@ -1,0 +1,172 @@
+// Internal shared definitions for libpwb200 (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "pw_b200.h"
+
+namespace pw {
+
+constexpr int kMaxAxes = 2 * PW_MAX_SUBSYSTEMS;  // density matrices double the axes
+constexpr int kMaxTargets = 2 * PW_MAX_TARGETS;  // row + column targets of a matrix
+constexpr int kMaxGroups = kMaxTargets + 1;      // runs of non-target axes
+constexpr int kNumSMs = 148;                     // B200
+
+// ---- complex helpers ------------------------------------------------------------
+template <typename R> struct CplxOf;
+template <> struct CplxOf<float> { using type = float2; };
+template <> struct CplxOf<double> { using type = double2; };
+template <typename V> struct RealOf;
+template <> struct RealOf<float2> { using type = float; };
+template <> struct RealOf<double2> { using type = double; };
+
+template <typename V>
+__host__ __device__ __forceinline__ V czero() {
+  V z; z.x = 0; z.y = 0; return z;
+}
+// acc += a * b
+template <typename V>
+__device__ __forceinline__ void cfma(V& acc, const V a, const V b) {
+  acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+// acc += conj(a) * b
+template <typename V>
+__device__ __forceinline__ void cfma_conja(V& acc, const V a, const V b) {
+  acc.x = fma(a.x, b.x, acc.x); acc.x = fma(a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y); acc.y = fma(-a.y, b.x, acc.y);
+}
+template <typename V>
+__device__ __forceinline__ typename RealOf<V>::type cabs2(const V a) {
+  return fma(a.x, a.x, a.y * a.y);
+}
+
+// ---- index maps -------------------------------------------------------------------
+// The state is a row-major tensor.  Target axes (in operator order) carry the
+// operator index j = mixed-radix(tdim) -> element offset sum digit*tstride.  The
+// remaining axes are merged into runs ("groups") of consecutive axes; a fiber id
+// f in [0, nfib) is mixed-radix over the groups in tensor order (last fastest).
+// `estride` multiplies every offset (N+1 walks the diagonal of a density matrix).
+struct FiberMap {
+  int ng;
+  uint64_t gsize[kMaxGroups];
+  int64_t gstride[kMaxGroups];
+  uint64_t nfib;
+
+  __host__ __device__ __forceinline__ int64_t base(uint64_t f) const {
+    int64_t off = 0;
+    if (nfib <= 0xffffffffull) {
+      uint32_t g = (uint32_t)f;
+#pragma unroll 1
+      for (int i = ng - 1; i > 0; --i) {
+        uint32_t gs = (uint32_t)gsize[i];
+        uint32_t q = g / gs;
+        off += (int64_t)(g - q * gs) * gstride[i];
+        g = q;
+      }
+      if (ng > 0) off += (int64_t)g * gstride[0];
+    } else {
+#pragma unroll 1
+      for (int i = ng - 1; i > 0; --i) {
+        uint64_t q = f / gsize[i];
+        off += (int64_t)(f - q * gsize[i]) * gstride[i];
+        f = q;
+      }
+      if (ng > 0) off += (int64_t)f * gstride[0];
+    }
+    return off;
+  }
+};
+
+struct TargetMap {
+  int nt;
+  uint32_t tdim[kMaxTargets];
+  int64_t tstride[kMaxTargets];
+  uint32_t t;  // prod(tdim)
+
+  __host__ __device__ __forceinline__ int64_t offset(uint32_t j) const {
+    int64_t off = 0;
+#pragma unroll 1
+    for (int i = nt - 1; i >= 0; --i) {
+      uint32_t q = j / tdim[i];
+      off += (int64_t)(j - q * tdim[i]) * tstride[i];
+      j = q;
+    }
+    return off;
+  }
+};
+
+struct Plan {
+  uint64_t N;  // total elements of the tensor the maps index
+  FiberMap fm;
+  TargetMap tm;
+};
+
+// Build maps for a tensor with `n` axes `dims` and target axes `targets` (given
+// order).  Returns PW_OK / PW_ERR_INVALID.
+int build_plan(const int64_t* dims, int n, const int32_t* targets, int nt, Plan* plan);
+// Doubled (density-matrix) tensor: axes dims ++ dims, targets rows then columns.
+int build_plan_matrix(const int64_t* dims, int n, const int32_t* targets, int nt,
+                      bool rows, bool cols, Plan* plan);
+
+// ---- bookkeeping -----------------------------------------------------------------
+extern std::atomic<uint64_t> g_launches;
+extern thread_local int g_last_cuda_error;
+
+inline int cuda_status(cudaError_t e) {
+  if (e == cudaSuccess) return PW_OK;
+  g_last_cuda_error = (int)e;
+  return PW_ERR_CUDA;
+}
+#define PW_CUDA(call)                                   \
+  do {                                                  \
+    int _s = ::pw::cuda_status((call));                 \
+    if (_s != PW_OK) return _s;                         \
+  } while (0)
+#define PW_TRY(call)                \
+  do {                              \
+    int _s = (call);                \
+    if (_s != PW_OK) return _s;     \
+  } while (0)
+#define PW_LAUNCHED()                                   \
+  do {                                                  \
+    ::pw::g_launches.fetch_add(1, std::memory_order_relaxed); \
+    PW_CUDA(cudaGetLastError());                        \
+  } while (0)
+
+inline int grid_for(uint64_t work_items, int block, int max_ctas_per_sm) {
+  uint64_t g = (work_items + block - 1) / block;
+  uint64_t cap = (uint64_t)kNumSMs * max_ctas_per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// Stream-ordered scratch buffer (freed on the same stream when it goes out of scope).
+struct Scratch {
+  void* p = nullptr;
+  cudaStream_t s = nullptr;
+  int alloc(size_t bytes, cudaStream_t stream) {
+    s = stream;
+    if (cudaMallocAsync(&p, bytes ? bytes : 16, stream) != cudaSuccess) {
+      p = nullptr;
+      (void)cudaGetLastError();
+      return PW_ERR_WORKSPACE;
+    }
+    return PW_OK;
+  }
+  ~Scratch() {
+    if (p) cudaFreeAsync(p, s);
+  }
+};
+
+// ---- internal launchers (one per .cu) ------------------------------------------
+// out = [out +] (O on plan.tm) in;  conj_op: use conj(O).  in may alias out unless
+// accumulate.  `op` is a device pointer, row-major (t x t).
+int launch_apply(const void* in, void* out, const void* op, const Plan& plan, int dtype,
+                 bool conj_op, bool accumulate, cudaStream_t stream);
+
+}  // namespace pw

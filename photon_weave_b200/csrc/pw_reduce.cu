@@ -1,0 +1,650 @@
+// Reductions that follow an apply (rows a7-a12 of SURVEY.md section 8):
+// measurement probabilities, partial traces, collapse gathers, POVM weights.
+//
+// All floating-point reductions are two-stage and ORDER-DETERMINISTIC (per-thread
+// private accumulators -> fixed tree inside the block -> fixed-order sum over
+// blocks): the same input always yields bit-identical probabilities, so the
+// sampled outcome under a fixed key is reproducible run to run.
+#include "pw_internal.cuh"
+#include "pw_threefry.h"
+
+namespace pw {
+
+constexpr int kRedBlock = 128;
+constexpr int kRedMaxBlocks = kNumSMs * 4;
+constexpr size_t kRedSmemBudget = 160 * 1024;
+
+// deterministic in-block tree sum of one double per thread; result valid in thread 0
+__device__ __forceinline__ double block_sum(double v, double* s_scratch) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) s_scratch[warp] = v;
+  __syncthreads();
+  double r = 0;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) r += s_scratch[w];
+  return r;
+}
+
+// ---- measurement probabilities -------------------------------------------------------
+// partial[b][j] = sum over the fibers block b owns of |x[fiber, j]|^2
+template <typename V>
+__global__ void __launch_bounds__(kRedBlock)
+k_probs_partial(const V* __restrict__ x, const FiberMap fm, const TargetMap tm,
+                const int64_t mult, double* __restrict__ partial) {
+  extern __shared__ double s_acc[];  // [t][blockDim] then scratch[4] then off[t]
+  const uint32_t t = tm.t;
+  double* s_scratch = s_acc + (size_t)t * blockDim.x;
+  int64_t* s_off = (int64_t*)(s_scratch + 4);
+  for (uint32_t j = threadIdx.x; j < t; j += blockDim.x) s_off[j] = tm.offset(j) * mult;
+  for (uint32_t j = 0; j < t; ++j) s_acc[(size_t)j * blockDim.x + threadIdx.x] = 0.0;
+  __syncthreads();
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < fm.nfib; f += stride) {
+    const int64_t base = fm.base(f) * mult;
+    for (uint32_t j = 0; j < t; ++j) {
+      const V v = x[base + s_off[j]];
+      s_acc[(size_t)j * blockDim.x + threadIdx.x] += (double)v.x * v.x + (double)v.y * v.y;
+    }
+  }
+  for (uint32_t j = 0; j < t; ++j) {
+    double r = block_sum(s_acc[(size_t)j * blockDim.x + threadIdx.x], s_scratch);
+    if (threadIdx.x == 0) partial[(size_t)blockIdx.x * t + j] = r;
+  }
+}
+
+// density-matrix diagonal: only the real part is summed (core/kernels.py:57)
+template <typename V>
+__global__ void __launch_bounds__(kRedBlock)
+k_probs_partial_diag(const V* __restrict__ x, const FiberMap fm, const TargetMap tm,
+                     const int64_t mult, double* __restrict__ partial) {
+  extern __shared__ double s_acc[];
+  const uint32_t t = tm.t;
+  double* s_scratch = s_acc + (size_t)t * blockDim.x;
+  int64_t* s_off = (int64_t*)(s_scratch + 4);
+  for (uint32_t j = threadIdx.x; j < t; j += blockDim.x) s_off[j] = tm.offset(j) * mult;
+  for (uint32_t j = 0; j < t; ++j) s_acc[(size_t)j * blockDim.x + threadIdx.x] = 0.0;
+  __syncthreads();
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < fm.nfib; f += stride) {
+    const int64_t base = fm.base(f) * mult;
+    for (uint32_t j = 0; j < t; ++j)
+      s_acc[(size_t)j * blockDim.x + threadIdx.x] += (double)x[base + s_off[j]].x;
+  }
+  for (uint32_t j = 0; j < t; ++j) {
+    double r = block_sum(s_acc[(size_t)j * blockDim.x + threadIdx.x], s_scratch);
+    if (threadIdx.x == 0) partial[(size_t)blockIdx.x * t + j] = r;
+  }
+}
+
+// large-t fallback: block (j, chunk) reduces one operator index over a slice of fibers
+template <typename V, bool DIAG>
+__global__ void __launch_bounds__(kRedBlock)
+k_probs_partial_wide(const V* __restrict__ x, const FiberMap fm, const TargetMap tm,
+                     const int64_t mult, const int nchunks, double* __restrict__ partial) {
+  __shared__ double s_scratch[4];
+  const uint32_t j = blockIdx.x / nchunks, c = blockIdx.x % nchunks;
+  const int64_t off = tm.offset(j) * mult;
+  double acc = 0;
+  for (uint64_t f = (uint64_t)c * blockDim.x + threadIdx.x; f < fm.nfib;
+       f += (uint64_t)nchunks * blockDim.x) {
+    const V v = x[fm.base(f) * mult + off];
+    acc += DIAG ? (double)v.x : (double)v.x * v.x + (double)v.y * v.y;
+  }
+  double r = block_sum(acc, s_scratch);
+  if (threadIdx.x == 0) partial[(size_t)c * tm.t + j] = r;
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256)
+k_probs_finalize(const double* __restrict__ partial, const int nblocks, const uint32_t t,
+                 R* __restrict__ probs) {
+  __shared__ double s_scratch[8];
+  __shared__ double s_total;
+  double local = 0;
+  for (uint32_t j = threadIdx.x; j < t; j += blockDim.x) {
+    double p = 0;
+    for (int b = 0; b < nblocks; ++b) p += partial[(size_t)b * t + j];
+    local += p;
+  }
+  double tot = block_sum(local, s_scratch);
+  if (threadIdx.x == 0) s_total = tot;
+  __syncthreads();
+  for (uint32_t j = threadIdx.x; j < t; j += blockDim.x) {
+    double p = 0;
+    for (int b = 0; b < nblocks; ++b) p += partial[(size_t)b * t + j];
+    // the reference divides in the state's real dtype (probs / jnp.sum(probs))
+    probs[j] = (R)((R)p / (R)s_total);
+  }
+}
+
+template <typename V>
+static int probs_impl(const V* x, void* probs, const Plan& p, int64_t mult, bool diag,
+                      cudaStream_t s) {
+  using R = typename RealOf<V>::type;
+  const uint32_t t = p.tm.t;
+  const size_t smem = ((size_t)t * kRedBlock + 4) * sizeof(double) + (size_t)t * sizeof(int64_t);
+  Scratch partial;
+  int nblocks;
+  if (smem <= kRedSmemBudget) {
+    nblocks = grid_for(p.fm.nfib, kRedBlock, 4);
+    if (nblocks > kRedMaxBlocks) nblocks = kRedMaxBlocks;
+    PW_TRY(partial.alloc(sizeof(double) * (size_t)nblocks * t, s));
+    auto kern = diag ? k_probs_partial_diag<V> : k_probs_partial<V>;
+    if (smem > 48 * 1024)
+      PW_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<nblocks, kRedBlock, smem, s>>>(x, p.fm, p.tm, mult, (double*)partial.p);
+    PW_LAUNCHED();
+  } else {
+    uint64_t want = (p.fm.nfib + kRedBlock - 1) / kRedBlock;
+    uint64_t cap = (uint64_t)kRedMaxBlocks * 8 / t;
+    nblocks = (int)(want < cap ? want : cap);
+    if (nblocks < 1) nblocks = 1;
+    if ((uint64_t)nblocks * t > 0x7fffffffull) return PW_ERR_UNSUPPORTED;
+    PW_TRY(partial.alloc(sizeof(double) * (size_t)nblocks * t, s));
+    if (diag)
+      k_probs_partial_wide<V, true><<<nblocks * t, kRedBlock, 0, s>>>(x, p.fm, p.tm, mult, nblocks, (double*)partial.p);
+    else
+      k_probs_partial_wide<V, false><<<nblocks * t, kRedBlock, 0, s>>>(x, p.fm, p.tm, mult, nblocks, (double*)partial.p);
+    PW_LAUNCHED();
+  }
+  k_probs_finalize<R><<<1, 256, 0, s>>>((const double*)partial.p, nblocks, t, (R*)probs);
+  PW_LAUNCHED();
+  return PW_OK;
+}
+
+// ---- reduced density matrix of kept subsystems from a state vector ------------------
+// partial[b][a*t+a'] (a <= a') = sum_f x[f,a] conj(x[f,a'])
+template <typename V>
+__global__ void __launch_bounds__(kRedBlock)
+k_reduced_partial(const V* __restrict__ x, const FiberMap fm, const TargetMap tm,
+                  double2* __restrict__ partial) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const uint32_t t = tm.t, npair = t * (t + 1) / 2;
+  double2* s_acc = (double2*)s_raw;                       // [npair][blockDim]
+  double2* s_x = s_acc + (size_t)npair * blockDim.x;      // [t][blockDim]
+  double* s_scratch = (double*)(s_x + (size_t)t * blockDim.x);
+  int64_t* s_off = (int64_t*)(s_scratch + 4);
+  for (uint32_t j = threadIdx.x; j < t; j += blockDim.x) s_off[j] = tm.offset(j);
+  for (uint32_t q = 0; q < npair; ++q) s_acc[(size_t)q * blockDim.x + threadIdx.x] = make_double2(0, 0);
+  __syncthreads();
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < fm.nfib; f += stride) {
+    const int64_t base = fm.base(f);
+    for (uint32_t j = 0; j < t; ++j) {
+      const V v = x[base + s_off[j]];
+      s_x[(size_t)j * blockDim.x + threadIdx.x] = make_double2(v.x, v.y);
+    }
+    uint32_t q = 0;
+    for (uint32_t a = 0; a < t; ++a) {
+      const double2 xa = s_x[(size_t)a * blockDim.x + threadIdx.x];
+      for (uint32_t b = a; b < t; ++b, ++q) {
+        const double2 xb = s_x[(size_t)b * blockDim.x + threadIdx.x];
+        double2 acc = s_acc[(size_t)q * blockDim.x + threadIdx.x];
+        acc.x += xa.x * xb.x + xa.y * xb.y;   // xa * conj(xb)
+        acc.y += xa.y * xb.x - xa.x * xb.y;
+        s_acc[(size_t)q * blockDim.x + threadIdx.x] = acc;
+      }
+    }
+  }
+  for (uint32_t q = 0; q < npair; ++q) {
+    const double2 v = s_acc[(size_t)q * blockDim.x + threadIdx.x];
+    double re = block_sum(v.x, s_scratch);
+    double im = block_sum(v.y, s_scratch);
+    if (threadIdx.x == 0) partial[(size_t)blockIdx.x * npair + q] = make_double2(re, im);
+  }
+}
+
+template <typename V>
+__global__ void k_reduced_finalize(const double2* __restrict__ partial, const int nblocks,
+                                   const uint32_t t, V* __restrict__ out) {
+  const uint32_t npair = t * (t + 1) / 2;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < npair; q += gridDim.x * blockDim.x) {
+    double re = 0, im = 0;
+    for (int b = 0; b < nblocks; ++b) {
+      const double2 v = partial[(size_t)b * npair + q];
+      re += v.x; im += v.y;
+    }
+    // invert q -> (a, b), a <= b, row-major upper triangle
+    uint32_t a = 0, rem = q;
+    while (rem >= t - a) { rem -= t - a; ++a; }
+    const uint32_t b2 = a + rem;
+    V v; v.x = re; v.y = im;
+    out[(size_t)a * t + b2] = v;
+    if (b2 != a) { v.y = -im; out[(size_t)b2 * t + a] = v; }
+  }
+}
+
+// wide fallback: one block per output element (a, a'), all fibers
+template <typename V>
+__global__ void __launch_bounds__(kRedBlock)
+k_reduced_wide(const V* __restrict__ x, const FiberMap fm, const TargetMap tm, V* __restrict__ out) {
+  __shared__ double s_scratch[4];
+  const uint32_t t = tm.t, a = blockIdx.x / t, b = blockIdx.x % t;
+  const int64_t oa = tm.offset(a), ob = tm.offset(b);
+  double re = 0, im = 0;
+  for (uint64_t f = threadIdx.x; f < fm.nfib; f += blockDim.x) {
+    const int64_t base = fm.base(f);
+    const V xa = x[base + oa], xb = x[base + ob];
+    re += (double)xa.x * xb.x + (double)xa.y * xb.y;
+    im += (double)xa.y * xb.x - (double)xa.x * xb.y;
+  }
+  re = block_sum(re, s_scratch);
+  im = block_sum(im, s_scratch);
+  if (threadIdx.x == 0) { V v; v.x = re; v.y = im; out[blockIdx.x] = v; }
+}
+
+template <typename V>
+static int reduced_impl(const V* x, V* out, const Plan& p, cudaStream_t s) {
+  const uint32_t t = p.tm.t;
+  const size_t npair = (size_t)t * (t + 1) / 2;
+  const size_t smem = npair * kRedBlock * sizeof(double2) + 4 * sizeof(double) +
+                      t * sizeof(int64_t) + (size_t)t * kRedBlock * sizeof(double2);
+  if (smem <= kRedSmemBudget) {
+    int nblocks = grid_for(p.fm.nfib, kRedBlock, 1);
+    Scratch partial;
+    PW_TRY(partial.alloc(sizeof(double2) * (size_t)nblocks * npair, s));
+    if (smem > 48 * 1024)
+      PW_CUDA(cudaFuncSetAttribute(k_reduced_partial<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_reduced_partial<V><<<nblocks, kRedBlock, smem, s>>>(x, p.fm, p.tm, (double2*)partial.p);
+    PW_LAUNCHED();
+    k_reduced_finalize<V><<<(int)((npair + 127) / 128), 128, 0, s>>>((const double2*)partial.p, nblocks, t, out);
+    PW_LAUNCHED();
+    return PW_OK;
+  }
+  if ((uint64_t)t * t > 0x7fffffffull) return PW_ERR_UNSUPPORTED;
+  k_reduced_wide<V><<<t * t, kRedBlock, 0, s>>>(x, p.fm, p.tm, out);
+  PW_LAUNCHED();
+  return PW_OK;
+}
+
+// ---- partial trace of a density matrix ----------------------------------------------
+// out[k, k'] = sum_f rho[row(k) + rest(f), col(k') + rest(f)]
+template <typename V, bool BLOCK_PER_OUT>
+__global__ void __launch_bounds__(kRedBlock)
+k_trace_out(const V* __restrict__ rho, const FiberMap fm, const TargetMap tm, const int64_t N,
+            V* __restrict__ out) {
+  __shared__ double s_scratch[4];
+  const uint64_t t = tm.t, nout = t * t;
+  if (BLOCK_PER_OUT) {
+    for (uint64_t o = blockIdx.x; o < nout; o += gridDim.x) {
+      const int64_t off = tm.offset((uint32_t)(o / t)) * N + tm.offset((uint32_t)(o % t));
+      double re = 0, im = 0;
+      for (uint64_t f = threadIdx.x; f < fm.nfib; f += blockDim.x) {
+        const V v = rho[off + fm.base(f) * (N + 1)];
+        re += v.x; im += v.y;
+      }
+      re = block_sum(re, s_scratch);
+      im = block_sum(im, s_scratch);
+      if (threadIdx.x == 0) { V v; v.x = re; v.y = im; out[o] = v; }
+    }
+  } else {
+    for (uint64_t o = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; o < nout;
+         o += (uint64_t)gridDim.x * blockDim.x) {
+      const int64_t off = tm.offset((uint32_t)(o / t)) * N + tm.offset((uint32_t)(o % t));
+      double re = 0, im = 0;
+      for (uint64_t f = 0; f < fm.nfib; ++f) {
+        const V v = rho[off + fm.base(f) * (N + 1)];
+        re += v.x; im += v.y;
+      }
+      V v; v.x = re; v.y = im; out[o] = v;
+    }
+  }
+}
+
+// ---- collapse (gather the selected slice and rescale) ---------------------------------
+template <typename V>
+__global__ void k_collapse_vec(const V* __restrict__ psi, V* __restrict__ post,
+                               const int64_t* __restrict__ outcome,
+                               const typename RealOf<V>::type* __restrict__ probs,
+                               const FiberMap fm, const TargetMap tm) {
+  using R = typename RealOf<V>::type;
+  const uint32_t o = (uint32_t)*outcome;
+  const int64_t off = tm.offset(o);
+  // the reference divides (core/kernels.py:205); dividing keeps the last bit equal
+  const R den = sqrt(probs[o] + (R)1e-18);
+  for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < fm.nfib;
+       f += (uint64_t)gridDim.x * blockDim.x) {
+    V v = psi[fm.base(f) + off];
+    v.x = v.x / den;
+    v.y = v.y / den;
+    post[f] = v;
+  }
+}
+
+template <typename V>
+__global__ void k_collapse_mat(const V* __restrict__ rho, V* __restrict__ post,
+                               const int64_t* __restrict__ outcome,
+                               const typename RealOf<V>::type* __restrict__ probs,
+                               const FiberMap fm, const TargetMap tm, const int64_t N) {
+  using R = typename RealOf<V>::type;
+  const uint32_t o = (uint32_t)*outcome;
+  const int64_t off = tm.offset(o);
+  const R den = probs[o] + (R)1e-18;
+  const uint64_t r = fm.nfib, total = r * r;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t fr = i / r, fc = i - fr * r;
+    V v = rho[(fm.base(fr) + off) * N + fm.base(fc) + off];
+    v.x = v.x / den;
+    v.y = v.y / den;
+    post[i] = v;
+  }
+}
+
+// ---- sampling ---------------------------------------------------------------------
+// jax.random.choice(key, a=t, p=probs): c = cumsum(p); r = c[-1]*(1-u); searchsorted-left
+template <typename R>
+__global__ void k_draw(const R* __restrict__ probs, const int64_t t, const uint32_t k0,
+                       const uint32_t k1, int64_t* __restrict__ outcome) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  uint32_t b0, b1;
+  threefry2x32(k0, k1, 0u, 0u, &b0, &b1);
+  R u;
+  if (sizeof(R) == 8) {
+    const unsigned long long bits = ((((unsigned long long)b0 << 32) | b1) >> 12) | 0x3FF0000000000000ull;
+    u = (R)(__longlong_as_double((long long)bits) - 1.0);
+  } else {
+    const uint32_t bits = ((b0 ^ b1) >> 9) | 0x3F800000u;
+    u = (R)(__uint_as_float(bits) - 1.0f);
+  }
+  R total = 0;
+  for (int64_t i = 0; i < t; ++i) total += probs[i];
+  const R r = total * ((R)1 - u);
+  R c = 0;
+  int64_t idx = t;
+  for (int64_t i = 0; i < t; ++i) {
+    c += probs[i];
+    if (!(c < r)) { idx = i; break; }
+  }
+  *outcome = idx;
+}
+
+// ---- POVM weights on the reduced state ----------------------------------------------
+template <typename V>
+__global__ void __launch_bounds__(kRedBlock)
+k_povm_traces(const V* __restrict__ rho_t, const V* __restrict__ ops, const int64_t t,
+              double* __restrict__ traces) {
+  __shared__ double s_scratch[4];
+  const V* E = ops + (size_t)blockIdx.x * t * t;
+  double acc = 0;
+  // Tr(E rho E^dagger) = sum_{a,b,c} E[a,b] rho[b,c] conj(E[a,c]); threads over (a,b)
+  for (int64_t ab = threadIdx.x; ab < t * t; ab += blockDim.x) {
+    const int64_t a = ab / t, b = ab % t;
+    const V e = E[ab];
+    double2 inner = make_double2(0, 0);
+    for (int64_t c = 0; c < t; ++c) {
+      const V r = rho_t[b * t + c], ec = E[a * t + c];
+      inner.x += (double)r.x * ec.x + (double)r.y * ec.y;   // r * conj(ec)
+      inner.y += (double)r.y * ec.x - (double)r.x * ec.y;
+    }
+    acc += (double)e.x * inner.x - (double)e.y * inner.y;    // real part only
+  }
+  acc = block_sum(acc, s_scratch);
+  if (threadIdx.x == 0) traces[blockIdx.x] = acc;
+}
+
+template <typename R>
+__global__ void k_povm_normalise(const double* __restrict__ traces_d, const int K,
+                                 R* __restrict__ probs, R* __restrict__ traces) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  R total = 0;
+  for (int k = 0; k < K; ++k) total += (R)traces_d[k];
+  for (int k = 0; k < K; ++k) {
+    traces[k] = (R)traces_d[k];
+    probs[k] = (R)traces_d[k] / total;
+  }
+}
+
+template <typename V>
+__global__ void k_povm_select(const V* __restrict__ ops, const int64_t t,
+                              const int64_t* __restrict__ outcome,
+                              const typename RealOf<V>::type* __restrict__ traces,
+                              V* __restrict__ op_out) {
+  using R = typename RealOf<V>::type;
+  const int64_t o = *outcome;
+  const R s = sqrt(traces[o] + (R)1e-18);
+  for (int64_t i = blockIdx.x * blockDim.x + threadIdx.x; i < t * t; i += gridDim.x * blockDim.x) {
+    V v = ops[o * t * t + i];
+    v.x /= s; v.y /= s;
+    op_out[i] = v;
+  }
+}
+
+// ---- norm / max / scale ---------------------------------------------------------------
+template <typename V>
+__global__ void __launch_bounds__(256)
+k_norm_partial(const V* __restrict__ x, const int64_t count, double* __restrict__ partial) {
+  __shared__ double s_scratch[8];
+  __shared__ double s_max[8];
+  double sum = 0, mx = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const V v = x[i];
+    const double a = (double)v.x * v.x + (double)v.y * v.y;
+    sum += a;
+    mx = a > mx ? a : mx;
+  }
+  sum = block_sum(sum, s_scratch);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)blockDim.x / 32; ++w) mx = fmax(mx, s_max[w]);
+    partial[2 * blockIdx.x] = sum;
+    partial[2 * blockIdx.x + 1] = mx;
+  }
+}
+
+__global__ void k_norm_finalize(const double* __restrict__ partial, const int nblocks,
+                                double* __restrict__ stats) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double sum = 0, mx = 0;
+  for (int b = 0; b < nblocks; ++b) {
+    sum += partial[2 * b];
+    mx = fmax(mx, partial[2 * b + 1]);
+  }
+  stats[0] = sum;
+  stats[1] = mx;
+}
+
+template <typename V>
+__global__ void k_scale(V* __restrict__ x, const int64_t count, const double* __restrict__ scale) {
+  using R = typename RealOf<V>::type;
+  const R s = (R)*scale;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    V v = x[i];
+    v.x *= s; v.y *= s;
+    x[i] = v;
+  }
+}
+
+}  // namespace pw
+
+using namespace pw;
+
+#define PW_DISPATCH(dtype, FN, ...)                                   \
+  ((dtype) == PW_C128 ? FN<double2>(__VA_ARGS__)                      \
+                      : ((dtype) == PW_C64 ? FN<float2>(__VA_ARGS__) : PW_ERR_INVALID))
+
+template <typename V>
+static int probs_vec_t(const void* psi, void* probs, const Plan& p, cudaStream_t s) {
+  return probs_impl<V>((const V*)psi, probs, p, 1, false, s);
+}
+template <typename V>
+static int probs_mat_t(const void* rho, void* probs, const Plan& p, cudaStream_t s) {
+  return probs_impl<V>((const V*)rho, probs, p, (int64_t)p.N + 1, true, s);
+}
+
+extern "C" int pw_probs_vec(const void* psi, void* probs, const int64_t* dims, int n,
+                            const int32_t* targets, int nt, int dtype, void* stream) {
+  if (!psi || !probs) return PW_ERR_INVALID;
+  Plan p;
+  PW_TRY(build_plan(dims, n, targets, nt, &p));
+  return PW_DISPATCH(dtype, probs_vec_t, psi, probs, p, (cudaStream_t)stream);
+}
+
+extern "C" int pw_probs_mat(const void* rho, void* probs, const int64_t* dims, int n,
+                            const int32_t* targets, int nt, int dtype, void* stream) {
+  if (!rho || !probs) return PW_ERR_INVALID;
+  Plan p;  // plan over the n-axis index; offsets are scaled by N+1 to walk the diagonal
+  PW_TRY(build_plan(dims, n, targets, nt, &p));
+  return PW_DISPATCH(dtype, probs_mat_t, rho, probs, p, (cudaStream_t)stream);
+}
+
+template <typename V>
+static int reduced_t(const void* psi, void* out, const Plan& p, cudaStream_t s) {
+  return reduced_impl<V>((const V*)psi, (V*)out, p, s);
+}
+
+extern "C" int pw_reduced_from_vec(const void* psi, void* out, const int64_t* dims, int n,
+                                   const int32_t* keep, int nkeep, int dtype, void* stream) {
+  if (!psi || !out) return PW_ERR_INVALID;
+  Plan p;
+  PW_TRY(build_plan(dims, n, keep, nkeep, &p));
+  return PW_DISPATCH(dtype, reduced_t, psi, out, p, (cudaStream_t)stream);
+}
+
+template <typename V>
+static int trace_out_t(const void* rho, void* out, const Plan& p, cudaStream_t s) {
+  const uint64_t nout = (uint64_t)p.tm.t * p.tm.t;
+  if (p.fm.nfib >= 64) {
+    int grid = (int)(nout < (uint64_t)kNumSMs * 16 ? nout : (uint64_t)kNumSMs * 16);
+    k_trace_out<V, true><<<grid, kRedBlock, 0, s>>>((const V*)rho, p.fm, p.tm, (int64_t)p.N, (V*)out);
+  } else {
+    int grid = grid_for(nout, kRedBlock, 16);
+    k_trace_out<V, false><<<grid, kRedBlock, 0, s>>>((const V*)rho, p.fm, p.tm, (int64_t)p.N, (V*)out);
+  }
+  PW_LAUNCHED();
+  return PW_OK;
+}
+
+extern "C" int pw_trace_out_mat(const void* rho, void* out, const int64_t* dims, int n,
+                                const int32_t* keep, int nkeep, int dtype, void* stream) {
+  if (!rho || !out) return PW_ERR_INVALID;
+  Plan p;
+  PW_TRY(build_plan(dims, n, keep, nkeep, &p));
+  if ((uint64_t)p.tm.t * p.tm.t > 0xffffffffull) return PW_ERR_UNSUPPORTED;
+  return PW_DISPATCH(dtype, trace_out_t, rho, out, p, (cudaStream_t)stream);
+}
+
+template <typename V>
+static int draw_t(const void* probs, int64_t t, uint32_t k0, uint32_t k1, int64_t* outcome,
+                  cudaStream_t s) {
+  using R = typename RealOf<V>::type;
+  k_draw<R><<<1, 32, 0, s>>>((const R*)probs, t, k0, k1, outcome);
+  PW_LAUNCHED();
+  return PW_OK;
+}
+
+extern "C" int pw_draw(const void* probs, int64_t t, uint32_t key0, uint32_t key1, int dtype,
+                       int64_t* outcome, void* stream) {
+  if (!probs || !outcome || t < 1) return PW_ERR_INVALID;
+  return PW_DISPATCH(dtype, draw_t, probs, t, key0, key1, outcome, (cudaStream_t)stream);
+}
+
+template <typename V>
+static int collapse_vec_t(const void* psi, void* post, const int64_t* outcome, const void* probs,
+                          const Plan& p, cudaStream_t s) {
+  using R = typename RealOf<V>::type;
+  k_collapse_vec<V><<<grid_for(p.fm.nfib, 256, 8), 256, 0, s>>>((const V*)psi, (V*)post, outcome,
+                                                               (const R*)probs, p.fm, p.tm);
+  PW_LAUNCHED();
+  return PW_OK;
+}
+
+extern "C" int pw_collapse_vec(const void* psi, void* post, const int64_t* outcome,
+                               const void* probs, const int64_t* dims, int n,
+                               const int32_t* targets, int nt, int dtype, void* stream) {
+  if (!psi || !post || !outcome || !probs) return PW_ERR_INVALID;
+  Plan p;
+  PW_TRY(build_plan(dims, n, targets, nt, &p));
+  return PW_DISPATCH(dtype, collapse_vec_t, psi, post, outcome, probs, p, (cudaStream_t)stream);
+}
+
+template <typename V>
+static int collapse_mat_t(const void* rho, void* post, const int64_t* outcome, const void* probs,
+                          const Plan& p, cudaStream_t s) {
+  using R = typename RealOf<V>::type;
+  k_collapse_mat<V><<<grid_for(p.fm.nfib * p.fm.nfib, 256, 8), 256, 0, s>>>(
+      (const V*)rho, (V*)post, outcome, (const R*)probs, p.fm, p.tm, (int64_t)p.N);
+  PW_LAUNCHED();
+  return PW_OK;
+}
+
+extern "C" int pw_collapse_mat(const void* rho, void* post, const int64_t* outcome,
+                               const void* probs, const int64_t* dims, int n,
+                               const int32_t* targets, int nt, int dtype, void* stream) {
+  if (!rho || !post || !outcome || !probs) return PW_ERR_INVALID;
+  Plan p;
+  PW_TRY(build_plan(dims, n, targets, nt, &p));
+  return PW_DISPATCH(dtype, collapse_mat_t, rho, post, outcome, probs, p, (cudaStream_t)stream);
+}
+
+template <typename V>
+static int povm_probs_t(const void* rho_t, const void* ops, int K, int64_t t, void* probs,
+                        void* traces, cudaStream_t s) {
+  using R = typename RealOf<V>::type;
+  Scratch tr;
+  PW_TRY(tr.alloc(sizeof(double) * K, s));
+  k_povm_traces<V><<<K, kRedBlock, 0, s>>>((const V*)rho_t, (const V*)ops, t, (double*)tr.p);
+  PW_LAUNCHED();
+  k_povm_normalise<R><<<1, 32, 0, s>>>((const double*)tr.p, K, (R*)probs, (R*)traces);
+  PW_LAUNCHED();
+  return PW_OK;
+}
+
+extern "C" int pw_povm_probs(const void* rho_t, const void* ops, int K, int64_t t, void* probs,
+                             void* traces, int dtype, void* stream) {
+  if (!rho_t || !ops || !probs || !traces || K < 1 || t < 1) return PW_ERR_INVALID;
+  return PW_DISPATCH(dtype, povm_probs_t, rho_t, ops, K, t, probs, traces, (cudaStream_t)stream);
+}
+
+template <typename V>
+static int povm_select_t(const void* ops, int64_t t, const int64_t* outcome, const void* traces,
+                         void* op_out, cudaStream_t s) {
+  using R = typename RealOf<V>::type;
+  k_povm_select<V><<<grid_for((uint64_t)t * t, 128, 1), 128, 0, s>>>((const V*)ops, t, outcome,
+                                                                    (const R*)traces, (V*)op_out);
+  PW_LAUNCHED();
+  return PW_OK;
+}
+
+extern "C" int pw_povm_select(const void* ops, int64_t t, const int64_t* outcome,
+                              const void* traces, void* op_out, int dtype, void* stream) {
+  if (!ops || !outcome || !traces || !op_out || t < 1) return PW_ERR_INVALID;
+  return PW_DISPATCH(dtype, povm_select_t, ops, t, outcome, traces, op_out, (cudaStream_t)stream);
+}
+
+template <typename V>
+static int norm_stats_t(const void* x, int64_t count, double* stats, cudaStream_t s) {
+  const int nblocks = grid_for((uint64_t)count, 256, 4);
+  Scratch partial;
+  PW_TRY(partial.alloc(sizeof(double) * 2 * nblocks, s));
+  k_norm_partial<V><<<nblocks, 256, 0, s>>>((const V*)x, count, (double*)partial.p);
+  PW_LAUNCHED();
+  k_norm_finalize<<<1, 32, 0, s>>>((const double*)partial.p, nblocks, stats);
+  PW_LAUNCHED();
+  return PW_OK;
+}
+
+extern "C" int pw_norm_stats(const void* x, int64_t count, int dtype, double* stats, void* stream) {
+  if (!x || !stats || count < 0) return PW_ERR_INVALID;
+  return PW_DISPATCH(dtype, norm_stats_t, x, count, stats, (cudaStream_t)stream);
+}
+
+template <typename V>
+static int scale_t(void* x, int64_t count, const double* scale, cudaStream_t s) {
+  k_scale<V><<<grid_for((uint64_t)count, 256, 8), 256, 0, s>>>((V*)x, count, scale);
+  PW_LAUNCHED();
+  return PW_OK;
+}
+
+extern "C" int pw_scale(void* x, int64_t count, const double* scale_dev, int dtype, void* stream) {
+  if (!x || !scale_dev || count < 0) return PW_ERR_INVALID;
+  return PW_DISPATCH(dtype, scale_t, x, count, scale_dev, (cudaStream_t)stream);
+}

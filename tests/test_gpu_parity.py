@@ -1,0 +1,320 @@
+"""
+Parity tests proper: the CUDA path (through the C ABI, via the reference-facing
+adapters) against the NumPy oracle on identical seeded inputs.
+
+Tolerances (BASELINE.json north_star): 1e-12 relative in complex128, 1e-5 in
+complex64; measurement outcomes bit-exact under a fixed key.
+"""
+
+import math
+
+import numpy as np
+import pytest
+
+import seam_cases as sc
+from oracle import adapters_np as oad
+from oracle import operators as ops
+from oracle import rng_threefry as orng
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+TOL = {np.complex128: 1e-12, np.complex64: 1e-5}
+
+
+@pytest.fixture(scope="module")
+def ad():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import __graft_entry__ as g
+
+    g.build()
+    from photon_weave_b200.core import adapters
+
+    return adapters
+
+
+class CudaBackend:
+    def __init__(self, ad):
+        self.ad = ad
+
+    @staticmethod
+    def arr(x):
+        return torch.as_tensor(np.asarray(x)).cuda()
+
+    @staticmethod
+    def np(x):
+        return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+    @staticmethod
+    def key(seed):
+        return orng.PRNGKey(seed)
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    scale = np.abs(b).max()
+    return np.abs(a - b).max() / (scale if scale > 0 else 1.0)
+
+
+def dev(x):
+    return torch.as_tensor(np.ascontiguousarray(x)).cuda()
+
+
+def host(x):
+    return x.detach().cpu().numpy()
+
+
+# --- the reference's own seam tests, against the CUDA path ---------------------
+
+
+@pytest.mark.parametrize("use_contraction", [False, True])
+@pytest.mark.parametrize("case", sc.CASES_BOTH_ROUTES, ids=lambda c: c.__name__)
+def test_seam_case_both_routes(ad, case, use_contraction):
+    case(CudaBackend(ad), use_contraction)
+
+
+@pytest.mark.parametrize("case", sc.CASES_SINGLE, ids=lambda c: c.__name__)
+def test_seam_case(ad, case):
+    case(CudaBackend(ad))
+
+
+# --- random-input parity against the oracle ----------------------------------------
+
+SHAPES = [
+    ((2, 3, 2), (1,)),
+    ((3, 2, 4), (2, 0)),
+    ((3, 2, 4), (0, 2)),
+    ((2, 3, 2, 2), (3, 1)),
+    ((4, 3), (1, 0)),
+    ((5,), (0,)),
+    ((2, 3, 2, 3), (2, 0, 3)),
+    ((6, 6, 6), (1,)),
+    ((6, 6, 6), (0, 1)),          # t = 36: generic / tiled path
+    ((5, 5, 5), (2, 0)),          # t = 25, reversed order
+    ((2, 2, 2, 2, 2, 2, 2), (6,)),
+    ((7, 1, 3), (0,)),            # singleton axis
+    ((64, 2), (0, 1)),            # Jaynes-Cummings shape: everything is a target, t = 128
+    ((3, 4, 5, 2), (1, 2)),
+]
+
+
+@pytest.mark.parametrize("cdtype", [np.complex128, np.complex64])
+@pytest.mark.parametrize("dims,targets", SHAPES)
+def test_apply_vector_parity(ad, dims, targets, cdtype):
+    N = math.prod(dims)
+    t = math.prod(dims[i] for i in targets)
+    psi = ops.random_state(N, 1, cdtype)
+    op = (ops.random_unitary(t, 7) * 1.1).astype(cdtype)
+    ref = oad.apply_operation_vector(dims, targets, psi.astype(np.complex128), op.astype(np.complex128), True)
+    for uc in (False, True):
+        out = host(ad.apply_operation_vector(dims, targets, dev(psi), dev(op), use_contraction=uc))
+        assert out.dtype == cdtype and out.shape == (N, 1)
+        assert rel_err(out, ref) < TOL[cdtype]
+
+
+MAT_SHAPES = [
+    ((2, 3, 2), (1,)),
+    ((3, 2, 4), (2, 0)),
+    ((2, 3, 2, 2), (3, 1)),
+    ((4, 3), (1, 0)),
+    ((5,), (0,)),
+    ((5, 5), (0,)),
+    ((5, 5), (1, 0)),             # t = 25 on a density matrix
+    ((3, 3, 3), (1,)),
+    ((8, 8), (1,)),
+    ((2, 2, 2, 2), (0, 3)),
+]
+
+
+@pytest.mark.parametrize("cdtype", [np.complex128, np.complex64])
+@pytest.mark.parametrize("dims,targets", MAT_SHAPES)
+def test_apply_matrix_and_kraus_parity(ad, dims, targets, cdtype):
+    N = math.prod(dims)
+    t = math.prod(dims[i] for i in targets)
+    rho = ops.random_density(N, 2, dtype=cdtype)
+    op = (ops.random_unitary(t, 3) * 0.9).astype(cdtype)
+    ref = oad.apply_operation_matrix(dims, targets, rho.astype(np.complex128), op.astype(np.complex128), True)
+    out = host(ad.apply_operation_matrix(dims, targets, dev(rho), dev(op)))
+    assert out.dtype == cdtype and out.shape == (N, N)
+    assert rel_err(out, ref) < TOL[cdtype]
+    kr = np.stack([ops.random_unitary(t, 10 + k) * (0.3 + 0.2 * k) for k in range(3)]).astype(cdtype)
+    refk = oad.apply_kraus_matrix(dims, targets, rho.astype(np.complex128), kr.astype(np.complex128), True)
+    for uc in (False, True):
+        outk = host(ad.apply_kraus_matrix(dims, targets, dev(rho), dev(kr), use_contraction=uc))
+        assert rel_err(outk, refk) < TOL[cdtype]
+    # list-of-operators input (state/utils/operations.py:260 stacks a Python list)
+    outl = host(ad.apply_kraus_matrix(dims, targets, dev(rho), [dev(k) for k in kr]))
+    assert rel_err(outl, refk) < TOL[cdtype]
+
+
+def test_loss_channel_preserves_trace_and_matches_oracle(ad):
+    dims = (5, 5, 5)
+    N = 125
+    rho = ops.random_density(N, 4)
+    ks = ops.loss_channel(5, 0.1)
+    for tg in [(0,), (1,), (2,)]:
+        out = host(ad.apply_kraus_matrix(dims, tg, dev(rho), dev(ks)))
+        assert abs(np.trace(out) - 1) < 1e-12
+        assert rel_err(out, oad.apply_kraus_matrix(dims, tg, rho, ks)) < 1e-12
+
+
+@pytest.mark.parametrize("cdtype", [np.complex128, np.complex64])
+@pytest.mark.parametrize(
+    "dims,keep",
+    [((2, 3, 2), (0, 2)), ((2, 3, 2), (2, 0)), ((3, 2, 4), (1,)), ((4, 3, 2, 2), (3, 0, 1)),
+     ((5, 5), (1,)), ((2, 2, 2), (0, 1, 2)), ((2, 2, 2), (2, 0, 1))],
+)
+def test_trace_out_parity_both_orders(ad, dims, keep, cdtype):
+    N = math.prod(dims)
+    rho = ops.random_density(N, 6, dtype=cdtype)
+    psi = ops.random_state(N, 8, cdtype)
+    for uc in (False, True):
+        ref = oad.trace_out_matrix(dims, keep, rho.astype(np.complex128), use_contraction=uc)
+        out = host(ad.trace_out_matrix(dims, keep, dev(rho), use_contraction=uc))
+        assert rel_err(out, ref) < TOL[cdtype]
+        if len(keep) < len(dims):
+            refv = oad.trace_out_vector(dims, keep, psi.astype(np.complex128), use_contraction=uc)
+            outv = host(ad.trace_out_vector(dims, keep, dev(psi), use_contraction=uc))
+            assert rel_err(outv, refv) < TOL[cdtype]
+
+
+@pytest.mark.parametrize("cdtype", [np.complex128, np.complex64])
+@pytest.mark.parametrize(
+    "dims,targets",
+    [((2, 3, 2), (1,)), ((3, 2, 4), (2, 0)), ((6, 6, 6), (1,)), ((4, 3, 5), (0, 1, 2)),
+     ((5, 4), (0,)), ((2, 2, 2, 2, 2), (4, 1))],
+)
+def test_measure_parity_and_bit_exact_outcomes(ad, dims, targets, cdtype):
+    N = math.prod(dims)
+    psi = ops.random_state(N, 21, cdtype)
+    rho = ops.random_density(N, 22, rank=3, dtype=cdtype)
+    tol = TOL[cdtype]
+    for seed in range(12):
+        key = orng.PRNGKey(seed)
+        o_ref, post_ref, probs_ref, _ = oad.measure_vector_with_probs(dims, targets, psi, key)
+        o, post, probs, k2 = ad.measure_vector_with_probs(dims, targets, dev(psi), key)
+        assert k2 is key
+        assert int(o) == int(o_ref)
+        assert rel_err(host(probs), probs_ref) < tol
+        assert rel_err(host(post), post_ref) < tol * 10
+        o_ref, post_ref, probs_ref, _ = oad.measure_matrix_with_probs(dims, targets, rho, key)
+        o, post, probs, _ = ad.measure_matrix_with_probs(dims, targets, dev(rho), key)
+        assert int(o) == int(o_ref)
+        assert rel_err(host(probs), probs_ref) < tol
+        assert rel_err(host(post), post_ref) < tol * 10
+    # plain variants return the same triple
+    o, post, _ = ad.measure_vector(dims, targets, dev(psi), orng.PRNGKey(5))
+    o_ref, post_ref, _ = oad.measure_vector(dims, targets, psi, orng.PRNGKey(5))
+    assert int(o) == o_ref and rel_err(host(post), post_ref) < tol * 10
+
+
+def test_reference_seed_kats_on_device(ad):
+    """tests/state/test_fock.py:346-380: seed 1 -> 0, seed 3 -> 1 (vector and matrix)."""
+    from photon_weave_b200.core import rng
+
+    psi = np.array([[1], [1]], dtype=np.complex128) / np.sqrt(2)
+    rho = psi @ psi.conj().T
+    for seed, want in ((1, 0), (3, 1)):
+        key = rng.split(rng.PRNGKey(seed))[0]
+        assert int(ad.measure_vector((2,), (0,), dev(psi), key)[0]) == want
+        assert int(ad.measure_matrix((2,), (0,), dev(rho), key)[0]) == want
+
+
+@pytest.mark.parametrize("cdtype", [np.complex128, np.complex64])
+def test_expectation_parity(ad, cdtype):
+    dims, targets = (3, 2, 4), (2, 0)
+    psi = ops.random_state(24, 31, cdtype)
+    rho = ops.random_density(24, 32, dtype=cdtype)
+    p_ref, post_ref = oad.measure_vector_expectation(dims, targets, psi.astype(np.complex128))
+    p, post = ad.measure_vector_expectation(dims, targets, dev(psi))
+    assert rel_err(host(p), p_ref) < TOL[cdtype] and rel_err(host(post), post_ref) < TOL[cdtype]
+    p_ref, post_ref = oad.measure_matrix_expectation(dims, targets, rho.astype(np.complex128))
+    p, post = ad.measure_matrix_expectation(dims, targets, dev(rho))
+    assert rel_err(host(p), p_ref) < TOL[cdtype] and rel_err(host(post), post_ref) < TOL[cdtype]
+
+
+@pytest.mark.parametrize("dims,targets", [((2, 3, 2), (1,)), ((3, 2, 2), (2, 0)), ((4,), (0,))])
+def test_povm_parity(ad, dims, targets):
+    N = math.prod(dims)
+    t = math.prod(dims[i] for i in targets)
+    rho = ops.random_density(N, 41)
+    # a 3-outcome POVM from a random unitary's column blocks
+    u = ops.random_unitary(t, 42)
+    projs = [np.diag((np.arange(t) % 3 == k).astype(float)) for k in range(3)]
+    es = np.stack([u @ p @ u.conj().T for p in projs])
+    for seed in range(8):
+        key = orng.PRNGKey(seed)
+        o_ref, post_ref, _ = oad.measure_povm_matrix(dims, targets, es, rho, key)
+        o, post, _ = ad.measure_povm_matrix(dims, targets, dev(es), dev(rho), key)
+        assert int(o) == int(o_ref)
+        assert rel_err(host(post), post_ref) < 1e-11
+
+
+def test_host_numpy_inputs_round_trip(ad):
+    dims, targets = (3, 4, 2), (1,)
+    psi = ops.random_state(24, 51)
+    op = ops.random_unitary(4, 52)
+    out = ad.apply_operation_vector(dims, targets, psi, op)
+    assert isinstance(out, np.ndarray)
+    assert rel_err(out, oad.apply_operation_vector(dims, targets, psi, op)) < 1e-12
+    o, post, _ = ad.measure_vector(dims, targets, psi, orng.PRNGKey(2))
+    assert isinstance(o, int) and isinstance(post, np.ndarray)
+
+
+def test_circuit_host_entry_point(ad):
+    from photon_weave_b200.core import ffi
+
+    dims = (4, 3, 5)
+    psi = ops.random_state(60, 61)
+    o1, o2 = ops.random_unitary(3, 62), ops.random_unitary(20, 63)
+    out = ffi.circuit_host(psi, False, dims, [(0, (1,), o1), (0, (2, 0), o2)])
+    ref = oad.apply_operation_vector(dims, (2, 0), oad.apply_operation_vector(dims, (1,), psi, o1), o2)
+    assert rel_err(out, ref) < 1e-12
+    rho = ops.random_density(12, 64)
+    ks = ops.loss_channel(3, 0.2)
+    u = ops.random_unitary(4, 65)
+    outm = ffi.circuit_host(rho, True, (4, 3), [(1, (0,), u), (2, (1,), ks)])
+    refm = oad.apply_kraus_matrix((4, 3), (1,), oad.apply_operation_matrix((4, 3), (0,), rho, u), ks)
+    assert rel_err(outm, refm) < 1e-12
+
+
+# --- size-independent properties at larger sizes -------------------------------------
+
+
+def test_unitary_preserves_norm_and_inverse_round_trip_large(ad):
+    from photon_weave_b200.core import ffi
+
+    dims = (6,) * 8  # 1.68M amplitudes
+    N = 6**8
+    g = torch.Generator(device="cuda").manual_seed(0)
+    psi = torch.randn(N, 2, generator=g, device="cuda", dtype=torch.float64)
+    psi = torch.view_as_complex(psi).reshape(N, 1)
+    n0 = float(ffi.norm_stats(psi)[0])
+    cur = psi
+    us = []
+    for ax in range(8):
+        u = ops.random_unitary(6, 100 + ax)
+        us.append(u)
+        cur = ad.apply_operation_vector(dims, (ax,), cur, dev(u))
+    bs = ops.beam_splitter(6, 6, np.pi / 4)
+    cur = ad.apply_operation_vector(dims, (2, 5), cur, dev(bs))
+    assert abs(float(ffi.norm_stats(cur)[0]) - n0) / n0 < 1e-12
+    cur = ad.apply_operation_vector(dims, (2, 5), cur, dev(bs.conj().T))
+    for ax in reversed(range(8)):
+        cur = ad.apply_operation_vector(dims, (ax,), cur, dev(us[ax].conj().T))
+    assert float((cur - psi).abs().max()) < 1e-12 * float(psi.abs().max()) * 50
+
+
+def test_linearity_and_sample_check_large(ad):
+    dims = (6,) * 7
+    N = 6**7
+    a = ops.random_state(N, 71)
+    b = ops.random_state(N, 72)
+    op = ops.displacement_operator(6, 0.5)
+    fa = host(ad.apply_operation_vector(dims, (3,), dev(a), dev(op)))
+    fb = host(ad.apply_operation_vector(dims, (3,), dev(b), dev(op)))
+    fab = host(ad.apply_operation_vector(dims, (3,), dev(2 * a - 1j * b), dev(op)))
+    assert rel_err(fab, 2 * fa - 1j * fb) < 1e-12
+    assert rel_err(fa, oad.apply_operation_vector(dims, (3,), a, op)) < 1e-12
