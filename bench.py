@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the photon_weave state-evolution hot path on B200.
+
+Workload (BASELINE.json configs[4], the only config quoted at 1/2/4/8 GPUs and the
+largest that fits one GPU): a 12-mode Fock state vector, cutoff 6, complex128
+(6^12 = 2.18e9 amplitudes, 34.83 GB).  One STEP is one circuit layer through
+``apply_operation``: a single-mode operator on every mode (displacement, phase
+shift, squeezing, dense random unitary, cycling) followed by a beam splitter on
+every even brick (0,1), (2,3), ... -- 18 operator applications, each updating all
+N amplitudes.  metric = amplitudes updated per second (whole job).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "state amplitudes updated/sec (apply_operation layer, 12-mode cutoff-6 state vector)"
+UNIT = "amplitudes/s"
+
+
+# ------------------------------------------------------------------------------------
+# workload definition (shared by both arms)
+# ------------------------------------------------------------------------------------
+
+
+def make_layer(modes: int, cutoff: int):
+    """[(targets, operator complex128, label)] -- SURVEY.md section 8d operator set."""
+    from oracle import operators as ops  # operator *construction* is input generation
+
+    single = [
+        ("displace", ops.displacement_operator(cutoff, 0.5)),
+        ("phase", ops.phase_operator(cutoff, 0.3)),
+        ("squeeze", ops.squeezing_operator(cutoff, 0.2 * (1 + 1j))),
+        ("unitary", ops.random_unitary(cutoff, 11)),
+    ]
+    layer = []
+    for m in range(modes):
+        name, op = single[m % len(single)]
+        layer.append(((m,), np.ascontiguousarray(op), f"{name}[{m}]"))
+    bs = np.ascontiguousarray(ops.beam_splitter(cutoff, cutoff, math.pi / 4))
+    for m in range(0, modes - 1, 2):
+        layer.append(((m, m + 1), bs, f"bs[{m},{m + 1}]"))
+    return layer
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = f"/tmp/pw_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-i", str(self.gpu), "-lms", "100"],
+                stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)),
+                       reasons=sorted(reasons), samples=len(sm))
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------------------------
+# CPU arm (oracle port), used for cpu_baseline and --impl reference
+# ------------------------------------------------------------------------------------
+
+
+def cpu_layer_throughput(modes: int, cutoff: int, steps: int, warmup: int):
+    from oracle import cpu_baseline as cb
+    from oracle import operators as ops
+
+    dims = (cutoff,) * modes
+    N = cutoff**modes
+    layer = [(t, o) for t, o, _ in make_layer(modes, cutoff)]
+    psi = ops.random_state(N, 0)
+    for _ in range(warmup):
+        psi = cb.run_layer(dims, layer, psi)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        psi = cb.run_layer(dims, layer, psi)
+    dt = time.perf_counter() - t0
+    return len(layer) * N * steps / dt, dt / steps, len(layer), N
+
+
+def pick_cpu_modes(cutoff: int, budget_s: float):
+    """Largest mode count whose layer is estimated to fit the time budget."""
+    from oracle import cpu_baseline as cb
+    from oracle import operators as ops
+
+    m = 8
+    dims = (cutoff,) * m
+    psi = ops.random_state(cutoff**m, 0)
+    layer = [(t, o) for t, o, _ in make_layer(m, cutoff)]
+    cb.run_layer(dims, layer, psi)
+    t0 = time.perf_counter()
+    cb.run_layer(dims, layer, psi)
+    per_amp_op = (time.perf_counter() - t0) / (len(layer) * cutoff**m)
+    best = m
+    for cand in (9, 10, 11):
+        nops = cand + cand // 2
+        if per_amp_op * nops * cutoff**cand <= budget_s:
+            best = cand
+    return best
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cutoff = args.cutoff
+    per_step_budget = 150.0 / max(args.steps + args.warmup, 1)
+    modes = pick_cpu_modes(cutoff, per_step_budget)
+    value, s_per_step, nops, N = cpu_layer_throughput(modes, cutoff, args.steps, args.warmup)
+    cores = os.cpu_count()
+    sample = (f"same layer pattern on a {modes}-mode cutoff-{cutoff} state vector "
+              f"({N} amplitudes, {nops} ops/step), NumPy/BLAS port of the reference path")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    N = args.cutoff**args.modes
+    return {
+        "workload": f"configs[4]: synthetic {args.modes}-mode state vector, cutoff {args.cutoff} "
+                    f"({N} amplitudes, {N * 16 / 1e9:.2f} GB complex128)",
+        "layer": f"{args.modes} single-mode ops (displace/phase/squeeze/dense unitary) + "
+                 f"{args.modes // 2} beam splitters on even bricks",
+        "ops_per_step": args.modes + args.modes // 2,
+        "sharding": "single device" if world == 1 else f"leading axes block-sharded over {world} ranks",
+        "l2": "state (>= 4 GB per rank) exceeds the 126 MB L2; no flush needed",
+    }
+
+
+# ------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------
+
+
+def run_gpu_arm(args):
+    import torch
+
+    import __graft_entry__ as g
+
+    g.build()
+    from photon_weave_b200 import _lib
+    from photon_weave_b200.core import ffi
+
+    lib = _lib.load()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if world > 1:
+        from photon_weave_b200.sharded import bench_sharded  # noqa: WPS433
+
+        return bench_sharded(args, dist, rank, world, local_rank, make_layer, workload_config,
+                             peaks, ClockSampler, METRIC, UNIT)
+
+    modes, cutoff = args.modes, args.cutoff
+    dims = (cutoff,) * modes
+    N = cutoff**modes
+    layer = make_layer(modes, cutoff)
+    d_ops = [torch.as_tensor(o).cuda() for _, o, _ in layer]
+    targets = [t for t, _, _ in layer]
+    nops = len(layer)
+
+    # synthetic state on the device (plumbing), normalised with our reductions
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    a = torch.view_as_complex(torch.randn(N, 2, generator=gen, device="cuda", dtype=torch.float64))
+    stats = ffi.norm_stats(a)
+    ffi.scale_(a, (1.0 / torch.sqrt(stats[:1])).contiguous())
+    b = torch.empty_like(a)
+
+    def layer_pass(src, dst, events=None):
+        for i in range(nops):
+            if events is not None:
+                events[i].record()
+            ffi.apply_vec(src, d_ops[i], dims, targets[i], out=dst)
+            src, dst = dst, src
+        return src, dst
+
+    for _ in range(args.warmup):
+        a, b = layer_pass(a, b)
+    torch.cuda.synchronize()
+
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(nops + 1)] for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    n0 = lib.pw_launch_count()
+    torch.cuda.synchronize()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for s in range(args.steps):
+        a, b = layer_pass(a, b, ev[s])
+        ev[s][nops].record()
+    t_end.record()
+    torch.cuda.synchronize()
+    launches = int(lib.pw_launch_count() - n0)
+    clocks = sampler.stop()
+    total_ms = t_start.elapsed_time(t_end)
+    ms_per_step = total_ms / args.steps
+    value = nops * N * args.steps / (total_ms * 1e-3)
+
+    # norm must still be 1: every operator in the layer is unitary
+    norm_after = float(ffi.norm_stats(a)[0])
+
+    # per-operation device times from the events recorded inside the timed region
+    per_op_ms = np.zeros(nops)
+    for s in range(args.steps):
+        for i in range(nops):
+            per_op_ms[i] += ev[s][i].elapsed_time(ev[s][i + 1])
+    per_op_ms /= args.steps
+    single_idx = [i for i in range(nops) if len(targets[i]) == 1]
+    pair_idx = [i for i in range(nops) if len(targets[i]) == 2]
+    peak, peak_src = peaks()
+    alg_bytes = 2 * N * 16
+    t_single = float(per_op_ms[single_idx].sum())
+    t_pair = float(per_op_ms[pair_idx].sum()) if pair_idx else 0.0
+    dom = single_idx if t_single >= t_pair else pair_idx
+    dom_name = "apply_vec single-mode (t=%d)" % cutoff if dom is single_idx else \
+        "apply_vec two-mode beam splitter (t=%d)" % (cutoff * cutoff)
+    dom_ms = float(per_op_ms[dom].mean())
+    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": dom_ms,
+        "share_of_step": (t_single if dom is single_idx else t_pair) / float(per_op_ms.sum()),
+    }
+    kernels = {
+        "single_mode": {"launches_per_step": len(single_idx),
+                        "avg_ms": float(per_op_ms[single_idx].mean()),
+                        "min_ms": float(per_op_ms[single_idx].min()),
+                        "max_ms": float(per_op_ms[single_idx].max()),
+                        "gbs": alg_bytes / (float(per_op_ms[single_idx].mean()) * 1e-3) / 1e9},
+    }
+    if pair_idx:
+        kernels["beam_splitter"] = {
+            "launches_per_step": len(pair_idx),
+            "avg_ms": float(per_op_ms[pair_idx].mean()),
+            "gbs": alg_bytes / (float(per_op_ms[pair_idx].mean()) * 1e-3) / 1e9}
+    kernels["per_op_ms"] = {layer[i][2]: round(float(per_op_ms[i]), 4) for i in range(nops)}
+
+    # ---- end to end: host buffers through the C ABI (pw_circuit_host) -------------------
+    e2e = run_e2e(args, torch, ffi, layer, a, N, nops)
+
+    # ---- CPU baseline on a bounded sample --------------------------------------------------
+    cpu = None
+    if not args.no_cpu:
+        m_cpu = pick_cpu_modes(cutoff, 6.0)
+        v, s_step, nops_c, n_c = cpu_layer_throughput(m_cpu, cutoff, 2, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": f"same layer pattern on a {m_cpu}-mode cutoff-{cutoff} state vector "
+                         f"({n_c} amplitudes), 2 timed steps, NumPy/BLAS port of the reference path"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+        "config": workload_config(args, 1), "clocks": clocks, "e2e": e2e,
+        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        "kernels": kernels, "norm_after": norm_after,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_e2e(args, torch, ffi, layer, dev_state, N, nops):
+    """Same step, host buffers: H2D(state + operators) + layer + D2H(state) per step."""
+    try:
+        import psutil
+
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 0
+    need = N * 16
+    if avail < need * 1.5 + (8 << 30):
+        return {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "skipped": f"host has {avail / 1e9:.0f} GB available, needs {need * 1.5 / 1e9:.0f} GB"}
+    dims = (args.cutoff,) * args.modes
+    h = torch.empty(N, dtype=torch.complex128, pin_memory=True)
+    h.copy_(dev_state.reshape(-1))
+    torch.cuda.synchronize()
+    h_np = h.numpy()
+    ops_list = [(0, t, o) for t, o, _ in layer]
+    op_bytes = sum(o.nbytes for _, o, _ in layer)
+    steps = max(1, min(args.steps, args.e2e_steps))
+    ffi.circuit_host(h_np, False, dims, ops_list, device=torch.cuda.current_device(), out=h_np)  # warm-up
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ffi.circuit_host(h_np, False, dims, ops_list, device=torch.cuda.current_device(), out=h_np)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": nops * N / dt, "unit": UNIT, "h2d_bytes_per_step": need + op_bytes,
+            "d2h_bytes_per_step": need, "ms_per_step": dt * 1e3, "steps": steps,
+            "api": "pw_circuit_host (C ABI, pinned host buffers in and out)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--modes", type=int, default=12)
+    ap.add_argument("--cutoff", type=int, default=6)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()
