@@ -341,7 +341,7 @@ def run_gpu_arm(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
         "config": workload_config(args, 1), "clocks": clocks, "e2e": e2e,
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-        "kernels": kernels, "norm_after": norm_after,
+        "kernels": kernels, "norm_after": norm_after, "paths": _lib.path_counters(),
     }
     print(json.dumps(line), flush=True)
 

@@ -57,6 +57,16 @@ const char* pw_status_string(int status);
 int pw_last_cuda_error(void);
 /* Number of kernels this library has launched since load (bench "gpu_launches"). */
 uint64_t pw_launch_count(void);
+/* Which apply path ran since load: out[0] register kernel (t<=8), out[1] generic
+ * fallback kernel, out[2] TMA-tiled kernel, out[3] tiled plans rejected (fell back). */
+void pw_path_counters(uint64_t out[4]);
+/* Tuning knobs (process-wide; also read once from the environment as PW_<NAME>):
+ *   "vec_path"   0 auto | 1 register/generic kernels only | 2 TMA-tiled whenever eligible
+ *   "mat_mode"   0 auto | 1 two-pass fallback | 2 tiled two-sided | 3 tiled superoperator
+ *   "tile_elems" complex elements per shared-memory tile (0 = default)
+ *   "ctas_per_sm" resident CTAs per SM for the tiled kernel (0 = derive from smem)
+ * Returns PW_ERR_INVALID for an unknown name. */
+int pw_set_option(const char* name, int value);
 
 /* ---- apply ------------------------------------------------------------------ */
 

@@ -44,6 +44,8 @@ SIGNATURES = {
     "pw_status_string": (C.c_char_p, [C.c_int]),
     "pw_last_cuda_error": (C.c_int, []),
     "pw_launch_count": (C.c_uint64, []),
+    "pw_path_counters": (None, [C.POINTER(C.c_uint64)]),
+    "pw_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "pw_apply_vec": (C.c_int, [_vp, _vp, _vp, _i64p, C.c_int, _i32p, C.c_int, C.c_int, _vp]),
     "pw_apply_mat": (C.c_int, [_vp, _vp, _vp, _i64p, C.c_int, _i32p, C.c_int, C.c_int, _vp]),
     "pw_kraus_mat": (
@@ -110,3 +112,14 @@ def i64_array(vals: Sequence[int]):
 
 def i32_array(vals: Sequence[int]):
     return (C.c_int32 * max(len(vals), 1))(*[int(v) for v in vals])
+
+
+def path_counters() -> dict:
+    """{'register': n, 'generic': n, 'tiled': n, 'tiled_rejected': n} since library load."""
+    buf = (C.c_uint64 * 4)()
+    load().pw_path_counters(buf)
+    return dict(zip(("register", "generic", "tiled", "tiled_rejected"), [int(v) for v in buf]))
+
+
+def set_option(name: str, value: int) -> None:
+    check(load().pw_set_option(name.encode(), int(value)), f"pw_set_option({name})")

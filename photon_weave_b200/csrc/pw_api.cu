@@ -2,6 +2,9 @@
 #include "pw_internal.cuh"
 #include "pw_threefry.h"
 
+#include <cstdlib>
+#include <cstring>
+
 extern "C" int pw_version(void) { return PW_B200_VERSION; }
 
 extern "C" const char* pw_status_string(int status) {
@@ -26,5 +29,38 @@ extern "C" int pw_rng_split(const uint32_t key[2], int num, uint32_t* out) {
   if (!key || !out || num < 0) return PW_ERR_INVALID;
   for (int i = 0; i < num; ++i)
     pw::threefry2x32(key[0], key[1], 0u, (uint32_t)i, &out[2 * i], &out[2 * i + 1]);
+  return PW_OK;
+}
+
+extern "C" void pw_path_counters(uint64_t out[4]) {
+  for (int i = 0; i < 4; ++i) out[i] = pw::g_paths[i].load(std::memory_order_relaxed);
+}
+
+namespace pw {
+Options& options() {
+  static Options* o = [] {
+    Options* p = new Options();
+    auto env = [](const char* n, std::atomic<int>& dst) {
+      const char* v = std::getenv(n);
+      if (v) dst.store(std::atoi(v));
+    };
+    env("PW_VEC_PATH", p->vec_path);
+    env("PW_MAT_MODE", p->mat_mode);
+    env("PW_TILE_ELEMS", p->tile_elems);
+    env("PW_CTAS_PER_SM", p->ctas_per_sm);
+    return p;
+  }();
+  return *o;
+}
+}  // namespace pw
+
+extern "C" int pw_set_option(const char* name, int value) {
+  if (!name) return PW_ERR_INVALID;
+  pw::Options& o = pw::options();
+  if (!std::strcmp(name, "vec_path")) o.vec_path.store(value);
+  else if (!std::strcmp(name, "mat_mode")) o.mat_mode.store(value);
+  else if (!std::strcmp(name, "tile_elems")) o.tile_elems.store(value);
+  else if (!std::strcmp(name, "ctas_per_sm")) o.ctas_per_sm.store(value);
+  else return PW_ERR_INVALID;
   return PW_OK;
 }

@@ -114,6 +114,7 @@ int build_plan_matrix(const int64_t* dims, int n, const int32_t* targets, int nt
 
 // ---- bookkeeping -----------------------------------------------------------------
 extern std::atomic<uint64_t> g_launches;
+extern std::atomic<uint64_t> g_paths[4];  // small, generic, tiled, tiled-rejected
 extern thread_local int g_last_cuda_error;
 
 inline int cuda_status(cudaError_t e) {
@@ -162,6 +163,12 @@ struct Scratch {
     if (p) cudaFreeAsync(p, s);
   }
 };
+
+// ---- tuning knobs (pw_set_option / PW_* environment) -------------------------
+struct Options {
+  std::atomic<int> vec_path{0}, mat_mode{0}, tile_elems{0}, ctas_per_sm{0};
+};
+Options& options();
 
 // ---- internal launchers (one per .cu) ------------------------------------------
 // out = [out +] (O on plan.tm) in;  conj_op: use conj(O).  in may alias out unless

@@ -4,6 +4,7 @@
 namespace pw {
 
 std::atomic<uint64_t> g_launches{0};
+std::atomic<uint64_t> g_paths[4];
 thread_local int g_last_cuda_error = 0;
 
 static int build_generic(const int64_t* dims, int n, const int* targets, int nt, Plan* plan) {
