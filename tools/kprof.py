@@ -1,0 +1,42 @@
+#!/usr/bin/env python
+"""Runs ONE libpwb200 case a few times (for ncu captures).  Usage:
+   python tools/kprof.py vec|mat <modes> <cutoff> <op: u|bs|phase|loss|dense2> <targets...> [--path P] [--tile E] [--reps R]"""
+import argparse, math, os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as g
+g.build()
+from oracle import operators as ops
+from photon_weave_b200 import _lib
+from photon_weave_b200.core import ffi
+
+ap = argparse.ArgumentParser()
+ap.add_argument("what"); ap.add_argument("modes", type=int); ap.add_argument("cutoff", type=int)
+ap.add_argument("op"); ap.add_argument("targets", type=int, nargs="+")
+ap.add_argument("--path", type=int, default=0); ap.add_argument("--tile", type=int, default=0)
+ap.add_argument("--ctas", type=int, default=0); ap.add_argument("--reps", type=int, default=4)
+a = ap.parse_args()
+_lib.set_option("vec_path", a.path); _lib.set_option("mat_mode", a.path)
+_lib.set_option("tile_elems", a.tile); _lib.set_option("ctas_per_sm", a.ctas)
+d, m = a.cutoff, a.modes
+dims = (d,) * m
+N = d**m
+n = N * N if a.what == "mat" else N
+gen = torch.Generator(device="cuda").manual_seed(0)
+x = torch.view_as_complex(torch.randn(n, 2, generator=gen, device="cuda", dtype=torch.float64))
+y = torch.empty_like(x)
+t = d ** len(a.targets)
+op = {"u": lambda: ops.random_unitary(t, 1), "bs": lambda: ops.beam_splitter(d, d, math.pi / 4),
+      "phase": lambda: ops.phase_operator(d, 0.3), "loss": lambda: ops.loss_channel(d, 0.1),
+      "dense2": lambda: ops.random_unitary(t, 2)}[a.op]()
+op = torch.as_tensor(np.ascontiguousarray(op)).cuda()
+for _ in range(a.reps):
+    if a.what == "vec":
+        ffi.apply_vec(x, op, dims, a.targets, out=y)
+    elif a.op == "loss":
+        ffi.kraus_mat(x, op, dims, a.targets, out=y)
+    else:
+        ffi.apply_mat(x, op, dims, a.targets, out=y)
+torch.cuda.synchronize()
+print("ok", _lib.path_counters())
