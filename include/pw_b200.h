@@ -159,6 +159,16 @@ int pw_norm_stats(const void* x, int64_t count, int dtype, double* stats, void* 
  * (state/composite_envelope.py:685-686). */
 int pw_scale(void* x, int64_t count, const double* scale_dev, int dtype, void* stream);
 
+/* ---- layout ------------------------------------------------------------------ */
+
+/* out = transpose(in.reshape(dims), perm), contiguous (out axis k = in axis perm[k]).
+ * Replaces the jnp.transpose passes of reorder_vector_front / reorder_matrix_front
+ * (core/adapters.py:210-296) and ProductState.reorder
+ * (state/composite_envelope.py:201-248; pass dims ++ dims for a density matrix);
+ * also the pack step of the multi-GPU axis swap.  in and out must not alias. */
+int pw_permute(const void* in, void* out, const int64_t* dims, int n, const int32_t* perm,
+               int dtype, void* stream);
+
 /* ---- host-side PRNG key management (pure integer, no device) --------------- */
 
 /* out[i] = jax.random.split(key, num)[i] (partitionable threefry2x32).

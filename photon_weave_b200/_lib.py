@@ -69,6 +69,7 @@ SIGNATURES = {
     "pw_povm_select": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, C.c_int, _vp]),
     "pw_norm_stats": (C.c_int, [_vp, C.c_int64, C.c_int, _vp, _vp]),
     "pw_scale": (C.c_int, [_vp, C.c_int64, _vp, C.c_int, _vp]),
+    "pw_permute": (C.c_int, [_vp, _vp, _i64p, C.c_int, _i32p, C.c_int, _vp]),
     "pw_rng_split": (C.c_int, [C.POINTER(C.c_uint32), C.c_int, C.POINTER(C.c_uint32)]),
     "pw_circuit_host": (
         C.c_int,

@@ -172,6 +172,18 @@ def scale_(x: torch.Tensor, scale_dev: torch.Tensor):
     return x
 
 
+def permute(x: torch.Tensor, dims, perm, out: Optional[torch.Tensor] = None):
+    """out = transpose(x.reshape(dims), perm) made contiguous (flat tensor returned)."""
+    lib = _lib.load()
+    out = torch.empty_like(x) if out is None else out
+    d, n, p, _ = _common(dims, perm)
+    _lib.check(
+        lib.pw_permute(x.data_ptr(), out.data_ptr(), d, n, p, A.code(x.dtype), A.stream_ptr()),
+        "pw_permute",
+    )
+    return out
+
+
 def rng_split(key, num: int = 2) -> np.ndarray:
     lib = _lib.load()
     k0, k1 = A.key_words(key)

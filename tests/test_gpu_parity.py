@@ -318,3 +318,34 @@ def test_linearity_and_sample_check_large(ad):
     fab = host(ad.apply_operation_vector(dims, (3,), dev(2 * a - 1j * b), dev(op)))
     assert rel_err(fab, 2 * fa - 1j * fb) < 1e-12
     assert rel_err(fa, oad.apply_operation_vector(dims, (3,), a, op)) < 1e-12
+
+
+@pytest.mark.parametrize("cdtype", [np.complex128, np.complex64])
+@pytest.mark.parametrize(
+    "dims,perm",
+    [((2, 3, 4), (2, 0, 1)), ((3, 2, 2, 5), (1, 3, 0, 2)), ((6, 6, 6), (0, 2, 1)), ((4, 1, 3), (2, 1, 0)),
+     ((2, 3, 2, 3), (0, 1, 2, 3))],
+)
+def test_permute_matches_numpy_transpose(ad, dims, perm, cdtype):
+    """pw_permute == jnp.transpose of reorder_vector_front (core/adapters.py:228-230)."""
+    from photon_weave_b200.core import ffi
+
+    N = math.prod(dims)
+    x = ops.random_state(N, 3, cdtype).reshape(-1)
+    out = host(ffi.permute(dev(x), dims, perm))
+    ref = np.ascontiguousarray(np.transpose(x.reshape(dims), perm)).reshape(-1)
+    assert np.array_equal(out, ref)
+
+
+def test_sharded_state_single_rank_cuda_backend(ad):
+    """World size 1 degenerates to the plain kernels (exercises CudaBackend wiring)."""
+    from photon_weave_b200.sharded import CudaBackend, ShardedStateVector, VAxis
+
+    dims = (6, 6, 6)
+    psi = ops.random_state(216, 9)
+    vaxes = [VAxis(g, d, 1) for g, d in enumerate(dims)]
+    st = ShardedStateVector(dims, dev(psi).reshape(-1), vaxes, [], 0, 1, None, CudaBackend())
+    bs = ops.beam_splitter(6, 6, np.pi / 4)
+    st.apply_operation(dev(bs), (2, 0))
+    ref = oad.apply_operation_vector(dims, (2, 0), psi, bs)
+    assert rel_err(host(st.local).reshape(-1, 1), ref) < 1e-12
