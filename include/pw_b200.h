@@ -57,12 +57,17 @@ const char* pw_status_string(int status);
 int pw_last_cuda_error(void);
 /* Number of kernels this library has launched since load (bench "gpu_launches"). */
 uint64_t pw_launch_count(void);
-/* Which apply path ran since load: out[0] register kernel (t<=8), out[1] generic
- * fallback kernel, out[2] TMA-tiled kernel, out[3] tiled plans rejected (fell back). */
-void pw_path_counters(uint64_t out[4]);
+/* Apply paths enqueued since load: out[0] register kernel (t<=8), out[1] generic
+ * fallback kernel, out[2] TMA-tiled kernel, out[3] tiled plans rejected (fell back),
+ * out[4] block-structured attempts (structure analysed on the device; the fallback
+ * enqueued behind it exits when the block kernel handled the operator). */
+void pw_path_counters(uint64_t out[5]);
 /* Tuning knobs (process-wide; also read once from the environment as PW_<NAME>):
  *   "vec_path"   0 auto | 1 register/generic kernels only | 2 TMA-tiled whenever eligible
+ *                | 3 block-structured attempt for every t (then tiled / generic)
  *   "mat_mode"   0 auto | 1 two-pass fallback | 2 tiled two-sided | 3 tiled superoperator
+ *                | 4 superoperator blocks, then two-pass (never the tiled kernel)
+ *   "blocks_min_elems" states smaller than this skip the block-structure analysis
  *   "tile_elems" complex elements per shared-memory tile (0 = default)
  *   "ctas_per_sm" resident CTAs per SM for the tiled kernel (0 = derive from smem)
  * Returns PW_ERR_INVALID for an unknown name. */

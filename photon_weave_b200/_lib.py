@@ -117,9 +117,10 @@ def i32_array(vals: Sequence[int]):
 
 def path_counters() -> dict:
     """{'register': n, 'generic': n, 'tiled': n, 'tiled_rejected': n} since library load."""
-    buf = (C.c_uint64 * 4)()
+    buf = (C.c_uint64 * 5)()
     load().pw_path_counters(buf)
-    return dict(zip(("register", "generic", "tiled", "tiled_rejected"), [int(v) for v in buf]))
+    names = ("register", "generic", "tiled", "tiled_rejected", "blocks_attempted")
+    return dict(zip(names, [int(v) for v in buf]))
 
 
 def set_option(name: str, value: int) -> None:

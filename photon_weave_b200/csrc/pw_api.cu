@@ -32,8 +32,8 @@ extern "C" int pw_rng_split(const uint32_t key[2], int num, uint32_t* out) {
   return PW_OK;
 }
 
-extern "C" void pw_path_counters(uint64_t out[4]) {
-  for (int i = 0; i < 4; ++i) out[i] = pw::g_paths[i].load(std::memory_order_relaxed);
+extern "C" void pw_path_counters(uint64_t out[5]) {
+  for (int i = 0; i < 5; ++i) out[i] = pw::g_paths[i].load(std::memory_order_relaxed);
 }
 
 namespace pw {
@@ -48,6 +48,7 @@ Options& options() {
     env("PW_MAT_MODE", p->mat_mode);
     env("PW_TILE_ELEMS", p->tile_elems);
     env("PW_CTAS_PER_SM", p->ctas_per_sm);
+    env("PW_BLOCKS_MIN_ELEMS", p->blocks_min_elems);
     return p;
   }();
   return *o;
@@ -61,6 +62,7 @@ extern "C" int pw_set_option(const char* name, int value) {
   else if (!std::strcmp(name, "mat_mode")) o.mat_mode.store(value);
   else if (!std::strcmp(name, "tile_elems")) o.tile_elems.store(value);
   else if (!std::strcmp(name, "ctas_per_sm")) o.ctas_per_sm.store(value);
+  else if (!std::strcmp(name, "blocks_min_elems")) o.blocks_min_elems.store(value);
   else return PW_ERR_INVALID;
   return PW_OK;
 }

@@ -7,6 +7,7 @@
 
 #include "pw_internal.cuh"
 #include "pw_tiled.cuh"
+#include "pw_blocks.cuh"
 
 namespace pw {
 
@@ -27,7 +28,8 @@ constexpr int small_min_blocks() {
 template <typename V, int T, bool CONJ, bool ACC>
 __global__ void __launch_bounds__(256, small_min_blocks<V, T>())
 k_apply_small(const V* in, V* out, const V* __restrict__ op, const FiberMap fm,
-              const TargetMap tm) {
+              const TargetMap tm, const int* __restrict__ skip) {
+  if (skip && *skip) return;
   __shared__ V s_op[T * T];
   __shared__ int64_t s_off[T];
   for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
@@ -68,7 +70,9 @@ k_apply_small(const V* in, V* out, const V* __restrict__ op, const FiberMap fm,
 template <typename V, bool CONJ, bool ACC>
 __global__ void __launch_bounds__(128)
 k_apply_generic(const V* __restrict__ in, V* __restrict__ out, const V* __restrict__ op,
-                const FiberMap fm, const TargetMap tm, const int64_t* __restrict__ toff) {
+                const FiberMap fm, const TargetMap tm, const int64_t* __restrict__ toff,
+                const int* __restrict__ skip) {
+  if (skip && *skip) return;
   const uint32_t t = tm.t;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < fm.nfib; f += stride) {
@@ -94,16 +98,16 @@ __global__ void k_target_offsets(const TargetMap tm, int64_t* toff) {
 
 template <typename V, int T>
 static int launch_small(const V* in, V* out, const V* op, const Plan& p, bool conj_op,
-                        bool acc, cudaStream_t s) {
+                        bool acc, cudaStream_t s, const int* skip) {
   const int block = 256;
   const int grid = grid_for(p.fm.nfib, block, 8);
   g_paths[0].fetch_add(1, std::memory_order_relaxed);
   if (conj_op) {
-    if (acc) k_apply_small<V, T, true, true><<<grid, block, 0, s>>>(in, out, op, p.fm, p.tm);
-    else     k_apply_small<V, T, true, false><<<grid, block, 0, s>>>(in, out, op, p.fm, p.tm);
+    if (acc) k_apply_small<V, T, true, true><<<grid, block, 0, s>>>(in, out, op, p.fm, p.tm, skip);
+    else     k_apply_small<V, T, true, false><<<grid, block, 0, s>>>(in, out, op, p.fm, p.tm, skip);
   } else {
-    if (acc) k_apply_small<V, T, false, true><<<grid, block, 0, s>>>(in, out, op, p.fm, p.tm);
-    else     k_apply_small<V, T, false, false><<<grid, block, 0, s>>>(in, out, op, p.fm, p.tm);
+    if (acc) k_apply_small<V, T, false, true><<<grid, block, 0, s>>>(in, out, op, p.fm, p.tm, skip);
+    else     k_apply_small<V, T, false, false><<<grid, block, 0, s>>>(in, out, op, p.fm, p.tm, skip);
   }
   PW_LAUNCHED();
   return PW_OK;
@@ -111,16 +115,16 @@ static int launch_small(const V* in, V* out, const V* op, const Plan& p, bool co
 
 template <typename V>
 static int launch_apply_t(const V* in, V* out, const V* op, const Plan& p, bool conj_op,
-                          bool acc, cudaStream_t s) {
+                          bool acc, cudaStream_t s, const int* skip) {
   switch (p.tm.t) {
-    case 1: return launch_small<V, 1>(in, out, op, p, conj_op, acc, s);
-    case 2: return launch_small<V, 2>(in, out, op, p, conj_op, acc, s);
-    case 3: return launch_small<V, 3>(in, out, op, p, conj_op, acc, s);
-    case 4: return launch_small<V, 4>(in, out, op, p, conj_op, acc, s);
-    case 5: return launch_small<V, 5>(in, out, op, p, conj_op, acc, s);
-    case 6: return launch_small<V, 6>(in, out, op, p, conj_op, acc, s);
-    case 7: return launch_small<V, 7>(in, out, op, p, conj_op, acc, s);
-    case 8: return launch_small<V, 8>(in, out, op, p, conj_op, acc, s);
+    case 1: return launch_small<V, 1>(in, out, op, p, conj_op, acc, s, skip);
+    case 2: return launch_small<V, 2>(in, out, op, p, conj_op, acc, s, skip);
+    case 3: return launch_small<V, 3>(in, out, op, p, conj_op, acc, s, skip);
+    case 4: return launch_small<V, 4>(in, out, op, p, conj_op, acc, s, skip);
+    case 5: return launch_small<V, 5>(in, out, op, p, conj_op, acc, s, skip);
+    case 6: return launch_small<V, 6>(in, out, op, p, conj_op, acc, s, skip);
+    case 7: return launch_small<V, 7>(in, out, op, p, conj_op, acc, s, skip);
+    case 8: return launch_small<V, 8>(in, out, op, p, conj_op, acc, s, skip);
     default: break;
   }
   g_paths[1].fetch_add(1, std::memory_order_relaxed);
@@ -138,24 +142,24 @@ static int launch_apply_t(const V* in, V* out, const V* op, const Plan& p, bool 
   const int block = 128;
   const int grid = grid_for(p.fm.nfib, block, 8);
   if (conj_op) {
-    if (acc) k_apply_generic<V, true, true><<<grid, block, 0, s>>>(src, out, op, p.fm, p.tm, (int64_t*)toff.p);
-    else     k_apply_generic<V, true, false><<<grid, block, 0, s>>>(src, out, op, p.fm, p.tm, (int64_t*)toff.p);
+    if (acc) k_apply_generic<V, true, true><<<grid, block, 0, s>>>(src, out, op, p.fm, p.tm, (int64_t*)toff.p, skip);
+    else     k_apply_generic<V, true, false><<<grid, block, 0, s>>>(src, out, op, p.fm, p.tm, (int64_t*)toff.p, skip);
   } else {
-    if (acc) k_apply_generic<V, false, true><<<grid, block, 0, s>>>(src, out, op, p.fm, p.tm, (int64_t*)toff.p);
-    else     k_apply_generic<V, false, false><<<grid, block, 0, s>>>(src, out, op, p.fm, p.tm, (int64_t*)toff.p);
+    if (acc) k_apply_generic<V, false, true><<<grid, block, 0, s>>>(src, out, op, p.fm, p.tm, (int64_t*)toff.p, skip);
+    else     k_apply_generic<V, false, false><<<grid, block, 0, s>>>(src, out, op, p.fm, p.tm, (int64_t*)toff.p, skip);
   }
   PW_LAUNCHED();
   return PW_OK;
 }
 
 int launch_apply(const void* in, void* out, const void* op, const Plan& plan, int dtype,
-                 bool conj_op, bool accumulate, cudaStream_t stream) {
+                 bool conj_op, bool accumulate, cudaStream_t stream, const int* skip) {
   if (dtype == PW_C128)
     return launch_apply_t<double2>((const double2*)in, (double2*)out, (const double2*)op, plan,
-                                   conj_op, accumulate, stream);
+                                   conj_op, accumulate, stream, skip);
   if (dtype == PW_C64)
     return launch_apply_t<float2>((const float2*)in, (float2*)out, (const float2*)op, plan,
-                                  conj_op, accumulate, stream);
+                                  conj_op, accumulate, stream, skip);
   return PW_ERR_INVALID;
 }
 
@@ -172,105 +176,170 @@ static uint32_t tile_elems(int dtype) {
   if (v > 0) return (uint32_t)v;
   return dtype == PW_C128 ? 1024u : 2048u;
 }
+// states below this many elements are launch-latency bound: skip structure analysis
+static uint64_t blocks_min_elems() {
+  return (uint64_t)options().blocks_min_elems.load(std::memory_order_relaxed);
+}
 
-extern "C" int pw_apply_vec(const void* psi, void* out, const void* op, const int64_t* dims,
-                            int n, const int32_t* targets, int nt, int dtype, void* stream) {
-  if (!psi || !out || !op || nt < 1) return PW_ERR_INVALID;
-  if (dtype != PW_C64 && dtype != PW_C128) return PW_ERR_INVALID;
+// One strided apply on an arbitrary axis list: out = (O or conj(O) on targets) in.
+//   t <= 8                      register kernel
+//   t <= 128, large, in != out  block-structured attempt, then a fallback that exits on
+//                               the device when the block kernel took the operator
+//   fallback                    TMA-tiled CSR kernel if eligible, else the generic kernel
+static int apply_axes(const void* in, void* out, const void* op, const int64_t* axes, int naxes,
+                      const int* targets, int nt, bool conj_op, int dtype, cudaStream_t s) {
   Plan p;
-  PW_TRY(build_plan(dims, n, targets, nt, &p));
-  const bool want_tiled = vec_path() == 2 || (vec_path() == 0 && p.tm.t > 8);
-  if (want_tiled) {
+  PW_TRY(build_plan_axes(axes, naxes, targets, nt, &p));
+  const int vp = vec_path();
+  if (p.tm.t <= 8 && vp != 2 && vp != 3) return launch_apply(in, out, op, p, dtype, conj_op, false, s);
+  BlockDesc bd;
+  const int* skip = nullptr;
+  if ((vp == 0 || vp == 3) && in != out && p.tm.t <= kBlockMaxT && p.N >= blocks_min_elems()) {
+    const int rc = launch_blocks(in, out, op, p, dtype, conj_op, &bd, s);
+    if (rc == PW_OK) skip = bd.skip_flag();
+    else if (rc != PW_ERR_UNSUPPORTED) return rc;
+  }
+  if (vp != 1) {
     TiledGeom g;
-    if (plan_tiled(dims, n, targets, nt, nullptr, 0, -1, elem_size(dtype), tile_elems(dtype), &g)) {
-      const int rc = launch_tiled(psi, out, op, 1, g, kModeVector, dtype, (cudaStream_t)stream);
+    if (plan_tiled(axes, naxes, targets, nt, nullptr, 0, -1, elem_size(dtype), tile_elems(dtype), &g)) {
+      const int rc = launch_tiled(in, out, op, 1, g, conj_op ? kModeVectorConj : kModeVector, dtype, s, skip);
       if (rc != PW_ERR_UNSUPPORTED) return rc;
     }
     g_paths[3].fetch_add(1, std::memory_order_relaxed);
   }
-  return launch_apply(psi, out, op, p, dtype, false, false, (cudaStream_t)stream);
+  return launch_apply(in, out, op, p, dtype, conj_op, false, s, skip);
 }
 
-// One HBM pass over rho when the (row target, column target) tile fits shared memory.
-static int try_tiled_matrix(const void* rho, void* out, const void* ops, int K, const int64_t* dims,
-                            int n, const int32_t* targets, int nt, int dtype, cudaStream_t s) {
-  if (mat_mode() == 1 || n > PW_MAX_SUBSYSTEMS || nt > PW_MAX_TARGETS) return PW_ERR_UNSUPPORTED;
+extern "C" int pw_apply_vec(const void* psi, void* out, const void* op, const int64_t* dims,
+                            int n, const int32_t* targets, int nt, int dtype, void* stream) {
+  if (!psi || !out || !op || nt < 1 || !dims || !targets) return PW_ERR_INVALID;
+  if (dtype != PW_C64 && dtype != PW_C128) return PW_ERR_INVALID;
+  if (n > PW_MAX_SUBSYSTEMS || nt > PW_MAX_TARGETS) return PW_ERR_INVALID;
+  return apply_axes(psi, out, op, dims, n, targets, nt, false, dtype, (cudaStream_t)stream);
+}
+
+struct MatrixReq {
   int64_t axes[kMaxAxes];
   int rows[kMaxTargets], cols[kMaxTargets], both[kMaxTargets];
-  uint64_t t = 1;
-  for (int i = 0; i < n; ++i) axes[i] = axes[n + i] = dims[i];
+  int n, nt;
+  uint64_t t, N;
+};
+
+static int matrix_req(const int64_t* dims, int n, const int32_t* targets, int nt, MatrixReq* r) {
+  if (!dims || !targets || n < 1 || n > PW_MAX_SUBSYSTEMS || nt < 1 || nt > PW_MAX_TARGETS)
+    return PW_ERR_INVALID;
+  r->n = n; r->nt = nt; r->t = 1; r->N = 1;
+  for (int i = 0; i < n; ++i) {
+    if (dims[i] < 1) return PW_ERR_INVALID;
+    r->axes[i] = r->axes[n + i] = dims[i];
+    r->N *= (uint64_t)dims[i];
+  }
   for (int k = 0; k < nt; ++k) {
     if (targets[k] < 0 || targets[k] >= n) return PW_ERR_INVALID;
-    rows[k] = both[k] = targets[k];
-    cols[k] = both[nt + k] = n + targets[k];
-    t *= (uint64_t)dims[targets[k]];
+    r->rows[k] = r->both[k] = targets[k];
+    r->cols[k] = r->both[nt + k] = n + targets[k];
+    r->t *= (uint64_t)dims[targets[k]];
   }
-  bool super = K > 1 && t * t <= 256 && (uint64_t)K * 2 >= t;
-  if (mat_mode() == 2) super = false;
-  if (mat_mode() == 3) super = t * t <= 1024;
-  TiledGeom g;
-  if (super) {
-    if (!plan_tiled(axes, 2 * n, both, 2 * nt, nullptr, 0, -1, elem_size(dtype), tile_elems(dtype), &g))
-      return PW_ERR_UNSUPPORTED;
-    return launch_tiled(rho, out, ops, K, g, kModeMatrixSuper, dtype, s);
-  }
-  if (!plan_tiled(axes, 2 * n, rows, nt, cols, nt, -1, elem_size(dtype), tile_elems(dtype), &g))
-    return PW_ERR_UNSUPPORTED;
-  return launch_tiled(rho, out, ops, K, g, kModeMatrixTwoSided, dtype, s);
+  return PW_OK;
 }
 
-// one side of a density-matrix update as a (possibly tiled) strided apply
-static int apply_side(const void* in, void* out, const void* op, const int64_t* dims, int n,
-                      const int32_t* targets, int nt, bool cols, bool accumulate, int dtype,
-                      cudaStream_t s) {
+// S = sum_k K_k (x) conj(K_k) on the device, then the block-structured kernel on the
+// (row targets, column targets) of the doubled tensor: ONE HBM pass whatever K is.
+static int try_super_blocks(const void* rho, void* out, const void* ops, int K, const MatrixReq& r,
+                            int dtype, cudaStream_t s, Scratch* super, BlockDesc* bd) {
+  if (rho == out || r.t * r.t > kBlockMaxT || r.N * r.N < blocks_min_elems()) return PW_ERR_UNSUPPORTED;
+  const size_t es = elem_size(dtype);
+  const uint64_t tt = r.t * r.t;
+  PW_TRY(super->alloc(es * tt * tt, s));
+  PW_TRY(build_superoperator(ops, K, (uint32_t)r.t, super->p, dtype, s));
   Plan p;
-  PW_TRY(build_plan_matrix(dims, n, targets, nt, !cols, cols, &p));
-  return launch_apply(in, out, op, p, dtype, cols, accumulate, s);
+  PW_TRY(build_plan_axes(r.axes, 2 * r.n, r.both, 2 * r.nt, &p));
+  return launch_blocks(rho, out, super->p, p, dtype, false, bd, s);
+}
+
+// one side of rho' = O rho O^dagger as a strided apply on the doubled tensor
+static int apply_side(const void* in, void* out, const void* op, const MatrixReq& r, bool cols,
+                      bool accumulate, int dtype, cudaStream_t s, const int* skip) {
+  const int* tg = cols ? r.cols : r.rows;
+  if (r.t <= 8 || skip || accumulate) {
+    Plan p;
+    PW_TRY(build_plan_axes(r.axes, 2 * r.n, tg, r.nt, &p));
+    return launch_apply(in, out, op, p, dtype, cols, accumulate, s, skip);
+  }
+  return apply_axes(in, out, op, r.axes, 2 * r.n, tg, r.nt, cols, dtype, s);
+}
+
+// fallback: two HBM passes per operator (row side, then conj on the column side)
+static int two_pass(const void* rho, void* out, const void* ops, int K, const MatrixReq& r,
+                    int dtype, cudaStream_t s, const int* skip) {
+  const size_t es = elem_size(dtype);
+  if (K == 1) {
+    PW_TRY(apply_side(rho, out, ops, r, false, false, dtype, s, skip));
+    return apply_side(out, out, ops, r, true, false, dtype, s, skip);
+  }
+  // out = sum_k (K_k rho) K_k^dagger; tmp holds K_k rho, the column pass accumulates
+  const size_t bytes = (size_t)(r.N * r.N) * es, op_bytes = (size_t)(r.t * r.t) * es;
+  Scratch tmp, src;
+  PW_TRY(tmp.alloc(bytes, s));
+  const void* in = rho;
+  if (rho == out) {
+    PW_TRY(src.alloc(bytes, s));
+    PW_CUDA(cudaMemcpyAsync(src.p, rho, bytes, cudaMemcpyDeviceToDevice, s));
+    in = src.p;
+  }
+  for (int k = 0; k < K; ++k) {
+    const char* opk = (const char*)ops + (size_t)k * op_bytes;
+    PW_TRY(apply_side(in, tmp.p, opk, r, false, false, dtype, s, skip));
+    PW_TRY(apply_side(tmp.p, out, opk, r, true, k > 0, dtype, s, skip));
+  }
+  return PW_OK;
+}
+
+static int matrix_dispatch(const void* rho, void* out, const void* ops, int K, const int64_t* dims,
+                           int n, const int32_t* targets, int nt, int dtype, cudaStream_t s) {
+  MatrixReq r;
+  PW_TRY(matrix_req(dims, n, targets, nt, &r));
+  const int mm = mat_mode();
+  const size_t es = elem_size(dtype);
+  Scratch super;
+  BlockDesc bd;
+  const int* skip = nullptr;
+  if (mm == 0 || mm == 4) {
+    const int rc = try_super_blocks(rho, out, ops, K, r, dtype, s, &super, &bd);
+    if (rc == PW_OK) skip = bd.skip_flag();
+    else if (rc != PW_ERR_UNSUPPORTED) return rc;
+  }
+  // single-pass tiled kernel (operator pairs applied on the resident tile)
+  const bool tiled_ok = mm == 2 || mm == 3 || (mm == 0 && (K > 1 || r.t > 8));
+  if (tiled_ok) {
+    bool super_mode = K > 1 && r.t * r.t <= 256 && (uint64_t)K * 2 >= r.t;
+    if (mm == 2) super_mode = false;
+    if (mm == 3) super_mode = r.t * r.t <= 1024;
+    TiledGeom g;
+    int rc = PW_ERR_UNSUPPORTED;
+    if (super_mode) {
+      if (plan_tiled(r.axes, 2 * n, r.both, 2 * nt, nullptr, 0, -1, es, tile_elems(dtype), &g))
+        rc = launch_tiled(rho, out, ops, K, g, kModeMatrixSuper, dtype, s, skip);
+    } else if (plan_tiled(r.axes, 2 * n, r.rows, nt, r.cols, nt, -1, es, tile_elems(dtype), &g)) {
+      rc = launch_tiled(rho, out, ops, K, g, kModeMatrixTwoSided, dtype, s, skip);
+    }
+    if (rc != PW_ERR_UNSUPPORTED) return rc;
+    g_paths[3].fetch_add(1, std::memory_order_relaxed);
+  }
+  return two_pass(rho, out, ops, K, r, dtype, s, skip);
 }
 
 extern "C" int pw_apply_mat(const void* rho, void* out, const void* op, const int64_t* dims,
                             int n, const int32_t* targets, int nt, int dtype, void* stream) {
-  if (!rho || !out || !op || nt < 1) return PW_ERR_INVALID;
+  if (!rho || !out || !op) return PW_ERR_INVALID;
   if (dtype != PW_C64 && dtype != PW_C128) return PW_ERR_INVALID;
-  cudaStream_t s = (cudaStream_t)stream;
-  const int rc = try_tiled_matrix(rho, out, op, 1, dims, n, targets, nt, dtype, s);
-  if (rc != PW_ERR_UNSUPPORTED) return rc;
-  g_paths[3].fetch_add(1, std::memory_order_relaxed);
-  // fallback, two HBM passes: left multiply on the row axes, conj(O) on the column axes
-  PW_TRY(apply_side(rho, out, op, dims, n, targets, nt, false, false, dtype, s));
-  return apply_side(out, out, op, dims, n, targets, nt, true, false, dtype, s);
+  return matrix_dispatch(rho, out, op, 1, dims, n, targets, nt, dtype, (cudaStream_t)stream);
 }
 
 extern "C" int pw_kraus_mat(const void* rho, void* out, const void* ops, int K,
                             const int64_t* dims, int n, const int32_t* targets, int nt,
                             int dtype, void* stream) {
-  if (!rho || !out || !ops || nt < 1 || K < 1) return PW_ERR_INVALID;
+  if (!rho || !out || !ops || K < 1) return PW_ERR_INVALID;
   if (dtype != PW_C64 && dtype != PW_C128) return PW_ERR_INVALID;
-  cudaStream_t s = (cudaStream_t)stream;
-  const int rc = try_tiled_matrix(rho, out, ops, K, dims, n, targets, nt, dtype, s);
-  if (rc != PW_ERR_UNSUPPORTED) return rc;
-  g_paths[3].fetch_add(1, std::memory_order_relaxed);
-  Plan rows;
-  PW_TRY(build_plan_matrix(dims, n, targets, nt, true, false, &rows));
-  const size_t es = elem_size(dtype);
-  const size_t op_bytes = (size_t)rows.tm.t * rows.tm.t * es;
-  if (K == 1) {
-    PW_TRY(apply_side(rho, out, ops, dims, n, targets, nt, false, false, dtype, s));
-    return apply_side(out, out, ops, dims, n, targets, nt, true, false, dtype, s);
-  }
-  // fallback: out = sum_k (K_k rho) K_k^dagger; tmp holds K_k rho, second pass accumulates
-  Scratch tmp, src;
-  PW_TRY(tmp.alloc(rows.N * es, s));
-  const void* in = rho;
-  if (rho == out) {
-    PW_TRY(src.alloc(rows.N * es, s));
-    PW_CUDA(cudaMemcpyAsync(src.p, rho, rows.N * es, cudaMemcpyDeviceToDevice, s));
-    in = src.p;
-  }
-  for (int k = 0; k < K; ++k) {
-    const char* opk = (const char*)ops + (size_t)k * op_bytes;
-    PW_TRY(apply_side(in, tmp.p, opk, dims, n, targets, nt, false, false, dtype, s));
-    PW_TRY(apply_side(tmp.p, out, opk, dims, n, targets, nt, true, k > 0, dtype, s));
-  }
-  return PW_OK;
+  return matrix_dispatch(rho, out, ops, K, dims, n, targets, nt, dtype, (cudaStream_t)stream);
 }

@@ -35,8 +35,13 @@ extern "C" int pw_circuit_host(const void* h_state, void* h_out, int is_matrix,
 
   Stream st;
   PW_CUDA(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
-  DevBuf state;
+  DevBuf state, other;
   PW_CUDA(cudaMalloc(&state.p, bytes));
+  // ping-pong when a second buffer fits (lets the block-structured path run); else in place
+  if (cudaMalloc(&other.p, bytes) != cudaSuccess) {
+    other.p = nullptr;
+    (void)cudaGetLastError();
+  }
 
   // operators: one small upload each, queued ahead of the state so they overlap it
   std::vector<DevBuf> dops(nops);
@@ -59,16 +64,18 @@ extern "C" int pw_circuit_host(const void* h_state, void* h_out, int is_matrix,
   for (int i = 0; i < nops; ++i) {
     const pw_host_op& o = ops[i];
     int rc;
+    void* dst = other.p ? other.p : state.p;
     if (o.kind == 0)
-      rc = pw_apply_vec(state.p, state.p, dops[i].p, dims, n, o.targets, o.nt, dtype, st.s);
+      rc = pw_apply_vec(state.p, dst, dops[i].p, dims, n, o.targets, o.nt, dtype, st.s);
     else if (o.kind == 1)
-      rc = pw_apply_mat(state.p, state.p, dops[i].p, dims, n, o.targets, o.nt, dtype, st.s);
+      rc = pw_apply_mat(state.p, dst, dops[i].p, dims, n, o.targets, o.nt, dtype, st.s);
     else
-      rc = pw_kraus_mat(state.p, state.p, dops[i].p, o.K, dims, n, o.targets, o.nt, dtype, st.s);
+      rc = pw_kraus_mat(state.p, dst, dops[i].p, o.K, dims, n, o.targets, o.nt, dtype, st.s);
     if (rc != PW_OK) {
       cudaStreamSynchronize(st.s);
       return rc;
     }
+    if (other.p) { void* tmp = state.p; state.p = other.p; other.p = tmp; }
   }
   PW_CUDA(cudaMemcpyAsync(h_out, state.p, bytes, cudaMemcpyDeviceToHost, st.s));
   PW_CUDA(cudaStreamSynchronize(st.s));

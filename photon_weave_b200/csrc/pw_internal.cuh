@@ -111,10 +111,12 @@ int build_plan(const int64_t* dims, int n, const int32_t* targets, int nt, Plan*
 // Doubled (density-matrix) tensor: axes dims ++ dims, targets rows then columns.
 int build_plan_matrix(const int64_t* dims, int n, const int32_t* targets, int nt,
                       bool rows, bool cols, Plan* plan);
+// Arbitrary axis list (up to kMaxAxes axes / kMaxTargets targets), e.g. dims ++ dims.
+int build_plan_axes(const int64_t* axes, int naxes, const int* targets, int nt, Plan* plan);
 
 // ---- bookkeeping -----------------------------------------------------------------
 extern std::atomic<uint64_t> g_launches;
-extern std::atomic<uint64_t> g_paths[4];  // small, generic, tiled, tiled-rejected
+extern std::atomic<uint64_t> g_paths[5];  // small, generic, tiled, tiled-rejected, blocks
 extern thread_local int g_last_cuda_error;
 
 inline int cuda_status(cudaError_t e) {
@@ -167,13 +169,16 @@ struct Scratch {
 // ---- tuning knobs (pw_set_option / PW_* environment) -------------------------
 struct Options {
   std::atomic<int> vec_path{0}, mat_mode{0}, tile_elems{0}, ctas_per_sm{0};
+  std::atomic<int> blocks_min_elems{1 << 18};  // below this, skip structure analysis
 };
 Options& options();
 
 // ---- internal launchers (one per .cu) ------------------------------------------
 // out = [out +] (O on plan.tm) in;  conj_op: use conj(O).  in may alias out unless
 // accumulate.  `op` is a device pointer, row-major (t x t).
+// `skip`: optional device flag; when *skip != 0 the kernels exit at once (another path
+// already produced the result).
 int launch_apply(const void* in, void* out, const void* op, const Plan& plan, int dtype,
-                 bool conj_op, bool accumulate, cudaStream_t stream);
+                 bool conj_op, bool accumulate, cudaStream_t stream, const int* skip = nullptr);
 
 }  // namespace pw

@@ -4,7 +4,7 @@
 namespace pw {
 
 std::atomic<uint64_t> g_launches{0};
-std::atomic<uint64_t> g_paths[4];
+std::atomic<uint64_t> g_paths[5];
 thread_local int g_last_cuda_error = 0;
 
 static int build_generic(const int64_t* dims, int n, const int* targets, int nt, Plan* plan) {
@@ -49,6 +49,10 @@ static int build_generic(const int64_t* dims, int n, const int* targets, int nt,
   }
   plan->N = N;
   return PW_OK;
+}
+
+int build_plan_axes(const int64_t* axes, int naxes, const int* targets, int nt, Plan* plan) {
+  return build_generic(axes, naxes, targets, nt, plan);
 }
 
 int build_plan(const int64_t* dims, int n, const int32_t* targets, int nt, Plan* plan) {

@@ -393,6 +393,7 @@ __global__ void __launch_bounds__(kTileThreads)
 k_tiled(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
         const __grid_constant__ TiledParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
+  if (P.skip && *P.skip) return;
   const TiledGeom& g = P.g;
   const uint32_t tile_bytes = (g.tile_elems * (uint32_t)sizeof(V) + 127u) & ~127u;
   const int nwork = P.mode == kModeMatrixTwoSided ? 2 : 1;
@@ -465,7 +466,10 @@ k_tiled(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
       }
       res = w1;
     } else {
-      run_pass<V, false>(in_buf[b], w0, g.kind[0], 0, s_foff0, s_toff0, P.rowptr, ents, false);
+      if (P.mode == kModeVectorConj)
+        run_pass<V, true>(in_buf[b], w0, g.kind[0], 0, s_foff0, s_toff0, P.rowptr, ents, false);
+      else
+        run_pass<V, false>(in_buf[b], w0, g.kind[0], 0, s_foff0, s_toff0, P.rowptr, ents, false);
       res = w0;
     }
     fence_proxy_async();  // generic-proxy writes of `res` -> visible to the TMA store
@@ -529,7 +533,7 @@ static bool encode_map(CUtensorMap* tm, const void* base, const TiledGeom& g, bo
 
 template <typename V>
 static int launch_tiled_t(const V* in, V* out, const V* ops, int K, const TiledGeom& g, int mode,
-                          cudaStream_t s) {
+                          cudaStream_t s, const int* skip) {
   if (((uintptr_t)in | (uintptr_t)out) & 15) return PW_ERR_UNSUPPORTED;
   const PassKind& k0 = g.kind[0];
   const V* csr_src = ops;
@@ -564,6 +568,7 @@ static int launch_tiled_t(const V* in, V* out, const V* ops, int K, const TiledG
   TiledParams P;
   P.g = g;
   P.mode = mode;
+  P.skip = skip;
   P.K = csrK;
   P.csr_cap = cap;
   P.rowptr = (const int32_t*)rowptr.p;
@@ -594,12 +599,24 @@ static int launch_tiled_t(const V* in, V* out, const V* ops, int K, const TiledG
 }
 
 int launch_tiled(const void* in, void* out, const void* ops, int K, const TiledGeom& g, int mode,
-                 int dtype, cudaStream_t stream) {
+                 int dtype, cudaStream_t stream, const int* skip) {
   if (dtype == PW_C128)
-    return launch_tiled_t<double2>((const double2*)in, (double2*)out, (const double2*)ops, K, g, mode, stream);
+    return launch_tiled_t<double2>((const double2*)in, (double2*)out, (const double2*)ops, K, g, mode, stream, skip);
   if (dtype == PW_C64)
-    return launch_tiled_t<float2>((const float2*)in, (float2*)out, (const float2*)ops, K, g, mode, stream);
+    return launch_tiled_t<float2>((const float2*)in, (float2*)out, (const float2*)ops, K, g, mode, stream, skip);
   return PW_ERR_INVALID;
+}
+
+int build_superoperator(const void* ops, int K, uint32_t t, void* S, int dtype, cudaStream_t s) {
+  const uint64_t total = (uint64_t)t * t * t * t;
+  if (dtype == PW_C128)
+    k_build_super<double2><<<grid_for(total, 256, 8), 256, 0, s>>>((const double2*)ops, K, t, (double2*)S);
+  else if (dtype == PW_C64)
+    k_build_super<float2><<<grid_for(total, 256, 8), 256, 0, s>>>((const float2*)ops, K, t, (float2*)S);
+  else
+    return PW_ERR_INVALID;
+  PW_LAUNCHED();
+  return PW_OK;
 }
 
 }  // namespace pw

@@ -48,13 +48,14 @@ struct TiledGeom {
 };
 
 // mode of the pass program executed per tile
-enum { kModeVector = 0, kModeMatrixTwoSided = 1, kModeMatrixSuper = 2 };
+enum { kModeVector = 0, kModeMatrixTwoSided = 1, kModeMatrixSuper = 2, kModeVectorConj = 3 };
 
 struct TiledParams {
   TiledGeom g;
   int mode;
   int K;                 // operators (Kraus terms); 1 for a plain apply
   uint32_t csr_cap;      // entries reserved per operator
+  const int* skip;       // optional device flag: exit when *skip != 0
   const int32_t* rowptr; // [K][t+1]
   const void* ents;      // [K][csr_cap] Entry<V>
 };
@@ -81,6 +82,9 @@ bool plan_tiled(const int64_t* axes, int naxes, const int* kind0, int nt0, const
 
 // Launches CSR preparation + the tiled kernel.  ops: device (K, t, t).  mode as above.
 int launch_tiled(const void* in, void* out, const void* ops, int K, const TiledGeom& g, int mode,
-                 int dtype, cudaStream_t stream);
+                 int dtype, cudaStream_t stream, const int* skip = nullptr);
+
+// S (t^2 x t^2) = sum_k K_k (x) conj(K_k), row-major, on the device.
+int build_superoperator(const void* ops, int K, uint32_t t, void* S, int dtype, cudaStream_t stream);
 
 }  // namespace pw
