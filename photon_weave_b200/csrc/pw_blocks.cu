@@ -184,8 +184,9 @@ static int launch_blocks_t(const V* in, V* out, const V* op, const Plan& p, bool
                            BlockDesc* d, cudaStream_t s) {
   const uint32_t t = p.tm.t;
   // descriptor storage: header | blocks[t] | offs[2t] | zero_offs[t] | vals[t*t]
-  const size_t b_hdr = 64, b_blk = sizeof(int4) * t, b_off = sizeof(int64_t) * 2 * t,
-               b_zero = sizeof(int64_t) * t, b_val = sizeof(V) * (size_t)t * t;
+  auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  const size_t b_hdr = 64, b_blk = sizeof(int4) * t, b_off = al(sizeof(int64_t) * 2 * t),
+               b_zero = al(sizeof(int64_t) * t), b_val = sizeof(V) * (size_t)t * t;
   PW_TRY(d->mem.alloc(b_hdr + b_blk + b_off + b_zero + b_val, s));
   char* base = (char*)d->mem.p;
   d->hdr = (BlockDescHeader*)base;
