@@ -186,15 +186,27 @@ static uint64_t blocks_min_elems() {
 //   t <= 128, large, in != out  block-structured attempt, then a fallback that exits on
 //                               the device when the block kernel took the operator
 //   fallback                    TMA-tiled CSR kernel if eligible, else the generic kernel
+// size of the innermost run of untouched axes if it is the contiguous (stride-1) one,
+// else 0 (the innermost axis of the tensor is a target)
+static uint64_t inner_rest_run(const Plan& p) {
+  if (p.fm.ng == 0) return 0;
+  return p.fm.gstride[p.fm.ng - 1] == 1 ? p.fm.gsize[p.fm.ng - 1] : 0;
+}
+
 static int apply_axes(const void* in, void* out, const void* op, const int64_t* axes, int naxes,
                       const int* targets, int nt, bool conj_op, int dtype, cudaStream_t s) {
   Plan p;
   PW_TRY(build_plan_axes(axes, naxes, targets, nt, &p));
   const int vp = vec_path();
-  if (p.tm.t <= 8 && vp != 2 && vp != 3) return launch_apply(in, out, op, p, dtype, conj_op, false, s);
+  const uint64_t r_in = inner_rest_run(p);
+  const uint64_t small_r = (uint64_t)options().small_r.load(std::memory_order_relaxed);
+  const bool large = p.N >= blocks_min_elems();
+  // tiled (TMA) staging pays when the contiguous direction belongs to the fibers themselves
+  const bool prefer_tiled = vp == 2 || (vp == 0 && large && r_in < small_r);
+  if (p.tm.t <= 8 && vp != 3 && !prefer_tiled) return launch_apply(in, out, op, p, dtype, conj_op, false, s);
   BlockDesc bd;
   const int* skip = nullptr;
-  if ((vp == 0 || vp == 3) && in != out && p.tm.t <= kBlockMaxT && p.N >= blocks_min_elems()) {
+  if ((vp == 0 || vp == 3) && !prefer_tiled && in != out && p.tm.t <= kBlockMaxT && large) {
     const int rc = launch_blocks(in, out, op, p, dtype, conj_op, &bd, s);
     if (rc == PW_OK) skip = bd.skip_flag();
     else if (rc != PW_ERR_UNSUPPORTED) return rc;
@@ -248,6 +260,12 @@ static int matrix_req(const int64_t* dims, int n, const int32_t* targets, int nt
 static int try_super_blocks(const void* rho, void* out, const void* ops, int K, const MatrixReq& r,
                             int dtype, cudaStream_t s, Scratch* super, BlockDesc* bd) {
   if (rho == out || r.t * r.t > kBlockMaxT || r.N * r.N < blocks_min_elems()) return PW_ERR_UNSUPPORTED;
+  {
+    Plan q;
+    PW_TRY(build_plan_axes(r.axes, 2 * r.n, r.both, 2 * r.nt, &q));
+    if (mat_mode() == 0 && inner_rest_run(q) < (uint64_t)options().small_r.load(std::memory_order_relaxed))
+      return PW_ERR_UNSUPPORTED;  // contiguous direction is a target: the tiled kernel stages it
+  }
   const size_t es = elem_size(dtype);
   const uint64_t tt = r.t * r.t;
   PW_TRY(super->alloc(es * tt * tt, s));
@@ -310,9 +328,11 @@ static int matrix_dispatch(const void* rho, void* out, const void* ops, int K, c
     else if (rc != PW_ERR_UNSUPPORTED) return rc;
   }
   // single-pass tiled kernel (operator pairs applied on the resident tile)
-  const bool tiled_ok = mm == 2 || mm == 3 || (mm == 0 && (K > 1 || r.t > 8));
+  const bool tiled_ok = mm == 2 || mm == 3 || mm == 0;
   if (tiled_ok) {
-    bool super_mode = K > 1 && r.t * r.t <= 256 && (uint64_t)K * 2 >= r.t;
+    // superoperator pass when it is cheap enough: Kraus sums always (t^2 <= 256), single
+    // operators when the structure analysis may find small blocks (t^2 <= 128)
+    bool super_mode = r.t * r.t <= 256 && ((K > 1 && (uint64_t)K * 2 >= r.t) || (K == 1 && skip == nullptr && r.t * r.t <= kBlockMaxT && mm == 0 && options().mat_super_single.load(std::memory_order_relaxed)));
     if (mm == 2) super_mode = false;
     if (mm == 3) super_mode = r.t * r.t <= 1024;
     TiledGeom g;

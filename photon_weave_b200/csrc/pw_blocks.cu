@@ -180,30 +180,46 @@ k_apply_blocks(const V* __restrict__ in, V* __restrict__ out, const FiberMap fm,
 }
 
 template <typename V>
-static int launch_blocks_t(const V* in, V* out, const V* op, const Plan& p, bool conj_op,
-                           BlockDesc* d, cudaStream_t s) {
-  const uint32_t t = p.tm.t;
+static int build_block_desc_t(const V* op, uint32_t t, bool conj_op, const TargetMap& tm,
+                              Scratch* mem, BlockArrays* arr, cudaStream_t s) {
   // descriptor storage: header | blocks[t] | offs[2t] | zero_offs[t] | vals[t*t]
   auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
   const size_t b_hdr = 64, b_blk = sizeof(int4) * t, b_off = al(sizeof(int64_t) * 2 * t),
                b_zero = al(sizeof(int64_t) * t), b_val = sizeof(V) * (size_t)t * t;
-  PW_TRY(d->mem.alloc(b_hdr + b_blk + b_off + b_zero + b_val, s));
-  char* base = (char*)d->mem.p;
-  d->hdr = (BlockDescHeader*)base;
-  int4* blocks = (int4*)(base + b_hdr);
-  int64_t* offs = (int64_t*)(base + b_hdr + b_blk);
-  int64_t* zero_offs = (int64_t*)(base + b_hdr + b_blk + b_off);
-  V* vals = (V*)(base + b_hdr + b_blk + b_off + b_zero);
-  k_build_blocks<V><<<1, 256, sizeof(int32_t) * 3 * t, s>>>(op, t, conj_op, p.tm, d->hdr, blocks, offs, vals,
-                                                          zero_offs);
+  PW_TRY(mem->alloc(b_hdr + b_blk + b_off + b_zero + b_val, s));
+  char* base = (char*)mem->p;
+  arr->hdr = (BlockDescHeader*)base;
+  arr->blocks = (int4*)(base + b_hdr);
+  arr->offs = (int64_t*)(base + b_hdr + b_blk);
+  arr->zero_offs = (int64_t*)(base + b_hdr + b_blk + b_off);
+  arr->vals = base + b_hdr + b_blk + b_off + b_zero;
+  k_build_blocks<V><<<1, 256, sizeof(int32_t) * 3 * t, s>>>(op, t, conj_op, tm, arr->hdr, arr->blocks,
+                                                          arr->offs, (V*)arr->vals, arr->zero_offs);
   PW_LAUNCHED();
+  return PW_OK;
+}
+
+int build_block_desc(const void* op, uint32_t t, bool conj_op, const TargetMap& tm, int dtype,
+                     Scratch* mem, BlockArrays* arr, cudaStream_t stream) {
+  if (t > kBlockMaxT) return PW_ERR_UNSUPPORTED;
+  if (dtype == PW_C128) return build_block_desc_t<double2>((const double2*)op, t, conj_op, tm, mem, arr, stream);
+  if (dtype == PW_C64) return build_block_desc_t<float2>((const float2*)op, t, conj_op, tm, mem, arr, stream);
+  return PW_ERR_INVALID;
+}
+
+template <typename V>
+static int launch_blocks_t(const V* in, V* out, const V* op, const Plan& p, bool conj_op,
+                           BlockDesc* d, cudaStream_t s) {
+  PW_TRY(build_block_desc_t<V>(op, p.tm.t, conj_op, p.tm, &d->mem, &d->arr, s));
+  d->hdr = d->arr.hdr;
+  const BlockArrays& A = d->arr;
   const int grid = grid_for(p.fm.nfib, 256, 8);
-  // three instantiations cover max block sizes (0,2], (2,4], (4,8]; two of them exit at once
-  k_apply_blocks<V, 2><<<grid, 256, 0, s>>>(in, out, p.fm, d->hdr, blocks, offs, vals, zero_offs);
+  // three instantiations cover max block sizes [0,2], (2,4], (4,8]; two of them exit at once
+  k_apply_blocks<V, 2><<<grid, 256, 0, s>>>(in, out, p.fm, A.hdr, A.blocks, A.offs, (const V*)A.vals, A.zero_offs);
   PW_LAUNCHED();
-  k_apply_blocks<V, 4><<<grid, 256, 0, s>>>(in, out, p.fm, d->hdr, blocks, offs, vals, zero_offs);
+  k_apply_blocks<V, 4><<<grid, 256, 0, s>>>(in, out, p.fm, A.hdr, A.blocks, A.offs, (const V*)A.vals, A.zero_offs);
   PW_LAUNCHED();
-  k_apply_blocks<V, 8><<<grid, 256, 0, s>>>(in, out, p.fm, d->hdr, blocks, offs, vals, zero_offs);
+  k_apply_blocks<V, 8><<<grid, 256, 0, s>>>(in, out, p.fm, A.hdr, A.blocks, A.offs, (const V*)A.vals, A.zero_offs);
   PW_LAUNCHED();
   g_paths[4].fetch_add(1, std::memory_order_relaxed);
   return PW_OK;

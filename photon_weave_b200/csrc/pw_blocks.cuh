@@ -14,11 +14,27 @@ struct BlockDescHeader {
   int usable;  // 1: the block kernel handles this operator; fallback kernels must exit
 };
 
+// device pointers of one analysed operator
+struct BlockArrays {
+  BlockDescHeader* hdr = nullptr;
+  int4* blocks = nullptr;        // per block: nr, nc, offset into offs, offset into vals
+  int64_t* offs = nullptr;       // per block: nc column offsets then nr row offsets (elements)
+  int64_t* zero_offs = nullptr;  // offsets of all-zero rows
+  void* vals = nullptr;          // per block: dense nr x nc values (row-major)
+};
+
 struct BlockDesc {
   Scratch mem;
+  BlockArrays arr;
   BlockDescHeader* hdr = nullptr;
   const int* skip_flag() const { return hdr ? &hdr->usable : nullptr; }
 };
+
+// Enqueues the structure analysis of a dense t x t operator (t <= kBlockMaxT); element
+// offsets come from `tm` (global strides for the direct kernel, tile strides for the
+// tiled kernel).
+int build_block_desc(const void* op, uint32_t t, bool conj_op, const TargetMap& tm, int dtype,
+                     Scratch* mem, BlockArrays* arr, cudaStream_t stream);
 
 // Enqueues structure analysis + the block apply kernels.  `conj_op`: use conj(op).
 // Requires in != out.  After this call the caller must enqueue a fallback path whose

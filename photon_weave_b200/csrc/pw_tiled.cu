@@ -388,6 +388,44 @@ __device__ __forceinline__ void run_pass(const V* __restrict__ src, V* __restric
   }
 }
 
+// Block-structured pass: the operator is a set of small dense blocks (rows R_b, columns
+// C_b).  Work item = (block, fiber), fibers fastest, so a warp mostly shares one block:
+// descriptor loads are broadcast, the <= MAXN inputs of the block are gathered from the
+// tile into registers, the dense product runs against broadcast values.
+template <typename V, int MAXN>
+__device__ __forceinline__ void run_pass_blocks(const V* __restrict__ src, V* __restrict__ dst,
+                                                const uint32_t nfib,
+                                                const int32_t* __restrict__ s_foff,
+                                                const BlockArrays& A) {
+  const int nblocks = A.hdr->nblocks, nzero = A.hdr->nzero;
+  const V* vals = (const V*)A.vals;
+  const uint32_t items = (uint32_t)nblocks * nfib;
+  for (uint32_t it = threadIdx.x; it < items; it += blockDim.x) {
+    const uint32_t b = it / nfib;
+    const int32_t fo = s_foff[it - b * nfib];
+    const int4 h = __ldg(A.blocks + b);
+    const int nr = h.x, nc = h.y;
+    const int64_t* bo = A.offs + h.z;
+    const V* bv = vals + h.w;
+    V x[MAXN];
+#pragma unroll
+    for (int j = 0; j < MAXN; ++j)
+      if (j < nc) x[j] = src[fo + (int32_t)__ldg(bo + j)];
+    for (int a = 0; a < nr; ++a) {
+      V acc = czero<V>();
+#pragma unroll
+      for (int j = 0; j < MAXN; ++j)
+        if (j < nc) cfma(acc, __ldg(bv + a * nc + j), x[j]);
+      dst[fo + (int32_t)__ldg(bo + nc + a)] = acc;
+    }
+  }
+  const uint32_t zitems = (uint32_t)nzero * nfib;
+  for (uint32_t it = threadIdx.x; it < zitems; it += blockDim.x) {
+    const uint32_t z = it / nfib;
+    dst[s_foff[it - z * nfib] + (int32_t)__ldg(A.zero_offs + z)] = czero<V>();
+  }
+}
+
 template <typename V>
 __global__ void __launch_bounds__(kTileThreads)
 k_tiled(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
@@ -396,13 +434,13 @@ k_tiled(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
   if (P.skip && *P.skip) return;
   const TiledGeom& g = P.g;
   const uint32_t tile_bytes = (g.tile_elems * (uint32_t)sizeof(V) + 127u) & ~127u;
+  const int NS = P.nstage;
   const int nwork = P.mode == kModeMatrixTwoSided ? 2 : 1;
-  V* in_buf[2] = {(V*)smem, (V*)(smem + tile_bytes)};
-  V* w0 = (V*)(smem + 2 * (size_t)tile_bytes);
-  V* w1 = (V*)(smem + 3 * (size_t)tile_bytes);
-  unsigned char* tail = smem + (size_t)(2 + nwork) * tile_bytes;
-  uint64_t* full = (uint64_t*)tail;  // [2]
-  int32_t* s_foff0 = (int32_t*)(tail + 16);
+  V* w0 = (V*)(smem + (size_t)NS * tile_bytes);
+  V* w1 = (V*)(smem + (size_t)(NS + 1) * tile_bytes);
+  unsigned char* tail = smem + (size_t)(NS + nwork) * tile_bytes;
+  uint64_t* full = (uint64_t*)tail;  // [NS] (room for 8)
+  int32_t* s_foff0 = (int32_t*)(tail + 64);
   int32_t* s_toff0 = s_foff0 + g.kind[0].nfib;
   int32_t* s_foff1 = s_toff0 + g.kind[0].t;
   int32_t* s_toff1 = s_foff1 + (g.nkinds > 1 ? g.kind[1].nfib : 0);
@@ -425,51 +463,63 @@ k_tiled(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
     for (uint32_t a = threadIdx.x; a < pk.t; a += blockDim.x) toff[a] = kind_offset(pk, a);
   }
   if (threadIdx.x == 0) {
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
+    for (int i = 0; i < NS; ++i) mbar_init(&full[i], 1);
     fence_barrier_init();
   }
   __syncthreads();
+
+  // block-structured compute when the device-side analysis found only small blocks
+  bool use_blocks = P.blk[0].hdr != nullptr && P.blk[0].hdr->usable != 0;
+  if (P.mode == kModeMatrixTwoSided)
+    use_blocks = use_blocks && P.K == 1 && P.blk[1].hdr != nullptr && P.blk[1].hdr->usable != 0;
 
   const uint64_t G = gridDim.x;
   const uint32_t tx_bytes = g.tile_elems * (uint32_t)sizeof(V);
   int32_t c[kMaxRuns];
   if (threadIdx.x == 0) {
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < NS; ++b) {
       const uint64_t tile = blockIdx.x + (uint64_t)b * G;
       if (tile < g.ntiles) {
         tile_coords(g, tile, c);
         mbar_expect_tx(&full[b], tx_bytes);
-        tma_load(&tm_in, g.rank, in_buf[b], &full[b], c);
+        tma_load(&tm_in, g.rank, smem + (size_t)b * tile_bytes, &full[b], c);
       }
     }
   }
 
   const Entry<V>* ents = (const Entry<V>*)P.ents;
-  uint32_t it = 0;
+  uint32_t it = 0, stage = 0, phase = 0;
   for (uint64_t tile = blockIdx.x; tile < g.ntiles; tile += G, ++it) {
-    const int b = it & 1;
-    mbar_wait(&full[b], (it >> 1) & 1);
+    V* in_tile = (V*)(smem + (size_t)stage * tile_bytes);
+    mbar_wait(&full[stage], phase);
     // the result buffer of the previous tile must have been read out by its TMA store
     if (threadIdx.x == 0) tma_store_wait_read0();
     __syncthreads();
 
     V* res;
     if (P.mode == kModeMatrixTwoSided) {
-      for (int k = 0; k < P.K; ++k) {
-        const int32_t* rp = P.rowptr + (size_t)k * (g.kind[0].t + 1);
-        const Entry<V>* en = ents + (size_t)k * P.csr_cap;
-        run_pass<V, false>(in_buf[b], w0, g.kind[0], 0, s_foff0, s_toff0, rp, en, false);
+      if (use_blocks) {
+        run_pass_blocks<V, kBlockMaxN>(in_tile, w0, g.kind[0].nfib, s_foff0, P.blk[0]);
         __syncthreads();
-        run_pass<V, true>(w0, w1, g.kind[1], 1, s_foff1, s_toff1, rp, en, k > 0);
-        __syncthreads();
+        run_pass_blocks<V, kBlockMaxN>(w0, w1, g.kind[1].nfib, s_foff1, P.blk[1]);
+      } else {
+        for (int k = 0; k < P.K; ++k) {
+          const int32_t* rp = P.rowptr + (size_t)k * (g.kind[0].t + 1);
+          const Entry<V>* en = ents + (size_t)k * P.csr_cap;
+          run_pass<V, false>(in_tile, w0, g.kind[0], 0, s_foff0, s_toff0, rp, en, false);
+          __syncthreads();
+          run_pass<V, true>(w0, w1, g.kind[1], 1, s_foff1, s_toff1, rp, en, k > 0);
+          if (k + 1 < P.K) __syncthreads();
+        }
       }
       res = w1;
     } else {
-      if (P.mode == kModeVectorConj)
-        run_pass<V, true>(in_buf[b], w0, g.kind[0], 0, s_foff0, s_toff0, P.rowptr, ents, false);
+      if (use_blocks)
+        run_pass_blocks<V, kBlockMaxN>(in_tile, w0, g.kind[0].nfib, s_foff0, P.blk[0]);
+      else if (P.mode == kModeVectorConj)
+        run_pass<V, true>(in_tile, w0, g.kind[0], 0, s_foff0, s_toff0, P.rowptr, ents, false);
       else
-        run_pass<V, false>(in_buf[b], w0, g.kind[0], 0, s_foff0, s_toff0, P.rowptr, ents, false);
+        run_pass<V, false>(in_tile, w0, g.kind[0], 0, s_foff0, s_toff0, P.rowptr, ents, false);
       res = w0;
     }
     fence_proxy_async();  // generic-proxy writes of `res` -> visible to the TMA store
@@ -478,13 +528,14 @@ k_tiled(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
       tile_coords(g, tile, c);
       tma_store(&tm_out, g.rank, res, c);
       tma_store_commit();
-      const uint64_t next = tile + 2 * G;  // in_buf[b] is free again: prefetch
+      const uint64_t next = tile + (uint64_t)NS * G;  // this stage is free again: prefetch
       if (next < g.ntiles) {
         tile_coords(g, next, c);
-        mbar_expect_tx(&full[b], tx_bytes);
-        tma_load(&tm_in, g.rank, in_buf[b], &full[b], c);
+        mbar_expect_tx(&full[stage], tx_bytes);
+        tma_load(&tm_in, g.rank, in_tile, &full[stage], c);
       }
     }
+    if (++stage == (uint32_t)NS) { stage = 0; phase ^= 1; }
   }
   if (threadIdx.x == 0) tma_store_wait_all();
 }
@@ -531,10 +582,19 @@ static bool encode_map(CUtensorMap* tm, const void* base, const TiledGeom& g, bo
   return r == CUDA_SUCCESS;
 }
 
+static TargetMap kind_target_map(const PassKind& pk) {
+  TargetMap tm;
+  tm.nt = pk.nt;
+  tm.t = pk.t;
+  for (int i = 0; i < pk.nt; ++i) { tm.tdim[i] = pk.tdim[i]; tm.tstride[i] = (int64_t)pk.tstride[i]; }
+  return tm;
+}
+
 template <typename V>
 static int launch_tiled_t(const V* in, V* out, const V* ops, int K, const TiledGeom& g, int mode,
                           cudaStream_t s, const int* skip) {
   if (((uintptr_t)in | (uintptr_t)out) & 15) return PW_ERR_UNSUPPORTED;
+  const int dtype = sizeof(V) == 16 ? PW_C128 : PW_C64;
   const PassKind& k0 = g.kind[0];
   const V* csr_src = ops;
   int csrK = K;
@@ -542,18 +602,15 @@ static int launch_tiled_t(const V* in, V* out, const V* ops, int K, const TiledG
   Scratch super;
   if (mode == kModeMatrixSuper) {
     // kind 0 acts on (row targets, col targets) with the t^2 x t^2 superoperator
-    const uint32_t tt = g.kind[0].t;  // = t_single^2
     uint32_t ts = 1;
-    while ((uint64_t)ts * ts < tt) ++ts;
-    PW_TRY(super.alloc(sizeof(V) * (size_t)tt * tt, s));
-    const uint64_t total = (uint64_t)tt * tt;
-    k_build_super<V><<<grid_for(total, 256, 8), 256, 0, s>>>(ops, K, ts, (V*)super.p);
-    PW_LAUNCHED();
+    while ((uint64_t)ts * ts < t) ++ts;
+    PW_TRY(super.alloc(sizeof(V) * (size_t)t * t, s));
+    PW_TRY(build_superoperator(ops, K, ts, super.p, dtype, s));
     csr_src = (const V*)super.p;
     csrK = 1;
   }
   const uint32_t cap = t * t;
-  Scratch rowptr, ents;
+  Scratch rowptr, ents, bmem0, bmem1;
   PW_TRY(rowptr.alloc(sizeof(int32_t) * (size_t)csrK * (t + 1), s));
   PW_TRY(ents.alloc(sizeof(Entry<V>) * (size_t)csrK * cap, s));
   k_build_csr<V><<<csrK, 256, sizeof(int32_t) * (t + 1), s>>>(
@@ -561,29 +618,42 @@ static int launch_tiled_t(const V* in, V* out, const V* ops, int K, const TiledG
       (Entry<V>*)ents.p);
   PW_LAUNCHED();
 
+  TiledParams P;
+  P.g = g;
+  P.mode = mode;
+  P.K = csrK;
+  P.skip = skip;
+  P.csr_cap = cap;
+  P.rowptr = (const int32_t*)rowptr.p;
+  P.ents = ents.p;
+  // block-structured descriptors with TILE offsets (single operator only)
+  if (csrK == 1 && t <= kBlockMaxT && options().vec_path.load(std::memory_order_relaxed) != 2) {
+    PW_TRY(build_block_desc(csr_src, t, mode == kModeVectorConj, kind_target_map(g.kind[0]), dtype,
+                            &bmem0, &P.blk[0], s));
+    if (mode == kModeMatrixTwoSided)
+      PW_TRY(build_block_desc(csr_src, t, true, kind_target_map(g.kind[1]), dtype, &bmem1, &P.blk[1], s));
+  }
+
   CUtensorMap tm_in, tm_out;
   if (!encode_map(&tm_in, in, g, sizeof(V) == 16) || !encode_map(&tm_out, out, g, sizeof(V) == 16))
     return PW_ERR_UNSUPPORTED;
 
-  TiledParams P;
-  P.g = g;
-  P.mode = mode;
-  P.skip = skip;
-  P.K = csrK;
-  P.csr_cap = cap;
-  P.rowptr = (const int32_t*)rowptr.p;
-  P.ents = ents.p;
-
   const uint32_t tile_bytes = (g.tile_elems * (uint32_t)sizeof(V) + 127u) & ~127u;
-  const int nbuf = 2 + (mode == kModeMatrixTwoSided ? 2 : 1);
-  size_t tables = 16;
+  const int nwork = mode == kModeMatrixTwoSided ? 2 : 1;
+  size_t tables = 64;
   for (int q = 0; q < g.nkinds; ++q) tables += sizeof(int32_t) * ((size_t)g.kind[q].nfib + g.kind[q].t);
-  const size_t smem = (size_t)nbuf * tile_bytes + tables;
+  // stages: as many as keep >= 2 CTAs per SM, between 2 and 4
+  int nstage = 4;
+  while (nstage > 2 && (size_t)(nstage + nwork) * tile_bytes + tables > 100 * 1024) --nstage;
+  const int forced_ns = options().nstage.load(std::memory_order_relaxed);
+  if (forced_ns >= 2 && forced_ns <= 8) nstage = forced_ns;
+  P.nstage = nstage;
+  const size_t smem = (size_t)(nstage + nwork) * tile_bytes + tables;
   if (smem > 220 * 1024) return PW_ERR_UNSUPPORTED;
-  static thread_local size_t attr_set = 0;
-  if (smem > attr_set) {
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
     PW_CUDA(cudaFuncSetAttribute(k_tiled<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
-    attr_set = 220 * 1024;
+    attr_set = true;
   }
   int ctas_per_sm = (int)((227 * 1024) / (smem + 1024));
   if (ctas_per_sm < 1) ctas_per_sm = 1;

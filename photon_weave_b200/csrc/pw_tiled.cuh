@@ -13,6 +13,7 @@
 #include <cuda.h>
 
 #include "pw_internal.cuh"
+#include "pw_blocks.cuh"
 
 namespace pw {
 
@@ -54,10 +55,14 @@ struct TiledParams {
   TiledGeom g;
   int mode;
   int K;                 // operators (Kraus terms); 1 for a plain apply
+  int nstage;            // input tiles in flight per CTA
   uint32_t csr_cap;      // entries reserved per operator
   const int* skip;       // optional device flag: exit when *skip != 0
   const int32_t* rowptr; // [K][t+1]
   const void* ents;      // [K][csr_cap] Entry<V>
+  // block-structured form of the operator per pass kind (tile offsets); hdr == nullptr
+  // or hdr->usable == 0 selects the CSR compute path instead
+  BlockArrays blk[2];
 };
 
 template <typename V> struct Entry;

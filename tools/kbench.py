@@ -147,7 +147,12 @@ if __name__ == "__main__":
     ap.add_argument("--tile-elems", type=int, nargs="+", default=[0])
     ap.add_argument("--c64", action="store_true")
     ap.add_argument("--slow", action="store_true")
+    ap.add_argument("--set", nargs="*", default=[], help="pw_set_option name=value ...")
     args = ap.parse_args()
+    for kv in args.set:
+        k, v = kv.split("=")
+        _lib.set_option(k, int(v))
+    print("options:", args.set, flush=True)
     if args.what == "vec":
         args.modes = args.modes or 12
         args.cutoff = args.cutoff or 6
