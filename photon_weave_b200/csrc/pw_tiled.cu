@@ -393,10 +393,10 @@ __device__ __forceinline__ void run_pass(const V* __restrict__ src, V* __restric
 // descriptor loads are broadcast, the <= MAXN inputs of the block are gathered from the
 // tile into registers, the dense product runs against broadcast values.
 template <typename V, int MAXN>
-__device__ __forceinline__ void run_pass_blocks(const V* __restrict__ src, V* __restrict__ dst,
+__device__ __noinline__ void run_pass_blocks(const V* __restrict__ src, V* __restrict__ dst,
                                                 const uint32_t nfib,
                                                 const int32_t* __restrict__ s_foff,
-                                                const BlockArrays& A) {
+                                                const BlockArrays A) {
   const int nblocks = A.hdr->nblocks, nzero = A.hdr->nzero;
   const V* vals = (const V*)A.vals;
   const uint32_t items = (uint32_t)nblocks * nfib;
@@ -411,6 +411,7 @@ __device__ __forceinline__ void run_pass_blocks(const V* __restrict__ src, V* __
 #pragma unroll
     for (int j = 0; j < MAXN; ++j)
       if (j < nc) x[j] = src[fo + (int32_t)__ldg(bo + j)];
+#pragma unroll 1
     for (int a = 0; a < nr; ++a) {
       V acc = czero<V>();
 #pragma unroll
@@ -426,12 +427,22 @@ __device__ __forceinline__ void run_pass_blocks(const V* __restrict__ src, V* __
   }
 }
 
-template <typename V>
-__global__ void __launch_bounds__(kTileThreads)
+// Two instantiations share the pipeline: BLOCKS = block-structured register compute (runs
+// only when the device-side analysis marked the operator usable), !BLOCKS = CSR compute
+// (runs otherwise).  Both are enqueued; exactly one does the work.
+template <typename V, bool BLOCKS>
+__global__ void __launch_bounds__(kTileThreads, 3)
 k_tiled(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out,
         const __grid_constant__ TiledParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   if (P.skip && *P.skip) return;
+  {
+    // block-structured compute when the device-side analysis found only small blocks
+    bool use_blocks = P.blk[0].hdr != nullptr && P.blk[0].hdr->usable != 0;
+    if (P.mode == kModeMatrixTwoSided)
+      use_blocks = use_blocks && P.K == 1 && P.blk[1].hdr != nullptr && P.blk[1].hdr->usable != 0;
+    if (use_blocks != BLOCKS) return;
+  }
   const TiledGeom& g = P.g;
   const uint32_t tile_bytes = (g.tile_elems * (uint32_t)sizeof(V) + 127u) & ~127u;
   const int NS = P.nstage;
@@ -468,11 +479,6 @@ k_tiled(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
   }
   __syncthreads();
 
-  // block-structured compute when the device-side analysis found only small blocks
-  bool use_blocks = P.blk[0].hdr != nullptr && P.blk[0].hdr->usable != 0;
-  if (P.mode == kModeMatrixTwoSided)
-    use_blocks = use_blocks && P.K == 1 && P.blk[1].hdr != nullptr && P.blk[1].hdr->usable != 0;
-
   const uint64_t G = gridDim.x;
   const uint32_t tx_bytes = g.tile_elems * (uint32_t)sizeof(V);
   int32_t c[kMaxRuns];
@@ -498,7 +504,7 @@ k_tiled(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
 
     V* res;
     if (P.mode == kModeMatrixTwoSided) {
-      if (use_blocks) {
+      if (BLOCKS) {
         run_pass_blocks<V, kBlockMaxN>(in_tile, w0, g.kind[0].nfib, s_foff0, P.blk[0]);
         __syncthreads();
         run_pass_blocks<V, kBlockMaxN>(w0, w1, g.kind[1].nfib, s_foff1, P.blk[1]);
@@ -514,7 +520,7 @@ k_tiled(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
       }
       res = w1;
     } else {
-      if (use_blocks)
+      if (BLOCKS)
         run_pass_blocks<V, kBlockMaxN>(in_tile, w0, g.kind[0].nfib, s_foff0, P.blk[0]);
       else if (P.mode == kModeVectorConj)
         run_pass<V, true>(in_tile, w0, g.kind[0], 0, s_foff0, s_toff0, P.rowptr, ents, false);
@@ -652,7 +658,8 @@ static int launch_tiled_t(const V* in, V* out, const V* ops, int K, const TiledG
   if (smem > 220 * 1024) return PW_ERR_UNSUPPORTED;
   static thread_local bool attr_set = false;
   if (!attr_set) {
-    PW_CUDA(cudaFuncSetAttribute(k_tiled<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+    PW_CUDA(cudaFuncSetAttribute(k_tiled<V, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+    PW_CUDA(cudaFuncSetAttribute(k_tiled<V, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
     attr_set = true;
   }
   int ctas_per_sm = (int)((227 * 1024) / (smem + 1024));
@@ -663,7 +670,11 @@ static int launch_tiled_t(const V* in, V* out, const V* ops, int K, const TiledG
   uint64_t grid = (uint64_t)kNumSMs * ctas_per_sm;
   if (grid > g.ntiles) grid = g.ntiles;
   g_paths[2].fetch_add(1, std::memory_order_relaxed);
-  k_tiled<V><<<(unsigned)grid, kTileThreads, smem, s>>>(tm_in, tm_out, P);
+  if (P.blk[0].hdr != nullptr) {
+    k_tiled<V, true><<<(unsigned)grid, kTileThreads, smem, s>>>(tm_in, tm_out, P);
+    PW_LAUNCHED();
+  }
+  k_tiled<V, false><<<(unsigned)grid, kTileThreads, smem, s>>>(tm_in, tm_out, P);
   PW_LAUNCHED();
   return PW_OK;
 }
