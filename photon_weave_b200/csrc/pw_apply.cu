@@ -201,8 +201,10 @@ static int apply_axes(const void* in, void* out, const void* op, const int64_t* 
   const uint64_t r_in = inner_rest_run(p);
   const uint64_t small_r = (uint64_t)options().small_r.load(std::memory_order_relaxed);
   const bool large = p.N >= blocks_min_elems();
-  // tiled (TMA) staging pays when the contiguous direction belongs to the fibers themselves
-  const bool prefer_tiled = vp == 2 || (vp == 0 && large && r_in < small_r);
+  // Measured on B200 (profiles/r1_kbench_*): the register kernel wins for every t <= 8
+  // layout; for t > 8 the direct block kernel wins when the contiguous direction is an
+  // untouched run (>= small_r elements), TMA-staged tiles win when it belongs to the fibers.
+  const bool prefer_tiled = vp == 2 || (vp == 0 && large && r_in < small_r && p.tm.t > 8);
   if (p.tm.t <= 8 && vp != 3 && !prefer_tiled) return launch_apply(in, out, op, p, dtype, conj_op, false, s);
   BlockDesc bd;
   const int* skip = nullptr;
@@ -328,7 +330,8 @@ static int matrix_dispatch(const void* rho, void* out, const void* ops, int K, c
     else if (rc != PW_ERR_UNSUPPORTED) return rc;
   }
   // single-pass tiled kernel (operator pairs applied on the resident tile)
-  const bool tiled_ok = mm == 2 || mm == 3 || mm == 0;
+  // single operators: two register-kernel passes beat the tiled two-sided kernel (measured)
+  const bool tiled_ok = mm == 2 || mm == 3 || (mm == 0 && (K > 1 || r.t > 8));
   if (tiled_ok) {
     // superoperator pass when it is cheap enough: Kraus sums always (t^2 <= 256), single
     // operators when the structure analysis may find small blocks (t^2 <= 128)
