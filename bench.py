@@ -60,6 +60,16 @@ def make_layer(modes: int, cutoff: int):
     return layer
 
 
+def ncu_traffic(kernel_key: str):
+    """dram__bytes_read+write per launch from the committed `ncu --set full` capture
+    (profiles/r1_traffic.json, produced by tools/ncu_summary.py); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        return json.load(open(path)).get(kernel_key, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -305,7 +315,9 @@ def run_gpu_arm(args):
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / peak,
+        "traffic": ncu_traffic("single_mode" if dom is single_idx else "beam_splitter"),
+        "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": dom_ms,
         "share_of_step": (t_single if dom is single_idx else t_pair) / float(per_op_ms.sum()),
     }
@@ -324,7 +336,15 @@ def run_gpu_arm(args):
     kernels["per_op_ms"] = {layer[i][2]: round(float(per_op_ms[i]), 4) for i in range(nops)}
 
     # ---- end to end: host buffers through the C ABI (pw_circuit_host) -------------------
-    e2e = run_e2e(args, torch, ffi, layer, a, N, nops)
+    e2e, h_pinned = run_e2e_prepare(args, torch, a, N)
+    del a, b
+    torch.cuda.empty_cache()
+    if h_pinned is not None:
+        e2e = run_e2e(args, torch, ffi, layer, h_pinned, N, nops)
+        del h_pinned
+
+    # ---- density-matrix side of the metric (configs[3]): Kraus / apply on a 5-mode rho -----
+    extras = None if args.no_extras else run_matrix_extras(torch, ffi, peak)
 
     # ---- CPU baseline on a bounded sample --------------------------------------------------
     cpu = None
@@ -341,13 +361,14 @@ def run_gpu_arm(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
         "config": workload_config(args, 1), "clocks": clocks, "e2e": e2e,
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-        "kernels": kernels, "norm_after": norm_after, "paths": _lib.path_counters(),
+        "kernels": kernels, "norm_after": norm_after, "density_matrix": extras,
+        "paths": _lib.path_counters(),
     }
     print(json.dumps(line), flush=True)
 
 
-def run_e2e(args, torch, ffi, layer, dev_state, N, nops):
-    """Same step, host buffers: H2D(state + operators) + layer + D2H(state) per step."""
+def run_e2e_prepare(args, torch, dev_state, N):
+    """Copy the evolved state into a pinned host buffer (outside any timed region)."""
     try:
         import psutil
 
@@ -356,24 +377,82 @@ def run_e2e(args, torch, ffi, layer, dev_state, N, nops):
         avail = 0
     need = N * 16
     if avail < need * 1.5 + (8 << 30):
-        return {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                "skipped": f"host has {avail / 1e9:.0f} GB available, needs {need * 1.5 / 1e9:.0f} GB"}
-    dims = (args.cutoff,) * args.modes
+        return ({"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                 "skipped": f"host has {avail / 1e9:.0f} GB available, needs {need * 1.5 / 1e9:.0f} GB"},
+                None)
     h = torch.empty(N, dtype=torch.complex128, pin_memory=True)
     h.copy_(dev_state.reshape(-1))
     torch.cuda.synchronize()
+    return None, h
+
+
+def run_e2e(args, torch, ffi, layer, h, N, nops):
+    """Same step, host buffers: H2D(state + operators) + layer + D2H(state) per step."""
+    dims = (args.cutoff,) * args.modes
+    need = N * 16
     h_np = h.numpy()
     ops_list = [(0, t, o) for t, o, _ in layer]
     op_bytes = sum(o.nbytes for _, o, _ in layer)
     steps = max(1, min(args.steps, args.e2e_steps))
-    ffi.circuit_host(h_np, False, dims, ops_list, device=torch.cuda.current_device(), out=h_np)  # warm-up
+    dev = torch.cuda.current_device()
+    ffi.circuit_host(h_np, False, dims, ops_list, device=dev, out=h_np)  # warm-up
     t0 = time.perf_counter()
     for _ in range(steps):
-        ffi.circuit_host(h_np, False, dims, ops_list, device=torch.cuda.current_device(), out=h_np)
+        ffi.circuit_host(h_np, False, dims, ops_list, device=dev, out=h_np)
     dt = (time.perf_counter() - t0) / steps
     return {"value": nops * N / dt, "unit": UNIT, "h2d_bytes_per_step": need + op_bytes,
             "d2h_bytes_per_step": need, "ms_per_step": dt * 1e3, "steps": steps,
             "api": "pw_circuit_host (C ABI, pinned host buffers in and out)"}
+
+
+def run_matrix_extras(torch, ffi, peak):
+    """configs[3]: 5-mode cutoff-8 density matrix (17.18 GB c128): Kraus loss channel and
+    operator applications, device-resident, CUDA-event timed (informational)."""
+    from oracle import operators as ops
+
+    d, m = 8, 5
+    dims = (d,) * m
+    D = d**m
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    rho = torch.view_as_complex(torch.randn(D * D, 2, generator=gen, device="cuda", dtype=torch.float64))
+    out = torch.empty_like(rho)
+    nbytes = 2 * D * D * 16
+
+    def dev(x):
+        return torch.as_tensor(np.ascontiguousarray(x)).cuda()
+
+    loss = dev(ops.loss_channel(d, 0.1))
+    u = dev(ops.random_unitary(d, 1))
+    ph = dev(ops.phase_operator(d, 0.3))
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    res = {"workload": "configs[3]: 5-mode cutoff-8 density matrix (2^30 entries, 17.18 GB complex128)",
+           "algorithmic_bytes_per_launch": nbytes}
+    for name, fn in [
+        ("kraus_loss_K8_mode2", lambda: ffi.kraus_mat(rho, loss, dims, (2,), out=out)),
+        ("apply_phase_mode1", lambda: ffi.apply_mat(rho, ph, dims, (1,), out=out)),
+        ("apply_dense_8x8_mode2", lambda: ffi.apply_mat(rho, u, dims, (2,), out=out)),
+    ]:
+        ms = timed(fn)
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        res[name] = {"ms": ms, "entries_per_s": D * D / (ms * 1e-3), "gbs": gbs, "frac_of_hbm_peak": gbs / peak}
+    ms = timed(lambda: ffi.probs(rho.reshape(D, D), dims, (1,), True), reps=5)
+    res["probs_mat_mode1"] = {"ms": ms}
+    ms = timed(lambda: ffi.trace_out_mat(rho.reshape(D, D), dims, (1,)), reps=5)
+    res["trace_out_keep_mode1"] = {"ms": ms}
+    del rho, out
+    torch.cuda.empty_cache()
+    return res
 
 
 def main():
@@ -386,6 +465,7 @@ def main():
     ap.add_argument("--cutoff", type=int, default=6)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -120,6 +120,42 @@ k_probs_finalize(const double* __restrict__ partial, const int nblocks, const ui
   }
 }
 
+// t <= 8: private register accumulators, one fiber per thread per iteration
+template <typename V, int T, bool DIAG>
+__global__ void __launch_bounds__(256)
+k_probs_small(const V* __restrict__ x, const FiberMap fm, const TargetMap tm, const int64_t mult,
+              double* __restrict__ partial) {
+  __shared__ double s_scratch[8];
+  __shared__ int64_t s_off[T];
+  if (threadIdx.x < T) s_off[threadIdx.x] = tm.offset(threadIdx.x) * mult;
+  __syncthreads();
+  double acc[T];
+#pragma unroll
+  for (int j = 0; j < T; ++j) acc[j] = 0.0;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < fm.nfib; f += stride) {
+    const int64_t base = fm.base(f) * mult;
+    V v[T];
+#pragma unroll
+    for (int j = 0; j < T; ++j) v[j] = x[base + s_off[j]];
+#pragma unroll
+    for (int j = 0; j < T; ++j)
+      acc[j] += DIAG ? (double)v[j].x : (double)v[j].x * v[j].x + (double)v[j].y * v[j].y;
+  }
+#pragma unroll
+  for (int j = 0; j < T; ++j) {
+    const double r = block_sum(acc[j], s_scratch);
+    if (threadIdx.x == 0) partial[(size_t)blockIdx.x * T + j] = r;
+  }
+}
+
+template <typename V, int T>
+static void launch_probs_small(const V* x, const Plan& p, int64_t mult, bool diag, int nblocks,
+                               double* partial, cudaStream_t s) {
+  if (diag) k_probs_small<V, T, true><<<nblocks, 256, 0, s>>>(x, p.fm, p.tm, mult, partial);
+  else      k_probs_small<V, T, false><<<nblocks, 256, 0, s>>>(x, p.fm, p.tm, mult, partial);
+}
+
 template <typename V>
 static int probs_impl(const V* x, void* probs, const Plan& p, int64_t mult, bool diag,
                       cudaStream_t s) {
@@ -128,7 +164,22 @@ static int probs_impl(const V* x, void* probs, const Plan& p, int64_t mult, bool
   const size_t smem = ((size_t)t * kRedBlock + 4) * sizeof(double) + (size_t)t * sizeof(int64_t);
   Scratch partial;
   int nblocks;
-  if (smem <= kRedSmemBudget) {
+  if (t <= 8) {
+    nblocks = grid_for(p.fm.nfib, 256, 6);
+    PW_TRY(partial.alloc(sizeof(double) * (size_t)nblocks * t, s));
+    double* pp = (double*)partial.p;
+    switch (t) {
+      case 1: launch_probs_small<V, 1>(x, p, mult, diag, nblocks, pp, s); break;
+      case 2: launch_probs_small<V, 2>(x, p, mult, diag, nblocks, pp, s); break;
+      case 3: launch_probs_small<V, 3>(x, p, mult, diag, nblocks, pp, s); break;
+      case 4: launch_probs_small<V, 4>(x, p, mult, diag, nblocks, pp, s); break;
+      case 5: launch_probs_small<V, 5>(x, p, mult, diag, nblocks, pp, s); break;
+      case 6: launch_probs_small<V, 6>(x, p, mult, diag, nblocks, pp, s); break;
+      case 7: launch_probs_small<V, 7>(x, p, mult, diag, nblocks, pp, s); break;
+      default: launch_probs_small<V, 8>(x, p, mult, diag, nblocks, pp, s); break;
+    }
+    PW_LAUNCHED();
+  } else if (smem <= kRedSmemBudget) {
     nblocks = grid_for(p.fm.nfib, kRedBlock, 4);
     if (nblocks > kRedMaxBlocks) nblocks = kRedMaxBlocks;
     PW_TRY(partial.alloc(sizeof(double) * (size_t)nblocks * t, s));
@@ -236,12 +287,74 @@ k_reduced_wide(const V* __restrict__ x, const FiberMap fm, const TargetMap tm, V
   if (threadIdx.x == 0) { V v; v.x = re; v.y = im; out[blockIdx.x] = v; }
 }
 
+// t <= 8: Hermitian accumulators in registers
+template <typename V, int T>
+__global__ void __launch_bounds__(256)
+k_reduced_small(const V* __restrict__ x, const FiberMap fm, const TargetMap tm,
+                double2* __restrict__ partial) {
+  constexpr int NP = T * (T + 1) / 2;
+  __shared__ double s_scratch[8];
+  __shared__ int64_t s_off[T];
+  if (threadIdx.x < T) s_off[threadIdx.x] = tm.offset(threadIdx.x);
+  __syncthreads();
+  double re[NP], im[NP];
+#pragma unroll
+  for (int q = 0; q < NP; ++q) { re[q] = 0.0; im[q] = 0.0; }
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < fm.nfib; f += stride) {
+    const int64_t base = fm.base(f);
+    double vx[T], vy[T];
+#pragma unroll
+    for (int j = 0; j < T; ++j) { const V v = x[base + s_off[j]]; vx[j] = v.x; vy[j] = v.y; }
+    int q = 0;
+#pragma unroll
+    for (int a = 0; a < T; ++a)
+#pragma unroll
+      for (int b = a; b < T; ++b, ++q) {
+        re[q] = fma(vx[a], vx[b], fma(vy[a], vy[b], re[q]));   // xa * conj(xb)
+        if (b != a) im[q] = fma(vy[a], vx[b], fma(-vx[a], vy[b], im[q]));
+      }
+  }
+#pragma unroll
+  for (int q = 0; q < NP; ++q) {
+    const double r = block_sum(re[q], s_scratch);
+    const double i = block_sum(im[q], s_scratch);
+    if (threadIdx.x == 0) partial[(size_t)blockIdx.x * NP + q] = make_double2(r, i);
+  }
+}
+
+template <typename V>
+static bool launch_reduced_small(const V* x, const Plan& p, int nblocks, double2* partial,
+                                 cudaStream_t s) {
+  switch (p.tm.t) {
+    case 1: k_reduced_small<V, 1><<<nblocks, 256, 0, s>>>(x, p.fm, p.tm, partial); return true;
+    case 2: k_reduced_small<V, 2><<<nblocks, 256, 0, s>>>(x, p.fm, p.tm, partial); return true;
+    case 3: k_reduced_small<V, 3><<<nblocks, 256, 0, s>>>(x, p.fm, p.tm, partial); return true;
+    case 4: k_reduced_small<V, 4><<<nblocks, 256, 0, s>>>(x, p.fm, p.tm, partial); return true;
+    case 5: k_reduced_small<V, 5><<<nblocks, 256, 0, s>>>(x, p.fm, p.tm, partial); return true;
+    case 6: k_reduced_small<V, 6><<<nblocks, 256, 0, s>>>(x, p.fm, p.tm, partial); return true;
+    case 7: k_reduced_small<V, 7><<<nblocks, 256, 0, s>>>(x, p.fm, p.tm, partial); return true;
+    case 8: k_reduced_small<V, 8><<<nblocks, 256, 0, s>>>(x, p.fm, p.tm, partial); return true;
+    default: return false;
+  }
+}
+
 template <typename V>
 static int reduced_impl(const V* x, V* out, const Plan& p, cudaStream_t s) {
   const uint32_t t = p.tm.t;
   const size_t npair = (size_t)t * (t + 1) / 2;
   const size_t smem = npair * kRedBlock * sizeof(double2) + 4 * sizeof(double) +
                       t * sizeof(int64_t) + (size_t)t * kRedBlock * sizeof(double2);
+  if (t <= 8) {
+    const int nblocks = grid_for(p.fm.nfib, 256, 2);
+    Scratch partial;
+    PW_TRY(partial.alloc(sizeof(double2) * (size_t)nblocks * npair, s));
+    launch_reduced_small<V>(x, p, nblocks, (double2*)partial.p, s);
+    PW_LAUNCHED();
+    k_reduced_finalize<V><<<(int)((npair + 127) / 128), 128, 0, s>>>((const double2*)partial.p, nblocks, t, out);
+    PW_LAUNCHED();
+    return PW_OK;
+  }
   if (smem <= kRedSmemBudget) {
     int nblocks = grid_for(p.fm.nfib, kRedBlock, 1);
     Scratch partial;
