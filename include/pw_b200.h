@@ -131,7 +131,8 @@ int pw_draw(const void* probs, int64_t t, uint32_t key0, uint32_t key1, int dtyp
 
 /* post (r) = psi[outcome, :] / sqrt(probs[outcome] + 1e-18); rest in tensor order.
  * `outcome` and `probs` are device pointers (outputs of pw_draw / pw_probs_vec).
- * Replaces core/kernels.py:205 (and :244). */
+ * probs == NULL: plain gather without rescaling (jnp.take of the legacy sequential path,
+ * state/utils/measurements.py:135).  Replaces core/kernels.py:205 (and :244). */
 int pw_collapse_vec(const void* psi, void* post, const int64_t* outcome, const void* probs,
                     const int64_t* dims, int n, const int32_t* targets, int nt, int dtype,
                     void* stream);

@@ -140,13 +140,13 @@ def apply_kraus_matrix(
 # --------------------------------------------------------------------------------
 
 
-def _measure(state_dims, target_indices, product_state, key, is_matrix: bool):
+def _measure(state_dims, target_indices, product_state, key, is_matrix: bool, rescale: bool = True):
     target_indices = tuple(target_indices)
     state_dims = tuple(state_dims)
     host, ps, _ = _prep(product_state)
     probs = ffi.probs(ps, state_dims, target_indices, is_matrix)
     outcome = ffi.draw(probs, key, ps.dtype)
-    post = ffi.collapse(ps, outcome, probs, state_dims, target_indices, is_matrix)
+    post = ffi.collapse(ps, outcome, probs if rescale else None, state_dims, target_indices, is_matrix)
     if host:
         return int(outcome.item()), post.cpu().numpy(), probs.cpu().numpy()
     return outcome, post, probs

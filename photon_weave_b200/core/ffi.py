@@ -117,7 +117,8 @@ def collapse(state: torch.Tensor, outcome: torch.Tensor, probs_t: torch.Tensor, 
     d, n, tg, nt = _common(dims, targets)
     fn = lib.pw_collapse_mat if is_matrix else lib.pw_collapse_vec
     _lib.check(
-        fn(state.data_ptr(), post.data_ptr(), outcome.data_ptr(), probs_t.data_ptr(), d, n, tg,
+        fn(state.data_ptr(), post.data_ptr(), outcome.data_ptr(),
+           probs_t.data_ptr() if probs_t is not None else None, d, n, tg,
            nt, A.code(state.dtype), A.stream_ptr()),
         "pw_collapse_mat" if is_matrix else "pw_collapse_vec",
     )

@@ -416,8 +416,9 @@ __global__ void k_collapse_vec(const V* __restrict__ psi, V* __restrict__ post,
   using R = typename RealOf<V>::type;
   const uint32_t o = (uint32_t)*outcome;
   const int64_t off = tm.offset(o);
-  // the reference divides (core/kernels.py:205); dividing keeps the last bit equal
-  const R den = sqrt(probs[o] + (R)1e-18);
+  // the reference divides (core/kernels.py:205); dividing keeps the last bit equal.
+  // probs == nullptr: plain gather (jnp.take of the legacy path, measurements.py:135)
+  const R den = probs ? sqrt(probs[o] + (R)1e-18) : (R)1;
   for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < fm.nfib;
        f += (uint64_t)gridDim.x * blockDim.x) {
     V v = psi[fm.base(f) + off];
@@ -435,7 +436,7 @@ __global__ void k_collapse_mat(const V* __restrict__ rho, V* __restrict__ post,
   using R = typename RealOf<V>::type;
   const uint32_t o = (uint32_t)*outcome;
   const int64_t off = tm.offset(o);
-  const R den = probs[o] + (R)1e-18;
+  const R den = probs ? probs[o] + (R)1e-18 : (R)1;
   const uint64_t r = fm.nfib, total = r * r;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (uint64_t)gridDim.x * blockDim.x) {
@@ -673,7 +674,7 @@ static int collapse_vec_t(const void* psi, void* post, const int64_t* outcome, c
 extern "C" int pw_collapse_vec(const void* psi, void* post, const int64_t* outcome,
                                const void* probs, const int64_t* dims, int n,
                                const int32_t* targets, int nt, int dtype, void* stream) {
-  if (!psi || !post || !outcome || !probs) return PW_ERR_INVALID;
+  if (!psi || !post || !outcome) return PW_ERR_INVALID;
   Plan p;
   PW_TRY(build_plan(dims, n, targets, nt, &p));
   return PW_DISPATCH(dtype, collapse_vec_t, psi, post, outcome, probs, p, (cudaStream_t)stream);
@@ -692,7 +693,7 @@ static int collapse_mat_t(const void* rho, void* post, const int64_t* outcome, c
 extern "C" int pw_collapse_mat(const void* rho, void* post, const int64_t* outcome,
                                const void* probs, const int64_t* dims, int n,
                                const int32_t* targets, int nt, int dtype, void* stream) {
-  if (!rho || !post || !outcome || !probs) return PW_ERR_INVALID;
+  if (!rho || !post || !outcome) return PW_ERR_INVALID;
   Plan p;
   PW_TRY(build_plan(dims, n, targets, nt, &p));
   return PW_DISPATCH(dtype, collapse_mat_t, rho, post, outcome, probs, p, (cudaStream_t)stream);
