@@ -111,10 +111,10 @@ def test_measurement_bridges_key_chains_match_oracle():
     for seed in range(6):
         key = orng.PRNGKey(seed)
         # joint path: borrow_key, one draw over prod(target dims), mixed-radix decode
-        outcomes, post, nxt = M.measure_vector_jit(states, [states[2], states[0]], dev(psi), key)
+        outcomes, post, nxt = M.measure_vector_jit(states, [states[0], states[2]], dev(psi), key)
         use_key, next_key = orng.borrow_key(key)
-        o_ref, post_ref, _ = oad.measure_vector(dims, (2, 0), psi, use_key)
-        assert outcomes[states[2]] == o_ref // 3 and outcomes[states[0]] == o_ref % 3
+        o_ref, post_ref, _ = oad.measure_vector(dims, (0, 2), psi, use_key)
+        assert outcomes[states[0]] == o_ref // 2 and outcomes[states[2]] == o_ref % 2
         assert np.array_equal(np.asarray(nxt), next_key)
         assert np.allclose(host(post), post_ref, atol=1e-12)
         outcomes, post, _ = M.measure_matrix_jit(states, [states[1]], dev(rho), key)
