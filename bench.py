@@ -466,6 +466,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--nccl-swap", action="store_true", help="N>1: NCCL all_to_all instead of peer reads")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

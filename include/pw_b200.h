@@ -175,6 +175,28 @@ int pw_scale(void* x, int64_t count, const double* scale_dev, int dtype, void* s
 int pw_permute(const void* in, void* out, const int64_t* dims, int n, const int32_t* perm,
                int dtype, void* stream);
 
+/* ---- multi-GPU: peer memory over NVLink (one process per GPU) ---------------------- */
+
+/* cudaMalloc + CUDA IPC export of a shard buffer; peers map it with pw_peer_open. */
+int pw_peer_alloc(size_t bytes, void** ptr, unsigned char handle[64]);
+int pw_peer_open(const unsigned char handle[64], void** ptr);
+int pw_peer_close(void* ptr);
+int pw_peer_free(void* ptr);
+
+/* Axis swap as a direct peer read: out[p * chunk + x] = srcs[p][x] for p < W.
+ * `srcs` is a HOST array of W device pointers (local or IPC-mapped peer memory), each
+ * already offset to the chunk this rank needs.  No collective library call. */
+int pw_gather_chunks(const void* const* srcs, int W, int64_t chunk_elems, void* out, int dtype,
+                     void* stream);
+
+/* The same swap FUSED with the operator application that follows it: the input of
+ * pw_apply_vec is the virtual concatenation of the W peer chunks (dims describe that
+ * concatenated tensor, prod(dims) = W * chunk_elems), loads go over NVLink, the result
+ * is written once to local memory.  Covers t <= 8 (PW_ERR_UNSUPPORTED otherwise). */
+int pw_apply_vec_gather(const void* const* srcs, int W, int64_t chunk_elems, void* out,
+                        const void* op, const int64_t* dims, int n, const int32_t* targets,
+                        int nt, int dtype, void* stream);
+
 /* ---- host-side PRNG key management (pure integer, no device) --------------- */
 
 /* out[i] = jax.random.split(key, num)[i] (partitionable threefry2x32).

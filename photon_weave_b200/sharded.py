@@ -42,8 +42,109 @@ class VAxis:
     weight: int   # multiplier of this coordinate inside subsystem g's index
 
 
+class _RawCuda:
+    """Zero-copy torch view of a raw device pointer (via __cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, numel: int, typestr: str):
+        self.__cuda_array_interface__ = {
+            "shape": (numel,), "typestr": typestr, "data": (ptr, False), "version": 3, "strides": None,
+        }
+
+
+class PeerBuffers:
+    """
+    Ping-pong shard buffers allocated by libpwb200 (cudaMalloc) and exported with CUDA IPC,
+    so every rank can read every other rank's shard directly over NVLink.
+    """
+
+    def __init__(self, numel: int, dtype: torch.dtype, nbuf: int, rank: int, world: int, dist: Any,
+                 device: int):
+        import ctypes as C
+
+        from . import _lib
+
+        lib = _lib.load()
+        self.rank, self.world, self.numel, self.dtype = rank, world, numel, dtype
+        self.esize = 16 if dtype == torch.complex128 else 8
+        self._lib = lib
+        self.local_ptrs: List[int] = []
+        handles = []
+        for _ in range(nbuf):
+            ptr = C.c_void_p()
+            h = (C.c_ubyte * 64)()
+            _lib.check(lib.pw_peer_alloc(numel * self.esize, C.byref(ptr), h), "pw_peer_alloc")
+            self.local_ptrs.append(int(ptr.value))
+            handles.append(bytes(h))
+        gathered: List[Any] = [None] * world
+        dist.all_gather_object(gathered, handles)
+        self.ptrs: List[List[int]] = []  # [buffer][rank]
+        self._opened: List[int] = []
+        for b in range(nbuf):
+            row = []
+            for r in range(world):
+                if r == rank:
+                    row.append(self.local_ptrs[b])
+                else:
+                    ptr = C.c_void_p()
+                    h = (C.c_ubyte * 64).from_buffer_copy(gathered[r][b])
+                    _lib.check(lib.pw_peer_open(h, C.byref(ptr)), "pw_peer_open")
+                    row.append(int(ptr.value))
+                    self._opened.append(int(ptr.value))
+            self.ptrs.append(row)
+        typestr = "<c16" if dtype == torch.complex128 else "<c8"
+        self.tensors = [
+            torch.as_tensor(_RawCuda(p, numel, typestr), device=torch.device("cuda", device))
+            for p in self.local_ptrs
+        ]
+
+    def index_of(self, t: torch.Tensor) -> int:
+        return self.local_ptrs.index(t.data_ptr())
+
+    def chunk_ptrs(self, buf: int, chunk_elems: int) -> List[int]:
+        """Pointer to chunk #rank inside every rank's buffer `buf`."""
+        off = self.rank * chunk_elems * self.esize
+        return [p + off for p in self.ptrs[buf]]
+
+    def close(self) -> None:
+        for p in self._opened:
+            self._lib.pw_peer_close(p)
+        self._opened = []
+        for p in self.local_ptrs:
+            self._lib.pw_peer_free(p)
+        self.local_ptrs = []
+
+
 class CudaBackend:
     """Local arithmetic through libpwb200 (the product path)."""
+
+    def gather_chunks(self, srcs: List[int], chunk_elems: int, out: torch.Tensor) -> None:
+        import ctypes as C
+
+        from . import _lib
+        from .core import _arrays as A
+
+        lib = _lib.load()
+        arr = (C.c_void_p * len(srcs))(*srcs)
+        _lib.check(lib.pw_gather_chunks(arr, len(srcs), chunk_elems, out.data_ptr(), A.code(out.dtype),
+                                        A.stream_ptr()), "pw_gather_chunks")
+
+    def apply_vec_gather(self, srcs: List[int], chunk_elems: int, out: torch.Tensor, op: torch.Tensor,
+                         dims, targets) -> bool:
+        """Fused swap + apply; False when the shape is outside the fused kernel (t > 8)."""
+        import ctypes as C
+
+        from . import _lib
+        from .core import _arrays as A
+
+        lib = _lib.load()
+        arr = (C.c_void_p * len(srcs))(*srcs)
+        rc = lib.pw_apply_vec_gather(arr, len(srcs), chunk_elems, out.data_ptr(), op.data_ptr(),
+                                     _lib.i64_array(dims), len(dims), _lib.i32_array(targets),
+                                     len(targets), A.code(out.dtype), A.stream_ptr())
+        if rc == 2:  # PW_ERR_UNSUPPORTED
+            return False
+        _lib.check(rc, "pw_apply_vec_gather")
+        return True
 
     def apply_vec(self, local: torch.Tensor, op: torch.Tensor, dims, targets, out=None):
         from .core import ffi
@@ -74,7 +175,7 @@ class ShardedStateVector:
 
     def __init__(self, global_dims: Sequence[int], local: torch.Tensor, vaxes: List[VAxis],
                  sparts: List[VAxis], rank: int, world: int, dist: Any, backend: Any,
-                 spare: Optional[torch.Tensor] = None):
+                 spare: Optional[torch.Tensor] = None, peers: Optional[PeerBuffers] = None):
         self.global_dims = tuple(int(d) for d in global_dims)
         self.local = local.reshape(-1)
         self.vaxes = list(vaxes)
@@ -83,8 +184,11 @@ class ShardedStateVector:
         self.dist = dist
         self.backend = backend
         self.spare = spare  # second buffer for out-of-place apply / all-to-all
+        self.peers = peers  # IPC-mapped shard buffers: swap = direct NVLink reads, no NCCL
         self.swaps = 0
         self.packs = 0
+        self.fused_swaps = 0
+        self._flag = None
         assert math.prod(s.extent for s in self.sparts) == world
         assert math.prod(v.extent for v in self.vaxes) == self.local.numel()
 
@@ -161,9 +265,21 @@ class ShardedStateVector:
 
     # ---- operations -------------------------------------------------------------------
 
+    def _barrier(self) -> None:
+        """Stream-ordered cross-rank barrier (a one-element all-reduce; no host sync)."""
+        if self._flag is None:
+            self._flag = torch.zeros(1, dtype=torch.float32, device=self.local.device)
+        self.dist.all_reduce(self._flag)
+
     def apply_operation(self, operator: torch.Tensor, axes: Sequence[int],
                         prefer_shard: Optional[Sequence[int]] = None) -> None:
         """psi <- (operator on global subsystems ``axes``) psi; swaps axes in if needed."""
+        if self.peers is not None and any(s.g in axes for s in self.sparts):
+            t = math.prod(self.global_dims[a] for a in axes)
+            if t <= 8:
+                # fused: the operator is applied while the swapped data streams in over NVLink
+                self.relayout(self._choose_parts(set(axes), prefer_shard), fused=(operator, axes))
+                return
         self.ensure_local(axes, prefer_shard)
         targets = self._targets_for(axes)
         out = self._buffers()
@@ -213,8 +329,9 @@ class ShardedStateVector:
             chosen.append(i)
         return sorted(chosen)
 
-    def relayout(self, positions: Sequence[int]) -> None:
-        """All-to-all axis swap: the virtual axes at ``positions`` become the rank digits."""
+    def relayout(self, positions: Sequence[int], fused=None) -> None:
+        """All-to-all axis swap: the virtual axes at ``positions`` become the rank digits.
+        ``fused=(operator, axes)``: apply that operator while gathering (peer mode only)."""
         positions = list(positions)
         k = len(positions)
         assert math.prod(self.vaxes[p].extent for p in positions) == self.world
@@ -227,13 +344,36 @@ class ShardedStateVector:
             self.vaxes = [self.vaxes[i] for i in perm]
             self.packs += 1
         recv = self._buffers()
+        new_sparts = self.vaxes[:k]
+        new_vaxes = [VAxis(s.g, s.extent, s.weight) for s in self.sparts] + self.vaxes[k:]
+        if self.peers is not None:
+            chunk = self.local.numel() // self.world
+            self._barrier()  # every rank has finished writing the buffer we are about to read
+            srcs = self.peers.chunk_ptrs(self.peers.index_of(self.local), chunk)
+            done = False
+            if fused is not None:
+                op, axes = fused
+                self.vaxes, self.sparts = new_vaxes, new_sparts
+                done = self.backend.apply_vec_gather(srcs, chunk, recv, op, self.local_dims,
+                                                     self._targets_for(axes))
+                if done:
+                    self.fused_swaps += 1
+            if not done:
+                self.backend.gather_chunks(srcs, chunk, recv)
+            self._barrier()  # peers are done reading before anyone overwrites the old buffer
+            self.local, self.spare = recv, self.local
+            self.vaxes, self.sparts = new_vaxes, new_sparts
+            self.swaps += 1
+            if fused is not None and not done:
+                self.apply_operation(fused[0], fused[1])
+            return
         # complex buffers travel as (n, 2) reals: equal row splits, one piece per rank
         self.dist.all_to_all_single(torch.view_as_real(recv), torch.view_as_real(self.local))
         self.local, self.spare = recv, self.local
-        new_sparts = self.vaxes[:k]
-        self.vaxes = [VAxis(s.g, s.extent, s.weight) for s in self.sparts] + self.vaxes[k:]
-        self.sparts = new_sparts
+        self.vaxes, self.sparts = new_vaxes, new_sparts
         self.swaps += 1
+        if fused is not None:
+            self.apply_operation(fused[0], fused[1])
 
     def norm2(self) -> torch.Tensor:
         """sum |psi|^2 over all ranks (device tensor)."""
@@ -290,9 +430,25 @@ def bench_sharded(args, dist, rank, world, local_rank, make_layer, workload_conf
     vaxes, sparts = ShardedStateVector.initial_layout(dims, world)
     n_local = N // world
     gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
-    local = torch.view_as_complex(
-        torch.randn(n_local, 2, generator=gen, device="cuda", dtype=torch.float64))
-    st = ShardedStateVector(dims, local, vaxes, sparts, rank, world, dist, CudaBackend())
+    peers = None
+    swap_impl = "torch.distributed.all_to_all_single (NCCL)"
+    if not getattr(args, "nccl_swap", False):
+        try:
+            peers = PeerBuffers(n_local, torch.complex128, 2, rank, world, dist, local_rank)
+            swap_impl = ("libpwb200 peer reads over NVLink (CUDA IPC): pw_apply_vec_gather fused "
+                         "swap+apply, pw_gather_chunks otherwise")
+        except Exception as exc:  # IPC unavailable: fall back to the NCCL collective
+            peers = None
+            swap_impl += f" [peer memory unavailable: {exc}]"
+    if peers is not None:
+        local, spare = peers.tensors[0], peers.tensors[1]
+        torch.view_as_real(local).normal_(generator=gen)
+    else:
+        local = torch.view_as_complex(
+            torch.randn(n_local, 2, generator=gen, device="cuda", dtype=torch.float64))
+        spare = None
+    st = ShardedStateVector(dims, local, vaxes, sparts, rank, world, dist, CudaBackend(),
+                            spare=spare, peers=peers)
     nrm = st.norm2()
     ffi.scale_(st.local, (1.0 / torch.sqrt(nrm)).contiguous())
 
@@ -319,13 +475,14 @@ def bench_sharded(args, dist, rank, world, local_rank, make_layer, workload_conf
             st.apply_operation(d_ops[i], layer[i][0])
         if events is not None:
             events[slot].record(); slot += 1
-        if second:
+        if second and st.peers is None:
             st.ensure_local(layer[second[0]][0] + tuple(a for i in second for a in layer[i][0]),
                             prefer_shard=other)
         for i in second:
             if events is not None:
                 events[slot].record(); slot += 1
-            st.apply_operation(d_ops[i], layer[i][0])
+            # peer mode: the first of these ops carries the swap (fused gather + apply)
+            st.apply_operation(d_ops[i], layer[i][0], prefer_shard=other)
         if events is not None:
             events[slot].record()
         return len(first)
@@ -340,7 +497,7 @@ def bench_sharded(args, dist, rank, world, local_rank, make_layer, workload_conf
     if rank == 0:
         sampler.start()
     n0 = lib.pw_launch_count()
-    swaps0, packs0 = st.swaps, st.packs
+    swaps0, packs0, fused0 = st.swaps, st.packs, st.fused_swaps
     torch.cuda.synchronize()
     dist.barrier()
     t0 = torch.cuda.Event(enable_timing=True)
@@ -361,6 +518,7 @@ def bench_sharded(args, dist, rank, world, local_rank, make_layer, workload_conf
     # swap time = the slot between the two phases
     swap_ms = 0.0
     op_ms = 0.0
+    fused_op_ms = 0.0
     for s in range(args.steps):
         nf = nfirst[s]
         for j in range(nops + 1):
@@ -369,6 +527,9 @@ def bench_sharded(args, dist, rank, world, local_rank, make_layer, workload_conf
                 swap_ms += dt
             else:
                 op_ms += dt
+            if j == nf + 1:
+                fused_op_ms += dt  # first op after the swap slot (carries the fused swap)
+    fused_op_ms /= args.steps
     swap_ms /= args.steps
     op_ms /= args.steps
     tm = torch.tensor([swap_ms, op_ms], device="cuda", dtype=torch.float64)
@@ -403,9 +564,15 @@ def bench_sharded(args, dist, rank, world, local_rank, make_layer, workload_conf
                           "gbs_per_rank_per_direction": swap_bytes * swaps / (swap_ms * 1e-3) / 1e9
                           if swap_ms > 0 else None,
                           "nvlink_reference_gbs": 770.0,
-                          "collective": "torch.distributed.all_to_all_single (NCCL)"},
+                          "fused_swaps_per_step": (st.fused_swaps - fused0) / args.steps,
+                          "fused_swap_plus_apply_ms": fused_op_ms if peers is not None else None,
+                          "implementation": swap_impl},
             "compute_ms_per_step": op_ms, "norm_after": norm_after,
         }
         print(json.dumps(line), flush=True)
     dist.barrier()
+    if peers is not None:
+        del st, local, spare
+        torch.cuda.synchronize()
+        peers.close()
     dist.destroy_process_group()

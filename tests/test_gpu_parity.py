@@ -349,3 +349,30 @@ def test_sharded_state_single_rank_cuda_backend(ad):
     st.apply_operation(dev(bs), (2, 0))
     ref = oad.apply_operation_vector(dims, (2, 0), psi, bs)
     assert rel_err(host(st.local).reshape(-1, 1), ref) < 1e-12
+
+
+def test_gather_kernels_single_process_emulation(ad):
+    """pw_gather_chunks / pw_apply_vec_gather with W chunks living on ONE GPU (the peer
+    pointers are ordinary device pointers here): fused gather+apply == apply(concat)."""
+    from photon_weave_b200.sharded import CudaBackend
+
+    be = CudaBackend()
+    W, dims = 4, (4, 3, 6, 5)          # virtual tensor: leading axis of extent W
+    N = math.prod(dims)
+    chunk = N // W
+    psi = ops.random_state(N, 77).reshape(-1)
+    pieces = [dev(psi[p * chunk:(p + 1) * chunk].copy()) for p in range(W)]
+    srcs = [t.data_ptr() for t in pieces]
+    out = torch.empty(N, dtype=torch.complex128, device="cuda")
+    be.gather_chunks(srcs, chunk, out)
+    assert np.array_equal(host(out), psi)
+    for targets in [(2,), (0,), (0, 1), (3, 0)]:
+        t = math.prod(dims[i] for i in targets)
+        if t > 8:
+            continue
+        op = ops.random_unitary(t, 5)
+        ok = be.apply_vec_gather(srcs, chunk, out, dev(op), dims, targets)
+        assert ok
+        ref = oad.apply_operation_vector(dims, targets, psi.reshape(-1, 1), op)
+        assert rel_err(host(out).reshape(-1, 1), ref) < 1e-12
+    assert be.apply_vec_gather(srcs, chunk, out, dev(ops.random_unitary(12, 1)), dims, (0, 1)) is False
