@@ -185,15 +185,16 @@ int pw_peer_free(void* ptr);
 
 /* Axis swap as a direct peer read: out[p * chunk + x] = srcs[p][x] for p < W.
  * `srcs` is a HOST array of W device pointers (local or IPC-mapped peer memory), each
- * already offset to the chunk this rank needs.  No collective library call. */
-int pw_gather_chunks(const void* const* srcs, int W, int64_t chunk_elems, void* out, int dtype,
-                     void* stream);
+ * already offset to the chunk this rank needs.  `rank` rotates the traversal so the W
+ * ranks pull from W different peers at any moment.  No collective library call. */
+int pw_gather_chunks(const void* const* srcs, int W, int64_t chunk_elems, int rank, void* out,
+                     int dtype, void* stream);
 
 /* The same swap FUSED with the operator application that follows it: the input of
  * pw_apply_vec is the virtual concatenation of the W peer chunks (dims describe that
  * concatenated tensor, prod(dims) = W * chunk_elems), loads go over NVLink, the result
  * is written once to local memory.  Covers t <= 8 (PW_ERR_UNSUPPORTED otherwise). */
-int pw_apply_vec_gather(const void* const* srcs, int W, int64_t chunk_elems, void* out,
+int pw_apply_vec_gather(const void* const* srcs, int W, int64_t chunk_elems, int rank, void* out,
                         const void* op, const int64_t* dims, int n, const int32_t* targets,
                         int nt, int dtype, void* stream);
 

@@ -74,10 +74,10 @@ SIGNATURES = {
     "pw_peer_open": (C.c_int, [C.POINTER(C.c_ubyte), C.POINTER(_vp)]),
     "pw_peer_close": (C.c_int, [_vp]),
     "pw_peer_free": (C.c_int, [_vp]),
-    "pw_gather_chunks": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int64, _vp, C.c_int, _vp]),
+    "pw_gather_chunks": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int64, C.c_int, _vp, C.c_int, _vp]),
     "pw_apply_vec_gather": (
         C.c_int,
-        [C.POINTER(_vp), C.c_int, C.c_int64, _vp, _vp, _i64p, C.c_int, _i32p, C.c_int, C.c_int, _vp],
+        [C.POINTER(_vp), C.c_int, C.c_int64, C.c_int, _vp, _vp, _i64p, C.c_int, _i32p, C.c_int, C.c_int, _vp],
     ),
     "pw_rng_split": (C.c_int, [C.POINTER(C.c_uint32), C.c_int, C.POINTER(C.c_uint32)]),
     "pw_circuit_host": (

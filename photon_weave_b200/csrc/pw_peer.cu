@@ -35,10 +35,13 @@ __device__ __forceinline__ const V* seg_addr(const SegIn& s, uint64_t e, bool sm
 // out[p * chunk + x] = peer_p[x]: coalesced 128-bit loads over NVLink, local stores
 template <typename V>
 __global__ void __launch_bounds__(256)
-k_gather_chunks(const SegIn s, const int W, V* __restrict__ out) {
+k_gather_chunks(const SegIn s, const int W, const uint64_t rot, V* __restrict__ out) {
   const uint64_t total = s.chunk * (uint64_t)W;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    // rotated start: at any moment the W ranks pull from W different peers
+    uint64_t e = i + rot;
+    if (e >= total) e -= total;
     const uint64_t p = e / s.chunk;
     out[e] = ((const V*)s.ptr[p])[e - p * s.chunk];
   }
@@ -49,14 +52,16 @@ k_gather_chunks(const SegIn s, const int W, V* __restrict__ out) {
 template <typename V, int T>
 __global__ void __launch_bounds__(256, (sizeof(V) == 16 ? (T <= 4 ? 4 : (T <= 6 ? 3 : 2)) : 3))
 k_apply_small_gather(const SegIn s, V* __restrict__ out, const V* __restrict__ op,
-                     const FiberMap fm, const TargetMap tm, const bool small) {
+                     const FiberMap fm, const TargetMap tm, const bool small, const uint64_t rot) {
   __shared__ V s_op[T * T];
   __shared__ int64_t s_off[T];
   for (int i = threadIdx.x; i < T * T; i += blockDim.x) s_op[i] = op[i];
   if (threadIdx.x < T) s_off[threadIdx.x] = tm.offset(threadIdx.x);
   __syncthreads();
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < fm.nfib; f += stride) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < fm.nfib; i += stride) {
+    uint64_t f = i + rot;  // rotated start: ranks hit different peers at any moment
+    if (f >= fm.nfib) f -= fm.nfib;
     const int64_t base = fm.base(f);
     int zero = 0;
     asm volatile("" : "+r"(zero));
@@ -75,22 +80,23 @@ k_apply_small_gather(const SegIn s, V* __restrict__ out, const V* __restrict__ o
 }
 
 template <typename V, int T>
-static void launch_gather_small(const SegIn& s, V* out, const V* op, const Plan& p, cudaStream_t st) {
+static void launch_gather_small(const SegIn& s, V* out, const V* op, const Plan& p, uint64_t rot, cudaStream_t st) {
   const bool small = p.N <= 0xffffffffull;
-  k_apply_small_gather<V, T><<<grid_for(p.fm.nfib, 256, 8), 256, 0, st>>>(s, out, op, p.fm, p.tm, small);
+  k_apply_small_gather<V, T><<<grid_for(p.fm.nfib, 256, 8), 256, 0, st>>>(s, out, op, p.fm, p.tm, small, rot);
 }
 
 template <typename V>
-static int apply_gather_t(const SegIn& s, V* out, const V* op, const Plan& p, cudaStream_t st) {
+static int apply_gather_t(const SegIn& s, V* out, const V* op, const Plan& p, int rank, int W, cudaStream_t st) {
+  const uint64_t rot = (p.fm.nfib / (uint64_t)W) * (uint64_t)(rank % W);
   switch (p.tm.t) {
-    case 1: launch_gather_small<V, 1>(s, out, op, p, st); break;
-    case 2: launch_gather_small<V, 2>(s, out, op, p, st); break;
-    case 3: launch_gather_small<V, 3>(s, out, op, p, st); break;
-    case 4: launch_gather_small<V, 4>(s, out, op, p, st); break;
-    case 5: launch_gather_small<V, 5>(s, out, op, p, st); break;
-    case 6: launch_gather_small<V, 6>(s, out, op, p, st); break;
-    case 7: launch_gather_small<V, 7>(s, out, op, p, st); break;
-    case 8: launch_gather_small<V, 8>(s, out, op, p, st); break;
+    case 1: launch_gather_small<V, 1>(s, out, op, p, rot, st); break;
+    case 2: launch_gather_small<V, 2>(s, out, op, p, rot, st); break;
+    case 3: launch_gather_small<V, 3>(s, out, op, p, rot, st); break;
+    case 4: launch_gather_small<V, 4>(s, out, op, p, rot, st); break;
+    case 5: launch_gather_small<V, 5>(s, out, op, p, rot, st); break;
+    case 6: launch_gather_small<V, 6>(s, out, op, p, rot, st); break;
+    case 7: launch_gather_small<V, 7>(s, out, op, p, rot, st); break;
+    case 8: launch_gather_small<V, 8>(s, out, op, p, rot, st); break;
     default: return PW_ERR_UNSUPPORTED;
   }
   PW_LAUNCHED();
@@ -140,22 +146,23 @@ static int make_seg(const void* const* srcs, int W, int64_t chunk, SegIn* s) {
   return PW_OK;
 }
 
-extern "C" int pw_gather_chunks(const void* const* srcs, int W, int64_t chunk_elems, void* out,
-                                int dtype, void* stream) {
+extern "C" int pw_gather_chunks(const void* const* srcs, int W, int64_t chunk_elems, int rank,
+                                void* out, int dtype, void* stream) {
   SegIn s;
   PW_TRY(make_seg(srcs, W, chunk_elems, &s));
   if (!out) return PW_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = grid_for((uint64_t)chunk_elems * W, 256, 8);
-  if (dtype == PW_C128) k_gather_chunks<double2><<<grid, 256, 0, st>>>(s, W, (double2*)out);
-  else if (dtype == PW_C64) k_gather_chunks<float2><<<grid, 256, 0, st>>>(s, W, (float2*)out);
+  const uint64_t rot = (uint64_t)chunk_elems * (uint64_t)(((rank % W) + W) % W);
+  if (dtype == PW_C128) k_gather_chunks<double2><<<grid, 256, 0, st>>>(s, W, rot, (double2*)out);
+  else if (dtype == PW_C64) k_gather_chunks<float2><<<grid, 256, 0, st>>>(s, W, rot, (float2*)out);
   else return PW_ERR_INVALID;
   PW_LAUNCHED();
   return PW_OK;
 }
 
-extern "C" int pw_apply_vec_gather(const void* const* srcs, int W, int64_t chunk_elems, void* out,
-                                   const void* op, const int64_t* dims, int n,
+extern "C" int pw_apply_vec_gather(const void* const* srcs, int W, int64_t chunk_elems, int rank,
+                                   void* out, const void* op, const int64_t* dims, int n,
                                    const int32_t* targets, int nt, int dtype, void* stream) {
   SegIn s;
   PW_TRY(make_seg(srcs, W, chunk_elems, &s));
@@ -163,7 +170,7 @@ extern "C" int pw_apply_vec_gather(const void* const* srcs, int W, int64_t chunk
   Plan p;
   PW_TRY(build_plan(dims, n, targets, nt, &p));
   if (p.N != (uint64_t)chunk_elems * (uint64_t)W) return PW_ERR_INVALID;
-  if (dtype == PW_C128) return apply_gather_t<double2>(s, (double2*)out, (const double2*)op, p, (cudaStream_t)stream);
-  if (dtype == PW_C64) return apply_gather_t<float2>(s, (float2*)out, (const float2*)op, p, (cudaStream_t)stream);
+  if (dtype == PW_C128) return apply_gather_t<double2>(s, (double2*)out, (const double2*)op, p, rank < 0 ? 0 : rank, W, (cudaStream_t)stream);
+  if (dtype == PW_C64) return apply_gather_t<float2>(s, (float2*)out, (const float2*)op, p, rank < 0 ? 0 : rank, W, (cudaStream_t)stream);
   return PW_ERR_INVALID;
 }

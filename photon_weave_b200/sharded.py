@@ -117,7 +117,7 @@ class PeerBuffers:
 class CudaBackend:
     """Local arithmetic through libpwb200 (the product path)."""
 
-    def gather_chunks(self, srcs: List[int], chunk_elems: int, out: torch.Tensor) -> None:
+    def gather_chunks(self, srcs: List[int], chunk_elems: int, out: torch.Tensor, rank: int = 0) -> None:
         import ctypes as C
 
         from . import _lib
@@ -125,11 +125,11 @@ class CudaBackend:
 
         lib = _lib.load()
         arr = (C.c_void_p * len(srcs))(*srcs)
-        _lib.check(lib.pw_gather_chunks(arr, len(srcs), chunk_elems, out.data_ptr(), A.code(out.dtype),
+        _lib.check(lib.pw_gather_chunks(arr, len(srcs), chunk_elems, rank, out.data_ptr(), A.code(out.dtype),
                                         A.stream_ptr()), "pw_gather_chunks")
 
     def apply_vec_gather(self, srcs: List[int], chunk_elems: int, out: torch.Tensor, op: torch.Tensor,
-                         dims, targets) -> bool:
+                         dims, targets, rank: int = 0) -> bool:
         """Fused swap + apply; False when the shape is outside the fused kernel (t > 8)."""
         import ctypes as C
 
@@ -138,7 +138,7 @@ class CudaBackend:
 
         lib = _lib.load()
         arr = (C.c_void_p * len(srcs))(*srcs)
-        rc = lib.pw_apply_vec_gather(arr, len(srcs), chunk_elems, out.data_ptr(), op.data_ptr(),
+        rc = lib.pw_apply_vec_gather(arr, len(srcs), chunk_elems, rank, out.data_ptr(), op.data_ptr(),
                                      _lib.i64_array(dims), len(dims), _lib.i32_array(targets),
                                      len(targets), A.code(out.dtype), A.stream_ptr())
         if rc == 2:  # PW_ERR_UNSUPPORTED
@@ -355,11 +355,11 @@ class ShardedStateVector:
                 op, axes = fused
                 self.vaxes, self.sparts = new_vaxes, new_sparts
                 done = self.backend.apply_vec_gather(srcs, chunk, recv, op, self.local_dims,
-                                                     self._targets_for(axes))
+                                                     self._targets_for(axes), rank=self.rank)
                 if done:
                     self.fused_swaps += 1
             if not done:
-                self.backend.gather_chunks(srcs, chunk, recv)
+                self.backend.gather_chunks(srcs, chunk, recv, rank=self.rank)
             self._barrier()  # peers are done reading before anyone overwrites the old buffer
             self.local, self.spare = recv, self.local
             self.vaxes, self.sparts = new_vaxes, new_sparts

@@ -364,14 +364,14 @@ def test_gather_kernels_single_process_emulation(ad):
     pieces = [dev(psi[p * chunk:(p + 1) * chunk].copy()) for p in range(W)]
     srcs = [t.data_ptr() for t in pieces]
     out = torch.empty(N, dtype=torch.complex128, device="cuda")
-    be.gather_chunks(srcs, chunk, out)
+    be.gather_chunks(srcs, chunk, out, rank=2)
     assert np.array_equal(host(out), psi)
     for targets in [(2,), (0,), (0, 1), (3, 0)]:
         t = math.prod(dims[i] for i in targets)
         if t > 8:
             continue
         op = ops.random_unitary(t, 5)
-        ok = be.apply_vec_gather(srcs, chunk, out, dev(op), dims, targets)
+        ok = be.apply_vec_gather(srcs, chunk, out, dev(op), dims, targets, rank=3)
         assert ok
         ref = oad.apply_operation_vector(dims, targets, psi.reshape(-1, 1), op)
         assert rel_err(host(out).reshape(-1, 1), ref) < 1e-12
