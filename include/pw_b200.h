@@ -95,6 +95,12 @@ int pw_apply_mat(const void* rho, void* out, const void* op, const int64_t* dims
 int pw_kraus_mat(const void* rho, void* out, const void* ops, int K, const int64_t* dims,
                  int n, const int32_t* targets, int nt, int dtype, void* stream);
 
+/* Two single-subsystem operators on DIFFERENT axes of equal dimension d (2..6) in one HBM
+ * pass: psi' = (A on axis_a)(B on axis_b) psi (the two commute).  Half the traffic of two
+ * pw_apply_vec calls.  PW_ERR_UNSUPPORTED outside that shape. */
+int pw_apply_vec_pair(const void* psi, void* out, const void* op_a, const void* op_b,
+                      const int64_t* dims, int n, int axis_a, int axis_b, int dtype, void* stream);
+
 /* ---- reductions ---------------------------------------------------------------- */
 
 /* out (t x t) = Tr_rest rho, kept subsystems ordered as listed in `keep`.
@@ -220,6 +226,14 @@ typedef struct {
  * selects vector / density-matrix layout.  Synchronises before returning. */
 int pw_circuit_host(const void* h_state, void* h_out, int is_matrix, const int64_t* dims,
                     int n, const pw_host_op* ops, int nops, int dtype, int device);
+
+/* Device-resident operation list: pw_host_op.op are DEVICE pointers here.  Ping-pongs
+ * between `state` and `scratch` (scratch may be NULL: in place); *result_in_scratch tells
+ * which buffer holds the result.  fuse != 0: adjacent single-subsystem vector operators on
+ * different axes (they commute) are applied as one pass (pw_apply_vec_pair).  Enqueue only. */
+int pw_circuit_device(void* state, void* scratch, int is_matrix, const int64_t* dims, int n,
+                      const pw_host_op* ops, int nops, int dtype, int fuse, void* stream,
+                      int* result_in_scratch);
 
 #ifdef __cplusplus
 }

@@ -185,6 +185,43 @@ def permute(x: torch.Tensor, dims, perm, out: Optional[torch.Tensor] = None):
     return out
 
 
+def apply_vec_pair(psi: torch.Tensor, op_a: torch.Tensor, op_b: torch.Tensor, dims, axis_a: int,
+                   axis_b: int, out: Optional[torch.Tensor] = None):
+    """(A on axis_a)(B on axis_b) psi in one pass; returns None when the shape is unsupported."""
+    lib = _lib.load()
+    out = torch.empty_like(psi) if out is None else out
+    rc = lib.pw_apply_vec_pair(psi.data_ptr(), out.data_ptr(), op_a.data_ptr(), op_b.data_ptr(),
+                               _lib.i64_array(dims), len(dims), int(axis_a), int(axis_b),
+                               A.code(psi.dtype), A.stream_ptr())
+    if rc == 2:
+        return None
+    _lib.check(rc, "pw_apply_vec_pair")
+    return out
+
+
+def circuit_device(state: torch.Tensor, scratch: Optional[torch.Tensor], is_matrix: bool, dims,
+                   ops_list, fuse: bool = True):
+    """Device-resident op list (pw_circuit_device): ops_list = [(kind, targets, device tensor)].
+    Returns (result, other) -- the two buffers, result first."""
+    lib = _lib.load()
+    arr = (_lib.pw_host_op * max(len(ops_list), 1))()
+    for i, (kind, targets, op) in enumerate(ops_list):
+        arr[i].kind = int(kind)
+        arr[i].nt = len(targets)
+        for k, tg in enumerate(targets):
+            arr[i].targets[k] = int(tg)
+        arr[i].K = int(op.shape[0]) if kind == 2 else 1
+        arr[i].op = op.data_ptr()
+    flag = C.c_int(0)
+    _lib.check(
+        lib.pw_circuit_device(state.data_ptr(), scratch.data_ptr() if scratch is not None else None,
+                              int(is_matrix), _lib.i64_array(dims), len(dims), arr, len(ops_list),
+                              A.code(state.dtype), int(fuse), A.stream_ptr(), C.byref(flag)),
+        "pw_circuit_device",
+    )
+    return (scratch, state) if flag.value else (state, scratch)
+
+
 def rng_split(key, num: int = 2) -> np.ndarray:
     lib = _lib.load()
     k0, k1 = A.key_words(key)

@@ -50,6 +50,8 @@ Options& options() {
     env("PW_CTAS_PER_SM", p->ctas_per_sm);
     env("PW_BLOCKS_MIN_ELEMS", p->blocks_min_elems);
     env("PW_NSTAGE", p->nstage);
+    env("PW_FUSE_PAIRS", p->fuse_pairs);
+    env("PW_CONTIG_KERNEL", p->contig_kernel);
     env("PW_SMALL_R", p->small_r);
     env("PW_MAT_SUPER_SINGLE", p->mat_super_single);
     return p;
@@ -67,6 +69,8 @@ extern "C" int pw_set_option(const char* name, int value) {
   else if (!std::strcmp(name, "ctas_per_sm")) o.ctas_per_sm.store(value);
   else if (!std::strcmp(name, "blocks_min_elems")) o.blocks_min_elems.store(value);
   else if (!std::strcmp(name, "nstage")) o.nstage.store(value);
+  else if (!std::strcmp(name, "fuse_pairs")) o.fuse_pairs.store(value);
+  else if (!std::strcmp(name, "contig_kernel")) o.contig_kernel.store(value);
   else if (!std::strcmp(name, "small_r")) o.small_r.store(value);
   else if (!std::strcmp(name, "mat_super_single")) o.mat_super_single.store(value);
   else return PW_ERR_INVALID;

@@ -63,6 +63,145 @@ k_apply_small(const V* in, V* out, const V* __restrict__ op, const FiberMap fm,
 }
 
 // ---------------------------------------------------------------------------------
+// Register path, CONTIGUOUS fibers (the targets are the innermost axes, so the tensor is
+// an array of t-element fibers).  Thread-per-fiber loads would touch 32 different lines
+// per instruction; instead a warp loads 32 fibers as T fully coalesced 512 B rows,
+// transposes them through a warp-private padded shared-memory buffer (no block barrier),
+// computes one fiber per lane in registers, and stores back the same way.
+// ---------------------------------------------------------------------------------
+template <int T>
+__device__ __forceinline__ int pad_idx(int e) { return e + (e >> 3); }
+
+template <typename V, int T, bool CONJ>
+__global__ void __launch_bounds__(256, (sizeof(V) == 16 && T >= 7) ? 2 : 3)
+k_apply_small_contig(const V* in, V* out, const V* __restrict__ op, const uint64_t nfib,
+                     const TargetMap tm, const int* __restrict__ skip) {
+  if (skip && *skip) return;
+  constexpr int kWarps = 8;
+  constexpr int kBuf = 32 * T + (32 * T) / 8 + 1;
+  __shared__ V s_op[T * T];
+  __shared__ int s_perm[T];      // operator index j -> position inside the contiguous fiber
+  __shared__ V s_buf[kWarps][kBuf];
+  for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
+    V o = op[i];
+    if (CONJ) o.y = -o.y;
+    s_op[i] = o;
+  }
+  if (threadIdx.x < T) s_perm[threadIdx.x] = (int)tm.offset(threadIdx.x);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  V* buf = s_buf[warp];
+  const uint64_t ngroups = (nfib + 31) / 32;
+  const uint64_t total = nfib * T;
+  const uint64_t gstride = (uint64_t)gridDim.x * kWarps;
+  for (uint64_t g = (uint64_t)blockIdx.x * kWarps + warp; g < ngroups; g += gstride) {
+    const uint64_t base = g * 32 * T;
+    V r[T];
+#pragma unroll
+    for (int i = 0; i < T; ++i) {
+      const uint64_t e = base + i * 32 + lane;
+      if (e < total) r[i] = in[e];
+    }
+#pragma unroll
+    for (int i = 0; i < T; ++i) buf[pad_idx<T>(i * 32 + lane)] = r[i];
+    __syncwarp();
+    int zero = 0;
+    asm volatile("" : "+r"(zero));
+    const V* sop = s_op + zero;
+    V x[T];
+#pragma unroll
+    for (int j = 0; j < T; ++j) x[j] = buf[pad_idx<T>(lane * T + s_perm[j])];
+    __syncwarp();
+#pragma unroll
+    for (int a = 0; a < T; ++a) {
+      V acc = czero<V>();
+#pragma unroll
+      for (int b = 0; b < T; ++b) cfma(acc, sop[a * T + b], x[b]);
+      buf[pad_idx<T>(lane * T + s_perm[a])] = acc;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < T; ++i) {
+      const uint64_t e = base + i * 32 + lane;
+      if (e < total) out[e] = buf[pad_idx<T>(i * 32 + lane)];
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Fused pair: two single-subsystem operators on DIFFERENT axes in ONE HBM pass.  A thread
+// holds the D x D sub-tensor spanned by the two axes in registers, applies U_a along the
+// first index and U_b along the second (2*D^3 complex FMAs), and writes it back: half the
+// memory traffic of two separate applications, identical arithmetic.
+// ---------------------------------------------------------------------------------
+template <typename V, int D>
+__global__ void __launch_bounds__(256, 1)
+k_apply_pair(const V* in, V* out, const V* __restrict__ opa, const V* __restrict__ opb,
+             const FiberMap fm, const TargetMap tm) {
+  __shared__ V s_a[D * D], s_b[D * D];
+  __shared__ int64_t s_off[D * D];
+  for (int i = threadIdx.x; i < D * D; i += blockDim.x) {
+    s_a[i] = opa[i];
+    s_b[i] = opb[i];
+    s_off[i] = tm.offset(i);
+  }
+  __syncthreads();
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < fm.nfib; f += stride) {
+    const int64_t base = fm.base(f);
+    int zero = 0;
+    asm volatile("" : "+r"(zero));
+    const V* sa = s_a + zero;
+    const V* sb = s_b + zero;
+    V x[D][D];
+    // first index, column by column: load column j, x[:, j] <- U_a column (keeps the live
+    // register set at one D x D tile plus one column)
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      V c[D];
+#pragma unroll
+      for (int b = 0; b < D; ++b) c[b] = in[base + s_off[b * D + j]];
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+        V acc = czero<V>();
+#pragma unroll
+        for (int b = 0; b < D; ++b) cfma(acc, sa[a * D + b], c[b]);
+        x[a][j] = acc;
+      }
+    }
+    // second index: x[i, :] <- U_b x[i, :], stored as each row completes
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+        V acc = czero<V>();
+#pragma unroll
+        for (int b = 0; b < D; ++b) cfma(acc, sb[a * D + b], x[i][b]);
+        out[base + s_off[i * D + a]] = acc;
+      }
+    }
+  }
+}
+
+template <typename V>
+static int launch_pair_t(const V* in, V* out, const V* opa, const V* opb, const Plan& p, int d,
+                         cudaStream_t s) {
+  const int grid = grid_for(p.fm.nfib, 256, 1);
+  switch (d) {
+    case 2: k_apply_pair<V, 2><<<grid, 256, 0, s>>>(in, out, opa, opb, p.fm, p.tm); break;
+    case 3: k_apply_pair<V, 3><<<grid, 256, 0, s>>>(in, out, opa, opb, p.fm, p.tm); break;
+    case 4: k_apply_pair<V, 4><<<grid, 256, 0, s>>>(in, out, opa, opb, p.fm, p.tm); break;
+    case 5: k_apply_pair<V, 5><<<grid, 256, 0, s>>>(in, out, opa, opb, p.fm, p.tm); break;
+    case 6: k_apply_pair<V, 6><<<grid, 256, 0, s>>>(in, out, opa, opb, p.fm, p.tm); break;
+    default: return PW_ERR_UNSUPPORTED;
+  }
+  g_paths[0].fetch_add(1, std::memory_order_relaxed);
+  PW_LAUNCHED();
+  return PW_OK;
+}
+
+// ---------------------------------------------------------------------------------
 // Generic path: any t.  One thread owns one fiber and re-reads it once per output
 // row (L1/L2 hits); operator rows stream from global/L2.  Requires in != out.
 // Correctness fallback for shapes the tiled kernels do not cover.
@@ -102,6 +241,15 @@ static int launch_small(const V* in, V* out, const V* op, const Plan& p, bool co
   const int block = 256;
   const int grid = grid_for(p.fm.nfib, block, 8);
   g_paths[0].fetch_add(1, std::memory_order_relaxed);
+  // array-of-contiguous-fibers layout: the warp-transposing variant keeps loads coalesced
+  if (!acc && T >= 2 && p.fm.ng == 1 && p.fm.gstride[0] == (int64_t)T && p.N == p.fm.nfib * T &&
+      p.fm.nfib >= 4096 && options().contig_kernel.load(std::memory_order_relaxed)) {
+    const int g2 = grid_for((p.fm.nfib + 31) / 32 * 32, block, 3);
+    if (conj_op) k_apply_small_contig<V, T, true><<<g2, block, 0, s>>>(in, out, op, p.fm.nfib, p.tm, skip);
+    else         k_apply_small_contig<V, T, false><<<g2, block, 0, s>>>(in, out, op, p.fm.nfib, p.tm, skip);
+    PW_LAUNCHED();
+    return PW_OK;
+  }
   if (conj_op) {
     if (acc) k_apply_small<V, T, true, true><<<grid, block, 0, s>>>(in, out, op, p.fm, p.tm, skip);
     else     k_apply_small<V, T, true, false><<<grid, block, 0, s>>>(in, out, op, p.fm, p.tm, skip);
@@ -365,4 +513,22 @@ extern "C" int pw_kraus_mat(const void* rho, void* out, const void* ops, int K,
   if (!rho || !out || !ops || K < 1) return PW_ERR_INVALID;
   if (dtype != PW_C64 && dtype != PW_C128) return PW_ERR_INVALID;
   return matrix_dispatch(rho, out, ops, K, dims, n, targets, nt, dtype, (cudaStream_t)stream);
+}
+
+extern "C" int pw_apply_vec_pair(const void* psi, void* out, const void* op_a, const void* op_b,
+                                 const int64_t* dims, int n, int axis_a, int axis_b, int dtype,
+                                 void* stream) {
+  if (!psi || !out || !op_a || !op_b || !dims || n < 2 || n > PW_MAX_SUBSYSTEMS) return PW_ERR_INVALID;
+  if (axis_a < 0 || axis_b < 0 || axis_a >= n || axis_b >= n || axis_a == axis_b) return PW_ERR_INVALID;
+  if (dims[axis_a] != dims[axis_b] || dims[axis_a] < 2 || dims[axis_a] > 6) return PW_ERR_UNSUPPORTED;
+  const int tg[2] = {axis_a, axis_b};
+  Plan p;
+  PW_TRY(build_plan(dims, n, tg, 2, &p));
+  if (dtype == PW_C128)
+    return launch_pair_t<double2>((const double2*)psi, (double2*)out, (const double2*)op_a,
+                                  (const double2*)op_b, p, (int)dims[axis_a], (cudaStream_t)stream);
+  if (dtype == PW_C64)
+    return launch_pair_t<float2>((const float2*)psi, (float2*)out, (const float2*)op_a,
+                                 (const float2*)op_b, p, (int)dims[axis_a], (cudaStream_t)stream);
+  return PW_ERR_INVALID;
 }

@@ -171,6 +171,8 @@ struct Options {
   std::atomic<int> vec_path{0}, mat_mode{0}, tile_elems{0}, ctas_per_sm{0};
   std::atomic<int> small_r{16};                // inner untouched run below this -> tiled staging
   std::atomic<int> mat_super_single{0};        // single operators on rho via superoperator tiles
+  std::atomic<int> contig_kernel{1};           // warp-transposing kernel for contiguous fibers
+  std::atomic<int> fuse_pairs{0};              // circuit entry points fuse adjacent single-axis ops
   std::atomic<int> nstage{0};                  // tiled kernel pipeline depth (0 = auto)
   std::atomic<int> blocks_min_elems{1 << 18};  // below this, skip structure analysis
 };

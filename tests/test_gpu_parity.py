@@ -376,3 +376,58 @@ def test_gather_kernels_single_process_emulation(ad):
         ref = oad.apply_operation_vector(dims, targets, psi.reshape(-1, 1), op)
         assert rel_err(host(out).reshape(-1, 1), ref) < 1e-12
     assert be.apply_vec_gather(srcs, chunk, out, dev(ops.random_unitary(12, 1)), dims, (0, 1)) is False
+
+
+@pytest.mark.parametrize("cdtype", [np.complex128, np.complex64])
+@pytest.mark.parametrize("dims,target", [((6,) * 7, (6,)), ((5, 4, 3, 8), (3,)), ((3, 2, 4, 2), (2, 3)),
+                                         ((3, 2, 2, 4), (3, 2)), ((7, 5, 2), (2,))])
+def test_contiguous_fiber_kernel_parity(ad, dims, target, cdtype):
+    """Targets on the innermost axes: warp-transposing register kernel (needs >= 4096 fibers
+    to be selected, so the leading axis is inflated)."""
+    big = (4096,) + tuple(dims)
+    tg = tuple(t + 1 for t in target)
+    N = math.prod(big)
+    t = math.prod(big[i] for i in tg)
+    psi = ops.random_state(N, 5, cdtype)
+    op = (ops.random_unitary(t, 6) * 0.9).astype(cdtype)
+    ref = oad.apply_operation_vector(big, tg, psi.astype(np.complex128), op.astype(np.complex128), True)
+    out = host(ad.apply_operation_vector(big, tg, dev(psi), dev(op)))
+    assert rel_err(out, ref) < TOL[cdtype]
+    rho_dims = (64,) + tuple(dims[-2:])
+    D = math.prod(rho_dims)
+    rho = ops.random_density(D, 7, dtype=cdtype)
+    last = len(rho_dims) - 1
+    d = rho_dims[last]
+    u = (ops.random_unitary(d, 8)).astype(cdtype)
+    refm = oad.apply_operation_matrix(rho_dims, (last,), rho.astype(np.complex128), u.astype(np.complex128), True)
+    outm = host(ad.apply_operation_matrix(rho_dims, (last,), dev(rho), dev(u)))
+    assert rel_err(outm, refm) < TOL[cdtype]
+
+
+@pytest.mark.parametrize("cdtype", [np.complex128, np.complex64])
+@pytest.mark.parametrize("d", [2, 3, 4, 5, 6])
+def test_fused_pair_and_device_circuit(ad, d, cdtype):
+    from photon_weave_b200.core import ffi
+
+    dims = (d, 3, d, 2, d)
+    N = math.prod(dims)
+    psi = ops.random_state(N, 9, cdtype)
+    ua, ub = ops.random_unitary(d, 1).astype(cdtype), ops.random_unitary(d, 2).astype(cdtype)
+    for (a, b) in [(0, 2), (4, 0), (2, 4)]:
+        out = ffi.apply_vec_pair(dev(psi), dev(ua), dev(ub), dims, a, b)
+        assert out is not None
+        ref = oad.apply_operation_vector(dims, (b,), oad.apply_operation_vector(
+            dims, (a,), psi.astype(np.complex128), ua.astype(np.complex128)), ub.astype(np.complex128))
+        assert rel_err(host(out).reshape(-1, 1), ref) < TOL[cdtype]
+    assert ffi.apply_vec_pair(dev(psi), dev(ua), dev(ops.random_unitary(3, 1).astype(cdtype)), dims, 0, 1) is None
+    # device-resident circuit, fused and unfused, equals op-by-op application
+    u3 = ops.random_unitary(3, 3).astype(cdtype)
+    bs = ops.beam_splitter(d, d, 0.4).astype(cdtype)
+    prog = [(0, (0,), ua), (0, (2,), ub), (0, (1,), u3), (0, (4,), ua), (0, (2, 4), bs), (0, (2,), ub)]
+    ref = psi.astype(np.complex128)
+    for _, tg, o in prog:
+        ref = oad.apply_operation_vector(dims, tg, ref, o.astype(np.complex128), True)
+    for fuse in (False, True):
+        st, sc = dev(psi).reshape(-1).clone(), torch.empty(N, dtype=dev(psi).dtype, device="cuda")
+        res, _ = ffi.circuit_device(st, sc, False, dims, [(k, tg, dev(o)) for k, tg, o in prog], fuse=fuse)
+        assert rel_err(host(res).reshape(-1, 1), ref) < TOL[cdtype] * 5

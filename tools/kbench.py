@@ -93,6 +93,11 @@ def bench_vec(args):
                     report(f"{tag} beam splitter {pair}", ms, best, nbytes)
                 ms, best = timeit(lambda: ffi.apply_vec(a, dense2, dims, (3, 4), out=b), reps=3, warm=1)
                 report(f"{tag} dense {d*d}x{d*d} (3,4)", ms, best, nbytes)
+    for pa, pb in [(3, 7), (0, 1), (modes - 2, modes - 1)]:
+        r = ffi.apply_vec_pair(a, u, u, dims, pa, pb, out=b)
+        if r is not None:
+            ms, best = timeit(lambda: ffi.apply_vec_pair(a, u, u, dims, pa, pb, out=b))
+            report(f"fused pair of {d}x{d} ops on axes ({pa},{pb}) [2 ops, 1 pass]", ms, best, nbytes)
     ms, best = timeit(lambda: ffi.probs(a, dims, (modes // 2,), False))
     report("probs_vec one mode", ms, best, N * es)
     ms, best = timeit(lambda: ffi.reduced_from_vec(a, dims, (modes // 2,)))
