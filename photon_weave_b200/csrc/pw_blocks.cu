@@ -167,7 +167,6 @@ k_apply_blocks(const V* __restrict__ in, V* __restrict__ out, const FiberMap fm,
 #pragma unroll
       for (int j = 0; j < MAXN; ++j)
         if (j < nc) x[j] = src[__ldg(bo + j)];
-#pragma unroll 1
       for (int a = 0; a < nr; ++a) {
         V acc = czero<V>();
 #pragma unroll

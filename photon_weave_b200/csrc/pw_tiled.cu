@@ -411,7 +411,6 @@ __device__ __noinline__ void run_pass_blocks(const V* __restrict__ src, V* __res
 #pragma unroll
     for (int j = 0; j < MAXN; ++j)
       if (j < nc) x[j] = src[fo + (int32_t)__ldg(bo + j)];
-#pragma unroll 1
     for (int a = 0; a < nr; ++a) {
       V acc = czero<V>();
 #pragma unroll
