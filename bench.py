@@ -345,6 +345,7 @@ def run_gpu_arm(args):
 
     # ---- density-matrix side of the metric (configs[3]): Kraus / apply on a 5-mode rho -----
     extras = None if args.no_extras else run_matrix_extras(torch, ffi, peak)
+    small = None if args.no_extras else run_small_configs(torch, ffi)
 
     # ---- CPU baseline on a bounded sample --------------------------------------------------
     cpu = None
@@ -361,7 +362,7 @@ def run_gpu_arm(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
         "config": workload_config(args, 1), "clocks": clocks, "e2e": e2e,
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-        "kernels": kernels, "norm_after": norm_after, "density_matrix": extras,
+        "kernels": kernels, "norm_after": norm_after, "density_matrix": extras, "small_configs": small,
         "paths": _lib.path_counters(),
     }
     print(json.dumps(line), flush=True)
@@ -452,6 +453,96 @@ def run_matrix_extras(torch, ffi, peak):
     res["trace_out_keep_mode1"] = {"ms": ms}
     del rho, out
     torch.cuda.empty_cache()
+    return res
+
+
+def run_small_configs(torch, ffi):
+    """configs[0..2] (launch-latency bound, L2 resident): microseconds per operation through
+    the seam, next to the NumPy port on the host (informational)."""
+    import math as _m
+
+    from oracle import adapters_np as oad
+    from oracle import operators as ops
+    from photon_weave_b200.core import adapters as ad
+
+    def dev(x):
+        return torch.as_tensor(np.ascontiguousarray(x)).cuda()
+
+    def gpu_us(fn, reps=200):
+        for _ in range(10):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps * 1e6
+
+    def cpu_us(fn, reps=50):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        return (time.perf_counter() - t0) / reps * 1e6
+
+    res = {}
+    # configs[0] Mach-Zehnder: 2 Fock modes (cutoff 2), BS - phase - BS, then two reduced states
+    dims = (2, 2)
+    bs, ph = ops.beam_splitter(2, 2, _m.pi / 4), ops.phase_operator(2, 0.7)
+    psi = np.zeros((4, 1), dtype=np.complex128); psi[2, 0] = 1
+    d_psi, d_bs, d_ph = dev(psi), dev(bs), dev(ph)
+
+    def mzi_gpu():
+        x = ad.apply_operation_vector(dims, (0, 1), d_psi, d_bs)
+        x = ad.apply_operation_vector(dims, (0,), x, d_ph)
+        x = ad.apply_operation_vector(dims, (0, 1), x, d_bs)
+        return ad.trace_out_vector(dims, (0,), x), ad.trace_out_vector(dims, (1,), x)
+
+    def mzi_cpu():
+        x = oad.apply_operation_vector(dims, (0, 1), psi, bs, True)
+        x = oad.apply_operation_vector(dims, (0,), x, ph, True)
+        x = oad.apply_operation_vector(dims, (0, 1), x, bs, True)
+        return oad.trace_out_vector(dims, (0,), x, True), oad.trace_out_vector(dims, (1,), x, True)
+
+    res["mach_zehnder_5_calls"] = {"gpu_us": gpu_us(mzi_gpu), "cpu_port_us": cpu_us(mzi_cpu)}
+    # configs[1] lossy 4-mode circuit on a density matrix, cutoff 5 (6.25 MB): BS + loss channels
+    dims = (5, 5, 5, 5)
+    D = 625
+    rho = ops.random_density(D, 3)
+    bs5, loss = ops.beam_splitter(5, 5, _m.pi / 4), ops.loss_channel(5, 0.1)
+    d_rho, d_bs5, d_loss = dev(rho), dev(bs5), dev(loss)
+    res["lossy_4mode_rho_bs"] = {
+        "gpu_us": gpu_us(lambda: ad.apply_operation_matrix(dims, (1, 2), d_rho, d_bs5), 50),
+        "cpu_port_us": cpu_us(lambda: oad.apply_operation_matrix(dims, (1, 2), rho, bs5, True), 3)}
+    res["lossy_4mode_rho_kraus_K5"] = {
+        "gpu_us": gpu_us(lambda: ad.apply_kraus_matrix(dims, (2,), d_rho, d_loss), 50),
+        "cpu_port_us": cpu_us(lambda: oad.apply_kraus_matrix(dims, (2,), rho, loss, True), 3)}
+    # configs[2] Jaynes-Cummings: cutoff 64 (x) qubit, 10k steps of (apply, trace_out(qubit))
+    dims = (64, 2)
+    U = ops.random_unitary(128, 5)
+    psi = ops.random_state(128, 6)
+    d_U, d_psi = dev(U), dev(psi).reshape(-1)
+    nsteps = 10000
+    ffi.evolve_vec(d_psi, d_U, dims, 10, keep=(1,))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out, red = ffi.evolve_vec(d_psi, d_U, dims, nsteps, keep=(1,))
+    red_host = red.cpu()
+    fused_s = time.perf_counter() - t0
+
+    def jc_step_gpu():
+        x = ad.apply_operation_vector(dims, (0, 1), d_psi.reshape(-1, 1), d_U)
+        return ad.trace_out_vector(dims, (1,), x)
+
+    def jc_step_cpu():
+        x = U @ psi
+        return oad.trace_out_vector(dims, (1,), x, True)
+
+    res["jaynes_cummings_10k_steps"] = {
+        "fused_kernel_total_ms": fused_s * 1e3, "fused_us_per_step": fused_s / nsteps * 1e6,
+        "per_call_api_us_per_step": gpu_us(jc_step_gpu, 200),
+        "cpu_port_us_per_step": cpu_us(jc_step_cpu, 200),
+        "norm_check": float(np.trace(red_host[-1].numpy()).real)}
     return res
 
 

@@ -101,6 +101,17 @@ int pw_kraus_mat(const void* rho, void* out, const void* ops, int K, const int64
 int pw_apply_vec_pair(const void* psi, void* out, const void* op_a, const void* op_b,
                       const int64_t* dims, int n, int axis_a, int axis_b, int dtype, void* stream);
 
+/* Fused multi-step evolution of a small state (prod(dims) <= 128) under ONE dense operator
+ * acting on ALL subsystems (op is N x N, indices in tensor order): psi <- op^nsteps psi in a
+ * single kernel.  If reduced_out != NULL it receives, for every step s, the reduced density
+ * matrix (tk x tk, tk = prod(dims[keep]) <= 8) of the state AFTER step s, i.e. what
+ * `apply_operation` + `trace_out` return per iteration of the Jaynes-Cummings loop
+ * (examples/jaynes_cummings_model.py:130-141).  New surface: the reference has no
+ * multi-step entry point. */
+int pw_evolve_vec(const void* psi, void* out, const void* op, const int64_t* dims, int n,
+                  const int32_t* keep, int nkeep, int nsteps, void* reduced_out, int dtype,
+                  void* stream);
+
 /* ---- reductions ---------------------------------------------------------------- */
 
 /* out (t x t) = Tr_rest rho, kept subsystems ordered as listed in `keep`.

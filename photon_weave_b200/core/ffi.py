@@ -222,6 +222,26 @@ def circuit_device(state: torch.Tensor, scratch: Optional[torch.Tensor], is_matr
     return (scratch, state) if flag.value else (state, scratch)
 
 
+def evolve_vec(psi: torch.Tensor, op: torch.Tensor, dims, nsteps: int, keep=None):
+    """psi <- op^nsteps psi in one kernel (small states); returns (psi_out, reduced[nsteps,tk,tk]
+    or None)."""
+    lib = _lib.load()
+    out = torch.empty_like(psi)
+    red = None
+    keep = list(keep) if keep is not None else []
+    if keep:
+        tk = math.prod(dims[i] for i in keep)
+        red = torch.empty((nsteps, tk, tk), dtype=psi.dtype, device=psi.device)
+    _lib.check(
+        lib.pw_evolve_vec(psi.data_ptr(), out.data_ptr(), op.data_ptr(), _lib.i64_array(dims), len(dims),
+                          _lib.i32_array(keep), len(keep), int(nsteps),
+                          red.data_ptr() if red is not None else None, A.code(psi.dtype),
+                          A.stream_ptr()),
+        "pw_evolve_vec",
+    )
+    return out, red
+
+
 def rng_split(key, num: int = 2) -> np.ndarray:
     lib = _lib.load()
     k0, k1 = A.key_words(key)

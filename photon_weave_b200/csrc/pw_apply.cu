@@ -354,6 +354,11 @@ static int apply_axes(const void* in, void* out, const void* op, const int64_t* 
   // untouched run (>= small_r elements), TMA-staged tiles win when it belongs to the fibers.
   const bool prefer_tiled = vp == 2 || (vp == 0 && large && r_in < small_r && p.tm.t > 8);
   if (p.tm.t <= 8 && vp != 3 && !prefer_tiled) return launch_apply(in, out, op, p, dtype, conj_op, false, s);
+  // launch-latency-bound states: one row-parallel dense kernel, no analysis, no tiles
+  if (vp == 0 && !large && in != out) {
+    const int rc = launch_apply_rows(in, out, op, p, dtype, conj_op, s);
+    if (rc != PW_ERR_UNSUPPORTED) return rc;
+  }
   BlockDesc bd;
   const int* skip = nullptr;
   if ((vp == 0 || vp == 3) && !prefer_tiled && in != out && p.tm.t <= kBlockMaxT && large) {

@@ -186,4 +186,8 @@ Options& options();
 int launch_apply(const void* in, void* out, const void* op, const Plan& plan, int dtype,
                  bool conj_op, bool accumulate, cudaStream_t stream, const int* skip = nullptr);
 
+// row-parallel dense apply for small states (pw_evolve.cu); PW_ERR_UNSUPPORTED if in == out
+int launch_apply_rows(const void* in, void* out, const void* op, const Plan& plan, int dtype,
+                      bool conj_op, cudaStream_t stream);
+
 }  // namespace pw

@@ -432,3 +432,37 @@ def test_fused_pair_and_device_circuit(ad, d, cdtype):
         st, sc = dev(psi).reshape(-1).clone(), torch.empty(N, dtype=dev(psi).dtype, device="cuda")
         res, _ = ffi.circuit_device(st, sc, False, dims, [(k, tg, dev(o)) for k, tg, o in prog], fuse=fuse)
         assert rel_err(host(res).reshape(-1, 1), ref) < TOL[cdtype] * 5
+
+
+@pytest.mark.parametrize("cdtype", [np.complex128, np.complex64])
+@pytest.mark.parametrize("dims,keep", [((64, 2), (1,)), ((5, 3, 2), (2, 0)), ((7,), (0,)), ((16, 8), (1,))])
+def test_fused_evolve_matches_stepwise(ad, dims, keep, cdtype):
+    """pw_evolve_vec == nsteps x (apply_operation on all subsystems, trace_out of `keep`)."""
+    from photon_weave_b200.core import ffi
+
+    N = math.prod(dims)
+    U = ops.random_unitary(N, 3).astype(cdtype)
+    psi = ops.random_state(N, 4, cdtype)
+    nsteps = 25
+    out, red = ffi.evolve_vec(dev(psi).reshape(-1), dev(U), dims, nsteps, keep=keep)
+    ref = psi.astype(np.complex128)
+    tol = TOL[cdtype] * (20 if cdtype == np.complex64 else 50)
+    for s in range(nsteps):
+        ref = U.astype(np.complex128) @ ref
+        want = oad.trace_out_vector(dims, keep, ref, use_contraction=False)
+        assert rel_err(host(red[s]), want) < tol
+    assert rel_err(host(out).reshape(-1, 1), ref) < tol
+    # without observables
+    out2, red2 = ffi.evolve_vec(dev(psi).reshape(-1), dev(U), dims, nsteps)
+    assert red2 is None and rel_err(host(out2).reshape(-1, 1), ref) < tol
+
+
+def test_small_state_dense_rows_path(ad):
+    """Launch-latency-bound shape (Jaynes-Cummings, t = 128, one fiber) and a t = 25 case."""
+    for dims, tg in [((64, 2), (0, 1)), ((5, 5, 3), (1, 0)), ((2, 36), (1,))]:
+        N = math.prod(dims)
+        t = math.prod(dims[i] for i in tg)
+        psi = ops.random_state(N, 1)
+        op = ops.random_unitary(t, 2)
+        out = host(ad.apply_operation_vector(dims, tg, dev(psi), dev(op)))
+        assert rel_err(out, oad.apply_operation_vector(dims, tg, psi, op)) < 1e-12
