@@ -6,55 +6,73 @@
 // memory, and emits the reduced density matrix of the kept subsystems after every step.
 //
 // Also: a row-parallel dense apply for launch-latency-bound states (t > 8, few fibers).
+#include <cooperative_groups.h>
+
 #include "pw_internal.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace pw {
 
 constexpr int kEvoMaxN = 128;   // state dimension handled by the fused kernel
-constexpr int kEvoTPR = 8;      // threads cooperating on one output row
-constexpr int kEvoSeg = kEvoMaxN / kEvoTPR;
+constexpr int kEvoRows = 32;    // output rows (= warps) per CTA
+constexpr int kEvoSeg = kEvoMaxN / 32;
 
+// A thread-block CLUSTER of ceil(N/32) CTAs shares the work: CTA c owns rows
+// [32c, 32c+32), one warp per row, lane l holds U[row, l + 32 j] in registers.  Every CTA
+// keeps the full state in its shared memory; after each step the owners write their new
+// amplitudes into EVERY CTA's buffer through distributed shared memory and the cluster
+// synchronises (one barrier per step, no global memory traffic inside the loop).
 template <typename V>
 __global__ void __launch_bounds__(1024, 1)
 k_evolve(const V* __restrict__ psi0, V* __restrict__ psi_out, const V* __restrict__ U, const int N,
          const int nsteps, const FiberMap fm, const TargetMap tm, V* __restrict__ reduced_out) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned crank = cluster.block_rank(), csize = cluster.num_blocks();
   __shared__ V xs[2][kEvoMaxN];
   __shared__ int s_koff[64];
   __shared__ int s_fbase[kEvoMaxN];
-  const int tid = threadIdx.x, a = tid / kEvoTPR, s = tid % kEvoTPR;
-  const int seg = (N + kEvoTPR - 1) / kEvoTPR;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int a = (int)crank * kEvoRows + warp;  // my output row
   V u[kEvoSeg];
 #pragma unroll
   for (int j = 0; j < kEvoSeg; ++j) {
-    const int b = s * seg + j;
-    u[j] = (a < N && j < seg && b < N) ? U[(size_t)a * N + b] : czero<V>();
+    const int b = lane + 32 * j;
+    u[j] = (a < N && b < N) ? U[(size_t)a * N + b] : czero<V>();
   }
   const int tk = (int)tm.t, nfib = (int)fm.nfib;
-  if (reduced_out) {
+  const bool observer = reduced_out != nullptr && crank == 0;
+  if (observer) {
     for (int i = tid; i < tk; i += blockDim.x) s_koff[i] = (int)tm.offset(i);
     for (int f = tid; f < nfib; f += blockDim.x) s_fbase[f] = (int)fm.base(f);
   }
   for (int i = tid; i < N; i += blockDim.x) xs[0][i] = psi0[i];
-  __syncthreads();
+  cluster.sync();
   int cur = 0;
   for (int step = 0; step < nsteps; ++step) {
     V acc = czero<V>();
 #pragma unroll
     for (int j = 0; j < kEvoSeg; ++j) {
-      const int b = s * seg + j;
-      if (j < seg && b < N) cfma(acc, u[j], xs[cur][b]);
+      const int b = lane + 32 * j;
+      if (b < N) cfma(acc, u[j], xs[cur][b]);
     }
 #pragma unroll
-    for (int o = kEvoTPR / 2; o > 0; o >>= 1) {
-      acc.x += __shfl_down_sync(0xffffffffu, acc.x, o, kEvoTPR);
-      acc.y += __shfl_down_sync(0xffffffffu, acc.y, o, kEvoTPR);
+    for (int o = 16; o > 0; o >>= 1) {
+      acc.x += __shfl_down_sync(0xffffffffu, acc.x, o);
+      acc.y += __shfl_down_sync(0xffffffffu, acc.y, o);
     }
-    if (s == 0 && a < N) xs[cur ^ 1][a] = acc;
-    __syncthreads();
+    acc.x = __shfl_sync(0xffffffffu, acc.x, 0);
+    acc.y = __shfl_sync(0xffffffffu, acc.y, 0);
+    // lane r < csize publishes the row's new amplitude into CTA r's next-state buffer
+    if (a < N && lane < (int)csize) {
+      V* remote = cluster.map_shared_rank(&xs[cur ^ 1][0], lane);
+      remote[a] = acc;
+    }
+    cluster.sync();
     cur ^= 1;
-    if (reduced_out) {
+    if (observer) {
       // rho_T[i, j] = sum_f x[f, i] conj(x[f, j]) of the NEW state; one warp per entry
-      const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+      const int nwarps = blockDim.x >> 5;
       for (int e = warp; e < tk * tk; e += nwarps) {
         const int i = e / tk, j = e - i * tk;
         double re = 0, im = 0;
@@ -75,7 +93,8 @@ k_evolve(const V* __restrict__ psi0, V* __restrict__ psi_out, const V* __restric
       }
     }
   }
-  for (int i = tid; i < N; i += blockDim.x) psi_out[i] = xs[cur][i];
+  if (crank == 0)
+    for (int i = tid; i < N; i += blockDim.x) psi_out[i] = xs[cur][i];
 }
 
 // Row-parallel dense apply for small states: block = one fiber (staged in shared memory),
@@ -132,15 +151,29 @@ extern "C" int pw_evolve_vec(const void* psi, void* out, const void* op, const i
   PW_TRY(build_plan(dims, n, keep, reduced_out ? nkeep : 0, &p));
   if (p.N > (uint64_t)kEvoMaxN) return PW_ERR_UNSUPPORTED;
   if (reduced_out && p.tm.t > 8) return PW_ERR_UNSUPPORTED;
-  cudaStream_t s = (cudaStream_t)stream;
-  if (dtype == PW_C128)
-    k_evolve<double2><<<1, 1024, 0, s>>>((const double2*)psi, (double2*)out, (const double2*)op, (int)p.N,
-                                         nsteps, p.fm, p.tm, (double2*)reduced_out);
-  else if (dtype == PW_C64)
-    k_evolve<float2><<<1, 1024, 0, s>>>((const float2*)psi, (float2*)out, (const float2*)op, (int)p.N,
-                                        nsteps, p.fm, p.tm, (float2*)reduced_out);
-  else
+  const int N = (int)p.N;
+  const unsigned csize = (unsigned)((N + kEvoRows - 1) / kEvoRows);  // 1..4 CTAs in one cluster
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(csize);
+  cfg.blockDim = dim3(1024);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (dtype == PW_C128) {
+    PW_CUDA(cudaLaunchKernelEx(&cfg, k_evolve<double2>, (const double2*)psi, (double2*)out,
+                               (const double2*)op, N, nsteps, p.fm, p.tm, (double2*)reduced_out));
+  } else if (dtype == PW_C64) {
+    PW_CUDA(cudaLaunchKernelEx(&cfg, k_evolve<float2>, (const float2*)psi, (float2*)out,
+                               (const float2*)op, N, nsteps, p.fm, p.tm, (float2*)reduced_out));
+  } else {
     return PW_ERR_INVALID;
+  }
   PW_LAUNCHED();
   return PW_OK;
 }
