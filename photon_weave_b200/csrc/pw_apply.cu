@@ -184,16 +184,105 @@ k_apply_pair(const V* in, V* out, const V* __restrict__ opa, const V* __restrict
   }
 }
 
+// Split variant: Q adjacent lanes share one D x D sub-tensor, each owning D/Q columns of
+// the SECOND index.  The first-index product is lane-local; for the second index every row
+// is assembled from the Q lanes with warp shuffles.  Keeps the register tile at D*D/Q
+// elements (D = 8 complex128 no longer fits one thread) and the loads coalesced.
+template <typename V, int D, int Q, bool CONJB>
+__global__ void __launch_bounds__(256, 1)
+k_apply_pair_split(const V* in, V* out, const V* __restrict__ opa, const V* __restrict__ opb,
+                   const FiberMap fm, const TargetMap tm, const int* __restrict__ skip) {
+  if (skip && *skip) return;
+  constexpr int C = D / Q;
+  static_assert(D % Q == 0 && (Q & (Q - 1)) == 0 && Q <= 32, "Q must be a power of two dividing D");
+  __shared__ V s_a[D * D], s_b[D * D];
+  __shared__ int64_t s_off[D * D];
+  for (int i = threadIdx.x; i < D * D; i += blockDim.x) {
+    s_a[i] = opa[i];
+    V b = opb[i];
+    if (CONJB) b.y = -b.y;
+    s_b[i] = b;
+    s_off[i] = tm.offset(i);
+  }
+  __syncthreads();
+  const int q = threadIdx.x % Q;
+  const int lane = threadIdx.x & 31, lane0 = lane - q;
+  const uint64_t nwork = fm.nfib * Q;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  // all lanes of a warp must take part in the shuffles: iterate on a warp-uniform bound
+  const uint64_t nwork_pad = (nwork + 31) / 32 * 32;
+  for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwork_pad; w += stride) {
+    const bool live = w < nwork;
+    const uint64_t f = live ? w / Q : 0;
+    const int64_t base = fm.base(f);
+    int zero = 0;
+    asm volatile("" : "+r"(zero));
+    const V* sa = s_a + zero;
+    const V* sb = s_b + zero;
+    V x[D][C];
+#pragma unroll
+    for (int jl = 0; jl < C; ++jl) {
+      V c[D];
+#pragma unroll
+      for (int b = 0; b < D; ++b) c[b] = live ? in[base + s_off[b * D + q * C + jl]] : czero<V>();
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+        V acc = czero<V>();
+#pragma unroll
+        for (int b = 0; b < D; ++b) cfma(acc, sa[a * D + b], c[b]);
+        x[a][jl] = acc;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      V y[D];
+#pragma unroll
+      for (int qq = 0; qq < Q; ++qq)
+#pragma unroll
+        for (int jl = 0; jl < C; ++jl) {
+          y[qq * C + jl].x = __shfl_sync(0xffffffffu, x[i][jl].x, lane0 + qq);
+          y[qq * C + jl].y = __shfl_sync(0xffffffffu, x[i][jl].y, lane0 + qq);
+        }
+#pragma unroll
+      for (int al = 0; al < C; ++al) {
+        V acc = czero<V>();
+#pragma unroll
+        for (int b = 0; b < D; ++b) cfma(acc, sb[(q * C + al) * D + b], y[b]);
+        if (live) out[base + s_off[i * D + q * C + al]] = acc;
+      }
+    }
+  }
+}
+
+template <typename V, int D, int Q>
+static void launch_pair_split(const V* in, V* out, const V* opa, const V* opb, const Plan& p,
+                              bool conj_b, cudaStream_t s, const int* skip) {
+  const int grid = grid_for(p.fm.nfib * Q, 256, 1);
+  if (conj_b) k_apply_pair_split<V, D, Q, true><<<grid, 256, 0, s>>>(in, out, opa, opb, p.fm, p.tm, skip);
+  else        k_apply_pair_split<V, D, Q, false><<<grid, 256, 0, s>>>(in, out, opa, opb, p.fm, p.tm, skip);
+}
+
 template <typename V>
 static int launch_pair_t(const V* in, V* out, const V* opa, const V* opb, const Plan& p, int d,
-                         cudaStream_t s) {
+                         bool conj_b, cudaStream_t s, const int* skip = nullptr) {
   const int grid = grid_for(p.fm.nfib, 256, 1);
+  const bool wide = sizeof(V) == 16;  // complex128: register tiles are twice as large
   switch (d) {
-    case 2: k_apply_pair<V, 2><<<grid, 256, 0, s>>>(in, out, opa, opb, p.fm, p.tm); break;
-    case 3: k_apply_pair<V, 3><<<grid, 256, 0, s>>>(in, out, opa, opb, p.fm, p.tm); break;
-    case 4: k_apply_pair<V, 4><<<grid, 256, 0, s>>>(in, out, opa, opb, p.fm, p.tm); break;
-    case 5: k_apply_pair<V, 5><<<grid, 256, 0, s>>>(in, out, opa, opb, p.fm, p.tm); break;
-    case 6: k_apply_pair<V, 6><<<grid, 256, 0, s>>>(in, out, opa, opb, p.fm, p.tm); break;
+    case 2: launch_pair_split<V, 2, 1>(in, out, opa, opb, p, conj_b, s, skip); break;
+    case 3: launch_pair_split<V, 3, 1>(in, out, opa, opb, p, conj_b, s, skip); break;
+    case 4: if (wide) launch_pair_split<V, 4, 2>(in, out, opa, opb, p, conj_b, s, skip);
+            else      launch_pair_split<V, 4, 1>(in, out, opa, opb, p, conj_b, s, skip);
+            break;
+    case 5: if (conj_b || skip) return PW_ERR_UNSUPPORTED;
+            k_apply_pair<V, 5><<<grid, 256, 0, s>>>(in, out, opa, opb, p.fm, p.tm); break;
+    case 6: if (wide) launch_pair_split<V, 6, 2>(in, out, opa, opb, p, conj_b, s, skip);
+            else      launch_pair_split<V, 6, 1>(in, out, opa, opb, p, conj_b, s, skip);
+            break;
+    case 7: if (conj_b || wide) return PW_ERR_UNSUPPORTED;
+            return PW_ERR_UNSUPPORTED;
+    case 8: if (wide) launch_pair_split<V, 8, 8>(in, out, opa, opb, p, conj_b, s, skip);
+            else      launch_pair_split<V, 8, 4>(in, out, opa, opb, p, conj_b, s, skip);
+            break;
     default: return PW_ERR_UNSUPPORTED;
   }
   g_paths[0].fetch_add(1, std::memory_order_relaxed);
@@ -502,6 +591,21 @@ static int matrix_dispatch(const void* rho, void* out, const void* ops, int K, c
     if (rc != PW_ERR_UNSUPPORTED) return rc;
     g_paths[3].fetch_add(1, std::memory_order_relaxed);
   }
+  // single operator on ONE subsystem: rows and columns are two commuting single-axis
+  // operators (O, conj(O)) on the doubled tensor -> one fused register pass
+  if (K == 1 && nt == 1 && rho != out && mm != 1) {
+    const int tg[2] = {r.rows[0], r.cols[0]};
+    Plan p;
+    PW_TRY(build_plan_axes(r.axes, 2 * n, tg, 2, &p));
+    int rc;
+    if (dtype == PW_C128)
+      rc = launch_pair_t<double2>((const double2*)rho, (double2*)out, (const double2*)ops,
+                                  (const double2*)ops, p, (int)r.t, true, s, skip);
+    else
+      rc = launch_pair_t<float2>((const float2*)rho, (float2*)out, (const float2*)ops,
+                                 (const float2*)ops, p, (int)r.t, true, s, skip);
+    if (rc != PW_ERR_UNSUPPORTED) return rc;
+  }
   return two_pass(rho, out, ops, K, r, dtype, s, skip);
 }
 
@@ -525,15 +629,15 @@ extern "C" int pw_apply_vec_pair(const void* psi, void* out, const void* op_a, c
                                  void* stream) {
   if (!psi || !out || !op_a || !op_b || !dims || n < 2 || n > PW_MAX_SUBSYSTEMS) return PW_ERR_INVALID;
   if (axis_a < 0 || axis_b < 0 || axis_a >= n || axis_b >= n || axis_a == axis_b) return PW_ERR_INVALID;
-  if (dims[axis_a] != dims[axis_b] || dims[axis_a] < 2 || dims[axis_a] > 6) return PW_ERR_UNSUPPORTED;
+  if (dims[axis_a] != dims[axis_b] || dims[axis_a] < 2 || dims[axis_a] > 8) return PW_ERR_UNSUPPORTED;
   const int tg[2] = {axis_a, axis_b};
   Plan p;
   PW_TRY(build_plan(dims, n, tg, 2, &p));
   if (dtype == PW_C128)
     return launch_pair_t<double2>((const double2*)psi, (double2*)out, (const double2*)op_a,
-                                  (const double2*)op_b, p, (int)dims[axis_a], (cudaStream_t)stream);
+                                  (const double2*)op_b, p, (int)dims[axis_a], false, (cudaStream_t)stream);
   if (dtype == PW_C64)
     return launch_pair_t<float2>((const float2*)psi, (float2*)out, (const float2*)op_a,
-                                 (const float2*)op_b, p, (int)dims[axis_a], (cudaStream_t)stream);
+                                 (const float2*)op_b, p, (int)dims[axis_a], false, (cudaStream_t)stream);
   return PW_ERR_INVALID;
 }
