@@ -593,7 +593,10 @@ static int matrix_dispatch(const void* rho, void* out, const void* ops, int K, c
   }
   // single operator on ONE subsystem: rows and columns are two commuting single-axis
   // operators (O, conj(O)) on the doubled tensor -> one fused register pass
-  if (K == 1 && nt == 1 && rho != out && mm != 1) {
+  // (measured: wins for d <= 4; for larger d the register tile limits occupancy and two
+  //  register-kernel passes are faster -- profiles/r1_kbench_mat_v6.txt)
+  const uint64_t pair_max_d = (uint64_t)options().mat_pair_max_d.load(std::memory_order_relaxed);
+  if (K == 1 && nt == 1 && rho != out && mm != 1 && r.t <= pair_max_d) {
     const int tg[2] = {r.rows[0], r.cols[0]};
     Plan p;
     PW_TRY(build_plan_axes(r.axes, 2 * n, tg, 2, &p));
