@@ -50,6 +50,7 @@ Options& options() {
     env("PW_CTAS_PER_SM", p->ctas_per_sm);
     env("PW_BLOCKS_MIN_ELEMS", p->blocks_min_elems);
     env("PW_NSTAGE", p->nstage);
+    env("PW_SEG_KERNEL", p->seg_kernel);
     env("PW_MAT_PAIR_MAX_D", p->mat_pair_max_d);
     env("PW_FUSE_PAIRS", p->fuse_pairs);
     env("PW_CONTIG_KERNEL", p->contig_kernel);
@@ -70,6 +71,7 @@ extern "C" int pw_set_option(const char* name, int value) {
   else if (!std::strcmp(name, "ctas_per_sm")) o.ctas_per_sm.store(value);
   else if (!std::strcmp(name, "blocks_min_elems")) o.blocks_min_elems.store(value);
   else if (!std::strcmp(name, "nstage")) o.nstage.store(value);
+  else if (!std::strcmp(name, "seg_kernel")) o.seg_kernel.store(value);
   else if (!std::strcmp(name, "mat_pair_max_d")) o.mat_pair_max_d.store(value);
   else if (!std::strcmp(name, "fuse_pairs")) o.fuse_pairs.store(value);
   else if (!std::strcmp(name, "contig_kernel")) o.contig_kernel.store(value);

@@ -454,6 +454,12 @@ static int apply_axes(const void* in, void* out, const void* op, const int64_t* 
     const int rc = launch_blocks(in, out, op, p, dtype, conj_op, &bd, s);
     if (rc == PW_OK) skip = bd.skip_flag();
     else if (rc != PW_ERR_UNSUPPORTED) return rc;
+  } else if (vp == 0 && prefer_tiled && in != out && r_in == 0 &&
+             options().seg_kernel.load(std::memory_order_relaxed)) {
+    // the contiguous direction belongs to the fibers: warp-staged block kernel first
+    const int rc = launch_blocks_seg(in, out, op, axes, naxes, targets, nt, dtype, conj_op, &bd, s);
+    if (rc == PW_OK) skip = bd.skip_flag();
+    else if (rc != PW_ERR_UNSUPPORTED) return rc;
   }
   if (vp != 1) {
     TiledGeom g;
@@ -504,18 +510,18 @@ static int matrix_req(const int64_t* dims, int n, const int32_t* targets, int nt
 static int try_super_blocks(const void* rho, void* out, const void* ops, int K, const MatrixReq& r,
                             int dtype, cudaStream_t s, Scratch* super, BlockDesc* bd) {
   if (rho == out || r.t * r.t > kBlockMaxT || r.N * r.N < blocks_min_elems()) return PW_ERR_UNSUPPORTED;
-  {
-    Plan q;
-    PW_TRY(build_plan_axes(r.axes, 2 * r.n, r.both, 2 * r.nt, &q));
-    if (mat_mode() == 0 && inner_rest_run(q) < (uint64_t)options().small_r.load(std::memory_order_relaxed))
-      return PW_ERR_UNSUPPORTED;  // contiguous direction is a target: the tiled kernel stages it
-  }
+  Plan p;
+  PW_TRY(build_plan_axes(r.axes, 2 * r.n, r.both, 2 * r.nt, &p));
+  const uint64_t r_in = inner_rest_run(p);
+  const bool staged = mat_mode() == 0 && r_in < (uint64_t)options().small_r.load(std::memory_order_relaxed);
+  if (staged && (r_in != 0 || !options().seg_kernel.load(std::memory_order_relaxed)))
+    return PW_ERR_UNSUPPORTED;  // short untouched inner run: the tiled kernel stages it
   const size_t es = elem_size(dtype);
   const uint64_t tt = r.t * r.t;
   PW_TRY(super->alloc(es * tt * tt, s));
   PW_TRY(build_superoperator(ops, K, (uint32_t)r.t, super->p, dtype, s));
-  Plan p;
-  PW_TRY(build_plan_axes(r.axes, 2 * r.n, r.both, 2 * r.nt, &p));
+  if (staged)  // the column target is the innermost axis: warp-staged block kernel
+    return launch_blocks_seg(rho, out, super->p, r.axes, 2 * r.n, r.both, 2 * r.nt, dtype, false, bd, s);
   return launch_blocks(rho, out, super->p, p, dtype, false, bd, s);
 }
 

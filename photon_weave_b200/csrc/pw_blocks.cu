@@ -110,6 +110,17 @@ k_build_blocks(const V* __restrict__ op, const uint32_t t, const bool conj_op, c
     hdr->maxn = s_maxn;
     hdr->nzero = s_nzero;
     hdr->usable = (s_maxn <= kBlockMaxN) ? 1 : 0;
+    // position a is written by the block of ROW a and read by the block of COLUMN a:
+    // in-place is safe iff those coincide wherever both exist (zero rows write too)
+    int safe = 1;
+    for (uint32_t a = 0; a < t; ++a) {
+      bool col_used = false;
+      for (uint32_t r = 0; r < t && !col_used; ++r) col_used = (lr[r] == lc[a]);
+      if (!col_used) continue;                 // nobody reads position a
+      if (lr[a] != lc[a]) safe = 0;            // written by another block (or cleared)
+    }
+    hdr->inplace_safe = safe;
+    hdr->seg_handled = (hdr->usable && safe) ? 1 : 0;
   }
   __syncthreads();
   for (int b = threadIdx.x; b < s_nblocks; b += blockDim.x) {
@@ -179,6 +190,102 @@ k_apply_blocks(const V* __restrict__ in, V* __restrict__ out, const FiberMap fm,
   }
 }
 
+// ---- staged (segmented) apply ------------------------------------------------------------
+struct SegGeom {
+  uint32_t t;          // operator dimension = elements per fiber
+  uint32_t lseg;       // contiguous elements per segment (innermost target run)
+  uint32_t nseg;       // segments per fiber
+  uint32_t pitch;      // shared-memory row pitch per fiber (odd -> conflict-free)
+  uint64_t M;          // extent of the rest run adjacent to the inner run (fibers lseg apart)
+  int64_t seg_off[64]; // global element offset of segment s
+  FiberMap outer;      // remaining untouched axes
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+}
+
+template <typename V, int MAXN>
+__global__ void __launch_bounds__(256)
+k_apply_blocks_seg(const V* __restrict__ in, V* __restrict__ out, const SegGeom g,
+                   const BlockDescHeader* __restrict__ hdr, const int4* __restrict__ blocks,
+                   const int64_t* __restrict__ offs, const V* __restrict__ vals,
+                   const int64_t* __restrict__ zero_offs) {
+  if (!hdr->seg_handled) return;
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  V* buf = (V*)s_raw + (size_t)warp * 32 * g.pitch;
+  const int nblocks = hdr->nblocks, nzero = hdr->nzero;
+  const uint64_t chunks = (g.M + 31) / 32;
+  const uint64_t ntasks = g.outer.nfib * chunks;
+  // lane-constant decomposition of the coalesced copy index e = it*32 + lane into
+  // (fiber q, position r) without divisions: each iteration adds 32 = qa*lseg + rb
+  const uint32_t qa = 32 / g.lseg, rb = 32 % g.lseg;
+  for (uint64_t task = (uint64_t)blockIdx.x * nwarps + warp; task < ntasks;
+       task += (uint64_t)gridDim.x * nwarps) {
+    const uint64_t o = task / chunks, c = task - o * chunks;
+    const uint64_t m0 = c * 32;
+    const uint32_t nvalid = (uint32_t)((g.M - m0) < 32 ? (g.M - m0) : 32);
+    const int64_t base = g.outer.base(o) + (int64_t)m0 * g.lseg;
+    const uint32_t row_elems = nvalid * g.lseg;
+    // ---- stage: nseg coalesced rows -> padded per-fiber rows in shared memory
+    for (uint32_t s = 0; s < g.nseg; ++s) {
+      const V* src = in + base + g.seg_off[s];
+      uint32_t q = (uint32_t)lane / g.lseg, r = (uint32_t)lane % g.lseg;
+      for (uint32_t e = lane; e < row_elems; e += 32) {
+        V* dst = buf + (size_t)q * g.pitch + s * g.lseg + r;
+        if (sizeof(V) == 16) cp_async16(dst, src + e); else cp_async8(dst, src + e);
+        q += qa; r += rb;
+        if (r >= g.lseg) { r -= g.lseg; ++q; }
+      }
+    }
+    cp_async_wait_all();
+    __syncwarp();
+    // ---- compute: one fiber per lane, blocks applied in place
+    if ((uint32_t)lane < nvalid) {
+      V* fib = buf + (size_t)lane * g.pitch;
+      for (int b = 0; b < nblocks; ++b) {
+        const int4 h = __ldg(blocks + b);
+        const int nr = h.x, nc = h.y;
+        const int64_t* bo = offs + h.z;
+        const V* bv = vals + h.w;
+        V x[MAXN];
+#pragma unroll
+        for (int j = 0; j < MAXN; ++j)
+          if (j < nc) x[j] = fib[(int32_t)__ldg(bo + j)];
+        for (int a = 0; a < nr; ++a) {
+          V acc = czero<V>();
+#pragma unroll
+          for (int j = 0; j < MAXN; ++j)
+            if (j < nc) cfma(acc, __ldg(bv + a * nc + j), x[j]);
+          fib[(int32_t)__ldg(bo + nc + a)] = acc;
+        }
+      }
+      for (int z = 0; z < nzero; ++z) fib[(int32_t)__ldg(zero_offs + z)] = czero<V>();
+    }
+    __syncwarp();
+    // ---- stream back, same coalesced row pattern
+    for (uint32_t s = 0; s < g.nseg; ++s) {
+      V* dstg = out + base + g.seg_off[s];
+      uint32_t q = (uint32_t)lane / g.lseg, r = (uint32_t)lane % g.lseg;
+      for (uint32_t e = lane; e < row_elems; e += 32) {
+        dstg[e] = buf[(size_t)q * g.pitch + s * g.lseg + r];
+        q += qa; r += rb;
+        if (r >= g.lseg) { r -= g.lseg; ++q; }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 template <typename V>
 static int build_block_desc_t(const V* op, uint32_t t, bool conj_op, const TargetMap& tm,
                               Scratch* mem, BlockArrays* arr, cudaStream_t s) {
@@ -232,6 +339,125 @@ int launch_blocks(const void* in, void* out, const void* op, const Plan& plan, i
     return launch_blocks_t<double2>((const double2*)in, (double2*)out, (const double2*)op, plan, conj_op, desc, stream);
   if (dtype == PW_C64)
     return launch_blocks_t<float2>((const float2*)in, (float2*)out, (const float2*)op, plan, conj_op, desc, stream);
+  return PW_ERR_INVALID;
+}
+
+// Geometry of the staged kernel; false when the innermost axis is not a target or the
+// sizes do not fit.
+static bool plan_seg(const int64_t* axes, int naxes, const int* targets, int nt, SegGeom* g,
+                     TargetMap* smem_tm) {
+  if (naxes < 1 || naxes > kMaxAxes || nt < 1 || nt > kMaxTargets) return false;
+  int64_t stride[kMaxAxes];
+  bool is_t[kMaxAxes] = {false};
+  uint64_t N = 1;
+  for (int i = naxes - 1; i >= 0; --i) { stride[i] = (int64_t)N; N *= (uint64_t)axes[i]; }
+  uint64_t t = 1;
+  for (int k = 0; k < nt; ++k) { is_t[targets[k]] = true; t *= (uint64_t)axes[targets[k]]; }
+  int a = naxes - 1;
+  while (a >= 0 && axes[a] == 1) --a;
+  if (a < 0 || !is_t[a]) return false;
+  // inner target run (contiguous, innermost)
+  const int inner_hi = a;
+  uint64_t lseg = 1;
+  while (a >= 0 && (is_t[a] || axes[a] == 1)) { if (is_t[a]) lseg *= (uint64_t)axes[a]; --a; }
+  const int inner_lo = a + 1;
+  // adjacent rest run
+  uint64_t M = 1;
+  while (a >= 0 && !is_t[a]) { M *= (uint64_t)axes[a]; --a; }
+  const int outer_hi = a;  // axes [0, outer_hi] are "outer"
+  if (t > kBlockMaxT || lseg > 0xffffffffull || t / lseg > 64 || M < 2) return false;
+  g->t = (uint32_t)t;
+  g->lseg = (uint32_t)lseg;
+  g->nseg = (uint32_t)(t / lseg);
+  g->pitch = (uint32_t)(t | 1);
+  g->M = M;
+  // outer axes: targets enumerate segments (tensor order, first most significant), the
+  // rest forms the outer fiber map
+  int outer_t[kMaxAxes], n_ot = 0;
+  FiberMap& fm = g->outer;
+  fm.ng = 0;
+  fm.nfib = 1;
+  int i = 0;
+  while (i <= outer_hi) {
+    if (is_t[i]) { if (axes[i] > 1) outer_t[n_ot++] = i; ++i; continue; }
+    uint64_t size = 1;
+    int last = i;
+    while (i <= outer_hi && !is_t[i]) { size *= (uint64_t)axes[i]; last = i; ++i; }
+    if (size == 1) continue;
+    if (fm.ng >= kMaxGroups) return false;
+    fm.gsize[fm.ng] = size;
+    fm.gstride[fm.ng] = stride[last];
+    fm.nfib *= size;
+    ++fm.ng;
+  }
+  for (uint32_t s = 0; s < g->nseg; ++s) {
+    uint32_t rem = s;
+    int64_t off = 0;
+    for (int k = n_ot - 1; k >= 0; --k) {
+      const uint32_t d = (uint32_t)axes[outer_t[k]];
+      off += (int64_t)(rem % d) * stride[outer_t[k]];
+      rem /= d;
+    }
+    g->seg_off[s] = off;
+  }
+  // shared-memory position of operator index j: inner-run axes keep their contiguous
+  // strides, outer target axes step by lseg in segment order
+  smem_tm->nt = nt;
+  smem_tm->t = (uint32_t)t;
+  for (int k = 0; k < nt; ++k) {
+    const int ax = targets[k];
+    smem_tm->tdim[k] = (uint32_t)axes[ax];
+    if (ax >= inner_lo && ax <= inner_hi) {
+      smem_tm->tstride[k] = stride[ax];  // innermost run: global strides ARE the in-row strides
+    } else {
+      int64_t st = (int64_t)lseg;
+      for (int q = n_ot - 1; q >= 0 && outer_t[q] != ax; --q) st *= axes[outer_t[q]];
+      smem_tm->tstride[k] = axes[ax] > 1 ? st : 0;
+    }
+  }
+  return true;
+}
+
+template <typename V>
+static int launch_blocks_seg_t(const V* in, V* out, const V* op, const SegGeom& g, const TargetMap& stm,
+                               bool conj_op, BlockDesc* d, cudaStream_t s) {
+  PW_TRY(build_block_desc_t<V>(op, g.t, conj_op, stm, &d->mem, &d->arr, s));
+  d->hdr = d->arr.hdr;
+  d->staged = true;
+  const size_t per_warp = (size_t)32 * g.pitch * sizeof(V);
+  int warps = (int)((72 * 1024) / per_warp);
+  if (warps < 1) return PW_ERR_UNSUPPORTED;
+  if (warps > 8) warps = 8;
+  const size_t smem = per_warp * warps;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    PW_CUDA(cudaFuncSetAttribute(k_apply_blocks_seg<V, kBlockMaxN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  const uint64_t ntasks = g.outer.nfib * ((g.M + 31) / 32);
+  int ctas = (int)((200 * 1024) / (smem + 1024));
+  if (ctas > 8) ctas = 8;
+  uint64_t grid = (ntasks + warps - 1) / warps;
+  if (grid > (uint64_t)kNumSMs * ctas) grid = (uint64_t)kNumSMs * ctas;
+  const BlockArrays& A = d->arr;
+  k_apply_blocks_seg<V, kBlockMaxN><<<(unsigned)grid, warps * 32, smem, s>>>(
+      in, out, g, A.hdr, A.blocks, A.offs, (const V*)A.vals, A.zero_offs);
+  PW_LAUNCHED();
+  g_paths[4].fetch_add(1, std::memory_order_relaxed);
+  return PW_OK;
+}
+
+int launch_blocks_seg(const void* in, void* out, const void* op, const int64_t* axes, int naxes,
+                      const int* targets, int nt, int dtype, bool conj_op, BlockDesc* desc,
+                      cudaStream_t stream) {
+  if (in == out) return PW_ERR_UNSUPPORTED;
+  SegGeom g;
+  TargetMap stm;
+  if (!plan_seg(axes, naxes, targets, nt, &g, &stm)) return PW_ERR_UNSUPPORTED;
+  if (dtype == PW_C128)
+    return launch_blocks_seg_t<double2>((const double2*)in, (double2*)out, (const double2*)op, g, stm, conj_op, desc, stream);
+  if (dtype == PW_C64)
+    return launch_blocks_seg_t<float2>((const float2*)in, (float2*)out, (const float2*)op, g, stm, conj_op, desc, stream);
   return PW_ERR_INVALID;
 }
 

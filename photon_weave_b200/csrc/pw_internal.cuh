@@ -174,6 +174,7 @@ struct Options {
   std::atomic<int> contig_kernel{1};           // warp-transposing kernel for contiguous fibers
   std::atomic<int> fuse_pairs{0};              // circuit entry points fuse adjacent single-axis ops
   std::atomic<int> mat_pair_max_d{4};          // single-pass U rho U^dagger register tile up to this d
+  std::atomic<int> seg_kernel{1};              // warp-staged block kernel for innermost-target layouts
   std::atomic<int> nstage{0};                  // tiled kernel pipeline depth (0 = auto)
   std::atomic<int> blocks_min_elems{1 << 18};  // below this, skip structure analysis
 };

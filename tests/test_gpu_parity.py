@@ -97,6 +97,11 @@ SHAPES = [
     ((7, 1, 3), (0,)),            # singleton axis
     ((64, 2), (0, 1)),            # Jaynes-Cummings shape: everything is a target, t = 128
     ((3, 4, 5, 2), (1, 2)),
+    ((7, 6, 6), (1, 2)),          # innermost contiguous target run (staged block kernel)
+    ((4, 3, 6, 6), (3, 2)),       # same, operator order reversed
+    ((6, 5, 6), (2, 0)),          # innermost + outermost targets: segmented fibers
+    ((3, 6, 2, 6), (3, 1)),
+    ((40, 6, 6), (2, 1)),         # more than one warp chunk, partial last chunk
 ]
 
 
@@ -147,6 +152,30 @@ def test_apply_matrix_and_kraus_parity(ad, dims, targets, cdtype):
     # list-of-operators input (state/utils/operations.py:260 stacks a Python list)
     outl = host(ad.apply_kraus_matrix(dims, targets, dev(rho), [dev(k) for k in kr]))
     assert rel_err(outl, refk) < TOL[cdtype]
+
+
+def test_structured_operators_on_innermost_axes(ad):
+    """Beam splitter / shift / diagonal operators (block structured) with the innermost axis
+    among the targets, plus a loss channel on the LAST mode of a density matrix."""
+    dims = (37, 6, 6)
+    N = math.prod(dims)
+    psi = ops.random_state(N, 3)
+    bs = ops.beam_splitter(6, 6, 0.7)
+    shift = np.kron(ops.creation_operator(6), ops.annihilation_operator(6))  # not in-place safe
+    diag = np.diag(np.exp(1j * np.arange(36) * 0.1))
+    for op, tg in [(bs, (1, 2)), (bs, (2, 1)), (shift, (1, 2)), (diag, (1, 2)), (bs, (2, 0))]:
+        t = math.prod(dims[i] for i in tg)
+        if op.shape[0] != t:
+            op = ops.beam_splitter(6, 37, 0.3) if t == 6 * 37 else op
+        out = host(ad.apply_operation_vector(dims, tg, dev(psi), dev(op)))
+        assert rel_err(out, oad.apply_operation_vector(dims, tg, psi, op, True)) < 1e-12
+    rho = ops.random_density(40 * 8, 4)
+    ks = ops.loss_channel(8, 0.15)
+    out = host(ad.apply_kraus_matrix((40, 8), (1,), dev(rho), dev(ks)))
+    assert rel_err(out, oad.apply_kraus_matrix((40, 8), (1,), rho, ks, True)) < 1e-12
+    ph = ops.phase_operator(8, 0.4)
+    out = host(ad.apply_operation_matrix((40, 8), (1,), dev(rho), dev(ph)))
+    assert rel_err(out, oad.apply_operation_matrix((40, 8), (1,), rho, ph, True)) < 1e-12
 
 
 def test_loss_channel_preserves_trace_and_matches_oracle(ad):
