@@ -107,6 +107,8 @@ k_build_blocks(const V* __restrict__ op, const uint32_t t, const bool conj_op, c
       vo += nr * nc;
     }
     hdr->nblocks = s_nblocks;
+    hdr->n_offs = io;
+    hdr->n_vals = (s_maxn <= kBlockMaxN) ? vo : 0;
     hdr->maxn = s_maxn;
     hdr->nzero = s_nzero;
     hdr->usable = (s_maxn <= kBlockMaxN) ? 1 : 0;
@@ -153,40 +155,27 @@ k_build_blocks(const V* __restrict__ op, const uint32_t t, const bool conj_op, c
 }
 
 // ---- apply -----------------------------------------------------------------------------
-template <typename V, int MAXN>
-__global__ void __launch_bounds__(256, (sizeof(V) == 16 ? (MAXN <= 4 ? 4 : 3) : 4))
-k_apply_blocks(const V* __restrict__ in, V* __restrict__ out, const FiberMap fm,
-               const BlockDescHeader* __restrict__ hdr, const int4* __restrict__ blocks,
-               const int64_t* __restrict__ offs, const V* __restrict__ vals,
-               const int64_t* __restrict__ zero_offs) {
-  // each instantiation owns max block sizes in (MAXN/2, MAXN] (MAXN = 2 also takes 0..1)
-  constexpr int LO = MAXN == 2 ? -1 : MAXN / 2;
-  const int maxn = hdr->maxn;
-  if (!hdr->usable || maxn <= LO || maxn > MAXN) return;
-  const int nblocks = hdr->nblocks, nzero = hdr->nzero;
+constexpr uint32_t kDescSmemCap = 24 * 1024;
+
+template <typename V>
+__global__ void __launch_bounds__(256, 3)
+k_apply_blocks(const V* __restrict__ in, V* __restrict__ out, const FiberMap fm, const BlockArrays A) {
+  extern __shared__ __align__(16) unsigned char s_desc[];
+  if (!A.hdr->usable) return;
+  const DescView<V> dv = desc_view<V>(A, s_desc, kDescSmemCap);
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < fm.nfib; f += stride) {
     const int64_t base = fm.base(f);
     const V* src = in + base;
     V* dst = out + base;
-    for (int b = 0; b < nblocks; ++b) {
-      const int4 h = __ldg(blocks + b);
-      const int nr = h.x, nc = h.y;
-      const int64_t* bo = offs + h.z;
-      const V* bv = vals + h.w;
-      V x[MAXN];
-#pragma unroll
-      for (int j = 0; j < MAXN; ++j)
-        if (j < nc) x[j] = src[__ldg(bo + j)];
-      for (int a = 0; a < nr; ++a) {
-        V acc = czero<V>();
-#pragma unroll
-        for (int j = 0; j < MAXN; ++j)
-          if (j < nc) cfma(acc, __ldg(bv + a * nc + j), x[j]);
-        dst[__ldg(bo + nc + a)] = acc;
-      }
+    for (int b = 0; b < dv.nblocks; ++b) {
+      const int4 h = dv.blocks[b];
+      const int64_t* bo = dv.offs + h.z;
+      block_product<V>(dv.vals + h.w, h.x, h.y,
+                       [&](int j) { return src[bo[j]]; },
+                       [&](int a, V v) { dst[bo[h.y + a]] = v; });
     }
-    for (int z = 0; z < nzero; ++z) dst[__ldg(zero_offs + z)] = czero<V>();
+    for (int z = 0; z < dv.nzero; ++z) dst[dv.zero_offs[z]] = czero<V>();
   }
 }
 
@@ -213,17 +202,15 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
 }
 
-template <typename V, int MAXN>
+template <typename V>
 __global__ void __launch_bounds__(256)
 k_apply_blocks_seg(const V* __restrict__ in, V* __restrict__ out, const SegGeom g,
-                   const BlockDescHeader* __restrict__ hdr, const int4* __restrict__ blocks,
-                   const int64_t* __restrict__ offs, const V* __restrict__ vals,
-                   const int64_t* __restrict__ zero_offs) {
-  if (!hdr->seg_handled) return;
+                   const BlockArrays A, const uint32_t desc_cap) {
+  if (!A.hdr->seg_handled) return;
   extern __shared__ __align__(16) unsigned char s_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  V* buf = (V*)s_raw + (size_t)warp * 32 * g.pitch;
-  const int nblocks = hdr->nblocks, nzero = hdr->nzero;
+  const DescView<V> dv = desc_view<V>(A, s_raw, desc_cap);
+  V* buf = (V*)(s_raw + desc_cap) + (size_t)warp * 32 * g.pitch;
   const uint64_t chunks = (g.M + 31) / 32;
   const uint64_t ntasks = g.outer.nfib * chunks;
   // lane-constant decomposition of the coalesced copy index e = it*32 + lane into
@@ -252,24 +239,14 @@ k_apply_blocks_seg(const V* __restrict__ in, V* __restrict__ out, const SegGeom 
     // ---- compute: one fiber per lane, blocks applied in place
     if ((uint32_t)lane < nvalid) {
       V* fib = buf + (size_t)lane * g.pitch;
-      for (int b = 0; b < nblocks; ++b) {
-        const int4 h = __ldg(blocks + b);
-        const int nr = h.x, nc = h.y;
-        const int64_t* bo = offs + h.z;
-        const V* bv = vals + h.w;
-        V x[MAXN];
-#pragma unroll
-        for (int j = 0; j < MAXN; ++j)
-          if (j < nc) x[j] = fib[(int32_t)__ldg(bo + j)];
-        for (int a = 0; a < nr; ++a) {
-          V acc = czero<V>();
-#pragma unroll
-          for (int j = 0; j < MAXN; ++j)
-            if (j < nc) cfma(acc, __ldg(bv + a * nc + j), x[j]);
-          fib[(int32_t)__ldg(bo + nc + a)] = acc;
-        }
+      for (int b = 0; b < dv.nblocks; ++b) {
+        const int4 h = dv.blocks[b];
+        const int64_t* bo = dv.offs + h.z;
+        block_product<V>(dv.vals + h.w, h.x, h.y,
+                         [&](int j) { return fib[(int32_t)bo[j]]; },
+                         [&](int a, V v) { fib[(int32_t)bo[h.y + a]] = v; });
       }
-      for (int z = 0; z < nzero; ++z) fib[(int32_t)__ldg(zero_offs + z)] = czero<V>();
+      for (int z = 0; z < dv.nzero; ++z) fib[(int32_t)dv.zero_offs[z]] = czero<V>();
     }
     __syncwarp();
     // ---- stream back, same coalesced row pattern
@@ -320,13 +297,8 @@ static int launch_blocks_t(const V* in, V* out, const V* op, const Plan& p, bool
   PW_TRY(build_block_desc_t<V>(op, p.tm.t, conj_op, p.tm, &d->mem, &d->arr, s));
   d->hdr = d->arr.hdr;
   const BlockArrays& A = d->arr;
-  const int grid = grid_for(p.fm.nfib, 256, 8);
-  // three instantiations cover max block sizes [0,2], (2,4], (4,8]; two of them exit at once
-  k_apply_blocks<V, 2><<<grid, 256, 0, s>>>(in, out, p.fm, A.hdr, A.blocks, A.offs, (const V*)A.vals, A.zero_offs);
-  PW_LAUNCHED();
-  k_apply_blocks<V, 4><<<grid, 256, 0, s>>>(in, out, p.fm, A.hdr, A.blocks, A.offs, (const V*)A.vals, A.zero_offs);
-  PW_LAUNCHED();
-  k_apply_blocks<V, 8><<<grid, 256, 0, s>>>(in, out, p.fm, A.hdr, A.blocks, A.offs, (const V*)A.vals, A.zero_offs);
+  const int grid = grid_for(p.fm.nfib, 256, 3);
+  k_apply_blocks<V><<<grid, 256, kDescSmemCap, s>>>(in, out, p.fm, A);
   PW_LAUNCHED();
   g_paths[4].fetch_add(1, std::memory_order_relaxed);
   return PW_OK;
@@ -425,23 +397,26 @@ static int launch_blocks_seg_t(const V* in, V* out, const V* op, const SegGeom& 
   d->hdr = d->arr.hdr;
   d->staged = true;
   const size_t per_warp = (size_t)32 * g.pitch * sizeof(V);
-  int warps = (int)((72 * 1024) / per_warp);
+  // descriptor copy (worst case for `usable` operators: t blocks, 2t offsets, 8t values)
+  uint32_t desc_cap = (uint32_t)(g.t * 16 + 2 * g.t * 8 + g.t * 8 + 8 * g.t * sizeof(V) + 64);
+  desc_cap = (desc_cap + 127u) & ~127u;
+  int warps = (int)((110 * 1024 - desc_cap) / per_warp);
   if (warps < 1) return PW_ERR_UNSUPPORTED;
   if (warps > 8) warps = 8;
-  const size_t smem = per_warp * warps;
+  const size_t smem = per_warp * warps + desc_cap;
   static thread_local bool attr_set = false;
   if (!attr_set) {
-    PW_CUDA(cudaFuncSetAttribute(k_apply_blocks_seg<V, kBlockMaxN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    PW_CUDA(cudaFuncSetAttribute(k_apply_blocks_seg<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   const uint64_t ntasks = g.outer.nfib * ((g.M + 31) / 32);
-  int ctas = (int)((200 * 1024) / (smem + 1024));
+  int ctas = (int)((227 * 1024) / (smem + 1024));
   if (ctas > 8) ctas = 8;
+  if (ctas < 1) ctas = 1;
   uint64_t grid = (ntasks + warps - 1) / warps;
   if (grid > (uint64_t)kNumSMs * ctas) grid = (uint64_t)kNumSMs * ctas;
   const BlockArrays& A = d->arr;
-  k_apply_blocks_seg<V, kBlockMaxN><<<(unsigned)grid, warps * 32, smem, s>>>(
-      in, out, g, A.hdr, A.blocks, A.offs, (const V*)A.vals, A.zero_offs);
+  k_apply_blocks_seg<V><<<(unsigned)grid, warps * 32, smem, s>>>(in, out, g, A, desc_cap);
   PW_LAUNCHED();
   g_paths[4].fetch_add(1, std::memory_order_relaxed);
   return PW_OK;

@@ -14,7 +14,8 @@ struct BlockDescHeader {
   int usable;  // 1: the block kernel handles this operator; fallback kernels must exit
   int inplace_safe;  // 1: no block writes a position a DIFFERENT block still has to read
   int seg_handled;   // usable && inplace_safe: the staged (segmented) kernel took it
-  int pad[2];
+  int n_offs;        // entries used in offs[]
+  int n_vals;        // entries used in vals[]
 };
 
 // device pointers of one analysed operator
@@ -35,6 +36,81 @@ struct BlockDesc {
     return hdr ? (staged ? &hdr->seg_handled : &hdr->usable) : nullptr;
   }
 };
+
+#ifdef __CUDACC__
+// Device view of a descriptor (global memory, or a shared-memory copy made by the CTA).
+template <typename V>
+struct DescView {
+  const int4* blocks;
+  const int64_t* offs;
+  const V* vals;
+  const int64_t* zero_offs;
+  int nblocks, nzero;
+};
+
+// bytes a shared-memory copy of the descriptor needs (16-byte aligned sections)
+__device__ __forceinline__ uint32_t desc_smem_bytes(const BlockDescHeader* h, uint32_t vsize) {
+  auto al = [](uint32_t x) { return (x + 15u) & ~15u; };
+  return al((uint32_t)h->nblocks * 16u) + al((uint32_t)h->n_offs * 8u) +
+         al((uint32_t)h->nzero * 8u) + al((uint32_t)h->n_vals * vsize);
+}
+
+// Copies the descriptor into `smem` when it fits `cap` bytes (all threads of the CTA must
+// call this; contains a __syncthreads) and returns a view of whichever copy to use.
+template <typename V>
+__device__ __forceinline__ DescView<V> desc_view(const BlockArrays& A, unsigned char* smem, uint32_t cap) {
+  DescView<V> v;
+  const BlockDescHeader* h = A.hdr;
+  v.nblocks = h->nblocks;
+  v.nzero = h->nzero;
+  v.blocks = A.blocks; v.offs = A.offs; v.vals = (const V*)A.vals; v.zero_offs = A.zero_offs;
+  const uint32_t need = desc_smem_bytes(h, (uint32_t)sizeof(V));
+  if (smem != nullptr && need <= cap) {
+    auto al = [](uint32_t x) { return (x + 15u) & ~15u; };
+    int4* sb = (int4*)smem;
+    int64_t* so = (int64_t*)(smem + al((uint32_t)h->nblocks * 16u));
+    int64_t* sz = (int64_t*)((unsigned char*)so + al((uint32_t)h->n_offs * 8u));
+    V* sv = (V*)((unsigned char*)sz + al((uint32_t)h->nzero * 8u));
+    for (int i = threadIdx.x; i < h->nblocks; i += blockDim.x) sb[i] = A.blocks[i];
+    for (int i = threadIdx.x; i < h->n_offs; i += blockDim.x) so[i] = A.offs[i];
+    for (int i = threadIdx.x; i < h->nzero; i += blockDim.x) sz[i] = A.zero_offs[i];
+    for (int i = threadIdx.x; i < h->n_vals; i += blockDim.x) sv[i] = ((const V*)A.vals)[i];
+    v.blocks = sb; v.offs = so; v.vals = sv; v.zero_offs = sz;
+  }
+  __syncthreads();
+  return v;
+}
+
+// y[rows] = B (nr x NC, dense) x[cols]; NC is a compile-time constant so the NC inputs
+// live in registers without predication.
+template <typename V, int NC, typename LoadX, typename StoreY>
+__device__ __forceinline__ void block_product_nc(const V* __restrict__ bv, const int nr, LoadX ldx, StoreY sty) {
+  V x[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) x[j] = ldx(j);
+  for (int a = 0; a < nr; ++a) {
+    V acc = czero<V>();
+#pragma unroll
+    for (int j = 0; j < NC; ++j) cfma(acc, bv[a * NC + j], x[j]);
+    sty(a, acc);
+  }
+}
+
+template <typename V, typename LoadX, typename StoreY>
+__device__ __forceinline__ void block_product(const V* __restrict__ bv, const int nr, const int nc, LoadX ldx, StoreY sty) {
+  switch (nc) {
+    case 1: block_product_nc<V, 1>(bv, nr, ldx, sty); break;
+    case 2: block_product_nc<V, 2>(bv, nr, ldx, sty); break;
+    case 3: block_product_nc<V, 3>(bv, nr, ldx, sty); break;
+    case 4: block_product_nc<V, 4>(bv, nr, ldx, sty); break;
+    case 5: block_product_nc<V, 5>(bv, nr, ldx, sty); break;
+    case 6: block_product_nc<V, 6>(bv, nr, ldx, sty); break;
+    case 7: block_product_nc<V, 7>(bv, nr, ldx, sty); break;
+    case 8: block_product_nc<V, 8>(bv, nr, ldx, sty); break;
+    default: break;  // nc == 0 cannot occur (blocks have >= 1 column); nc > 8 is not `usable`
+  }
+}
+#endif  // __CUDACC__
 
 // Enqueues the structure analysis of a dense t x t operator (t <= kBlockMaxT); element
 // offsets come from `tm` (global strides for the direct kernel, tile strides for the

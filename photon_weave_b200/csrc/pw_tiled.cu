@@ -392,11 +392,11 @@ __device__ __forceinline__ void run_pass(const V* __restrict__ src, V* __restric
 // C_b).  Work item = (block, fiber), fibers fastest, so a warp mostly shares one block:
 // descriptor loads are broadcast, the <= MAXN inputs of the block are gathered from the
 // tile into registers, the dense product runs against broadcast values.
-template <typename V, int MAXN>
+template <typename V>
 __device__ __noinline__ void run_pass_blocks(const V* __restrict__ src, V* __restrict__ dst,
-                                                const uint32_t nfib,
-                                                const int32_t* __restrict__ s_foff,
-                                                const BlockArrays A) {
+                                             const uint32_t nfib,
+                                             const int32_t* __restrict__ s_foff,
+                                             const BlockArrays A) {
   const int nblocks = A.hdr->nblocks, nzero = A.hdr->nzero;
   const V* vals = (const V*)A.vals;
   const uint32_t items = (uint32_t)nblocks * nfib;
@@ -404,20 +404,10 @@ __device__ __noinline__ void run_pass_blocks(const V* __restrict__ src, V* __res
     const uint32_t b = it / nfib;
     const int32_t fo = s_foff[it - b * nfib];
     const int4 h = __ldg(A.blocks + b);
-    const int nr = h.x, nc = h.y;
     const int64_t* bo = A.offs + h.z;
-    const V* bv = vals + h.w;
-    V x[MAXN];
-#pragma unroll
-    for (int j = 0; j < MAXN; ++j)
-      if (j < nc) x[j] = src[fo + (int32_t)__ldg(bo + j)];
-    for (int a = 0; a < nr; ++a) {
-      V acc = czero<V>();
-#pragma unroll
-      for (int j = 0; j < MAXN; ++j)
-        if (j < nc) cfma(acc, __ldg(bv + a * nc + j), x[j]);
-      dst[fo + (int32_t)__ldg(bo + nc + a)] = acc;
-    }
+    block_product<V>(vals + h.w, h.x, h.y,
+                     [&](int j) { return src[fo + (int32_t)__ldg(bo + j)]; },
+                     [&](int a, V v) { dst[fo + (int32_t)__ldg(bo + h.y + a)] = v; });
   }
   const uint32_t zitems = (uint32_t)nzero * nfib;
   for (uint32_t it = threadIdx.x; it < zitems; it += blockDim.x) {
@@ -504,9 +494,9 @@ k_tiled(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
     V* res;
     if (P.mode == kModeMatrixTwoSided) {
       if (BLOCKS) {
-        run_pass_blocks<V, kBlockMaxN>(in_tile, w0, g.kind[0].nfib, s_foff0, P.blk[0]);
+        run_pass_blocks<V>(in_tile, w0, g.kind[0].nfib, s_foff0, P.blk[0]);
         __syncthreads();
-        run_pass_blocks<V, kBlockMaxN>(w0, w1, g.kind[1].nfib, s_foff1, P.blk[1]);
+        run_pass_blocks<V>(w0, w1, g.kind[1].nfib, s_foff1, P.blk[1]);
       } else {
         for (int k = 0; k < P.K; ++k) {
           const int32_t* rp = P.rowptr + (size_t)k * (g.kind[0].t + 1);
@@ -520,7 +510,7 @@ k_tiled(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUten
       res = w1;
     } else {
       if (BLOCKS)
-        run_pass_blocks<V, kBlockMaxN>(in_tile, w0, g.kind[0].nfib, s_foff0, P.blk[0]);
+        run_pass_blocks<V>(in_tile, w0, g.kind[0].nfib, s_foff0, P.blk[0]);
       else if (P.mode == kModeVectorConj)
         run_pass<V, true>(in_tile, w0, g.kind[0], 0, s_foff0, s_toff0, P.rowptr, ents, false);
       else
