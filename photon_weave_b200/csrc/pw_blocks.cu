@@ -163,17 +163,41 @@ k_apply_blocks(const V* __restrict__ in, V* __restrict__ out, const FiberMap fm,
   extern __shared__ __align__(16) unsigned char s_desc[];
   if (!A.hdr->usable) return;
   const DescView<V> dv = desc_view<V>(A, s_desc, kDescSmemCap);
+  const bool scalar_blocks = A.hdr->maxn == 1;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < fm.nfib; f += stride) {
     const int64_t base = fm.base(f);
     const V* src = in + base;
     V* dst = out + base;
-    for (int b = 0; b < dv.nblocks; ++b) {
-      const int4 h = dv.blocks[b];
-      const int64_t* bo = dv.offs + h.z;
-      block_product<V>(dv.vals + h.w, h.x, h.y,
-                       [&](int j) { return src[bo[j]]; },
-                       [&](int a, V v) { dst[bo[h.y + a]] = v; });
+    if (scalar_blocks) {
+      // every block is 1 x 1 (diagonal / shift / generalized permutation): out[r_b] = v_b in[c_b];
+      // blocks are laid out back to back (offs = c0 r0 c1 r1 ..., vals = v0 v1 ...), and the
+      // loads are independent, so issue four at a time
+      int b = 0;
+      for (; b + 4 <= dv.nblocks; b += 4) {
+        V x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = src[dv.offs[2 * (b + u)]];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          V acc = czero<V>();
+          cfma(acc, dv.vals[b + u], x[u]);
+          dst[dv.offs[2 * (b + u) + 1]] = acc;
+        }
+      }
+      for (; b < dv.nblocks; ++b) {
+        V acc = czero<V>();
+        cfma(acc, dv.vals[b], src[dv.offs[2 * b]]);
+        dst[dv.offs[2 * b + 1]] = acc;
+      }
+    } else {
+      for (int b = 0; b < dv.nblocks; ++b) {
+        const int4 h = dv.blocks[b];
+        const int64_t* bo = dv.offs + h.z;
+        block_product<V>(dv.vals + h.w, h.x, h.y,
+                         [&](int j) { return src[bo[j]]; },
+                         [&](int a, V v) { dst[bo[h.y + a]] = v; });
+      }
     }
     for (int z = 0; z < dv.nzero; ++z) dst[dv.zero_offs[z]] = czero<V>();
   }
