@@ -148,12 +148,17 @@ inline int grid_for(uint64_t work_items, int block, int max_ctas_per_sm) {
   return (int)g;
 }
 
+// Keep freed scratch memory cached in the device's default pool (the default release
+// threshold of 0 hands multi-GB scratch back to the driver at every synchronisation).
+void keep_pool_memory();
+
 // Stream-ordered scratch buffer (freed on the same stream when it goes out of scope).
 struct Scratch {
   void* p = nullptr;
   cudaStream_t s = nullptr;
   int alloc(size_t bytes, cudaStream_t stream) {
     s = stream;
+    keep_pool_memory();
     if (cudaMallocAsync(&p, bytes ? bytes : 16, stream) != cudaSuccess) {
       p = nullptr;
       (void)cudaGetLastError();

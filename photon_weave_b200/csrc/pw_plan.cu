@@ -7,6 +7,20 @@ std::atomic<uint64_t> g_launches{0};
 std::atomic<uint64_t> g_paths[5];
 thread_local int g_last_cuda_error = 0;
 
+void keep_pool_memory() {
+  static thread_local int done_for = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return; }
+  if (done_for == dev) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t thr = ~0ull;
+    (void)cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  (void)cudaGetLastError();
+  done_for = dev;
+}
+
 static int build_generic(const int64_t* dims, int n, const int* targets, int nt, Plan* plan) {
   if (n < 1 || n > kMaxAxes || nt < 0 || nt > kMaxTargets || !dims || (nt && !targets))
     return PW_ERR_INVALID;
