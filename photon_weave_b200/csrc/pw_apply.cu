@@ -49,15 +49,17 @@ k_apply_small(const V* in, V* out, const V* __restrict__ op, const FiberMap fm,
     asm volatile("" : "+r"(zero));
     const V* sop = s_op + zero;
     V x[T];
+    // streaming data, no reuse: L2-only loads avoid L1's sector over-fetch on rows that are
+    // not 128 B aligned (measured: 12 % extra DRAM reads with default caching at R = 36)
 #pragma unroll
-    for (int j = 0; j < T; ++j) x[j] = in[base + s_off[j]];
+    for (int j = 0; j < T; ++j) x[j] = __ldcg(in + base + s_off[j]);
 #pragma unroll
     for (int a = 0; a < T; ++a) {
       V acc = czero<V>();
       if (ACC) acc = out[base + s_off[a]];
 #pragma unroll
       for (int b = 0; b < T; ++b) cfma(acc, sop[a * T + b], x[b]);
-      out[base + s_off[a]] = acc;
+      __stcg(out + base + s_off[a], acc);
     }
   }
 }

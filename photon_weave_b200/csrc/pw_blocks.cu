@@ -177,29 +177,29 @@ k_apply_blocks(const V* __restrict__ in, V* __restrict__ out, const FiberMap fm,
       for (; b + 4 <= dv.nblocks; b += 4) {
         V x[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) x[u] = src[dv.offs[2 * (b + u)]];
+        for (int u = 0; u < 4; ++u) x[u] = __ldcg(src + dv.offs[2 * (b + u)]);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           V acc = czero<V>();
           cfma(acc, dv.vals[b + u], x[u]);
-          dst[dv.offs[2 * (b + u) + 1]] = acc;
+          __stcg(dst + dv.offs[2 * (b + u) + 1], acc);
         }
       }
       for (; b < dv.nblocks; ++b) {
         V acc = czero<V>();
-        cfma(acc, dv.vals[b], src[dv.offs[2 * b]]);
-        dst[dv.offs[2 * b + 1]] = acc;
+        cfma(acc, dv.vals[b], __ldcg(src + dv.offs[2 * b]));
+        __stcg(dst + dv.offs[2 * b + 1], acc);
       }
     } else {
       for (int b = 0; b < dv.nblocks; ++b) {
         const int4 h = dv.blocks[b];
         const int64_t* bo = dv.offs + h.z;
         block_product<V>(dv.vals + h.w, h.x, h.y,
-                         [&](int j) { return src[bo[j]]; },
-                         [&](int a, V v) { dst[bo[h.y + a]] = v; });
+                         [&](int j) { return __ldcg(src + bo[j]); },
+                         [&](int a, V v) { __stcg(dst + bo[h.y + a], v); });
       }
     }
-    for (int z = 0; z < dv.nzero; ++z) dst[dv.zero_offs[z]] = czero<V>();
+    for (int z = 0; z < dv.nzero; ++z) __stcg(dst + dv.zero_offs[z], czero<V>());
   }
 }
 
