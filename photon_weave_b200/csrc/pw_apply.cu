@@ -102,7 +102,7 @@ k_apply_small_contig(const V* in, V* out, const V* __restrict__ op, const uint64
 #pragma unroll
     for (int i = 0; i < T; ++i) {
       const uint64_t e = base + i * 32 + lane;
-      if (e < total) r[i] = in[e];
+      if (e < total) r[i] = __ldcg(in + e);
     }
 #pragma unroll
     for (int i = 0; i < T; ++i) buf[pad_idx<T>(i * 32 + lane)] = r[i];
@@ -125,7 +125,7 @@ k_apply_small_contig(const V* in, V* out, const V* __restrict__ op, const uint64
 #pragma unroll
     for (int i = 0; i < T; ++i) {
       const uint64_t e = base + i * 32 + lane;
-      if (e < total) out[e] = buf[pad_idx<T>(i * 32 + lane)];
+      if (e < total) __stcg(out + e, buf[pad_idx<T>(i * 32 + lane)]);
     }
     __syncwarp();
   }
@@ -163,7 +163,7 @@ k_apply_pair(const V* in, V* out, const V* __restrict__ opa, const V* __restrict
     for (int j = 0; j < D; ++j) {
       V c[D];
 #pragma unroll
-      for (int b = 0; b < D; ++b) c[b] = in[base + s_off[b * D + j]];
+      for (int b = 0; b < D; ++b) c[b] = __ldcg(in + base + s_off[b * D + j]);
 #pragma unroll
       for (int a = 0; a < D; ++a) {
         V acc = czero<V>();
@@ -180,7 +180,7 @@ k_apply_pair(const V* in, V* out, const V* __restrict__ opa, const V* __restrict
         V acc = czero<V>();
 #pragma unroll
         for (int b = 0; b < D; ++b) cfma(acc, sb[a * D + b], x[i][b]);
-        out[base + s_off[i * D + a]] = acc;
+        __stcg(out + base + s_off[i * D + a], acc);
       }
     }
   }
@@ -226,7 +226,7 @@ k_apply_pair_split(const V* in, V* out, const V* __restrict__ opa, const V* __re
     for (int jl = 0; jl < C; ++jl) {
       V c[D];
 #pragma unroll
-      for (int b = 0; b < D; ++b) c[b] = live ? in[base + s_off[b * D + q * C + jl]] : czero<V>();
+      for (int b = 0; b < D; ++b) c[b] = live ? __ldcg(in + base + s_off[b * D + q * C + jl]) : czero<V>();
 #pragma unroll
       for (int a = 0; a < D; ++a) {
         V acc = czero<V>();
@@ -250,7 +250,7 @@ k_apply_pair_split(const V* in, V* out, const V* __restrict__ opa, const V* __re
         V acc = czero<V>();
 #pragma unroll
         for (int b = 0; b < D; ++b) cfma(acc, sb[(q * C + al) * D + b], y[b]);
-        if (live) out[base + s_off[i * D + q * C + al]] = acc;
+        if (live) __stcg(out + base + s_off[i * D + q * C + al], acc);
       }
     }
   }

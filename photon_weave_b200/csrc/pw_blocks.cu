@@ -278,7 +278,7 @@ k_apply_blocks_seg(const V* __restrict__ in, V* __restrict__ out, const SegGeom 
       V* dstg = out + base + g.seg_off[s];
       uint32_t q = (uint32_t)lane / g.lseg, r = (uint32_t)lane % g.lseg;
       for (uint32_t e = lane; e < row_elems; e += 32) {
-        dstg[e] = buf[(size_t)q * g.pitch + s * g.lseg + r];
+        __stcg(dstg + e, buf[(size_t)q * g.pitch + s * g.lseg + r]);
         q += qa; r += rb;
         if (r >= g.lseg) { r -= g.lseg; ++q; }
       }

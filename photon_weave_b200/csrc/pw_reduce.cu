@@ -137,7 +137,7 @@ k_probs_small(const V* __restrict__ x, const FiberMap fm, const TargetMap tm, co
     const int64_t base = fm.base(f) * mult;
     V v[T];
 #pragma unroll
-    for (int j = 0; j < T; ++j) v[j] = x[base + s_off[j]];
+    for (int j = 0; j < T; ++j) v[j] = __ldcg(x + base + s_off[j]);
 #pragma unroll
     for (int j = 0; j < T; ++j)
       acc[j] += DIAG ? (double)v[j].x : (double)v[j].x * v[j].x + (double)v[j].y * v[j].y;
@@ -305,7 +305,7 @@ k_reduced_small(const V* __restrict__ x, const FiberMap fm, const TargetMap tm,
     const int64_t base = fm.base(f);
     double vx[T], vy[T];
 #pragma unroll
-    for (int j = 0; j < T; ++j) { const V v = x[base + s_off[j]]; vx[j] = v.x; vy[j] = v.y; }
+    for (int j = 0; j < T; ++j) { const V v = __ldcg(x + base + s_off[j]); vx[j] = v.x; vy[j] = v.y; }
     int q = 0;
 #pragma unroll
     for (int a = 0; a < T; ++a)
