@@ -192,6 +192,29 @@ int pw_scale(void* x, int64_t count, const double* scale_dev, int dtype, void* s
 int pw_permute(const void* in, void* out, const int64_t* dims, int n, const int32_t* perm,
                int dtype, void* stream);
 
+/* out = the same tensor with dims[axis] = new_dim (zero padding or truncation); for a density
+ * matrix (is_matrix) both the row and the column copy of the subsystem are resized.
+ * Replaces ProductState.resize_fock (state/composite_envelope.py:495-585; the caller does the
+ * occupancy check with pw_probs_* before shrinking). */
+int pw_resize_axis(const void* in, void* out, const int64_t* dims, int n, int axis,
+                   int64_t new_dim, int is_matrix, int dtype, void* stream);
+
+/* out = kron(a, b) for row-major (rows x cols) operands; column vectors have cols = 1.
+ * Replaces kron_reduce in CompositeEnvelope.combine (core/ops.py:53-64,
+ * state/composite_envelope.py:915-948). */
+int pw_kron(const void* a, const void* b, void* out, int64_t rows_a, int64_t cols_a,
+            int64_t rows_b, int64_t cols_b, int dtype, void* stream);
+
+/* rho = psi psi^dagger (state_expand Vector -> Matrix, state/utils/state_transform.py:58-63). */
+int pw_expand_vec(const void* psi, void* rho, int64_t n, int dtype, void* stream);
+
+/* state_contract Matrix -> Vector (state/utils/state_transform.py:122-137) without rho@rho and
+ * eigh: info[0] = Tr(rho^2) = sum |rho_ij|^2, info[1] = Tr rho; *flag = |Tr(rho^2) - 1| < tol;
+ * when set, psi = the pure state with the global phase fixed so that psi[0] is real >= 0
+ * (the reference's convention).  info / flag are device pointers. */
+int pw_contract_mat(const void* rho, int64_t n, double tol, void* psi, double* info, int* flag,
+                    int dtype, void* stream);
+
 /* ---- multi-GPU: peer memory over NVLink (one process per GPU) ---------------------- */
 
 /* cudaMalloc + CUDA IPC export of a shard buffer; peers map it with pw_peer_open. */

@@ -25,4 +25,4 @@ the BASELINE shapes are unpinned by the reference itself (its tests never exceed
 independent dense ``kron`` construction at small sizes.
 """
 
-from . import einsum_strings, kernels_np, adapters_np, rng_threefry, operators  # noqa: F401
+from . import einsum_strings, kernels_np, adapters_np, rng_threefry, operators, layout_np  # noqa: F401

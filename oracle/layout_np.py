@@ -1,0 +1,60 @@
+"""
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+NumPy restatement of the layout / representation steps either side of an apply
+(SURVEY.md section 8f.2).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+
+def resize_fock_vector(dims, axis, new_dim, psi):
+    """state/composite_envelope.py:513-542 (pad with zeros / slice along one subsystem)."""
+    t = np.asarray(psi).reshape(dims)
+    if new_dim >= dims[axis]:
+        pad = [(0, 0)] * len(dims)
+        pad[axis] = (0, new_dim - dims[axis])
+        t = np.pad(t, pad, mode="constant")
+    else:
+        sl = [slice(None)] * len(dims)
+        sl[axis] = slice(0, new_dim)
+        t = t[tuple(sl)]
+    return np.ascontiguousarray(t).reshape(-1, 1)
+
+
+def resize_fock_matrix(dims, axis, new_dim, rho):
+    """The intended effect of state/composite_envelope.py:543-585: pad / slice the subsystem on
+    BOTH the row and the column side."""
+    n = len(dims)
+    t = np.asarray(rho).reshape(tuple(dims) + tuple(dims))
+    if new_dim >= dims[axis]:
+        pad = [(0, 0)] * (2 * n)
+        pad[axis] = pad[n + axis] = (0, new_dim - dims[axis])
+        t = np.pad(t, pad, mode="constant")
+    else:
+        sl = [slice(None)] * (2 * n)
+        sl[axis] = sl[n + axis] = slice(0, new_dim)
+        t = t[tuple(sl)]
+    nd = list(dims)
+    nd[axis] = new_dim
+    N = int(np.prod(nd))
+    return np.ascontiguousarray(t).reshape(N, N)
+
+
+def state_expand_vector(psi):
+    """state/utils/state_transform.py:58-63."""
+    v = np.asarray(psi).reshape(-1)
+    return np.outer(v, np.conj(v))
+
+
+def state_contract_matrix(rho, tol=1e-6):
+    """state/utils/state_transform.py:122-137 -> (state, success)."""
+    rho = np.asarray(rho)
+    if abs(np.trace(rho @ rho) - 1) < tol:
+        w, v = np.linalg.eigh(rho)
+        psi = v[:, int(np.argmax(w))].reshape(-1, 1)
+        psi = psi * np.exp(-1j * np.angle(psi[0]))
+        return psi, True
+    return rho, False

@@ -70,6 +70,10 @@ SIGNATURES = {
     "pw_norm_stats": (C.c_int, [_vp, C.c_int64, C.c_int, _vp, _vp]),
     "pw_scale": (C.c_int, [_vp, C.c_int64, _vp, C.c_int, _vp]),
     "pw_permute": (C.c_int, [_vp, _vp, _i64p, C.c_int, _i32p, C.c_int, _vp]),
+    "pw_resize_axis": (C.c_int, [_vp, _vp, _i64p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, _vp]),
+    "pw_kron": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, _vp]),
+    "pw_expand_vec": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, _vp]),
+    "pw_contract_mat": (C.c_int, [_vp, C.c_int64, C.c_double, _vp, _vp, _vp, C.c_int, _vp]),
     "pw_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp), C.POINTER(C.c_ubyte)]),
     "pw_peer_open": (C.c_int, [C.POINTER(C.c_ubyte), C.POINTER(_vp)]),
     "pw_peer_close": (C.c_int, [_vp]),

@@ -242,6 +242,59 @@ def evolve_vec(psi: torch.Tensor, op: torch.Tensor, dims, nsteps: int, keep=None
     return out, red
 
 
+def resize_axis(x: torch.Tensor, dims, axis: int, new_dim: int, is_matrix: bool):
+    """Pad / truncate one subsystem (both row and column copies for a density matrix)."""
+    lib = _lib.load()
+    nd = list(dims)
+    nd[axis] = int(new_dim)
+    n_new = math.prod(nd)
+    shape = (n_new, n_new) if is_matrix else (n_new, 1)
+    out = torch.empty(shape, dtype=x.dtype, device=x.device)
+    _lib.check(
+        lib.pw_resize_axis(x.data_ptr(), out.data_ptr(), _lib.i64_array(dims), len(dims), int(axis),
+                           int(new_dim), int(is_matrix), A.code(x.dtype), A.stream_ptr()),
+        "pw_resize_axis",
+    )
+    return out
+
+
+def kron(a: torch.Tensor, b: torch.Tensor):
+    lib = _lib.load()
+    ra, ca = a.shape
+    rb, cb = b.shape
+    out = torch.empty((ra * rb, ca * cb), dtype=a.dtype, device=a.device)
+    _lib.check(
+        lib.pw_kron(a.data_ptr(), b.data_ptr(), out.data_ptr(), ra, ca, rb, cb, A.code(a.dtype),
+                    A.stream_ptr()),
+        "pw_kron",
+    )
+    return out
+
+
+def expand_vec(psi: torch.Tensor):
+    lib = _lib.load()
+    n = psi.numel()
+    out = torch.empty((n, n), dtype=psi.dtype, device=psi.device)
+    _lib.check(lib.pw_expand_vec(psi.data_ptr(), out.data_ptr(), n, A.code(psi.dtype), A.stream_ptr()),
+               "pw_expand_vec")
+    return out
+
+
+def contract_mat(rho: torch.Tensor, tol: float = 1e-6):
+    """(psi (n,1), info [Tr rho^2, Tr rho], flag) -- all device tensors, no host sync."""
+    lib = _lib.load()
+    n = int(rho.shape[0])
+    psi = torch.zeros((n, 1), dtype=rho.dtype, device=rho.device)
+    info = torch.empty((2,), dtype=torch.float64, device=rho.device)
+    flag = torch.empty((), dtype=torch.int32, device=rho.device)
+    _lib.check(
+        lib.pw_contract_mat(rho.data_ptr(), n, float(tol), psi.data_ptr(), info.data_ptr(),
+                            flag.data_ptr(), A.code(rho.dtype), A.stream_ptr()),
+        "pw_contract_mat",
+    )
+    return psi, info, flag
+
+
 def rng_split(key, num: int = 2) -> np.ndarray:
     lib = _lib.load()
     k0, k1 = A.key_words(key)

@@ -495,3 +495,34 @@ def test_small_state_dense_rows_path(ad):
         op = ops.random_unitary(t, 2)
         out = host(ad.apply_operation_vector(dims, tg, dev(psi), dev(op)))
         assert rel_err(out, oad.apply_operation_vector(dims, tg, psi, op)) < 1e-12
+
+
+def test_layout_ops_parity(ad):
+    """pw_resize_axis / pw_kron / pw_expand_vec / pw_contract_mat against the oracle restatement
+    of resize_fock, kron_reduce, state_expand and state_contract."""
+    from oracle import layout_np as lay
+    from photon_weave_b200.core import ffi
+
+    dims = (3, 4, 2)
+    psi = ops.random_state(24, 1)
+    rho = ops.random_density(24, 2)
+    for axis, nd in [(1, 6), (1, 2), (0, 5), (2, 1), (2, 4)]:
+        out = host(ffi.resize_axis(dev(psi), dims, axis, nd, False))
+        assert np.array_equal(out, lay.resize_fock_vector(dims, axis, nd, psi))
+        outm = host(ffi.resize_axis(dev(rho), dims, axis, nd, True))
+        assert np.array_equal(outm, lay.resize_fock_matrix(dims, axis, nd, rho))
+    a, b = ops.random_state(5, 3), ops.random_state(7, 4)
+    assert rel_err(host(ffi.kron(dev(a), dev(b))), np.kron(a, b)) < 1e-15
+    A_, B_ = ops.random_density(4, 5), ops.random_density(3, 6)
+    assert rel_err(host(ffi.kron(dev(A_), dev(B_))), np.kron(A_, B_)) < 1e-15
+    assert rel_err(host(ffi.expand_vec(dev(psi))), lay.state_expand_vector(psi)) < 1e-15
+    # contraction of a pure state: same vector and phase convention as eigh + phase removal
+    pure = lay.state_expand_vector(psi)
+    got, info, flag = ffi.contract_mat(dev(pure))
+    want, ok = lay.state_contract_matrix(pure)
+    assert ok and int(flag) == 1
+    assert abs(float(info[0]) - 1) < 1e-12 and abs(float(info[1]) - 1) < 1e-12
+    assert rel_err(host(got), want) < 1e-12
+    got, info, flag = ffi.contract_mat(dev(rho))
+    assert int(flag) == 0 and not lay.state_contract_matrix(rho)[1]
+    assert abs(float(info[0]) - np.trace(rho @ rho).real) < 1e-12
