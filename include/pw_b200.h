@@ -178,6 +178,17 @@ int pw_povm_select(const void* ops, int64_t t, const int64_t* outcome, const voi
 /* stats[0] = sum |x|^2, stats[1] = max |x|^2 over `count` complex elements (doubles). */
 int pw_norm_stats(const void* x, int64_t count, int dtype, double* stats, void* stream);
 
+/* Fused post-apply bookkeeping, ONE pass over psi (is_matrix = 0) or over the diagonal of
+ * rho (is_matrix = 1):  levels[i] = highest basis index of subsystem i that carries a
+ * non-zero amplitude / population (-1 when the state is all zeros), for every subsystem at
+ * once; stats[0] = sum |psi|^2 (or Tr rho), stats[1] = max |x|^2.  levels is n device
+ * int32, stats two device doubles; n <= 16.  Replaces the per-Fock-mode
+ * trace_out -> psi psi^dagger -> num_quanta_{vector,matrix} loop the reference runs after
+ * every composite apply (state/composite_envelope.py:680-696, _math/ops.py:472-512); equal
+ * to it for physical (positive semi-definite) states. */
+int pw_occupancy(const void* state, const int64_t* dims, int n, int is_matrix, int dtype,
+                 int32_t* levels, double* stats, void* stream);
+
 /* x *= *scale_dev (a device double); e.g. 1/sqrt(norm) for Operation.renormalize
  * (state/composite_envelope.py:685-686). */
 int pw_scale(void* x, int64_t count, const double* scale_dev, int dtype, void* stream);

@@ -58,3 +58,33 @@ def state_contract_matrix(rho, tol=1e-6):
         psi = psi * np.exp(-1j * np.angle(psi[0]))
         return psi, True
     return rho, False
+
+
+def num_quanta_vector(vector):
+    """_math/ops.py:472-486 (highest row index holding a non-zero entry)."""
+    return int(np.nonzero(np.asarray(vector))[0][-1])
+
+
+def num_quanta_matrix(matrix):
+    """_math/ops.py:489-512."""
+    m = np.asarray(matrix)
+    rows = np.where(np.any(m != 0, axis=1))[0]
+    cols = np.where(np.any(m != 0, axis=0))[0]
+    return int(max(rows[-1], cols[-1]))
+
+
+def occupancy_levels(dims, state, is_matrix=False):
+    """The per-subsystem loop of state/composite_envelope.py:688-696: reduce the product state to
+    each subsystem (state/utils/trace_out.py:17-25 for vectors, core/adapters.py:696-733 for
+    matrices) and take num_quanta of the reduced density matrix."""
+    from . import adapters_np as ad
+
+    out = []
+    for i in range(len(dims)):
+        if is_matrix:
+            red = ad.trace_out_matrix(tuple(dims), (i,), np.asarray(state))
+            out.append(num_quanta_matrix(red))
+        else:
+            red = ad.trace_out_vector(tuple(dims), (i,), np.asarray(state))
+            out.append(num_quanta_matrix(red))
+    return out

@@ -163,6 +163,22 @@ def norm_stats(x: torch.Tensor):
     return stats
 
 
+def occupancy(state: torch.Tensor, dims, is_matrix: bool = False):
+    """One pass: (levels int32[n], stats float64[2]) -- highest non-zero basis index of every
+    subsystem, and [sum |psi|^2 or Tr rho, max |x|^2].  Device tensors, no host sync."""
+    lib = _lib.load()
+    d = _lib.i64_array(dims)
+    levels = torch.empty((len(dims),), dtype=torch.int32, device=state.device)
+    stats = torch.empty((2,), dtype=torch.float64, device=state.device)
+    _lib.check(
+        lib.pw_occupancy(state.data_ptr(), d, len(dims), int(bool(is_matrix)),
+                         A.code(state.dtype), levels.data_ptr(), stats.data_ptr(),
+                         A.stream_ptr()),
+        "pw_occupancy",
+    )
+    return levels, stats
+
+
 def scale_(x: torch.Tensor, scale_dev: torch.Tensor):
     lib = _lib.load()
     _lib.check(

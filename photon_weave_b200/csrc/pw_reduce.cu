@@ -577,6 +577,147 @@ __global__ void k_scale(V* __restrict__ x, const int64_t count, const double* __
   }
 }
 
+
+// ---- fused post-apply bookkeeping ---------------------------
+// One pass over a state vector (or the diagonal of a density matrix) that yields, for
+// EVERY subsystem at once, the highest basis index carrying a non-zero amplitude, plus
+// the squared norm (trace) and the largest |x|^2.  The reference obtains the same
+// integers with one trace_out -> psi psi^dagger -> nonzero() per Fock mode after every
+// composite apply (state/composite_envelope.py:688-696, _math/ops.py:472-512).
+//
+// Index model: the trailing axes whose product Q fits one tile are "lo"; the axis before
+// them is cut into chunks of `ch` rows so that a tile (ch*Q contiguous elements) stays
+// within kOccCap; everything above is "hi".  A thread always owns the same in-tile
+// positions p = tid + 256 u, so per element it only sets bit u of a 64-bit mask; the
+// mixed-radix decode of p happens once per thread at the end.  Hi digits are uniform over
+// a tile and advance by an odometer.
+constexpr int kOccCap = 16384;   // 256 threads x 64 mask bits
+constexpr int kOccMaxAxes = 16;
+
+struct OccParams {
+  int n, j;                 // axes; chunked axis (-1: the whole state is one tile)
+  uint32_t Q, ch, nch, dj;  // lo product, chunk rows, chunks per axis j, dims[j]
+  uint64_t ntiles, tiles_per_cta, stride;
+  uint32_t dims[kOccMaxAxes];
+};
+
+template <typename V, bool DIAG>
+__global__ void __launch_bounds__(256)
+k_occupancy(const V* __restrict__ x, const OccParams P, int* __restrict__ levels,
+            double* __restrict__ partial) {
+  __shared__ int s_lvl[kOccMaxAxes];
+  __shared__ double s_scratch[8];
+  __shared__ double s_max[8];
+  const int tid = threadIdx.x;
+  if (tid < kOccMaxAxes) s_lvl[tid] = -1;
+  __syncthreads();
+
+  const uint64_t t0 = (uint64_t)blockIdx.x * P.tiles_per_cta;
+  uint64_t t1 = t0 + P.tiles_per_cta;
+  if (t1 > P.ntiles) t1 = P.ntiles;
+
+  // odometer over (hi digits..., chunk c)
+  uint32_t dg[kOccMaxAxes];
+  int lvl[kOccMaxAxes];
+#pragma unroll
+  for (int i = 0; i < kOccMaxAxes; ++i) { dg[i] = 0; lvl[i] = -1; }
+  uint32_t c = (uint32_t)(t0 % P.nch);
+  {
+    uint64_t h = t0 / P.nch;
+#pragma unroll
+    for (int i = kOccMaxAxes - 1; i >= 0; --i)
+      if (i < P.j) { dg[i] = (uint32_t)(h % P.dims[i]); h /= P.dims[i]; }
+  }
+  uint64_t hi_flat = t0 / P.nch;
+
+  uint64_t mask_lo = 0, mask_c = 0;
+  int cmax = -1;
+  double sum = 0, mx = 0;
+  const uint32_t rowQ = P.dj * P.Q;
+
+  for (uint64_t t = t0; t < t1; ++t) {
+    const uint64_t base = hi_flat * rowQ + (uint64_t)c * P.ch * P.Q;
+    const uint32_t rows = (c + 1 == P.nch) ? (P.dj - c * P.ch) : P.ch;
+    const uint32_t len = rows * P.Q;
+    uint64_t m = 0;
+    for (uint32_t u0 = 0; u0 * 256u < len; u0 += 8) {
+      V v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint32_t p = tid + 256u * (u0 + k);
+        v[k] = p < len ? __ldcg(x + (base + p) * P.stride) : V{0, 0};
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const double a2 = (double)v[k].x * v[k].x + (double)v[k].y * v[k].y;
+        sum += DIAG ? (double)v[k].x : a2;
+        mx = a2 > mx ? a2 : mx;
+        m |= (uint64_t)(v[k].x != 0 || v[k].y != 0) << (u0 + k);
+      }
+    }
+    if (m) {
+      mask_lo |= m;
+      if ((int)c > cmax) { cmax = (int)c; mask_c = m; }
+      else if ((int)c == cmax) mask_c |= m;
+#pragma unroll
+      for (int i = 0; i < kOccMaxAxes; ++i)
+        if (i < P.j) lvl[i] = max(lvl[i], (int)dg[i]);
+    }
+    // advance
+    if (++c == P.nch) {
+      c = 0;
+      ++hi_flat;
+      bool carry = true;
+#pragma unroll
+      for (int i = kOccMaxAxes - 1; i >= 0; --i)
+        if (i < P.j && carry) {
+          if (++dg[i] == P.dims[i]) dg[i] = 0; else carry = false;
+        }
+    }
+  }
+
+  // decode this thread's positions once
+  if (mask_lo) {
+#pragma unroll
+    for (int i = 0; i < kOccMaxAxes; ++i)
+      if (i < P.j && lvl[i] >= 0) atomicMax(&s_lvl[i], lvl[i]);
+    int lo_lvl[kOccMaxAxes];
+#pragma unroll
+    for (int i = 0; i < kOccMaxAxes; ++i) lo_lvl[i] = -1;
+    int row_best = -1;
+    for (int u = 0; u < 64; ++u) {
+      if (!((mask_lo >> u) & 1)) continue;
+      const uint32_t p = tid + 256u * u;
+      uint32_t q = p % P.Q;
+      if ((mask_c >> u) & 1) row_best = max(row_best, (int)(p / P.Q));
+#pragma unroll
+      for (int i = kOccMaxAxes - 1; i >= 0; --i)
+        if (i > P.j && i < P.n) {
+          lo_lvl[i] = max(lo_lvl[i], (int)(q % P.dims[i]));
+          q /= P.dims[i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kOccMaxAxes; ++i)
+      if (i > P.j && i < P.n && lo_lvl[i] >= 0) atomicMax(&s_lvl[i], lo_lvl[i]);
+    if (P.j >= 0 && row_best >= 0) {
+      // chunk axis: the maximum over blocks combines (cmax, row) lexicographically
+      atomicMax(&s_lvl[P.j], cmax * (int)P.ch + row_best);
+    }
+  }
+  sum = block_sum(sum, s_scratch);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
+  if ((tid & 31) == 0) s_max[tid >> 5] = mx;
+  __syncthreads();
+  if (tid < P.n && s_lvl[tid] >= 0) atomicMax(&levels[tid], s_lvl[tid]);
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w) mx = fmax(mx, s_max[w]);
+    partial[2 * blockIdx.x] = sum;
+    partial[2 * blockIdx.x + 1] = mx;
+  }
+}
+
 }  // namespace pw
 
 using namespace pw;
@@ -749,6 +890,55 @@ static int norm_stats_t(const void* x, int64_t count, double* stats, cudaStream_
 extern "C" int pw_norm_stats(const void* x, int64_t count, int dtype, double* stats, void* stream) {
   if (!x || !stats || count < 0) return PW_ERR_INVALID;
   return PW_DISPATCH(dtype, norm_stats_t, x, count, stats, (cudaStream_t)stream);
+}
+
+template <typename V>
+static int occupancy_t(const void* x, const OccParams& P, int nblocks, int is_matrix,
+                       int32_t* levels, double* stats, cudaStream_t s) {
+  Scratch partial;
+  PW_TRY(partial.alloc(sizeof(double) * 2 * nblocks, s));
+  PW_CUDA(cudaMemsetAsync(levels, 0xFF, sizeof(int32_t) * P.n, s));  // all -1
+  if (is_matrix)
+    k_occupancy<V, true><<<nblocks, 256, 0, s>>>((const V*)x, P, levels, (double*)partial.p);
+  else
+    k_occupancy<V, false><<<nblocks, 256, 0, s>>>((const V*)x, P, levels, (double*)partial.p);
+  PW_LAUNCHED();
+  k_norm_finalize<<<1, 32, 0, s>>>((const double*)partial.p, nblocks, stats);
+  PW_LAUNCHED();
+  return PW_OK;
+}
+
+extern "C" int pw_occupancy(const void* state, const int64_t* dims, int n, int is_matrix,
+                            int dtype, int32_t* levels, double* stats, void* stream) {
+  if (!state || !dims || !levels || !stats || n < 1) return PW_ERR_INVALID;
+  if (n > kOccMaxAxes) return PW_ERR_UNSUPPORTED;
+  OccParams P{};
+  uint64_t N = 1;
+  for (int i = 0; i < n; ++i) {
+    if (dims[i] < 1 || dims[i] > 0x7fffffff) return PW_ERR_INVALID;
+    P.dims[i] = (uint32_t)dims[i];
+    N *= (uint64_t)dims[i];
+  }
+  P.n = n;
+  uint64_t Q = 1;
+  int k = n;  // axes [k, n) are lo
+  while (k > 0 && Q * (uint64_t)dims[k - 1] <= (uint64_t)kOccCap) Q *= (uint64_t)dims[--k];
+  P.j = k - 1;
+  P.Q = (uint32_t)Q;
+  if (P.j >= 0) {
+    P.dj = P.dims[P.j];
+    P.ch = (uint32_t)std::min<uint64_t>(P.dj, (uint64_t)kOccCap / Q);
+    P.nch = (P.dj + P.ch - 1) / P.ch;
+  } else {
+    P.dj = P.ch = P.nch = 1;
+  }
+  P.ntiles = N / ((uint64_t)P.dj * Q) * P.nch;
+  P.stride = is_matrix ? N + 1 : 1;
+  const uint64_t want = std::min<uint64_t>(P.ntiles, (uint64_t)kNumSMs * 6);
+  P.tiles_per_cta = (P.ntiles + want - 1) / want;
+  const int nblocks = (int)((P.ntiles + P.tiles_per_cta - 1) / P.tiles_per_cta);
+  return PW_DISPATCH(dtype, occupancy_t, state, P, nblocks, is_matrix, levels, stats,
+                     (cudaStream_t)stream);
 }
 
 template <typename V>

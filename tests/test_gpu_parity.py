@@ -526,3 +526,41 @@ def test_layout_ops_parity(ad):
     got, info, flag = ffi.contract_mat(dev(rho))
     assert int(flag) == 0 and not lay.state_contract_matrix(rho)[1]
     assert abs(float(info[0]) - np.trace(rho @ rho).real) < 1e-12
+
+
+@pytest.mark.parametrize(
+    "dims",
+    [(4, 3, 5), (64, 2), (6,) * 6, (3, 40000), (20000,), (2, 9000, 3), (5, 5, 5, 5), (7, 6, 5, 4, 3, 2, 2, 3)],
+)
+def test_occupancy_matches_reference_loop(dims):
+    """pw_occupancy == trace_out -> num_quanta per subsystem (composite_envelope.py:688-696)."""
+    from oracle import layout_np as lay
+    from photon_weave_b200.core import ffi
+
+    rng = np.random.default_rng(len(dims))
+    N = int(np.prod(dims))
+    for trial in range(3):
+        # a random sub-box of occupied levels, sparse inside it
+        hi = [int(rng.integers(0, d)) for d in dims]
+        t = np.zeros(dims, dtype=np.complex128)
+        box = tuple(slice(0, h + 1) for h in hi)
+        vals = rng.standard_normal(t[box].shape) + 1j * rng.standard_normal(t[box].shape)
+        vals *= rng.random(t[box].shape) < (0.3 if trial else 1.0)
+        t[box] = vals
+        t[tuple(hi)] = 0.5 - 0.25j  # make the corner occupied so the expected answer is hi
+        psi = t.reshape(-1, 1)
+        levels, stats = ffi.occupancy(dev(psi), dims, False)
+        assert levels.tolist() == hi
+        assert abs(float(stats[0]) - np.vdot(psi, psi).real) < 1e-9 * max(1.0, np.vdot(psi, psi).real)
+        assert abs(float(stats[1]) - np.max(np.abs(psi) ** 2)) < 1e-12 * np.max(np.abs(psi) ** 2)
+        if N <= 4096:
+            assert levels.tolist() == lay.occupancy_levels(dims, psi, False)
+            A_ = rng.standard_normal((N, 2)) + 1j * rng.standard_normal((N, 2))
+            A_ *= (np.abs(psi) > 0)
+            rho = A_ @ A_.conj().T
+            lm, sm = ffi.occupancy(dev(rho), dims, True)
+            assert lm.tolist() == lay.occupancy_levels(dims, rho, True)
+            assert abs(float(sm[0]) - np.trace(rho).real) < 1e-9 * np.trace(rho).real
+    z = np.zeros((N, 1), dtype=np.complex64)
+    levels, stats = ffi.occupancy(dev(z), dims, False)
+    assert levels.tolist() == [-1] * len(dims) and float(stats[0]) == 0.0

@@ -104,6 +104,8 @@ def bench_vec(args):
     report("reduced_from_vec one mode", ms, best, N * es)
     ms, best = timeit(lambda: ffi.norm_stats(a))
     report("norm_stats", ms, best, N * es)
+    ms, best = timeit(lambda: ffi.occupancy(a, dims, False))
+    report(f"occupancy (all {modes} modes' top level + norm, one pass)", ms, best, N * es)
     print(_lib.path_counters())
 
 
