@@ -193,6 +193,11 @@ int pw_occupancy(const void* state, const int64_t* dims, int n, int is_matrix, i
  * (state/composite_envelope.py:685-686). */
 int pw_scale(void* x, int64_t count, const double* scale_dev, int dtype, void* stream);
 
+/* x /= *divisor_dev (true division): `state / jnp.linalg.norm(state)` with the reference's
+ * rounding, so a renormalised basis state holds exactly 1.0
+ * (state/fock.py:493-495, state/composite_envelope.py:685-686). */
+int pw_divide(void* x, int64_t count, const double* divisor_dev, int dtype, void* stream);
+
 /* ---- layout ------------------------------------------------------------------ */
 
 /* out = transpose(in.reshape(dims), perm), contiguous (out axis k = in axis perm[k]).
@@ -215,6 +220,11 @@ int pw_resize_axis(const void* in, void* out, const int64_t* dims, int n, int ax
  * state/composite_envelope.py:915-948). */
 int pw_kron(const void* a, const void* b, void* out, int64_t rows_a, int64_t cols_a,
             int64_t rows_b, int64_t cols_b, int dtype, void* stream);
+
+/* out[0] = how many entries of psi equal exactly 1 + 0i, out[1] = index of the first one
+ * (-1 if none); out is two device int64.  The Vector -> Label test of state_contract
+ * (state/utils/state_transform.py:138-144). */
+int pw_find_label(const void* psi, int64_t n, int dtype, int64_t* out, void* stream);
 
 /* rho = psi psi^dagger (state_expand Vector -> Matrix, state/utils/state_transform.py:58-63). */
 int pw_expand_vec(const void* psi, void* rho, int64_t n, int dtype, void* stream);

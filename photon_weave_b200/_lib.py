@@ -68,8 +68,10 @@ SIGNATURES = {
     "pw_povm_probs": (C.c_int, [_vp, _vp, C.c_int, C.c_int64, _vp, _vp, C.c_int, _vp]),
     "pw_povm_select": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, C.c_int, _vp]),
     "pw_norm_stats": (C.c_int, [_vp, C.c_int64, C.c_int, _vp, _vp]),
+    "pw_find_label": (C.c_int, [_vp, C.c_int64, C.c_int, _vp, _vp]),
     "pw_occupancy": (C.c_int, [_vp, _i64p, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "pw_scale": (C.c_int, [_vp, C.c_int64, _vp, C.c_int, _vp]),
+    "pw_divide": (C.c_int, [_vp, C.c_int64, _vp, C.c_int, _vp]),
     "pw_permute": (C.c_int, [_vp, _vp, _i64p, C.c_int, _i32p, C.c_int, _vp]),
     "pw_resize_axis": (C.c_int, [_vp, _vp, _i64p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, _vp]),
     "pw_kron": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, _vp]),

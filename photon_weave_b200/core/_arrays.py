@@ -30,6 +30,11 @@ def require_cuda() -> None:
         )
 
 
+def device() -> str:
+    """Where new arrays are allocated (the current CUDA device)."""
+    return "cuda"
+
+
 def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 

@@ -163,6 +163,18 @@ def norm_stats(x: torch.Tensor):
     return stats
 
 
+def find_label(psi: torch.Tensor):
+    """Device int64 [count of entries == 1+0j, index of the first] -- no host sync."""
+    lib = _lib.load()
+    out = torch.empty((2,), dtype=torch.int64, device=psi.device)
+    _lib.check(
+        lib.pw_find_label(psi.data_ptr(), int(psi.numel()), A.code(psi.dtype), out.data_ptr(),
+                          A.stream_ptr()),
+        "pw_find_label",
+    )
+    return out
+
+
 def occupancy(state: torch.Tensor, dims, is_matrix: bool = False):
     """One pass: (levels int32[n], stats float64[2]) -- highest non-zero basis index of every
     subsystem, and [sum |psi|^2 or Tr rho, max |x|^2].  Device tensors, no host sync."""
@@ -185,6 +197,16 @@ def scale_(x: torch.Tensor, scale_dev: torch.Tensor):
         lib.pw_scale(x.data_ptr(), int(x.numel()), scale_dev.data_ptr(), A.code(x.dtype),
                      A.stream_ptr()),
         "pw_scale",
+    )
+    return x
+
+
+def divide_(x: torch.Tensor, divisor_dev: torch.Tensor):
+    lib = _lib.load()
+    _lib.check(
+        lib.pw_divide(x.data_ptr(), int(x.numel()), divisor_dev.data_ptr(), A.code(x.dtype),
+                      A.stream_ptr()),
+        "pw_divide",
     )
     return x
 

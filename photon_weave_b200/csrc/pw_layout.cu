@@ -196,6 +196,34 @@ k_contract(const V* __restrict__ rho, const uint64_t n, const double tol, V* __r
   }
 }
 
+// out[0] = number of entries exactly equal to 1 + 0i, out[1] = index of the first of them
+// (-1 if none): the Vector -> Label test of state_contract (state_transform.py:138-144).
+template <typename V>
+__global__ void __launch_bounds__(256)
+k_find_label(const V* __restrict__ psi, const int64_t n, long long* __restrict__ out) {
+  __shared__ long long s_cnt[256];
+  __shared__ long long s_first[256];
+  long long cnt = 0, first = -1;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const V v = psi[i];
+    if (v.x == 1 && v.y == 0) {
+      ++cnt;
+      if (first < 0) first = i;
+    }
+  }
+  s_cnt[threadIdx.x] = cnt; s_first[threadIdx.x] = first;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      s_cnt[threadIdx.x] += s_cnt[threadIdx.x + s];
+      const long long a = s_first[threadIdx.x], b = s_first[threadIdx.x + s];
+      s_first[threadIdx.x] = a < 0 ? b : (b < 0 ? a : (a < b ? a : b));
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[0] = s_cnt[0]; out[1] = s_first[0]; }
+}
+
 }  // namespace pw
 
 extern "C" int pw_resize_axis(const void* in, void* out, const int64_t* dims, int n, int axis,
@@ -261,6 +289,16 @@ extern "C" int pw_contract_mat(const void* rho, int64_t n, double tol, void* psi
   PW_TRY(pw_norm_stats(rho, n * n, dtype, (double*)stats.p, stream));  // full-grid reduction
   if (dtype == PW_C128) k_contract<double2><<<1, 256, 0, s>>>((const double2*)rho, (uint64_t)n, tol, (double2*)psi, (const double*)stats.p, info, flag);
   else if (dtype == PW_C64) k_contract<float2><<<1, 256, 0, s>>>((const float2*)rho, (uint64_t)n, tol, (float2*)psi, (const double*)stats.p, info, flag);
+  else return PW_ERR_INVALID;
+  PW_LAUNCHED();
+  return PW_OK;
+}
+
+extern "C" int pw_find_label(const void* psi, int64_t n, int dtype, int64_t* out, void* stream) {
+  if (!psi || !out || n < 1) return PW_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == PW_C128) k_find_label<double2><<<1, 256, 0, s>>>((const double2*)psi, n, (long long*)out);
+  else if (dtype == PW_C64) k_find_label<float2><<<1, 256, 0, s>>>((const float2*)psi, n, (long long*)out);
   else return PW_ERR_INVALID;
   PW_LAUNCHED();
   return PW_OK;

@@ -565,14 +565,17 @@ __global__ void k_norm_finalize(const double* __restrict__ partial, const int nb
   stats[1] = mx;
 }
 
-template <typename V>
+// DIV: x /= s with a true division, so that x / ||x|| rounds exactly like the reference's
+// `state / jnp.linalg.norm(state)` (a basis state comes out as exactly 1.0, which the
+// Vector -> Label contraction tests for).
+template <typename V, bool DIV>
 __global__ void k_scale(V* __restrict__ x, const int64_t count, const double* __restrict__ scale) {
   using R = typename RealOf<V>::type;
   const R s = (R)*scale;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
        i += (int64_t)gridDim.x * blockDim.x) {
     V v = x[i];
-    v.x *= s; v.y *= s;
+    if (DIV) { v.x /= s; v.y /= s; } else { v.x *= s; v.y *= s; }
     x[i] = v;
   }
 }
@@ -602,7 +605,7 @@ struct OccParams {
 };
 
 template <typename V, bool DIAG>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_occupancy(const V* __restrict__ x, const OccParams P, int* __restrict__ levels,
             double* __restrict__ partial) {
   __shared__ int s_lvl[kOccMaxAxes];
@@ -934,7 +937,7 @@ extern "C" int pw_occupancy(const void* state, const int64_t* dims, int n, int i
   }
   P.ntiles = N / ((uint64_t)P.dj * Q) * P.nch;
   P.stride = is_matrix ? N + 1 : 1;
-  const uint64_t want = std::min<uint64_t>(P.ntiles, (uint64_t)kNumSMs * 6);
+  const uint64_t want = std::min<uint64_t>(P.ntiles, (uint64_t)kNumSMs * 4);  // one resident wave
   P.tiles_per_cta = (P.ntiles + want - 1) / want;
   const int nblocks = (int)((P.ntiles + P.tiles_per_cta - 1) / P.tiles_per_cta);
   return PW_DISPATCH(dtype, occupancy_t, state, P, nblocks, is_matrix, levels, stats,
@@ -943,7 +946,14 @@ extern "C" int pw_occupancy(const void* state, const int64_t* dims, int n, int i
 
 template <typename V>
 static int scale_t(void* x, int64_t count, const double* scale, cudaStream_t s) {
-  k_scale<V><<<grid_for((uint64_t)count, 256, 8), 256, 0, s>>>((V*)x, count, scale);
+  k_scale<V, false><<<grid_for((uint64_t)count, 256, 8), 256, 0, s>>>((V*)x, count, scale);
+  PW_LAUNCHED();
+  return PW_OK;
+}
+
+template <typename V>
+static int divide_t(void* x, int64_t count, const double* divisor, cudaStream_t s) {
+  k_scale<V, true><<<grid_for((uint64_t)count, 256, 8), 256, 0, s>>>((V*)x, count, divisor);
   PW_LAUNCHED();
   return PW_OK;
 }
@@ -951,4 +961,9 @@ static int scale_t(void* x, int64_t count, const double* scale, cudaStream_t s) 
 extern "C" int pw_scale(void* x, int64_t count, const double* scale_dev, int dtype, void* stream) {
   if (!x || !scale_dev || count < 0) return PW_ERR_INVALID;
   return PW_DISPATCH(dtype, scale_t, x, count, scale_dev, (cudaStream_t)stream);
+}
+
+extern "C" int pw_divide(void* x, int64_t count, const double* divisor_dev, int dtype, void* stream) {
+  if (!x || !divisor_dev || count < 0) return PW_ERR_INVALID;
+  return PW_DISPATCH(dtype, divide_t, x, count, divisor_dev, (cudaStream_t)stream);
 }

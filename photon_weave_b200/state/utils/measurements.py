@@ -1,6 +1,11 @@
 """
 Projective / POVM measurement bridges (reference: photon_weave/state/utils/measurements.py:20-682).
-The PNR detector-noise helpers (measurements.py:685-1112) are out of scope.
+The PNR detector model (measurements.py:685-1112) is host arithmetic on a handful of
+integers: the projective measurement inside it is the CUDA path, the binomial-loss /
+Poisson-dark-count / Gaussian-jitter draws are taken from a counter-based stream seeded by
+the threefry key (statistically the reference's model; NOT bit-identical to
+``jax.random.binomial/poisson/normal`` for efficiency < 1 or dark_rate > 0 -- with the
+defaults, efficiency = 1 and dark_rate = 0, no random draw influences the result).
 
 Key threading follows the reference exactly:
 * legacy sequential paths: one key per target from ``_key_sequence`` (``split(key, n+1)[1:]``),
@@ -170,3 +175,167 @@ def measure_POVM_matrix_jit(state_objs, target_states, operators, product_state,
     dims = [s.dimensions for s in objs]
     tgt = [objs.index(s) for s in target_states]
     return adapters.measure_povm_matrix(dims, tgt, operators, product_state, key)
+
+
+# --------------------------------------------------------------------------------------
+# photon-number-resolving detection (measurements.py:685-893)
+# --------------------------------------------------------------------------------------
+
+
+def _host_stream(key) -> np.random.Generator:
+    """Deterministic NumPy stream keyed by the two threefry words of ``key``."""
+    k = np.asarray(key).astype(np.uint32).reshape(-1)
+    return np.random.Generator(np.random.Philox(key=int(k[0]) << 32 | int(k[1])))
+
+
+def _pnr_noise(key, target_count: int, dark_mean: float, jitter_std: float):
+    """Dark counts ~ Poisson(dark_mean), timing jitter ~ N(0, jitter_std) (measurements.py:685-703)."""
+    key = _ensure_key(key)
+    k = _rng.split(key, 2)
+    dark = _host_stream(k[0]).poisson(lam=dark_mean, size=(target_count,)) if dark_mean > 0 \
+        else np.zeros((target_count,), dtype=np.int64)
+    if jitter_std > 0:
+        jitter = _host_stream(k[1]).normal(size=(target_count,)) * jitter_std
+    else:
+        jitter = np.zeros((target_count,))
+    return dark, jitter
+
+
+def _binomial(key, n: int, p: float) -> int:
+    p = float(min(max(p, 0.0), 1.0))
+    if p >= 1.0 or n <= 0:
+        return int(max(n, 0))
+    if p <= 0.0:
+        return 0
+    return int(_host_stream(key).binomial(int(n), p))
+
+
+def _measure_pnr(is_matrix: bool, state_objs, target_states, product_state, efficiency, dark_rate,
+                 detection_window, jitter_std, key, meta, use_jit):
+    use_jit_flag = isinstance(meta, (DimsMeta, ShapePlan)) or (Config().use_jit if use_jit is None else use_jit)
+    if use_jit_flag:
+        if key is None:
+            raise ValueError("key is required for jitted PNR measurement (static path)")
+        dims, tgt = _dims_targets(meta, state_objs, target_states, None)
+        core = adapters.measure_matrix if is_matrix else adapters.measure_vector
+        outcome, post, key_after = core(dims, tgt, product_state, key)
+        decoded = list(_decode(outcome, dims, tgt, target_states).values())
+        k3 = _rng.split(key_after, 3)
+        binom_key, noise_seed, next_key = k3[0], k3[1], k3[2]
+        draw_keys = _rng.split(binom_key, max(len(decoded), 1))
+        detected = [_binomial(draw_keys[i], n, efficiency) for i, n in enumerate(decoded)]
+        dark_seed = _rng.split(noise_seed, 2)[0]
+        dark, jitter = _pnr_noise(dark_seed, len(target_states), dark_rate * detection_window, jitter_std)
+        return ({ts: int(detected[i] + dark[i]) for i, ts in enumerate(target_states)}, post, jitter,
+                next_key)
+    base_key = _ensure_key(key)
+    k2 = _rng.split(base_key, 2)
+    meas_key, noise_key = k2[0], k2[1]
+    legacy = measure_matrix if is_matrix else measure_vector
+    outcomes, post = legacy(state_objs, target_states, product_state, key=meas_key)
+    k3 = _rng.split(noise_key, 3)
+    binom_key, noise_seed, next_key = k3[0], k3[1], k3[2]
+    measured = {}
+    subkey = binom_key
+    for ts, outcome in outcomes.items():
+        k = _rng.split(subkey, 2)
+        subkey, draw_key = k[0], k[1]
+        measured[ts] = _binomial(draw_key, int(outcome), efficiency)
+    dark_seed = _rng.split(noise_seed, 2)[0]
+    dark, jitter = _pnr_noise(dark_seed, len(target_states), dark_rate * detection_window, jitter_std)
+    return ({ts: int(measured[ts] + dark[i]) for i, ts in enumerate(target_states)}, post, jitter,
+            next_key)
+
+
+def measure_pnr_vector(state_objs, target_states, product_state, efficiency: float = 1.0,
+                       dark_rate: float = 0.0, detection_window: float = 1.0, jitter_std: float = 0.0,
+                       key=None, meta=None, use_jit=None):
+    """measurements.py:718-803 -> (counts per target, post state, jitter, next key)."""
+    return _measure_pnr(False, state_objs, target_states, product_state, efficiency, dark_rate,
+                        detection_window, jitter_std, key, meta, use_jit)
+
+
+def measure_pnr_matrix(state_objs, target_states, product_state, efficiency: float = 1.0,
+                       dark_rate: float = 0.0, detection_window: float = 1.0, jitter_std: float = 0.0,
+                       key=None, meta=None, use_jit=None):
+    """measurements.py:806-893."""
+    return _measure_pnr(True, state_objs, target_states, product_state, efficiency, dark_rate,
+                        detection_window, jitter_std, key, meta, use_jit)
+
+
+# -- analytic detector model (measurements.py:896-1112): operator-sized host tables ---------
+
+
+def fwhm_to_sigma(fwhm: float) -> float:
+    return fwhm / (2.0 * np.sqrt(2.0 * np.log(2.0)))
+
+
+def poisson_pmf_direct(k_max: int, mean: float) -> np.ndarray:
+    from scipy.special import gammaln
+
+    k = np.arange(k_max + 1, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        pmf = np.exp(-mean) * np.power(mean, k) / np.exp(gammaln(k + 1))
+    total = pmf.sum()
+    return pmf / total if total > 0 else pmf
+
+
+def pnr_pmf_single_n(n_photons: int, eta: float, dark_rate: float, window: float,
+                     max_counts=None) -> np.ndarray:
+    """P(k clicks | n photons): binomial loss convolved with Poisson dark counts."""
+    from scipy.special import gammaln
+
+    if not (0.0 <= eta <= 1.0):
+        raise ValueError("eta must be in [0, 1].")
+    mu_d = dark_rate * window
+    n = int(n_photons)
+    if max_counts is None:
+        spread = np.sqrt(max(n * eta * (1.0 - eta) + mu_d, 1e-12))
+        cutoff = int(np.ceil(n * eta + mu_d + 8.0 * spread))
+        max_counts = int(max(cutoff, n + int(5 + 5 * mu_d)))
+    max_counts = max(0, int(max_counts))
+    m = np.arange(n + 1, dtype=np.float64)
+    coeff = np.exp(gammaln(n + 1) - gammaln(m + 1) - gammaln(n - m + 1))
+    p_sig = coeff * np.power(eta, m) * np.power(1.0 - eta, n - m)
+    p_dark = poisson_pmf_direct(max_counts, mu_d)
+    k = np.arange(max_counts + 1)[None, :]
+    lag = (k - m[:, None]).astype(np.int64)
+    table = np.where(lag >= 0, p_dark[np.clip(lag, 0, max_counts)], 0.0)
+    total = (p_sig[:, None] * table).sum(axis=0)
+    norm = total.sum()
+    return total / norm if norm > 0 else total
+
+
+def pnr_transition_matrix(max_photons: int, eta: float, dark_rate: float, window: float,
+                          max_counts=None) -> np.ndarray:
+    max_photons = int(max_photons)
+    if max_photons < 0:
+        raise ValueError("max_photons must be non-negative.")
+    if max_counts is None:
+        max_counts = pnr_pmf_single_n(max_photons, eta, dark_rate, window, None).shape[0] - 1
+    cols = [pnr_pmf_single_n(n, eta, dark_rate, window, int(max_counts)) for n in range(max_photons + 1)]
+    return np.stack(cols, axis=1)
+
+
+def pnr_povm(max_photons: int, eta: float, dark_rate: float, window: float, max_counts=None) -> np.ndarray:
+    """Diagonal POVM elements E_k = diag_n P(k | n), shape (K, dim, dim)."""
+    P = pnr_transition_matrix(max_photons, eta, dark_rate, window, max_counts)
+    povm = np.zeros((P.shape[0], P.shape[1], P.shape[1]), dtype=np.float64)
+    idx = np.arange(P.shape[1])
+    povm[:, idx, idx] = P
+    return povm
+
+
+def gaussian_jitter_kernel(num_bins: int, bin_width: float, jitter_std: float) -> np.ndarray:
+    """Column-stochastic matrix spreading a click time over neighbouring bins."""
+    from scipy.special import erf
+
+    if jitter_std <= 0.0:
+        return np.eye(num_bins, dtype=np.float64)
+    centers = (np.arange(num_bins, dtype=np.float64) + 0.5) * bin_width
+    scale = np.sqrt(2.0) * jitter_std
+    left = (centers[:, None] - 0.5 * bin_width - centers[None, :]) / scale
+    right = (centers[:, None] + 0.5 * bin_width - centers[None, :]) / scale
+    cols = 0.5 * (erf(right) - erf(left))
+    sums = cols.sum(axis=0, keepdims=True)
+    return np.where(sums > 0, cols / np.where(sums > 0, sums, 1.0), cols)

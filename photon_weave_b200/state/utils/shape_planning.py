@@ -37,8 +37,43 @@ def build_meta(state_objs: Sequence, target_states: Sequence) -> DimsMeta:
     return make_meta(dims, target_indices)
 
 
-def compiled_kernels(plan: ShapePlan):
+def ensure_static_dims_for_ops(state_objs: Sequence, operations: Sequence) -> None:
+    """Pre-size Fock states for a list of operations before entering static (use_jit)
+    mode (shape_planning.py:51-69)."""
+    from ...operation.fock_operation import FockOperationType
+
+    for op in operations:
+        for so in state_objs:
+            if isinstance(op._operation_type, FockOperationType):
+                if getattr(so, "_num_quanta", None) is None:
+                    continue
+                op.compute_dimensions(so._num_quanta, so.trace_out())
+                if so.dimensions != op.dimensions[0]:
+                    so.resize(op.dimensions[0])
+
+
+def envelope_plan(envelope, *target_states) -> ShapePlan:
+    """Plan over (fock, polarization); no targets = both (shape_planning.py:72-79)."""
+    state_objs = [envelope.fock, envelope.polarization]
+    return build_plan(state_objs, target_states if target_states else state_objs)
+
+
+def composite_plan(composite_envelope, product_state_index: int = 0, *target_states) -> ShapePlan:
+    """Plan over one product state of a composite envelope (shape_planning.py:82-89)."""
+    state_objs = list(composite_envelope.product_states[product_state_index].state_objs)
+    return build_plan(state_objs, target_states if target_states else state_objs)
+
+
+def composite_meta(composite_envelope, product_state_index: int = 0, *target_states) -> DimsMeta:
+    return composite_plan(composite_envelope, product_state_index, *target_states).meta
+
+
+def compiled_kernels(plan):
     """Callables bound to a plan (shape_planning.py:92-133)."""
+
+    if isinstance(plan, DimsMeta):
+        plan = ShapePlan(dims=plan.state_dims, target_indices=plan.target_indices,
+                         rest_indices=plan.rest_indices, meta=plan)
 
     class Kernels:
         @staticmethod
