@@ -84,11 +84,16 @@ def test_large_product_state_through_the_container_api():
     ref = renorm(oad.apply_operation_vector(dims, (7,), ref, oops.squeezing_operator(d, 0.1 + 0.1j)))
     assert [s.dimensions for s in focks] == [d] * n  # a dense state keeps every level occupied
     red = ce.trace_out(focks[7], focks[2])
-    want = oad.trace_out_vector(dims, (7, 2), ref)
+    # (the oracle's trace_out_vector forms psi psi^dagger like the reference: too large here)
+    t = ref.reshape(dims).transpose(7, 2, 0, 1, 3, 4, 5, 6).reshape(d * d, -1)
+    want = t @ t.conj().T
     assert np.abs(red.cpu().numpy() - want).max() < 1e-12
     ce.reorder(*focks)
     got = ps.state.cpu().numpy()
     assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-12
-    probs, _ = ce.measure_expectation(focks[3])
-    p = (np.abs(ref.reshape(dims)) ** 2).sum(axis=(0, 1, 2, 4, 5, 6, 7))
+    # expectation of measuring seven modes: joint probabilities + reduced state of the eighth
+    probs, rest = ce.measure_expectation(*focks[:7])
+    amp = ref.reshape(d**7, d)
+    p = (np.abs(amp) ** 2).sum(axis=1)
     assert np.abs(probs.cpu().numpy() - p / p.sum()).max() < 1e-12
+    assert np.abs(rest.cpu().numpy() - amp.T @ amp.conj()).max() < 1e-12
