@@ -290,6 +290,22 @@ int pw_circuit_device(void* state, void* scratch, int is_matrix, const int64_t* 
                       const pw_host_op* ops, int nops, int dtype, int fuse, void* stream,
                       int* result_in_scratch);
 
+/* ---- streaming host-buffer pipeline ------------------------------------------------
+ * Throughput version of pw_circuit_host for callers that evolve many states (sweeps,
+ * trajectories): up to `nbuf` (2..8, 4 sustains the PCIe rate) state buffers stay in HBM and
+ * the upload of job k+1, the kernels of job k and the download of job k-1 run concurrently on
+ * three streams, so PCIe is used full duplex.  submit only enqueues (h_state / h_out should be
+ * pinned and must stay valid until the job's wait returns; they may not alias another job in
+ * flight); wait blocks until that job's result is in h_out.  Not thread safe per pipeline. */
+typedef struct pw_pipeline pw_pipeline;
+int pw_pipeline_create(int is_matrix, const int64_t* dims, int n, int dtype, int device,
+                       int nbuf, pw_pipeline** out);
+int pw_pipeline_buffers(const pw_pipeline* pl);   /* buffers actually allocated (>= 2) */
+int pw_pipeline_submit(pw_pipeline* pl, const void* h_state, void* h_out, const pw_host_op* ops,
+                       int nops, int64_t* ticket);
+int pw_pipeline_wait(pw_pipeline* pl, int64_t ticket);
+int pw_pipeline_destroy(pw_pipeline* pl);
+
 #ifdef __cplusplus
 }
 #endif

@@ -101,6 +101,13 @@ SIGNATURES = {
         C.c_int,
         [_vp, _vp, C.c_int, _i64p, C.c_int, C.POINTER(pw_host_op), C.c_int, C.c_int, C.c_int],
     ),
+    "pw_pipeline_create": (C.c_int, [C.c_int, _i64p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.POINTER(C.c_void_p)]),
+    "pw_pipeline_buffers": (C.c_int, [_vp]),
+    "pw_pipeline_submit": (C.c_int, [_vp, _vp, _vp, C.POINTER(pw_host_op), C.c_int,
+                                     C.POINTER(C.c_int64)]),
+    "pw_pipeline_wait": (C.c_int, [_vp, C.c_int64]),
+    "pw_pipeline_destroy": (C.c_int, [_vp]),
 }
 
 _lib = None

@@ -342,6 +342,82 @@ def rng_split(key, num: int = 2) -> np.ndarray:
     return np.frombuffer(out, dtype=np.uint32).reshape(num, 2).copy()
 
 
+def _host_ops(ops_list, cdt):
+    arr = (_lib.pw_host_op * max(len(ops_list), 1))()
+    keep = []
+    for i, (kind, targets, op) in enumerate(ops_list):
+        op = np.ascontiguousarray(op, dtype=cdt)
+        keep.append(op)
+        arr[i].kind = int(kind)
+        arr[i].nt = len(targets)
+        for k, tg in enumerate(targets):
+            arr[i].targets[k] = int(tg)
+        arr[i].K = int(op.shape[0]) if kind == 2 else 1
+        arr[i].op = op.ctypes.data
+    return arr, keep
+
+
+class HostPipeline:
+    """
+    Streaming host-buffer path (pw_pipeline_*): ``submit`` enqueues upload + operation list +
+    download of one state and returns a ticket, ``wait`` blocks until that result is in its
+    output buffer.  Uploads, kernels and downloads of consecutive jobs overlap (PCIe full
+    duplex).  Host buffers should be pinned and must not be shared by jobs in flight.
+    """
+
+    def __init__(self, dims, is_matrix: bool = False, dtype=np.complex128, device: int = 0,
+                 buffers: int = 4):
+        self._lib = _lib.load()
+        self.dims = tuple(int(d) for d in dims)
+        self.is_matrix = bool(is_matrix)
+        self.cdt = np.complex128 if np.dtype(dtype) == np.complex128 else np.complex64
+        self._h = C.c_void_p()
+        _lib.check(
+            self._lib.pw_pipeline_create(int(is_matrix), _lib.i64_array(self.dims), len(self.dims),
+                                         _lib.PW_C128 if self.cdt == np.complex128 else _lib.PW_C64,
+                                         int(device), int(buffers), C.byref(self._h)),
+            "pw_pipeline_create")
+        self._keep = {}
+
+    @property
+    def buffers(self) -> int:
+        return int(self._lib.pw_pipeline_buffers(self._h))
+
+    def submit(self, h_state: np.ndarray, out: np.ndarray, ops_list) -> int:
+        assert h_state.dtype == self.cdt and out.dtype == self.cdt
+        assert h_state.flags.c_contiguous and out.flags.c_contiguous
+        arr, keep = _host_ops(ops_list, self.cdt)
+        ticket = C.c_int64(-1)
+        _lib.check(self._lib.pw_pipeline_submit(self._h, h_state.ctypes.data, out.ctypes.data, arr,
+                                                len(ops_list), C.byref(ticket)),
+                   "pw_pipeline_submit")
+        self._keep[ticket.value] = (keep, h_state, out)
+        return int(ticket.value)
+
+    def wait(self, ticket: int) -> np.ndarray:
+        _lib.check(self._lib.pw_pipeline_wait(self._h, int(ticket)), "pw_pipeline_wait")
+        _, _, out = self._keep.pop(int(ticket), (None, None, None))
+        return out
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.pw_pipeline_destroy(self._h)
+            self._h = C.c_void_p()
+            self._keep.clear()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def circuit_host(h_state: np.ndarray, is_matrix: bool, dims, ops_list, device: int = 0,
                  out: Optional[np.ndarray] = None) -> np.ndarray:
     """

@@ -139,3 +139,183 @@ extern "C" int pw_circuit_host(const void* h_state, void* h_out, int is_matrix,
   PW_CUDA(cudaStreamSynchronize(st.s));
   return PW_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// Streaming host-buffer pipeline.
+//
+// pw_circuit_host is latency-bound by PCIe: upload, compute and download of one call run
+// back to back (34.8 GB each way for the 12-mode vector = 2 x ~0.65 s around 0.22 s of
+// kernels).  A caller that evolves many states (parameter sweeps, trajectories, batches)
+// wants THROUGHPUT: this pipeline keeps up to `nbuf` state buffers in HBM and three
+// streams (H2D, compute, D2H), so the upload of job k+1 and the download of job k-1 run
+// on the two DMA engines while job k computes -- PCIe is used full duplex and the per-job
+// time approaches max(upload, download).  Everything is stream ordered (events); submit
+// never blocks on the device, wait blocks on one job's download only.
+//
+// Buffer pool: a job takes the two least recently released buffers (X for the upload, Z as
+// the ping-pong scratch); after its kernels the buffer that does not hold the result is
+// released at once, the result buffer when its download completes.  A buffer stays busy
+// for upload + compute + download, so nbuf = 4 (3 jobs in flight + scratch) sustains the
+// PCIe rate; nbuf = 2 degenerates to the serial schedule of pw_circuit_host.
+// ---------------------------------------------------------------------------------------
+#include <deque>
+
+struct pw_pipeline {
+  int device = 0, is_matrix = 0, n = 0, dtype = 0;
+  int64_t dims[PW_MAX_SUBSYSTEMS];
+  size_t bytes = 0, es = 0;
+  cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr, s_ops = nullptr;
+  struct Buf { void* p; cudaEvent_t free_ev; };
+  std::deque<Buf> pool;            // least recently released first
+  std::vector<void*> owned;        // for destruction
+  struct Slot { void* arena = nullptr; size_t cap = 0; cudaEvent_t ops_ev = nullptr, done_ev = nullptr;
+                int64_t ticket = -1; };
+  std::vector<Slot> slots;         // ring of in-flight jobs (operator arenas + completion events)
+  int64_t next_ticket = 0;
+};
+
+extern "C" int pw_pipeline_destroy(pw_pipeline* pl) {
+  if (!pl) return PW_OK;
+  cudaSetDevice(pl->device);
+  if (pl->s_d2h) cudaStreamSynchronize(pl->s_d2h);
+  if (pl->s_comp) cudaStreamSynchronize(pl->s_comp);
+  if (pl->s_h2d) cudaStreamSynchronize(pl->s_h2d);
+  for (auto& b : pl->pool) if (b.free_ev) cudaEventDestroy(b.free_ev);
+  for (void* p : pl->owned) cudaFree(p);
+  for (auto& s : pl->slots) {
+    if (s.arena) cudaFree(s.arena);
+    if (s.ops_ev) cudaEventDestroy(s.ops_ev);
+    if (s.done_ev) cudaEventDestroy(s.done_ev);
+  }
+  for (cudaStream_t s : {pl->s_h2d, pl->s_comp, pl->s_d2h, pl->s_ops}) if (s) cudaStreamDestroy(s);
+  delete pl;
+  return PW_OK;
+}
+
+extern "C" int pw_pipeline_create(int is_matrix, const int64_t* dims, int n, int dtype, int device,
+                                  int nbuf, pw_pipeline** out) {
+  if (!out || !dims || n < 1 || n > PW_MAX_SUBSYSTEMS || nbuf < 2 || nbuf > 8) return PW_ERR_INVALID;
+  if (dtype != PW_C64 && dtype != PW_C128) return PW_ERR_INVALID;
+  PW_CUDA(cudaSetDevice(device));
+  pw_pipeline* pl = new pw_pipeline();
+  pl->device = device; pl->is_matrix = is_matrix; pl->n = n; pl->dtype = dtype;
+  pl->es = dtype == PW_C128 ? 16 : 8;
+  uint64_t N = 1;
+  for (int i = 0; i < n; ++i) {
+    if (dims[i] < 1) { delete pl; return PW_ERR_INVALID; }
+    pl->dims[i] = dims[i];
+    N *= (uint64_t)dims[i];
+  }
+  pl->bytes = (is_matrix ? N * N : N) * pl->es;
+  auto fail = [&](int code) { pw_pipeline_destroy(pl); return code; };
+  for (cudaStream_t* s : {&pl->s_h2d, &pl->s_comp, &pl->s_d2h, &pl->s_ops})
+    if (cudaStreamCreateWithFlags(s, cudaStreamNonBlocking) != cudaSuccess) return fail(PW_ERR_CUDA);
+  for (int i = 0; i < nbuf; ++i) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, pl->bytes) != cudaSuccess) {
+      (void)cudaGetLastError();
+      break;  // run with what fits (>= 2)
+    }
+    pl->owned.push_back(p);
+    cudaEvent_t ev;
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return fail(PW_ERR_CUDA);
+    cudaEventRecord(ev, pl->s_comp);
+    pl->pool.push_back({p, ev});
+  }
+  if (pl->pool.size() < 2) return fail(PW_ERR_CUDA);
+  pl->slots.resize(pl->pool.size());
+  for (auto& s : pl->slots) {
+    if (cudaEventCreateWithFlags(&s.ops_ev, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.done_ev, cudaEventDisableTiming) != cudaSuccess)
+      return fail(PW_ERR_CUDA);
+  }
+  *out = pl;
+  return PW_OK;
+}
+
+extern "C" int pw_pipeline_buffers(const pw_pipeline* pl) { return pl ? (int)pl->owned.size() : 0; }
+
+extern "C" int pw_pipeline_wait(pw_pipeline* pl, int64_t ticket) {
+  if (!pl || ticket < 0 || ticket >= pl->next_ticket) return PW_ERR_INVALID;
+  auto& slot = pl->slots[ticket % (int64_t)pl->slots.size()];
+  if (slot.ticket != ticket) return PW_OK;  // the slot was reused: that job finished long ago
+  PW_CUDA(cudaSetDevice(pl->device));
+  PW_CUDA(cudaEventSynchronize(slot.done_ev));
+  return PW_OK;
+}
+
+extern "C" int pw_pipeline_submit(pw_pipeline* pl, const void* h_state, void* h_out,
+                                  const pw_host_op* ops, int nops, int64_t* ticket) {
+  if (!pl || !h_state || !h_out || nops < 0 || (nops && !ops)) return PW_ERR_INVALID;
+  PW_CUDA(cudaSetDevice(pl->device));
+  PW_TRY(check_ops(pl->is_matrix, pl->dims, pl->n, ops, nops));
+  const int64_t tk = pl->next_ticket;
+  auto& slot = pl->slots[tk % (int64_t)pl->slots.size()];
+  if (slot.ticket >= 0) PW_CUDA(cudaEventSynchronize(slot.done_ev));  // ring full: oldest job first
+
+  // operators -> this slot's arena (its own stream, so the small copies never queue behind
+  // a 35 GB upload)
+  std::vector<size_t> off(nops);
+  size_t total = 0;
+  for (int i = 0; i < nops; ++i) {
+    uint64_t t = 1;
+    for (int k = 0; k < ops[i].nt; ++k) t *= (uint64_t)pl->dims[ops[i].targets[k]];
+    const int K = ops[i].kind == 2 ? ops[i].K : 1;
+    off[i] = total;
+    total += (((size_t)K * t * t * pl->es) + 255) & ~(size_t)255;
+  }
+  if (total > slot.cap) {
+    if (slot.arena) PW_CUDA(cudaFree(slot.arena));
+    slot.arena = nullptr;
+    slot.cap = 0;
+    PW_CUDA(cudaMalloc(&slot.arena, total));
+    slot.cap = total;
+  }
+  std::vector<void*> dev_ops(nops);
+  for (int i = 0; i < nops; ++i) {
+    dev_ops[i] = (char*)slot.arena + off[i];
+    const size_t ob = (i + 1 < nops ? off[i + 1] : total) - off[i];
+    uint64_t t = 1;
+    for (int k = 0; k < ops[i].nt; ++k) t *= (uint64_t)pl->dims[ops[i].targets[k]];
+    const size_t exact = (size_t)(ops[i].kind == 2 ? ops[i].K : 1) * t * t * pl->es;
+    (void)ob;
+    PW_CUDA(cudaMemcpyAsync(dev_ops[i], ops[i].op, exact, cudaMemcpyHostToDevice, pl->s_ops));
+  }
+  PW_CUDA(cudaEventRecord(slot.ops_ev, pl->s_ops));
+
+  pw_pipeline::Buf X = pl->pool.front(); pl->pool.pop_front();
+  pw_pipeline::Buf Z = pl->pool.front(); pl->pool.pop_front();
+
+  // upload
+  PW_CUDA(cudaStreamWaitEvent(pl->s_h2d, X.free_ev, 0));
+  PW_CUDA(cudaMemcpyAsync(X.p, h_state, pl->bytes, cudaMemcpyHostToDevice, pl->s_h2d));
+  PW_CUDA(cudaEventRecord(X.free_ev, pl->s_h2d));  // reused as "upload done"
+  // compute
+  PW_CUDA(cudaStreamWaitEvent(pl->s_comp, X.free_ev, 0));
+  PW_CUDA(cudaStreamWaitEvent(pl->s_comp, Z.free_ev, 0));
+  PW_CUDA(cudaStreamWaitEvent(pl->s_comp, slot.ops_ev, 0));
+  void* cur = X.p;
+  void* other = Z.p;
+  const int fuse = pw::options().fuse_pairs.load(std::memory_order_relaxed);
+  const int rc = run_ops(&cur, &other, pl->is_matrix, pl->dims, pl->n, ops, dev_ops.data(), nops,
+                         pl->dtype, fuse, pl->s_comp);
+  pw_pipeline::Buf R = (cur == X.p) ? X : Z;   // holds the result
+  pw_pipeline::Buf O = (cur == X.p) ? Z : X;   // free as soon as the kernels are done
+  cudaEventRecord(O.free_ev, pl->s_comp);
+  pl->pool.push_back(O);
+  if (rc != PW_OK) {
+    cudaEventRecord(R.free_ev, pl->s_comp);
+    pl->pool.push_back(R);
+    return rc;
+  }
+  // download
+  PW_CUDA(cudaStreamWaitEvent(pl->s_d2h, O.free_ev, 0));
+  PW_CUDA(cudaMemcpyAsync(h_out, R.p, pl->bytes, cudaMemcpyDeviceToHost, pl->s_d2h));
+  PW_CUDA(cudaEventRecord(R.free_ev, pl->s_d2h));
+  PW_CUDA(cudaEventRecord(slot.done_ev, pl->s_d2h));
+  pl->pool.push_back(R);
+  slot.ticket = tk;
+  pl->next_ticket = tk + 1;
+  if (ticket) *ticket = tk;
+  return PW_OK;
+}

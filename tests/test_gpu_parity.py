@@ -564,3 +564,41 @@ def test_occupancy_matches_reference_loop(dims):
     z = np.zeros((N, 1), dtype=np.complex64)
     levels, stats = ffi.occupancy(dev(z), dims, False)
     assert levels.tolist() == [-1] * len(dims) and float(stats[0]) == 0.0
+
+
+def test_host_pipeline_matches_serial_path():
+    """pw_pipeline_submit/wait: several jobs in flight with different inputs and operator
+    lists give exactly what pw_circuit_host gives, job by job."""
+    import torch
+
+    from photon_weave_b200.core import ffi
+
+    dims = (3, 4, 5, 2)
+    n = int(np.prod(dims))
+    jobs = []
+    for j in range(7):
+        psi = ops.random_state(n, 100 + j)
+        oplist = [(0, (j % 4,), ops.random_unitary(dims[j % 4], j)),
+               (0, (3, 1), ops.random_unitary(8, 50 + j))]
+        if j % 2:
+            oplist.append((0, (2,), ops.random_unitary(5, 70 + j)))  # odd count: result in the scratch
+        jobs.append((psi, oplist))
+    want = [ffi.circuit_host(psi, False, dims, oplist) for psi, oplist in jobs]
+    for nbuf in (2, 3, 4):
+        ins = [torch.as_tensor(psi.reshape(-1)).pin_memory().numpy() for psi, _ in jobs]
+        outs = [torch.empty(n, dtype=torch.complex128).pin_memory().numpy() for _ in jobs]
+        with ffi.HostPipeline(dims, False, np.complex128, buffers=nbuf) as pl:
+            assert pl.buffers == nbuf
+            tickets = [pl.submit(ins[j], outs[j], jobs[j][1]) for j in range(len(jobs))]
+            for tk in reversed(tickets):
+                pl.wait(tk)
+        for j in range(len(jobs)):
+            assert np.array_equal(outs[j].reshape(-1), want[j].reshape(-1)), (nbuf, j)
+    rho = ops.random_density(12, 5)
+    ks = ops.loss_channel(3, 0.2)
+    wantm = ffi.circuit_host(rho, True, (4, 3), [(1, (0,), ops.random_unitary(4, 1)), (2, (1,), ks)])
+    outm = np.empty_like(rho)
+    with ffi.HostPipeline((4, 3), True, np.complex128, buffers=2) as pl:
+        pl.wait(pl.submit(np.ascontiguousarray(rho), outm,
+                          [(1, (0,), ops.random_unitary(4, 1)), (2, (1,), ks)]))
+    assert np.array_equal(outm, wantm)
