@@ -56,6 +56,8 @@ Options& options() {
     env("PW_CONTIG_KERNEL", p->contig_kernel);
     env("PW_SMALL_R", p->small_r);
     env("PW_MAT_SUPER_SINGLE", p->mat_super_single);
+    env("PW_TWO_SIDED", p->two_sided);
+    env("PW_TS_CTAS", p->ts_ctas);
     return p;
   }();
   return *o;
@@ -77,6 +79,8 @@ extern "C" int pw_set_option(const char* name, int value) {
   else if (!std::strcmp(name, "contig_kernel")) o.contig_kernel.store(value);
   else if (!std::strcmp(name, "small_r")) o.small_r.store(value);
   else if (!std::strcmp(name, "mat_super_single")) o.mat_super_single.store(value);
+  else if (!std::strcmp(name, "two_sided")) o.two_sided.store(value);
+  else if (!std::strcmp(name, "ts_ctas")) o.ts_ctas.store(value);
   else return PW_ERR_INVALID;
   return PW_OK;
 }

@@ -588,6 +588,21 @@ static int matrix_dispatch(const void* rho, void* out, const void* ops, int K, c
     if (rc == PW_OK) skip = bd.skip_flag();
     else if (rc != PW_ERR_UNSUPPORTED) return rc;
   }
+  // single operator, untouched innermost axis: ONE pass through shared-memory tiles
+  // (dense d <= 8 operators, beam-splitter-like block structure); decided on the device
+  TwoSided ts;
+  if (K == 1 && mm == 0 && rho != out && r.t >= 2 && r.t <= kBlockMaxT && r.N * r.N >= blocks_min_elems() &&
+      options().two_sided.load(std::memory_order_relaxed)) {
+    Plan pb, pr, pc;
+    PW_TRY(build_plan_axes(r.axes, 2 * r.n, r.both, 2 * r.nt, &pb));
+    if (inner_rest_run(pb) >= 4) {
+      PW_TRY(build_plan_axes(r.axes, 2 * r.n, r.rows, r.nt, &pr));
+      PW_TRY(build_plan_axes(r.axes, 2 * r.n, r.cols, r.nt, &pc));
+      const int rc = launch_two_sided(rho, out, ops, pb.fm, pr.tm, pc.tm, dtype, skip, &ts, s);
+      if (rc == PW_OK) skip = ts.skip;
+      else if (rc != PW_ERR_UNSUPPORTED) return rc;
+    }
+  }
   // single-pass tiled kernel (operator pairs applied on the resident tile)
   // single operators: two register-kernel passes beat the tiled two-sided kernel (measured)
   const bool tiled_ok = mm == 2 || mm == 3 || (mm == 0 && (K > 1 || r.t > 8));

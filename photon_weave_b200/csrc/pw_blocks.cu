@@ -460,4 +460,121 @@ int launch_blocks_seg(const void* in, void* out, const void* op, const int64_t* 
   return PW_ERR_INVALID;
 }
 
+// ---- two-sided single pass: rho' = U rho U^dagger ------------------------------------------
+// The row side and the column side of a density-matrix update commute, but a thread that
+// owns a row-side fiber cannot reach across the column side.  Here a CTA stages one
+// (row block k) x (column block l) x (32 adjacent fibers) tile through shared memory:
+//
+//   stage 1  warp j (a column of block l) loads the nc_k inputs rho[C_k, C_l[j], fiber]
+//            (32 adjacent fibers per load = one coalesced 512 B row), multiplies by B_k and
+//            parks the nr_k results in shared memory;
+//   stage 2  warp i (a row of block k) reads its nc_l parked values, multiplies by
+//            conj(B_l) and streams the nr_l outputs to HBM, again one coalesced row each.
+//
+// Every element of rho is read once and written once: ONE HBM pass for U rho U^dagger with
+// a dense d <= 8 operator (one 8 x 8 block pair) or a block-structured two-mode operator
+// (beam splitter: photon-number sectors, 15 x 15 block pairs for d = 8), against the two
+// passes of the row-then-column route.  The innermost axis must not be a target (the
+// "fibers" are then adjacent in memory); structure is analysed on the device like for the
+// one-sided block kernel, `flags` carries the outcome to the fallback kernels.
+constexpr int kTsWarps = 8;
+constexpr uint32_t kTsDescCap = 10 * 1024;   // per side; BS d=8: 15 blocks, 128 offsets, 344 values
+
+struct TsFlags { int handled; int any; };
+
+__global__ void k_ts_flags(const BlockDescHeader* __restrict__ L, const BlockDescHeader* __restrict__ R,
+                           const int* __restrict__ other, TsFlags* __restrict__ f) {
+  const int o = other ? *other : 0;
+  const int h = (!o && L->usable && R->usable && L->nzero == 0 && R->nzero == 0 && L->maxn >= 2) ? 1 : 0;
+  f->handled = h;
+  f->any = (h || o) ? 1 : 0;
+}
+
+template <typename V>
+__global__ void __launch_bounds__(kTsWarps * 32, 3)
+k_two_sided(const V* __restrict__ in, V* __restrict__ out, const FiberMap fm, const BlockArrays L,
+            const BlockArrays R, const TsFlags* __restrict__ flags) {
+  if (!flags->handled) return;
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const DescView<V> dl = desc_view<V>(L, s_raw, kTsDescCap);
+  const DescView<V> dr = desc_view<V>(R, s_raw + kTsDescCap, kTsDescCap);
+  V* tile = (V*)(s_raw + 2 * kTsDescCap);  // [i < 8][j < 8][lane < 32]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t chunks = (fm.nfib + 31) / 32;
+  const uint32_t npairs = (uint32_t)dl.nblocks * (uint32_t)dr.nblocks;
+  const uint64_t units = chunks * npairs;
+  for (uint64_t u = blockIdx.x; u < units; u += gridDim.x) {
+    const uint64_t c = u / npairs;
+    const uint32_t pr = (uint32_t)(u - c * npairs);
+    const uint32_t k = pr / (uint32_t)dr.nblocks, l = pr - k * (uint32_t)dr.nblocks;
+    const uint64_t f = c * 32 + lane;
+    const bool live = f < fm.nfib;
+    const int64_t base = live ? fm.base(f) : 0;
+    const int4 hk = dl.blocks[k], hl = dr.blocks[l];
+    const int64_t* ko = dl.offs + hk.z;   // nc_k input row offsets, then nr_k output row offsets
+    const int64_t* lo = dr.offs + hl.z;   // nc_l input column offsets, then nr_l output column offsets
+    if (live) {
+      for (int j = warp; j < hl.y; j += kTsWarps) {
+        const V* src = in + base + lo[j];
+        block_product<V>(dl.vals + hk.w, hk.x, hk.y,
+                         [&](int a) { return __ldcg(src + ko[a]); },
+                         [&](int i, V v) { tile[(i * 8 + j) * 32 + lane] = v; });
+      }
+    }
+    __syncthreads();
+    if (live) {
+      for (int i = warp; i < hk.x; i += kTsWarps) {
+        V* dst = out + base + ko[hk.y + i];
+        block_product<V>(dr.vals + hl.w, hl.x, hl.y,
+                         [&](int b) { return tile[(i * 8 + b) * 32 + lane]; },
+                         [&](int j, V v) { __stcg(dst + lo[hl.y + j], v); });
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename V>
+static int launch_two_sided_t(const V* rho, V* out, const V* op, const FiberMap& fm,
+                              const TargetMap& rows, const TargetMap& cols, const int* other,
+                              TwoSided* ts, cudaStream_t s) {
+  PW_TRY(build_block_desc_t<V>(op, rows.t, false, rows, &ts->memL, &ts->L, s));
+  PW_TRY(build_block_desc_t<V>(op, cols.t, true, cols, &ts->memR, &ts->R, s));
+  PW_TRY(ts->flag_mem.alloc(sizeof(TsFlags), s));
+  TsFlags* flags = (TsFlags*)ts->flag_mem.p;
+  k_ts_flags<<<1, 1, 0, s>>>(ts->L.hdr, ts->R.hdr, other, flags);
+  PW_LAUNCHED();
+  const size_t smem = 2 * kTsDescCap + sizeof(V) * 8 * 8 * 32;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PW_CUDA(cudaFuncSetAttribute(k_two_sided<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(2 * kTsDescCap + sizeof(double2) * 8 * 8 * 32)));
+    PW_CUDA(cudaFuncSetAttribute(k_two_sided<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(2 * kTsDescCap + sizeof(float2) * 8 * 8 * 32)));
+    attr_set = true;
+  }
+  const int per_sm = options().ts_ctas.load(std::memory_order_relaxed);
+  k_two_sided<V><<<kNumSMs * (per_sm > 0 ? per_sm : 3), kTsWarps * 32, smem, s>>>(rho, out, fm, ts->L, ts->R, flags);
+  PW_LAUNCHED();
+  g_paths[4].fetch_add(1, std::memory_order_relaxed);
+  ts->skip = &flags->any;
+  return PW_OK;
+}
+
+int launch_two_sided(const void* rho, void* out, const void* op, const FiberMap& fm,
+                     const TargetMap& rows, const TargetMap& cols, int dtype, const int* other_handled,
+                     TwoSided* ts, cudaStream_t stream) {
+  if (rho == out || rows.t != cols.t || rows.t > kBlockMaxT) return PW_ERR_UNSUPPORTED;
+  // the descriptor copies must fit their shared-memory slots: blocks + offsets + values
+  const size_t vsz = dtype == PW_C128 ? 16 : 8;
+  if (rows.t * 16 + rows.t * 2 * 8 + (size_t)rows.t * kBlockMaxN * vsz + 64 > kTsDescCap) return PW_ERR_UNSUPPORTED;
+  if (dtype == PW_C128)
+    return launch_two_sided_t<double2>((const double2*)rho, (double2*)out, (const double2*)op, fm, rows,
+                                       cols, other_handled, ts, stream);
+  if (dtype == PW_C64)
+    return launch_two_sided_t<float2>((const float2*)rho, (float2*)out, (const float2*)op, fm, rows,
+                                      cols, other_handled, ts, stream);
+  return PW_ERR_INVALID;
+}
+
 }  // namespace pw

@@ -133,4 +133,19 @@ int launch_blocks_seg(const void* in, void* out, const void* op, const int64_t* 
                       const int* targets, int nt, int dtype, bool conj_op, BlockDesc* desc,
                       cudaStream_t stream);
 
+// Two-sided single pass rho' = U rho U^dagger for a dense d <= 8 or block-structured operator
+// (see pw_blocks.cu).  `fm` enumerates the fibers of the doubled tensor (every axis that is
+// neither a row nor a column target), `rows` / `cols` map the operator index to element
+// offsets on the two sides.  `other_handled` (device flag or nullptr): a path enqueued
+// earlier that already produced `out`.  After the call `ts->skip` is the device flag the
+// fallback kernels must honour.  Requires rho != out and an untouched innermost axis.
+struct TwoSided {
+  Scratch memL, memR, flag_mem;
+  BlockArrays L, R;
+  const int* skip = nullptr;
+};
+int launch_two_sided(const void* rho, void* out, const void* op, const FiberMap& fm,
+                     const TargetMap& rows, const TargetMap& cols, int dtype, const int* other_handled,
+                     TwoSided* ts, cudaStream_t stream);
+
 }  // namespace pw

@@ -182,6 +182,8 @@ struct Options {
   std::atomic<int> seg_kernel{1};              // warp-staged block kernel for innermost-target layouts
   std::atomic<int> nstage{0};                  // tiled kernel pipeline depth (0 = auto)
   std::atomic<int> blocks_min_elems{1 << 18};  // below this, skip structure analysis
+  std::atomic<int> two_sided{1};               // single-pass U rho U^dagger through shared-memory tiles
+  std::atomic<int> ts_ctas{0};                 // CTAs per SM of that kernel (0 = default 3)
 };
 Options& options();
 

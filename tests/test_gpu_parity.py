@@ -602,3 +602,43 @@ def test_host_pipeline_matches_serial_path():
         pl.wait(pl.submit(np.ascontiguousarray(rho), outm,
                           [(1, (0,), ops.random_unitary(4, 1)), (2, (1,), ks)]))
     assert np.array_equal(outm, wantm)
+
+
+@pytest.mark.parametrize("cdtype", [np.complex128, np.complex64])
+def test_two_sided_single_pass_kernel(ad, cdtype):
+    """U rho U^dagger through the shared-memory two-sided kernel (dense d <= 8 operators and
+    block-structured two-mode operators, innermost axis untouched), including ragged fiber
+    counts, operator-order targets and the operators it must hand to the fallbacks (zero rows,
+    diagonal, blocks larger than 8)."""
+    from photon_weave_b200 import _lib
+
+    tol = TOL[cdtype]
+
+    def check(dims, targets, op, seed):
+        N = math.prod(dims)
+        rho = ops.random_density(N, seed, dtype=cdtype)
+        ref = oad.apply_operation_matrix(dims, targets, rho.astype(np.complex128),
+                                         np.asarray(op, dtype=np.complex128), True)
+        out = host(ad.apply_operation_matrix(dims, targets, dev(rho), dev(np.asarray(op, dtype=cdtype))))
+        assert rel_err(out, ref) < tol, (dims, targets)
+
+    # large enough for the structured paths without touching the tuning knobs
+    check((8, 8, 10), (0,), ops.random_unitary(8, 1), 1)
+    check((8, 8, 10), (1,), ops.displacement_operator(8, 0.4), 2)
+    check((8, 8, 10), (0, 1), ops.beam_splitter(8, 8, 0.6), 3)
+    check((8, 8, 10), (1, 0), ops.beam_splitter(8, 8, 0.6), 4)
+    check((6, 5, 7, 3), (1,), ops.random_unitary(5, 5), 5)
+    check((6, 5, 7, 3), (2, 0), ops.beam_splitter(7, 6, 0.3), 6)
+    _lib.set_option("blocks_min_elems", 0)
+    try:
+        for tg in [(0,), (1,), (0, 1), (1, 0)]:
+            t = math.prod((3, 4, 5)[i] for i in tg)
+            check((3, 4, 5), tg, ops.random_unitary(t, 7) if t <= 8 else
+                  ops.beam_splitter(*[(3, 4, 5)[i] for i in tg], 0.5), 7)
+        check((4, 6, 9), (1,), ops.annihilation_operator(6) + 0.1 * np.eye(6), 8)
+        check((4, 6, 9), (1,), ops.annihilation_operator(6), 9)          # zero row: fallback
+        check((4, 6, 9), (1,), ops.phase_operator(6, 0.3), 10)           # diagonal: scalar blocks
+        check((4, 4, 9), (0, 1), ops.random_unitary(16, 11), 11)         # one 16 x 16 block: fallback
+        check((2, 2, 2, 7), (2, 0), ops.random_unitary(4, 12), 12)
+    finally:
+        _lib.set_option("blocks_min_elems", 1 << 18)

@@ -136,8 +136,9 @@ def bench_mat(args):
             ms, best = timeit(lambda: ffi.apply_mat(a, ph, dims, (1,), out=b), reps=3, warm=1)
             report(f"{tag} apply_mat phase axis 1", ms, best, nbytes)
             if args.slow:
-                ms, best = timeit(lambda: ffi.apply_mat(a, bs, dims, (1, 2), out=b), reps=2, warm=1)
-                report(f"{tag} apply_mat beam splitter (1,2)", ms, best, nbytes)
+                for pair in [(0, 1), (1, 2), (modes - 2, modes - 1), (modes - 1, 0)]:
+                    ms, best = timeit(lambda: ffi.apply_mat(a, bs, dims, pair, out=b), reps=3, warm=1)
+                    report(f"{tag} apply_mat beam splitter {pair}", ms, best, nbytes)
     ms, best = timeit(lambda: ffi.probs(a.reshape(D, D), dims, (1,), True))
     report("probs_mat one mode (diagonal only)", ms, best, D * es)
     ms, best = timeit(lambda: ffi.trace_out_mat(a.reshape(D, D), dims, (1,)))
