@@ -544,13 +544,15 @@ static int two_pass(const void* rho, void* out, const void* ops, int K, const Ma
                     int dtype, cudaStream_t s, const int* skip) {
   const size_t es = elem_size(dtype);
   if (K == 1) {
-    if (r.t > 8 && !skip && rho != out) {
+    if (r.t > 8 && rho != out) {
       // large operators: keep BOTH sides out of place (rho -> tmp -> out) so each side can
       // take the block-structured kernels (a beam splitter on rho: 2 x ~90 % passes)
       Scratch tmp2;
       if (tmp2.alloc((size_t)(r.N * r.N) * es, s) == PW_OK) {
-        PW_TRY(apply_side(rho, tmp2.p, ops, r, false, false, dtype, s, nullptr));
-        return apply_side(tmp2.p, out, ops, r, true, false, dtype, s, nullptr);
+        // (with a skip flag the sides run the skippable kernels; in place would cost an
+        // unconditional copy of rho)
+        PW_TRY(apply_side(rho, tmp2.p, ops, r, false, false, dtype, s, skip));
+        return apply_side(tmp2.p, out, ops, r, true, false, dtype, s, skip);
       }
     }
     PW_TRY(apply_side(rho, out, ops, r, false, false, dtype, s, skip));

@@ -462,76 +462,184 @@ int launch_blocks_seg(const void* in, void* out, const void* op, const int64_t* 
 
 // ---- two-sided single pass: rho' = U rho U^dagger ------------------------------------------
 // The row side and the column side of a density-matrix update commute, but a thread that
-// owns a row-side fiber cannot reach across the column side.  Here a CTA stages one
-// (row block k) x (column block l) x (32 adjacent fibers) tile through shared memory:
+// owns a row-side fiber cannot reach across the column side.  Here a CTA stages tiles of
+// (row block k) x (column block l) x (32 adjacent fibers) through shared memory:
 //
-//   stage 1  warp j (a column of block l) loads the nc_k inputs rho[C_k, C_l[j], fiber]
-//            (32 adjacent fibers per load = one coalesced 512 B row), multiplies by B_k and
-//            parks the nr_k results in shared memory;
-//   stage 2  warp i (a row of block k) reads its nc_l parked values, multiplies by
-//            conj(B_l) and streams the nr_l outputs to HBM, again one coalesced row each.
+//   load     cp.async copies the tile (one coalesced 512 B row per operator index pair) into
+//            shared memory -- for the NEXT tile while the current one is being computed;
+//   stage 1  a warp takes one column of a block pair, multiplies its nc_k values by B_k and
+//            writes the results back in place;
+//   stage 2  a warp takes one row, multiplies by conj(B_l) and streams the outputs to HBM,
+//            again one coalesced row per store.
 //
-// Every element of rho is read once and written once: ONE HBM pass for U rho U^dagger with
-// a dense d <= 8 operator (one 8 x 8 block pair) or a block-structured two-mode operator
-// (beam splitter: photon-number sectors, 15 x 15 block pairs for d = 8), against the two
-// passes of the row-then-column route.  The innermost axis must not be a target (the
-// "fibers" are then adjacent in memory); structure is analysed on the device like for the
-// one-sided block kernel, `flags` carries the outcome to the fallback kernels.
+// Every element of rho is read once and written once: ONE HBM pass for U rho U^dagger with a
+// dense d <= 8 operator (one 8 x 8 block pair) or a block-structured two-mode operator (beam
+// splitter: photon-number sectors, 15 x 15 block pairs for d = 8), against the two passes of
+// the row-then-column route.  Small block pairs are packed into 64-slot groups so that the
+// eight warps stay busy.  The innermost axis must not be a target (the 32 fibers of a tile are
+// then adjacent in memory).  Structure is analysed on the device like for the one-sided block
+// kernel; `flags` carries the outcome to the fallback kernels.
 constexpr int kTsWarps = 8;
-constexpr uint32_t kTsDescCap = 10 * 1024;   // per side; BS d=8: 15 blocks, 128 offsets, 344 values
+constexpr int kTsSlots = 64;                 // tile = 64 slots x 32 lanes
+constexpr uint32_t kTsValCap = 8 * 1024;     // per side: block values (BS d=8: 344 x 16 B)
 
-struct TsFlags { int handled; int any; };
+struct TsFlags { int handled; int any; int ngroups; int pad; };
 
-__global__ void k_ts_flags(const BlockDescHeader* __restrict__ L, const BlockDescHeader* __restrict__ R,
-                           const int* __restrict__ other, TsFlags* __restrict__ f) {
-  const int o = other ? *other : 0;
-  const int h = (!o && L->usable && R->usable && L->nzero == 0 && R->nzero == 0 && L->maxn >= 2) ? 1 : 0;
-  f->handled = h;
-  f->any = (h || o) ? 1 : 0;
-}
+struct TsTables {
+  TsFlags* flags;
+  int4* groups;        // 2 per group: (slot0, nslots, item1_0, nitems1), (item2_0, nitems2, -, -)
+  int4* pairs;         // scratch of the builder: (k, l, slot0, group)
+  int64_t* in_off;     // [t*t] element offset of every slot (input side)
+  int64_t* out_off;    // [t*t] (output side)
+  int4* item1;         // (slot in tile, n, stride, value offset)   stage 1: a column of a pair
+  int4* item2;         // (slot in tile, n, value offset, -)        stage 2: a row of a pair
+};
 
 template <typename V>
-__global__ void __launch_bounds__(kTsWarps * 32, 3)
-k_two_sided(const V* __restrict__ in, V* __restrict__ out, const FiberMap fm, const BlockArrays L,
-            const BlockArrays R, const TsFlags* __restrict__ flags) {
-  if (!flags->handled) return;
-  extern __shared__ __align__(16) unsigned char s_raw[];
-  const DescView<V> dl = desc_view<V>(L, s_raw, kTsDescCap);
-  const DescView<V> dr = desc_view<V>(R, s_raw + kTsDescCap, kTsDescCap);
-  V* tile = (V*)(s_raw + 2 * kTsDescCap);  // [i < 8][j < 8][lane < 32]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint64_t chunks = (fm.nfib + 31) / 32;
-  const uint32_t npairs = (uint32_t)dl.nblocks * (uint32_t)dr.nblocks;
-  const uint64_t units = chunks * npairs;
-  for (uint64_t u = blockIdx.x; u < units; u += gridDim.x) {
-    const uint64_t c = u / npairs;
-    const uint32_t pr = (uint32_t)(u - c * npairs);
-    const uint32_t k = pr / (uint32_t)dr.nblocks, l = pr - k * (uint32_t)dr.nblocks;
-    const uint64_t f = c * 32 + lane;
-    const bool live = f < fm.nfib;
-    const int64_t base = live ? fm.base(f) : 0;
-    const int4 hk = dl.blocks[k], hl = dr.blocks[l];
-    const int64_t* ko = dl.offs + hk.z;   // nc_k input row offsets, then nr_k output row offsets
-    const int64_t* lo = dr.offs + hl.z;   // nc_l input column offsets, then nr_l output column offsets
-    if (live) {
-      for (int j = warp; j < hl.y; j += kTsWarps) {
-        const V* src = in + base + lo[j];
-        block_product<V>(dl.vals + hk.w, hk.x, hk.y,
-                         [&](int a) { return __ldcg(src + ko[a]); },
-                         [&](int i, V v) { tile[(i * 8 + j) * 32 + lane] = v; });
-      }
+__global__ void __launch_bounds__(256)
+k_ts_build(const BlockArrays L, const BlockArrays R, const int* __restrict__ other, const TsTables T,
+           const uint32_t val_cap) {
+  __shared__ int s_handled, s_npairs;
+  const BlockDescHeader* hl = L.hdr;
+  const BlockDescHeader* hr = R.hdr;
+  if (threadIdx.x == 0) {
+    const int o = other ? *other : 0;
+    int h = (!o && hl->usable && hr->usable && hl->nzero == 0 && hr->nzero == 0 && hl->maxn >= 2 &&
+             hl->nblocks == hr->nblocks) ? 1 : 0;
+    if (h && ((uint32_t)hl->n_vals * sizeof(V) > val_cap || (uint32_t)hr->n_vals * sizeof(V) > val_cap)) h = 0;
+    if (h)
+      for (int b = 0; b < hl->nblocks && h; ++b)
+        if (L.blocks[b].x != L.blocks[b].y || R.blocks[b].x != R.blocks[b].y) h = 0;  // in place: square blocks
+    int ng = 0;
+    if (h) {
+      // greedy packing of the block pairs (k major) into groups of <= kTsSlots slots
+      const int m = hl->nblocks;
+      int slot0 = 0, used = 0, gslot0 = 0, it1 = 0, it2 = 0, git1 = 0, git2 = 0, np = 0;
+      for (int k = 0; k < m; ++k)
+        for (int l = 0; l < m; ++l) {
+          const int nk = L.blocks[k].y, nl = R.blocks[l].y, sz = nk * nl;
+          if (used + sz > kTsSlots) {
+            T.groups[2 * ng] = make_int4(gslot0, used, git1, it1 - git1);
+            T.groups[2 * ng + 1] = make_int4(git2, it2 - git2, 0, 0);
+            ++ng; gslot0 = slot0; used = 0; git1 = it1; git2 = it2;
+          }
+          T.pairs[np++] = make_int4(k, l, slot0, (it1 << 16) | it2);  // item offsets fit 16 bits (t <= 128)
+          slot0 += sz; used += sz; it1 += nl; it2 += nk;
+        }
+      T.groups[2 * ng] = make_int4(gslot0, used, git1, it1 - git1);
+      T.groups[2 * ng + 1] = make_int4(git2, it2 - git2, 0, 0);
+      ++ng;
+      s_npairs = np;
     }
-    __syncthreads();
-    if (live) {
-      for (int i = warp; i < hk.x; i += kTsWarps) {
-        V* dst = out + base + ko[hk.y + i];
-        block_product<V>(dr.vals + hl.w, hl.x, hl.y,
-                         [&](int b) { return tile[(i * 8 + b) * 32 + lane]; },
-                         [&](int j, V v) { __stcg(dst + lo[hl.y + j], v); });
-      }
-    }
-    __syncthreads();
+    T.flags->handled = h;
+    T.flags->any = (h || o) ? 1 : 0;
+    T.flags->ngroups = ng;
+    s_handled = h;
   }
+  __syncthreads();
+  if (!s_handled) return;
+  // group start slot of every pair: recover by scanning groups (few); then fill the tables
+  const int ng = T.flags->ngroups;
+  for (int p = threadIdx.x; p < s_npairs; p += blockDim.x) {
+    const int4 pr = T.pairs[p];
+    const int k = pr.x, l = pr.y, slot0 = pr.z, it1 = pr.w >> 16, it2 = pr.w & 0xffff;
+    int g = 0;
+    while (g + 1 < ng && T.groups[2 * (g + 1)].x <= slot0) ++g;
+    const int local0 = slot0 - T.groups[2 * g].x;
+    const int4 hk = L.blocks[k], hq = R.blocks[l];
+    const int nk = hk.y, nl = hq.y;
+    const int64_t* ko = L.offs + hk.z;
+    const int64_t* lo = R.offs + hq.z;
+    for (int a = 0; a < nk; ++a)
+      for (int b = 0; b < nl; ++b) {
+        T.in_off[slot0 + a * nl + b] = ko[a] + lo[b];
+        T.out_off[slot0 + a * nl + b] = ko[nk + a] + lo[nl + b];
+      }
+    for (int j = 0; j < nl; ++j) T.item1[it1 + j] = make_int4(local0 + j, nk, nl, hk.w);
+    for (int i2 = 0; i2 < nk; ++i2) T.item2[it2 + i2] = make_int4(local0 + i2 * nl, nl, hq.w, 0);
+  }
+}
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename V>
+__global__ void __launch_bounds__(kTsWarps * 32, 2)
+k_two_sided(const V* __restrict__ in, V* __restrict__ out, const FiberMap fm, const BlockArrays L,
+            const BlockArrays R, const TsTables T) {
+  if (!T.flags->handled) return;
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  V* vl = (V*)s_raw;                       // row-side block values
+  V* vr = (V*)(s_raw + kTsValCap);         // column-side block values (already conjugated)
+  V* tile0 = (V*)(s_raw + 2 * kTsValCap);  // [2][kTsSlots][32]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < L.hdr->n_vals; i += blockDim.x) vl[i] = ((const V*)L.vals)[i];
+  for (int i = threadIdx.x; i < R.hdr->n_vals; i += blockDim.x) vr[i] = ((const V*)R.vals)[i];
+  const uint32_t G = (uint32_t)T.flags->ngroups;
+  const uint64_t chunks = (fm.nfib + 31) / 32;
+  const uint64_t units = chunks * G;
+
+  auto issue = [&](uint64_t u, V* tile, int64_t* base_out) {
+    // chunk index fastest: CTAs that run side by side work on adjacent memory with the same
+    // slot offsets (DRAM page and TLB locality)
+    const uint32_t g = (uint32_t)(u / chunks);
+    const uint64_t c = u - (uint64_t)g * chunks;
+    const uint64_t f = c * 32 + lane;
+    const int64_t base = f < fm.nfib ? fm.base(f) : -1;
+    *base_out = base;
+    if (base >= 0) {
+      const int4 g0 = __ldg(T.groups + 2 * g);
+      const int64_t* off = T.in_off + g0.x;
+      for (int sl = warp; sl < g0.y; sl += kTsWarps) {
+        const V* src = in + base + __ldg(off + sl);
+        if (sizeof(V) == 16) cp_async16(tile + sl * 32 + lane, src); else cp_async8(tile + sl * 32 + lane, src);
+      }
+    }
+    cp_async_commit();
+  };
+
+  uint64_t u = blockIdx.x;
+  int64_t base_cur = -1, base_next = -1;
+  int cur = 0;
+  if (u < units) issue(u, tile0, &base_cur);
+  for (; u < units; u += gridDim.x) {
+    V* tile = tile0 + (size_t)cur * kTsSlots * 32;
+    const uint64_t un = u + gridDim.x;
+    if (un < units) issue(un, tile0 + (size_t)(cur ^ 1) * kTsSlots * 32, &base_next);
+    else cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    const uint32_t g = (uint32_t)(u / chunks);
+    const int4 g0 = __ldg(T.groups + 2 * g), g1 = __ldg(T.groups + 2 * g + 1);
+    if (base_cur >= 0) {
+      for (int it = warp; it < g0.w; it += kTsWarps) {
+        const int4 w = __ldg(T.item1 + g0.z + it);
+        V* col = tile + w.x * 32 + lane;
+        const int stride = w.z * 32;
+        block_product<V, 4>(vl + w.w, w.y, w.y,
+                         [&](int a) { return col[a * stride]; },
+                         [&](int i, V v) { col[i * stride] = v; });
+      }
+    }
+    __syncthreads();
+    if (base_cur >= 0) {
+      const int64_t* oo = T.out_off + g0.x;
+      for (int it = warp; it < g1.y; it += kTsWarps) {
+        const int4 w = __ldg(T.item2 + g1.x + it);
+        const V* row = tile + w.x * 32 + lane;
+        V* dst = out + base_cur;
+        const int64_t* ro = oo + w.x;
+        block_product<V, 4>(vr + w.z, w.y, w.y,
+                         [&](int b) { return row[b * 32]; },
+                         [&](int j, V v) { __stcg(dst + __ldg(ro + j), v); });
+      }
+    }
+    __syncthreads();
+    base_cur = base_next;
+    cur ^= 1;
+  }
+  cp_async_wait<0>();
 }
 
 template <typename V>
@@ -540,24 +648,36 @@ static int launch_two_sided_t(const V* rho, V* out, const V* op, const FiberMap&
                               TwoSided* ts, cudaStream_t s) {
   PW_TRY(build_block_desc_t<V>(op, rows.t, false, rows, &ts->memL, &ts->L, s));
   PW_TRY(build_block_desc_t<V>(op, cols.t, true, cols, &ts->memR, &ts->R, s));
-  PW_TRY(ts->flag_mem.alloc(sizeof(TsFlags), s));
-  TsFlags* flags = (TsFlags*)ts->flag_mem.p;
-  k_ts_flags<<<1, 1, 0, s>>>(ts->L.hdr, ts->R.hdr, other, flags);
+  const size_t t = rows.t, tt = t * t;
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t b_flags = 256, b_groups = al(sizeof(int4) * 2 * tt), b_pairs = al(sizeof(int4) * tt),
+               b_off = al(sizeof(int64_t) * tt), b_item = al(sizeof(int4) * tt);
+  PW_TRY(ts->flag_mem.alloc(b_flags + b_groups + b_pairs + 2 * b_off + 2 * b_item, s));
+  char* base = (char*)ts->flag_mem.p;
+  TsTables T;
+  T.flags = (TsFlags*)base;
+  T.groups = (int4*)(base + b_flags);
+  T.pairs = (int4*)(base + b_flags + b_groups);
+  T.in_off = (int64_t*)(base + b_flags + b_groups + b_pairs);
+  T.out_off = (int64_t*)(base + b_flags + b_groups + b_pairs + b_off);
+  T.item1 = (int4*)(base + b_flags + b_groups + b_pairs + 2 * b_off);
+  T.item2 = (int4*)(base + b_flags + b_groups + b_pairs + 2 * b_off + b_item);
+  k_ts_build<V><<<1, 256, 0, s>>>(ts->L, ts->R, other, T, kTsValCap);
   PW_LAUNCHED();
-  const size_t smem = 2 * kTsDescCap + sizeof(V) * 8 * 8 * 32;
+  const size_t smem = 2 * kTsValCap + sizeof(V) * 2 * kTsSlots * 32;
   static bool attr_set = false;
   if (!attr_set) {
     PW_CUDA(cudaFuncSetAttribute(k_two_sided<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(2 * kTsDescCap + sizeof(double2) * 8 * 8 * 32)));
+                                 (int)(2 * kTsValCap + sizeof(double2) * 2 * kTsSlots * 32)));
     PW_CUDA(cudaFuncSetAttribute(k_two_sided<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(2 * kTsDescCap + sizeof(float2) * 8 * 8 * 32)));
+                                 (int)(2 * kTsValCap + sizeof(float2) * 2 * kTsSlots * 32)));
     attr_set = true;
   }
   const int per_sm = options().ts_ctas.load(std::memory_order_relaxed);
-  k_two_sided<V><<<kNumSMs * (per_sm > 0 ? per_sm : 3), kTsWarps * 32, smem, s>>>(rho, out, fm, ts->L, ts->R, flags);
+  k_two_sided<V><<<kNumSMs * (per_sm > 0 ? per_sm : 2), kTsWarps * 32, smem, s>>>(rho, out, fm, ts->L, ts->R, T);
   PW_LAUNCHED();
   g_paths[4].fetch_add(1, std::memory_order_relaxed);
-  ts->skip = &flags->any;
+  ts->skip = &T.flags->any;
   return PW_OK;
 }
 
@@ -565,9 +685,6 @@ int launch_two_sided(const void* rho, void* out, const void* op, const FiberMap&
                      const TargetMap& rows, const TargetMap& cols, int dtype, const int* other_handled,
                      TwoSided* ts, cudaStream_t stream) {
   if (rho == out || rows.t != cols.t || rows.t > kBlockMaxT) return PW_ERR_UNSUPPORTED;
-  // the descriptor copies must fit their shared-memory slots: blocks + offsets + values
-  const size_t vsz = dtype == PW_C128 ? 16 : 8;
-  if (rows.t * 16 + rows.t * 2 * 8 + (size_t)rows.t * kBlockMaxN * vsz + 64 > kTsDescCap) return PW_ERR_UNSUPPORTED;
   if (dtype == PW_C128)
     return launch_two_sided_t<double2>((const double2*)rho, (double2*)out, (const double2*)op, fm, rows,
                                        cols, other_handled, ts, stream);

@@ -83,12 +83,27 @@ __device__ __forceinline__ DescView<V> desc_view(const BlockArrays& A, unsigned 
 
 // y[rows] = B (nr x NC, dense) x[cols]; NC is a compile-time constant so the NC inputs
 // live in registers without predication.
-template <typename V, int NC, typename LoadX, typename StoreY>
+template <typename V, int NC, int UR, typename LoadX, typename StoreY>
 __device__ __forceinline__ void block_product_nc(const V* __restrict__ bv, const int nr, LoadX ldx, StoreY sty) {
   V x[NC];
 #pragma unroll
   for (int j = 0; j < NC; ++j) x[j] = ldx(j);
-  for (int a = 0; a < nr; ++a) {
+  // four output rows at a time: eight independent FMA chains per thread keep the FP64 pipe
+  // busy at low occupancy (the dependent chain of one row is 2 * NC FMAs long)
+  int a = 0;
+  if (UR >= 4)
+  for (; a + 4 <= nr; a += 4) {
+    V acc0 = czero<V>(), acc1 = czero<V>(), acc2 = czero<V>(), acc3 = czero<V>();
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      cfma(acc0, bv[a * NC + j], x[j]);
+      cfma(acc1, bv[(a + 1) * NC + j], x[j]);
+      cfma(acc2, bv[(a + 2) * NC + j], x[j]);
+      cfma(acc3, bv[(a + 3) * NC + j], x[j]);
+    }
+    sty(a, acc0); sty(a + 1, acc1); sty(a + 2, acc2); sty(a + 3, acc3);
+  }
+  for (; a < nr; ++a) {
     V acc = czero<V>();
 #pragma unroll
     for (int j = 0; j < NC; ++j) cfma(acc, bv[a * NC + j], x[j]);
@@ -96,17 +111,17 @@ __device__ __forceinline__ void block_product_nc(const V* __restrict__ bv, const
   }
 }
 
-template <typename V, typename LoadX, typename StoreY>
+template <typename V, int UR = 1, typename LoadX, typename StoreY>
 __device__ __forceinline__ void block_product(const V* __restrict__ bv, const int nr, const int nc, LoadX ldx, StoreY sty) {
   switch (nc) {
-    case 1: block_product_nc<V, 1>(bv, nr, ldx, sty); break;
-    case 2: block_product_nc<V, 2>(bv, nr, ldx, sty); break;
-    case 3: block_product_nc<V, 3>(bv, nr, ldx, sty); break;
-    case 4: block_product_nc<V, 4>(bv, nr, ldx, sty); break;
-    case 5: block_product_nc<V, 5>(bv, nr, ldx, sty); break;
-    case 6: block_product_nc<V, 6>(bv, nr, ldx, sty); break;
-    case 7: block_product_nc<V, 7>(bv, nr, ldx, sty); break;
-    case 8: block_product_nc<V, 8>(bv, nr, ldx, sty); break;
+    case 1: block_product_nc<V, 1, UR>(bv, nr, ldx, sty); break;
+    case 2: block_product_nc<V, 2, UR>(bv, nr, ldx, sty); break;
+    case 3: block_product_nc<V, 3, UR>(bv, nr, ldx, sty); break;
+    case 4: block_product_nc<V, 4, UR>(bv, nr, ldx, sty); break;
+    case 5: block_product_nc<V, 5, UR>(bv, nr, ldx, sty); break;
+    case 6: block_product_nc<V, 6, UR>(bv, nr, ldx, sty); break;
+    case 7: block_product_nc<V, 7, UR>(bv, nr, ldx, sty); break;
+    case 8: block_product_nc<V, 8, UR>(bv, nr, ldx, sty); break;
     default: break;  // nc == 0 cannot occur (blocks have >= 1 column); nc > 8 is not `usable`
   }
 }
