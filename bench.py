@@ -469,6 +469,7 @@ def run_matrix_extras(torch, ffi, peak):
     loss = dev(ops.loss_channel(d, 0.1))
     u = dev(ops.random_unitary(d, 1))
     ph = dev(ops.phase_operator(d, 0.3))
+    bs = dev(ops.beam_splitter(d, d, math.pi / 4))
 
     def timed(fn, reps=3):
         fn()
@@ -487,6 +488,7 @@ def run_matrix_extras(torch, ffi, peak):
         ("kraus_loss_K8_mode2", lambda: ffi.kraus_mat(rho, loss, dims, (2,), out=out)),
         ("apply_phase_mode1", lambda: ffi.apply_mat(rho, ph, dims, (1,), out=out)),
         ("apply_dense_8x8_mode2", lambda: ffi.apply_mat(rho, u, dims, (2,), out=out)),
+        ("apply_beam_splitter_modes_1_2", lambda: ffi.apply_mat(rho, bs, dims, (1, 2), out=out)),
     ]:
         ms = timed(fn)
         gbs = nbytes / (ms * 1e-3) / 1e9
