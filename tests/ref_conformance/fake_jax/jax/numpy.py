@@ -73,7 +73,9 @@ for _name in ["array", "asarray", "allclose", "sqrt", "zeros", "conj", "conjugat
               "ones_like", "zeros_like", "matmul", "copy", "vstack", "hstack", "transpose", "reshape",
               "clip", "all", "any", "array_equal", "ones", "abs", "sum", "prod", "outer", "dot", "angle",
               "identity", "linspace", "max", "min", "argmax", "where", "nonzero", "concatenate", "log",
-              "power", "cumsum", "tensordot", "einsum", "squeeze", "expand_dims", "isnan", "pad", "take"]:
+              "power", "cumsum", "tensordot", "einsum", "squeeze", "expand_dims", "isnan", "pad", "take",
+              "mean", "std", "var", "round", "floor", "ceil", "log2", "log10", "tan", "arctan2", "sign", "mod",
+              "maximum", "minimum", "argmin", "sort", "unique", "flip", "roll", "tile", "repeat", "full", "empty"]:
     globals()[_name] = _lift(getattr(_np, _name))
 
 

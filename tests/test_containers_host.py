@@ -29,3 +29,22 @@ def _fresh_config():
 def test_container_case_on_host_shim(case):
     with host_shim.host_backend():
         case()
+
+
+def test_examples_on_host_shim():
+    """examples/ against their analytic results (host logic; the CUDA run is in
+    test_gpu_containers.py)."""
+    import os
+    import sys
+
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "examples"))
+    import jaynes_cummings
+    import mach_zehnder
+
+    with host_shim.host_backend():
+        pops, analytic, _, _ = jaynes_cummings.run(cutoff=8, steps=40)
+        assert np.abs(pops - analytic).max() < 1e-9
+        for phi, p, want, _ in mach_zehnder.run(points=5, shots=2):
+            assert abs(p - want) < 1e-12

@@ -97,3 +97,19 @@ def test_large_product_state_through_the_container_api():
     p = (np.abs(amp) ** 2).sum(axis=1)
     assert np.abs(probs.cpu().numpy() - p / p.sum()).max() < 1e-12
     assert np.abs(rest.cpu().numpy() - amp.T @ amp.conj()).max() < 1e-12
+
+
+def test_examples_on_cuda():
+    """examples/ (BASELINE configs[0] and configs[2] through the container API) against their
+    analytic results."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "examples"))
+    import jaynes_cummings
+    import mach_zehnder
+
+    pops, analytic, per_step, dims = jaynes_cummings.run(cutoff=64, steps=60)
+    assert np.abs(pops - analytic).max() < 1e-9
+    for phi, p, want, _ in mach_zehnder.run(points=5, shots=2):
+        assert abs(p - want) < 1e-12

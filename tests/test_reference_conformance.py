@@ -36,3 +36,37 @@ def test_reference_suite_passes_on_the_host_shim():
     assert counts.get("failed", 0) == 0 and counts.get("error", 0) == 0, tail
     assert counts.get("passed", 0) >= 280, tail
     assert counts.get("skipped", 0) <= ALLOWED_SKIPS, tail
+
+
+def _run_example(name):
+    code = (
+        "import sys; sys.path.insert(0, %r); import run_reference_example as r; "
+        "g = r.run(%r, 'host'); import json, numpy as np; "
+        "print('RESULT ' + json.dumps({k: [float(np.real(x)) for x in g[k]] "
+        "for k in ('qubit_excited_populations',) if k in g}))"
+    ) % (os.path.join(ROOT, "tests", "ref_conformance"), os.path.join("/root/reference/examples", name))
+    proc = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert proc.returncode == 0, proc.stderr[-3000:]
+    line = [ln for ln in proc.stdout.splitlines() if ln.startswith("RESULT ")][-1]
+    import json
+
+    return json.loads(line[len("RESULT "):])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/examples"), reason="/root/reference is not present here")
+def test_reference_examples_run_unmodified():
+    """The reference's example scripts (BASELINE configs[0] and configs[2] among them) run
+    unmodified against this package; the Jaynes-Cummings one must show the analytic Rabi
+    oscillation of its Hamiltonian: |1>_field |0>_qubit couples to |2>|1> with strength
+    sqrt(2) g at detuning 2 w (g = w = pi), so p(t) = (2/3) sin^2(sqrt(3) pi t); the script
+    reports p / ||rho_qubit||_F."""
+    import numpy as np
+
+    _run_example("mach_zehnder_interferometer.py")
+    _run_example("time_bin_encoding.py")
+    res = _run_example("jaynes_cummings_model.py")
+    pops = np.array(res["qubit_excited_populations"])
+    assert len(pops) == 300
+    t = (np.arange(300) + 1) * 0.01
+    p = (2.0 / 3.0) * np.sin(np.sqrt(3.0) * np.pi * t) ** 2
+    assert np.abs(pops - p / np.sqrt(p**2 + (1 - p) ** 2)).max() < 1e-9
