@@ -58,6 +58,7 @@ Options& options() {
     env("PW_MAT_SUPER_SINGLE", p->mat_super_single);
     env("PW_TWO_SIDED", p->two_sided);
     env("PW_TS_CTAS", p->ts_ctas);
+    env("PW_TS_MMA", p->ts_mma);
     return p;
   }();
   return *o;
@@ -81,6 +82,7 @@ extern "C" int pw_set_option(const char* name, int value) {
   else if (!std::strcmp(name, "mat_super_single")) o.mat_super_single.store(value);
   else if (!std::strcmp(name, "two_sided")) o.two_sided.store(value);
   else if (!std::strcmp(name, "ts_ctas")) o.ts_ctas.store(value);
+  else if (!std::strcmp(name, "ts_mma")) o.ts_mma.store(value);
   else return PW_ERR_INVALID;
   return PW_OK;
 }

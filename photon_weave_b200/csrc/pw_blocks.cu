@@ -483,7 +483,7 @@ constexpr int kTsWarps = 8;
 constexpr int kTsSlots = 64;                 // tile = 64 slots x 32 lanes
 constexpr uint32_t kTsValCap = 8 * 1024;     // per side: block values (BS d=8: 344 x 16 B)
 
-struct TsFlags { int handled; int any; int ngroups; int pad; };
+struct TsFlags { int handled; int any; int ngroups; int use_mma; };
 
 struct TsTables {
   TsFlags* flags;
@@ -493,12 +493,13 @@ struct TsTables {
   int64_t* out_off;    // [t*t] (output side)
   int4* item1;         // (slot in tile, n, stride, value offset)   stage 1: a column of a pair
   int4* item2;         // (slot in tile, n, value offset, -)        stage 2: a row of a pair
+  int* in_row;         // [t*t] row a of every slot inside its block pair (tensor-core kernel: swizzle)
 };
 
 template <typename V>
 __global__ void __launch_bounds__(256)
 k_ts_build(const BlockArrays L, const BlockArrays R, const int* __restrict__ other, const TsTables T,
-           const uint32_t val_cap) {
+           const uint32_t val_cap, const int mma_ok) {
   __shared__ int s_handled, s_npairs;
   const BlockDescHeader* hl = L.hdr;
   const BlockDescHeader* hr = R.hdr;
@@ -534,6 +535,9 @@ k_ts_build(const BlockArrays L, const BlockArrays R, const int* __restrict__ oth
     T.flags->handled = h;
     T.flags->any = (h || o) ? 1 : 0;
     T.flags->ngroups = ng;
+    // one dense block (d = 5..8 single-mode operator): FP64 tensor cores; many small blocks
+    // (beam splitter sectors) run faster on the scalar kernel (measured)
+    T.flags->use_mma = (h && mma_ok && hl->nblocks == 1 && hl->maxn >= 5) ? 1 : 0;
     s_handled = h;
   }
   __syncthreads();
@@ -553,10 +557,11 @@ k_ts_build(const BlockArrays L, const BlockArrays R, const int* __restrict__ oth
     for (int a = 0; a < nk; ++a)
       for (int b = 0; b < nl; ++b) {
         T.in_off[slot0 + a * nl + b] = ko[a] + lo[b];
+        T.in_row[slot0 + a * nl + b] = a;
         T.out_off[slot0 + a * nl + b] = ko[nk + a] + lo[nl + b];
       }
-    for (int j = 0; j < nl; ++j) T.item1[it1 + j] = make_int4(local0 + j, nk, nl, hk.w);
-    for (int i2 = 0; i2 < nk; ++i2) T.item2[it2 + i2] = make_int4(local0 + i2 * nl, nl, hq.w, 0);
+    for (int j = 0; j < nl; ++j) T.item1[it1 + j] = make_int4(local0 + j, nk | (j << 8), nl, hk.w);
+    for (int i2 = 0; i2 < nk; ++i2) T.item2[it2 + i2] = make_int4(local0 + i2 * nl, nl, hq.w, i2);
   }
 }
 
@@ -568,7 +573,7 @@ template <typename V>
 __global__ void __launch_bounds__(kTsWarps * 32, 2)
 k_two_sided(const V* __restrict__ in, V* __restrict__ out, const FiberMap fm, const BlockArrays L,
             const BlockArrays R, const TsTables T) {
-  if (!T.flags->handled) return;
+  if (!T.flags->handled || T.flags->use_mma) return;
   extern __shared__ __align__(16) unsigned char s_raw[];
   V* vl = (V*)s_raw;                       // row-side block values
   V* vr = (V*)(s_raw + kTsValCap);         // column-side block values (already conjugated)
@@ -617,7 +622,7 @@ k_two_sided(const V* __restrict__ in, V* __restrict__ out, const FiberMap fm, co
         const int4 w = __ldg(T.item1 + g0.z + it);
         V* col = tile + w.x * 32 + lane;
         const int stride = w.z * 32;
-        block_product<V, 4>(vl + w.w, w.y, w.y,
+        block_product<V, 4>(vl + w.w, w.y & 0xff, w.y & 0xff,
                          [&](int a) { return col[a * stride]; },
                          [&](int i, V v) { col[i * stride] = v; });
       }
@@ -642,6 +647,144 @@ k_two_sided(const V* __restrict__ in, V* __restrict__ out, const FiberMap fm, co
   cp_async_wait<0>();
 }
 
+// ---- the same pass on the FP64 tensor cores (complex128) --------------------------------------
+// The scalar kernel above is bound by what surrounds its FMAs: every complex FMA needs a
+// broadcast shared-memory load of an operator entry, and 16 warps per SM cannot hide the FP64
+// latency.  mma.sync.m8n8k4.f64 keeps the operator in registers as an A fragment (two complex
+// values per lane) and performs 256 FMAs per instruction.  A complex product Y = B X is the real
+// product [Yr; Yi] = [Br -Bi; Bi Br] [Xr; Xi]: M = 16 (two m8 tiles: real and imaginary rows),
+// K = 16 (four k4 steps: real then imaginary inputs), N = 8 fibers per n-tile, four n-tiles per
+// warp item.  The lane that owns (row gid, k/column pair tig) needs X at rows {tig, 4 + tig} of
+// fiber gid: one 128-bit shared load yields the real AND imaginary part, i.e. the B fragments of
+// two k-steps.  The tile is stored XOR-swizzled (fiber index ^ 2 (row & 3)) so that those loads
+// are bank-conflict free.
+__device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, const double a, const double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// Single dense block (n = 5..8): the slot of operator index pair (a, b) is a * n + b, so no
+// item tables are needed; the operator fragments live in registers for the whole kernel.
+// Three tile buffers: the loads run two tiles ahead and a tile costs two barriers.
+__global__ void __launch_bounds__(kTsWarps * 32, 2)
+k_two_sided_mma(const double2* __restrict__ in, double2* __restrict__ out, const FiberMap fm,
+                const BlockArrays L, const BlockArrays R, const TsTables T) {
+  using V = double2;
+  if (!T.flags->handled || !T.flags->use_mma) return;
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  V* tile0 = (V*)s_raw;                                          // [3][kTsSlots][32], swizzled
+  int64_t* s_base = (int64_t*)(tile0 + 3 * kTsSlots * 32);       // [3][32] fiber bases (-1: past the end)
+  int64_t* s_off = s_base + 3 * 32;                              // [4][8]: row in, column in, row out, column out
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = L.blocks[0].x;
+  if (threadIdx.x < 4 * 8) {
+    const int which = threadIdx.x >> 3, e = threadIdx.x & 7;
+    int64_t v = 0;
+    if (e < n) {
+      const int64_t* ko = L.offs + L.blocks[0].z;
+      const int64_t* lo = R.offs + R.blocks[0].z;
+      v = which == 0 ? ko[e] : which == 1 ? lo[e] : which == 2 ? ko[n + e] : lo[n + e];
+    }
+    s_off[threadIdx.x] = v;
+  }
+  // operator fragments: lane (gid, tig) holds W[gid][tig] and W[gid][4 + tig]
+  const int gid = lane >> 2, tig = lane & 3;
+  V l0 = make_double2(0.0, 0.0), l1 = l0, r0 = l0, r1 = l0;
+  if (gid < n) {
+    const V* wl = (const V*)L.vals + L.blocks[0].w;
+    const V* wr = (const V*)R.vals + R.blocks[0].w;
+    if (tig < n) { l0 = wl[gid * n + tig]; r0 = wr[gid * n + tig]; }
+    if (4 + tig < n) { l1 = wl[gid * n + 4 + tig]; r1 = wr[gid * n + 4 + tig]; }
+  }
+  __syncthreads();
+  const uint64_t units = (fm.nfib + 31) / 32;
+  const int nslots = n * n;
+
+  auto issue = [&](uint64_t u, int buf) {
+    if (u < units) {
+      const uint64_t f = u * 32 + lane;
+      const int64_t base = f < fm.nfib ? fm.base(f) : -1;
+      if (warp == 0) s_base[buf * 32 + lane] = base;
+      if (base >= 0) {
+        V* tile = tile0 + (size_t)buf * kTsSlots * 32;
+        for (int sl = warp; sl < nslots; sl += kTsWarps) {
+          const int a = sl / n, b = sl - a * n;
+          cp_async16(tile + sl * 32 + (lane ^ (2 * (a & 3))), in + base + s_off[a] + s_off[8 + b]);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+
+  // one item: out[i][f] = sum_a W[i][a] x[a][f]; fragments w0 / w1 precomputed
+  auto product = [&](const V w0, const V w1, auto ldx, auto sty) {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int f = 8 * nt + gid;
+      V x0 = make_double2(0.0, 0.0), x1 = x0;
+      if (tig < n) x0 = ldx(tig, f);
+      if (4 + tig < n) x1 = ldx(4 + tig, f);
+      double re0 = 0.0, re1 = 0.0, im0 = 0.0, im1 = 0.0;
+      dmma8x8x4(re0, re1, w0.x, x0.x);
+      dmma8x8x4(im0, im1, w0.y, x0.x);
+      dmma8x8x4(re0, re1, -w0.y, x0.y);
+      dmma8x8x4(im0, im1, w0.x, x0.y);
+      dmma8x8x4(re0, re1, w1.x, x1.x);
+      dmma8x8x4(im0, im1, w1.y, x1.x);
+      dmma8x8x4(re0, re1, -w1.y, x1.y);
+      dmma8x8x4(im0, im1, w1.x, x1.y);
+      sty(nt, 8 * nt + 2 * tig, make_double2(re0, im0), make_double2(re1, im1));
+    }
+  };
+
+  uint64_t u = blockIdx.x;
+  int cur = 0;
+  issue(u, 0);
+  issue(u + gridDim.x, 1);
+  for (; u < units; u += gridDim.x) {
+    V* tile = tile0 + (size_t)cur * kTsSlots * 32;
+    cp_async_wait<1>();
+    __syncthreads();
+    issue(u + 2 * (uint64_t)gridDim.x, cur == 0 ? 2 : cur - 1);  // the buffer of the previous tile
+    // stage 1: column j of the tile, in place
+    for (int j = warp; j < n; j += kTsWarps) {
+      V* col = tile + j * 32;
+      V y0[4], y1[4];
+      product(l0, l1, [&](int a, int f) { return col[a * n * 32 + (f ^ (2 * (a & 3)))]; },
+              [&](int nt, int f, V v0, V v1) { y0[nt] = v0; y1[nt] = v1; (void)f; });
+      __syncwarp();  // every lane has read its inputs before the column is overwritten
+      if (gid < n) {
+        V* dst = col + gid * n * 32;
+        const int sw = (2 * (j & 3)) ^ (gid & 1);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int f = 8 * nt + 2 * tig;
+          dst[f ^ sw] = y0[nt];
+          dst[(f + 1) ^ sw] = y1[nt];
+        }
+      }
+    }
+    __syncthreads();
+    // stage 2: row i of the tile, streamed to HBM
+    const int64_t* sb = s_base + cur * 32;
+    for (int i = warp; i < n; i += kTsWarps) {
+      const V* row = tile + i * n * 32;
+      const int64_t ro = s_off[16 + i] + (gid < n ? s_off[24 + gid] : 0);
+      product(r0, r1, [&](int b, int f) { return row[b * 32 + (f ^ (2 * (b & 3)) ^ (i & 1))]; },
+              [&](int nt, int f, V v0, V v1) {
+                (void)nt;
+                if (gid < n) {
+                  const int64_t b0 = sb[f], b1 = sb[f + 1];
+                  if (b0 >= 0) __stcg(out + b0 + ro, v0);
+                  if (b1 >= 0) __stcg(out + b1 + ro, v1);
+                }
+              });
+    }
+    cur = cur == 2 ? 0 : cur + 1;
+  }
+  cp_async_wait<0>();
+}
+
 template <typename V>
 static int launch_two_sided_t(const V* rho, V* out, const V* op, const FiberMap& fm,
                               const TargetMap& rows, const TargetMap& cols, const int* other,
@@ -651,8 +794,8 @@ static int launch_two_sided_t(const V* rho, V* out, const V* op, const FiberMap&
   const size_t t = rows.t, tt = t * t;
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const size_t b_flags = 256, b_groups = al(sizeof(int4) * 2 * tt), b_pairs = al(sizeof(int4) * tt),
-               b_off = al(sizeof(int64_t) * tt), b_item = al(sizeof(int4) * tt);
-  PW_TRY(ts->flag_mem.alloc(b_flags + b_groups + b_pairs + 2 * b_off + 2 * b_item, s));
+               b_off = al(sizeof(int64_t) * tt), b_item = al(sizeof(int4) * tt), b_row = al(sizeof(int) * tt);
+  PW_TRY(ts->flag_mem.alloc(b_flags + b_groups + b_pairs + 2 * b_off + 2 * b_item + b_row, s));
   char* base = (char*)ts->flag_mem.p;
   TsTables T;
   T.flags = (TsFlags*)base;
@@ -662,7 +805,9 @@ static int launch_two_sided_t(const V* rho, V* out, const V* op, const FiberMap&
   T.out_off = (int64_t*)(base + b_flags + b_groups + b_pairs + b_off);
   T.item1 = (int4*)(base + b_flags + b_groups + b_pairs + 2 * b_off);
   T.item2 = (int4*)(base + b_flags + b_groups + b_pairs + 2 * b_off + b_item);
-  k_ts_build<V><<<1, 256, 0, s>>>(ts->L, ts->R, other, T, kTsValCap);
+  T.in_row = (int*)(base + b_flags + b_groups + b_pairs + 2 * b_off + 2 * b_item);
+  k_ts_build<V><<<1, 256, 0, s>>>(ts->L, ts->R, other, T, kTsValCap,
+                                  (sizeof(V) == 16 && options().ts_mma.load(std::memory_order_relaxed)) ? 1 : 0);
   PW_LAUNCHED();
   const size_t smem = 2 * kTsValCap + sizeof(V) * 2 * kTsSlots * 32;
   static bool attr_set = false;
@@ -674,7 +819,18 @@ static int launch_two_sided_t(const V* rho, V* out, const V* op, const FiberMap&
     attr_set = true;
   }
   const int per_sm = options().ts_ctas.load(std::memory_order_relaxed);
-  k_two_sided<V><<<kNumSMs * (per_sm > 0 ? per_sm : 2), kTsWarps * 32, smem, s>>>(rho, out, fm, ts->L, ts->R, T);
+  const int grid = kNumSMs * (per_sm > 0 ? per_sm : 2);
+  k_two_sided<V><<<grid, kTsWarps * 32, smem, s>>>(rho, out, fm, ts->L, ts->R, T);
+  if (sizeof(V) == 16 && options().ts_mma.load(std::memory_order_relaxed)) {
+    PW_LAUNCHED();
+    static bool attr_mma = false;
+    const size_t smem_mma = sizeof(double2) * 3 * kTsSlots * 32 + (3 * 32 + 4 * 8) * sizeof(int64_t);
+    if (!attr_mma) {
+      PW_CUDA(cudaFuncSetAttribute(k_two_sided_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma));
+      attr_mma = true;
+    }
+    k_two_sided_mma<<<grid, kTsWarps * 32, smem_mma, s>>>((const double2*)rho, (double2*)out, fm, ts->L, ts->R, T);
+  }
   PW_LAUNCHED();
   g_paths[4].fetch_add(1, std::memory_order_relaxed);
   ts->skip = &T.flags->any;

@@ -83,11 +83,14 @@ __device__ __forceinline__ DescView<V> desc_view(const BlockArrays& A, unsigned 
 
 // y[rows] = B (nr x NC, dense) x[cols]; NC is a compile-time constant so the NC inputs
 // live in registers without predication.
-template <typename V, int NC, int UR, typename LoadX, typename StoreY>
+// SYNCW: __syncwarp() between the loads and the stores (in-place use where a lane's outputs
+// land on positions another lane of the same warp reads)
+template <typename V, int NC, int UR, bool SYNCW, typename LoadX, typename StoreY>
 __device__ __forceinline__ void block_product_nc(const V* __restrict__ bv, const int nr, LoadX ldx, StoreY sty) {
   V x[NC];
 #pragma unroll
   for (int j = 0; j < NC; ++j) x[j] = ldx(j);
+  if (SYNCW) __syncwarp();
   // four output rows at a time: eight independent FMA chains per thread keep the FP64 pipe
   // busy at low occupancy (the dependent chain of one row is 2 * NC FMAs long)
   int a = 0;
@@ -111,17 +114,17 @@ __device__ __forceinline__ void block_product_nc(const V* __restrict__ bv, const
   }
 }
 
-template <typename V, int UR = 1, typename LoadX, typename StoreY>
+template <typename V, int UR = 1, bool SYNCW = false, typename LoadX, typename StoreY>
 __device__ __forceinline__ void block_product(const V* __restrict__ bv, const int nr, const int nc, LoadX ldx, StoreY sty) {
   switch (nc) {
-    case 1: block_product_nc<V, 1, UR>(bv, nr, ldx, sty); break;
-    case 2: block_product_nc<V, 2, UR>(bv, nr, ldx, sty); break;
-    case 3: block_product_nc<V, 3, UR>(bv, nr, ldx, sty); break;
-    case 4: block_product_nc<V, 4, UR>(bv, nr, ldx, sty); break;
-    case 5: block_product_nc<V, 5, UR>(bv, nr, ldx, sty); break;
-    case 6: block_product_nc<V, 6, UR>(bv, nr, ldx, sty); break;
-    case 7: block_product_nc<V, 7, UR>(bv, nr, ldx, sty); break;
-    case 8: block_product_nc<V, 8, UR>(bv, nr, ldx, sty); break;
+    case 1: block_product_nc<V, 1, UR, SYNCW>(bv, nr, ldx, sty); break;
+    case 2: block_product_nc<V, 2, UR, SYNCW>(bv, nr, ldx, sty); break;
+    case 3: block_product_nc<V, 3, UR, SYNCW>(bv, nr, ldx, sty); break;
+    case 4: block_product_nc<V, 4, UR, SYNCW>(bv, nr, ldx, sty); break;
+    case 5: block_product_nc<V, 5, UR, SYNCW>(bv, nr, ldx, sty); break;
+    case 6: block_product_nc<V, 6, UR, SYNCW>(bv, nr, ldx, sty); break;
+    case 7: block_product_nc<V, 7, UR, SYNCW>(bv, nr, ldx, sty); break;
+    case 8: block_product_nc<V, 8, UR, SYNCW>(bv, nr, ldx, sty); break;
     default: break;  // nc == 0 cannot occur (blocks have >= 1 column); nc > 8 is not `usable`
   }
 }
