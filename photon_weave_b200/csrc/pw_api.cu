@@ -59,6 +59,7 @@ Options& options() {
     env("PW_TWO_SIDED", p->two_sided);
     env("PW_TS_CTAS", p->ts_ctas);
     env("PW_TS_MMA", p->ts_mma);
+    env("PW_TS_ORDER", p->ts_order);
     return p;
   }();
   return *o;
@@ -83,6 +84,7 @@ extern "C" int pw_set_option(const char* name, int value) {
   else if (!std::strcmp(name, "two_sided")) o.two_sided.store(value);
   else if (!std::strcmp(name, "ts_ctas")) o.ts_ctas.store(value);
   else if (!std::strcmp(name, "ts_mma")) o.ts_mma.store(value);
+  else if (!std::strcmp(name, "ts_order")) o.ts_order.store(value);
   else return PW_ERR_INVALID;
   return PW_OK;
 }

@@ -597,7 +597,9 @@ static int matrix_dispatch(const void* rho, void* out, const void* ops, int K, c
       options().two_sided.load(std::memory_order_relaxed)) {
     Plan pb, pr, pc;
     PW_TRY(build_plan_axes(r.axes, 2 * r.n, r.both, 2 * r.nt, &pb));
-    if (inner_rest_run(pb) >= 4) {
+    // (innermost axis a target: launch_two_sided takes the geometries it has a kernel for)
+    const uint64_t r_in = inner_rest_run(pb);
+    if (r_in >= 4 || r_in == 0) {
       PW_TRY(build_plan_axes(r.axes, 2 * r.n, r.rows, r.nt, &pr));
       PW_TRY(build_plan_axes(r.axes, 2 * r.n, r.cols, r.nt, &pc));
       const int rc = launch_two_sided(rho, out, ops, pb.fm, pr.tm, pc.tm, dtype, skip, &ts, s);

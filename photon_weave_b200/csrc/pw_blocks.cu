@@ -28,34 +28,57 @@ template <typename V>
 __global__ void __launch_bounds__(256)
 k_build_blocks(const V* __restrict__ op, const uint32_t t, const bool conj_op, const TargetMap tm,
                BlockDescHeader* __restrict__ hdr, int4* __restrict__ blocks,
-               int64_t* __restrict__ offs, V* __restrict__ vals, int64_t* __restrict__ zero_offs) {
-  extern __shared__ int32_t s_i[];
-  int32_t* lr = s_i;           // [t] row labels
+               int64_t* __restrict__ offs, V* __restrict__ vals, int64_t* __restrict__ zero_offs,
+               const int* __restrict__ skip) {
+  extern __shared__ __align__(16) int32_t s_i[];
+  int4* s_blk = (int4*)s_i;    // [t] block table (copied out at the end)
+  int32_t* lr = s_i + 4 * t;   // [t] row labels
   int32_t* lc = lr + t;        // [t] column labels
   int32_t* bid = lc + t;       // [t] label -> block id
+  uint32_t* nzr = (uint32_t*)(bid + t);   // [t][4] nonzero columns of every row (bit masks, t <= 128)
+  uint32_t* nzc = nzr + 4 * t;            // [t][4] nonzero rows of every column
+  int32_t* s_rc = (int32_t*)(nzc + 4 * t);  // [t] rank of column c inside its block
+  int32_t* s_rr = s_rc + t;               // [t] rank of row a inside its block
   __shared__ int s_changed;
   __shared__ int s_nblocks, s_maxn, s_nzero;
   const int32_t INF = 0x7fffffff;
+  if (skip != nullptr && *skip != 0) {
+    // another path already produced the result: nobody may take this descriptor
+    if (threadIdx.x == 0) {
+      hdr->nblocks = 0; hdr->maxn = 0; hdr->nzero = 0; hdr->usable = 0; hdr->inplace_safe = 0;
+      hdr->seg_handled = 0; hdr->n_offs = 0; hdr->n_vals = 0;
+    }
+    return;
+  }
+  for (uint32_t i = threadIdx.x; i < 8 * t; i += blockDim.x) nzr[i] = 0;
   for (uint32_t i = threadIdx.x; i < t; i += blockDim.x) { lr[i] = INF; lc[i] = (int32_t)i; }
+  __syncthreads();
+  // ONE coalesced pass over the operator: the structure analysis runs on bit masks
+  for (uint32_t e = threadIdx.x; e < t * t; e += blockDim.x) {
+    const V v = op[e];
+    if (v.x != 0 || v.y != 0) {
+      const uint32_t a = e / t, b = e - a * t;
+      atomicOr(&nzr[4 * a + (b >> 5)], 1u << (b & 31));
+      atomicOr(&nzc[4 * b + (a >> 5)], 1u << (a & 31));
+    }
+  }
   __syncthreads();
   for (uint32_t iter = 0; iter < 2 * t + 2; ++iter) {
     if (threadIdx.x == 0) s_changed = 0;
     __syncthreads();
     for (uint32_t a = threadIdx.x; a < t; a += blockDim.x) {
       int32_t m = lr[a];
-      for (uint32_t b = 0; b < t; ++b) {
-        const V v = op[(size_t)a * t + b];
-        if (v.x != 0 || v.y != 0) m = min(m, lc[b]);
-      }
+      for (uint32_t w = 0; w < 4; ++w)
+        for (uint32_t bits = nzr[4 * a + w]; bits; bits &= bits - 1)
+          m = min(m, lc[32 * w + __ffs(bits) - 1]);
       if (m != lr[a]) { lr[a] = m; s_changed = 1; }
     }
     __syncthreads();
     for (uint32_t b = threadIdx.x; b < t; b += blockDim.x) {
       int32_t m = lc[b];
-      for (uint32_t a = 0; a < t; ++a) {
-        const V v = op[(size_t)a * t + b];
-        if (v.x != 0 || v.y != 0) m = min(m, lr[a]);
-      }
+      for (uint32_t w = 0; w < 4; ++w)
+        for (uint32_t bits = nzc[4 * b + w]; bits; bits &= bits - 1)
+          m = min(m, lr[32 * w + __ffs(bits) - 1]);
       if (m != lc[b]) { lc[b] = m; s_changed = 1; }
     }
     __syncthreads();
@@ -63,16 +86,14 @@ k_build_blocks(const V* __restrict__ op, const uint32_t t, const bool conj_op, c
     __syncthreads();
   }
   // columns whose label is their own index AND that touch at least one row open a block
+  for (uint32_t b = threadIdx.x; b < t; b += blockDim.x) bid[b] = -1;
+  __syncthreads();
+  for (uint32_t a = threadIdx.x; a < t; a += blockDim.x)
+    if (lr[a] != INF) bid[lr[a]] = -2;  // the component of this label has rows
+  __syncthreads();
   if (threadIdx.x == 0) {
     int nb = 0;
-    for (uint32_t b = 0; b < t; ++b) {
-      bid[b] = -1;
-      if (lc[b] == (int32_t)b) {
-        bool used = false;
-        for (uint32_t a = 0; a < t && !used; ++a) used = (lr[a] == (int32_t)b);
-        if (used) bid[b] = nb++;
-      }
-    }
+    for (uint32_t b = 0; b < t; ++b) bid[b] = (lc[b] == (int32_t)b && bid[b] == -2) ? nb++ : -1;
     s_nblocks = nb;
     s_maxn = 0;
     int nz = 0;
@@ -81,8 +102,7 @@ k_build_blocks(const V* __restrict__ op, const uint32_t t, const bool conj_op, c
     s_nzero = nz;
   }
   __syncthreads();
-  // one thread per block gathers its members; offsets/values are laid out per block in
-  // fixed-size slots (a block can never exceed t members)
+  // sizes of every block (one thread per component root)
   for (uint32_t root = threadIdx.x; root < t; root += blockDim.x) {
     const int b = bid[root];
     if (b < 0) continue;
@@ -90,68 +110,68 @@ k_build_blocks(const V* __restrict__ op, const uint32_t t, const bool conj_op, c
     for (uint32_t c = 0; c < t; ++c) nc += (lc[c] == (int32_t)root);
     for (uint32_t a = 0; a < t; ++a) nr += (lr[a] == (int32_t)root);
     atomicMax(&s_maxn, max(nr, nc));
-    blocks[b] = make_int4(nr, nc, (int)root, 0);
+    s_blk[b] = make_int4(nr, nc, 0, 0);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    // exclusive scans for the packed layouts
+    // exclusive scans for the packed layouts: s_blk[b] = (nr, nc, index offset, value offset)
     int io = 0, vo = 0;
     for (int b = 0; b < s_nblocks; ++b) {
-      int4 h = blocks[b];
-      const int nr = h.x, nc = h.y;
-      h.w = vo;            // value offset
-      blocks[b] = make_int4(nr, nc, h.z, vo);
-      // reuse bid[root] to carry the index offset of this block
-      bid[h.z] = io;
-      io += nr + nc;
-      vo += nr * nc;
+      const int4 h = s_blk[b];
+      s_blk[b] = make_int4(h.x, h.y, io, vo);
+      io += h.x + h.y;
+      vo += h.x * h.y;
     }
     hdr->nblocks = s_nblocks;
     hdr->n_offs = io;
     hdr->n_vals = (s_maxn <= kBlockMaxN) ? vo : 0;
     hdr->maxn = s_maxn;
     hdr->nzero = s_nzero;
-    hdr->usable = (s_maxn <= kBlockMaxN) ? 1 : 0;
+    const int usable = (s_maxn <= kBlockMaxN) ? 1 : 0;
+    hdr->usable = usable;
     // position a is written by the block of ROW a and read by the block of COLUMN a:
     // in-place is safe iff those coincide wherever both exist (zero rows write too)
     int safe = 1;
     for (uint32_t a = 0; a < t; ++a) {
-      bool col_used = false;
-      for (uint32_t r = 0; r < t && !col_used; ++r) col_used = (lr[r] == lc[a]);
+      const bool col_used = bid[lc[a]] >= 0;   // the component of column a has rows
       if (!col_used) continue;                 // nobody reads position a
       if (lr[a] != lc[a]) safe = 0;            // written by another block (or cleared)
     }
     hdr->inplace_safe = safe;
-    hdr->seg_handled = (hdr->usable && safe) ? 1 : 0;
+    hdr->seg_handled = (usable && safe) ? 1 : 0;
   }
   __syncthreads();
-  for (int b = threadIdx.x; b < s_nblocks; b += blockDim.x) {
-    const int4 h = blocks[b];
-    const int nr = h.x, nc = h.y, root = h.z, vo = h.w;
-    const int io = bid[root];
-    int cols[kBlockMaxN];
-    // columns first, then rows
-    int k = 0;
-    for (uint32_t c = 0; c < t; ++c)
-      if (lc[c] == root) {
-        if (k < kBlockMaxN) cols[k] = (int)c;
-        offs[io + k] = tm.offset(c);
-        ++k;
-      }
-    int r = 0;
-    for (uint32_t a = 0; a < t; ++a)
-      if (lr[a] == root) {
-        offs[io + nc + r] = tm.offset(a);
-        if (nc <= kBlockMaxN)
-          for (int j = 0; j < nc; ++j) {
-            V v = op[(size_t)a * t + cols[j]];
-            if (conj_op) v.y = -v.y;
-            vals[vo + r * nc + j] = v;
-          }
-        ++r;
-      }
-    blocks[b] = make_int4(nr, nc, io, vo);
+  // rank of every column / row inside its block (tensor order), and the element offsets:
+  // columns first, then rows
+  for (uint32_t i = threadIdx.x; i < t; i += blockDim.x) {
+    int rc = -1, rr = -1;
+    const int bc = bid[lc[i]];
+    if (bc >= 0) {
+      rc = 0;
+      for (uint32_t c = 0; c < i; ++c) rc += (lc[c] == lc[i]);
+      offs[s_blk[bc].z + rc] = tm.offset(i);
+    }
+    if (lr[i] != INF) {
+      const int4 h = s_blk[bid[lr[i]]];
+      rr = 0;
+      for (uint32_t a = 0; a < i; ++a) rr += (lr[a] == lr[i]);
+      offs[h.z + h.y + rr] = tm.offset(i);
+    }
+    s_rc[i] = rc;
+    s_rr[i] = rr;
   }
+  __syncthreads();
+  // dense block values: one coalesced pass over the operator
+  if (s_maxn <= kBlockMaxN)
+    for (uint32_t e = threadIdx.x; e < t * t; e += blockDim.x) {
+      const uint32_t a = e / t, c = e - a * t;
+      if (lr[a] == INF || lr[a] != lc[c]) continue;
+      const int4 h = s_blk[bid[lr[a]]];
+      V v = op[e];
+      if (conj_op) v.y = -v.y;
+      vals[h.w + s_rr[a] * h.y + s_rc[c]] = v;
+    }
+  for (int b = threadIdx.x; b < s_nblocks; b += blockDim.x) blocks[b] = s_blk[b];
 }
 
 // ---- apply -----------------------------------------------------------------------------
@@ -289,7 +309,7 @@ k_apply_blocks_seg(const V* __restrict__ in, V* __restrict__ out, const SegGeom 
 
 template <typename V>
 static int build_block_desc_t(const V* op, uint32_t t, bool conj_op, const TargetMap& tm,
-                              Scratch* mem, BlockArrays* arr, cudaStream_t s) {
+                              Scratch* mem, BlockArrays* arr, cudaStream_t s, const int* skip = nullptr) {
   // descriptor storage: header | blocks[t] | offs[2t] | zero_offs[t] | vals[t*t]
   auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
   const size_t b_hdr = 64, b_blk = sizeof(int4) * t, b_off = al(sizeof(int64_t) * 2 * t),
@@ -301,17 +321,17 @@ static int build_block_desc_t(const V* op, uint32_t t, bool conj_op, const Targe
   arr->offs = (int64_t*)(base + b_hdr + b_blk);
   arr->zero_offs = (int64_t*)(base + b_hdr + b_blk + b_off);
   arr->vals = base + b_hdr + b_blk + b_off + b_zero;
-  k_build_blocks<V><<<1, 256, sizeof(int32_t) * 3 * t, s>>>(op, t, conj_op, tm, arr->hdr, arr->blocks,
-                                                          arr->offs, (V*)arr->vals, arr->zero_offs);
+  k_build_blocks<V><<<1, 256, sizeof(int32_t) * 20 * t, s>>>(op, t, conj_op, tm, arr->hdr, arr->blocks,
+                                                           arr->offs, (V*)arr->vals, arr->zero_offs, skip);
   PW_LAUNCHED();
   return PW_OK;
 }
 
 int build_block_desc(const void* op, uint32_t t, bool conj_op, const TargetMap& tm, int dtype,
-                     Scratch* mem, BlockArrays* arr, cudaStream_t stream) {
+                     Scratch* mem, BlockArrays* arr, cudaStream_t stream, const int* skip) {
   if (t > kBlockMaxT) return PW_ERR_UNSUPPORTED;
-  if (dtype == PW_C128) return build_block_desc_t<double2>((const double2*)op, t, conj_op, tm, mem, arr, stream);
-  if (dtype == PW_C64) return build_block_desc_t<float2>((const float2*)op, t, conj_op, tm, mem, arr, stream);
+  if (dtype == PW_C128) return build_block_desc_t<double2>((const double2*)op, t, conj_op, tm, mem, arr, stream, skip);
+  if (dtype == PW_C64) return build_block_desc_t<float2>((const float2*)op, t, conj_op, tm, mem, arr, stream, skip);
   return PW_ERR_INVALID;
 }
 
@@ -483,7 +503,9 @@ constexpr int kTsWarps = 8;
 constexpr int kTsSlots = 64;                 // tile = 64 slots x 32 lanes
 constexpr uint32_t kTsValCap = 8 * 1024;     // per side: block values (BS d=8: 344 x 16 B)
 
-struct TsFlags { int handled; int any; int ngroups; int use_mma; };
+constexpr int kTsMaxSb = 16;                 // tensor-core kernel: super-blocks per side
+
+struct TsFlags { int handled; int any; int ngroups; int use_mma; int nsb; };
 
 struct TsTables {
   TsFlags* flags;
@@ -494,31 +516,74 @@ struct TsTables {
   int4* item1;         // (slot in tile, n, stride, value offset)   stage 1: a column of a pair
   int4* item2;         // (slot in tile, n, value offset, -)        stage 2: a row of a pair
   int* in_row;         // [t*t] row a of every slot inside its block pair (tensor-core kernel: swizzle)
+  // tensor-core kernel: the blocks of one side packed into super-blocks of <= 8 indices
+  int* sb_n;           // [kTsMaxSb] indices per super-block
+  int2* sb_blk;        // [t] per block: (super-block, first index inside it)
+  int64_t* sb_off;     // [4][kTsMaxSb][8] element offsets: row in, column in, row out, column out
+  void* sb_w;          // [2][kTsMaxSb][8][8] zero-padded block-diagonal values: row side, column side (conjugated)
 };
 
 template <typename V>
 __global__ void __launch_bounds__(256)
 k_ts_build(const BlockArrays L, const BlockArrays R, const int* __restrict__ other, const TsTables T,
-           const uint32_t val_cap, const int mma_ok) {
-  __shared__ int s_handled, s_npairs;
+           const uint32_t val_cap, const int mma_ok, const int inner) {
+  __shared__ int s_handled, s_npairs, s_mma, s_square;
+  __shared__ int s_bn[kBlockMaxT];  // block sides (thread 0 below must not walk global memory)
   const BlockDescHeader* hl = L.hdr;
   const BlockDescHeader* hr = R.hdr;
+  if (threadIdx.x == 0) s_square = 1;
+  __syncthreads();
+  {
+    const int m = hl->nblocks == hr->nblocks ? min(hl->nblocks, (int)kBlockMaxT) : 0;
+    for (int b = threadIdx.x; b < m; b += blockDim.x) {
+      const int4 x = L.blocks[b], y = R.blocks[b];
+      s_bn[b] = x.x;
+      if (x.x != x.y || y.x != y.y || x.x != y.x) s_square = 0;  // in place: square blocks
+    }
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
     const int o = other ? *other : 0;
     int h = (!o && hl->usable && hr->usable && hl->nzero == 0 && hr->nzero == 0 && hl->maxn >= 2 &&
              hl->nblocks == hr->nblocks) ? 1 : 0;
     if (h && ((uint32_t)hl->n_vals * sizeof(V) > val_cap || (uint32_t)hr->n_vals * sizeof(V) > val_cap)) h = 0;
-    if (h)
-      for (int b = 0; b < hl->nblocks && h; ++b)
-        if (L.blocks[b].x != L.blocks[b].y || R.blocks[b].x != R.blocks[b].y) h = 0;  // in place: square blocks
+    if (!s_square) h = 0;
+    // tensor cores: first-fit-decreasing packing of the blocks into super-blocks of <= 8
+    // indices (beam splitter, cutoff 8: sectors 1..8..1 -> 8 | 7+1 | 7+1 | 6+2 | 6+2 | 5+3 |
+    // 5+3 | 4+4, i.e. eight full 8 x 8 tensor-core operands, no padding work)
+    int nsb = 0, mma = 0;
+    if (h && mma_ok && hl->maxn <= 8) {
+      const int m = hl->nblocks;
+      int total = 0, fill[kTsMaxSb];
+      mma = 1;
+      for (int sz = 8; sz >= 1 && mma; --sz)
+        for (int b = 0; b < m && mma; ++b) {
+          if (s_bn[b] != sz) continue;
+          int s = 0;
+          while (s < nsb && fill[s] + sz > 8) ++s;
+          if (s == nsb) {
+            if (nsb == kTsMaxSb) { mma = 0; break; }
+            fill[nsb++] = 0;
+          }
+          T.sb_blk[b] = make_int2(s, fill[s]);
+          fill[s] += sz;
+          total += sz;
+        }
+      if (total < 5) mma = 0;  // tiny operators: the scalar kernel / register tiles
+      for (int s = 0; s < nsb && mma; ++s) T.sb_n[s] = fill[s];
+    }
+    // innermost (contiguous) column target: only the tensor-core kernel has the transposing
+    // load, and only for ONE dense block whose columns are the contiguous run itself
+    if (inner && !(mma && hl->nblocks == 1)) h = 0;
+    if (!h) mma = 0;
     int ng = 0;
-    if (h) {
+    if (h && !mma) {
       // greedy packing of the block pairs (k major) into groups of <= kTsSlots slots
       const int m = hl->nblocks;
       int slot0 = 0, used = 0, gslot0 = 0, it1 = 0, it2 = 0, git1 = 0, git2 = 0, np = 0;
       for (int k = 0; k < m; ++k)
         for (int l = 0; l < m; ++l) {
-          const int nk = L.blocks[k].y, nl = R.blocks[l].y, sz = nk * nl;
+          const int nk = s_bn[k], nl = s_bn[l], sz = nk * nl;
           if (used + sz > kTsSlots) {
             T.groups[2 * ng] = make_int4(gslot0, used, git1, it1 - git1);
             T.groups[2 * ng + 1] = make_int4(git2, it2 - git2, 0, 0);
@@ -535,13 +600,40 @@ k_ts_build(const BlockArrays L, const BlockArrays R, const int* __restrict__ oth
     T.flags->handled = h;
     T.flags->any = (h || o) ? 1 : 0;
     T.flags->ngroups = ng;
-    // one dense block (d = 5..8 single-mode operator): FP64 tensor cores; many small blocks
-    // (beam splitter sectors) run faster on the scalar kernel (measured)
-    T.flags->use_mma = (h && mma_ok && hl->nblocks == 1 && hl->maxn >= 5) ? 1 : 0;
+    T.flags->use_mma = mma;
+    T.flags->nsb = nsb;
     s_handled = h;
+    s_mma = mma;
   }
   __syncthreads();
   if (!s_handled) return;
+  if (s_mma) {
+    V* w = (V*)T.sb_w;
+    for (int i = threadIdx.x; i < 2 * kTsMaxSb * 64; i += blockDim.x) w[i] = czero<V>();
+    for (int i = threadIdx.x; i < 4 * kTsMaxSb * 8; i += blockDim.x) T.sb_off[i] = 0;
+    __syncthreads();
+    for (int b = threadIdx.x; b < hl->nblocks; b += blockDim.x) {
+      const int4 hk = L.blocks[b], hq = R.blocks[b];
+      const int2 sp = T.sb_blk[b];
+      const int n = hk.x;
+      const int64_t* ko = L.offs + hk.z;
+      const int64_t* lo = R.offs + hq.z;
+      const V* vl = (const V*)L.vals + hk.w;
+      const V* vr = (const V*)R.vals + hq.w;
+      for (int a = 0; a < n; ++a) {
+        const int e = sp.x * 8 + sp.y + a;
+        T.sb_off[0 * kTsMaxSb * 8 + e] = ko[a];
+        T.sb_off[1 * kTsMaxSb * 8 + e] = lo[a];
+        T.sb_off[2 * kTsMaxSb * 8 + e] = ko[n + a];
+        T.sb_off[3 * kTsMaxSb * 8 + e] = lo[n + a];
+        for (int c = 0; c < n; ++c) {
+          w[(sp.x * 8 + sp.y + a) * 8 + sp.y + c] = vl[a * n + c];
+          w[((kTsMaxSb + sp.x) * 8 + sp.y + a) * 8 + sp.y + c] = vr[a * n + c];
+        }
+      }
+    }
+    return;
+  }
   // group start slot of every pair: recover by scanning groups (few); then fill the tables
   const int ng = T.flags->ngroups;
   for (int p = threadIdx.x; p < s_npairs; p += blockDim.x) {
@@ -663,67 +755,116 @@ __device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, const double a
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// Single dense block (n = 5..8): the slot of operator index pair (a, b) is a * n + b, so no
-// item tables are needed; the operator fragments live in registers for the whole kernel.
-// Three tile buffers: the loads run two tiles ahead and a tile costs two barriers.
-__global__ void __launch_bounds__(kTsWarps * 32, 2)
-k_two_sided_mma(const double2* __restrict__ in, double2* __restrict__ out, const FiberMap fm,
-                const BlockArrays L, const BlockArrays R, const TsTables T) {
+// A unit of work is (super-block pair (K, L)) x (32 fibers): slot (a, b) = a * n_L + b holds
+// operator index pair (row index a of K, column index b of L).  A single dense d = 5..8
+// operator is one super-block; a cutoff-8 beam splitter is eight, every one a full 8 x 8 operand.
+// The operand fragments of a unit come from the zero-padded tables of k_ts_build (L1/L2
+// resident).  Three tile buffers: the loads run two tiles ahead and a tile costs two barriers.
+//
+// `inner`: the column target is the innermost (contiguous) axis.  The 32 fibers of a chunk are
+// then n apart and, for a fixed row index a, (fiber f, column index b) is ONE contiguous run of
+// 32 n elements.  The tile keeps that order -- element (a, b, f) at a * 256 + f * 8 + (b ^ sigma(f, a))
+// -- so that a cp.async instruction's destinations stay inside whole 128-byte shared-memory rows
+// (scattering the 16-byte pieces over slots doubles the L2 -> SM sectors: measured); sigma
+// permutes inside each row such that the stage 1 reads and writes and the stage 2 reads are all
+// bank-conflict free.  The stores of stage 2 are coalesced as they are (8 column outputs x 4
+// fiber pairs = four full 128-byte lines per instruction).
+__device__ __forceinline__ int ts_sigma(const int f, const int a) {
+  return ((f & 1) << 2) ^ (f & 6) ^ (a & 3);
+}
+
+template <bool MULTI, bool INNER>
+__device__ __forceinline__ void two_sided_mma_body(const double2* __restrict__ in, double2* __restrict__ out,
+                                                   const FiberMap& fm, const TsTables& T,
+                                                   unsigned char* s_raw, const int order) {
   using V = double2;
-  if (!T.flags->handled || !T.flags->use_mma) return;
-  extern __shared__ __align__(16) unsigned char s_raw[];
+  constexpr bool inner = INNER;
   V* tile0 = (V*)s_raw;                                          // [3][kTsSlots][32], swizzled
   int64_t* s_base = (int64_t*)(tile0 + 3 * kTsSlots * 32);       // [3][32] fiber bases (-1: past the end)
-  int64_t* s_off = s_base + 3 * 32;                              // [4][8]: row in, column in, row out, column out
+  int64_t* s_off = s_base + 3 * 32;                              // [4][kTsMaxSb][8]
+  int* s_n = (int*)(s_off + 4 * kTsMaxSb * 8);                   // [kTsMaxSb]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n = L.blocks[0].x;
-  if (threadIdx.x < 4 * 8) {
-    const int which = threadIdx.x >> 3, e = threadIdx.x & 7;
-    int64_t v = 0;
-    if (e < n) {
-      const int64_t* ko = L.offs + L.blocks[0].z;
-      const int64_t* lo = R.offs + R.blocks[0].z;
-      v = which == 0 ? ko[e] : which == 1 ? lo[e] : which == 2 ? ko[n + e] : lo[n + e];
-    }
-    s_off[threadIdx.x] = v;
-  }
-  // operator fragments: lane (gid, tig) holds W[gid][tig] and W[gid][4 + tig]
-  const int gid = lane >> 2, tig = lane & 3;
-  V l0 = make_double2(0.0, 0.0), l1 = l0, r0 = l0, r1 = l0;
-  if (gid < n) {
-    const V* wl = (const V*)L.vals + L.blocks[0].w;
-    const V* wr = (const V*)R.vals + R.blocks[0].w;
-    if (tig < n) { l0 = wl[gid * n + tig]; r0 = wr[gid * n + tig]; }
-    if (4 + tig < n) { l1 = wl[gid * n + 4 + tig]; r1 = wr[gid * n + 4 + tig]; }
-  }
+  const uint32_t nsb = MULTI ? (uint32_t)T.flags->nsb : 1u;
+  for (int i = threadIdx.x; i < 4 * kTsMaxSb * 8; i += blockDim.x) s_off[i] = T.sb_off[i];
+  if (threadIdx.x < kTsMaxSb) s_n[threadIdx.x] = threadIdx.x < (int)nsb ? T.sb_n[threadIdx.x] : 0;
   __syncthreads();
-  const uint64_t units = (fm.nfib + 31) / 32;
-  const int nslots = n * n;
+  const int64_t* rin = s_off;
+  const int64_t* cin = s_off + kTsMaxSb * 8;
+  const int64_t* rout = s_off + 2 * kTsMaxSb * 8;
+  const int64_t* cout = s_off + 3 * kTsMaxSb * 8;
+  const int gid = lane >> 2, tig = lane & 3;
+  const uint64_t chunks = (fm.nfib + 31) / 32;
+  const uint64_t units = chunks * nsb * nsb;
+  const V* wtab = (const V*)T.sb_w;
+
+  // chunk index fastest: CTAs that run side by side work on adjacent memory
+  auto decode = [&](uint64_t u, uint32_t& K, uint32_t& L, uint64_t& c) {
+    if (!MULTI) { K = 0; L = 0; c = u; return; }
+    uint32_t p;
+    if (order == 0) {
+      p = (uint32_t)(u / chunks);
+      c = u - (uint64_t)p * chunks;
+    } else {  // pair index fastest: consecutive units sweep one chunk's whole operator block
+      c = u / (nsb * nsb);
+      p = (uint32_t)(u - c * (nsb * nsb));
+    }
+    K = p / nsb;
+    L = p - K * nsb;
+  };
 
   auto issue = [&](uint64_t u, int buf) {
     if (u < units) {
-      const uint64_t f = u * 32 + lane;
-      const int64_t base = f < fm.nfib ? fm.base(f) : -1;
-      if (warp == 0) s_base[buf * 32 + lane] = base;
-      if (base >= 0) {
-        V* tile = tile0 + (size_t)buf * kTsSlots * 32;
-        for (int sl = warp; sl < nslots; sl += kTsWarps) {
-          const int a = sl / n, b = sl - a * n;
-          cp_async16(tile + sl * 32 + (lane ^ (2 * (a & 3))), in + base + s_off[a] + s_off[8 + b]);
+      uint32_t K, L;
+      uint64_t c;
+      decode(u, K, L, c);
+      const int nK = s_n[K], nL = s_n[L];
+      V* tile = tile0 + (size_t)buf * kTsSlots * 32;
+      if (!inner) {
+        const uint64_t f = c * 32 + lane;
+        const int64_t base = f < fm.nfib ? fm.base(f) : -1;
+        if (warp == 0) s_base[buf * 32 + lane] = base;
+        if (base >= 0) {
+          const int64_t* ro = rin + K * 8;
+          const int64_t* co = cin + L * 8;
+          int a = 0, b = warp;
+          while (b >= nL) { b -= nL; ++a; }
+          for (; a < nK;) {
+            cp_async16(tile + (a * nL + b) * 32 + (lane ^ (2 * (a & 3))), in + base + ro[a] + co[b]);
+            b += kTsWarps;
+            while (b >= nL) { b -= nL; ++a; }
+          }
+        }
+      } else {
+        // one super-block (K = L = 0, n = nK = nL); fibers of the chunk: base0 + i * n
+        const int64_t base0 = fm.base(c * 32);
+        const uint64_t left = fm.nfib - c * 32;
+        const int nvalid = left < 32 ? (int)left : 32;
+        if (warp == 0) s_base[buf * 32 + lane] = lane < nvalid ? base0 + (int64_t)lane * nL : -1;
+        for (int a = warp; a < nK; a += kTsWarps) {
+          const V* src = in + base0 + rin[a];
+          V* dst = tile + a * 256;
+          int f = lane / nL, b = lane - f * nL;
+          const int qa = 32 / nL, rb = 32 - qa * nL;
+          for (int e = lane; e < nvalid * nL; e += 32) {
+            cp_async16(dst + f * 8 + (b ^ ts_sigma(f, a)), src + e);
+            f += qa; b += rb;
+            if (b >= nL) { b -= nL; ++f; }
+          }
         }
       }
     }
     cp_async_commit();
   };
 
-  // one item: out[i][f] = sum_a W[i][a] x[a][f]; fragments w0 / w1 precomputed
-  auto product = [&](const V w0, const V w1, auto ldx, auto sty) {
+  // one item: out[i][f] = sum_a W[i][a] x[a][f]; fragments w0 / w1: lane (gid, tig) holds
+  // W[gid][tig] and W[gid][4 + tig]; nx = valid input indices
+  auto product = [&](const V w0, const V w1, const int nx, auto ldx, auto sty) {
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       const int f = 8 * nt + gid;
       V x0 = make_double2(0.0, 0.0), x1 = x0;
-      if (tig < n) x0 = ldx(tig, f);
-      if (4 + tig < n) x1 = ldx(4 + tig, f);
+      if (tig < nx) x0 = ldx(tig, f);
+      if (4 + tig < nx) x1 = ldx(4 + tig, f);
       double re0 = 0.0, re1 = 0.0, im0 = 0.0, im1 = 0.0;
       dmma8x8x4(re0, re1, w0.x, x0.x);
       dmma8x8x4(im0, im1, w0.y, x0.x);
@@ -741,20 +882,45 @@ k_two_sided_mma(const double2* __restrict__ in, double2* __restrict__ out, const
   int cur = 0;
   issue(u, 0);
   issue(u + gridDim.x, 1);
+  // operand fragments (zero padded to 8 x 8): per unit, or once for a single super-block
+  V l0 = __ldg(wtab + gid * 8 + tig), l1 = __ldg(wtab + gid * 8 + 4 + tig);
+  V r0 = __ldg(wtab + kTsMaxSb * 64 + gid * 8 + tig), r1 = __ldg(wtab + kTsMaxSb * 64 + gid * 8 + 4 + tig);
   for (; u < units; u += gridDim.x) {
     V* tile = tile0 + (size_t)cur * kTsSlots * 32;
+    uint32_t K, L;
+    uint64_t c;
+    decode(u, K, L, c);
+    const int nK = s_n[K], nL = s_n[L];
+    if (MULTI) {
+      const V* wl = wtab + (size_t)K * 64 + gid * 8 + tig;
+      const V* wr = wtab + (size_t)(kTsMaxSb + L) * 64 + gid * 8 + tig;
+      l0 = __ldg(wl); l1 = __ldg(wl + 4); r0 = __ldg(wr); r1 = __ldg(wr + 4);
+    }
     cp_async_wait<1>();
     __syncthreads();
     issue(u + 2 * (uint64_t)gridDim.x, cur == 0 ? 2 : cur - 1);  // the buffer of the previous tile
     // stage 1: column j of the tile, in place
-    for (int j = warp; j < n; j += kTsWarps) {
+    for (int j = warp; j < nL; j += kTsWarps) {
       V* col = tile + j * 32;
       V y0[4], y1[4];
-      product(l0, l1, [&](int a, int f) { return col[a * n * 32 + (f ^ (2 * (a & 3)))]; },
-              [&](int nt, int f, V v0, V v1) { y0[nt] = v0; y1[nt] = v1; (void)f; });
+      if (inner)
+        product(l0, l1, nK, [&](int a, int f) { return tile[a * 256 + f * 8 + (j ^ ts_sigma(f, a))]; },
+                [&](int nt, int f, V v0, V v1) { y0[nt] = v0; y1[nt] = v1; (void)f; });
+      else
+        product(l0, l1, nK, [&](int a, int f) { return col[a * nL * 32 + (f ^ (2 * (a & 3)))]; },
+                [&](int nt, int f, V v0, V v1) { y0[nt] = v0; y1[nt] = v1; (void)f; });
       __syncwarp();  // every lane has read its inputs before the column is overwritten
-      if (gid < n) {
-        V* dst = col + gid * n * 32;
+      if (inner) {
+        if (gid < nK) {
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            const int f = 8 * nt + 2 * tig;
+            tile[gid * 256 + f * 8 + (j ^ ts_sigma(f, gid))] = y0[nt];
+            tile[gid * 256 + (f + 1) * 8 + (j ^ ts_sigma(f + 1, gid))] = y1[nt];
+          }
+        }
+      } else if (gid < nK) {
+        V* dst = col + gid * nL * 32;
         const int sw = (2 * (j & 3)) ^ (gid & 1);
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
@@ -767,13 +933,17 @@ k_two_sided_mma(const double2* __restrict__ in, double2* __restrict__ out, const
     __syncthreads();
     // stage 2: row i of the tile, streamed to HBM
     const int64_t* sb = s_base + cur * 32;
-    for (int i = warp; i < n; i += kTsWarps) {
-      const V* row = tile + i * n * 32;
-      const int64_t ro = s_off[16 + i] + (gid < n ? s_off[24 + gid] : 0);
-      product(r0, r1, [&](int b, int f) { return row[b * 32 + (f ^ (2 * (b & 3)) ^ (i & 1))]; },
+    for (int i = warp; i < nK; i += kTsWarps) {
+      const V* row = tile + i * nL * 32;
+      const int64_t ro = rout[K * 8 + i] + cout[L * 8 + gid];
+      product(r0, r1, nL,
+              [&](int b, int f) {
+                return inner ? tile[i * 256 + f * 8 + (b ^ ts_sigma(f, i))]
+                             : row[b * 32 + (f ^ (2 * (b & 3)) ^ (i & 1))];
+              },
               [&](int nt, int f, V v0, V v1) {
                 (void)nt;
-                if (gid < n) {
+                if (gid < nL) {
                   const int64_t b0 = sb[f], b1 = sb[f + 1];
                   if (b0 >= 0) __stcg(out + b0 + ro, v0);
                   if (b1 >= 0) __stcg(out + b1 + ro, v1);
@@ -785,17 +955,30 @@ k_two_sided_mma(const double2* __restrict__ in, double2* __restrict__ out, const
   cp_async_wait<0>();
 }
 
+__global__ void __launch_bounds__(kTsWarps * 32, 2)
+k_two_sided_mma(const double2* __restrict__ in, double2* __restrict__ out, const FiberMap fm,
+                const TsTables T, const int inner, const int order) {
+  if (!T.flags->handled || !T.flags->use_mma) return;
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  if (inner) two_sided_mma_body<false, true>(in, out, fm, T, s_raw, 0);
+  else if (T.flags->nsb == 1) two_sided_mma_body<false, false>(in, out, fm, T, s_raw, 0);
+  else two_sided_mma_body<true, false>(in, out, fm, T, s_raw, order);
+}
+
 template <typename V>
 static int launch_two_sided_t(const V* rho, V* out, const V* op, const FiberMap& fm,
                               const TargetMap& rows, const TargetMap& cols, const int* other,
-                              TwoSided* ts, cudaStream_t s) {
+                              const bool inner, TwoSided* ts, cudaStream_t s) {
   PW_TRY(build_block_desc_t<V>(op, rows.t, false, rows, &ts->memL, &ts->L, s));
   PW_TRY(build_block_desc_t<V>(op, cols.t, true, cols, &ts->memR, &ts->R, s));
   const size_t t = rows.t, tt = t * t;
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const size_t b_flags = 256, b_groups = al(sizeof(int4) * 2 * tt), b_pairs = al(sizeof(int4) * tt),
-               b_off = al(sizeof(int64_t) * tt), b_item = al(sizeof(int4) * tt), b_row = al(sizeof(int) * tt);
-  PW_TRY(ts->flag_mem.alloc(b_flags + b_groups + b_pairs + 2 * b_off + 2 * b_item + b_row, s));
+               b_off = al(sizeof(int64_t) * tt), b_item = al(sizeof(int4) * tt), b_row = al(sizeof(int) * tt),
+               b_sbn = al(sizeof(int) * kTsMaxSb), b_sbblk = al(sizeof(int2) * t),
+               b_sboff = al(sizeof(int64_t) * 4 * kTsMaxSb * 8), b_sbw = al(sizeof(V) * 2 * kTsMaxSb * 64);
+  PW_TRY(ts->flag_mem.alloc(b_flags + b_groups + b_pairs + 2 * b_off + 2 * b_item + b_row + b_sbn + b_sbblk +
+                            b_sboff + b_sbw, s));
   char* base = (char*)ts->flag_mem.p;
   TsTables T;
   T.flags = (TsFlags*)base;
@@ -806,8 +989,14 @@ static int launch_two_sided_t(const V* rho, V* out, const V* op, const FiberMap&
   T.item1 = (int4*)(base + b_flags + b_groups + b_pairs + 2 * b_off);
   T.item2 = (int4*)(base + b_flags + b_groups + b_pairs + 2 * b_off + b_item);
   T.in_row = (int*)(base + b_flags + b_groups + b_pairs + 2 * b_off + 2 * b_item);
-  k_ts_build<V><<<1, 256, 0, s>>>(ts->L, ts->R, other, T, kTsValCap,
-                                  (sizeof(V) == 16 && options().ts_mma.load(std::memory_order_relaxed)) ? 1 : 0);
+  char* sbb = base + b_flags + b_groups + b_pairs + 2 * b_off + 2 * b_item + b_row;
+  T.sb_n = (int*)sbb;
+  T.sb_blk = (int2*)(sbb + b_sbn);
+  T.sb_off = (int64_t*)(sbb + b_sbn + b_sbblk);
+  T.sb_w = sbb + b_sbn + b_sbblk + b_sboff;
+  const bool mma_ok = sizeof(V) == 16 && options().ts_mma.load(std::memory_order_relaxed);
+  if (inner && !mma_ok) return PW_ERR_UNSUPPORTED;
+  k_ts_build<V><<<1, 256, 0, s>>>(ts->L, ts->R, other, T, kTsValCap, mma_ok ? 1 : 0, inner ? 1 : 0);
   PW_LAUNCHED();
   const size_t smem = 2 * kTsValCap + sizeof(V) * 2 * kTsSlots * 32;
   static bool attr_set = false;
@@ -821,15 +1010,17 @@ static int launch_two_sided_t(const V* rho, V* out, const V* op, const FiberMap&
   const int per_sm = options().ts_ctas.load(std::memory_order_relaxed);
   const int grid = kNumSMs * (per_sm > 0 ? per_sm : 2);
   k_two_sided<V><<<grid, kTsWarps * 32, smem, s>>>(rho, out, fm, ts->L, ts->R, T);
-  if (sizeof(V) == 16 && options().ts_mma.load(std::memory_order_relaxed)) {
+  if (mma_ok) {
     PW_LAUNCHED();
     static bool attr_mma = false;
-    const size_t smem_mma = sizeof(double2) * 3 * kTsSlots * 32 + (3 * 32 + 4 * 8) * sizeof(int64_t);
+    const size_t smem_mma = sizeof(double2) * 3 * kTsSlots * 32 + (3 * 32 + 4 * kTsMaxSb * 8) * sizeof(int64_t) +
+                            kTsMaxSb * sizeof(int);
     if (!attr_mma) {
       PW_CUDA(cudaFuncSetAttribute(k_two_sided_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma));
       attr_mma = true;
     }
-    k_two_sided_mma<<<grid, kTsWarps * 32, smem_mma, s>>>((const double2*)rho, (double2*)out, fm, ts->L, ts->R, T);
+    k_two_sided_mma<<<grid, kTsWarps * 32, smem_mma, s>>>((const double2*)rho, (double2*)out, fm, T, inner ? 1 : 0,
+                                                            options().ts_order.load(std::memory_order_relaxed));
   }
   PW_LAUNCHED();
   g_paths[4].fetch_add(1, std::memory_order_relaxed);
@@ -841,12 +1032,21 @@ int launch_two_sided(const void* rho, void* out, const void* op, const FiberMap&
                      const TargetMap& rows, const TargetMap& cols, int dtype, const int* other_handled,
                      TwoSided* ts, cudaStream_t stream) {
   if (rho == out || rows.t != cols.t || rows.t > kBlockMaxT) return PW_ERR_UNSUPPORTED;
+  // innermost axis: untouched (adjacent fibers), or the single column target of a 5..8-level
+  // operator with whole chunks of 32 fibers in the run next to it (tensor-core kernel only)
+  bool inner = false;
+  if (fm.ng == 0) return PW_ERR_UNSUPPORTED;
+  if (fm.gstride[fm.ng - 1] != 1) {
+    inner = cols.nt == 1 && cols.tstride[0] == 1 && cols.t >= 5 && cols.t <= 8 &&
+            fm.gstride[fm.ng - 1] == (int64_t)cols.t && fm.gsize[fm.ng - 1] % 32 == 0;
+    if (!inner) return PW_ERR_UNSUPPORTED;
+  }
   if (dtype == PW_C128)
     return launch_two_sided_t<double2>((const double2*)rho, (double2*)out, (const double2*)op, fm, rows,
-                                       cols, other_handled, ts, stream);
+                                       cols, other_handled, inner, ts, stream);
   if (dtype == PW_C64)
     return launch_two_sided_t<float2>((const float2*)rho, (float2*)out, (const float2*)op, fm, rows,
-                                      cols, other_handled, ts, stream);
+                                      cols, other_handled, inner, ts, stream);
   return PW_ERR_INVALID;
 }
 

@@ -133,8 +133,10 @@ __device__ __forceinline__ void block_product(const V* __restrict__ bv, const in
 // Enqueues the structure analysis of a dense t x t operator (t <= kBlockMaxT); element
 // offsets come from `tm` (global strides for the direct kernel, tile strides for the
 // tiled kernel).
+// `skip` (optional device flag): when set the analysis is not run and the descriptor reports
+// "not usable".
 int build_block_desc(const void* op, uint32_t t, bool conj_op, const TargetMap& tm, int dtype,
-                     Scratch* mem, BlockArrays* arr, cudaStream_t stream);
+                     Scratch* mem, BlockArrays* arr, cudaStream_t stream, const int* skip = nullptr);
 
 // Enqueues structure analysis + the block apply kernels.  `conj_op`: use conj(op).
 // Requires in != out.  After this call the caller must enqueue a fallback path whose

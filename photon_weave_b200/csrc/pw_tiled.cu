@@ -172,8 +172,9 @@ template <typename V>
 __global__ void __launch_bounds__(256)
 k_build_csr(const V* __restrict__ ops, const uint32_t t, const uint32_t cap, const PassKind k0,
             const PassKind k1, const int nkinds, int32_t* __restrict__ rowptr,
-            Entry<V>* __restrict__ ents) {
+            Entry<V>* __restrict__ ents, const int* __restrict__ skip) {
   extern __shared__ int32_t s_cnt[];  // [t + 1]
+  if (skip != nullptr && *skip != 0) return;  // the consumer exits on the same flag
   const V* op = ops + (size_t)blockIdx.x * t * t;
   int32_t* rp = rowptr + (size_t)blockIdx.x * (t + 1);
   Entry<V>* en = ents + (size_t)blockIdx.x * cap;
@@ -610,7 +611,7 @@ static int launch_tiled_t(const V* in, V* out, const V* ops, int K, const TiledG
   PW_TRY(ents.alloc(sizeof(Entry<V>) * (size_t)csrK * cap, s));
   k_build_csr<V><<<csrK, 256, sizeof(int32_t) * (t + 1), s>>>(
       csr_src, t, cap, g.kind[0], g.kind[g.nkinds > 1 ? 1 : 0], g.nkinds, (int32_t*)rowptr.p,
-      (Entry<V>*)ents.p);
+      (Entry<V>*)ents.p, skip);
   PW_LAUNCHED();
 
   TiledParams P;
@@ -624,9 +625,9 @@ static int launch_tiled_t(const V* in, V* out, const V* ops, int K, const TiledG
   // block-structured descriptors with TILE offsets (single operator only)
   if (csrK == 1 && t <= kBlockMaxT && options().vec_path.load(std::memory_order_relaxed) != 2) {
     PW_TRY(build_block_desc(csr_src, t, mode == kModeVectorConj, kind_target_map(g.kind[0]), dtype,
-                            &bmem0, &P.blk[0], s));
+                            &bmem0, &P.blk[0], s, skip));
     if (mode == kModeMatrixTwoSided)
-      PW_TRY(build_block_desc(csr_src, t, true, kind_target_map(g.kind[1]), dtype, &bmem1, &P.blk[1], s));
+      PW_TRY(build_block_desc(csr_src, t, true, kind_target_map(g.kind[1]), dtype, &bmem1, &P.blk[1], s, skip));
   }
 
   CUtensorMap tm_in, tm_out;

@@ -629,6 +629,16 @@ def test_two_sided_single_pass_kernel(ad, cdtype):
     check((8, 8, 10), (1, 0), ops.beam_splitter(8, 8, 0.6), 4)
     check((6, 5, 7, 3), (1,), ops.random_unitary(5, 5), 5)
     check((6, 5, 7, 3), (2, 0), ops.beam_splitter(7, 6, 0.3), 6)
+    # innermost axis IS the target (tensor-core kernel with the transposing load, complex128;
+    # complex64 and ragged runs take the two-pass route)
+    check((8, 8, 8), (2,), ops.random_unitary(8, 21), 21)
+    check((4, 16, 6), (2,), ops.random_unitary(6, 22), 22)
+    check((2, 32, 5), (2,), ops.squeezing_operator(5, 0.2 + 0.2j), 23)
+    check((64, 7), (1,), ops.random_unitary(7, 24), 24)
+    check((3, 24, 8), (2,), ops.random_unitary(8, 25), 25)           # run of 72: not whole chunks
+    # beam splitters whose sectors pack into several super-blocks (cutoffs 8, 5, 7 x 6)
+    check((3, 8, 8, 4), (1, 2), ops.beam_splitter(8, 8, 0.9), 26)
+    check((5, 5, 5, 5), (3, 1), ops.beam_splitter(5, 5, 0.7), 27)
     _lib.set_option("blocks_min_elems", 0)
     try:
         for tg in [(0,), (1,), (0, 1), (1, 0)]:
