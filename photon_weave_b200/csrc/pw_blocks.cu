@@ -504,6 +504,7 @@ constexpr int kTsSlots = 64;                 // tile = 64 slots x 32 lanes
 constexpr uint32_t kTsValCap = 8 * 1024;     // per side: block values (BS d=8: 344 x 16 B)
 
 constexpr int kTsMaxSb = 16;                 // tensor-core kernel: super-blocks per side
+constexpr int kTwMaxSb = 8;                  // wide-tile variant (innermost column targets)
 
 struct TsFlags { int handled; int any; int ngroups; int use_mma; int nsb; };
 
@@ -574,7 +575,13 @@ k_ts_build(const BlockArrays L, const BlockArrays R, const int* __restrict__ oth
     }
     // innermost (contiguous) column target: only the tensor-core kernel has the transposing
     // load, and only for ONE dense block whose columns are the contiguous run itself
-    if (inner && !(mma && hl->nblocks == 1)) h = 0;
+    // (inner bit 1: the column targets ARE the innermost run -> wide-tile kernel; bit 2: one
+    //  5..8-level column target with whole chunks of 32 fibers next to it -> 32-fiber tiles)
+    if (inner) {
+      if (mma && hl->nblocks == 1 && (inner & 2)) mma = 1;
+      else if (mma && nsb <= kTwMaxSb && hr->inplace_safe) mma = 2;
+      else h = 0;
+    }
     if (!h) mma = 0;
     int ng = 0;
     if (h && !mma) {
@@ -958,17 +965,205 @@ __device__ __forceinline__ void two_sided_mma_body(const double2* __restrict__ i
 __global__ void __launch_bounds__(kTsWarps * 32, 2)
 k_two_sided_mma(const double2* __restrict__ in, double2* __restrict__ out, const FiberMap fm,
                 const TsTables T, const int inner, const int order) {
-  if (!T.flags->handled || !T.flags->use_mma) return;
+  if (!T.flags->handled || T.flags->use_mma != 1) return;
   extern __shared__ __align__(16) unsigned char s_raw[];
   if (inner) two_sided_mma_body<false, true>(in, out, fm, T, s_raw, 0);
   else if (T.flags->nsb == 1) two_sided_mma_body<false, false>(in, out, fm, T, s_raw, 0);
   else two_sided_mma_body<true, false>(in, out, fm, T, s_raw, order);
 }
 
+
+// ---- wide tiles: the column targets are the innermost (contiguous) run -----------------------
+// With the column targets innermost (beam splitter on the last two modes), the column index
+// pairs of a super-block are scattered 16-byte pieces inside every run of t elements; the only
+// coalesced unit is the whole run.  A tile is therefore (row super-block K: <= 8 rows) x (F
+// fibers) x (ALL t column indices), F t ~ 512 elements per row (64 KB per tile, two buffers, one
+// 16-warp CTA per SM).  Row r of the tile is a contiguous piece of memory and keeps its order
+// (fiber-major, sigma-permuted inside 8-element groups as above).  Stage 1 works on the t columns
+// (operand: row block K), stage 2 on (row, column super-block L) and gathers its <= 8 inputs by
+// their position in the run.
+constexpr int kTwWarps = 16;
+constexpr int kTwRow = 512;   // elements per tile row
+constexpr int kTwBufs = 3;    // tile buffers (loads run two tiles ahead)
+
+struct TwMeta { int64_t base0; int K; int nvalid; };
+
+__global__ void __launch_bounds__(kTwWarps * 32, 1)
+k_two_sided_mma_wide(const double2* __restrict__ in, double2* __restrict__ out, const FiberMap fm,
+                     const TsTables T, const int t) {
+  using V = double2;
+  if (!T.flags->handled || T.flags->use_mma != 2) return;
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  V* tile0 = (V*)s_raw;                                       // [kTwBufs][8][kTwRow]
+  V* s_w = tile0 + kTwBufs * 8 * kTwRow;                      // [2][kTwMaxSb][64]
+  int64_t* s_roff = (int64_t*)(s_w + 2 * kTwMaxSb * 64);      // [2][kTwMaxSb][8] row offsets: in, out
+  TwMeta* s_meta = (TwMeta*)(s_roff + 2 * kTwMaxSb * 8);      // [kTwBufs]
+  int* s_cpos = (int*)(s_meta + kTwBufs);                     // [2][kTwMaxSb][8] column positions: in, out
+  int* s_n = s_cpos + 2 * kTwMaxSb * 8;                       // [kTwMaxSb]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int nsb = T.flags->nsb;
+  for (int i = threadIdx.x; i < 2 * kTwMaxSb * 64; i += blockDim.x) {
+    const int side = i / (kTwMaxSb * 64), r = i - side * (kTwMaxSb * 64);
+    s_w[i] = ((const V*)T.sb_w)[side * kTsMaxSb * 64 + r];
+  }
+  for (int i = threadIdx.x; i < 2 * kTwMaxSb * 8; i += blockDim.x) {
+    const int which = i / (kTwMaxSb * 8), r = i - which * (kTwMaxSb * 8);
+    s_roff[i] = T.sb_off[(2 * which) * kTsMaxSb * 8 + r];            // tables 0 (row in), 2 (row out)
+    s_cpos[i] = (int)T.sb_off[(2 * which + 1) * kTsMaxSb * 8 + r];   // tables 1 (column in), 3 (column out)
+  }
+  if (threadIdx.x < kTwMaxSb) s_n[threadIdx.x] = threadIdx.x < nsb ? T.sb_n[threadIdx.x] : 0;
+  __syncthreads();
+  const int64_t* rin = s_roff;
+  const int64_t* rout = s_roff + kTwMaxSb * 8;
+  const int* cin = s_cpos;
+  const int* cout = s_cpos + kTwMaxSb * 8;
+  const int tp = (t + 7) & ~7;                 // padded run (the sigma permutation stays inside 8-groups)
+  const int F = (kTwRow / tp) & ~7;            // fibers per tile: 64, 32, 16 or 8
+  const int nq = F >> 3, qsh = 31 - __clz(nq); // fiber octets per tile (a power of two)
+  const uint32_t inv_t = 0xffffffffu / (uint32_t)t + 1;      // r / t for r < 2^16
+  const uint32_t inv_nsb = 0xffffu / (uint32_t)nsb + 1;      // x / nsb for x < 2^8 (16-bit shift)
+  const uint32_t gl = (uint32_t)fm.gsize[fm.ng - 1];         // fibers per run of runs (stride t)
+  const uint32_t cpr = (gl + F - 1) / F;
+  const uint32_t chunks = (uint32_t)(fm.nfib / gl) * cpr;    // (host: chunks * nsb < 2^32)
+  const uint32_t units = chunks * (uint32_t)nsb;
+
+  // chunk fastest, K slowest
+  auto issue = [&](uint32_t u, int buf) {
+    if (u < units) {
+      const uint32_t K = u / chunks, c = u - K * chunks;
+      const uint32_t o = c / cpr, w = c - o * cpr;
+      const uint32_t f0 = w * F;
+      const int nvalid = (gl - f0) < (uint32_t)F ? (int)(gl - f0) : F;
+      const int64_t base0 = fm.base((uint64_t)o * gl + f0);
+      if (threadIdx.x == 0) { s_meta[buf].base0 = base0; s_meta[buf].K = (int)K; s_meta[buf].nvalid = nvalid; }
+      const int nK = s_n[K];
+      const int rowlen = nvalid * t;
+      V* tile = tile0 + (size_t)buf * 8 * kTwRow;
+      const int64_t* ro = rin + K * 8;
+      for (int r = threadIdx.x; r < rowlen; r += kTwWarps * 32) {
+        const int f = (int)__umulhi((uint32_t)r, inv_t), j = r - f * t;
+        V* dst = tile + f * tp;
+        const int jj = j ^ ((f & 1) << 2) ^ (f & 6);
+        const V* src = in + base0 + r;
+        for (int a = 0; a < nK; ++a) cp_async16(dst + a * kTwRow + (jj ^ (a & 3)), src + ro[a]);
+      }
+    }
+    cp_async_commit();
+  };
+
+  auto mma_item = [&](const V w0, const V w1, const V x0, const V x1, V& y0, V& y1) {
+    double re0 = 0.0, re1 = 0.0, im0 = 0.0, im1 = 0.0;
+    dmma8x8x4(re0, re1, w0.x, x0.x);
+    dmma8x8x4(im0, im1, w0.y, x0.x);
+    dmma8x8x4(re0, re1, -w0.y, x0.y);
+    dmma8x8x4(im0, im1, w0.x, x0.y);
+    dmma8x8x4(re0, re1, w1.x, x1.x);
+    dmma8x8x4(im0, im1, w1.y, x1.x);
+    dmma8x8x4(re0, re1, -w1.y, x1.y);
+    dmma8x8x4(im0, im1, w1.x, x1.y);
+    y0 = make_double2(re0, im0);
+    y1 = make_double2(re1, im1);
+  };
+
+  // lane constants of the sigma-permuted positions (see ts_sigma): reads take fiber gid of an
+  // octet, writes take fibers 2 tig and 2 tig + 1
+  const int sf = ((gid & 1) << 2) ^ (gid & 6);
+  const int rd1 = tig * kTwRow + gid * tp, s1 = sf ^ tig;             // stage 1 read: rows tig, 4 + tig
+  const int wr1 = gid * kTwRow + 2 * tig * tp, s2 = (2 * tig) ^ (gid & 3);  // stage 1 write: row gid
+  const V zero = make_double2(0.0, 0.0);
+
+  // Two barriers per tile: S1 between the stages, S2 after stage 2.  The copy-out of tile n has
+  // no barrier behind it, so it overlaps with stage 1 of tile n + 1 (already resident: every
+  // thread waits for its own loads of tile n + 1 before S2); the buffer of tile n is refilled
+  // (tile n + 3) after S1 of tile n + 1, when every warp has finished copying it out.
+  const uint32_t g = gridDim.x;
+  uint32_t u = blockIdx.x;
+  int cur = 0;
+  issue(u, 0);
+  issue(u + g, 1);
+  cp_async_wait<1>();
+  __syncthreads();
+  for (uint32_t n = 0; u < units; u += g, ++n) {
+    V* tile = tile0 + (size_t)cur * 8 * kTwRow;
+    const TwMeta meta = s_meta[cur];
+    const int K = meta.K, nK = s_n[K];
+    const V l0 = s_w[K * 64 + gid * 8 + tig], l1 = s_w[K * 64 + gid * 8 + 4 + tig];
+    // stage 1: (column j, fiber octet q), in place; two items per step (independent DMMA chains)
+    const int n1 = t << qsh;
+    for (int it = warp; it < n1; it += 2 * kTwWarps) {
+      const int itb = it + kTwWarps;
+      const bool two = itb < n1;
+      const int ja = it >> qsh, qa = (it & (nq - 1)) * 8 * tp;
+      const int jb = itb >> qsh, qb = (itb & (nq - 1)) * 8 * tp;
+      V xa0 = zero, xa1 = zero, xb0 = zero, xb1 = zero, ya0, ya1, yb0, yb1;
+      if (tig < nK) {
+        xa0 = tile[rd1 + qa + (ja ^ s1)];
+        if (two) xb0 = tile[rd1 + qb + (jb ^ s1)];
+      }
+      if (4 + tig < nK) {
+        xa1 = tile[rd1 + 4 * kTwRow + qa + (ja ^ s1)];
+        if (two) xb1 = tile[rd1 + 4 * kTwRow + qb + (jb ^ s1)];
+      }
+      mma_item(l0, l1, xa0, xa1, ya0, ya1);
+      mma_item(l0, l1, xb0, xb1, yb0, yb1);
+      __syncwarp();
+      if (gid < nK) {
+        tile[wr1 + qa + (ja ^ s2)] = ya0;
+        tile[wr1 + qa + tp + (ja ^ s2 ^ 4)] = ya1;
+        if (two) {
+          tile[wr1 + qb + (jb ^ s2)] = yb0;
+          tile[wr1 + qb + tp + (jb ^ s2 ^ 4)] = yb1;
+        }
+      }
+    }
+    __syncthreads();  // S1
+    if (n > 0) issue(u + 2 * g, cur == 0 ? kTwBufs - 1 : cur - 1);  // the buffer of the previous tile
+    else issue(u + 2 * g, 2);
+    // stage 2: (row i, column super-block L, fiber octet q), in place as well (the blocks'
+    // output positions are their input positions: hdr->inplace_safe) -- a scattered 16-byte
+    // store per output costs one L1 line transaction each
+    for (int it = warp; it < ((nK * nsb) << qsh); it += kTwWarps) {
+      const int qo = (it & (nq - 1)) * 8 * tp, r2 = it >> qsh;
+      const int i = (int)(((uint32_t)r2 * inv_nsb) >> 16), L = r2 - i * nsb;
+      const int nL = s_n[L];
+      const V r0 = s_w[(kTwMaxSb + L) * 64 + gid * 8 + tig], r1 = s_w[(kTwMaxSb + L) * 64 + gid * 8 + 4 + tig];
+      V* row = tile + i * kTwRow + qo;
+      const int sg = sf ^ (i & 3);
+      V x0 = zero, x1 = zero, y0, y1;
+      if (tig < nL) x0 = row[gid * tp + (cin[L * 8 + tig] ^ sg)];
+      if (4 + tig < nL) x1 = row[gid * tp + (cin[L * 8 + 4 + tig] ^ sg)];
+      mma_item(r0, r1, x0, x1, y0, y1);
+      __syncwarp();
+      if (gid < nL) {
+        const int pos = cout[L * 8 + gid] ^ (2 * tig) ^ (i & 3);
+        row[2 * tig * tp + pos] = y0;
+        row[(2 * tig + 1) * tp + (pos ^ 4)] = y1;
+      }
+    }
+    cp_async_wait<1>();  // own loads of the NEXT tile (the one issued above may still fly)
+    __syncthreads();     // S2
+    // copy out: whole rows, coalesced
+    {
+      const int rowlen = meta.nvalid * t;
+      const int64_t* ro = rout + K * 8;
+      for (int r = threadIdx.x; r < rowlen; r += kTwWarps * 32) {
+        const int f = (int)__umulhi((uint32_t)r, inv_t), j = r - f * t;
+        const V* src = tile + f * tp;
+        const int jj = j ^ ((f & 1) << 2) ^ (f & 6);
+        V* dst = out + meta.base0 + r;
+        for (int i = 0; i < nK; ++i) __stcg(dst + ro[i], src[i * kTwRow + (jj ^ (i & 3))]);
+      }
+    }
+    cur = cur == kTwBufs - 1 ? 0 : cur + 1;
+  }
+  cp_async_wait<0>();
+}
+
 template <typename V>
 static int launch_two_sided_t(const V* rho, V* out, const V* op, const FiberMap& fm,
                               const TargetMap& rows, const TargetMap& cols, const int* other,
-                              const bool inner, TwoSided* ts, cudaStream_t s) {
+                              const int inner, TwoSided* ts, cudaStream_t s) {
   PW_TRY(build_block_desc_t<V>(op, rows.t, false, rows, &ts->memL, &ts->L, s));
   PW_TRY(build_block_desc_t<V>(op, cols.t, true, cols, &ts->memR, &ts->R, s));
   const size_t t = rows.t, tt = t * t;
@@ -996,7 +1191,7 @@ static int launch_two_sided_t(const V* rho, V* out, const V* op, const FiberMap&
   T.sb_w = sbb + b_sbn + b_sbblk + b_sboff;
   const bool mma_ok = sizeof(V) == 16 && options().ts_mma.load(std::memory_order_relaxed);
   if (inner && !mma_ok) return PW_ERR_UNSUPPORTED;
-  k_ts_build<V><<<1, 256, 0, s>>>(ts->L, ts->R, other, T, kTsValCap, mma_ok ? 1 : 0, inner ? 1 : 0);
+  k_ts_build<V><<<1, 256, 0, s>>>(ts->L, ts->R, other, T, kTsValCap, mma_ok ? 1 : 0, inner);
   PW_LAUNCHED();
   const size_t smem = 2 * kTsValCap + sizeof(V) * 2 * kTsSlots * 32;
   static bool attr_set = false;
@@ -1021,6 +1216,18 @@ static int launch_two_sided_t(const V* rho, V* out, const V* op, const FiberMap&
     }
     k_two_sided_mma<<<grid, kTsWarps * 32, smem_mma, s>>>((const double2*)rho, (double2*)out, fm, T, inner ? 1 : 0,
                                                             options().ts_order.load(std::memory_order_relaxed));
+    if (inner) {
+      PW_LAUNCHED();
+      static bool attr_wide = false;
+      const size_t smem_wide = sizeof(double2) * (kTwBufs * 8 * kTwRow + 2 * kTwMaxSb * 64) +
+                               sizeof(int64_t) * 2 * kTwMaxSb * 8 + sizeof(TwMeta) * kTwBufs +
+                               sizeof(int) * (2 * kTwMaxSb * 8 + kTwMaxSb);
+      if (!attr_wide) {
+        PW_CUDA(cudaFuncSetAttribute(k_two_sided_mma_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wide));
+        attr_wide = true;
+      }
+      k_two_sided_mma_wide<<<kNumSMs, kTwWarps * 32, smem_wide, s>>>((const double2*)rho, (double2*)out, fm, T, (int)cols.t);
+    }
   }
   PW_LAUNCHED();
   g_paths[4].fetch_add(1, std::memory_order_relaxed);
@@ -1034,12 +1241,16 @@ int launch_two_sided(const void* rho, void* out, const void* op, const FiberMap&
   if (rho == out || rows.t != cols.t || rows.t > kBlockMaxT) return PW_ERR_UNSUPPORTED;
   // innermost axis: untouched (adjacent fibers), or the single column target of a 5..8-level
   // operator with whole chunks of 32 fibers in the run next to it (tensor-core kernel only)
-  bool inner = false;
+  // bit 1: the column targets are exactly the innermost run of t elements (wide tiles);
+  // bit 2: ... and ONE 5..8-level target with whole chunks of 32 fibers next to it (32-fiber tiles)
+  int inner = 0;
   if (fm.ng == 0) return PW_ERR_UNSUPPORTED;
   if (fm.gstride[fm.ng - 1] != 1) {
-    inner = cols.nt == 1 && cols.tstride[0] == 1 && cols.t >= 5 && cols.t <= 8 &&
-            fm.gstride[fm.ng - 1] == (int64_t)cols.t && fm.gsize[fm.ng - 1] % 32 == 0;
-    if (!inner) return PW_ERR_UNSUPPORTED;
+    bool run = fm.gstride[fm.ng - 1] == (int64_t)cols.t && cols.t >= 5 && cols.t <= 64 && dtype == PW_C128;
+    for (int k = 0; k < cols.nt && run; ++k) run = cols.tdim[k] == 1 || cols.tstride[k] < (int64_t)cols.t;
+    if (!run || fm.nfib >= (1ull << 28)) return PW_ERR_UNSUPPORTED;  // (32-bit unit index in the kernel)
+    inner = 1;
+    if (cols.nt == 1 && cols.tstride[0] == 1 && cols.t <= 8 && fm.gsize[fm.ng - 1] % 32 == 0) inner |= 2;
   }
   if (dtype == PW_C128)
     return launch_two_sided_t<double2>((const double2*)rho, (double2*)out, (const double2*)op, fm, rows,

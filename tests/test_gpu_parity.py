@@ -635,7 +635,14 @@ def test_two_sided_single_pass_kernel(ad, cdtype):
     check((4, 16, 6), (2,), ops.random_unitary(6, 22), 22)
     check((2, 32, 5), (2,), ops.squeezing_operator(5, 0.2 + 0.2j), 23)
     check((64, 7), (1,), ops.random_unitary(7, 24), 24)
-    check((3, 24, 8), (2,), ops.random_unitary(8, 25), 25)           # run of 72: not whole chunks
+    check((3, 24, 8), (2,), ops.random_unitary(8, 25), 25)           # run of 72: ragged wide tiles
+    check((9, 11, 6), (2,), ops.random_unitary(6, 28), 28)
+    # two-mode operators on the innermost modes (wide-tile tensor-core kernel)
+    check((3, 8, 8), (1, 2), ops.beam_splitter(8, 8, 0.4), 29)
+    check((3, 8, 8), (2, 1), ops.beam_splitter(8, 8, 0.4), 30)
+    check((5, 5, 5, 5), (2, 3), ops.beam_splitter(5, 5, 1.1), 31)
+    check((4, 3, 7, 6), (3, 2), ops.beam_splitter(6, 7, 0.8), 32)
+    check((10, 4, 7, 2, 4), (2, 3, 4), np.kron(ops.random_unitary(7, 33), ops.random_unitary(8, 34)), 33)
     # beam splitters whose sectors pack into several super-blocks (cutoffs 8, 5, 7 x 6)
     check((3, 8, 8, 4), (1, 2), ops.beam_splitter(8, 8, 0.9), 26)
     check((5, 5, 5, 5), (3, 1), ops.beam_splitter(5, 5, 0.7), 27)
