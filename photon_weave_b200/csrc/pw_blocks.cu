@@ -1003,9 +1003,11 @@ k_two_sided_mma_wide(const double2* __restrict__ in, double2* __restrict__ out, 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gid = lane >> 2, tig = lane & 3;
   const int nsb = T.flags->nsb;
+  // operand tables; column c of row r sits at r * 8 + (c ^ 4 (r & 1)): the fragment loads of a
+  // quarter warp (two rows x four columns) then hit eight different 16-byte bank groups
   for (int i = threadIdx.x; i < 2 * kTwMaxSb * 64; i += blockDim.x) {
     const int side = i / (kTwMaxSb * 64), r = i - side * (kTwMaxSb * 64);
-    s_w[i] = ((const V*)T.sb_w)[side * kTsMaxSb * 64 + r];
+    s_w[i ^ (((r >> 3) & 1) << 2)] = ((const V*)T.sb_w)[side * kTsMaxSb * 64 + r];
   }
   for (int i = threadIdx.x; i < 2 * kTwMaxSb * 8; i += blockDim.x) {
     const int which = i / (kTwMaxSb * 8), r = i - which * (kTwMaxSb * 8);
@@ -1028,8 +1030,12 @@ k_two_sided_mma_wide(const double2* __restrict__ in, double2* __restrict__ out, 
   const uint32_t chunks = (uint32_t)(fm.nfib / gl) * cpr;    // (host: chunks * nsb < 2^32)
   const uint32_t units = chunks * (uint32_t)nsb;
 
-  // chunk fastest, K slowest
-  auto issue = [&](uint32_t u, int buf) {
+  // chunk fastest, K slowest.  Loads are issued in two steps so that the rows can be spread
+  // over the stage 2 loop: prepare (decode the unit, publish its meta data) and rows [a0, a1).
+  struct Pending { const V* src; V* dst; const int64_t* ro; int nK, rowlen; };
+  auto issue_prepare = [&](uint32_t u, int buf) {
+    Pending p;
+    p.nK = 0; p.rowlen = 0; p.src = in; p.dst = tile0; p.ro = rin;
     if (u < units) {
       const uint32_t K = u / chunks, c = u - K * chunks;
       const uint32_t o = c / cpr, w = c - o * cpr;
@@ -1037,19 +1043,37 @@ k_two_sided_mma_wide(const double2* __restrict__ in, double2* __restrict__ out, 
       const int nvalid = (gl - f0) < (uint32_t)F ? (int)(gl - f0) : F;
       const int64_t base0 = fm.base((uint64_t)o * gl + f0);
       if (threadIdx.x == 0) { s_meta[buf].base0 = base0; s_meta[buf].K = (int)K; s_meta[buf].nvalid = nvalid; }
-      const int nK = s_n[K];
-      const int rowlen = nvalid * t;
-      V* tile = tile0 + (size_t)buf * 8 * kTwRow;
-      const int64_t* ro = rin + K * 8;
-      for (int r = threadIdx.x; r < rowlen; r += kTwWarps * 32) {
-        const int f = (int)__umulhi((uint32_t)r, inv_t), j = r - f * t;
-        V* dst = tile + f * tp;
-        const int jj = j ^ ((f & 1) << 2) ^ (f & 6);
-        const V* src = in + base0 + r;
-        for (int a = 0; a < nK; ++a) cp_async16(dst + a * kTwRow + (jj ^ (a & 3)), src + ro[a]);
-      }
+      p.nK = s_n[K];
+      p.rowlen = nvalid * t;
+      p.src = in + base0;
+      p.dst = tile0 + (size_t)buf * 8 * kTwRow;
+      p.ro = rin + K * 8;
     }
-    cp_async_commit();
+    return p;
+  };
+  auto issue_rows = [&](const Pending& p, int a0, int a1) {
+    if (a1 > p.nK) a1 = p.nK;
+    for (int r = threadIdx.x; r < p.rowlen; r += kTwWarps * 32) {
+      const int f = (int)__umulhi((uint32_t)r, inv_t), j = r - f * t;
+      V* dst = p.dst + f * tp;
+      const int jj = j ^ ((f & 1) << 2) ^ (f & 6);
+      const V* src = p.src + r;
+      for (int a = a0; a < a1; ++a) cp_async16(dst + a * kTwRow + (jj ^ (a & 3)), src + p.ro[a]);
+    }
+  };
+  // copy-out of rows [i0, i1) of a finished tile: whole rows, coalesced
+  auto copy_rows = [&](const V* tile, const TwMeta& m, int i0, int i1) {
+    const int nK = s_n[m.K];
+    if (i1 > nK) i1 = nK;
+    const int rowlen = m.nvalid * t;
+    const int64_t* ro = rout + m.K * 8;
+    for (int r = threadIdx.x; r < rowlen; r += kTwWarps * 32) {
+      const int f = (int)__umulhi((uint32_t)r, inv_t), j = r - f * t;
+      const V* src = tile + f * tp;
+      const int jj = j ^ ((f & 1) << 2) ^ (f & 6);
+      V* dst = out + m.base0 + r;
+      for (int i = i0; i < i1; ++i) __stcg(dst + ro[i], src[i * kTwRow + (jj ^ (i & 3))]);
+    }
   };
 
   auto mma_item = [&](const V w0, const V w1, const V x0, const V x1, V& y0, V& y1) {
@@ -1071,26 +1095,40 @@ k_two_sided_mma_wide(const double2* __restrict__ in, double2* __restrict__ out, 
   const int sf = ((gid & 1) << 2) ^ (gid & 6);
   const int rd1 = tig * kTwRow + gid * tp, s1 = sf ^ tig;             // stage 1 read: rows tig, 4 + tig
   const int wr1 = gid * kTwRow + 2 * tig * tp, s2 = (2 * tig) ^ (gid & 3);  // stage 1 write: row gid
+  const int fsw = (gid & 1) << 2;  // operand table swizzle
   const V zero = make_double2(0.0, 0.0);
 
-  // Two barriers per tile: S1 between the stages, S2 after stage 2.  The copy-out of tile n has
-  // no barrier behind it, so it overlaps with stage 1 of tile n + 1 (already resident: every
-  // thread waits for its own loads of tile n + 1 before S2); the buffer of tile n is refilled
-  // (tile n + 3) after S1 of tile n + 1, when every warp has finished copying it out.
+  // Two barriers per tile: S1 between the stages, S2 after stage 2.  The memory work is
+  // interleaved with the tensor-core work of the SAME warps (all warps of the CTA move in lock
+  // step, so separate phases would leave the DMMA pipe idle while the LSU works and vice versa):
+  // the copy-out of tile n - 1 is spread over the stage 1 loop of tile n, the loads of tile n + 2
+  // (into the buffer of tile n - 1, free after S1) over its stage 2 loop.
   const uint32_t g = gridDim.x;
   uint32_t u = blockIdx.x;
   int cur = 0;
-  issue(u, 0);
-  issue(u + g, 1);
+  {
+    const Pending p0 = issue_prepare(u, 0);
+    issue_rows(p0, 0, 8);
+    cp_async_commit();
+    const Pending p1 = issue_prepare(u + g, 1);
+    issue_rows(p1, 0, 8);
+    cp_async_commit();
+  }
   cp_async_wait<1>();
   __syncthreads();
-  for (uint32_t n = 0; u < units; u += g, ++n) {
+  TwMeta prev;
+  prev.base0 = 0; prev.K = 0; prev.nvalid = 0;  // nothing to copy out before the first tile
+  int Lc = -1, nLc = 0, c0 = 0, c1 = 0, cw = 0;  // cached column super-block of stage 2
+  V r0 = zero, r1 = zero;
+  const V* prev_tile = tile0;
+  for (; u < units; u += g) {
     V* tile = tile0 + (size_t)cur * 8 * kTwRow;
     const TwMeta meta = s_meta[cur];
     const int K = meta.K, nK = s_n[K];
-    const V l0 = s_w[K * 64 + gid * 8 + tig], l1 = s_w[K * 64 + gid * 8 + 4 + tig];
+    const V l0 = s_w[K * 64 + gid * 8 + (tig ^ fsw)], l1 = s_w[K * 64 + gid * 8 + ((4 + tig) ^ fsw)];
     // stage 1: (column j, fiber octet q), in place; two items per step (independent DMMA chains)
     const int n1 = t << qsh;
+    int crow = 0;
     for (int it = warp; it < n1; it += 2 * kTwWarps) {
       const int itb = it + kTwWarps;
       const bool two = itb < n1;
@@ -1107,6 +1145,8 @@ k_two_sided_mma_wide(const double2* __restrict__ in, double2* __restrict__ out, 
       }
       mma_item(l0, l1, xa0, xa1, ya0, ya1);
       mma_item(l0, l1, xb0, xb1, yb0, yb1);
+      copy_rows(prev_tile, prev, crow, crow + 4);  // while the tensor cores work
+      crow += 4;
       __syncwarp();
       if (gid < nK) {
         tile[wr1 + qa + (ja ^ s2)] = ya0;
@@ -1117,46 +1157,73 @@ k_two_sided_mma_wide(const double2* __restrict__ in, double2* __restrict__ out, 
         }
       }
     }
-    __syncthreads();  // S1
-    if (n > 0) issue(u + 2 * g, cur == 0 ? kTwBufs - 1 : cur - 1);  // the buffer of the previous tile
-    else issue(u + 2 * g, 2);
+    copy_rows(prev_tile, prev, crow, 8);
+    __syncthreads();  // S1: stage 1 done; the previous tile is copied out, its buffer is free
+    const Pending pend = issue_prepare(u + 2 * g, cur == 0 ? kTwBufs - 1 : cur - 1);
+    int lrow = 0;
     // stage 2: (row i, column super-block L, fiber octet q), in place as well (the blocks'
     // output positions are their input positions: hdr->inplace_safe) -- a scattered 16-byte
     // store per output costs one L1 line transaction each
-    for (int it = warp; it < ((nK * nsb) << qsh); it += kTwWarps) {
-      const int qo = (it & (nq - 1)) * 8 * tp, r2 = it >> qsh;
-      const int i = (int)(((uint32_t)r2 * inv_nsb) >> 16), L = r2 - i * nsb;
-      const int nL = s_n[L];
-      const V r0 = s_w[(kTwMaxSb + L) * 64 + gid * 8 + tig], r1 = s_w[(kTwMaxSb + L) * 64 + gid * 8 + 4 + tig];
-      V* row = tile + i * kTwRow + qo;
-      const int sg = sf ^ (i & 3);
-      V x0 = zero, x1 = zero, y0, y1;
-      if (tig < nL) x0 = row[gid * tp + (cin[L * 8 + tig] ^ sg)];
-      if (4 + tig < nL) x1 = row[gid * tp + (cin[L * 8 + 4 + tig] ^ sg)];
-      mma_item(r0, r1, x0, x1, y0, y1);
+    // (the column super-block of a warp's items rarely changes -- never for nsb = 8, 4, 2, 1 with
+    //  one fiber octet -- so its operand fragments and positions stay in registers)
+    const int n2 = (nK * nsb) << qsh;
+    for (int it = warp; it < n2; it += 2 * kTwWarps) {
+      const int itb = it + kTwWarps;
+      const bool two = itb < n2;
+      const int qa = (it & (nq - 1)) * 8 * tp, ra = it >> qsh;
+      const int ia = (int)(((uint32_t)ra * inv_nsb) >> 16), La = ra - ia * nsb;
+      const int qb = (itb & (nq - 1)) * 8 * tp, rb = itb >> qsh;
+      const int ib = (int)(((uint32_t)rb * inv_nsb) >> 16), Lb = two ? rb - ib * nsb : La;
+      if (La != Lc) {
+        Lc = La;
+        nLc = s_n[La];
+        c0 = cin[La * 8 + tig]; c1 = cin[La * 8 + 4 + tig]; cw = cout[La * 8 + gid] ^ (2 * tig);
+        r0 = s_w[(kTwMaxSb + La) * 64 + gid * 8 + (tig ^ fsw)];
+        r1 = s_w[(kTwMaxSb + La) * 64 + gid * 8 + ((4 + tig) ^ fsw)];
+      }
+      V* rowa = tile + ia * kTwRow + qa;
+      V xa0 = zero, xa1 = zero, ya0, ya1;
+      if (tig < nLc) xa0 = rowa[gid * tp + (c0 ^ sf ^ (ia & 3))];
+      if (4 + tig < nLc) xa1 = rowa[gid * tp + (c1 ^ sf ^ (ia & 3))];
+      mma_item(r0, r1, xa0, xa1, ya0, ya1);
+      const int nLa = nLc, cwa = cw;
+      if (Lb != Lc) {
+        Lc = Lb;
+        nLc = s_n[Lb];
+        c0 = cin[Lb * 8 + tig]; c1 = cin[Lb * 8 + 4 + tig]; cw = cout[Lb * 8 + gid] ^ (2 * tig);
+        r0 = s_w[(kTwMaxSb + Lb) * 64 + gid * 8 + (tig ^ fsw)];
+        r1 = s_w[(kTwMaxSb + Lb) * 64 + gid * 8 + ((4 + tig) ^ fsw)];
+      }
+      V* rowb = tile + ib * kTwRow + qb;
+      V xb0 = zero, xb1 = zero, yb0, yb1;
+      if (two) {
+        if (tig < nLc) xb0 = rowb[gid * tp + (c0 ^ sf ^ (ib & 3))];
+        if (4 + tig < nLc) xb1 = rowb[gid * tp + (c1 ^ sf ^ (ib & 3))];
+      }
+      mma_item(r0, r1, xb0, xb1, yb0, yb1);
+      issue_rows(pend, lrow, lrow + 4);  // while the tensor cores work
+      lrow += 4;
       __syncwarp();
-      if (gid < nL) {
-        const int pos = cout[L * 8 + gid] ^ (2 * tig) ^ (i & 3);
-        row[2 * tig * tp + pos] = y0;
-        row[(2 * tig + 1) * tp + (pos ^ 4)] = y1;
+      if (gid < nLa) {
+        const int pos = cwa ^ (ia & 3);
+        rowa[2 * tig * tp + pos] = ya0;
+        rowa[(2 * tig + 1) * tp + (pos ^ 4)] = ya1;
+      }
+      if (two && gid < nLc) {
+        const int pos = cw ^ (ib & 3);
+        rowb[2 * tig * tp + pos] = yb0;
+        rowb[(2 * tig + 1) * tp + (pos ^ 4)] = yb1;
       }
     }
-    cp_async_wait<1>();  // own loads of the NEXT tile (the one issued above may still fly)
-    __syncthreads();     // S2
-    // copy out: whole rows, coalesced
-    {
-      const int rowlen = meta.nvalid * t;
-      const int64_t* ro = rout + K * 8;
-      for (int r = threadIdx.x; r < rowlen; r += kTwWarps * 32) {
-        const int f = (int)__umulhi((uint32_t)r, inv_t), j = r - f * t;
-        const V* src = tile + f * tp;
-        const int jj = j ^ ((f & 1) << 2) ^ (f & 6);
-        V* dst = out + meta.base0 + r;
-        for (int i = 0; i < nK; ++i) __stcg(dst + ro[i], src[i * kTwRow + (jj ^ (i & 3))]);
-      }
-    }
+    issue_rows(pend, lrow, 8);
+    cp_async_commit();
+    cp_async_wait<1>();  // own loads of the NEXT tile (the ones just issued may still fly)
+    __syncthreads();     // S2: stage 2 done, the next tile is visible to everybody
+    prev = meta;
+    prev_tile = tile;
     cur = cur == kTwBufs - 1 ? 0 : cur + 1;
   }
+  copy_rows(prev_tile, prev, 0, 8);
   cp_async_wait<0>();
 }
 
