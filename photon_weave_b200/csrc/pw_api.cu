@@ -60,6 +60,7 @@ Options& options() {
     env("PW_TS_CTAS", p->ts_ctas);
     env("PW_TS_MMA", p->ts_mma);
     env("PW_TS_ORDER", p->ts_order);
+    env("PW_DENSE_MMA", p->dense_mma);
     return p;
   }();
   return *o;
@@ -85,6 +86,7 @@ extern "C" int pw_set_option(const char* name, int value) {
   else if (!std::strcmp(name, "ts_ctas")) o.ts_ctas.store(value);
   else if (!std::strcmp(name, "ts_mma")) o.ts_mma.store(value);
   else if (!std::strcmp(name, "ts_order")) o.ts_order.store(value);
+  else if (!std::strcmp(name, "dense_mma")) o.dense_mma.store(value);
   else return PW_ERR_INVALID;
   return PW_OK;
 }

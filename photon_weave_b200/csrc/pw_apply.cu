@@ -8,6 +8,7 @@
 #include "pw_internal.cuh"
 #include "pw_tiled.cuh"
 #include "pw_blocks.cuh"
+#include "pw_dense.cuh"
 
 namespace pw {
 
@@ -462,6 +463,12 @@ static int apply_axes(const void* in, void* out, const void* op, const int64_t* 
     const int rc = launch_blocks_seg(in, out, op, axes, naxes, targets, nt, dtype, conj_op, &bd, s);
     if (rc == PW_OK) skip = bd.skip_flag();
     else if (rc != PW_ERR_UNSUPPORTED) return rc;
+  }
+  // dense (or not usefully structured) complex128 operators up to 64 x 64 with adjacent fibers:
+  // FP64 tensor cores
+  if (vp == 0 && large && !prefer_tiled && options().dense_mma.load(std::memory_order_relaxed)) {
+    const int rc = launch_dense_mma(in, out, op, p, dtype, conj_op, s, skip);
+    if (rc != PW_ERR_UNSUPPORTED) return rc;
   }
   if (vp != 1) {
     TiledGeom g;

@@ -1,0 +1,168 @@
+// Dense one-sided apply on the FP64 tensor cores (complex128, 8 < t <= 64).
+//
+// A dense t x t operator on a complex128 state costs 8 t flop per 32 bytes moved; beyond t ~ 16
+// the FP64 pipe, not HBM, is the roof (DESIGN.md "c128 FP64 second roof").  The FMA pipe with its
+// broadcast shared-memory operand loads reaches ~6 TFLOP/s there (k_tiled: 10 % of the HBM roof
+// for a dense 36 x 36 two-mode operator); mma.sync.m8n8k4.f64 keeps the operands in fragments
+// and performs 256 FMAs per instruction.
+//
+// A CTA stages tiles of (all t operator indices) x (64 adjacent fibers) in shared memory with
+// cp.async (double buffered, XOR swizzled).  A warp item is (8 output rows) x (32 fibers): four
+// complex 8 x 8 accumulator tiles; per step of four complex inputs it loads ONE operator fragment
+// (reused by the four fiber octets) and four state fragments -- each a single 128-bit shared
+// load that yields the real AND the imaginary part -- and issues 16 DMMAs:
+//   [Yr; Yi] = [Wr -Wi; Wi Wr] [Xr; Xi].
+// The accumulators are streamed to HBM straight from the fragments (a lane owns two adjacent
+// fibers of one output row: one full 32-byte sector).
+#include "pw_internal.cuh"
+#include "pw_dense.cuh"
+
+namespace pw {
+
+namespace {
+
+constexpr int kDmFib = 64;       // fibers per tile
+constexpr int kDmMaxT = 64;
+
+__device__ __forceinline__ void dmma(double& d0, double& d1, const double a, const double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// blockDim = 32 * nwarps; dynamic smem: W [8 nm][wp] | offs [t] | base [2][64] | tiles [2][t][64]
+__global__ void __launch_bounds__(512, 1)
+k_apply_dense_mma(const double2* __restrict__ in, double2* __restrict__ out,
+                  const double2* __restrict__ op, const int conj_op, const FiberMap fm,
+                  const TargetMap tm, const int* __restrict__ skip) {
+  using V = double2;
+  if (skip != nullptr && *skip != 0) return;
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const int t = (int)tm.t;
+  const int nm = (t + 7) >> 3;             // groups of 8 output rows
+  const int ks = (t + 3) >> 2;             // steps of 4 complex inputs
+  const int wp = (4 * ks + 7) & ~7;        // operand row pitch (multiple of 8: bank analysis)
+  V* s_w = (V*)s_raw;                                        // [8 nm][wp], column c at (c ^ 4 (row & 1))
+  int64_t* s_off = (int64_t*)(s_w + 8 * nm * wp);            // [t]
+  int64_t* s_base = s_off + ((t + 1) & ~1);                  // [2][kDmFib]
+  V* tile0 = (V*)(s_base + 2 * kDmFib);                      // [2][t][kDmFib], fiber f of row j at (f ^ 2 (j & 3))
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  for (int i = threadIdx.x; i < 8 * nm * wp; i += blockDim.x) {
+    const int r = i / wp, c = i - r * wp;
+    V v = make_double2(0.0, 0.0);
+    if (r < t && c < t) {
+      v = op[(size_t)r * t + c];
+      if (conj_op) v.y = -v.y;
+    }
+    s_w[r * wp + (c ^ ((r & 1) << 2))] = v;
+  }
+  for (int j = threadIdx.x; j < t; j += blockDim.x) s_off[j] = tm.offset((uint32_t)j);
+  __syncthreads();
+  const uint64_t units = (fm.nfib + kDmFib - 1) / kDmFib;
+
+  auto issue = [&](uint64_t u, int buf) {
+    if (u < units) {
+      V* tile = tile0 + (size_t)buf * t * kDmFib;
+      const uint64_t fa = u * kDmFib + lane, fb = fa + 32;
+      const int64_t ba = fa < fm.nfib ? fm.base(fa) : -1, bb = fb < fm.nfib ? fm.base(fb) : -1;
+      if (warp == 0) { s_base[buf * kDmFib + lane] = ba; s_base[buf * kDmFib + 32 + lane] = bb; }
+      for (int j = warp; j < t; j += nwarps) {
+        const int sw = 2 * (j & 3);
+        const int64_t o = s_off[j];
+        if (ba >= 0) cp16(tile + j * kDmFib + (lane ^ sw), in + ba + o);
+        if (bb >= 0) cp16(tile + j * kDmFib + 32 + (lane ^ sw), in + bb + o);
+      }
+    }
+    cp_commit();
+  };
+
+  const int nitems = nm * (kDmFib / 32);
+  const int fsw = (gid & 1) << 2;
+  uint64_t u = blockIdx.x;
+  int cur = 0;
+  issue(u, 0);
+  for (; u < units; u += gridDim.x) {
+    const V* tile = tile0 + (size_t)cur * t * kDmFib;
+    issue(u + gridDim.x, cur ^ 1);
+    cp_wait<1>();
+    __syncthreads();
+    const int64_t* sb = s_base + cur * kDmFib;
+    for (int it = warp; it < nitems; it += nwarps) {
+      const int m = it >> 1, h = it & 1;
+      const int row = 8 * m + gid;
+      double acc[4][4];
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[n][q] = 0.0;
+      const V* wrow = s_w + row * wp;
+      const V* xcol = tile + 32 * h + (gid ^ (2 * tig));   // + j * 64 + 8 n   (j & 3 == tig)
+#pragma unroll 2
+      for (int k = 0; k < ks; ++k) {
+        const int j = 4 * k + tig;
+        const V w = wrow[(4 * k + tig) ^ fsw];
+        V x[4];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) x[n] = j < t ? xcol[j * kDmFib + 8 * n] : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          dmma(acc[n][0], acc[n][1], w.x, x[n].x);
+          dmma(acc[n][2], acc[n][3], w.y, x[n].x);
+          dmma(acc[n][0], acc[n][1], -w.y, x[n].y);
+          dmma(acc[n][2], acc[n][3], w.x, x[n].y);
+        }
+      }
+      if (row < t) {
+        const int64_t ro = s_off[row];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          const int f = 32 * h + 8 * n + 2 * tig;
+          const int64_t b0 = sb[f], b1 = sb[f + 1];
+          if (b0 >= 0) __stcg(out + b0 + ro, make_double2(acc[n][0], acc[n][2]));
+          if (b1 >= 0) __stcg(out + b1 + ro, make_double2(acc[n][1], acc[n][3]));
+        }
+      }
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  cp_wait<0>();
+}
+
+}  // namespace
+
+int launch_dense_mma(const void* in, void* out, const void* op, const Plan& p, int dtype, bool conj_op,
+                     cudaStream_t s, const int* skip) {
+  const int t = (int)p.tm.t;
+  if (dtype != PW_C128 || in == out || t <= 8 || t > kDmMaxT || p.fm.ng == 0) return PW_ERR_UNSUPPORTED;
+  if (p.fm.gstride[p.fm.ng - 1] != 1 || p.fm.gsize[p.fm.ng - 1] < 16) return PW_ERR_UNSUPPORTED;
+  const int nm = (t + 7) >> 3, ks = (t + 3) >> 2, wp = (4 * ks + 7) & ~7;
+  const size_t smem = sizeof(double2) * (size_t)(8 * nm * wp) + sizeof(int64_t) * (size_t)(((t + 1) & ~1) + 2 * kDmFib) +
+                      sizeof(double2) * (size_t)2 * t * kDmFib;
+  if (smem > 220 * 1024) return PW_ERR_UNSUPPORTED;
+  static size_t attr_bytes = 0;
+  if (smem > attr_bytes) {
+    PW_CUDA(cudaFuncSetAttribute(k_apply_dense_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+    attr_bytes = 220 * 1024;
+  }
+  // one warp per item (8 rows x 32 fibers); two CTAs per SM when the tiles allow it
+  int nwarps = 2 * nm;
+  if (nwarps > 16) nwarps = 16;
+  const int ctas = (smem + 1024) * 2 <= 227 * 1024 ? 2 : 1;
+  const uint64_t units = (p.fm.nfib + kDmFib - 1) / kDmFib;
+  uint64_t grid = (uint64_t)kNumSMs * ctas;
+  if (grid > units) grid = units;
+  k_apply_dense_mma<<<(unsigned)grid, nwarps * 32, smem, s>>>((const double2*)in, (double2*)out, (const double2*)op,
+                                                              conj_op ? 1 : 0, p.fm, p.tm, skip);
+  PW_LAUNCHED();
+  return PW_OK;
+}
+
+}  // namespace pw

@@ -659,3 +659,40 @@ def test_two_sided_single_pass_kernel(ad, cdtype):
         check((2, 2, 2, 7), (2, 0), ops.random_unitary(4, 12), 12)
     finally:
         _lib.set_option("blocks_min_elems", 1 << 18)
+
+
+def test_dense_tensor_core_kernel(ad):
+    """Dense complex128 operators with 8 < t <= 64 on adjacent fibers take the FP64 tensor-core
+    kernel (pw_dense.cu): vectors, the conjugated column side of a density matrix, ragged fiber
+    counts, operator-order targets, t not a multiple of 4 or 8."""
+    from photon_weave_b200 import _lib
+
+    tol = TOL[np.complex128]
+
+    def check_vec(dims, targets, op, seed):
+        N = math.prod(dims)
+        psi = ops.random_state(N, seed)
+        ref = oad.apply_operation_vector(dims, targets, psi, np.asarray(op, dtype=np.complex128), True)
+        out = host(ad.apply_operation_vector(dims, targets, dev(psi), dev(np.asarray(op, dtype=np.complex128))))
+        assert rel_err(out, ref) < tol, (dims, targets)
+
+    def check_mat(dims, targets, op, seed):
+        N = math.prod(dims)
+        rho = ops.random_density(N, seed)
+        ref = oad.apply_operation_matrix(dims, targets, rho, np.asarray(op, dtype=np.complex128), True)
+        out = host(ad.apply_operation_matrix(dims, targets, dev(rho), dev(np.asarray(op, dtype=np.complex128))))
+        assert rel_err(out, ref) < tol, (dims, targets)
+
+    _lib.set_option("blocks_min_elems", 0)
+    try:
+        check_vec((6, 6, 50), (0, 1), ops.random_unitary(36, 41), 41)
+        check_vec((6, 6, 50), (1, 0), ops.random_unitary(36, 42), 42)
+        check_vec((3, 8, 8, 77), (1, 2), ops.random_unitary(64, 43), 43)
+        check_vec((9, 3, 5, 33), (0,), ops.random_unitary(9, 44), 44)
+        check_vec((2, 13, 2, 19), (1,), ops.displacement_operator(13, 0.3 + 0.1j), 45)
+        check_vec((5, 7, 16), (1, 0), ops.random_unitary(35, 46), 46)
+        check_vec((3, 3, 3, 40), (2, 0, 1), ops.random_unitary(27, 47), 47)
+        check_mat((4, 4, 20), (0, 1), ops.random_unitary(16, 48), 48)
+        check_mat((3, 5, 16), (1, 0), ops.random_unitary(15, 49), 49)
+    finally:
+        _lib.set_option("blocks_min_elems", 1 << 18)
