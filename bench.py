@@ -334,6 +334,27 @@ def run_gpu_arm(args):
             "avg_ms": float(per_op_ms[pair_idx].mean()),
             "gbs": alg_bytes / (float(per_op_ms[pair_idx].mean()) * 1e-3) / 1e9}
     kernels["per_op_ms"] = {layer[i][2]: round(float(per_op_ms[i]), 4) for i in range(nops)}
+    if not args.no_extras and modes >= 5:
+        # worst case of the sweep: a dense Haar-random two-mode operator.  FP64-bound
+        # (8 t real flop per 32 bytes), served by the FP64 tensor-core kernel (pw_dense.cu).
+        from oracle import operators as _ops  # input generation only
+
+        t2 = cutoff * cutoff
+        dense2 = torch.as_tensor(np.ascontiguousarray(_ops.random_unitary(t2, 2))).cuda()
+        ffi.apply_vec(a, dense2, dims, (3, 4), out=b)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            ffi.apply_vec(a, dense2, dims, (3, 4), out=b)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        kernels["dense_%dx%d_modes_3_4" % (t2, t2)] = {
+            "ms": ms, "gbs": alg_bytes / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": alg_bytes / (ms * 1e-3) / 1e9 / peak,
+            "fp64_tflops": 8.0 * N * t2 / (ms * 1e-3) / 1e12,
+            "note": "FP64-bound: 8*t real flop per amplitude; mma.sync m8n8k4 f64"}
+        del dense2
 
     # ---- end to end: host buffers through the C ABI (pw_circuit_host) -------------------
     e2e, h_pinned = run_e2e_prepare(args, torch, a, N)
@@ -488,7 +509,10 @@ def run_matrix_extras(torch, ffi, peak):
         ("kraus_loss_K8_mode2", lambda: ffi.kraus_mat(rho, loss, dims, (2,), out=out)),
         ("apply_phase_mode1", lambda: ffi.apply_mat(rho, ph, dims, (1,), out=out)),
         ("apply_dense_8x8_mode2", lambda: ffi.apply_mat(rho, u, dims, (2,), out=out)),
+        ("apply_dense_8x8_mode4_innermost", lambda: ffi.apply_mat(rho, u, dims, (4,), out=out)),
         ("apply_beam_splitter_modes_1_2", lambda: ffi.apply_mat(rho, bs, dims, (1, 2), out=out)),
+        ("apply_beam_splitter_modes_3_4_innermost", lambda: ffi.apply_mat(rho, bs, dims, (3, 4), out=out)),
+        ("kraus_loss_K8_mode4_innermost", lambda: ffi.kraus_mat(rho, loss, dims, (4,), out=out)),
     ]:
         ms = timed(fn)
         gbs = nbytes / (ms * 1e-3) / 1e9

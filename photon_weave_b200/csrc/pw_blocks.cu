@@ -249,13 +249,18 @@ __device__ __forceinline__ void cp_async_wait_all() {
 template <typename V>
 __global__ void __launch_bounds__(256)
 k_apply_blocks_seg(const V* __restrict__ in, V* __restrict__ out, const SegGeom g,
-                   const BlockArrays A, const uint32_t desc_cap) {
+                   const BlockArrays A, const uint32_t desc_cap, const uint32_t fpw) {
   if (!A.hdr->seg_handled) return;
   extern __shared__ __align__(16) unsigned char s_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const DescView<V> dv = desc_view<V>(A, s_raw, desc_cap);
-  V* buf = (V*)(s_raw + desc_cap) + (size_t)warp * 32 * g.pitch;
-  const uint64_t chunks = (g.M + 31) / 32;
+  // a warp stages `fpw` (32, 16 or 8) adjacent fibers; 32 / fpw lanes share a fiber and take
+  // every (32 / fpw)-th block (blocks are independent): smaller stages -> more resident warps
+  // to overlap one warp's load -> compute -> store sequence with the others'
+  const uint32_t lpf = 32 / fpw;
+  const uint32_t myfib = (uint32_t)lane / lpf, sub = (uint32_t)lane - myfib * lpf;
+  V* buf = (V*)(s_raw + desc_cap) + (size_t)warp * fpw * g.pitch;
+  const uint64_t chunks = (g.M + fpw - 1) / fpw;
   const uint64_t ntasks = g.outer.nfib * chunks;
   // lane-constant decomposition of the coalesced copy index e = it*32 + lane into
   // (fiber q, position r) without divisions: each iteration adds 32 = qa*lseg + rb
@@ -263,8 +268,8 @@ k_apply_blocks_seg(const V* __restrict__ in, V* __restrict__ out, const SegGeom 
   for (uint64_t task = (uint64_t)blockIdx.x * nwarps + warp; task < ntasks;
        task += (uint64_t)gridDim.x * nwarps) {
     const uint64_t o = task / chunks, c = task - o * chunks;
-    const uint64_t m0 = c * 32;
-    const uint32_t nvalid = (uint32_t)((g.M - m0) < 32 ? (g.M - m0) : 32);
+    const uint64_t m0 = c * fpw;
+    const uint32_t nvalid = (uint32_t)((g.M - m0) < fpw ? (g.M - m0) : fpw);
     const int64_t base = g.outer.base(o) + (int64_t)m0 * g.lseg;
     const uint32_t row_elems = nvalid * g.lseg;
     // ---- stage: nseg coalesced rows -> padded per-fiber rows in shared memory
@@ -280,17 +285,17 @@ k_apply_blocks_seg(const V* __restrict__ in, V* __restrict__ out, const SegGeom 
     }
     cp_async_wait_all();
     __syncwarp();
-    // ---- compute: one fiber per lane, blocks applied in place
-    if ((uint32_t)lane < nvalid) {
-      V* fib = buf + (size_t)lane * g.pitch;
-      for (int b = 0; b < dv.nblocks; ++b) {
+    // ---- compute: blocks applied in place
+    if (myfib < nvalid) {
+      V* fib = buf + (size_t)myfib * g.pitch;
+      for (int b = (int)sub; b < dv.nblocks; b += (int)lpf) {
         const int4 h = dv.blocks[b];
         const int64_t* bo = dv.offs + h.z;
         block_product<V>(dv.vals + h.w, h.x, h.y,
                          [&](int j) { return fib[(int32_t)bo[j]]; },
                          [&](int a, V v) { fib[(int32_t)bo[h.y + a]] = v; });
       }
-      for (int z = 0; z < dv.nzero; ++z) fib[(int32_t)dv.zero_offs[z]] = czero<V>();
+      for (int z = (int)sub; z < dv.nzero; z += (int)lpf) fib[(int32_t)dv.zero_offs[z]] = czero<V>();
     }
     __syncwarp();
     // ---- stream back, same coalesced row pattern
@@ -440,10 +445,17 @@ static int launch_blocks_seg_t(const V* in, V* out, const V* op, const SegGeom& 
   PW_TRY(build_block_desc_t<V>(op, g.t, conj_op, stm, &d->mem, &d->arr, s));
   d->hdr = d->arr.hdr;
   d->staged = true;
-  const size_t per_warp = (size_t)32 * g.pitch * sizeof(V);
   // descriptor copy (worst case for `usable` operators: t blocks, 2t offsets, 8t values)
   uint32_t desc_cap = (uint32_t)(g.t * 16 + 2 * g.t * 8 + g.t * 8 + 8 * g.t * sizeof(V) + 64);
   desc_cap = (desc_cap + 127u) & ~127u;
+  // fibers per warp stage: 32 (measured: 16 / 8 with lanes sharing a fiber buy more resident
+  // warps but the lanes' different block shapes diverge -- 10.5 / 16.4 ms against 10.7 ms for the
+  // loss channel on the innermost mode of rho, 16.9 / 26.8 against 15.1 ms for the beam splitter
+  // on the two innermost modes of the vector)
+  uint32_t fpw = 32;
+  const int forced = options().seg_fpw.load(std::memory_order_relaxed);
+  if (forced == 32 || forced == 16 || forced == 8) fpw = (uint32_t)forced;
+  const size_t per_warp = (size_t)fpw * g.pitch * sizeof(V);
   int warps = (int)((110 * 1024 - desc_cap) / per_warp);
   if (warps < 1) return PW_ERR_UNSUPPORTED;
   if (warps > 8) warps = 8;
@@ -453,14 +465,14 @@ static int launch_blocks_seg_t(const V* in, V* out, const V* op, const SegGeom& 
     PW_CUDA(cudaFuncSetAttribute(k_apply_blocks_seg<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  const uint64_t ntasks = g.outer.nfib * ((g.M + 31) / 32);
+  const uint64_t ntasks = g.outer.nfib * ((g.M + fpw - 1) / fpw);
   int ctas = (int)((227 * 1024) / (smem + 1024));
   if (ctas > 8) ctas = 8;
   if (ctas < 1) ctas = 1;
   uint64_t grid = (ntasks + warps - 1) / warps;
   if (grid > (uint64_t)kNumSMs * ctas) grid = (uint64_t)kNumSMs * ctas;
   const BlockArrays& A = d->arr;
-  k_apply_blocks_seg<V><<<(unsigned)grid, warps * 32, smem, s>>>(in, out, g, A, desc_cap);
+  k_apply_blocks_seg<V><<<(unsigned)grid, warps * 32, smem, s>>>(in, out, g, A, desc_cap, fpw);
   PW_LAUNCHED();
   g_paths[4].fetch_add(1, std::memory_order_relaxed);
   return PW_OK;
