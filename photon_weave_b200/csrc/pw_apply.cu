@@ -466,7 +466,7 @@ static int apply_axes(const void* in, void* out, const void* op, const int64_t* 
   }
   // dense (or not usefully structured) complex128 operators up to 64 x 64 with adjacent fibers:
   // FP64 tensor cores
-  if (vp == 0 && large && !prefer_tiled && options().dense_mma.load(std::memory_order_relaxed)) {
+  if (vp == 0 && large && options().dense_mma.load(std::memory_order_relaxed)) {
     const int rc = launch_dense_mma(in, out, op, p, dtype, conj_op, s, skip);
     if (rc != PW_ERR_UNSUPPORTED) return rc;
   }

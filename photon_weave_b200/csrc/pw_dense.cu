@@ -14,6 +14,12 @@
 //   [Yr; Yi] = [Wr -Wi; Wi Wr] [Xr; Xi].
 // The accumulators are streamed to HBM straight from the fragments (a lane owns two adjacent
 // fibers of one output row: one full 32-byte sector).
+//
+// INNER: the targets ARE the innermost axes, i.e. a fiber is a contiguous run of t elements and
+// 64 adjacent fibers are one contiguous piece of memory.  The tile keeps that order ([fiber][t],
+// pitch = 4 mod 8 elements so that the state fragments of a quarter warp -- two fibers x four
+// inputs -- fall into eight different 16-byte bank groups), the loads are one coalesced copy, and
+// a store instruction writes four full 128-byte lines (eight adjacent output rows per fiber).
 #include "pw_internal.cuh"
 #include "pw_dense.cuh"
 
@@ -37,6 +43,8 @@ template <int N>
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // blockDim = 32 * nwarps; dynamic smem: W [8 nm][wp] | offs [t] | base [2][64] | tiles [2][t][64]
+// (INNER: tiles [2][64][tp]; base[buf][0..1] = first element of the tile, valid fibers)
+template <bool INNER>
 __global__ void __launch_bounds__(512, 1)
 k_apply_dense_mma(const double2* __restrict__ in, double2* __restrict__ out,
                   const double2* __restrict__ op, const int conj_op, const FiberMap fm,
@@ -52,6 +60,12 @@ k_apply_dense_mma(const double2* __restrict__ in, double2* __restrict__ out,
   int64_t* s_off = (int64_t*)(s_w + 8 * nm * wp);            // [t]
   int64_t* s_base = s_off + ((t + 1) & ~1);                  // [2][kDmFib]
   V* tile0 = (V*)(s_base + 2 * kDmFib);                      // [2][t][kDmFib], fiber f of row j at (f ^ 2 (j & 3))
+  int tp = t;                                                // INNER: fiber pitch, 4 mod 8
+  while ((tp & 7) != 4) ++tp;
+  const size_t tile_elems = INNER ? (size_t)kDmFib * tp : (size_t)t * kDmFib;
+  const uint32_t inv_t = 0xffffffffu / (uint32_t)t + 1;      // e / t for e < 2^16
+  const uint64_t gl = INNER ? fm.gsize[fm.ng - 1] : 1;       // INNER: fibers per contiguous run
+  const uint64_t cpr = (gl + kDmFib - 1) / kDmFib;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int gid = lane >> 2, tig = lane & 3;
   for (int i = threadIdx.x; i < 8 * nm * wp; i += blockDim.x) {
@@ -65,11 +79,28 @@ k_apply_dense_mma(const double2* __restrict__ in, double2* __restrict__ out,
   }
   for (int j = threadIdx.x; j < t; j += blockDim.x) s_off[j] = tm.offset((uint32_t)j);
   __syncthreads();
-  const uint64_t units = (fm.nfib + kDmFib - 1) / kDmFib;
+  const uint64_t units = INNER ? (fm.nfib / gl) * cpr : (fm.nfib + kDmFib - 1) / kDmFib;
 
   auto issue = [&](uint64_t u, int buf) {
+    if (INNER) {
+      if (u < units) {
+        V* tile = tile0 + (size_t)buf * tile_elems;
+        const uint64_t o = u / cpr, w = u - o * cpr;
+        const uint64_t f0 = w * kDmFib;
+        const int nvalid = (gl - f0) < (uint64_t)kDmFib ? (int)(gl - f0) : kDmFib;
+        const int64_t base0 = fm.base(o * gl + f0);
+        if (threadIdx.x == 0) { s_base[buf * kDmFib] = base0; s_base[buf * kDmFib + 1] = nvalid; }
+        const V* src = in + base0;
+        for (int e = threadIdx.x; e < nvalid * t; e += blockDim.x) {
+          const int f = (int)__umulhi((uint32_t)e, inv_t);
+          cp16(tile + f * tp + (e - f * t), src + e);
+        }
+      }
+      cp_commit();
+      return;
+    }
     if (u < units) {
-      V* tile = tile0 + (size_t)buf * t * kDmFib;
+      V* tile = tile0 + (size_t)buf * tile_elems;
       const uint64_t fa = u * kDmFib + lane, fb = fa + 32;
       const int64_t ba = fa < fm.nfib ? fm.base(fa) : -1, bb = fb < fm.nfib ? fm.base(fb) : -1;
       if (warp == 0) { s_base[buf * kDmFib + lane] = ba; s_base[buf * kDmFib + 32 + lane] = bb; }
@@ -89,7 +120,7 @@ k_apply_dense_mma(const double2* __restrict__ in, double2* __restrict__ out,
   int cur = 0;
   issue(u, 0);
   for (; u < units; u += gridDim.x) {
-    const V* tile = tile0 + (size_t)cur * t * kDmFib;
+    const V* tile = tile0 + (size_t)cur * tile_elems;
     issue(u + gridDim.x, cur ^ 1);
     cp_wait<1>();
     __syncthreads();
@@ -103,14 +134,21 @@ k_apply_dense_mma(const double2* __restrict__ in, double2* __restrict__ out,
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[n][q] = 0.0;
       const V* wrow = s_w + row * wp;
-      const V* xcol = tile + 32 * h + (gid ^ (2 * tig));   // + j * 64 + 8 n   (j & 3 == tig)
+      const V* xcol = INNER ? tile + (32 * h + gid) * tp                 // + 8 n tp + position of j
+                            : tile + 32 * h + (gid ^ (2 * tig));        // + j * 64 + 8 n   (j & 3 == tig)
 #pragma unroll 2
       for (int k = 0; k < ks; ++k) {
         const int j = 4 * k + tig;
         const V w = wrow[(4 * k + tig) ^ fsw];
         V x[4];
+        if (INNER) {
+          const int pj = j < t ? (int)s_off[j] : 0;
 #pragma unroll
-        for (int n = 0; n < 4; ++n) x[n] = j < t ? xcol[j * kDmFib + 8 * n] : make_double2(0.0, 0.0);
+          for (int n = 0; n < 4; ++n) x[n] = j < t ? xcol[8 * n * tp + pj] : make_double2(0.0, 0.0);
+        } else {
+#pragma unroll
+          for (int n = 0; n < 4; ++n) x[n] = j < t ? xcol[j * kDmFib + 8 * n] : make_double2(0.0, 0.0);
+        }
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
           dmma(acc[n][0], acc[n][1], w.x, x[n].x);
@@ -119,7 +157,18 @@ k_apply_dense_mma(const double2* __restrict__ in, double2* __restrict__ out,
           dmma(acc[n][2], acc[n][3], w.x, x[n].y);
         }
       }
-      if (row < t) {
+      if (INNER) {
+        if (row < t) {
+          const int nvalid = (int)sb[1];
+          V* dst = out + sb[0] + s_off[row];
+#pragma unroll
+          for (int n = 0; n < 4; ++n) {
+            const int f = 32 * h + 8 * n + 2 * tig;
+            if (f < nvalid) __stcg(dst + (int64_t)f * t, make_double2(acc[n][0], acc[n][2]));
+            if (f + 1 < nvalid) __stcg(dst + (int64_t)(f + 1) * t, make_double2(acc[n][1], acc[n][3]));
+          }
+        }
+      } else if (row < t) {
         const int64_t ro = s_off[row];
 #pragma unroll
         for (int n = 0; n < 4; ++n) {
@@ -142,25 +191,41 @@ int launch_dense_mma(const void* in, void* out, const void* op, const Plan& p, i
                      cudaStream_t s, const int* skip) {
   const int t = (int)p.tm.t;
   if (dtype != PW_C128 || in == out || t <= 8 || t > kDmMaxT || p.fm.ng == 0) return PW_ERR_UNSUPPORTED;
-  if (p.fm.gstride[p.fm.ng - 1] != 1 || p.fm.gsize[p.fm.ng - 1] < 16) return PW_ERR_UNSUPPORTED;
+  // fibers adjacent in memory (untouched innermost run), or the targets are the innermost run
+  bool inner = false;
+  if (p.fm.gstride[p.fm.ng - 1] != 1) {
+    inner = p.fm.gstride[p.fm.ng - 1] == (int64_t)t;
+    for (int k = 0; k < p.tm.nt && inner; ++k) inner = p.tm.tdim[k] == 1 || p.tm.tstride[k] < (int64_t)t;
+    if (!inner) return PW_ERR_UNSUPPORTED;
+  } else if (p.fm.gsize[p.fm.ng - 1] < 16) {
+    return PW_ERR_UNSUPPORTED;
+  }
   const int nm = (t + 7) >> 3, ks = (t + 3) >> 2, wp = (4 * ks + 7) & ~7;
+  int tp = t;
+  while ((tp & 7) != 4) ++tp;
   const size_t smem = sizeof(double2) * (size_t)(8 * nm * wp) + sizeof(int64_t) * (size_t)(((t + 1) & ~1) + 2 * kDmFib) +
-                      sizeof(double2) * (size_t)2 * t * kDmFib;
+                      sizeof(double2) * (size_t)2 * (inner ? tp : t) * kDmFib;
   if (smem > 220 * 1024) return PW_ERR_UNSUPPORTED;
-  static size_t attr_bytes = 0;
-  if (smem > attr_bytes) {
-    PW_CUDA(cudaFuncSetAttribute(k_apply_dense_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
-    attr_bytes = 220 * 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PW_CUDA(cudaFuncSetAttribute(k_apply_dense_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+    PW_CUDA(cudaFuncSetAttribute(k_apply_dense_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+    attr_set = true;
   }
   // one warp per item (8 rows x 32 fibers); two CTAs per SM when the tiles allow it
   int nwarps = 2 * nm;
   if (nwarps > 16) nwarps = 16;
   const int ctas = (smem + 1024) * 2 <= 227 * 1024 ? 2 : 1;
-  const uint64_t units = (p.fm.nfib + kDmFib - 1) / kDmFib;
+  const uint64_t gl = inner ? p.fm.gsize[p.fm.ng - 1] : 1;
+  const uint64_t units = inner ? (p.fm.nfib / gl) * ((gl + kDmFib - 1) / kDmFib) : (p.fm.nfib + kDmFib - 1) / kDmFib;
   uint64_t grid = (uint64_t)kNumSMs * ctas;
   if (grid > units) grid = units;
-  k_apply_dense_mma<<<(unsigned)grid, nwarps * 32, smem, s>>>((const double2*)in, (double2*)out, (const double2*)op,
-                                                              conj_op ? 1 : 0, p.fm, p.tm, skip);
+  if (inner)
+    k_apply_dense_mma<true><<<(unsigned)grid, nwarps * 32, smem, s>>>((const double2*)in, (double2*)out, (const double2*)op,
+                                                                      conj_op ? 1 : 0, p.fm, p.tm, skip);
+  else
+    k_apply_dense_mma<false><<<(unsigned)grid, nwarps * 32, smem, s>>>((const double2*)in, (double2*)out, (const double2*)op,
+                                                                       conj_op ? 1 : 0, p.fm, p.tm, skip);
   PW_LAUNCHED();
   return PW_OK;
 }

@@ -693,6 +693,13 @@ def test_dense_tensor_core_kernel(ad):
         check_vec((5, 7, 16), (1, 0), ops.random_unitary(35, 46), 46)
         check_vec((3, 3, 3, 40), (2, 0, 1), ops.random_unitary(27, 47), 47)
         check_mat((4, 4, 20), (0, 1), ops.random_unitary(16, 48), 48)
+        # targets = the innermost axes (contiguous fibers): transposing tile layout
+        check_vec((50, 6, 6), (1, 2), ops.random_unitary(36, 51), 51)
+        check_vec((50, 6, 6), (2, 1), ops.random_unitary(36, 52), 52)
+        check_vec((7, 13), (1,), ops.random_unitary(13, 53), 53)
+        check_vec((3, 70, 8, 8), (2, 3), ops.random_unitary(64, 54), 54)
+        check_mat((20, 4, 4), (1, 2), ops.random_unitary(16, 55), 55)
+        check_mat((33, 11), (1,), ops.random_unitary(11, 56), 56)
         check_mat((3, 5, 16), (1, 0), ops.random_unitary(15, 49), 49)
     finally:
         _lib.set_option("blocks_min_elems", 1 << 18)
