@@ -249,8 +249,9 @@ __device__ __forceinline__ void cp_async_wait_all() {
 template <typename V>
 __global__ void __launch_bounds__(256)
 k_apply_blocks_seg(const V* __restrict__ in, V* __restrict__ out, const SegGeom g,
-                   const BlockArrays A, const uint32_t desc_cap, const uint32_t fpw) {
-  if (!A.hdr->seg_handled) return;
+                   const BlockArrays A, const uint32_t desc_cap, const uint32_t fpw,
+                   const int* __restrict__ mma_taken) {
+  if (!A.hdr->seg_handled || (mma_taken != nullptr && *mma_taken != 0)) return;
   extern __shared__ __align__(16) unsigned char s_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const DescView<V> dv = desc_view<V>(A, s_raw, desc_cap);
@@ -439,12 +440,20 @@ static bool plan_seg(const int64_t* axes, int naxes, const int* targets, int nt,
   return true;
 }
 
+// tensor-core variant of the staged kernel (complex128; defined at the end of this file):
+// enqueues the super-block packing and the kernel; *mma_taken = device flag the scalar kernel
+// must honour (nullptr when the variant does not apply)
+static int enqueue_seg_mma(const void* in, void* out, const SegGeom& g, BlockDesc* d, int dtype,
+                           cudaStream_t s, const int** mma_taken);
+
 template <typename V>
 static int launch_blocks_seg_t(const V* in, V* out, const V* op, const SegGeom& g, const TargetMap& stm,
                                bool conj_op, BlockDesc* d, cudaStream_t s) {
   PW_TRY(build_block_desc_t<V>(op, g.t, conj_op, stm, &d->mem, &d->arr, s));
   d->hdr = d->arr.hdr;
   d->staged = true;
+  const int* mma_taken = nullptr;
+  PW_TRY(enqueue_seg_mma(in, out, g, d, sizeof(V) == 16 ? PW_C128 : PW_C64, s, &mma_taken));
   // descriptor copy (worst case for `usable` operators: t blocks, 2t offsets, 8t values)
   uint32_t desc_cap = (uint32_t)(g.t * 16 + 2 * g.t * 8 + g.t * 8 + 8 * g.t * sizeof(V) + 64);
   desc_cap = (desc_cap + 127u) & ~127u;
@@ -472,7 +481,7 @@ static int launch_blocks_seg_t(const V* in, V* out, const V* op, const SegGeom& 
   uint64_t grid = (ntasks + warps - 1) / warps;
   if (grid > (uint64_t)kNumSMs * ctas) grid = (uint64_t)kNumSMs * ctas;
   const BlockArrays& A = d->arr;
-  k_apply_blocks_seg<V><<<(unsigned)grid, warps * 32, smem, s>>>(in, out, g, A, desc_cap, fpw);
+  k_apply_blocks_seg<V><<<(unsigned)grid, warps * 32, smem, s>>>(in, out, g, A, desc_cap, fpw, mma_taken);
   PW_LAUNCHED();
   g_paths[4].fetch_add(1, std::memory_order_relaxed);
   return PW_OK;
@@ -1338,6 +1347,239 @@ int launch_two_sided(const void* rho, void* out, const void* op, const FiberMap&
     return launch_two_sided_t<float2>((const float2*)rho, (float2*)out, (const float2*)op, fm, rows,
                                       cols, other_handled, inner, ts, stream);
   return PW_ERR_INVALID;
+}
+
+// ---- staged block kernel on the FP64 tensor cores ---------------------------------------------
+// Same geometry as k_apply_blocks_seg (the innermost axis is a target: a fiber's t elements are
+// nseg contiguous segments), but a CTA stages 64 adjacent fibers, the blocks are packed into
+// super-blocks of <= 8 indices (first-fit decreasing, like the two-sided kernel) and a warp item
+// is (super-block) x (32 fibers): 8 shared loads, 32 DMMAs, 8 shared stores, in place.  The tile
+// is [fiber][t] (pitch a multiple of 8, position p of fiber f at p ^ sigma(f): loads, fragment
+// reads and fragment writes are all bank-conflict free and a cp.async instruction stays inside
+// whole 128-byte rows); copy-in and copy-out are the coalesced segment rows of the scalar
+// kernel.  The scalar kernel is bound by its per-fiber instruction stream (52 % of the HBM roof
+// for the loss channel on the innermost mode of rho); here the arithmetic is 0.125 DMMA per
+// element and the kernel is HBM-bound.
+constexpr int kSgFib = 64;
+constexpr int kSgMaxSb = 16;
+
+struct SegSb {
+  int* flags;      // [0] = 1: the tensor-core kernel runs (and the scalar one exits); [1] = nsb
+  int* sb_n;       // [kSgMaxSb]
+  int2* sb_blk;    // [t] per block: (super-block, first index)
+  int* pos;        // [2][kSgMaxSb][8] positions inside the fiber row: inputs, outputs
+  double2* w;      // [kSgMaxSb][8][8] zero-padded block-diagonal values, column c of row r at (c ^ 4 (r & 1))
+};
+
+__global__ void __launch_bounds__(128)
+k_seg_sb_build(const BlockArrays A, const SegSb S) {
+  __shared__ int s_bn[kBlockMaxT];
+  __shared__ int s_ok, s_square;
+  const BlockDescHeader* h = A.hdr;
+  if (threadIdx.x == 0) s_square = 1;
+  __syncthreads();
+  const int m = h->seg_handled ? min(h->nblocks, (int)kBlockMaxT) : 0;
+  for (int b = threadIdx.x; b < m; b += blockDim.x) {
+    const int4 x = A.blocks[b];
+    s_bn[b] = x.x;
+    if (x.x != x.y) s_square = 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // all 1 x 1 (diagonal / permutation) operators stay on the scalar kernel
+    int ok = (h->seg_handled && h->nzero == 0 && h->maxn >= 2 && h->maxn <= 8 && s_square) ? 1 : 0;
+    int nsb = 0, fill[kSgMaxSb];
+    for (int sz = 8; sz >= 1 && ok; --sz)
+      for (int b = 0; b < m && ok; ++b) {
+        if (s_bn[b] != sz) continue;
+        int q = 0;
+        while (q < nsb && fill[q] + sz > 8) ++q;
+        if (q == nsb) {
+          if (nsb == kSgMaxSb) { ok = 0; break; }
+          fill[nsb++] = 0;
+        }
+        S.sb_blk[b] = make_int2(q, fill[q]);
+        fill[q] += sz;
+      }
+    for (int q = 0; q < nsb && ok; ++q) S.sb_n[q] = fill[q];
+    S.flags[0] = ok;
+    S.flags[1] = nsb;
+    s_ok = ok;
+  }
+  __syncthreads();
+  if (!s_ok) return;
+  for (int i = threadIdx.x; i < kSgMaxSb * 64; i += blockDim.x) S.w[i] = make_double2(0.0, 0.0);
+  for (int i = threadIdx.x; i < 2 * kSgMaxSb * 8; i += blockDim.x) S.pos[i] = 0;
+  __syncthreads();
+  for (int b = threadIdx.x; b < m; b += blockDim.x) {
+    const int4 hb = A.blocks[b];
+    const int2 sp = S.sb_blk[b];
+    const int n = hb.x;
+    const int64_t* bo = A.offs + hb.z;   // n column (input) positions, then n row (output) positions
+    const double2* v = (const double2*)A.vals + hb.w;
+    for (int a = 0; a < n; ++a) {
+      const int r = sp.y + a;
+      S.pos[sp.x * 8 + r] = (int)bo[a];
+      S.pos[(kSgMaxSb + sp.x) * 8 + r] = (int)bo[n + a];
+      for (int c = 0; c < n; ++c) S.w[sp.x * 64 + r * 8 + ((sp.y + c) ^ ((r & 1) << 2))] = v[a * n + c];
+    }
+  }
+}
+
+struct SgMeta { int64_t base; int nvalid; int pad; };
+
+__global__ void __launch_bounds__(512, 1)
+k_apply_blocks_seg_mma(const double2* __restrict__ in, double2* __restrict__ out, const SegGeom g,
+                       const SegSb S) {
+  using V = double2;
+  if (!S.flags[0]) return;
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  const int t = (int)g.t, tp = (t + 7) & ~7;
+  V* s_w = (V*)s_raw;                                   // [kSgMaxSb][64]
+  V* tile0 = s_w + kSgMaxSb * 64;                       // [2][kSgFib][tp]
+  SgMeta* s_meta = (SgMeta*)(tile0 + 2 * kSgFib * tp);  // [2]
+  int* s_pos = (int*)(s_meta + 2);                      // [2][kSgMaxSb][8]
+  int* s_n = s_pos + 2 * kSgMaxSb * 8;                  // [kSgMaxSb]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int nsb = S.flags[1];
+  for (int i = threadIdx.x; i < kSgMaxSb * 64; i += blockDim.x) s_w[i] = S.w[i];
+  for (int i = threadIdx.x; i < 2 * kSgMaxSb * 8; i += blockDim.x) s_pos[i] = S.pos[i];
+  if (threadIdx.x < kSgMaxSb) s_n[threadIdx.x] = threadIdx.x < nsb ? S.sb_n[threadIdx.x] : 0;
+  __syncthreads();
+  const uint32_t lseg = g.lseg;
+  const uint32_t inv_l = 0xffffffffu / lseg + 1;        // e / lseg for e < 2^16
+  const uint64_t chunks = (g.M + kSgFib - 1) / kSgFib;
+  const uint64_t units = g.outer.nfib * chunks;
+
+  auto sigma = [](int f) { return ((f & 1) << 2) ^ (f & 6); };
+  // copy the nseg coalesced segment rows of a tile: global <-> [fiber][position ^ sigma(fiber)]
+  auto decode = [&](uint64_t u, int64_t& base, int& nvalid) {
+    const uint64_t o = u / chunks, c = u - o * chunks;
+    const uint64_t m0 = c * kSgFib;
+    nvalid = (g.M - m0) < (uint64_t)kSgFib ? (int)(g.M - m0) : kSgFib;
+    base = g.outer.base(o) + (int64_t)m0 * lseg;
+  };
+  auto issue = [&](uint64_t u, int buf) {
+    if (u < units) {
+      int64_t base;
+      int nvalid;
+      decode(u, base, nvalid);
+      if (threadIdx.x == 0) { s_meta[buf].base = base; s_meta[buf].nvalid = nvalid; }
+      V* tile = tile0 + (size_t)buf * kSgFib * tp;
+      const int rowlen = nvalid * (int)lseg;
+      for (uint32_t sg = 0; sg < g.nseg; ++sg) {
+        const V* src = in + base + g.seg_off[sg];
+        for (int e = threadIdx.x; e < rowlen; e += blockDim.x) {
+          const int f = (int)__umulhi((uint32_t)e, inv_l);
+          const int p = (int)(sg * lseg) + (e - f * (int)lseg);
+          cp_async16(tile + f * tp + (p ^ sigma(f)), src + e);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+
+  const int sf = sigma(gid);             // fragment reads: fiber 8 n + gid
+  const int fsw = (gid & 1) << 2;
+  const V zero = make_double2(0.0, 0.0);
+  uint64_t u = blockIdx.x;
+  int cur = 0;
+  issue(u, 0);
+  for (; u < units; u += gridDim.x) {
+    V* tile = tile0 + (size_t)cur * kSgFib * tp;
+    __syncthreads();  // the other buffer has been copied out
+    issue(u + gridDim.x, cur ^ 1);
+    cp_async_wait<1>();
+    __syncthreads();
+    const SgMeta meta = s_meta[cur];
+    for (int it = warp; it < 2 * nsb; it += nwarps) {
+      const int sb = it >> 1, h = it & 1;
+      const int n = s_n[sb];
+      const V w0 = s_w[sb * 64 + gid * 8 + (tig ^ fsw)], w1 = s_w[sb * 64 + gid * 8 + ((4 + tig) ^ fsw)];
+      const int p0 = s_pos[sb * 8 + tig] ^ sf, p1 = s_pos[sb * 8 + 4 + tig] ^ sf;
+      V* xf = tile + (32 * h + gid) * tp;
+      double acc[4][4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const V x0 = tig < n ? xf[8 * q * tp + p0] : zero;
+        const V x1 = 4 + tig < n ? xf[8 * q * tp + p1] : zero;
+        acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0;
+        dmma8x8x4(acc[q][0], acc[q][1], w0.x, x0.x);
+        dmma8x8x4(acc[q][2], acc[q][3], w0.y, x0.x);
+        dmma8x8x4(acc[q][0], acc[q][1], -w0.y, x0.y);
+        dmma8x8x4(acc[q][2], acc[q][3], w0.x, x0.y);
+        dmma8x8x4(acc[q][0], acc[q][1], w1.x, x1.x);
+        dmma8x8x4(acc[q][2], acc[q][3], w1.y, x1.x);
+        dmma8x8x4(acc[q][0], acc[q][1], -w1.y, x1.y);
+        dmma8x8x4(acc[q][2], acc[q][3], w1.x, x1.y);
+      }
+      __syncwarp();  // every lane has read its inputs before the positions are overwritten
+      if (gid < n) {
+        const int po = s_pos[(kSgMaxSb + sb) * 8 + gid] ^ (2 * tig);   // sigma(8 q + 2 tig) = 2 tig
+        V* yf = tile + (32 * h + 2 * tig) * tp;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          yf[8 * q * tp + po] = make_double2(acc[q][0], acc[q][2]);
+          yf[(8 * q + 1) * tp + (po ^ 4)] = make_double2(acc[q][1], acc[q][3]);
+        }
+      }
+    }
+    __syncthreads();
+    {
+      const int rowlen = meta.nvalid * (int)lseg;
+      for (uint32_t sg = 0; sg < g.nseg; ++sg) {
+        V* dst = out + meta.base + g.seg_off[sg];
+        for (int e = threadIdx.x; e < rowlen; e += blockDim.x) {
+          const int f = (int)__umulhi((uint32_t)e, inv_l);
+          const int p = (int)(sg * lseg) + (e - f * (int)lseg);
+          __stcg(dst + e, tile[f * tp + (p ^ sigma(f))]);
+        }
+      }
+    }
+    cur ^= 1;
+  }
+  cp_async_wait<0>();
+}
+
+static int enqueue_seg_mma(const void* in, void* out, const SegGeom& g, BlockDesc* d, int dtype,
+                           cudaStream_t s, const int** mma_taken) {
+  *mma_taken = nullptr;
+  if (dtype != PW_C128 || g.t > 64 || g.t < 4 || g.lseg > 1024 ||
+      !options().seg_mma.load(std::memory_order_relaxed))
+    return PW_OK;
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t b_flags = 256, b_n = al(sizeof(int) * kSgMaxSb), b_blk = al(sizeof(int2) * g.t),
+               b_pos = al(sizeof(int) * 2 * kSgMaxSb * 8), b_w = al(sizeof(double2) * kSgMaxSb * 64);
+  PW_TRY(d->mem2.alloc(b_flags + b_n + b_blk + b_pos + b_w, s));
+  char* base = (char*)d->mem2.p;
+  SegSb S;
+  S.flags = (int*)base;
+  S.sb_n = (int*)(base + b_flags);
+  S.sb_blk = (int2*)(base + b_flags + b_n);
+  S.pos = (int*)(base + b_flags + b_n + b_blk);
+  S.w = (double2*)(base + b_flags + b_n + b_blk + b_pos);
+  k_seg_sb_build<<<1, 128, 0, s>>>(d->arr, S);
+  PW_LAUNCHED();
+  const int tp = ((int)g.t + 7) & ~7;
+  const size_t smem = sizeof(double2) * (size_t)(kSgMaxSb * 64 + 2 * kSgFib * tp) + sizeof(SgMeta) * 2 +
+                      sizeof(int) * (2 * kSgMaxSb * 8 + kSgMaxSb);
+  static bool attr_set = false;
+  if (!attr_set) {
+    PW_CUDA(cudaFuncSetAttribute(k_apply_blocks_seg_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  int nwarps = 2 * (((int)g.t + 7) / 8);
+  if (nwarps < 4) nwarps = 4;
+  if (nwarps > 16) nwarps = 16;
+  const int ctas = (smem + 1024) * 2 <= 227 * 1024 ? 2 : 1;
+  const uint64_t units = g.outer.nfib * ((g.M + kSgFib - 1) / kSgFib);
+  uint64_t grid = (uint64_t)kNumSMs * ctas;
+  if (grid > units) grid = units;
+  k_apply_blocks_seg_mma<<<(unsigned)grid, nwarps * 32, smem, s>>>((const double2*)in, (double2*)out, g, S);
+  PW_LAUNCHED();
+  *mma_taken = S.flags;
+  return PW_OK;
 }
 
 }  // namespace pw

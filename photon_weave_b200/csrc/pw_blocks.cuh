@@ -28,7 +28,7 @@ struct BlockArrays {
 };
 
 struct BlockDesc {
-  Scratch mem;
+  Scratch mem, mem2;  // descriptor; tensor-core tables of the staged kernel
   BlockArrays arr;
   BlockDescHeader* hdr = nullptr;
   bool staged = false;  // launch_blocks_seg was used: the flag to honour is seg_handled

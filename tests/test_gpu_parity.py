@@ -703,3 +703,38 @@ def test_dense_tensor_core_kernel(ad):
         check_mat((3, 5, 16), (1, 0), ops.random_unitary(15, 49), 49)
     finally:
         _lib.set_option("blocks_min_elems", 1 << 18)
+
+
+def test_staged_block_kernel_on_tensor_cores(ad):
+    """Block-structured complex128 operators whose innermost axis is a target take the staged
+    kernel's tensor-core variant (super-blocks of <= 8 indices, pw_blocks.cu): beam splitters on
+    the innermost modes, innermost + far targets (segmented fibers), loss channels on the
+    innermost mode of a density matrix (superoperator blocks), ragged fiber counts."""
+    from photon_weave_b200 import _lib
+
+    tol = TOL[np.complex128]
+    _lib.set_option("blocks_min_elems", 0)
+    try:
+        for seed, (dims, targets, op) in enumerate([
+            ((70, 6, 6), (1, 2), ops.beam_splitter(6, 6, 0.7)),
+            ((70, 6, 6), (2, 1), ops.beam_splitter(6, 6, 0.7)),
+            ((6, 100, 6), (2, 0), ops.beam_splitter(6, 6, 1.2)),
+            ((6, 100, 6), (0, 2), ops.beam_splitter(6, 6, 1.2)),
+            ((8, 3, 33, 8), (0, 3), ops.beam_splitter(8, 8, 0.3)),
+            ((5, 77, 7), (2, 0), ops.beam_splitter(7, 5, 0.9)),
+            ((3, 4, 5, 4), (3, 1), np.kron(ops.random_unitary(4, 1), np.eye(4))[:, np.random.default_rng(3).permutation(16)]),
+        ]):
+            N = math.prod(dims)
+            psi = ops.random_state(N, 60 + seed)
+            ref = oad.apply_operation_vector(dims, targets, psi, np.asarray(op, dtype=np.complex128), True)
+            out = host(ad.apply_operation_vector(dims, targets, dev(psi), dev(np.asarray(op, dtype=np.complex128))))
+            assert rel_err(out, ref) < tol, (dims, targets)
+        for seed, (dims, targets, d) in enumerate([((70, 8), (1,), 8), ((5, 9, 6), (2,), 6), ((130, 5), (1,), 5)]):
+            N = math.prod(dims)
+            rho = ops.random_density(N, 70 + seed)
+            ks = ops.loss_channel(d, 0.2)
+            ref = oad.apply_kraus_matrix(dims, targets, rho, ks, True)
+            out = host(ad.apply_kraus_matrix(dims, targets, dev(rho), dev(ks)))
+            assert rel_err(out, ref) < tol, (dims, targets)
+    finally:
+        _lib.set_option("blocks_min_elems", 1 << 18)
