@@ -445,7 +445,19 @@ static int apply_axes(const void* in, void* out, const void* op, const int64_t* 
   // layout; for t > 8 the direct block kernel wins when the contiguous direction is an
   // untouched run (>= small_r elements), TMA-staged tiles win when it belongs to the fibers.
   const bool prefer_tiled = vp == 2 || (vp == 0 && large && r_in < small_r && p.tm.t > 8);
-  if (p.tm.t <= 8 && vp != 3 && !prefer_tiled) return launch_apply(in, out, op, p, dtype, conj_op, false, s);
+  if (p.tm.t <= 8 && vp != 3 && !prefer_tiled) {
+    // 5..8-level complex128 operator on the innermost axis (contiguous fibers): the staged
+    // tensor-core kernel (HBM-bound) first, the warp-transposing register kernel as fallback
+    BlockDesc bd8;
+    const int* skip8 = nullptr;
+    if (vp == 0 && dtype == PW_C128 && p.tm.t >= 5 && large && in != out && r_in == 0 &&
+        options().seg_mma.load(std::memory_order_relaxed) > 1) {
+      const int rc = launch_blocks_seg(in, out, op, axes, naxes, targets, nt, dtype, conj_op, &bd8, s, true);
+      if (rc == PW_OK) skip8 = bd8.skip_flag();
+      else if (rc != PW_ERR_UNSUPPORTED) return rc;
+    }
+    return launch_apply(in, out, op, p, dtype, conj_op, false, s, skip8);
+  }
   // launch-latency-bound states: one row-parallel dense kernel, no analysis, no tiles
   if (vp == 0 && !large && in != out) {
     const int rc = launch_apply_rows(in, out, op, p, dtype, conj_op, s);

@@ -448,12 +448,18 @@ static int enqueue_seg_mma(const void* in, void* out, const SegGeom& g, BlockDes
 
 template <typename V>
 static int launch_blocks_seg_t(const V* in, V* out, const V* op, const SegGeom& g, const TargetMap& stm,
-                               bool conj_op, BlockDesc* d, cudaStream_t s) {
+                               bool conj_op, BlockDesc* d, cudaStream_t s, bool mma_only) {
   PW_TRY(build_block_desc_t<V>(op, g.t, conj_op, stm, &d->mem, &d->arr, s));
   d->hdr = d->arr.hdr;
   d->staged = true;
   const int* mma_taken = nullptr;
   PW_TRY(enqueue_seg_mma(in, out, g, d, sizeof(V) == 16 ? PW_C128 : PW_C64, s, &mma_taken));
+  if (mma_only) {
+    if (mma_taken == nullptr) return PW_ERR_UNSUPPORTED;
+    d->mma_flag = mma_taken;
+    g_paths[4].fetch_add(1, std::memory_order_relaxed);
+    return PW_OK;
+  }
   // descriptor copy (worst case for `usable` operators: t blocks, 2t offsets, 8t values)
   uint32_t desc_cap = (uint32_t)(g.t * 16 + 2 * g.t * 8 + g.t * 8 + 8 * g.t * sizeof(V) + 64);
   desc_cap = (desc_cap + 127u) & ~127u;
@@ -489,15 +495,15 @@ static int launch_blocks_seg_t(const V* in, V* out, const V* op, const SegGeom& 
 
 int launch_blocks_seg(const void* in, void* out, const void* op, const int64_t* axes, int naxes,
                       const int* targets, int nt, int dtype, bool conj_op, BlockDesc* desc,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, bool mma_only) {
   if (in == out) return PW_ERR_UNSUPPORTED;
   SegGeom g;
   TargetMap stm;
   if (!plan_seg(axes, naxes, targets, nt, &g, &stm)) return PW_ERR_UNSUPPORTED;
   if (dtype == PW_C128)
-    return launch_blocks_seg_t<double2>((const double2*)in, (double2*)out, (const double2*)op, g, stm, conj_op, desc, stream);
+    return launch_blocks_seg_t<double2>((const double2*)in, (double2*)out, (const double2*)op, g, stm, conj_op, desc, stream, mma_only);
   if (dtype == PW_C64)
-    return launch_blocks_seg_t<float2>((const float2*)in, (float2*)out, (const float2*)op, g, stm, conj_op, desc, stream);
+    return launch_blocks_seg_t<float2>((const float2*)in, (float2*)out, (const float2*)op, g, stm, conj_op, desc, stream, mma_only);
   return PW_ERR_INVALID;
 }
 
@@ -1360,8 +1366,13 @@ int launch_two_sided(const void* rho, void* out, const void* op, const FiberMap&
 // kernel.  The scalar kernel is bound by its per-fiber instruction stream (52 % of the HBM roof
 // for the loss channel on the innermost mode of rho); here the arithmetic is 0.125 DMMA per
 // element and the kernel is HBM-bound.
-constexpr int kSgFib = 64;
 constexpr int kSgMaxSb = 16;
+// fibers per tile: a multiple of 64 that makes the tile ~32 KB (64 for t >= 32, 512 for t = 4)
+static inline int seg_mma_fibers(int t) {
+  const int tp = (t + 7) & ~7;
+  int f = (2048 / tp) & ~63;
+  return f < 64 ? 64 : f;
+}
 
 struct SegSb {
   int* flags;      // [0] = 1: the tensor-core kernel runs (and the scalar one exits); [1] = nsb
@@ -1430,7 +1441,7 @@ struct SgMeta { int64_t base; int nvalid; int pad; };
 
 __global__ void __launch_bounds__(512, 1)
 k_apply_blocks_seg_mma(const double2* __restrict__ in, double2* __restrict__ out, const SegGeom g,
-                       const SegSb S) {
+                       const SegSb S, const int kSgFib) {
   using V = double2;
   if (!S.flags[0]) return;
   extern __shared__ __align__(16) unsigned char s_raw[];
@@ -1493,8 +1504,9 @@ k_apply_blocks_seg_mma(const double2* __restrict__ in, double2* __restrict__ out
     cp_async_wait<1>();
     __syncthreads();
     const SgMeta meta = s_meta[cur];
-    for (int it = warp; it < 2 * nsb; it += nwarps) {
-      const int sb = it >> 1, h = it & 1;
+    const int halves = kSgFib >> 5;  // groups of 32 fibers
+    for (int it = warp; it < halves * nsb; it += nwarps) {
+      const int sb = it / halves, h = it - sb * halves;
       const int n = s_n[sb];
       const V w0 = s_w[sb * 64 + gid * 8 + (tig ^ fsw)], w1 = s_w[sb * 64 + gid * 8 + ((4 + tig) ^ fsw)];
       const int p0 = s_pos[sb * 8 + tig] ^ sf, p1 = s_pos[sb * 8 + 4 + tig] ^ sf;
@@ -1562,6 +1574,7 @@ static int enqueue_seg_mma(const void* in, void* out, const SegGeom& g, BlockDes
   k_seg_sb_build<<<1, 128, 0, s>>>(d->arr, S);
   PW_LAUNCHED();
   const int tp = ((int)g.t + 7) & ~7;
+  const int kSgFib = seg_mma_fibers((int)g.t);
   const size_t smem = sizeof(double2) * (size_t)(kSgMaxSb * 64 + 2 * kSgFib * tp) + sizeof(SgMeta) * 2 +
                       sizeof(int) * (2 * kSgMaxSb * 8 + kSgMaxSb);
   static bool attr_set = false;
@@ -1569,14 +1582,14 @@ static int enqueue_seg_mma(const void* in, void* out, const SegGeom& g, BlockDes
     PW_CUDA(cudaFuncSetAttribute(k_apply_blocks_seg_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  int nwarps = 2 * (((int)g.t + 7) / 8);
+  int nwarps = (kSgFib / 32) * (((int)g.t + 7) / 8);  // one warp per (32 fibers, 8 indices)
   if (nwarps < 4) nwarps = 4;
   if (nwarps > 16) nwarps = 16;
   const int ctas = (smem + 1024) * 2 <= 227 * 1024 ? 2 : 1;
   const uint64_t units = g.outer.nfib * ((g.M + kSgFib - 1) / kSgFib);
   uint64_t grid = (uint64_t)kNumSMs * ctas;
   if (grid > units) grid = units;
-  k_apply_blocks_seg_mma<<<(unsigned)grid, nwarps * 32, smem, s>>>((const double2*)in, (double2*)out, g, S);
+  k_apply_blocks_seg_mma<<<(unsigned)grid, nwarps * 32, smem, s>>>((const double2*)in, (double2*)out, g, S, kSgFib);
   PW_LAUNCHED();
   *mma_taken = S.flags;
   return PW_OK;

@@ -32,7 +32,9 @@ struct BlockDesc {
   BlockArrays arr;
   BlockDescHeader* hdr = nullptr;
   bool staged = false;  // launch_blocks_seg was used: the flag to honour is seg_handled
+  const int* mma_flag = nullptr;  // staged, tensor-core variant only: its own "taken" flag
   const int* skip_flag() const {
+    if (mma_flag) return mma_flag;
     return hdr ? (staged ? &hdr->seg_handled : &hdr->usable) : nullptr;
   }
 };
@@ -149,9 +151,11 @@ int launch_blocks(const void* in, void* out, const void* op, const Plan& plan, i
 // fiber per lane), and streams the rows back.  Runs when the analysis reports
 // usable && inplace_safe (desc->hdr->seg_handled); the fallback must take that as skip flag.
 // Returns PW_ERR_UNSUPPORTED when the geometry does not fit.
+// `mma_only`: enqueue only the tensor-core variant (complex128, t <= 64; used for t <= 8, where
+// the register kernels are the fallback); PW_ERR_UNSUPPORTED when it does not apply.
 int launch_blocks_seg(const void* in, void* out, const void* op, const int64_t* axes, int naxes,
                       const int* targets, int nt, int dtype, bool conj_op, BlockDesc* desc,
-                      cudaStream_t stream);
+                      cudaStream_t stream, bool mma_only = false);
 
 // Two-sided single pass rho' = U rho U^dagger for a dense d <= 8 or block-structured operator
 // (see pw_blocks.cu).  `fm` enumerates the fibers of the doubled tensor (every axis that is
