@@ -14,6 +14,9 @@ WANT = {
     "launch__registers_per_thread": "registers",
     "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_pct",
+    "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active": "dmma_pipe_pct",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed": "smem_wavefront_pct",
+    "smsp__inst_executed.sum": "warp_instructions",
 }
 UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1}
 
