@@ -832,16 +832,20 @@ __device__ __forceinline__ void two_sided_mma_body(const double2* __restrict__ i
   const V* wtab = (const V*)T.sb_w;
 
   // chunk index fastest: CTAs that run side by side work on adjacent memory
+  // (32-bit arithmetic: the host guarantees units < 2^32)
+  const uint32_t chunks32 = (uint32_t)chunks, nsb2 = nsb * nsb;
   auto decode = [&](uint64_t u, uint32_t& K, uint32_t& L, uint64_t& c) {
     if (!MULTI) { K = 0; L = 0; c = u; return; }
-    uint32_t p;
+    const uint32_t u32 = (uint32_t)u;
+    uint32_t p, c32;
     if (order == 0) {
-      p = (uint32_t)(u / chunks);
-      c = u - (uint64_t)p * chunks;
+      p = u32 / chunks32;
+      c32 = u32 - p * chunks32;
     } else {  // pair index fastest: consecutive units sweep one chunk's whole operator block
-      c = u / (nsb * nsb);
-      p = (uint32_t)(u - c * (nsb * nsb));
+      c32 = u32 / nsb2;
+      p = u32 - c32 * nsb2;
     }
+    c = c32;
     K = p / nsb;
     L = p - K * nsb;
   };
@@ -860,12 +864,20 @@ __device__ __forceinline__ void two_sided_mma_body(const double2* __restrict__ i
         if (base >= 0) {
           const int64_t* ro = rin + K * 8;
           const int64_t* co = cin + L * 8;
-          int a = 0, b = warp;
-          while (b >= nL) { b -= nL; ++a; }
-          for (; a < nK;) {
-            cp_async16(tile + (a * nL + b) * 32 + (lane ^ (2 * (a & 3))), in + base + ro[a] + co[b]);
-            b += kTsWarps;
+          if (nL == kTsWarps) {
+            // full super-block: warp w copies column w of every row
+            const V* src = in + base + co[warp];
+            V* dst = tile + warp * 32;
+            for (int a = 0; a < nK; ++a)
+              cp_async16(dst + a * (kTsWarps * 32) + (lane ^ (2 * (a & 3))), src + ro[a]);
+          } else {
+            int a = 0, b = warp;
             while (b >= nL) { b -= nL; ++a; }
+            for (; a < nK;) {
+              cp_async16(tile + (a * nL + b) * 32 + (lane ^ (2 * (a & 3))), in + base + ro[a] + co[b]);
+              b += kTsWarps;
+              while (b >= nL) { b -= nL; ++a; }
+            }
           }
         }
       } else {
@@ -1283,7 +1295,8 @@ static int launch_two_sided_t(const V* rho, V* out, const V* op, const FiberMap&
   T.sb_blk = (int2*)(sbb + b_sbn);
   T.sb_off = (int64_t*)(sbb + b_sbn + b_sbblk);
   T.sb_w = sbb + b_sbn + b_sbblk + b_sboff;
-  const bool mma_ok = sizeof(V) == 16 && options().ts_mma.load(std::memory_order_relaxed);
+  // (the tensor-core kernels index their units with 32 bits)
+  const bool mma_ok = sizeof(V) == 16 && options().ts_mma.load(std::memory_order_relaxed) && fm.nfib < (1ull << 28);
   if (inner && !mma_ok) return PW_ERR_UNSUPPORTED;
   k_ts_build<V><<<1, 256, 0, s>>>(ts->L, ts->R, other, T, kTsValCap, mma_ok ? 1 : 0, inner);
   PW_LAUNCHED();
