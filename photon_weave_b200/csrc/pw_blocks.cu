@@ -1464,9 +1464,11 @@ k_apply_blocks_seg_mma(const double2* __restrict__ in, double2* __restrict__ out
   SgMeta* s_meta = (SgMeta*)(tile0 + 2 * kSgFib * tp);  // [2]
   int* s_pos = (int*)(s_meta + 2);                      // [2][kSgMaxSb][8]
   int* s_n = s_pos + 2 * kSgMaxSb * 8;                  // [kSgMaxSb]
+  __shared__ int64_t s_seg[64];                         // segment offsets
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int gid = lane >> 2, tig = lane & 3;
   const int nsb = S.flags[1];
+  if (threadIdx.x < 64) s_seg[threadIdx.x] = threadIdx.x < g.nseg ? g.seg_off[threadIdx.x] : 0;
   for (int i = threadIdx.x; i < kSgMaxSb * 64; i += blockDim.x) s_w[i] = S.w[i];
   for (int i = threadIdx.x; i < 2 * kSgMaxSb * 8; i += blockDim.x) s_pos[i] = S.pos[i];
   if (threadIdx.x < kSgMaxSb) s_n[threadIdx.x] = threadIdx.x < nsb ? S.sb_n[threadIdx.x] : 0;
@@ -1492,12 +1494,24 @@ k_apply_blocks_seg_mma(const double2* __restrict__ in, double2* __restrict__ out
       if (threadIdx.x == 0) { s_meta[buf].base = base; s_meta[buf].nvalid = nvalid; }
       V* tile = tile0 + (size_t)buf * kSgFib * tp;
       const int rowlen = nvalid * (int)lseg;
-      for (uint32_t sg = 0; sg < g.nseg; ++sg) {
-        const V* src = in + base + g.seg_off[sg];
+      if (g.nseg >= 4) {
+        // many short segments: the (fiber, position) arithmetic once per element column
         for (int e = threadIdx.x; e < rowlen; e += blockDim.x) {
           const int f = (int)__umulhi((uint32_t)e, inv_l);
-          const int p = (int)(sg * lseg) + (e - f * (int)lseg);
-          cp_async16(tile + f * tp + (p ^ sigma(f)), src + e);
+          const int jr = e - f * (int)lseg, sf_ = sigma(f);
+          V* dst = tile + f * tp;
+          const V* src = in + base + e;
+          for (uint32_t sg = 0; sg < g.nseg; ++sg)
+            cp_async16(dst + (((int)(sg * lseg) + jr) ^ sf_), src + s_seg[sg]);
+        }
+      } else {
+        for (uint32_t sg = 0; sg < g.nseg; ++sg) {
+          const V* src = in + base + s_seg[sg];
+          for (int e = threadIdx.x; e < rowlen; e += blockDim.x) {
+            const int f = (int)__umulhi((uint32_t)e, inv_l);
+            const int p = (int)(sg * lseg) + (e - f * (int)lseg);
+            cp_async16(tile + f * tp + (p ^ sigma(f)), src + e);
+          }
         }
       }
     }
@@ -1553,12 +1567,23 @@ k_apply_blocks_seg_mma(const double2* __restrict__ in, double2* __restrict__ out
     __syncthreads();
     {
       const int rowlen = meta.nvalid * (int)lseg;
-      for (uint32_t sg = 0; sg < g.nseg; ++sg) {
-        V* dst = out + meta.base + g.seg_off[sg];
+      if (g.nseg >= 4) {
         for (int e = threadIdx.x; e < rowlen; e += blockDim.x) {
           const int f = (int)__umulhi((uint32_t)e, inv_l);
-          const int p = (int)(sg * lseg) + (e - f * (int)lseg);
-          __stcg(dst + e, tile[f * tp + (p ^ sigma(f))]);
+          const int jr = e - f * (int)lseg, sf_ = sigma(f);
+          const V* src = tile + f * tp;
+          V* dst = out + meta.base + e;
+          for (uint32_t sg = 0; sg < g.nseg; ++sg)
+            __stcg(dst + s_seg[sg], src[((int)(sg * lseg) + jr) ^ sf_]);
+        }
+      } else {
+        for (uint32_t sg = 0; sg < g.nseg; ++sg) {
+          V* dst = out + meta.base + s_seg[sg];
+          for (int e = threadIdx.x; e < rowlen; e += blockDim.x) {
+            const int f = (int)__umulhi((uint32_t)e, inv_l);
+            const int p = (int)(sg * lseg) + (e - f * (int)lseg);
+            __stcg(dst + e, tile[f * tp + (p ^ sigma(f))]);
+          }
         }
       }
     }
