@@ -531,7 +531,7 @@ constexpr int kTsSlots = 64;                 // tile = 64 slots x 32 lanes
 constexpr uint32_t kTsValCap = 8 * 1024;     // per side: block values (BS d=8: 344 x 16 B)
 
 constexpr int kTsMaxSb = 16;                 // tensor-core kernel: super-blocks per side
-constexpr int kTwMaxSb = 8;                  // wide-tile variant (innermost column targets)
+constexpr int kTwMaxSb = 8;                  // row-tile variant (innermost column targets)
 
 struct TsFlags { int handled; int any; int ngroups; int use_mma; int nsb; };
 
@@ -602,7 +602,7 @@ k_ts_build(const BlockArrays L, const BlockArrays R, const int* __restrict__ oth
     }
     // innermost (contiguous) column target: only the tensor-core kernel has the transposing
     // load, and only for ONE dense block whose columns are the contiguous run itself
-    // (inner bit 1: the column targets ARE the innermost run -> wide-tile kernel; bit 2: one
+    // (inner bit 1: the column targets ARE the innermost run -> row-tile kernel; bit 2: one
     //  5..8-level column target with whole chunks of 32 fibers next to it -> 32-fiber tiles)
     if (inner) {
       if (mma && hl->nblocks == 1 && (inner & 2)) mma = 1;
@@ -1012,46 +1012,53 @@ k_two_sided_mma(const double2* __restrict__ in, double2* __restrict__ out, const
 }
 
 
-// ---- wide tiles: the column targets are the innermost (contiguous) run -----------------------
-// With the column targets innermost (beam splitter on the last two modes), the column index
-// pairs of a super-block are scattered 16-byte pieces inside every run of t elements; the only
-// coalesced unit is the whole run.  A tile is therefore (row super-block K: <= 8 rows) x (F
-// fibers) x (ALL t column indices), F t ~ 512 elements per row (64 KB per tile, two buffers, one
-// 16-warp CTA per SM).  Row r of the tile is a contiguous piece of memory and keeps its order
-// (fiber-major, sigma-permuted inside 8-element groups as above).  Stage 1 works on the t columns
-// (operand: row block K), stage 2 on (row, column super-block L) and gathers its <= 8 inputs by
-// their position in the run.
-constexpr int kTwWarps = 16;
-constexpr int kTwRow = 512;   // elements per tile row
-constexpr int kTwBufs = 3;    // tile buffers (loads run two tiles ahead)
-
 struct TwMeta { int64_t base0; int K; int nvalid; };
 
-__global__ void __launch_bounds__(kTwWarps * 32, 1)
-k_two_sided_mma_wide(const double2* __restrict__ in, double2* __restrict__ out, const FiberMap fm,
+// ---- row tiles: the column targets are the innermost (contiguous) run ---------------------------
+// With the column targets innermost (beam splitter on the last two modes), the column index
+// pairs of a super-block are scattered 16-byte pieces inside every run of t elements; the only
+// coalesced unit is the whole run, so a tile holds ALL t positions of its fibers.
+// The free (N) dimension of an MMA is any set of eight independent columns.  Stage 1 (row side)
+// mixes the rows of the tile, so eight CONSECUTIVE COLUMN POSITIONS of one fiber are as good as
+// eight fibers; stage 2 (column side) mixes positions inside a row, so the EIGHT ROWS of one fiber
+// are its free dimension.  A tile therefore needs neither 8 nor 32 fibers: (8 rows) x (F fibers
+// x all t positions) = 2048 elements = 32 KB, three buffers and two decoupled 8-warp CTAs per SM
+// (the shape of k_two_sided_mma), instead of one lock-stepped 16-warp CTA with 64 KB tiles.
+//   element (row a, fiber f, position j)  at  a * 256 + f * tp + (j ^ sigma(a)),
+//   sigma(a) = 2 (a & 3) ^ (a & 4)
+// column side (first, in place): B fragment (k = position cin[tig] / cin[4 + tig], n = row pi(gid)),
+//   C fragment (position cout[gid], rows pi(2 tig) = tig and pi(2 tig + 1) = tig + 4),
+//   pi(g) = (g >> 1) + 4 (g & 1);
+// row side (second, streamed to HBM from the fragments -- the sides commute): B fragment (k = row
+//   tig / 4 + tig, n = position 8 q + gid), C fragment (row gid, positions 8 q + 2 tig, + 1: one
+//   full sector per lane, one full 128-byte line per quarter warp);
+// all three shared-memory access patterns are bank-conflict free for positions that are
+// consecutive modulo 8 (beam-splitter sectors: 7 k + n), the copies stay inside whole 128-byte rows.
+constexpr int kTnWarps = 8;
+constexpr int kTnRow = 256;   // elements per tile row (F fibers x padded t)
+constexpr int kTnBufs = 3;
+
+__global__ void __launch_bounds__(kTnWarps * 32, 2)
+k_two_sided_mma_rows(const double2* __restrict__ in, double2* __restrict__ out, const FiberMap fm,
                      const TsTables T, const int t) {
   using V = double2;
   if (!T.flags->handled || T.flags->use_mma != 2) return;
   extern __shared__ __align__(16) unsigned char s_raw[];
-  V* tile0 = (V*)s_raw;                                       // [kTwBufs][8][kTwRow]
-  V* s_w = tile0 + kTwBufs * 8 * kTwRow;                      // [2][kTwMaxSb][64]
-  int64_t* s_roff = (int64_t*)(s_w + 2 * kTwMaxSb * 64);      // [2][kTwMaxSb][8] row offsets: in, out
-  TwMeta* s_meta = (TwMeta*)(s_roff + 2 * kTwMaxSb * 8);      // [kTwBufs]
-  int* s_cpos = (int*)(s_meta + kTwBufs);                     // [2][kTwMaxSb][8] column positions: in, out
+  V* tile0 = (V*)s_raw;                                       // [kTnBufs][8][kTnRow]
+  V* s_w = tile0 + kTnBufs * 8 * kTnRow;                      // [kTwMaxSb][64] column-side operands (swizzled)
+  int64_t* s_roff = (int64_t*)(s_w + kTwMaxSb * 64);          // [2][kTwMaxSb][8] row offsets: in, out
+  TwMeta* s_meta = (TwMeta*)(s_roff + 2 * kTwMaxSb * 8);      // [kTnBufs]
+  int* s_cpos = (int*)(s_meta + kTnBufs);                     // [2][kTwMaxSb][8] column positions: in, out
   int* s_n = s_cpos + 2 * kTwMaxSb * 8;                       // [kTwMaxSb]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gid = lane >> 2, tig = lane & 3;
   const int nsb = T.flags->nsb;
-  // operand tables; column c of row r sits at r * 8 + (c ^ 4 (r & 1)): the fragment loads of a
-  // quarter warp (two rows x four columns) then hit eight different 16-byte bank groups
-  for (int i = threadIdx.x; i < 2 * kTwMaxSb * 64; i += blockDim.x) {
-    const int side = i / (kTwMaxSb * 64), r = i - side * (kTwMaxSb * 64);
-    s_w[i ^ (((r >> 3) & 1) << 2)] = ((const V*)T.sb_w)[side * kTsMaxSb * 64 + r];
-  }
+  for (int i = threadIdx.x; i < kTwMaxSb * 64; i += blockDim.x)
+    s_w[i ^ (((i >> 3) & 1) << 2)] = ((const V*)T.sb_w)[kTsMaxSb * 64 + i];
   for (int i = threadIdx.x; i < 2 * kTwMaxSb * 8; i += blockDim.x) {
     const int which = i / (kTwMaxSb * 8), r = i - which * (kTwMaxSb * 8);
-    s_roff[i] = T.sb_off[(2 * which) * kTsMaxSb * 8 + r];            // tables 0 (row in), 2 (row out)
-    s_cpos[i] = (int)T.sb_off[(2 * which + 1) * kTsMaxSb * 8 + r];   // tables 1 (column in), 3 (column out)
+    s_roff[i] = T.sb_off[(2 * which) * kTsMaxSb * 8 + r];
+    s_cpos[i] = (int)T.sb_off[(2 * which + 1) * kTsMaxSb * 8 + r];
   }
   if (threadIdx.x < kTwMaxSb) s_n[threadIdx.x] = threadIdx.x < nsb ? T.sb_n[threadIdx.x] : 0;
   __syncthreads();
@@ -1059,22 +1066,20 @@ k_two_sided_mma_wide(const double2* __restrict__ in, double2* __restrict__ out, 
   const int64_t* rout = s_roff + kTwMaxSb * 8;
   const int* cin = s_cpos;
   const int* cout = s_cpos + kTwMaxSb * 8;
-  const int tp = (t + 7) & ~7;                 // padded run (the sigma permutation stays inside 8-groups)
-  const int F = (kTwRow / tp) & ~7;            // fibers per tile: 64, 32, 16 or 8
-  const int nq = F >> 3, qsh = 31 - __clz(nq); // fiber octets per tile (a power of two)
-  const uint32_t inv_t = 0xffffffffu / (uint32_t)t + 1;      // r / t for r < 2^16
-  const uint32_t inv_nsb = 0xffffu / (uint32_t)nsb + 1;      // x / nsb for x < 2^8 (16-bit shift)
-  const uint32_t gl = (uint32_t)fm.gsize[fm.ng - 1];         // fibers per run of runs (stride t)
+  const int tp = (t + 7) & ~7;
+  const int F = kTnRow / tp;                   // fibers per tile (t <= 64: at least 4)
+  const int nq = tp >> 3;                      // position octets per fiber
+  const uint32_t inv_t = 0xffffffffu / (uint32_t)t + 1;
+  const uint32_t inv_nq = 0xffffu / (uint32_t)nq + 1, inv_nsb = 0xffffu / (uint32_t)nsb + 1;
+  const uint32_t gl = (uint32_t)fm.gsize[fm.ng - 1];
   const uint32_t cpr = (gl + F - 1) / F;
-  const uint32_t chunks = (uint32_t)(fm.nfib / gl) * cpr;    // (host: chunks * nsb < 2^32)
+  const uint32_t chunks = (uint32_t)(fm.nfib / gl) * cpr;
   const uint32_t units = chunks * (uint32_t)nsb;
+  const V* wl_tab = (const V*)T.sb_w;          // row-side operands (global, L1 resident)
 
-  // chunk fastest, K slowest.  Loads are issued in two steps so that the rows can be spread
-  // over the stage 2 loop: prepare (decode the unit, publish its meta data) and rows [a0, a1).
-  struct Pending { const V* src; V* dst; const int64_t* ro; int nK, rowlen; };
-  auto issue_prepare = [&](uint32_t u, int buf) {
-    Pending p;
-    p.nK = 0; p.rowlen = 0; p.src = in; p.dst = tile0; p.ro = rin;
+  auto sig = [](int a) { return (2 * (a & 3)) ^ (a & 4); };
+
+  auto issue = [&](uint32_t u, int buf) {
     if (u < units) {
       const uint32_t K = u / chunks, c = u - K * chunks;
       const uint32_t o = c / cpr, w = c - o * cpr;
@@ -1082,37 +1087,17 @@ k_two_sided_mma_wide(const double2* __restrict__ in, double2* __restrict__ out, 
       const int nvalid = (gl - f0) < (uint32_t)F ? (int)(gl - f0) : F;
       const int64_t base0 = fm.base((uint64_t)o * gl + f0);
       if (threadIdx.x == 0) { s_meta[buf].base0 = base0; s_meta[buf].K = (int)K; s_meta[buf].nvalid = nvalid; }
-      p.nK = s_n[K];
-      p.rowlen = nvalid * t;
-      p.src = in + base0;
-      p.dst = tile0 + (size_t)buf * 8 * kTwRow;
-      p.ro = rin + K * 8;
+      const int nK = s_n[K];
+      V* tile = tile0 + (size_t)buf * 8 * kTnRow;
+      const int64_t* ro = rin + K * 8;
+      for (int r = threadIdx.x; r < nvalid * t; r += kTnWarps * 32) {
+        const int f = (int)__umulhi((uint32_t)r, inv_t), j = r - f * t;
+        V* dst = tile + f * tp;
+        const V* src = in + base0 + r;
+        for (int a = 0; a < nK; ++a) cp_async16(dst + a * kTnRow + (j ^ sig(a)), src + ro[a]);
+      }
     }
-    return p;
-  };
-  auto issue_rows = [&](const Pending& p, int a0, int a1) {
-    if (a1 > p.nK) a1 = p.nK;
-    for (int r = threadIdx.x; r < p.rowlen; r += kTwWarps * 32) {
-      const int f = (int)__umulhi((uint32_t)r, inv_t), j = r - f * t;
-      V* dst = p.dst + f * tp;
-      const int jj = j ^ ((f & 1) << 2) ^ (f & 6);
-      const V* src = p.src + r;
-      for (int a = a0; a < a1; ++a) cp_async16(dst + a * kTwRow + (jj ^ (a & 3)), src + p.ro[a]);
-    }
-  };
-  // copy-out of rows [i0, i1) of a finished tile: whole rows, coalesced
-  auto copy_rows = [&](const V* tile, const TwMeta& m, int i0, int i1) {
-    const int nK = s_n[m.K];
-    if (i1 > nK) i1 = nK;
-    const int rowlen = m.nvalid * t;
-    const int64_t* ro = rout + m.K * 8;
-    for (int r = threadIdx.x; r < rowlen; r += kTwWarps * 32) {
-      const int f = (int)__umulhi((uint32_t)r, inv_t), j = r - f * t;
-      const V* src = tile + f * tp;
-      const int jj = j ^ ((f & 1) << 2) ^ (f & 6);
-      V* dst = out + m.base0 + r;
-      for (int i = i0; i < i1; ++i) __stcg(dst + ro[i], src[i * kTwRow + (jj ^ (i & 3))]);
-    }
+    cp_async_commit();
   };
 
   auto mma_item = [&](const V w0, const V w1, const V x0, const V x1, V& y0, V& y1) {
@@ -1129,140 +1114,95 @@ k_two_sided_mma_wide(const double2* __restrict__ in, double2* __restrict__ out, 
     y1 = make_double2(re1, im1);
   };
 
-  // lane constants of the sigma-permuted positions (see ts_sigma): reads take fiber gid of an
-  // octet, writes take fibers 2 tig and 2 tig + 1
-  const int sf = ((gid & 1) << 2) ^ (gid & 6);
-  const int rd1 = tig * kTwRow + gid * tp, s1 = sf ^ tig;             // stage 1 read: rows tig, 4 + tig
-  const int wr1 = gid * kTwRow + 2 * tig * tp, s2 = (2 * tig) ^ (gid & 3);  // stage 1 write: row gid
-  const int fsw = (gid & 1) << 2;  // operand table swizzle
+  const int fsw = (gid & 1) << 2;
   const V zero = make_double2(0.0, 0.0);
+  // row-side lane constants: read rows tig / 4 + tig at position octet + gid
+  const int rd1a = tig * kTnRow + (gid ^ sig(tig)), rd1b = (4 + tig) * kTnRow + (gid ^ sig(4 + tig));
+  // column-side lane constants: read row pi(gid), write rows tig and tig + 4
+  const int prow = (gid >> 1) + 4 * (gid & 1);
+  const int rd2 = prow * kTnRow, sg2 = sig(prow);
+  const int wr2a = tig * kTnRow, wr2b = (4 + tig) * kTnRow, sa = sig(tig), sb4 = sig(4 + tig);
 
-  // Two barriers per tile: S1 between the stages, S2 after stage 2.  The memory work is
-  // interleaved with the tensor-core work of the SAME warps (all warps of the CTA move in lock
-  // step, so separate phases would leave the DMMA pipe idle while the LSU works and vice versa):
-  // the copy-out of tile n - 1 is spread over the stage 1 loop of tile n, the loads of tile n + 2
-  // (into the buffer of tile n - 1, free after S1) over its stage 2 loop.
   const uint32_t g = gridDim.x;
   uint32_t u = blockIdx.x;
   int cur = 0;
-  {
-    const Pending p0 = issue_prepare(u, 0);
-    issue_rows(p0, 0, 8);
-    cp_async_commit();
-    const Pending p1 = issue_prepare(u + g, 1);
-    issue_rows(p1, 0, 8);
-    cp_async_commit();
-  }
-  cp_async_wait<1>();
-  __syncthreads();
-  TwMeta prev;
-  prev.base0 = 0; prev.K = 0; prev.nvalid = 0;  // nothing to copy out before the first tile
-  int Lc = -1, nLc = 0, c0 = 0, c1 = 0, cw = 0;  // cached column super-block of stage 2
-  V r0 = zero, r1 = zero;
-  const V* prev_tile = tile0;
+  issue(u, 0);
+  issue(u + g, 1);
   for (; u < units; u += g) {
-    V* tile = tile0 + (size_t)cur * 8 * kTwRow;
+    V* tile = tile0 + (size_t)cur * 8 * kTnRow;
+    cp_async_wait<1>();
+    __syncthreads();  // A: tile `cur` is resident; the previous tile has been copied out
+    issue(u + 2 * g, cur == 0 ? kTnBufs - 1 : cur - 1);
     const TwMeta meta = s_meta[cur];
     const int K = meta.K, nK = s_n[K];
-    const V l0 = s_w[K * 64 + gid * 8 + (tig ^ fsw)], l1 = s_w[K * 64 + gid * 8 + ((4 + tig) ^ fsw)];
-    // stage 1: (column j, fiber octet q), in place; two items per step (independent DMMA chains)
-    const int n1 = t << qsh;
-    int crow = 0;
-    for (int it = warp; it < n1; it += 2 * kTwWarps) {
-      const int itb = it + kTwWarps;
-      const bool two = itb < n1;
-      const int ja = it >> qsh, qa = (it & (nq - 1)) * 8 * tp;
-      const int jb = itb >> qsh, qb = (itb & (nq - 1)) * 8 * tp;
-      V xa0 = zero, xa1 = zero, xb0 = zero, xb1 = zero, ya0, ya1, yb0, yb1;
-      if (tig < nK) {
-        xa0 = tile[rd1 + qa + (ja ^ s1)];
-        if (two) xb0 = tile[rd1 + qb + (jb ^ s1)];
+    const V l0 = __ldg(wl_tab + K * 64 + gid * 8 + tig), l1 = __ldg(wl_tab + K * 64 + gid * 8 + 4 + tig);
+    // The two sides commute: the COLUMN side runs first, in place, so that the row side can
+    // stream its accumulators straight to HBM -- a lane owns positions 8 q + 2 tig and + 1 of one
+    // output row (one full 32-byte sector, a quarter warp one full 128-byte line).  Four items per
+    // step: eight independent DMMA chains per warp.
+    constexpr int kB = 4;
+    // stage 1 (column side): (fiber f, column super-block L), positions mixed inside every row
+    const int n2 = F * nsb;
+    for (int it0 = warp; it0 < n2; it0 += kB * kTnWarps) {
+      V* fib[kB];
+      int nLb[kB], posb[kB];
+      V x0[kB], x1[kB], y0[kB], y1[kB], r0[kB], r1[kB];
+#pragma unroll
+      for (int b = 0; b < kB; ++b) {
+        const int it = it0 + b * kTnWarps;
+        const int itc = it < n2 ? it : it0;
+        const int f = (int)(((uint32_t)itc * inv_nsb) >> 16), L = itc - f * nsb;
+        nLb[b] = it < n2 ? s_n[L] : 0;
+        r0[b] = s_w[L * 64 + gid * 8 + (tig ^ fsw)];
+        r1[b] = s_w[L * 64 + gid * 8 + ((4 + tig) ^ fsw)];
+        fib[b] = tile + f * tp;
+        posb[b] = cout[L * 8 + gid];
+        x0[b] = tig < nLb[b] ? fib[b][rd2 + (cin[L * 8 + tig] ^ sg2)] : zero;
+        x1[b] = 4 + tig < nLb[b] ? fib[b][rd2 + (cin[L * 8 + 4 + tig] ^ sg2)] : zero;
       }
-      if (4 + tig < nK) {
-        xa1 = tile[rd1 + 4 * kTwRow + qa + (ja ^ s1)];
-        if (two) xb1 = tile[rd1 + 4 * kTwRow + qb + (jb ^ s1)];
-      }
-      mma_item(l0, l1, xa0, xa1, ya0, ya1);
-      mma_item(l0, l1, xb0, xb1, yb0, yb1);
-      copy_rows(prev_tile, prev, crow, crow + 4);  // while the tensor cores work
-      crow += 4;
+#pragma unroll
+      for (int b = 0; b < kB; ++b) mma_item(r0[b], r1[b], x0[b], x1[b], y0[b], y1[b]);
       __syncwarp();
+#pragma unroll
+      for (int b = 0; b < kB; ++b)
+        if (gid < nLb[b]) {
+          fib[b][wr2a + (posb[b] ^ sa)] = y0[b];
+          fib[b][wr2b + (posb[b] ^ sb4)] = y1[b];
+        }
+    }
+    __syncthreads();  // B
+    // stage 2 (row side): (fiber f, position octet q), rows mixed, streamed to HBM
+    const int n1 = F * nq;
+    V* orow = out + meta.base0 + rout[K * 8 + (gid < nK ? gid : 0)] + 2 * tig;
+    for (int it0 = warp; it0 < n1; it0 += kB * kTnWarps) {
+      int fq[kB];
+      V x0[kB], x1[kB], y0[kB], y1[kB];
+#pragma unroll
+      for (int b = 0; b < kB; ++b) {
+        const int it = it0 + b * kTnWarps;
+        const int itc = it < n1 ? it : it0;
+        const int f = (int)(((uint32_t)itc * inv_nq) >> 16), q = itc - f * nq;
+        const V* col = tile + f * tp + 8 * q;
+        fq[b] = it < n1 ? (f << 8) | q : -1;
+        x0[b] = (tig < nK && it < n1) ? col[rd1a] : zero;
+        x1[b] = (4 + tig < nK && it < n1) ? col[rd1b] : zero;
+      }
+#pragma unroll
+      for (int b = 0; b < kB; ++b) mma_item(l0, l1, x0[b], x1[b], y0[b], y1[b]);
       if (gid < nK) {
-        tile[wr1 + qa + (ja ^ s2)] = ya0;
-        tile[wr1 + qa + tp + (ja ^ s2 ^ 4)] = ya1;
-        if (two) {
-          tile[wr1 + qb + (jb ^ s2)] = yb0;
-          tile[wr1 + qb + tp + (jb ^ s2 ^ 4)] = yb1;
+#pragma unroll
+        for (int b = 0; b < kB; ++b) {
+          if (fq[b] < 0) continue;
+          const int f = fq[b] >> 8, j = 8 * (fq[b] & 255) + 2 * tig;
+          if (f >= meta.nvalid) continue;
+          V* dst = orow + (int64_t)f * t + 8 * (fq[b] & 255);
+          if (j < t) __stcg(dst, y0[b]);
+          if (j + 1 < t) __stcg(dst + 1, y1[b]);
         }
       }
     }
-    copy_rows(prev_tile, prev, crow, 8);
-    __syncthreads();  // S1: stage 1 done; the previous tile is copied out, its buffer is free
-    const Pending pend = issue_prepare(u + 2 * g, cur == 0 ? kTwBufs - 1 : cur - 1);
-    int lrow = 0;
-    // stage 2: (row i, column super-block L, fiber octet q), in place as well (the blocks'
-    // output positions are their input positions: hdr->inplace_safe) -- a scattered 16-byte
-    // store per output costs one L1 line transaction each
-    // (the column super-block of a warp's items rarely changes -- never for nsb = 8, 4, 2, 1 with
-    //  one fiber octet -- so its operand fragments and positions stay in registers)
-    const int n2 = (nK * nsb) << qsh;
-    for (int it = warp; it < n2; it += 2 * kTwWarps) {
-      const int itb = it + kTwWarps;
-      const bool two = itb < n2;
-      const int qa = (it & (nq - 1)) * 8 * tp, ra = it >> qsh;
-      const int ia = (int)(((uint32_t)ra * inv_nsb) >> 16), La = ra - ia * nsb;
-      const int qb = (itb & (nq - 1)) * 8 * tp, rb = itb >> qsh;
-      const int ib = (int)(((uint32_t)rb * inv_nsb) >> 16), Lb = two ? rb - ib * nsb : La;
-      if (La != Lc) {
-        Lc = La;
-        nLc = s_n[La];
-        c0 = cin[La * 8 + tig]; c1 = cin[La * 8 + 4 + tig]; cw = cout[La * 8 + gid] ^ (2 * tig);
-        r0 = s_w[(kTwMaxSb + La) * 64 + gid * 8 + (tig ^ fsw)];
-        r1 = s_w[(kTwMaxSb + La) * 64 + gid * 8 + ((4 + tig) ^ fsw)];
-      }
-      V* rowa = tile + ia * kTwRow + qa;
-      V xa0 = zero, xa1 = zero, ya0, ya1;
-      if (tig < nLc) xa0 = rowa[gid * tp + (c0 ^ sf ^ (ia & 3))];
-      if (4 + tig < nLc) xa1 = rowa[gid * tp + (c1 ^ sf ^ (ia & 3))];
-      mma_item(r0, r1, xa0, xa1, ya0, ya1);
-      const int nLa = nLc, cwa = cw;
-      if (Lb != Lc) {
-        Lc = Lb;
-        nLc = s_n[Lb];
-        c0 = cin[Lb * 8 + tig]; c1 = cin[Lb * 8 + 4 + tig]; cw = cout[Lb * 8 + gid] ^ (2 * tig);
-        r0 = s_w[(kTwMaxSb + Lb) * 64 + gid * 8 + (tig ^ fsw)];
-        r1 = s_w[(kTwMaxSb + Lb) * 64 + gid * 8 + ((4 + tig) ^ fsw)];
-      }
-      V* rowb = tile + ib * kTwRow + qb;
-      V xb0 = zero, xb1 = zero, yb0, yb1;
-      if (two) {
-        if (tig < nLc) xb0 = rowb[gid * tp + (c0 ^ sf ^ (ib & 3))];
-        if (4 + tig < nLc) xb1 = rowb[gid * tp + (c1 ^ sf ^ (ib & 3))];
-      }
-      mma_item(r0, r1, xb0, xb1, yb0, yb1);
-      issue_rows(pend, lrow, lrow + 4);  // while the tensor cores work
-      lrow += 4;
-      __syncwarp();
-      if (gid < nLa) {
-        const int pos = cwa ^ (ia & 3);
-        rowa[2 * tig * tp + pos] = ya0;
-        rowa[(2 * tig + 1) * tp + (pos ^ 4)] = ya1;
-      }
-      if (two && gid < nLc) {
-        const int pos = cw ^ (ib & 3);
-        rowb[2 * tig * tp + pos] = yb0;
-        rowb[(2 * tig + 1) * tp + (pos ^ 4)] = yb1;
-      }
-    }
-    issue_rows(pend, lrow, 8);
-    cp_async_commit();
-    cp_async_wait<1>();  // own loads of the NEXT tile (the ones just issued may still fly)
-    __syncthreads();     // S2: stage 2 done, the next tile is visible to everybody
-    prev = meta;
-    prev_tile = tile;
-    cur = cur == kTwBufs - 1 ? 0 : cur + 1;
+    cur = cur == kTnBufs - 1 ? 0 : cur + 1;
   }
-  copy_rows(prev_tile, prev, 0, 8);
   cp_async_wait<0>();
 }
 
@@ -1325,15 +1265,15 @@ static int launch_two_sided_t(const V* rho, V* out, const V* op, const FiberMap&
                                                             options().ts_order.load(std::memory_order_relaxed));
     if (inner) {
       PW_LAUNCHED();
-      static bool attr_wide = false;
-      const size_t smem_wide = sizeof(double2) * (kTwBufs * 8 * kTwRow + 2 * kTwMaxSb * 64) +
-                               sizeof(int64_t) * 2 * kTwMaxSb * 8 + sizeof(TwMeta) * kTwBufs +
+      static bool attr_rows = false;
+      const size_t smem_rows = sizeof(double2) * (kTnBufs * 8 * kTnRow + kTwMaxSb * 64) +
+                               sizeof(int64_t) * 2 * kTwMaxSb * 8 + sizeof(TwMeta) * kTnBufs +
                                sizeof(int) * (2 * kTwMaxSb * 8 + kTwMaxSb);
-      if (!attr_wide) {
-        PW_CUDA(cudaFuncSetAttribute(k_two_sided_mma_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wide));
-        attr_wide = true;
+      if (!attr_rows) {
+        PW_CUDA(cudaFuncSetAttribute(k_two_sided_mma_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+        attr_rows = true;
       }
-      k_two_sided_mma_wide<<<kNumSMs, kTwWarps * 32, smem_wide, s>>>((const double2*)rho, (double2*)out, fm, T, (int)cols.t);
+      k_two_sided_mma_rows<<<2 * kNumSMs, kTnWarps * 32, smem_rows, s>>>((const double2*)rho, (double2*)out, fm, T, (int)cols.t);
     }
   }
   PW_LAUNCHED();
@@ -1348,7 +1288,7 @@ int launch_two_sided(const void* rho, void* out, const void* op, const FiberMap&
   if (rho == out || rows.t != cols.t || rows.t > kBlockMaxT) return PW_ERR_UNSUPPORTED;
   // innermost axis: untouched (adjacent fibers), or the single column target of a 5..8-level
   // operator with whole chunks of 32 fibers in the run next to it (tensor-core kernel only)
-  // bit 1: the column targets are exactly the innermost run of t elements (wide tiles);
+  // bit 1: the column targets are exactly the innermost run of t elements (row tiles);
   // bit 2: ... and ONE 5..8-level target with whole chunks of 32 fibers next to it (32-fiber tiles)
   int inner = 0;
   if (fm.ng == 0) return PW_ERR_UNSUPPORTED;
