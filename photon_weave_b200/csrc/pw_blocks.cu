@@ -1040,7 +1040,7 @@ constexpr int kTnBufs = 3;
 
 __global__ void __launch_bounds__(kTnWarps * 32, 2)
 k_two_sided_mma_rows(const double2* __restrict__ in, double2* __restrict__ out, const FiberMap fm,
-                     const TsTables T, const int t) {
+                     const TsTables T, const int t, const int order) {
   using V = double2;
   if (!T.flags->handled || T.flags->use_mma != 2) return;
   extern __shared__ __align__(16) unsigned char s_raw[];
@@ -1081,7 +1081,9 @@ k_two_sided_mma_rows(const double2* __restrict__ in, double2* __restrict__ out, 
 
   auto issue = [&](uint32_t u, int buf) {
     if (u < units) {
-      const uint32_t K = u / chunks, c = u - K * chunks;
+      uint32_t K, c;
+      if (order == 0) { K = u / chunks; c = u - K * chunks; }       // chunk fastest
+      else { c = u / (uint32_t)nsb; K = u - c * (uint32_t)nsb; }    // row super-block fastest
       const uint32_t o = c / cpr, w = c - o * cpr;
       const uint32_t f0 = w * F;
       const int nvalid = (gl - f0) < (uint32_t)F ? (int)(gl - f0) : F;
@@ -1273,7 +1275,8 @@ static int launch_two_sided_t(const V* rho, V* out, const V* op, const FiberMap&
         PW_CUDA(cudaFuncSetAttribute(k_two_sided_mma_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
         attr_rows = true;
       }
-      k_two_sided_mma_rows<<<2 * kNumSMs, kTnWarps * 32, smem_rows, s>>>((const double2*)rho, (double2*)out, fm, T, (int)cols.t);
+      k_two_sided_mma_rows<<<2 * kNumSMs, kTnWarps * 32, smem_rows, s>>>((const double2*)rho, (double2*)out, fm, T, (int)cols.t,
+                                                                      options().ts_order.load(std::memory_order_relaxed));
     }
   }
   PW_LAUNCHED();
