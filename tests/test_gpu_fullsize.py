@@ -57,8 +57,10 @@ def test_config4_vector_full_size_properties(ffi):
     a, b = psi.clone(), torch.empty_like(psi)
     us = {ax: ops.random_unitary(d, 50 + ax) for ax in (0, 5, 9, 11)}
     bs = ops.beam_splitter(d, d, math.pi / 5)
+    dense2 = ops.random_unitary(d * d, 77)   # dense two-mode operators: FP64 tensor-core kernel
     prog = [((0,), us[0]), ((5,), us[5]), ((9,), us[9]), ((11,), us[11]),
-            ((2, 3), bs), ((10, 11), bs), ((11, 0), bs), ((4, 8), bs)]
+            ((2, 3), bs), ((10, 11), bs), ((11, 0), bs), ((3, 4), dense2), ((11, 10), dense2),
+            ((4, 8), bs)]
     for tg, op in prog:
         ffi.apply_vec(a, dev(op), dims, tg, out=b)
         a, b = b, a
@@ -116,6 +118,30 @@ def test_config3_density_matrix_full_size_properties(ffi):
     ws = [ffi.apply_vec(v, dev(u), dims, (3,)) for v in vs]
     corner = sum(torch.outer(w[:256], w[:256].conj()) for w in ws) / 3.0
     assert float((out[:256, :256] - corner).abs().max()) < 1e-15
+    # the tensor-core two-sided kernels (dense on the innermost mode, beam splitter sectors packed
+    # into super-blocks, row tiles for the innermost mode pair) against the vector picture on
+    # 256 x 256 randomly sampled entries, then the inverse round trip of the whole sequence
+    bs = ops.beam_splitter(d, d, math.pi / 5)
+    seq = [((4,), u), ((1, 2), bs), ((3, 4), bs), ((4, 0), bs), ((0,), ops.random_unitary(d, 10))]
+    a, b = out, torch.empty_like(out)
+    rng = np.random.default_rng(5)
+    I = torch.as_tensor(rng.choice(D, 256, replace=False), device="cuda")
+    J = torch.as_tensor(rng.choice(D, 256, replace=False), device="cuda")
+    start = a.clone()
+    for tg, op in seq:
+        ffi.apply_mat(a.reshape(-1), dev(op), dims, tg, out=b.reshape(-1))
+        ws = [ffi.apply_vec(w, dev(op), dims, tg) for w in ws]
+        a, b = b, a
+        want = sum(torch.outer(w[I], w[J].conj()) for w in ws) / 3.0
+        assert float((a[I][:, J] - want).abs().max()) < 1e-15, tg
+        assert abs(float(torch.diagonal(a).sum().real) - tr0) < 1e-11, tg
+    for tg, op in reversed(seq):
+        ffi.apply_mat(a.reshape(-1), dev(op.conj().T), dims, tg, out=b.reshape(-1))
+        a, b = b, a
+    assert max_abs_diff(a.reshape(-1), start.reshape(-1)) < 1e-15
+    out = a
+    del b, start
+    ws = [ffi.apply_vec(v, dev(u), dims, (3,)) for v in vs]
     # measurement probabilities of one mode agree between the matrix and vector pictures
     p_mat = ffi.probs(out, dims, (3,), True)
     p_vec = sum(ffi.probs(w, dims, (3,), False) * float(ffi.norm_stats(w)[0]) for w in ws) / 3.0
