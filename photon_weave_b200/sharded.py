@@ -545,6 +545,7 @@ def bench_sharded(args, dist, rank, world, local_rank, make_layer, workload_conf
         avg_op_ms = op_ms / nops
         achieved = alg_bytes / (avg_op_ms * 1e-3) / 1e9
         swap_bytes = n_local * 16 * (world - 1) / world
+        fused_per_step = (st.fused_swaps - fused0) / args.steps
         line = {
             "metric": METRIC, "value": nops * N * args.steps / (total_ms * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -561,10 +562,12 @@ def bench_sharded(args, dist, rank, world, local_rank, make_layer, workload_conf
             "cpu_baseline": None,
             "axis_swap": {"swaps_per_step": swaps, "packs_per_step": packs, "ms_per_step": swap_ms,
                           "bytes_sent_per_rank": swap_bytes,
-                          "gbs_per_rank_per_direction": swap_bytes * swaps / (swap_ms * 1e-3) / 1e9
-                          if swap_ms > 0 else None,
+                          # stand-alone swaps only: a swap fused into the apply kernel has no
+                          # duration of its own (fused_swap_plus_apply_ms is the fused kernel)
+                          "gbs_per_rank_per_direction": swap_bytes * (swaps - fused_per_step) / (swap_ms * 1e-3) / 1e9
+                          if swap_ms > 0 and swaps - fused_per_step > 0 else None,
                           "nvlink_reference_gbs": 770.0,
-                          "fused_swaps_per_step": (st.fused_swaps - fused0) / args.steps,
+                          "fused_swaps_per_step": fused_per_step,
                           "fused_swap_plus_apply_ms": fused_op_ms if peers is not None else None,
                           "implementation": swap_impl},
             "compute_ms_per_step": op_ms, "norm_after": norm_after,
