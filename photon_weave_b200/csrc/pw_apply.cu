@@ -608,6 +608,16 @@ static int matrix_dispatch(const void* rho, void* out, const void* ops, int K, c
     const int rc = try_super_blocks(rho, out, ops, K, r, dtype, s, &super, &bd);
     if (rc == PW_OK) skip = bd.skip_flag();
     else if (rc != PW_ERR_UNSUPPORTED) return rc;
+    // a Kraus sum whose superoperator is dense (no usable block structure): the t^2 x t^2
+    // superoperator is ONE dense one-sided operator on the doubled tensor -> FP64 tensor cores
+    // (one pass whatever K is; K row + column passes otherwise)
+    if (rc == PW_OK && K > 1 && mm == 0 && !bd.staged && r.t * r.t <= 64 &&
+        options().dense_mma.load(std::memory_order_relaxed)) {
+      Plan pb;
+      PW_TRY(build_plan_axes(r.axes, 2 * r.n, r.both, 2 * r.nt, &pb));
+      const int rc2 = launch_dense_mma(rho, out, super.p, pb, dtype, false, s, skip);
+      if (rc2 != PW_ERR_UNSUPPORTED) return rc2;
+    }
   }
   // single operator, untouched innermost axis: ONE pass through shared-memory tiles
   // (dense d <= 8 operators, beam-splitter-like block structure); decided on the device

@@ -698,6 +698,16 @@ def test_dense_tensor_core_kernel(ad):
         check_vec((50, 6, 6), (2, 1), ops.random_unitary(36, 52), 52)
         check_vec((7, 13), (1,), ops.random_unitary(13, 53), 53)
         check_vec((3, 70, 8, 8), (2, 3), ops.random_unitary(64, 54), 54)
+        # Kraus sum with a dense superoperator (8^2 = 64): one dense pass on the doubled tensor
+        for dims_k, tg_k, dk in [((8, 70), (0,), 8), ((3, 6, 40), (1,), 6), ((5, 2, 2, 33), (1, 2), 4)]:
+            rng = np.random.default_rng(57)
+            ks = rng.standard_normal((3, dk, dk)) + 1j * rng.standard_normal((3, dk, dk))
+            ks /= np.sqrt(np.trace(sum(k.conj().T @ k for k in ks)).real / dk)
+            Nk = math.prod(dims_k)
+            rho = ops.random_density(Nk, 58)
+            ref = oad.apply_kraus_matrix(dims_k, tg_k, rho, ks, True)
+            out = host(ad.apply_kraus_matrix(dims_k, tg_k, dev(rho), dev(ks)))
+            assert rel_err(out, ref) < tol, (dims_k, tg_k)
         check_mat((20, 4, 4), (1, 2), ops.random_unitary(16, 55), 55)
         check_mat((33, 11), (1,), ops.random_unitary(11, 56), 56)
         check_mat((3, 5, 16), (1, 0), ops.random_unitary(15, 49), 49)

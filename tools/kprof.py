@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Runs ONE libpwb200 case a few times (for ncu captures).  Usage:
-   python tools/kprof.py vec|mat <modes> <cutoff> <op: u|bs|phase|loss|dense2> <targets...> [--path P] [--tile E] [--reps R]"""
+   python tools/kprof.py vec|mat <modes> <cutoff> <op: u|bs|phase|loss|krausd|dense2> <targets...> [--path P] [--tile E] [--reps R]"""
 import argparse, math, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -34,13 +34,14 @@ y = torch.empty_like(x)
 t = d ** len(a.targets)
 op = {"u": lambda: ops.random_unitary(t, 1), "bs": lambda: ops.beam_splitter(d, d, math.pi / 4),
       "phase": lambda: ops.phase_operator(d, 0.3), "loss": lambda: ops.loss_channel(d, 0.1),
-      "dense2": lambda: ops.random_unitary(t, 2)}[a.op]()
+      "dense2": lambda: ops.random_unitary(t, 2),
+      "krausd": lambda: np.stack([ops.random_unitary(t, 10 + k) / 2.0 for k in range(4)])}[a.op]()
 op = torch.as_tensor(np.ascontiguousarray(op)).cuda()
 def run():
     for _ in range(a.reps):
         if a.what == "vec":
             ffi.apply_vec(x, op, dims, a.targets, out=y)
-        elif a.op == "loss":
+        elif a.op in ("loss", "krausd"):
             ffi.kraus_mat(x, op, dims, a.targets, out=y)
         else:
             ffi.apply_mat(x, op, dims, a.targets, out=y)
