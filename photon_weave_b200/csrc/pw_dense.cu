@@ -31,8 +31,8 @@ constexpr int kDmFib = 64;       // fibers per tile
 constexpr int kDmMaxT = 64;
 
 __device__ __forceinline__ void dmma(double& d0, double& d1, const double a, const double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 __device__ __forceinline__ void cp16(void* smem_dst, const void* gsrc) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -149,13 +149,16 @@ k_apply_dense_mma(const double2* __restrict__ in, double2* __restrict__ out,
 #pragma unroll
           for (int n = 0; n < 4; ++n) x[n] = j < t ? xcol[j * kDmFib + 8 * n] : make_double2(0.0, 0.0);
         }
+        // step-major issue order: the eight accumulator chains advance together (a warp issues
+        // in order; consecutive DMMAs must be independent to keep the tensor pipe busy)
 #pragma unroll
-        for (int n = 0; n < 4; ++n) {
-          dmma(acc[n][0], acc[n][1], w.x, x[n].x);
-          dmma(acc[n][2], acc[n][3], w.y, x[n].x);
-          dmma(acc[n][0], acc[n][1], -w.y, x[n].y);
-          dmma(acc[n][2], acc[n][3], w.x, x[n].y);
-        }
+        for (int n = 0; n < 4; ++n) dmma(acc[n][0], acc[n][1], w.x, x[n].x);
+#pragma unroll
+        for (int n = 0; n < 4; ++n) dmma(acc[n][2], acc[n][3], w.y, x[n].x);
+#pragma unroll
+        for (int n = 0; n < 4; ++n) dmma(acc[n][0], acc[n][1], -w.y, x[n].y);
+#pragma unroll
+        for (int n = 0; n < 4; ++n) dmma(acc[n][2], acc[n][3], w.x, x[n].y);
       }
       if (INNER) {
         if (row < t) {
