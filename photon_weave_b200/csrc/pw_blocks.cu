@@ -1170,7 +1170,11 @@ k_two_sided_mma_rows(const double2* __restrict__ in, double2* __restrict__ out, 
     // step: eight independent DMMA chains per warp.
     constexpr int kB = 4;
     // stage 1 (column side): (fiber f, column super-block L), positions mixed inside every row
-    const int n2 = (order & 2) ? 0 : F * nsb;   // DEBUG(order & 2): no column side
+#ifdef PW_TS_ABLATE  // profiling builds only (make EXTRA=-DPW_TS_ABLATE): ts_order bit 2 = no column side
+    const int n2 = (order & 2) ? 0 : F * nsb;
+#else
+    const int n2 = F * nsb;
+#endif
     for (int it0 = warp; it0 < n2; it0 += kB * kTnWarps) {
       V* fib[kB];
       int nLb[kB], posb[kB];
@@ -1214,12 +1218,13 @@ k_two_sided_mma_rows(const double2* __restrict__ in, double2* __restrict__ out, 
         x0[b] = (tig < nK && it < n1) ? col[rd1a] : zero;
         x1[b] = (4 + tig < nK && it < n1) ? col[rd1b] : zero;
       }
-      if (order & 4) {  // DEBUG(order & 4): no row-side arithmetic
+#ifdef PW_TS_ABLATE  // ts_order bit 4 = no row-side arithmetic (copies the inputs)
+      if (order & 4) {
 #pragma unroll
         for (int b = 0; b < kB; ++b) { y0[b] = x0[b]; y1[b] = x1[b]; }
-      } else {
+      } else
+#endif
         cmma_batch<kB, true>(&l0, &l1, x0, x1, y0, y1);
-      }
       if (gid < nK) {
 #pragma unroll
         for (int b = 0; b < kB; ++b) {
