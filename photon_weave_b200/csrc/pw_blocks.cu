@@ -1077,12 +1077,19 @@ constexpr int kTnWarps = 8;
 constexpr int kTnRow = 256;   // elements per tile row (F fibers x padded t)
 constexpr int kTnBufs = 3;
 
+// Column targets = the innermost run (lseg positions) x outer column targets (nseg segments):
+// position p = s * lseg + jr of fiber f lives at seg_off[s] + f * lseg + jr.  A beam splitter on
+// the last two modes is one segment (lseg = t); on modes (4, 0) it is eight segments of eight.
+struct TnSeg { int lseg, nseg; int64_t seg_off[64]; };
+
 __global__ void __launch_bounds__(kTnWarps * 32, 2)
 k_two_sided_mma_rows(const double2* __restrict__ in, double2* __restrict__ out, const FiberMap fm,
-                     const TsTables T, const int t, const int order) {
+                     const TsTables T, const int t, const int order, const TnSeg seg) {
   using V = double2;
   if (!T.flags->handled || T.flags->use_mma != 2) return;
   extern __shared__ __align__(16) unsigned char s_raw[];
+  __shared__ int64_t s_seg[64];
+  if (threadIdx.x < 64) s_seg[threadIdx.x] = threadIdx.x < seg.nseg ? seg.seg_off[threadIdx.x] : 0;
   V* tile0 = (V*)s_raw;                                       // [kTnBufs][8][kTnRow]
   V* s_w = tile0 + kTnBufs * 8 * kTnRow;                      // [kTwMaxSb][64] column-side operands (swizzled)
   int64_t* s_roff = (int64_t*)(s_w + kTwMaxSb * 64);          // [2][kTwMaxSb][8] row offsets: in, out
@@ -1108,7 +1115,8 @@ k_two_sided_mma_rows(const double2* __restrict__ in, double2* __restrict__ out, 
   const int tp = (t + 7) & ~7;
   const int F = kTnRow / tp;                   // fibers per tile (t <= 64: at least 4)
   const int nq = tp >> 3;                      // position octets per fiber
-  const uint32_t inv_t = 0xffffffffu / (uint32_t)t + 1;
+  const int lseg = seg.lseg, nseg = seg.nseg;
+  const uint32_t inv_l = 0xffffffffu / (uint32_t)lseg + 1;   // x / lseg for x < 2^16
   const uint32_t inv_nq = 0xffffu / (uint32_t)nq + 1, inv_nsb = 0xffffu / (uint32_t)nsb + 1;
   const uint32_t gl = (uint32_t)fm.gsize[fm.ng - 1];
   const uint32_t cpr = (gl + F - 1) / F;
@@ -1131,10 +1139,14 @@ k_two_sided_mma_rows(const double2* __restrict__ in, double2* __restrict__ out, 
       const int nK = s_n[K];
       V* tile = tile0 + (size_t)buf * 8 * kTnRow;
       const int64_t* ro = rin + K * 8;
-      for (int r = threadIdx.x; r < nvalid * t; r += kTnWarps * 32) {
-        const int f = (int)__umulhi((uint32_t)r, inv_t), j = r - f * t;
+      // per segment the F fibers x lseg positions are one contiguous piece
+      const int rowlen = nvalid * lseg;
+      for (int idx = threadIdx.x; idx < rowlen * nseg; idx += kTnWarps * 32) {
+        const int sg = nseg == 1 ? 0 : idx / rowlen;
+        const int e = idx - sg * rowlen;
+        const int f = (int)__umulhi((uint32_t)e, inv_l), j = sg * lseg + (e - f * lseg);
         V* dst = tile + f * tp;
-        const V* src = in + base0 + r;
+        const V* src = in + base0 + s_seg[sg] + e;
         for (int a = 0; a < nK; ++a) cp_async16(dst + a * kTnRow + (j ^ sig(a)), src + ro[a]);
       }
     }
@@ -1204,7 +1216,7 @@ k_two_sided_mma_rows(const double2* __restrict__ in, double2* __restrict__ out, 
     __syncthreads();  // B
     // stage 2 (row side): (fiber f, position octet q), rows mixed, streamed to HBM
     const int n1 = F * nq;
-    V* orow = out + meta.base0 + rout[K * 8 + (gid < nK ? gid : 0)] + 2 * tig;
+    V* orow = out + meta.base0 + rout[K * 8 + (gid < nK ? gid : 0)];
     for (int it0 = warp; it0 < n1; it0 += kB * kTnWarps) {
       int fq[kB];
       V x0[kB], x1[kB], y0[kB], y1[kB];
@@ -1231,9 +1243,10 @@ k_two_sided_mma_rows(const double2* __restrict__ in, double2* __restrict__ out, 
           if (fq[b] < 0) continue;
           const int f = fq[b] >> 8, j = 8 * (fq[b] & 255) + 2 * tig;
           if (f >= meta.nvalid) continue;
-          V* dst = orow + (int64_t)f * t + 8 * (fq[b] & 255);
-          if (j < t) __stcg(dst, y0[b]);
-          if (j + 1 < t) __stcg(dst + 1, y1[b]);
+          const int sg0 = (int)__umulhi((uint32_t)j, inv_l), sg1 = (int)__umulhi((uint32_t)(j + 1), inv_l);
+          V* dst = orow + (int64_t)f * lseg;
+          if (j < t) __stcg(dst + s_seg[sg0] + (j - sg0 * lseg), y0[b]);
+          if (j + 1 < t) __stcg(dst + s_seg[sg1] + (j + 1 - sg1 * lseg), y1[b]);
         }
       }
     }
@@ -1245,9 +1258,11 @@ k_two_sided_mma_rows(const double2* __restrict__ in, double2* __restrict__ out, 
 template <typename V>
 static int launch_two_sided_t(const V* rho, V* out, const V* op, const FiberMap& fm,
                               const TargetMap& rows, const TargetMap& cols, const int* other,
-                              const int inner, TwoSided* ts, cudaStream_t s) {
+                              const int inner, const TnSeg& seg, const TargetMap& cols_pos,
+                              TwoSided* ts, cudaStream_t s) {
   PW_TRY(build_block_desc_t<V>(op, rows.t, false, rows, &ts->memL, &ts->L, s));
-  PW_TRY(build_block_desc_t<V>(op, cols.t, true, cols, &ts->memR, &ts->R, s));
+  // innermost column targets: the column side is addressed by POSITION inside the fiber row
+  PW_TRY(build_block_desc_t<V>(op, cols.t, true, inner ? cols_pos : cols, &ts->memR, &ts->R, s));
   const size_t t = rows.t, tt = t * t;
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const size_t b_flags = 256, b_groups = al(sizeof(int4) * 2 * tt), b_pairs = al(sizeof(int4) * tt),
@@ -1310,7 +1325,7 @@ static int launch_two_sided_t(const V* rho, V* out, const V* op, const FiberMap&
         attr_rows = true;
       }
       k_two_sided_mma_rows<<<2 * kNumSMs, kTnWarps * 32, smem_rows, s>>>((const double2*)rho, (double2*)out, fm, T, (int)cols.t,
-                                                                      options().ts_order.load(std::memory_order_relaxed));
+                                                                      options().ts_order.load(std::memory_order_relaxed), seg);
     }
   }
   PW_LAUNCHED();
@@ -1328,20 +1343,51 @@ int launch_two_sided(const void* rho, void* out, const void* op, const FiberMap&
   // bit 1: the column targets are exactly the innermost run of t elements (row tiles);
   // bit 2: ... and ONE 5..8-level target with whole chunks of 32 fibers next to it (32-fiber tiles)
   int inner = 0;
+  TnSeg seg;
+  seg.lseg = (int)cols.t; seg.nseg = 1; seg.seg_off[0] = 0;
+  TargetMap cols_pos = cols;
   if (fm.ng == 0) return PW_ERR_UNSUPPORTED;
   if (fm.gstride[fm.ng - 1] != 1) {
-    bool run = fm.gstride[fm.ng - 1] == (int64_t)cols.t && cols.t >= 5 && cols.t <= 64 && dtype == PW_C128;
-    for (int k = 0; k < cols.nt && run; ++k) run = cols.tdim[k] == 1 || cols.tstride[k] < (int64_t)cols.t;
-    if (!run || fm.nfib >= (1ull << 28)) return PW_ERR_UNSUPPORTED;  // (32-bit unit index in the kernel)
+    // the innermost axis is a column target: the column targets below the last untouched run
+    // must fill the innermost run exactly (lseg positions); the other column targets enumerate
+    // segments (tensor order, last fastest)
+    const int64_t L = fm.gstride[fm.ng - 1];
+    if (dtype != PW_C128 || cols.t < 5 || cols.t > 64 || fm.nfib >= (1ull << 28)) return PW_ERR_UNSUPPORTED;
+    int64_t prod_in = 1;
+    int outer[kMaxTargets], n_out = 0;
+    for (int k = 0; k < cols.nt; ++k) {
+      if (cols.tdim[k] == 1) { cols_pos.tstride[k] = 0; continue; }
+      if (cols.tstride[k] < L) prod_in *= cols.tdim[k];
+      else outer[n_out++] = k;
+    }
+    if (prod_in != L || L > 64 || cols.t % (uint32_t)L != 0 || cols.t / (uint32_t)L > 64) return PW_ERR_UNSUPPORTED;
+    for (int i = 1; i < n_out; ++i)  // sort by stride, descending (tensor order)
+      for (int j = i; j > 0 && cols.tstride[outer[j]] > cols.tstride[outer[j - 1]]; --j) {
+        const int tmp = outer[j]; outer[j] = outer[j - 1]; outer[j - 1] = tmp;
+      }
+    seg.lseg = (int)L;
+    seg.nseg = (int)(cols.t / (uint32_t)L);
+    int64_t ps = L;
+    for (int i = n_out - 1; i >= 0; --i) { cols_pos.tstride[outer[i]] = ps; ps *= cols.tdim[outer[i]]; }
+    for (int sg = 0; sg < seg.nseg; ++sg) {
+      int rem = sg;
+      int64_t off = 0;
+      for (int i = n_out - 1; i >= 0; --i) {
+        const int dd = (int)cols.tdim[outer[i]];
+        off += (int64_t)(rem % dd) * cols.tstride[outer[i]];
+        rem /= dd;
+      }
+      seg.seg_off[sg] = off;
+    }
     inner = 1;
     if (cols.nt == 1 && cols.tstride[0] == 1 && cols.t <= 8 && fm.gsize[fm.ng - 1] % 32 == 0) inner |= 2;
   }
   if (dtype == PW_C128)
     return launch_two_sided_t<double2>((const double2*)rho, (double2*)out, (const double2*)op, fm, rows,
-                                       cols, other_handled, inner, ts, stream);
+                                       cols, other_handled, inner, seg, cols_pos, ts, stream);
   if (dtype == PW_C64)
     return launch_two_sided_t<float2>((const float2*)rho, (float2*)out, (const float2*)op, fm, rows,
-                                      cols, other_handled, inner, ts, stream);
+                                      cols, other_handled, inner, seg, cols_pos, ts, stream);
   return PW_ERR_INVALID;
 }
 

@@ -643,6 +643,12 @@ def test_two_sided_single_pass_kernel(ad, cdtype):
     check((5, 5, 5, 5), (2, 3), ops.beam_splitter(5, 5, 1.1), 31)
     check((4, 3, 7, 6), (3, 2), ops.beam_splitter(6, 7, 0.8), 32)
     check((10, 4, 7, 2, 4), (2, 3, 4), np.kron(ops.random_unitary(7, 33), ops.random_unitary(8, 34)), 33)
+    # innermost + far column targets: segmented fiber rows
+    check((8, 3, 8), (2, 0), ops.beam_splitter(8, 8, 0.5), 35)
+    check((8, 3, 8), (0, 2), ops.beam_splitter(8, 8, 0.5), 36)
+    check((4, 9, 2, 6), (3, 0), ops.beam_splitter(6, 4, 0.6), 37)
+    check((5, 2, 7, 5), (0, 3), ops.beam_splitter(5, 5, 0.2), 38)
+    check((3, 2, 5, 4, 3), (4, 0, 3), np.kron(np.kron(ops.random_unitary(3, 39), np.eye(3)), ops.random_unitary(4, 40)), 39)
     # beam splitters whose sectors pack into several super-blocks (cutoffs 8, 5, 7 x 6)
     check((3, 8, 8, 4), (1, 2), ops.beam_splitter(8, 8, 0.9), 26)
     check((5, 5, 5, 5), (3, 1), ops.beam_splitter(5, 5, 0.7), 27)
