@@ -1117,7 +1117,7 @@ k_two_sided_mma_rows(const double2* __restrict__ in, double2* __restrict__ out, 
   const int nq = tp >> 3;                      // position octets per fiber
   const int lseg = seg.lseg, nseg = seg.nseg;
   const uint32_t inv_l = 0xffffffffu / (uint32_t)lseg + 1;   // x / lseg for x < 2^16
-  const uint32_t inv_nq = 0xffffu / (uint32_t)nq + 1, inv_nsb = 0xffffu / (uint32_t)nsb + 1;
+  const uint32_t inv_nq = 0xffffu / (uint32_t)nq + 1;
   const uint32_t gl = (uint32_t)fm.gsize[fm.ng - 1];
   const uint32_t cpr = (gl + F - 1) / F;
   const uint32_t chunks = (uint32_t)(fm.nfib / gl) * cpr;
@@ -1183,35 +1183,38 @@ k_two_sided_mma_rows(const double2* __restrict__ in, double2* __restrict__ out, 
     constexpr int kB = 4;
     // stage 1 (column side): (fiber f, column super-block L), positions mixed inside every row
 #ifdef PW_TS_ABLATE  // profiling builds only (make EXTRA=-DPW_TS_ABLATE): ts_order bit 2 = no column side
-    const int n2 = (order & 2) ? 0 : F * nsb;
+    const int n2g = (order & 2) ? 0 : nsb * ((F + kB - 1) / kB);
 #else
-    const int n2 = F * nsb;
+    const int n2g = nsb * ((F + kB - 1) / kB);
 #endif
-    for (int it0 = warp; it0 < n2; it0 += kB * kTnWarps) {
-      V* fib[kB];
-      int nLb[kB], posb[kB];
-      V x0[kB], x1[kB], y0[kB], y1[kB], r0[kB], r1[kB];
+    // an item is (column super-block L, group of kB fibers): operand fragments and positions are
+    // loaded once per item and shared by its fibers
+    const int ngrp = (F + kB - 1) / kB;
+    for (int it = warp; it < n2g; it += kTnWarps) {
+      const int L = it / ngrp, f0 = (it - L * ngrp) * kB;
+      const int nL = s_n[L];
+      const V r0 = s_w[L * 64 + gid * 8 + (tig ^ fsw)], r1 = s_w[L * 64 + gid * 8 + ((4 + tig) ^ fsw)];
+      const int c0 = rd2 + (cin[L * 8 + tig] ^ sg2), c1 = rd2 + (cin[L * 8 + 4 + tig] ^ sg2);
+      const int pos = cout[L * 8 + gid];
+      const int wa = wr2a + (pos ^ sa), wb = wr2b + (pos ^ sb4);
+      V x0[kB], x1[kB], y0[kB], y1[kB];
 #pragma unroll
       for (int b = 0; b < kB; ++b) {
-        const int it = it0 + b * kTnWarps;
-        const int itc = it < n2 ? it : it0;
-        const int f = (int)(((uint32_t)itc * inv_nsb) >> 16), L = itc - f * nsb;
-        nLb[b] = it < n2 ? s_n[L] : 0;
-        r0[b] = s_w[L * 64 + gid * 8 + (tig ^ fsw)];
-        r1[b] = s_w[L * 64 + gid * 8 + ((4 + tig) ^ fsw)];
-        fib[b] = tile + f * tp;
-        posb[b] = cout[L * 8 + gid];
-        x0[b] = tig < nLb[b] ? fib[b][rd2 + (cin[L * 8 + tig] ^ sg2)] : zero;
-        x1[b] = 4 + tig < nLb[b] ? fib[b][rd2 + (cin[L * 8 + 4 + tig] ^ sg2)] : zero;
+        const V* fib = tile + (f0 + b) * tp;
+        x0[b] = (tig < nL && f0 + b < F) ? fib[c0] : zero;
+        x1[b] = (4 + tig < nL && f0 + b < F) ? fib[c1] : zero;
       }
-      cmma_batch<kB, false>(r0, r1, x0, x1, y0, y1);
+      cmma_batch<kB, true>(&r0, &r1, x0, x1, y0, y1);
       __syncwarp();
+      if (gid < nL) {
 #pragma unroll
-      for (int b = 0; b < kB; ++b)
-        if (gid < nLb[b]) {
-          fib[b][wr2a + (posb[b] ^ sa)] = y0[b];
-          fib[b][wr2b + (posb[b] ^ sb4)] = y1[b];
-        }
+        for (int b = 0; b < kB; ++b)
+          if (f0 + b < F) {
+            V* fib = tile + (f0 + b) * tp;
+            fib[wa] = y0[b];
+            fib[wb] = y1[b];
+          }
+      }
     }
     __syncthreads();  // B
     // stage 2 (row side): (fiber f, position octet q), rows mixed, streamed to HBM
