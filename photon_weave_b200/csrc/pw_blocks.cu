@@ -789,6 +789,20 @@ __device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, const double a
       : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+// Two complex128 values that are usually adjacent in memory (the two fibers / positions of an
+// accumulator fragment): ONE 256-bit store (sm_100: STG.E.256) when they are, two 128-bit stores
+// otherwise.
+__device__ __forceinline__ void st_pair(double2* p0, double2* p1, const double2 v0, const double2 v1,
+                                        const bool ok0, const bool ok1) {
+  if (ok0 && ok1 && p1 == p0 + 1 && (reinterpret_cast<uintptr_t>(p0) & 31) == 0) {
+    asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p0), "d"(v0.x), "d"(v0.y), "d"(v1.x), "d"(v1.y)
+                 : "memory");
+  } else {
+    if (ok0) __stcg(p0, v0);
+    if (ok1) __stcg(p1, v1);
+  }
+}
+
 // Complex 8 x 8 products of NB independent items, issued STEP-major: the 2 NB accumulator chains
 // advance together, so that consecutive DMMAs in program order are independent (a warp issues in
 // order).  Measured: 6 % faster than item-major order in the row-tile kernel, no difference in
@@ -1030,8 +1044,7 @@ __device__ __forceinline__ void two_sided_mma_body(const double2* __restrict__ i
                 (void)nt;
                 if (gid < nL) {
                   const int64_t b0 = sb[f], b1 = sb[f + 1];
-                  if (b0 >= 0) __stcg(out + b0 + ro, v0);
-                  if (b1 >= 0) __stcg(out + b1 + ro, v1);
+                  st_pair(out + b0 + ro, out + b1 + ro, v0, v1, b0 >= 0, b1 >= 0);
                 }
               });
     }
@@ -1248,8 +1261,8 @@ k_two_sided_mma_rows(const double2* __restrict__ in, double2* __restrict__ out, 
           if (f >= meta.nvalid) continue;
           const int sg0 = (int)__umulhi((uint32_t)j, inv_l), sg1 = (int)__umulhi((uint32_t)(j + 1), inv_l);
           V* dst = orow + (int64_t)f * lseg;
-          if (j < t) __stcg(dst + s_seg[sg0] + (j - sg0 * lseg), y0[b]);
-          if (j + 1 < t) __stcg(dst + s_seg[sg1] + (j + 1 - sg1 * lseg), y1[b]);
+          st_pair(dst + s_seg[sg0] + (j - sg0 * lseg), dst + s_seg[sg1] + (j + 1 - sg1 * lseg), y0[b], y1[b],
+                  j < t, j + 1 < t);
         }
       }
     }
