@@ -1598,7 +1598,21 @@ k_apply_blocks_seg_mma(const double2* __restrict__ in, double2* __restrict__ out
     __syncthreads();
     {
       const int rowlen = meta.nvalid * (int)lseg;
-      if (g.nseg >= 4) {
+      if ((lseg & 1) == 0 && g.nseg < 4) {
+        // few long even segments: two adjacent positions per thread, one 256-bit store
+        // (many short segments: measured slower -- fewer active threads per row)
+        for (int e = 2 * threadIdx.x; e < rowlen; e += 2 * blockDim.x) {
+          const int f = (int)__umulhi((uint32_t)e, inv_l);
+          const int jr = e - f * (int)lseg, sf_ = sigma(f);
+          const V* src = tile + f * tp;
+          V* dst = out + meta.base + e;
+          for (uint32_t sg = 0; sg < g.nseg; ++sg) {
+            const int p = (int)(sg * lseg) + jr;
+            V* d0 = dst + s_seg[sg];
+            st_pair(d0, d0 + 1, src[p ^ sf_], src[(p + 1) ^ sf_], true, true);
+          }
+        }
+      } else if (g.nseg >= 4) {
         for (int e = threadIdx.x; e < rowlen; e += blockDim.x) {
           const int f = (int)__umulhi((uint32_t)e, inv_l);
           const int jr = e - f * (int)lseg, sf_ = sigma(f);

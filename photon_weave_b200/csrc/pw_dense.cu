@@ -38,6 +38,17 @@ __device__ __forceinline__ void cp16(void* smem_dst, const void* gsrc) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
+// two values that are usually adjacent in memory: one 256-bit store when they are
+__device__ __forceinline__ void st_pair(double2* p0, double2* p1, const double2 v0, const double2 v1,
+                                        const bool ok0, const bool ok1) {
+  if (ok0 && ok1 && p1 == p0 + 1 && (reinterpret_cast<uintptr_t>(p0) & 31) == 0) {
+    asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p0), "d"(v0.x), "d"(v0.y), "d"(v1.x), "d"(v1.y)
+                 : "memory");
+  } else {
+    if (ok0) __stcg(p0, v0);
+    if (ok1) __stcg(p1, v1);
+  }
+}
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -177,8 +188,8 @@ k_apply_dense_mma(const double2* __restrict__ in, double2* __restrict__ out,
         for (int n = 0; n < 4; ++n) {
           const int f = 32 * h + 8 * n + 2 * tig;
           const int64_t b0 = sb[f], b1 = sb[f + 1];
-          if (b0 >= 0) __stcg(out + b0 + ro, make_double2(acc[n][0], acc[n][2]));
-          if (b1 >= 0) __stcg(out + b1 + ro, make_double2(acc[n][1], acc[n][3]));
+          st_pair(out + b0 + ro, out + b1 + ro, make_double2(acc[n][0], acc[n][2]),
+                  make_double2(acc[n][1], acc[n][3]), b0 >= 0, b1 >= 0);
         }
       }
     }
