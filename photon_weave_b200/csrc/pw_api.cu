@@ -49,6 +49,7 @@ Options& options() {
     env("PW_TILE_ELEMS", p->tile_elems);
     env("PW_CTAS_PER_SM", p->ctas_per_sm);
     env("PW_BLOCKS_MIN_ELEMS", p->blocks_min_elems);
+    env("PW_BLOCKS_MIN_ELEMS_SMALL_T", p->blocks_min_elems_small_t);
     env("PW_NSTAGE", p->nstage);
     env("PW_SEG_KERNEL", p->seg_kernel);
     env("PW_MAT_PAIR_MAX_D", p->mat_pair_max_d);
@@ -84,6 +85,7 @@ extern "C" int pw_set_option(const char* name, int value) {
   else if (!std::strcmp(name, "contig_kernel")) o.contig_kernel.store(value);
   else if (!std::strcmp(name, "small_r")) o.small_r.store(value);
   else if (!std::strcmp(name, "mat_super_single")) o.mat_super_single.store(value);
+  else if (!std::strcmp(name, "blocks_min_elems_small_t")) o.blocks_min_elems_small_t.store(value);
   else if (!std::strcmp(name, "two_sided")) o.two_sided.store(value);
   else if (!std::strcmp(name, "ts_ctas")) o.ts_ctas.store(value);
   else if (!std::strcmp(name, "ts_mma")) o.ts_mma.store(value);

@@ -420,6 +420,16 @@ static uint32_t tile_elems(int dtype) {
 static uint64_t blocks_min_elems() {
   return (uint64_t)options().blocks_min_elems.load(std::memory_order_relaxed);
 }
+// A SINGLE operator with t <= 8 on a density matrix: the structured one-pass paths cost ~50 us of
+// analysis kernels, the fallback is two register-kernel passes -- the analysis pays off only
+// when a pass takes longer than that (measured on the 6.25 MB rho of the lossy-circuit config:
+// dense 5 x 5 69 us with analysis, 14 us without).
+static uint64_t matrix_min_elems(int K, uint64_t t) {
+  const uint64_t base = blocks_min_elems();
+  if (K != 1 || t > 8 || base == 0) return base;
+  const uint64_t small_t = (uint64_t)options().blocks_min_elems_small_t.load(std::memory_order_relaxed);
+  return small_t > base ? small_t : base;
+}
 
 // One strided apply on an arbitrary axis list: out = (O or conj(O) on targets) in.
 //   t <= 8                      register kernel
@@ -530,7 +540,7 @@ static int matrix_req(const int64_t* dims, int n, const int32_t* targets, int nt
 // (row targets, column targets) of the doubled tensor: ONE HBM pass whatever K is.
 static int try_super_blocks(const void* rho, void* out, const void* ops, int K, const MatrixReq& r,
                             int dtype, cudaStream_t s, Scratch* super, BlockDesc* bd) {
-  if (rho == out || r.t * r.t > kBlockMaxT || r.N * r.N < blocks_min_elems()) return PW_ERR_UNSUPPORTED;
+  if (rho == out || r.t * r.t > kBlockMaxT || r.N * r.N < matrix_min_elems(K, r.t)) return PW_ERR_UNSUPPORTED;
   Plan p;
   PW_TRY(build_plan_axes(r.axes, 2 * r.n, r.both, 2 * r.nt, &p));
   const uint64_t r_in = inner_rest_run(p);
@@ -622,7 +632,7 @@ static int matrix_dispatch(const void* rho, void* out, const void* ops, int K, c
   // single operator, untouched innermost axis: ONE pass through shared-memory tiles
   // (dense d <= 8 operators, beam-splitter-like block structure); decided on the device
   TwoSided ts;
-  if (K == 1 && mm == 0 && rho != out && r.t >= 2 && r.t <= kBlockMaxT && r.N * r.N >= blocks_min_elems() &&
+  if (K == 1 && mm == 0 && rho != out && r.t >= 2 && r.t <= kBlockMaxT && r.N * r.N >= matrix_min_elems(K, r.t) &&
       options().two_sided.load(std::memory_order_relaxed)) {
     Plan pb, pr, pc;
     PW_TRY(build_plan_axes(r.axes, 2 * r.n, r.both, 2 * r.nt, &pb));

@@ -182,6 +182,7 @@ struct Options {
   std::atomic<int> seg_kernel{1};              // warp-staged block kernel for innermost-target layouts
   std::atomic<int> nstage{0};                  // tiled kernel pipeline depth (0 = auto)
   std::atomic<int> blocks_min_elems{1 << 18};  // below this, skip structure analysis
+  std::atomic<int> blocks_min_elems_small_t{1 << 22};  // same, single t <= 8 operator on a density matrix
   std::atomic<int> two_sided{1};               // single-pass U rho U^dagger through shared-memory tiles
   std::atomic<int> ts_ctas{0};                 // CTAs per SM of that kernel (0 = default 2)
   std::atomic<int> seg_mma{1};                 // staged block kernel on the FP64 tensor cores (complex128, t <= 64)

@@ -622,38 +622,39 @@ def test_two_sided_single_pass_kernel(ad, cdtype):
         out = host(ad.apply_operation_matrix(dims, targets, dev(rho), dev(np.asarray(op, dtype=cdtype))))
         assert rel_err(out, ref) < tol, (dims, targets)
 
-    # large enough for the structured paths without touching the tuning knobs
-    check((8, 8, 10), (0,), ops.random_unitary(8, 1), 1)
-    check((8, 8, 10), (1,), ops.displacement_operator(8, 0.4), 2)
-    check((8, 8, 10), (0, 1), ops.beam_splitter(8, 8, 0.6), 3)
-    check((8, 8, 10), (1, 0), ops.beam_splitter(8, 8, 0.6), 4)
-    check((6, 5, 7, 3), (1,), ops.random_unitary(5, 5), 5)
-    check((6, 5, 7, 3), (2, 0), ops.beam_splitter(7, 6, 0.3), 6)
-    # innermost axis IS the target (tensor-core kernel with the transposing load, complex128;
-    # complex64 and ragged runs take the two-pass route)
-    check((8, 8, 8), (2,), ops.random_unitary(8, 21), 21)
-    check((4, 16, 6), (2,), ops.random_unitary(6, 22), 22)
-    check((2, 32, 5), (2,), ops.squeezing_operator(5, 0.2 + 0.2j), 23)
-    check((64, 7), (1,), ops.random_unitary(7, 24), 24)
-    check((3, 24, 8), (2,), ops.random_unitary(8, 25), 25)           # run of 72: ragged wide tiles
-    check((9, 11, 6), (2,), ops.random_unitary(6, 28), 28)
-    # two-mode operators on the innermost modes (wide-tile tensor-core kernel)
-    check((3, 8, 8), (1, 2), ops.beam_splitter(8, 8, 0.4), 29)
-    check((3, 8, 8), (2, 1), ops.beam_splitter(8, 8, 0.4), 30)
-    check((5, 5, 5, 5), (2, 3), ops.beam_splitter(5, 5, 1.1), 31)
-    check((4, 3, 7, 6), (3, 2), ops.beam_splitter(6, 7, 0.8), 32)
-    check((10, 4, 7, 2, 4), (2, 3, 4), np.kron(ops.random_unitary(7, 33), ops.random_unitary(8, 34)), 33)
-    # innermost + far column targets: segmented fiber rows
-    check((8, 3, 8), (2, 0), ops.beam_splitter(8, 8, 0.5), 35)
-    check((8, 3, 8), (0, 2), ops.beam_splitter(8, 8, 0.5), 36)
-    check((4, 9, 2, 6), (3, 0), ops.beam_splitter(6, 4, 0.6), 37)
-    check((5, 2, 7, 5), (0, 3), ops.beam_splitter(5, 5, 0.2), 38)
-    check((3, 2, 5, 4, 3), (4, 0, 3), np.kron(np.kron(ops.random_unitary(3, 39), np.eye(3)), ops.random_unitary(4, 40)), 39)
-    # beam splitters whose sectors pack into several super-blocks (cutoffs 8, 5, 7 x 6)
-    check((3, 8, 8, 4), (1, 2), ops.beam_splitter(8, 8, 0.9), 26)
-    check((5, 5, 5, 5), (3, 1), ops.beam_splitter(5, 5, 0.7), 27)
+    # (thresholds off: every shape below takes the structured / tensor-core paths)
     _lib.set_option("blocks_min_elems", 0)
     try:
+        # large enough for the structured paths without touching the tuning knobs
+        check((8, 8, 10), (0,), ops.random_unitary(8, 1), 1)
+        check((8, 8, 10), (1,), ops.displacement_operator(8, 0.4), 2)
+        check((8, 8, 10), (0, 1), ops.beam_splitter(8, 8, 0.6), 3)
+        check((8, 8, 10), (1, 0), ops.beam_splitter(8, 8, 0.6), 4)
+        check((6, 5, 7, 3), (1,), ops.random_unitary(5, 5), 5)
+        check((6, 5, 7, 3), (2, 0), ops.beam_splitter(7, 6, 0.3), 6)
+        # innermost axis IS the target (tensor-core kernel with the transposing load, complex128;
+        # complex64 and ragged runs take the two-pass route)
+        check((8, 8, 8), (2,), ops.random_unitary(8, 21), 21)
+        check((4, 16, 6), (2,), ops.random_unitary(6, 22), 22)
+        check((2, 32, 5), (2,), ops.squeezing_operator(5, 0.2 + 0.2j), 23)
+        check((64, 7), (1,), ops.random_unitary(7, 24), 24)
+        check((3, 24, 8), (2,), ops.random_unitary(8, 25), 25)           # run of 72: ragged wide tiles
+        check((9, 11, 6), (2,), ops.random_unitary(6, 28), 28)
+        # two-mode operators on the innermost modes (wide-tile tensor-core kernel)
+        check((3, 8, 8), (1, 2), ops.beam_splitter(8, 8, 0.4), 29)
+        check((3, 8, 8), (2, 1), ops.beam_splitter(8, 8, 0.4), 30)
+        check((5, 5, 5, 5), (2, 3), ops.beam_splitter(5, 5, 1.1), 31)
+        check((4, 3, 7, 6), (3, 2), ops.beam_splitter(6, 7, 0.8), 32)
+        check((10, 4, 7, 2, 4), (2, 3, 4), np.kron(ops.random_unitary(7, 33), ops.random_unitary(8, 34)), 33)
+        # innermost + far column targets: segmented fiber rows
+        check((8, 3, 8), (2, 0), ops.beam_splitter(8, 8, 0.5), 35)
+        check((8, 3, 8), (0, 2), ops.beam_splitter(8, 8, 0.5), 36)
+        check((4, 9, 2, 6), (3, 0), ops.beam_splitter(6, 4, 0.6), 37)
+        check((5, 2, 7, 5), (0, 3), ops.beam_splitter(5, 5, 0.2), 38)
+        check((3, 2, 5, 4, 3), (4, 0, 3), np.kron(np.kron(ops.random_unitary(3, 39), np.eye(3)), ops.random_unitary(4, 40)), 39)
+        # beam splitters whose sectors pack into several super-blocks (cutoffs 8, 5, 7 x 6)
+        check((3, 8, 8, 4), (1, 2), ops.beam_splitter(8, 8, 0.9), 26)
+        check((5, 5, 5, 5), (3, 1), ops.beam_splitter(5, 5, 0.7), 27)
         for tg in [(0,), (1,), (0, 1), (1, 0)]:
             t = math.prod((3, 4, 5)[i] for i in tg)
             check((3, 4, 5), tg, ops.random_unitary(t, 7) if t <= 8 else
@@ -665,6 +666,10 @@ def test_two_sided_single_pass_kernel(ad, cdtype):
         check((2, 2, 2, 7), (2, 0), ops.random_unitary(4, 12), 12)
     finally:
         _lib.set_option("blocks_min_elems", 1 << 18)
+    # default thresholds: a single t <= 8 operator on a small rho skips the analysis (two
+    # register-kernel passes), a beam splitter of the same size takes the structured path
+    check((8, 8, 10), (0,), ops.random_unitary(8, 1), 1)
+    check((8, 8, 10), (0, 1), ops.beam_splitter(8, 8, 0.6), 3)
 
 
 def test_dense_tensor_core_kernel(ad):
