@@ -26,10 +26,20 @@ namespace pw {
 // converges to label = smallest column index of the component.
 template <typename V>
 __global__ void __launch_bounds__(256)
-k_build_blocks(const V* __restrict__ op, const uint32_t t, const bool conj_op, const TargetMap tm,
-               BlockDescHeader* __restrict__ hdr, int4* __restrict__ blocks,
-               int64_t* __restrict__ offs, V* __restrict__ vals, int64_t* __restrict__ zero_offs,
+k_build_blocks(const V* __restrict__ op, const uint32_t t, const bool conj0, const TargetMap tm0,
+               const BlockArrays A0, const bool conj1, const TargetMap tm1, const BlockArrays A1,
                const int* __restrict__ skip) {
+  // one CTA per descriptor: gridDim.x = 2 analyses the same operator for two offset maps at once
+  // (row side and conjugated column side of U rho U^dagger)
+  const bool second = blockIdx.x == 1;
+  const bool conj_op = second ? conj1 : conj0;
+  const TargetMap& tm = second ? tm1 : tm0;
+  const BlockArrays& A = second ? A1 : A0;
+  BlockDescHeader* __restrict__ hdr = A.hdr;
+  int4* __restrict__ blocks = A.blocks;
+  int64_t* __restrict__ offs = A.offs;
+  V* __restrict__ vals = (V*)A.vals;
+  int64_t* __restrict__ zero_offs = A.zero_offs;
   extern __shared__ __align__(16) int32_t s_i[];
   int4* s_blk = (int4*)s_i;    // [t] block table (copied out at the end)
   int32_t* lr = s_i + 4 * t;   // [t] row labels
@@ -314,8 +324,7 @@ k_apply_blocks_seg(const V* __restrict__ in, V* __restrict__ out, const SegGeom 
 }
 
 template <typename V>
-static int build_block_desc_t(const V* op, uint32_t t, bool conj_op, const TargetMap& tm,
-                              Scratch* mem, BlockArrays* arr, cudaStream_t s, const int* skip = nullptr) {
+static int alloc_block_desc(uint32_t t, Scratch* mem, BlockArrays* arr, cudaStream_t s) {
   // descriptor storage: header | blocks[t] | offs[2t] | zero_offs[t] | vals[t*t]
   auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
   const size_t b_hdr = 64, b_blk = sizeof(int4) * t, b_off = al(sizeof(int64_t) * 2 * t),
@@ -327,8 +336,26 @@ static int build_block_desc_t(const V* op, uint32_t t, bool conj_op, const Targe
   arr->offs = (int64_t*)(base + b_hdr + b_blk);
   arr->zero_offs = (int64_t*)(base + b_hdr + b_blk + b_off);
   arr->vals = base + b_hdr + b_blk + b_off + b_zero;
-  k_build_blocks<V><<<1, 256, sizeof(int32_t) * 20 * t, s>>>(op, t, conj_op, tm, arr->hdr, arr->blocks,
-                                                           arr->offs, (V*)arr->vals, arr->zero_offs, skip);
+  return PW_OK;
+}
+
+template <typename V>
+static int build_block_desc_t(const V* op, uint32_t t, bool conj_op, const TargetMap& tm,
+                              Scratch* mem, BlockArrays* arr, cudaStream_t s, const int* skip = nullptr) {
+  PW_TRY(alloc_block_desc<V>(t, mem, arr, s));
+  k_build_blocks<V><<<1, 256, sizeof(int32_t) * 20 * t, s>>>(op, t, conj_op, tm, *arr, conj_op, tm, *arr, skip);
+  PW_LAUNCHED();
+  return PW_OK;
+}
+
+// two descriptors of the same operator in ONE launch (two CTAs)
+template <typename V>
+static int build_block_desc_pair_t(const V* op, uint32_t t, bool conj0, const TargetMap& tm0, Scratch* mem0,
+                                   BlockArrays* arr0, bool conj1, const TargetMap& tm1, Scratch* mem1,
+                                   BlockArrays* arr1, cudaStream_t s) {
+  PW_TRY(alloc_block_desc<V>(t, mem0, arr0, s));
+  PW_TRY(alloc_block_desc<V>(t, mem1, arr1, s));
+  k_build_blocks<V><<<2, 256, sizeof(int32_t) * 20 * t, s>>>(op, t, conj0, tm0, *arr0, conj1, tm1, *arr1, nullptr);
   PW_LAUNCHED();
   return PW_OK;
 }
@@ -642,28 +669,38 @@ k_ts_build(const BlockArrays L, const BlockArrays R, const int* __restrict__ oth
   __syncthreads();
   if (!s_handled) return;
   if (s_mma) {
+    // super-block tables: one thread per (super-block, index) row -- block and local row come
+    // from a shared map filled by one thread per block
+    __shared__ short s_map[kTsMaxSb * 8][2];
     V* w = (V*)T.sb_w;
     for (int i = threadIdx.x; i < 2 * kTsMaxSb * 64; i += blockDim.x) w[i] = czero<V>();
     for (int i = threadIdx.x; i < 4 * kTsMaxSb * 8; i += blockDim.x) T.sb_off[i] = 0;
+    for (int i = threadIdx.x; i < kTsMaxSb * 8; i += blockDim.x) s_map[i][0] = -1;
     __syncthreads();
     for (int b = threadIdx.x; b < hl->nblocks; b += blockDim.x) {
-      const int4 hk = L.blocks[b], hq = R.blocks[b];
       const int2 sp = T.sb_blk[b];
-      const int n = hk.x;
+      for (int a = 0; a < s_bn[b]; ++a) {
+        s_map[sp.x * 8 + sp.y + a][0] = (short)b;
+        s_map[sp.x * 8 + sp.y + a][1] = (short)a;
+      }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < kTsMaxSb * 8; e += blockDim.x) {
+      const int b = s_map[e][0], a = s_map[e][1];
+      if (b < 0) continue;
+      const int4 hk = L.blocks[b], hq = R.blocks[b];
+      const int n = hk.x, c0 = (e & 7) - a;  // first index of the block inside its super-block
       const int64_t* ko = L.offs + hk.z;
       const int64_t* lo = R.offs + hq.z;
-      const V* vl = (const V*)L.vals + hk.w;
-      const V* vr = (const V*)R.vals + hq.w;
-      for (int a = 0; a < n; ++a) {
-        const int e = sp.x * 8 + sp.y + a;
-        T.sb_off[0 * kTsMaxSb * 8 + e] = ko[a];
-        T.sb_off[1 * kTsMaxSb * 8 + e] = lo[a];
-        T.sb_off[2 * kTsMaxSb * 8 + e] = ko[n + a];
-        T.sb_off[3 * kTsMaxSb * 8 + e] = lo[n + a];
-        for (int c = 0; c < n; ++c) {
-          w[(sp.x * 8 + sp.y + a) * 8 + sp.y + c] = vl[a * n + c];
-          w[((kTsMaxSb + sp.x) * 8 + sp.y + a) * 8 + sp.y + c] = vr[a * n + c];
-        }
+      const V* vl = (const V*)L.vals + hk.w + a * n;
+      const V* vr = (const V*)R.vals + hq.w + a * n;
+      T.sb_off[0 * kTsMaxSb * 8 + e] = ko[a];
+      T.sb_off[1 * kTsMaxSb * 8 + e] = lo[a];
+      T.sb_off[2 * kTsMaxSb * 8 + e] = ko[n + a];
+      T.sb_off[3 * kTsMaxSb * 8 + e] = lo[n + a];
+      for (int c = 0; c < n; ++c) {
+        w[e * 8 + c0 + c] = vl[c];
+        w[(kTsMaxSb * 8 + e) * 8 + c0 + c] = vr[c];
       }
     }
     return;
@@ -1032,6 +1069,34 @@ __device__ __forceinline__ void two_sided_mma_body(const double2* __restrict__ i
     __syncthreads();
     // stage 2: row i of the tile, streamed to HBM
     const int64_t* sb = s_base + cur * 32;
+    if (inner) {
+      // innermost column target: the TRANSPOSED product (operands swapped: A = X^T from the
+      // tile, B = W^T -- the very same register values) leaves a lane with two ADJACENT output
+      // positions of ONE fiber: a 256-bit store per lane, a full 128-byte line per quarter warp
+      for (int i = warp; i < nK; i += kTsWarps) {
+        const int64_t ro = rout[K * 8 + i] + 2 * tig;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int f = 8 * nt + gid;
+          V x0 = make_double2(0.0, 0.0), x1 = x0;
+          if (tig < nL) x0 = tile[i * 256 + f * 8 + (tig ^ ts_sigma(f, i))];
+          if (4 + tig < nL) x1 = tile[i * 256 + f * 8 + ((4 + tig) ^ ts_sigma(f, i))];
+          double re0 = 0.0, re1 = 0.0, im0 = 0.0, im1 = 0.0;
+          dmma8x8x4(re0, re1, x0.x, r0.x);
+          dmma8x8x4(im0, im1, x0.x, r0.y);
+          dmma8x8x4(re0, re1, -x0.y, r0.y);
+          dmma8x8x4(im0, im1, x0.y, r0.x);
+          dmma8x8x4(re0, re1, x1.x, r1.x);
+          dmma8x8x4(im0, im1, x1.x, r1.y);
+          dmma8x8x4(re0, re1, -x1.y, r1.y);
+          dmma8x8x4(im0, im1, x1.y, r1.x);
+          const int64_t b0 = sb[f];
+          V* dst = out + b0 + ro;
+          st_pair(dst, dst + 1, make_double2(re0, im0), make_double2(re1, im1), b0 >= 0 && 2 * tig < nL,
+                  b0 >= 0 && 2 * tig + 1 < nL);
+        }
+      }
+    } else
     for (int i = warp; i < nK; i += kTsWarps) {
       const V* row = tile + i * nL * 32;
       const int64_t ro = rout[K * 8 + i] + cout[L * 8 + gid];
@@ -1276,9 +1341,9 @@ static int launch_two_sided_t(const V* rho, V* out, const V* op, const FiberMap&
                               const TargetMap& rows, const TargetMap& cols, const int* other,
                               const int inner, const TnSeg& seg, const TargetMap& cols_pos,
                               TwoSided* ts, cudaStream_t s) {
-  PW_TRY(build_block_desc_t<V>(op, rows.t, false, rows, &ts->memL, &ts->L, s));
-  // innermost column targets: the column side is addressed by POSITION inside the fiber row
-  PW_TRY(build_block_desc_t<V>(op, cols.t, true, inner ? cols_pos : cols, &ts->memR, &ts->R, s));
+  // (innermost column targets: the column side is addressed by POSITION inside the fiber row)
+  PW_TRY(build_block_desc_pair_t<V>(op, rows.t, false, rows, &ts->memL, &ts->L, true, inner ? cols_pos : cols,
+                                    &ts->memR, &ts->R, s));
   const size_t t = rows.t, tt = t * t;
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const size_t b_flags = 256, b_groups = al(sizeof(int4) * 2 * tt), b_pairs = al(sizeof(int4) * tt),
