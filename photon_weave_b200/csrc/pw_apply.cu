@@ -327,6 +327,67 @@ __global__ void k_target_offsets(const TargetMap tm, int64_t* toff) {
   if (j < tm.t) toff[j] = tm.offset(j);
 }
 
+// ---------------------------------------------------------------------------------
+// CONTIGUOUS fibers on the FP64 tensor cores (complex128, one 5..8-level target on the
+// innermost axis).  The transposed product Y^T = X^T W^T makes the FIBERS the M dimension of
+// mma.sync.m8n8k4: lane (gid, tig) of an A fragment needs X[fiber gid][input tig] -- a plain
+// 128-bit global load, the eight lanes of a quarter warp reading two 64-byte pieces -- and a lane
+// of the C fragment holds two ADJACENT outputs of one fiber: one 256-bit store.  No shared
+// memory, no barrier, 8 loads + 32 DMMAs + 4 stores per lane and 32 fibers; the operator sits in
+// two registers per lane.  (The warp-transposing register kernel needs 36 broadcast shared
+// loads per fiber and is sensitive to the SM clock: 11.7 ms alone, 14.1 ms inside the
+// power-capped bench layer on the 34.8 GB vector.)
+// ---------------------------------------------------------------------------------
+template <bool CONJ>
+__global__ void __launch_bounds__(256)
+k_apply_contig_mma(const double2* __restrict__ in, double2* __restrict__ out, const double2* __restrict__ op,
+                   const int t, const uint64_t nfib, const int* __restrict__ skip) {
+  using V = double2;
+  if (skip && *skip) return;
+  const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+  const V zero = make_double2(0.0, 0.0);
+  // B = W^T fragments: lane (k = tig, n = gid) holds W[gid][tig] and W[gid][4 + tig]
+  V w0 = zero, w1 = zero;
+  if (gid < t) {
+    if (tig < t) w0 = op[gid * t + tig];
+    if (4 + tig < t) w1 = op[gid * t + 4 + tig];
+    if (CONJ) { w0.y = -w0.y; w1.y = -w1.y; }
+  }
+  const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+  const uint64_t ngroups = (nfib + 31) / 32;
+  for (uint64_t g = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < ngroups; g += nwarps) {
+    V x0[4], x1[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const uint64_t f = g * 32 + 8 * m + gid;
+      const V* src = in + f * t;
+      x0[m] = (f < nfib && tig < t) ? __ldcg(src + tig) : zero;
+      x1[m] = (f < nfib && 4 + tig < t) ? __ldcg(src + 4 + tig) : zero;
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      double re0 = 0.0, re1 = 0.0, im0 = 0.0, im1 = 0.0;
+      asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(re0), "+d"(re1) : "d"(x0[m].x), "d"(w0.x));
+      asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(im0), "+d"(im1) : "d"(x0[m].x), "d"(w0.y));
+      asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(re0), "+d"(re1) : "d"(-x0[m].y), "d"(w0.y));
+      asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(im0), "+d"(im1) : "d"(x0[m].y), "d"(w0.x));
+      asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(re0), "+d"(re1) : "d"(x1[m].x), "d"(w1.x));
+      asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(im0), "+d"(im1) : "d"(x1[m].x), "d"(w1.y));
+      asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(re0), "+d"(re1) : "d"(-x1[m].y), "d"(w1.y));
+      asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(im0), "+d"(im1) : "d"(x1[m].y), "d"(w1.x));
+      const uint64_t f = g * 32 + 8 * m + gid;
+      V* dst = out + f * t + 2 * tig;
+      const bool ok0 = f < nfib && 2 * tig < t, ok1 = f < nfib && 2 * tig + 1 < t;
+      if (ok0 && ok1 && (reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
+        asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(dst), "d"(re0), "d"(im0), "d"(re1), "d"(im1) : "memory");
+      } else {
+        if (ok0) __stcg(dst, make_double2(re0, im0));
+        if (ok1) __stcg(dst + 1, make_double2(re1, im1));
+      }
+    }
+  }
+}
+
 template <typename V, int T>
 static int launch_small(const V* in, V* out, const V* op, const Plan& p, bool conj_op,
                         bool acc, cudaStream_t s, const int* skip) {
@@ -336,6 +397,14 @@ static int launch_small(const V* in, V* out, const V* op, const Plan& p, bool co
   // array-of-contiguous-fibers layout: the warp-transposing variant keeps loads coalesced
   if (!acc && T >= 2 && p.fm.ng == 1 && p.fm.gstride[0] == (int64_t)T && p.N == p.fm.nfib * T &&
       p.fm.nfib >= 4096 && options().contig_kernel.load(std::memory_order_relaxed)) {
+    if (sizeof(V) == 16 && T >= 5 && p.tm.nt == 1 && in != out &&
+        options().contig_mma.load(std::memory_order_relaxed)) {
+      const int g3 = grid_for((p.fm.nfib + 31) / 32 * 32, block, 8);
+      if (conj_op) k_apply_contig_mma<true><<<g3, block, 0, s>>>((const double2*)in, (double2*)out, (const double2*)op, T, p.fm.nfib, skip);
+      else         k_apply_contig_mma<false><<<g3, block, 0, s>>>((const double2*)in, (double2*)out, (const double2*)op, T, p.fm.nfib, skip);
+      PW_LAUNCHED();
+      return PW_OK;
+    }
     const int g2 = grid_for((p.fm.nfib + 31) / 32 * 32, block, 3);
     if (conj_op) k_apply_small_contig<V, T, true><<<g2, block, 0, s>>>(in, out, op, p.fm.nfib, p.tm, skip);
     else         k_apply_small_contig<V, T, false><<<g2, block, 0, s>>>(in, out, op, p.fm.nfib, p.tm, skip);

@@ -759,3 +759,26 @@ def test_staged_block_kernel_on_tensor_cores(ad):
             assert rel_err(out, ref) < tol, (dims, targets)
     finally:
         _lib.set_option("blocks_min_elems", 1 << 18)
+
+
+def test_contiguous_fibers_on_tensor_cores(ad):
+    """One 5..8-level complex128 operator on the innermost axis (contiguous fibers): the
+    direct-from-global tensor-core kernel (transposed product, 256-bit stores), including odd t
+    (unaligned pairs), ragged fiber counts and the conjugated column pass of a density matrix."""
+    tol = TOL[np.complex128]
+    for seed, (dims, d) in enumerate([((5000, 6), 6), ((4101, 5), 5), ((4099, 7), 7), ((70, 61, 8), 8),
+                                      ((3, 1500, 6), 6)]):
+        N = math.prod(dims)
+        psi = ops.random_state(N, 80 + seed)
+        op = ops.random_unitary(d, 90 + seed) * (1.0 + 0.1 * seed)
+        tg = (len(dims) - 1,)
+        ref = oad.apply_operation_vector(dims, tg, psi, op, True)
+        out = host(ad.apply_operation_vector(dims, tg, dev(psi), dev(op)))
+        assert rel_err(out, ref) < tol, dims
+    for seed, (dims, d) in enumerate([((70, 8), 8), ((90, 6), 6), ((75, 7), 7)]):
+        N = math.prod(dims)
+        rho = ops.random_density(N, 95 + seed)
+        op = ops.random_unitary(d, 97 + seed)
+        ref = oad.apply_operation_matrix(dims, (1,), rho, op, True)
+        out = host(ad.apply_operation_matrix(dims, (1,), dev(rho), dev(op)))
+        assert rel_err(out, ref) < tol, dims
