@@ -65,7 +65,6 @@ Options& options() {
     env("PW_DENSE_MMA", p->dense_mma);
     env("PW_SEG_FPW", p->seg_fpw);
     env("PW_SEG_MMA", p->seg_mma);
-    env("PW_BLOCKS_MMA", p->blocks_mma);
     return p;
   }();
   return *o;
@@ -96,7 +95,6 @@ extern "C" int pw_set_option(const char* name, int value) {
   else if (!std::strcmp(name, "dense_mma")) o.dense_mma.store(value);
   else if (!std::strcmp(name, "seg_fpw")) o.seg_fpw.store(value);
   else if (!std::strcmp(name, "seg_mma")) o.seg_mma.store(value);
-  else if (!std::strcmp(name, "blocks_mma")) o.blocks_mma.store(value);
   else return PW_ERR_INVALID;
   return PW_OK;
 }

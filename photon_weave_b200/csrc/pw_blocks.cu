@@ -189,10 +189,9 @@ constexpr uint32_t kDescSmemCap = 24 * 1024;
 
 template <typename V>
 __global__ void __launch_bounds__(256, 3)
-k_apply_blocks(const V* __restrict__ in, V* __restrict__ out, const FiberMap fm, const BlockArrays A,
-               const int* __restrict__ mma_taken) {
+k_apply_blocks(const V* __restrict__ in, V* __restrict__ out, const FiberMap fm, const BlockArrays A) {
   extern __shared__ __align__(16) unsigned char s_desc[];
-  if (!A.hdr->usable || (mma_taken != nullptr && *mma_taken != 0)) return;
+  if (!A.hdr->usable) return;
   const DescView<V> dv = desc_view<V>(A, s_desc, kDescSmemCap);
   const bool scalar_blocks = A.hdr->maxn == 1;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -369,19 +368,14 @@ int build_block_desc(const void* op, uint32_t t, bool conj_op, const TargetMap& 
   return PW_ERR_INVALID;
 }
 
-static int enqueue_blocks_mma(const void* in, void* out, const FiberMap& fm, uint32_t t, BlockDesc* d,
-                              int dtype, cudaStream_t s, const int** mma_taken);
-
 template <typename V>
 static int launch_blocks_t(const V* in, V* out, const V* op, const Plan& p, bool conj_op,
                            BlockDesc* d, cudaStream_t s) {
   PW_TRY(build_block_desc_t<V>(op, p.tm.t, conj_op, p.tm, &d->mem, &d->arr, s));
   d->hdr = d->arr.hdr;
   const BlockArrays& A = d->arr;
-  const int* mma_taken = nullptr;
-  PW_TRY(enqueue_blocks_mma(in, out, p.fm, p.tm.t, d, sizeof(V) == 16 ? PW_C128 : PW_C64, s, &mma_taken));
   const int grid = grid_for(p.fm.nfib, 256, 3);
-  k_apply_blocks<V><<<grid, 256, kDescSmemCap, s>>>(in, out, p.fm, A, mma_taken);
+  k_apply_blocks<V><<<grid, 256, kDescSmemCap, s>>>(in, out, p.fm, A);
   PW_LAUNCHED();
   g_paths[4].fetch_add(1, std::memory_order_relaxed);
   return PW_OK;
@@ -1503,19 +1497,16 @@ struct SegSb {
   int2* sb_blk;    // [t] per block: (super-block, first index)
   int* pos;        // [2][kSgMaxSb][8] positions inside the fiber row: inputs, outputs
   double2* w;      // [kSgMaxSb][8][8] zero-padded block-diagonal values, column c of row r at (c ^ 4 (r & 1))
-  int64_t* off64;  // [2][kSgMaxSb][8] the same as element offsets (direct kernel: global strides)
 };
 
 __global__ void __launch_bounds__(128)
-k_seg_sb_build(const BlockArrays A, const SegSb S, const int staged, const int max_sb) {
+k_seg_sb_build(const BlockArrays A, const SegSb S) {
   __shared__ int s_bn[kBlockMaxT];
   __shared__ int s_ok, s_square;
   const BlockDescHeader* h = A.hdr;
   if (threadIdx.x == 0) s_square = 1;
   __syncthreads();
-  // staged kernel: in place (seg_handled); direct kernel: out of place, `usable` is enough
-  const int handled = staged ? h->seg_handled : h->usable;
-  const int m = handled ? min(h->nblocks, (int)kBlockMaxT) : 0;
+  const int m = h->seg_handled ? min(h->nblocks, (int)kBlockMaxT) : 0;
   for (int b = threadIdx.x; b < m; b += blockDim.x) {
     const int4 x = A.blocks[b];
     s_bn[b] = x.x;
@@ -1524,7 +1515,7 @@ k_seg_sb_build(const BlockArrays A, const SegSb S, const int staged, const int m
   __syncthreads();
   if (threadIdx.x == 0) {
     // all 1 x 1 (diagonal / permutation) operators stay on the scalar kernel
-    int ok = (handled && h->nzero == 0 && h->maxn >= 2 && h->maxn <= 8 && s_square) ? 1 : 0;
+    int ok = (h->seg_handled && h->nzero == 0 && h->maxn >= 2 && h->maxn <= 8 && s_square) ? 1 : 0;
     int nsb = 0, fill[kSgMaxSb];
     for (int sz = 8; sz >= 1 && ok; --sz)
       for (int b = 0; b < m && ok; ++b) {
@@ -1532,7 +1523,7 @@ k_seg_sb_build(const BlockArrays A, const SegSb S, const int staged, const int m
         int q = 0;
         while (q < nsb && fill[q] + sz > 8) ++q;
         if (q == nsb) {
-          if (nsb == max_sb) { ok = 0; break; }
+          if (nsb == kSgMaxSb) { ok = 0; break; }
           fill[nsb++] = 0;
         }
         S.sb_blk[b] = make_int2(q, fill[q]);
@@ -1546,7 +1537,7 @@ k_seg_sb_build(const BlockArrays A, const SegSb S, const int staged, const int m
   __syncthreads();
   if (!s_ok) return;
   for (int i = threadIdx.x; i < kSgMaxSb * 64; i += blockDim.x) S.w[i] = make_double2(0.0, 0.0);
-  for (int i = threadIdx.x; i < 2 * kSgMaxSb * 8; i += blockDim.x) { S.pos[i] = 0; S.off64[i] = 0; }
+  for (int i = threadIdx.x; i < 2 * kSgMaxSb * 8; i += blockDim.x) S.pos[i] = 0;
   __syncthreads();
   for (int b = threadIdx.x; b < m; b += blockDim.x) {
     const int4 hb = A.blocks[b];
@@ -1558,8 +1549,6 @@ k_seg_sb_build(const BlockArrays A, const SegSb S, const int staged, const int m
       const int r = sp.y + a;
       S.pos[sp.x * 8 + r] = (int)bo[a];
       S.pos[(kSgMaxSb + sp.x) * 8 + r] = (int)bo[n + a];
-      S.off64[sp.x * 8 + r] = bo[a];
-      S.off64[(kSgMaxSb + sp.x) * 8 + r] = bo[n + a];
       for (int c = 0; c < n; ++c) S.w[sp.x * 64 + r * 8 + ((sp.y + c) ^ ((r & 1) << 2))] = v[a * n + c];
     }
   }
@@ -1721,9 +1710,8 @@ static int enqueue_seg_mma(const void* in, void* out, const SegGeom& g, BlockDes
     return PW_OK;
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const size_t b_flags = 256, b_n = al(sizeof(int) * kSgMaxSb), b_blk = al(sizeof(int2) * g.t),
-               b_pos = al(sizeof(int) * 2 * kSgMaxSb * 8), b_w = al(sizeof(double2) * kSgMaxSb * 64),
-               b_o64 = al(sizeof(int64_t) * 2 * kSgMaxSb * 8);
-  PW_TRY(d->mem2.alloc(b_flags + b_n + b_blk + b_pos + b_w + b_o64, s));
+               b_pos = al(sizeof(int) * 2 * kSgMaxSb * 8), b_w = al(sizeof(double2) * kSgMaxSb * 64);
+  PW_TRY(d->mem2.alloc(b_flags + b_n + b_blk + b_pos + b_w, s));
   char* base = (char*)d->mem2.p;
   SegSb S;
   S.flags = (int*)base;
@@ -1731,8 +1719,7 @@ static int enqueue_seg_mma(const void* in, void* out, const SegGeom& g, BlockDes
   S.sb_blk = (int2*)(base + b_flags + b_n);
   S.pos = (int*)(base + b_flags + b_n + b_blk);
   S.w = (double2*)(base + b_flags + b_n + b_blk + b_pos);
-  S.off64 = (int64_t*)(base + b_flags + b_n + b_blk + b_pos + b_w);
-  k_seg_sb_build<<<1, 128, 0, s>>>(d->arr, S, 1, kSgMaxSb);
+  k_seg_sb_build<<<1, 128, 0, s>>>(d->arr, S);
   PW_LAUNCHED();
   const int tp = ((int)g.t + 7) & ~7;
   const int kSgFib = seg_mma_fibers((int)g.t);
@@ -1751,141 +1738,6 @@ static int enqueue_seg_mma(const void* in, void* out, const SegGeom& g, BlockDes
   uint64_t grid = (uint64_t)kNumSMs * ctas;
   if (grid > units) grid = units;
   k_apply_blocks_seg_mma<<<(unsigned)grid, nwarps * 32, smem, s>>>((const double2*)in, (double2*)out, g, S, kSgFib);
-  PW_LAUNCHED();
-  *mma_taken = S.flags;
-  return PW_OK;
-}
-
-// ---- direct block kernel on the FP64 tensor cores ----------------------------------------------
-// The block-structured apply for layouts with adjacent fibers (untouched innermost axis): tiles of
-// (8 nsb slots) x (64 adjacent fibers), cp.async double buffered, XOR swizzled like the dense
-// kernel; a warp item is (super-block) x (32 fibers): 8 shared loads, 32 DMMAs and four 256-bit
-// stores straight from the accumulator fragments (out of place: no write-back to the tile).
-// k_apply_blocks (one fiber per thread on the FMA pipe) reaches 89-91 % of the HBM roof for the
-// beam splitter on the 34.8 GB vector; its per-fiber instruction stream is the limit.
-constexpr int kDbFib = 64;
-
-__global__ void __launch_bounds__(512, 1)
-k_apply_blocks_mma(const double2* __restrict__ in, double2* __restrict__ out, const FiberMap fm,
-                   const SegSb S) {
-  using V = double2;
-  if (!S.flags[0]) return;
-  extern __shared__ __align__(16) unsigned char s_raw[];
-  const int nsb = S.flags[1];
-  V* s_w = (V*)s_raw;                                        // [kSgMaxSb][64]
-  int64_t* s_off = (int64_t*)(s_w + kSgMaxSb * 64);          // [2][kSgMaxSb][8]: in, out
-  int64_t* s_base = s_off + 2 * kSgMaxSb * 8;                // [2][kDbFib]
-  int* s_n = (int*)(s_base + 2 * kDbFib);                    // [kSgMaxSb]
-  V* tile0 = (V*)(s_n + kSgMaxSb);                           // [2][8 nsb][kDbFib]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int gid = lane >> 2, tig = lane & 3;
-  for (int i = threadIdx.x; i < kSgMaxSb * 64; i += blockDim.x) s_w[i] = S.w[i];
-  for (int i = threadIdx.x; i < 2 * kSgMaxSb * 8; i += blockDim.x) s_off[i] = S.off64[i];
-  if (threadIdx.x < kSgMaxSb) s_n[threadIdx.x] = threadIdx.x < nsb ? S.sb_n[threadIdx.x] : 0;
-  __syncthreads();
-  const int nslots = 8 * nsb;
-  const uint64_t units = (fm.nfib + kDbFib - 1) / kDbFib;
-
-  auto issue = [&](uint64_t u, int buf) {
-    if (u < units) {
-      V* tile = tile0 + (size_t)buf * nslots * kDbFib;
-      const uint64_t fa = u * kDbFib + lane, fb = fa + 32;
-      const int64_t ba = fa < fm.nfib ? fm.base(fa) : -1, bb = fb < fm.nfib ? fm.base(fb) : -1;
-      if (warp == 0) { s_base[buf * kDbFib + lane] = ba; s_base[buf * kDbFib + 32 + lane] = bb; }
-      for (int sl = warp; sl < nslots; sl += nwarps) {
-        if ((sl & 7) >= s_n[sl >> 3]) continue;
-        const int sw = 2 * (sl & 3);
-        const int64_t o = s_off[sl];
-        if (ba >= 0) cp_async16(tile + sl * kDbFib + (lane ^ sw), in + ba + o);
-        if (bb >= 0) cp_async16(tile + sl * kDbFib + 32 + (lane ^ sw), in + bb + o);
-      }
-    }
-    cp_async_commit();
-  };
-
-  const int fsw = (gid & 1) << 2;
-  const V zero = make_double2(0.0, 0.0);
-  uint64_t u = blockIdx.x;
-  int cur = 0;
-  issue(u, 0);
-  for (; u < units; u += gridDim.x) {
-    const V* tile = tile0 + (size_t)cur * nslots * kDbFib;
-    issue(u + gridDim.x, cur ^ 1);
-    cp_async_wait<1>();
-    __syncthreads();
-    const int64_t* sb = s_base + cur * kDbFib;
-    for (int it = warp; it < 2 * nsb; it += nwarps) {
-      const int sbi = it >> 1, h = it & 1;
-      const int n = s_n[sbi];
-      const V w0 = s_w[sbi * 64 + gid * 8 + (tig ^ fsw)], w1 = s_w[sbi * 64 + gid * 8 + ((4 + tig) ^ fsw)];
-      // slot 8 sbi + tig (and + 4): swizzle 2 (slot & 3) = 2 tig
-      const V* xc = tile + (8 * sbi + tig) * kDbFib + 32 * h + (gid ^ (2 * tig));
-      V x0[4], x1[4], y0[4], y1[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        x0[q] = tig < n ? xc[8 * q] : zero;
-        x1[q] = 4 + tig < n ? xc[4 * kDbFib + 8 * q] : zero;
-      }
-      cmma_batch<4, true>(&w0, &w1, x0, x1, y0, y1);
-      if (gid < n) {
-        const int64_t ro = s_off[(kSgMaxSb + sbi) * 8 + gid];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int f = 32 * h + 8 * q + 2 * tig;
-          const int64_t b0 = sb[f], b1 = sb[f + 1];
-          st_pair(out + b0 + ro, out + b1 + ro, y0[q], y1[q], b0 >= 0, b1 >= 0);
-        }
-      }
-    }
-    __syncthreads();
-    cur ^= 1;
-  }
-  cp_async_wait<0>();
-}
-
-// Enqueues the packing and the direct tensor-core kernel for a descriptor built by
-// launch_blocks; *mma_taken: device flag the scalar kernel must honour.
-static int enqueue_blocks_mma(const void* in, void* out, const FiberMap& fm, uint32_t t, BlockDesc* d,
-                              int dtype, cudaStream_t s, const int** mma_taken) {
-  *mma_taken = nullptr;
-  if (dtype != PW_C128 || t > 64 || t < 4 || fm.ng == 0 || fm.gstride[fm.ng - 1] != 1 ||
-      fm.gsize[fm.ng - 1] < 16 || !options().blocks_mma.load(std::memory_order_relaxed))
-    return PW_OK;
-  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  const size_t b_flags = 256, b_n = al(sizeof(int) * kSgMaxSb), b_blk = al(sizeof(int2) * t),
-               b_pos = al(sizeof(int) * 2 * kSgMaxSb * 8), b_w = al(sizeof(double2) * kSgMaxSb * 64),
-               b_o64 = al(sizeof(int64_t) * 2 * kSgMaxSb * 8);
-  PW_TRY(d->mem2.alloc(b_flags + b_n + b_blk + b_pos + b_w + b_o64, s));
-  char* base = (char*)d->mem2.p;
-  SegSb S;
-  S.flags = (int*)base;
-  S.sb_n = (int*)(base + b_flags);
-  S.sb_blk = (int2*)(base + b_flags + b_n);
-  S.pos = (int*)(base + b_flags + b_n + b_blk);
-  S.w = (double2*)(base + b_flags + b_n + b_blk + b_pos);
-  S.off64 = (int64_t*)(base + b_flags + b_n + b_blk + b_pos + b_w);
-  // super-blocks the tiles have room for: one more than a perfect packing (photon-number sectors
-  // pack perfectly); operators that need more stay on the scalar kernel
-  int max_sb = ((int)t + 7) / 8 + 1;
-  if (max_sb > 11) max_sb = 11;
-  k_seg_sb_build<<<1, 128, 0, s>>>(d->arr, S, 0, max_sb);
-  PW_LAUNCHED();
-  const size_t smem = sizeof(double2) * kSgMaxSb * 64 + sizeof(int64_t) * (2 * kSgMaxSb * 8 + 2 * kDbFib) +
-                      sizeof(int) * kSgMaxSb + sizeof(double2) * (size_t)2 * 8 * max_sb * kDbFib;
-  if (smem > 200 * 1024) return PW_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PW_CUDA(cudaFuncSetAttribute(k_apply_blocks_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
-  int nwarps = 2 * (((int)t + 7) / 8);
-  if (nwarps < 4) nwarps = 4;
-  if (nwarps > 16) nwarps = 16;
-  const int ctas = (smem + 1024) * 2 <= 227 * 1024 ? 2 : 1;
-  const uint64_t units = (fm.nfib + kDbFib - 1) / kDbFib;
-  uint64_t grid = (uint64_t)kNumSMs * ctas;
-  if (grid > units) grid = units;
-  k_apply_blocks_mma<<<(unsigned)grid, nwarps * 32, smem, s>>>((const double2*)in, (double2*)out, fm, S);
   PW_LAUNCHED();
   *mma_taken = S.flags;
   return PW_OK;

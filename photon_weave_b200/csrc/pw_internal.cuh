@@ -186,7 +186,6 @@ struct Options {
   std::atomic<int> blocks_min_elems_small_t{1 << 22};  // same, single t <= 8 operator on a density matrix
   std::atomic<int> two_sided{1};               // single-pass U rho U^dagger through shared-memory tiles
   std::atomic<int> ts_ctas{0};                 // CTAs per SM of that kernel (0 = default 2)
-  std::atomic<int> blocks_mma{0};              // direct block kernel on the FP64 tensor cores (complex128, t <= 64)
   std::atomic<int> seg_mma{1};                 // staged block kernel on the FP64 tensor cores (complex128, t <= 64)
   std::atomic<int> seg_fpw{0};                 // staged block kernel: fibers per warp stage (0 = auto; 32, 16, 8)
   std::atomic<int> dense_mma{1};               // dense complex128 operators, 8 < t <= 64: FP64 tensor-core kernel
