@@ -56,6 +56,7 @@ Options& options() {
     env("PW_FUSE_PAIRS", p->fuse_pairs);
     env("PW_CONTIG_KERNEL", p->contig_kernel);
     env("PW_CONTIG_MMA", p->contig_mma);
+    env("PW_DIAG_KERNEL", p->diag_kernel);
     env("PW_SMALL_R", p->small_r);
     env("PW_MAT_SUPER_SINGLE", p->mat_super_single);
     env("PW_TWO_SIDED", p->two_sided);
@@ -88,6 +89,7 @@ extern "C" int pw_set_option(const char* name, int value) {
   else if (!std::strcmp(name, "mat_super_single")) o.mat_super_single.store(value);
   else if (!std::strcmp(name, "blocks_min_elems_small_t")) o.blocks_min_elems_small_t.store(value);
   else if (!std::strcmp(name, "contig_mma")) o.contig_mma.store(value);
+  else if (!std::strcmp(name, "diag_kernel")) o.diag_kernel.store(value);
   else if (!std::strcmp(name, "two_sided")) o.two_sided.store(value);
   else if (!std::strcmp(name, "ts_ctas")) o.ts_ctas.store(value);
   else if (!std::strcmp(name, "ts_mma")) o.ts_mma.store(value);

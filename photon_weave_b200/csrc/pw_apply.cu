@@ -505,6 +505,113 @@ static uint64_t matrix_min_elems(int K, uint64_t t) {
 //   t <= 128, large, in != out  block-structured attempt, then a fallback that exits on
 //                               the device when the block kernel took the operator
 //   fallback                    TMA-tiled CSR kernel if eligible, else the generic kernel
+// ---------------------------------------------------------------------------------
+// Diagonal operators (phase shifts, Kerr phases, ...): out[i] = O[j, j] in[i] with j read off the
+// digits of i -- a pure streaming pass, fully coalesced WHATEVER the target axes are (the
+// register kernel walks fibers and loses 5-20 % on short untouched inner runs).  The operator
+// lives on the device, so a one-warp kernel tests it and the streaming kernel exits when it is
+// not diagonal; the regular path then runs with the same flag as its skip flag.
+// ---------------------------------------------------------------------------------
+template <typename V>
+__global__ void k_diag_check(const V* __restrict__ op, const uint32_t t, int* __restrict__ flag) {
+  int ok = 1;
+  for (uint32_t e = threadIdx.x; e < t * t; e += 32) {
+    const V v = op[e];
+    if (e / t != e % t && (v.x != 0 || v.y != 0)) ok = 0;
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  if (threadIdx.x == 0) *flag = ok;
+}
+
+// two adjacent elements with ONE access: 256-bit for complex128 (sm_100 LDG/STG.E.256), 128-bit
+// for complex64 (two separate 16-byte accesses would fetch every sector twice from L2)
+__device__ __forceinline__ void ld_pair(const double2* p, double2& a, double2& b) {
+  asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+}
+__device__ __forceinline__ void st_pair2(double2* p, const double2 a, const double2 b) {
+  asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
+}
+__device__ __forceinline__ void ld_pair(const float2* p, float2& a, float2& b) {
+  const float4 v = __ldcg(reinterpret_cast<const float4*>(p));
+  a = make_float2(v.x, v.y);
+  b = make_float2(v.z, v.w);
+}
+__device__ __forceinline__ void st_pair2(float2* p, const float2 a, const float2 b) {
+  __stcg(reinterpret_cast<float4*>(p), make_float4(a.x, a.y, b.x, b.y));
+}
+
+// 32-bit indices (N < 2^32) keep the digit arithmetic cheap; PAIR: every target stride is even, so
+// elements 2 i and 2 i + 1 share their digits and a thread moves them with ONE 2 x 16-byte access
+// pair (complex128: 256-bit).
+template <typename V, bool CONJ, bool PAIR>
+__global__ void __launch_bounds__(256)
+k_apply_diag(const V* __restrict__ in, V* __restrict__ out, const V* __restrict__ op, const uint32_t N,
+             const TargetMap tm, const int* __restrict__ flag) {
+  if (!*flag) return;
+  __shared__ V s_d[8];
+  if (threadIdx.x < tm.t) {
+    V v = op[threadIdx.x * (tm.t + 1)];
+    if (CONJ) v.y = -v.y;
+    s_d[threadIdx.x] = v;
+  }
+  __syncthreads();
+  const int nt = tm.nt;
+  const uint32_t ts0 = (uint32_t)tm.tstride[0], td0 = tm.tdim[0];  // (one target: registers only)
+  const uint32_t step = PAIR ? 2 : 1;
+  const uint32_t stride = gridDim.x * blockDim.x * step;
+  // (i + stride may wrap for N close to 2^32: the loop condition checks the wrap)
+  for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) * step; i < N; ) {
+    uint32_t j = (i / ts0) % td0;
+#pragma unroll 1
+    for (int k = 1; k < nt; ++k) j = j * tm.tdim[k] + (i / (uint32_t)tm.tstride[k]) % tm.tdim[k];
+    const V dgl = s_d[j];
+    if (PAIR) {
+      V x0, x1, y0, y1;
+      ld_pair(in + i, x0, x1);
+      y0.x = dgl.x * x0.x - dgl.y * x0.y; y0.y = dgl.x * x0.y + dgl.y * x0.x;
+      y1.x = dgl.x * x1.x - dgl.y * x1.y; y1.y = dgl.x * x1.y + dgl.y * x1.x;
+      st_pair2(out + i, y0, y1);
+    } else {
+      const V x = __ldcg(in + i);
+      V y;
+      y.x = dgl.x * x.x - dgl.y * x.y; y.y = dgl.x * x.y + dgl.y * x.x;
+      __stcg(out + i, y);
+    }
+    const uint32_t nxt = i + stride;
+    if (nxt < i) break;
+    i = nxt;
+  }
+}
+
+template <typename V>
+static int try_diag(const V* in, V* out, const V* op, const Plan& p, bool conj_op, cudaStream_t s,
+                    Scratch* flag_mem, const int** flag) {
+  *flag = nullptr;
+  if (p.N >= (1ull << 32) || p.N < (1ull << 22) || p.tm.t > 8) return PW_OK;
+  TargetMap tm = p.tm;
+  bool even = (p.N & 1) == 0 && (((uintptr_t)in | (uintptr_t)out) & (2 * sizeof(V) - 1)) == 0;
+  for (int k = 0; k < tm.nt; ++k) {
+    if (tm.tdim[k] == 1) { tm.tstride[k] = 1; continue; }  // (singleton targets: digit 0)
+    if (tm.tstride[k] <= 0) return PW_OK;
+    if (tm.tstride[k] & 1) even = false;
+  }
+  PW_TRY(flag_mem->alloc(sizeof(int), s));
+  k_diag_check<V><<<1, 32, 0, s>>>(op, p.tm.t, (int*)flag_mem->p);
+  PW_LAUNCHED();
+  const int* fl = (const int*)flag_mem->p;
+  const int grid = grid_for(even ? p.N / 2 : p.N, 256, 8);
+  if (even) {
+    if (conj_op) k_apply_diag<V, true, true><<<grid, 256, 0, s>>>(in, out, op, (uint32_t)p.N, tm, fl);
+    else         k_apply_diag<V, false, true><<<grid, 256, 0, s>>>(in, out, op, (uint32_t)p.N, tm, fl);
+  } else {
+    if (conj_op) k_apply_diag<V, true, false><<<grid, 256, 0, s>>>(in, out, op, (uint32_t)p.N, tm, fl);
+    else         k_apply_diag<V, false, false><<<grid, 256, 0, s>>>(in, out, op, (uint32_t)p.N, tm, fl);
+  }
+  PW_LAUNCHED();
+  *flag = fl;
+  return PW_OK;
+}
+
 // size of the innermost run of untouched axes if it is the contiguous (stride-1) one,
 // else 0 (the innermost axis of the tensor is a target)
 static uint64_t inner_rest_run(const Plan& p) {
@@ -529,6 +636,19 @@ static int apply_axes(const void* in, void* out, const void* op, const int64_t* 
     // tensor-core kernel (HBM-bound) first, the warp-transposing register kernel as fallback
     BlockDesc bd8;
     const int* skip8 = nullptr;
+    // diagonal operators on large states: one streaming pass (decided on the device)
+    Scratch diag_flag;
+    // (only where the register kernel is weak: a short untouched inner run -- measured 11.3 ms
+    //  for every axis of the 34.8 GB vector against 11.4 / 13.1 / 13.4 ms at R >= 1296 / 216 / 36;
+    //  contiguous fibers, R = 0, have the tensor-core kernel at 10.7 ms)
+    if (vp == 0 && large && p.tm.t >= 2 && r_in > 0 && r_in < 1024 &&
+        options().diag_kernel.load(std::memory_order_relaxed)) {
+      if (dtype == PW_C128)
+        PW_TRY(try_diag<double2>((const double2*)in, (double2*)out, (const double2*)op, p, conj_op, s, &diag_flag, &skip8));
+      else
+        PW_TRY(try_diag<float2>((const float2*)in, (float2*)out, (const float2*)op, p, conj_op, s, &diag_flag, &skip8));
+      if (skip8) return launch_apply(in, out, op, p, dtype, conj_op, false, s, skip8);
+    }
     if (vp == 0 && dtype == PW_C128 && p.tm.t >= 5 && large && in != out && r_in == 0 &&
         options().seg_mma.load(std::memory_order_relaxed) > 1) {
       const int rc = launch_blocks_seg(in, out, op, axes, naxes, targets, nt, dtype, conj_op, &bd8, s, true);

@@ -177,6 +177,7 @@ struct Options {
   std::atomic<int> small_r{16};                // inner untouched run below this -> tiled staging
   std::atomic<int> mat_super_single{0};        // single operators on rho via superoperator tiles
   std::atomic<int> contig_kernel{1};           // warp-transposing kernel for contiguous fibers
+  std::atomic<int> diag_kernel{1};             // diagonal t <= 8 operators on large vectors: one streaming pass
   std::atomic<int> contig_mma{1};              // ... on the FP64 tensor cores (complex128, one 5..8-level target)
   std::atomic<int> fuse_pairs{0};              // circuit entry points fuse adjacent single-axis ops
   std::atomic<int> mat_pair_max_d{4};          // single-pass U rho U^dagger register tile up to this d

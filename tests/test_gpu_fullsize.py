@@ -58,7 +58,8 @@ def test_config4_vector_full_size_properties(ffi):
     us = {ax: ops.random_unitary(d, 50 + ax) for ax in (0, 5, 9, 11)}
     bs = ops.beam_splitter(d, d, math.pi / 5)
     dense2 = ops.random_unitary(d * d, 77)   # dense two-mode operators: FP64 tensor-core kernel
-    prog = [((0,), us[0]), ((5,), us[5]), ((9,), us[9]), ((11,), us[11]),
+    ph = ops.phase_operator(d, 0.41)           # diagonal operators: streaming kernel
+    prog = [((0,), us[0]), ((5,), us[5]), ((9,), us[9]), ((11,), us[11]), ((9,), ph), ((0,), ph), ((11,), ph),
             ((2, 3), bs), ((10, 11), bs), ((11, 0), bs), ((3, 4), dense2), ((11, 10), dense2),
             ((4, 8), bs)]
     for tg, op in prog:

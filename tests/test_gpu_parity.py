@@ -782,3 +782,25 @@ def test_contiguous_fibers_on_tensor_cores(ad):
         ref = oad.apply_operation_matrix(dims, (1,), rho, op, True)
         out = host(ad.apply_operation_matrix(dims, (1,), dev(rho), dev(op)))
         assert rel_err(out, ref) < tol, dims
+
+
+@pytest.mark.parametrize("cdtype", [np.complex128, np.complex64])
+def test_diagonal_operator_streaming_kernel(ad, cdtype):
+    """Diagonal operators on large vectors (>= 2^22 amplitudes) take the streaming kernel
+    (device-side test of the operator, element pairs, several targets); a non-diagonal
+    operator of the same shape must fall through to the register kernel."""
+    tol = TOL[cdtype]
+    dims = (6,) * 8 + (4,)                      # 6.7 M amplitudes; targets with a short inner run take the kernel
+    N = math.prod(dims)
+    psi = ops.random_state(N, 3, cdtype)
+    ph6, ph4 = ops.phase_operator(6, 0.37), ops.phase_operator(4, -1.1)
+    cases = [((3,), ph6), ((0,), ph6), ((7,), ph6), ((8,), ph4), ((2, 7), np.kron(ph6, ph6)[:36, :36]),
+             ((8, 1), np.kron(ph4, ops.phase_operator(2, 0.5))[:8, :8] if False else np.diag(np.exp(1j * np.arange(24) * 0.1))),
+             ((4,), ops.displacement_operator(6, 0.3))]
+    for tg, op in cases:
+        t = math.prod(dims[i] for i in tg)
+        op = np.asarray(op, dtype=np.complex128)
+        assert op.shape == (t, t)
+        ref = oad.apply_operation_vector(dims, tg, psi.astype(np.complex128), op, True)
+        out = host(ad.apply_operation_vector(dims, tg, dev(psi), dev(op.astype(cdtype))))
+        assert rel_err(out, ref) < tol, tg
