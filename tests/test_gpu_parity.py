@@ -794,7 +794,7 @@ def test_diagonal_operator_streaming_kernel(ad, cdtype):
     N = math.prod(dims)
     psi = ops.random_state(N, 3, cdtype)
     ph6, ph4 = ops.phase_operator(6, 0.37), ops.phase_operator(4, -1.1)
-    cases = [((3,), ph6), ((0,), ph6), ((7,), ph6), ((8,), ph4), ((2, 7), np.kron(ph6, ph6)),
+    cases = [((3,), ph6), ((0,), ph6), ((7,), ph6), ((6,), ph6), ((5,), ph6), ((8,), ph4), ((2, 7), np.kron(ph6, ph6)),
              ((8, 1), np.diag(np.exp(1j * np.arange(24) * 0.1))),     # t = 24 > 8: not the streaming kernel
              ((4,), ops.displacement_operator(6, 0.3))]
     for tg, op in cases:
