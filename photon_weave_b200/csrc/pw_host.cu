@@ -51,16 +51,41 @@ static int run_ops(void** cur, void** other, int is_matrix, const int64_t* dims,
   return PW_OK;
 }
 
+// bytes of the state (vector: N, density matrix: N^2 elements) with the overflow guard of
+// build_generic (pw_plan.cu): anything beyond 2^62 elements is rejected, never wrapped.
+static int state_bytes(int is_matrix, const int64_t* dims, int n, size_t es, size_t* bytes) {
+  uint64_t N = 1;
+  for (int i = 0; i < n; ++i) {
+    if (dims[i] < 1) return PW_ERR_INVALID;
+    if (N > (1ull << 62) / (uint64_t)dims[i]) return PW_ERR_INVALID;
+    N *= (uint64_t)dims[i];
+  }
+  uint64_t count = N;
+  if (is_matrix) {
+    if (N > (1ull << 31)) return PW_ERR_INVALID;  // N^2 * 16 must stay below 2^66 -> cap at 2^62 elements
+    count = N * N;
+  }
+  if (count > (1ull << 62) / es) return PW_ERR_INVALID;
+  *bytes = (size_t)(count * es);
+  return PW_OK;
+}
+
 static int check_ops(int is_matrix, const int64_t* dims, int n, const pw_host_op* ops, int nops) {
   for (int i = 0; i < nops; ++i) {
     const pw_host_op& o = ops[i];
     if (o.nt < 1 || o.nt > PW_MAX_TARGETS || !o.op) return PW_ERR_INVALID;
     if ((o.kind != 0) != (is_matrix != 0)) return PW_ERR_INVALID;
     if (o.kind == 2 && o.K < 1) return PW_ERR_INVALID;
-    for (int k = 0; k < o.nt; ++k)
-      if (o.targets[k] < 0 || o.targets[k] >= n) return PW_ERR_INVALID;
+    uint32_t seen = 0;
+    uint64_t t = 1;
+    for (int k = 0; k < o.nt; ++k) {
+      const int a = o.targets[k];
+      if (a < 0 || a >= n || (seen >> a & 1u)) return PW_ERR_INVALID;  // out of range / duplicate
+      seen |= 1u << a;
+      t *= (uint64_t)dims[a];
+      if (t > 0xffffffffull) return PW_ERR_UNSUPPORTED;
+    }
   }
-  (void)dims;
   return PW_OK;
 }
 
@@ -86,15 +111,11 @@ extern "C" int pw_circuit_host(const void* h_state, void* h_out, int is_matrix,
   if (!h_state || !h_out || !dims || n < 1 || n > PW_MAX_SUBSYSTEMS || nops < 0 || (nops && !ops))
     return PW_ERR_INVALID;
   if (dtype != PW_C64 && dtype != PW_C128) return PW_ERR_INVALID;
-  PW_CUDA(cudaSetDevice(device));
   const size_t es = dtype == PW_C128 ? 16 : 8;
-  uint64_t N = 1;
-  for (int i = 0; i < n; ++i) {
-    if (dims[i] < 1) return PW_ERR_INVALID;
-    N *= (uint64_t)dims[i];
-  }
-  const uint64_t count = is_matrix ? N * N : N;
-  const size_t bytes = count * es;
+  size_t bytes = 0;
+  PW_TRY(state_bytes(is_matrix, dims, n, es, &bytes));
+  PW_TRY(check_ops(is_matrix, dims, n, ops, nops));
+  PW_CUDA(cudaSetDevice(device));
 
   Stream st;
   PW_CUDA(cudaStreamCreateWithFlags(&st.s, cudaStreamNonBlocking));
@@ -109,16 +130,10 @@ extern "C" int pw_circuit_host(const void* h_state, void* h_out, int is_matrix,
   // operators: one small upload each, queued ahead of the state so they overlap it
   std::vector<DevBuf> dops(nops);
   for (int i = 0; i < nops; ++i) {
-    const pw_host_op& o = ops[i];
-    if (o.nt < 1 || o.nt > PW_MAX_TARGETS || !o.op) return PW_ERR_INVALID;
-    if ((o.kind != 0) != (is_matrix != 0)) return PW_ERR_INVALID;
+    const pw_host_op& o = ops[i];  // validated by check_ops above
     uint64_t t = 1;
-    for (int k = 0; k < o.nt; ++k) {
-      if (o.targets[k] < 0 || o.targets[k] >= n) return PW_ERR_INVALID;
-      t *= (uint64_t)dims[o.targets[k]];
-    }
+    for (int k = 0; k < o.nt; ++k) t *= (uint64_t)dims[o.targets[k]];
     const int K = o.kind == 2 ? o.K : 1;
-    if (K < 1) return PW_ERR_INVALID;
     const size_t ob = (size_t)K * t * t * es;
     PW_CUDA(cudaMalloc(&dops[i].p, ob));
     PW_CUDA(cudaMemcpyAsync(dops[i].p, o.op, ob, cudaMemcpyHostToDevice, st.s));
@@ -200,13 +215,8 @@ extern "C" int pw_pipeline_create(int is_matrix, const int64_t* dims, int n, int
   pw_pipeline* pl = new pw_pipeline();
   pl->device = device; pl->is_matrix = is_matrix; pl->n = n; pl->dtype = dtype;
   pl->es = dtype == PW_C128 ? 16 : 8;
-  uint64_t N = 1;
-  for (int i = 0; i < n; ++i) {
-    if (dims[i] < 1) { delete pl; return PW_ERR_INVALID; }
-    pl->dims[i] = dims[i];
-    N *= (uint64_t)dims[i];
-  }
-  pl->bytes = (is_matrix ? N * N : N) * pl->es;
+  if (state_bytes(is_matrix, dims, n, pl->es, &pl->bytes) != PW_OK) { delete pl; return PW_ERR_INVALID; }
+  for (int i = 0; i < n; ++i) pl->dims[i] = dims[i];
   auto fail = [&](int code) { pw_pipeline_destroy(pl); return code; };
   for (cudaStream_t* s : {&pl->s_h2d, &pl->s_comp, &pl->s_d2h, &pl->s_ops})
     if (cudaStreamCreateWithFlags(s, cudaStreamNonBlocking) != cudaSuccess) return fail(PW_ERR_CUDA);
@@ -283,8 +293,32 @@ extern "C" int pw_pipeline_submit(pw_pipeline* pl, const void* h_state, void* h_
   }
   PW_CUDA(cudaEventRecord(slot.ops_ev, pl->s_ops));
 
+  if (pl->pool.size() < 2) return PW_ERR_INVALID;
   pw_pipeline::Buf X = pl->pool.front(); pl->pool.pop_front();
   pw_pipeline::Buf Z = pl->pool.front(); pl->pool.pop_front();
+  // Whatever happens below, both buffers go back to the pool: on an early (error) return their
+  // "free" events are recorded behind everything already queued on the three streams, so a
+  // later job can never touch a buffer that is still being copied.
+  struct PoolGuard {
+    pw_pipeline* pl; pw_pipeline::Buf a, b; bool armed = true;
+    ~PoolGuard() {
+      if (!armed) return;
+      for (pw_pipeline::Buf* x : {&a, &b}) {
+        cudaStreamWaitEvent(pl->s_d2h, x->free_ev, 0);
+        cudaEvent_t tmp;
+        if (cudaEventCreateWithFlags(&tmp, cudaEventDisableTiming) == cudaSuccess) {
+          for (cudaStream_t st : {pl->s_h2d, pl->s_comp}) {
+            cudaEventRecord(tmp, st);
+            cudaStreamWaitEvent(pl->s_d2h, tmp, 0);
+          }
+          cudaEventDestroy(tmp);
+        }
+        cudaEventRecord(x->free_ev, pl->s_d2h);
+        pl->pool.push_back(*x);
+      }
+      (void)cudaGetLastError();
+    }
+  } guard{pl, X, Z};
 
   // upload
   PW_CUDA(cudaStreamWaitEvent(pl->s_h2d, X.free_ev, 0));
@@ -301,18 +335,15 @@ extern "C" int pw_pipeline_submit(pw_pipeline* pl, const void* h_state, void* h_
                          pl->dtype, fuse, pl->s_comp);
   pw_pipeline::Buf R = (cur == X.p) ? X : Z;   // holds the result
   pw_pipeline::Buf O = (cur == X.p) ? Z : X;   // free as soon as the kernels are done
-  cudaEventRecord(O.free_ev, pl->s_comp);
-  pl->pool.push_back(O);
-  if (rc != PW_OK) {
-    cudaEventRecord(R.free_ev, pl->s_comp);
-    pl->pool.push_back(R);
-    return rc;
-  }
+  if (rc != PW_OK) return rc;  // guard returns X and Z
+  PW_CUDA(cudaEventRecord(O.free_ev, pl->s_comp));
   // download
   PW_CUDA(cudaStreamWaitEvent(pl->s_d2h, O.free_ev, 0));
   PW_CUDA(cudaMemcpyAsync(h_out, R.p, pl->bytes, cudaMemcpyDeviceToHost, pl->s_d2h));
   PW_CUDA(cudaEventRecord(R.free_ev, pl->s_d2h));
   PW_CUDA(cudaEventRecord(slot.done_ev, pl->s_d2h));
+  guard.armed = false;
+  pl->pool.push_back(O);
   pl->pool.push_back(R);
   slot.ticket = tk;
   pl->next_ticket = tk + 1;

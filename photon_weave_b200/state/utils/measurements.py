@@ -216,7 +216,14 @@ def _measure_pnr(is_matrix: bool, state_objs, target_states, product_state, effi
     if use_jit_flag:
         if key is None:
             raise ValueError("key is required for jitted PNR measurement (static path)")
-        dims, tgt = _dims_targets(meta, state_objs, target_states, None)
+        if meta is None:
+            # measurements.py:781-783: the PNR path indexes the targets in the GIVEN order (the
+            # joint draw and the decode both follow target_states), unlike measure_*_jit above
+            objs = list(state_objs)
+            dims = [s.dimensions for s in objs]
+            tgt = [objs.index(s) for s in target_states]
+        else:
+            dims, tgt = _dims_targets(meta, state_objs, target_states, None)
         core = adapters.measure_matrix if is_matrix else adapters.measure_vector
         outcome, post, key_after = core(dims, tgt, product_state, key)
         decoded = list(_decode(outcome, dims, tgt, target_states).values())

@@ -180,6 +180,26 @@ def fock_pnr_ideal_detector():
     assert next_key is not None and not np.array_equal(np.asarray(next_key), np.asarray(key))
 
 
+def pnr_two_targets_in_reversed_order():
+    """state/utils/measurements.py:781-783: the jitted PNR path measures and decodes in the
+    GIVEN target order.  A basis state |2>_A |1>_B with targets (B, A) must report B=1, A=2
+    (decoding in tensor order while zipping in given order would swap them)."""
+    from photon_weave_b200.state.utils import measurements as ms
+
+    class _Obj:
+        def __init__(self, d):
+            self.dimensions = d
+
+    a, b = _Obj(4), _Obj(3)
+    psi = np.zeros((12, 1), dtype=np.complex128)
+    psi[2 * 3 + 1, 0] = 1.0
+    for fn, st in ((ms.measure_pnr_vector, psi), (ms.measure_pnr_matrix, psi @ psi.conj().T)):
+        counts, post, jitter, nk = fn([a, b], (b, a), st, key=rng.PRNGKey(5), use_jit=True)
+        assert counts[b] == 1 and counts[a] == 2, counts
+        counts, _, _, _ = fn([a, b], (a, b), st, key=rng.PRNGKey(5), use_jit=True)
+        assert counts[a] == 2 and counts[b] == 1, counts
+
+
 def polarization_labels_and_gates():
     """state/test_polarization.py + operation/test_polarization_operation.py."""
     for label, vec in ((PolarizationLabel.H, [1, 0]), (PolarizationLabel.V, [0, 1]),
@@ -634,6 +654,7 @@ CASES = [
     fock_measure_seed_kats,
     fock_resize,
     fock_pnr_ideal_detector,
+    pnr_two_targets_in_reversed_order,
     polarization_labels_and_gates,
     polarization_measure_seed_kats,
     custom_state_operation_kraus_povm,

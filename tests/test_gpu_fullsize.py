@@ -1,9 +1,14 @@
 """
-BASELINE.json full sizes through size-independent properties (the oracle cannot hold
-them): configs[4] 12-mode cutoff-6 state vector (34.8 GB) and configs[3] 5-mode cutoff-8
-density matrix (17.2 GB).  Unitary norm preservation, inverse round trip, trace
-preservation of a Kraus channel, agreement of independent kernel paths, and a sampled
-comparison of individual fibers against the NumPy oracle.
+BASELINE.json full sizes: configs[4] 12-mode cutoff-6 state vector (34.8 GB) and configs[3]
+5-mode cutoff-8 density matrix (17.2 GB).  The oracle cannot hold them, so
+
+* after EVERY operation, randomly sampled fibers (vector) / fiber-pair blocks (density matrix)
+  of the INPUT are brought to the host, the operator (or Kraus sum) is applied to them with
+  NumPy -- the arithmetic of core/kernels.py:62-98, 101-145, 148-186 on that fiber -- and compared
+  with the same entries of the CUDA OUTPUT (<= 1e-12 relative): a unitary-but-wrong kernel,
+  a wrong permutation or an index overflow beyond 2^32 bytes fails here;
+* size-independent properties on top: norm / trace preservation, inverse round trip,
+  Hermiticity, agreement of the matrix and vector pictures.
 """
 
 import math
@@ -46,6 +51,61 @@ def max_abs_diff(a, b, chunks=12):
     return worst
 
 
+def _strides(dims):
+    st, acc = [], 1
+    for d in reversed(dims):
+        st.append(acc)
+        acc *= d
+    return list(reversed(st))
+
+
+def _target_offsets(dims, tg):
+    """Element offsets of the operator index j (targets in the GIVEN order, adapters.py:53)."""
+    st = _strides(dims)
+    off = np.zeros(1, dtype=np.int64)
+    for a in tg:
+        off = (off[:, None] + np.arange(dims[a], dtype=np.int64)[None, :] * st[a]).reshape(-1)
+    return off
+
+
+def _fiber_bases(dims, tg, rng, count):
+    """Random fiber origins (target digits zero), half of them from the last 1 % of the array."""
+    st = np.array(_strides(dims), dtype=np.int64)
+    idx = rng.integers(0, np.array(dims), size=(count, len(dims)))
+    idx[count // 2:, 0] = dims[0] - 1
+    idx[count // 2:, 1] = dims[1] - 1
+    idx[:, list(tg)] = 0
+    return idx @ st
+
+
+def check_vec_fibers(x_in, x_out, op, dims, tg, rng, count=64, tol=1e-12):
+    """out[fiber] == op @ in[fiber] on `count` sampled fibers (NumPy on the sampled INPUT)."""
+    pos = _fiber_bases(dims, tg, rng, count)[:, None] + _target_offsets(dims, tg)[None, :]
+    pos_d = torch.as_tensor(pos, device=x_in.device)
+    xin = x_in.reshape(-1)[pos_d].cpu().numpy()
+    got = x_out.reshape(-1)[pos_d].cpu().numpy()
+    want = xin @ np.asarray(op).T
+    err = np.abs(got - want).max() / max(np.abs(want).max(), 1e-300)
+    assert err < tol, (tg, err)
+
+
+def check_mat_blocks(r_in, r_out, kraus, dims, tg, rng, count=48, tol=1e-12):
+    """out[rows(I), cols(J)] == sum_k K in[rows(I), cols(J)] K^dagger on sampled fiber pairs."""
+    D = math.prod(dims)
+    toff = _target_offsets(dims, tg)
+    rows = _fiber_bases(dims, tg, rng, count)[:, None] + toff[None, :]
+    cols = _fiber_bases(dims, tg, rng, count)[:, None] + toff[None, :]
+    flat = rows[:, :, None] * D + cols[:, None, :]
+    flat_d = torch.as_tensor(flat, device=r_in.device)
+    bin_ = r_in.reshape(-1)[flat_d].cpu().numpy()
+    got = r_out.reshape(-1)[flat_d].cpu().numpy()
+    ks = np.asarray(kraus)
+    ks = ks[None] if ks.ndim == 2 else ks
+    want = sum(np.einsum("ab,nbc,dc->nad", k, bin_, k.conj()) for k in ks)
+    err = np.abs(got - want).max() / max(np.abs(want).max(), 1e-300)
+    assert err < tol, (tg, err)
+
+
 def test_config4_vector_full_size_properties(ffi):
     modes, d = 12, 6
     dims = (d,) * modes
@@ -62,24 +122,13 @@ def test_config4_vector_full_size_properties(ffi):
     prog = [((0,), us[0]), ((5,), us[5]), ((9,), us[9]), ((11,), us[11]), ((9,), ph), ((0,), ph), ((11,), ph),
             ((2, 3), bs), ((10, 11), bs), ((11, 0), bs), ((3, 4), dense2), ((11, 10), dense2),
             ((4, 8), bs)]
+    prog += [((8,), us[9]), ((10,), us[0]), ((8, 9), bs), ((2, 9), bs), ((6, 1), dense2)]
+    rng = np.random.default_rng(0)
     for tg, op in prog:
         ffi.apply_vec(a, dev(op), dims, tg, out=b)
+        check_vec_fibers(a, b, op, dims, tg, rng)      # every operation, against NumPy on its input
         a, b = b, a
     assert abs(float(ffi.norm_stats(a)[0]) - 1.0) < 1e-12
-    # sampled fibers of the LAST operation against the oracle: redo it on b's input
-    # (b currently holds the input of the last op), compare 64 random fibers
-    tg, op = prog[-1]
-    rng = np.random.default_rng(0)
-    strides = [d ** (modes - 1 - i) for i in range(modes)]
-    toff = np.array([i * strides[tg[0]] + j * strides[tg[1]] for i in range(d) for j in range(d)])
-    for _ in range(64):
-        idx = rng.integers(0, d, size=modes)
-        idx[list(tg)] = 0
-        base = int(np.dot(idx, strides))
-        pos = torch.as_tensor(base + toff, device="cuda")
-        x = b[pos].cpu().numpy()
-        y = a[pos].cpu().numpy()
-        assert np.abs(op @ x - y).max() < 1e-14 * 10
     # inverse round trip back to psi
     for tg, op in reversed(prog):
         ffi.apply_vec(a, dev(op.conj().T), dims, tg, out=b)
@@ -106,9 +155,12 @@ def test_config3_density_matrix_full_size_properties(ffi):
     out = torch.empty_like(rho)
     tr0 = float(torch.diagonal(rho).sum().real)
     assert abs(tr0 - 1.0) < 1e-12
-    loss = dev(ops.loss_channel(d, 0.2))
+    loss_h = ops.loss_channel(d, 0.2)
+    loss = dev(loss_h)
+    rng_s = np.random.default_rng(11)
     for ax in (0, 2, 4):
         ffi.kraus_mat(rho.reshape(-1), loss, dims, (ax,), out=out.reshape(-1))
+        check_mat_blocks(rho, out, loss_h, dims, (ax,), rng_s)
         assert abs(float(torch.diagonal(out).sum().real) - tr0) < 1e-11      # trace preserving
         herm = float((out[:512, :512] - out[:512, :512].conj().T).abs().max())
         assert herm < 1e-15                                                     # stays Hermitian
@@ -116,6 +168,16 @@ def test_config3_density_matrix_full_size_properties(ffi):
     # (U rho U^dagger) built from the evolved vectors, checked on a 256 x 256 corner
     u = ops.random_unitary(d, 9)
     ffi.apply_mat(rho.reshape(-1), dev(u), dims, (3,), out=out.reshape(-1))
+    check_mat_blocks(rho, out, u, dims, (3,), rng_s)
+    # dense Kraus channel (K = 3 random contractions: dense superoperator route) and a phase
+    kd = np.stack([ops.random_unitary(d, 30 + k) for k in range(3)]) / math.sqrt(3.0)
+    scratch = torch.empty_like(rho)
+    ffi.kraus_mat(rho.reshape(-1), dev(kd), dims, (1,), out=scratch.reshape(-1))
+    check_mat_blocks(rho, scratch, kd, dims, (1,), rng_s)
+    ph = ops.phase_operator(d, 0.37)
+    ffi.apply_mat(rho.reshape(-1), dev(ph), dims, (4,), out=scratch.reshape(-1))
+    check_mat_blocks(rho, scratch, ph, dims, (4,), rng_s)
+    del scratch
     ws = [ffi.apply_vec(v, dev(u), dims, (3,)) for v in vs]
     corner = sum(torch.outer(w[:256], w[:256].conj()) for w in ws) / 3.0
     assert float((out[:256, :256] - corner).abs().max()) < 1e-15
@@ -131,6 +193,7 @@ def test_config3_density_matrix_full_size_properties(ffi):
     start = a.clone()
     for tg, op in seq:
         ffi.apply_mat(a.reshape(-1), dev(op), dims, tg, out=b.reshape(-1))
+        check_mat_blocks(a, b, op, dims, tg, rng_s, count=12 if len(tg) == 2 else 48)
         ws = [ffi.apply_vec(w, dev(op), dims, tg) for w in ws]
         a, b = b, a
         want = sum(torch.outer(w[I], w[J].conj()) for w in ws) / 3.0
