@@ -60,6 +60,37 @@ def make_layer(modes: int, cutoff: int):
     return layer
 
 
+def make_rho_layer(modes: int, cutoff: int):
+    """configs[3] layer: a photon-loss Kraus channel (K = cutoff operators) on every
+    mode, then beam splitters on the even bricks.  [(targets, operator(s) complex128, label)]."""
+    from oracle import operators as ops  # operator *construction* is input generation
+
+    loss = np.ascontiguousarray(ops.loss_channel(cutoff, 0.1))
+    layer = [((m,), loss, f"kraus_loss[{m}]") for m in range(modes)]
+    bs = np.ascontiguousarray(ops.beam_splitter(cutoff, cutoff, math.pi / 4))
+    for m in range(0, modes - 1, 2):
+        layer.append(((m, m + 1), bs, f"bs[{m},{m + 1}]"))
+    return layer
+
+
+def oracle_apply(kind, dims, targets, state, op):
+    """The checker of the N>1 parity preflight (oracle/ is test infrastructure: it only CHECKS)."""
+    from oracle import adapters_np as oad
+
+    if kind == "vec":
+        return oad.apply_operation_vector(tuple(dims), tuple(targets), state, op, True)
+    if op.ndim == 3:
+        return oad.apply_kraus_matrix(tuple(dims), tuple(targets), state, op, True)
+    return oad.apply_operation_matrix(tuple(dims), tuple(targets), state, op, True)
+
+
+def preflight_input(kind, dims):
+    from oracle import operators as ops
+
+    n = int(np.prod(dims))
+    return ops.random_state(n, 99) if kind == "vec" else ops.random_density(n, 98)
+
+
 def ncu_traffic(kernel_key: str):
     """dram__bytes_read+write per launch from the committed `ncu --set full` capture
     (profiles/r1_traffic.json, produced by tools/ncu_summary.py); None if absent."""
@@ -178,25 +209,87 @@ def pick_cpu_modes(cutoff: int, budget_s: float):
     return best
 
 
+def reference_layer_jax(modes, cutoff, steps, warmup):
+    """The REAL reference (photon_weave on JAX-CPU) when it is importable on this box:
+    adapters.apply_operation_vector_jit (core/adapters.py:752-780), use_contraction=True (the
+    library default route), timed like benchmarks/contraction_vs_jitted.py:64-75."""
+    import jax  # noqa: F401 -- raises ImportError where jax is absent (this image)
+    import jax.numpy as jnp
+
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(ref_dir) and ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    from photon_weave.core import adapters as rad  # the unmodified reference package
+    from oracle import operators as ops
+
+    dims = (cutoff,) * modes
+    N = cutoff**modes
+    layer = [(t, jnp.asarray(o)) for t, o, _ in make_layer(modes, cutoff)]
+    psi = jnp.asarray(ops.random_state(N, 0))
+
+    def run(x):
+        for t, o in layer:
+            x = rad.apply_operation_vector_jit(dims, tuple(t), x, o, True)
+        return jax.block_until_ready(x)
+
+    for _ in range(max(warmup, 1)):
+        psi = run(psi)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        psi = run(psi)
+    dt = time.perf_counter() - t0
+    return len(layer) * N * steps / dt, dt / steps, len(layer), N
+
+
+def pin_blas_threads():
+    """Let the NumPy/BLAS port use every host core, and say how many it got."""
+    cores = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+
+        threadpool_limits(limits=cores)
+        got = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+        return cores, int(got)
+    except Exception:
+        return cores, None
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cutoff = args.cutoff
+    cores, blas_threads = pin_blas_threads()
     per_step_budget = 150.0 / max(args.steps + args.warmup, 1)
     modes = pick_cpu_modes(cutoff, per_step_budget)
-    value, s_per_step, nops, N = cpu_layer_throughput(modes, cutoff, args.steps, args.warmup)
-    cores = os.cpu_count()
+    kind, what = "port", "NumPy/BLAS port of the reference path (oracle/cpu_baseline.py; jax is not installable here)"
+    try:
+        value, s_per_step, nops, N = reference_layer_jax(modes, cutoff, args.steps, args.warmup)
+        kind, what = "reference", "photon_weave adapters.apply_operation_vector_jit on JAX-CPU (use_contraction=True)"
+    except ImportError:
+        value, s_per_step, nops, N = cpu_layer_throughput(modes, cutoff, args.steps, args.warmup)
     sample = (f"same layer pattern on a {modes}-mode cutoff-{cutoff} state vector "
-              f"({N} amplitudes, {nops} ops/step), NumPy/BLAS port of the reference path")
+              f"({N} amplitudes, {nops} ops/step), {what}")
+    # config describes what THIS arm ran: a bounded sample of the workload (per-amplitude
+    # throughput is the comparable quantity), not the 12-mode state of the GPU arm
+    cfg = {
+        "workload": f"bounded CPU sample of configs[4]: {modes}-mode state vector, cutoff {cutoff} "
+                    f"({N} amplitudes, {N * 16 / 1e9:.3f} GB complex128)",
+        "layer": f"{modes} single-mode ops (displace/phase/squeeze/dense unitary) + "
+                 f"{modes // 2} beam splitters on even bricks",
+        "ops_per_step": nops, "sample_modes": modes, "sample_amplitudes": N,
+        "gpu_arm_modes": args.modes, "same_size_as_gpu_arm": modes == args.modes,
+        "comparison": "per-amplitude throughput (amplitudes updated/s); the CPU cannot hold the 34.8 GB state twice",
+        "sharding": "host CPU, all cores",
+    }
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "c128", "data": "synthetic",
-        "config": workload_config(args, 1),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": sample},
+        "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "blas_threads": blas_threads,
+                         "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -241,11 +334,22 @@ def run_gpu_arm(args):
 
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    if world > 1:
-        from photon_weave_b200.sharded import bench_sharded  # noqa: WPS433
+    if world > 1 or args.workload == "rho":
+        from photon_weave_b200 import bench_sharded as bs  # noqa: WPS433
 
-        return bench_sharded(args, dist, rank, world, local_rank, make_layer, workload_config,
-                             peaks, ClockSampler, METRIC, UNIT)
+        def preflight(kind, want_peers):
+            # N>1 only: a small state through the same schedule on the same ranks vs the oracle
+            if world == 1 or args.no_preflight:
+                return None
+            return bs.parity_preflight(dist, rank, world, local_rank, kind,
+                                       make_layer if kind == "vec" else make_rho_layer,
+                                       oracle_apply, preflight_input, want_peers)
+
+        if args.workload == "rho":
+            return bs.bench_sharded_rho(args, dist, rank, world, local_rank, make_rho_layer, peaks,
+                                        ClockSampler, preflight)
+        return bs.bench_sharded(args, dist, rank, world, local_rank, make_layer, workload_config,
+                                peaks, ClockSampler, METRIC, UNIT, preflight)
 
     modes, cutoff = args.modes, args.cutoff
     dims = (cutoff,) * modes
@@ -371,18 +475,37 @@ def run_gpu_arm(args):
     # ---- CPU baseline on a bounded sample --------------------------------------------------
     cpu = None
     if not args.no_cpu:
+        pin_blas_threads()
         m_cpu = pick_cpu_modes(cutoff, 6.0)
         v, s_step, nops_c, n_c = cpu_layer_throughput(m_cpu, cutoff, 2, 1)
-        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+        cores, blas_threads = pin_blas_threads()
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "blas_threads": blas_threads, "kind": "port",
                "sample": f"same layer pattern on a {m_cpu}-mode cutoff-{cutoff} state vector "
                          f"({n_c} amplitudes), 2 timed steps, NumPy/BLAS port of the reference path"}
 
+    roofline_kraus = None
+    if extras:
+        # the Kraus side of the metric (configs[3]): loss channel, K = 8, on a middle mode of the
+        # 17.18 GB rho -- ONE pass, algorithmic bytes 2 N^2 16 B independent of K
+        k = extras["kraus_loss_K8_mode2"]
+        roofline_kraus = {
+            "bound": "hbm", "kernel": "pw_kraus_mat: loss channel K=8 on mode 2 of the 5-mode cutoff-8 rho "
+                                      "(k_build_super + k_apply_blocks, one HBM pass)",
+            "achieved": k["gbs"], "peak": peak, "unit": "GB/s", "frac": k["gbs"] / peak,
+            "traffic": ncu_traffic("kraus_loss"), "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": extras["algorithmic_bytes_per_launch"], "avg_launch_ms": k["ms"],
+            "entries_per_s": k["entries_per_s"],
+            "innermost_mode": {"ms": extras["kraus_loss_K8_mode4_innermost"]["ms"],
+                               "frac": extras["kraus_loss_K8_mode4_innermost"]["frac_of_hbm_peak"]},
+        }
+    e2e_serial = e2e.get("serial") if isinstance(e2e, dict) else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
-        "config": workload_config(args, 1), "clocks": clocks, "e2e": e2e,
-        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        "config": workload_config(args, 1), "clocks": clocks, "e2e": e2e, "e2e_serial": e2e_serial,
+        "gpu_launches": launches, "roofline": roofline, "roofline_kraus": roofline_kraus,
+        "cpu_baseline": cpu,
         "kernels": kernels, "norm_after": norm_after, "density_matrix": extras, "small_configs": small,
         "paths": _lib.path_counters(),
     }
@@ -465,8 +588,12 @@ def run_e2e(args, torch, ffi, layer, h, N, nops):
     check = float(np.vdot(o_np[:1 << 20], o_np[:1 << 20]).real)
     del h_out
     out.update({"value": nops * N / dt, "ms_per_step": dt * 1e3, "steps": psteps,
-                "api": "pw_pipeline_submit/wait (C ABI, pinned host buffers; upload of step k+1, "
-                       "kernels of step k and download of step k-1 overlap; fill and drain timed)",
+                "api": "pw_pipeline_submit/wait (C ABI, pinned host buffers): THROUGHPUT over INDEPENDENT "
+                       "JOBS -- each step is a separate job (its own upload, layer and download; the same "
+                       "input buffer re-submitted), up to three in flight, so the upload of job k+1, the "
+                       "kernels of job k and the download of job k-1 overlap; fill and drain timed.  "
+                       "The latency of ONE job is e2e_serial (pw_circuit_host).",
+                "mode": "pipelined, independent jobs",
                 "device_buffers": nbuf, "serial": serial, "checksum_first_1Mi": check})
     return out
 
@@ -505,8 +632,12 @@ def run_matrix_extras(torch, ffi, peak):
 
     res = {"workload": "configs[3]: 5-mode cutoff-8 density matrix (2^30 entries, 17.18 GB complex128)",
            "algorithmic_bytes_per_launch": nbytes}
+    res["kraus_loss_K8_mode2"] = None
+    ms = timed(lambda: ffi.kraus_mat(rho, loss, dims, (2,), out=out), reps=8)
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    res["kraus_loss_K8_mode2"] = {"ms": ms, "entries_per_s": D * D / (ms * 1e-3), "gbs": gbs,
+                                  "frac_of_hbm_peak": gbs / peak, "reps": 8}
     for name, fn in [
-        ("kraus_loss_K8_mode2", lambda: ffi.kraus_mat(rho, loss, dims, (2,), out=out)),
         ("apply_phase_mode1", lambda: ffi.apply_mat(rho, ph, dims, (1,), out=out)),
         ("apply_dense_8x8_mode2", lambda: ffi.apply_mat(rho, u, dims, (2,), out=out)),
         ("apply_dense_8x8_mode4_innermost", lambda: ffi.apply_mat(rho, u, dims, (4,), out=out)),
@@ -631,6 +762,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--nccl-swap", action="store_true", help="N>1: NCCL all_to_all instead of peer reads")
+    ap.add_argument("--workload", default="vec", choices=["vec", "rho"],
+                    help="vec: configs[4] 12-mode state vector (headline); rho: configs[3] 5-mode "
+                         "density matrix, Kraus + beam-splitter layer (row-sharded for N>1)")
+    ap.add_argument("--rho-modes", type=int, default=5)
+    ap.add_argument("--rho-cutoff", type=int, default=8)
+    ap.add_argument("--no-preflight", action="store_true", help="N>1: skip the parity preflight")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

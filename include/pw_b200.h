@@ -259,6 +259,44 @@ int pw_apply_vec_gather(const void* const* srcs, int W, int64_t chunk_elems, int
                         const void* op, const int64_t* dims, int n, const int32_t* targets,
                         int nt, int dtype, void* stream);
 
+/* ---- multi-GPU layer: blocks of a sharded state -------------------------------------------
+ * One process per GPU holds a BLOCK of the state (photon_weave_b200/sharded.py): a row slab of
+ * rho, or a slab of psi over virtual axes.  Such a block is not a dense tensor of the global
+ * dims, so these entry points take explicit axes / (extent, element stride) lists.  The
+ * reference has no distributed code; the arithmetic per block is that of the functions cited. */
+
+/* out = sum_k (K_k on row_targets) x (conj(K_k) on col_targets), x a row-major tensor over
+ * `naxes` axes (a rectangular block of rho: row axes then column axes).  K = 1: U rho U^dagger.
+ * Same kernels and one-pass dispatch as pw_apply_mat / pw_kraus_mat (core/kernels.py:101-186),
+ * which are the special case axes = dims ++ dims. */
+int pw_kraus_axes(const void* x, void* out, const void* ops, int K, const int64_t* axes, int naxes,
+                  const int32_t* row_targets, int ntr, const int32_t* col_targets, int ntc,
+                  int dtype, void* stream);
+
+/* sums[j] = sum over the `rest` axes of |x|^2 (real_part = 0) or Re x (real_part = 1) at target
+ * index j (mixed radix over the tgt axes, first most significant): the UN-NORMALISED partial
+ * sums of core/kernels.py:28-59 on one rank's block; `x` is already offset to the block (and,
+ * for rho, strides walk its diagonal).  sums is t device doubles. */
+int pw_sums_strided(const void* x, const int64_t* rest_extent, const int64_t* rest_stride, int nrest,
+                    const int64_t* tgt_extent, const int64_t* tgt_stride, int ntgt, int real_part,
+                    double* sums, int dtype, void* stream);
+
+/* probs[j] = sums[j] / sum(sums) in the state's real dtype (after the cross-rank all-reduce). */
+int pw_probs_from_sums(const double* sums, int64_t t, void* probs, int dtype, void* stream);
+
+/* out[j, j'] = sum over the rest axes of x[rest + row(j) + col(j')]: partial trace of a block of
+ * rho (core/kernels.py:301-319) whose traced index pairs are walked by the rest strides. */
+int pw_trace_strided(const void* x, const int64_t* rest_extent, const int64_t* rest_stride, int nrest,
+                     const int64_t* row_extent, const int64_t* row_stride, int nrow,
+                     const int64_t* col_extent, const int64_t* col_stride, int ncol, void* out,
+                     int dtype, void* stream);
+
+/* out (contiguous, row-major over the axes) = x[strided view] / den; mode 0: den = 1,
+ * 1: sqrt(probs[*outcome] + 1e-18) (core/kernels.py:205), 2: probs[*outcome] + 1e-18 (:225). */
+int pw_gather_strided(const void* x, const int64_t* extent, const int64_t* stride, int naxes,
+                      void* out, const void* probs, const int64_t* outcome, int mode, int dtype,
+                      void* stream);
+
 /* ---- host-side PRNG key management (pure integer, no device) --------------- */
 
 /* out[i] = jax.random.split(key, num)[i] (partitionable threefry2x32).

@@ -86,6 +86,23 @@ SIGNATURES = {
         C.c_int,
         [C.POINTER(_vp), C.c_int, C.c_int64, C.c_int, _vp, _vp, _i64p, C.c_int, _i32p, C.c_int, C.c_int, _vp],
     ),
+    "pw_kraus_axes": (
+        C.c_int,
+        [_vp, _vp, _vp, C.c_int, _i64p, C.c_int, _i32p, C.c_int, _i32p, C.c_int, C.c_int, _vp],
+    ),
+    "pw_sums_strided": (
+        C.c_int,
+        [_vp, _i64p, _i64p, C.c_int, _i64p, _i64p, C.c_int, C.c_int, _vp, C.c_int, _vp],
+    ),
+    "pw_probs_from_sums": (C.c_int, [_vp, C.c_int64, _vp, C.c_int, _vp]),
+    "pw_trace_strided": (
+        C.c_int,
+        [_vp, _i64p, _i64p, C.c_int, _i64p, _i64p, C.c_int, _i64p, _i64p, C.c_int, _vp, C.c_int, _vp],
+    ),
+    "pw_gather_strided": (
+        C.c_int,
+        [_vp, _i64p, _i64p, C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, _vp],
+    ),
     "pw_rng_split": (C.c_int, [C.POINTER(C.c_uint32), C.c_int, C.POINTER(C.c_uint32)]),
     "pw_apply_vec_pair": (C.c_int, [_vp, _vp, _vp, _vp, _i64p, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "pw_evolve_vec": (
@@ -141,7 +158,7 @@ def check(status: int, what: str) -> None:
 
 
 def i64_array(vals: Sequence[int]):
-    return (C.c_int64 * len(vals))(*[int(v) for v in vals])
+    return (C.c_int64 * max(len(vals), 1))(*[int(v) for v in vals])
 
 
 def i32_array(vals: Sequence[int]):

@@ -333,6 +333,89 @@ def contract_mat(rho: torch.Tensor, tol: float = 1e-6):
     return psi, info, flag
 
 
+# ---- blocks of a sharded state (multi-GPU layer, photon_weave_b200/sharded.py) ---------------
+
+
+def _view(pairs):
+    """[(extent, stride)] -> two ctypes int64 arrays + count."""
+    ext = [int(e) for e, _ in pairs]
+    st = [int(s) for _, s in pairs]
+    return _lib.i64_array(ext), _lib.i64_array(st), len(pairs)
+
+
+def _esize(dtype: torch.dtype) -> int:
+    return 16 if dtype == torch.complex128 else 8
+
+
+def kraus_axes(x: torch.Tensor, ops: torch.Tensor, axes, row_targets, col_targets,
+               out: Optional[torch.Tensor] = None):
+    """out = sum_k (K_k on row_targets)(conj K_k on col_targets) x, x a tensor over ``axes``."""
+    lib = _lib.load()
+    out = torch.empty_like(x) if out is None else out
+    _lib.check(
+        lib.pw_kraus_axes(x.data_ptr(), out.data_ptr(), ops.data_ptr(), int(ops.shape[0]),
+                          _lib.i64_array(axes), len(axes), _lib.i32_array(row_targets), len(row_targets),
+                          _lib.i32_array(col_targets), len(col_targets), A.code(x.dtype), A.stream_ptr()),
+        "pw_kraus_axes",
+    )
+    return out
+
+
+def sums_strided(x: torch.Tensor, offset: int, rest, tgt, real_part: bool):
+    """Un-normalised float64 sums over the ``rest`` view per joint index of the ``tgt`` view."""
+    lib = _lib.load()
+    t = math.prod(e for e, _ in tgt) if tgt else 1
+    out = torch.empty((t,), dtype=torch.float64, device=x.device)
+    re, rs, nr = _view(rest)
+    te, ts, nt = _view(tgt)
+    _lib.check(
+        lib.pw_sums_strided(x.data_ptr() + int(offset) * _esize(x.dtype), re, rs, nr, te, ts, nt,
+                            int(bool(real_part)), out.data_ptr(), A.code(x.dtype), A.stream_ptr()),
+        "pw_sums_strided",
+    )
+    return out
+
+
+def probs_from_sums(sums: torch.Tensor, cdtype: torch.dtype):
+    lib = _lib.load()
+    out = torch.empty((sums.numel(),), dtype=A.real_dtype(cdtype), device=sums.device)
+    _lib.check(lib.pw_probs_from_sums(sums.data_ptr(), int(sums.numel()), out.data_ptr(), A.code(cdtype),
+                                      A.stream_ptr()), "pw_probs_from_sums")
+    return out
+
+
+def trace_strided(x: torch.Tensor, offset: int, rest, rows, cols):
+    lib = _lib.load()
+    tr = math.prod(e for e, _ in rows) if rows else 1
+    tc = math.prod(e for e, _ in cols) if cols else 1
+    out = torch.empty((tr, tc), dtype=x.dtype, device=x.device)
+    re, rs, nr = _view(rest)
+    we, ws, nw = _view(rows)
+    ce, cs, nc = _view(cols)
+    _lib.check(
+        lib.pw_trace_strided(x.data_ptr() + int(offset) * _esize(x.dtype), re, rs, nr, we, ws, nw,
+                             ce, cs, nc, out.data_ptr(), A.code(x.dtype), A.stream_ptr()),
+        "pw_trace_strided",
+    )
+    return out
+
+
+def gather_strided(x: torch.Tensor, offset: int, view, probs_t, outcome, mode: int):
+    """Contiguous copy of a strided view, divided by 1 / sqrt(p_o + 1e-18) / (p_o + 1e-18)."""
+    lib = _lib.load()
+    n = math.prod(e for e, _ in view) if view else 1
+    out = torch.empty((n,), dtype=x.dtype, device=x.device)
+    ve, vs, nv = _view(view)
+    _lib.check(
+        lib.pw_gather_strided(x.data_ptr() + int(offset) * _esize(x.dtype), ve, vs, nv, out.data_ptr(),
+                              probs_t.data_ptr() if probs_t is not None else None,
+                              outcome.data_ptr() if outcome is not None else None, int(mode),
+                              A.code(x.dtype), A.stream_ptr()),
+        "pw_gather_strided",
+    )
+    return out
+
+
 def rng_split(key, num: int = 2) -> np.ndarray:
     lib = _lib.load()
     k0, k1 = A.key_words(key)

@@ -700,38 +700,64 @@ extern "C" int pw_apply_vec(const void* psi, void* out, const void* op, const in
   return apply_axes(psi, out, op, dims, n, targets, nt, false, dtype, (cudaStream_t)stream);
 }
 
+// A (possibly rectangular) block of a density matrix as a tensor over `naxes` axes with the
+// operator acting on `rows` (as O) and on `cols` (as conj(O)).  pw_apply_mat / pw_kraus_mat
+// use axes = dims ++ dims; the multi-GPU layer passes a rank's row slab (pw_kraus_axes).
 struct MatrixReq {
   int64_t axes[kMaxAxes];
   int rows[kMaxTargets], cols[kMaxTargets], both[kMaxTargets];
-  int n, nt;
-  uint64_t t, N;
+  int naxes, ntr, ntc;
+  uint64_t t, total;  // operator dimension; elements of the block
 };
+
+static int matrix_req_axes(const int64_t* axes, int naxes, const int32_t* rows, int ntr,
+                           const int32_t* cols, int ntc, MatrixReq* r) {
+  if (!axes || !rows || !cols || naxes < 2 || naxes > kMaxAxes || ntr < 1 || ntc < 1 ||
+      ntr + ntc > kMaxTargets)
+    return PW_ERR_INVALID;
+  r->naxes = naxes; r->ntr = ntr; r->ntc = ntc; r->t = 1; r->total = 1;
+  for (int i = 0; i < naxes; ++i) {
+    if (axes[i] < 1) return PW_ERR_INVALID;
+    r->axes[i] = axes[i];
+    if (r->total > (1ull << 62) / (uint64_t)axes[i]) return PW_ERR_INVALID;
+    r->total *= (uint64_t)axes[i];
+  }
+  uint64_t tc = 1;
+  for (int k = 0; k < ntr; ++k) {
+    if (rows[k] < 0 || rows[k] >= naxes) return PW_ERR_INVALID;
+    r->rows[k] = r->both[k] = rows[k];
+    r->t *= (uint64_t)axes[rows[k]];
+  }
+  for (int k = 0; k < ntc; ++k) {
+    if (cols[k] < 0 || cols[k] >= naxes) return PW_ERR_INVALID;
+    r->cols[k] = r->both[ntr + k] = cols[k];
+    tc *= (uint64_t)axes[cols[k]];
+  }
+  if (tc != r->t) return PW_ERR_INVALID;  // the same operator acts on both sides
+  return PW_OK;
+}
 
 static int matrix_req(const int64_t* dims, int n, const int32_t* targets, int nt, MatrixReq* r) {
   if (!dims || !targets || n < 1 || n > PW_MAX_SUBSYSTEMS || nt < 1 || nt > PW_MAX_TARGETS)
     return PW_ERR_INVALID;
-  r->n = n; r->nt = nt; r->t = 1; r->N = 1;
-  for (int i = 0; i < n; ++i) {
-    if (dims[i] < 1) return PW_ERR_INVALID;
-    r->axes[i] = r->axes[n + i] = dims[i];
-    r->N *= (uint64_t)dims[i];
-  }
+  int64_t axes[kMaxAxes];
+  int32_t rows[PW_MAX_TARGETS], cols[PW_MAX_TARGETS];
+  for (int i = 0; i < n; ++i) axes[i] = axes[n + i] = dims[i];
   for (int k = 0; k < nt; ++k) {
     if (targets[k] < 0 || targets[k] >= n) return PW_ERR_INVALID;
-    r->rows[k] = r->both[k] = targets[k];
-    r->cols[k] = r->both[nt + k] = n + targets[k];
-    r->t *= (uint64_t)dims[targets[k]];
+    rows[k] = targets[k];
+    cols[k] = n + targets[k];
   }
-  return PW_OK;
+  return matrix_req_axes(axes, 2 * n, rows, nt, cols, nt, r);
 }
 
 // S = sum_k K_k (x) conj(K_k) on the device, then the block-structured kernel on the
 // (row targets, column targets) of the doubled tensor: ONE HBM pass whatever K is.
 static int try_super_blocks(const void* rho, void* out, const void* ops, int K, const MatrixReq& r,
                             int dtype, cudaStream_t s, Scratch* super, BlockDesc* bd) {
-  if (rho == out || r.t * r.t > kBlockMaxT || r.N * r.N < matrix_min_elems(K, r.t)) return PW_ERR_UNSUPPORTED;
+  if (rho == out || r.t * r.t > kBlockMaxT || r.total < matrix_min_elems(K, r.t)) return PW_ERR_UNSUPPORTED;
   Plan p;
-  PW_TRY(build_plan_axes(r.axes, 2 * r.n, r.both, 2 * r.nt, &p));
+  PW_TRY(build_plan_axes(r.axes, r.naxes, r.both, r.ntr + r.ntc, &p));
   const uint64_t r_in = inner_rest_run(p);
   const bool staged = mat_mode() == 0 && r_in < (uint64_t)options().small_r.load(std::memory_order_relaxed);
   if (staged && (r_in != 0 || !options().seg_kernel.load(std::memory_order_relaxed)))
@@ -741,7 +767,7 @@ static int try_super_blocks(const void* rho, void* out, const void* ops, int K, 
   PW_TRY(super->alloc(es * tt * tt, s));
   PW_TRY(build_superoperator(ops, K, (uint32_t)r.t, super->p, dtype, s));
   if (staged)  // the column target is the innermost axis: warp-staged block kernel
-    return launch_blocks_seg(rho, out, super->p, r.axes, 2 * r.n, r.both, 2 * r.nt, dtype, false, bd, s);
+    return launch_blocks_seg(rho, out, super->p, r.axes, r.naxes, r.both, r.ntr + r.ntc, dtype, false, bd, s);
   return launch_blocks(rho, out, super->p, p, dtype, false, bd, s);
 }
 
@@ -751,10 +777,10 @@ static int apply_side(const void* in, void* out, const void* op, const MatrixReq
   const int* tg = cols ? r.cols : r.rows;
   if (r.t <= 8 || skip || accumulate) {
     Plan p;
-    PW_TRY(build_plan_axes(r.axes, 2 * r.n, tg, r.nt, &p));
+    PW_TRY(build_plan_axes(r.axes, r.naxes, tg, cols ? r.ntc : r.ntr, &p));
     return launch_apply(in, out, op, p, dtype, cols, accumulate, s, skip);
   }
-  return apply_axes(in, out, op, r.axes, 2 * r.n, tg, r.nt, cols, dtype, s);
+  return apply_axes(in, out, op, r.axes, r.naxes, tg, cols ? r.ntc : r.ntr, cols, dtype, s);
 }
 
 // fallback: two HBM passes per operator (row side, then conj on the column side)
@@ -766,7 +792,7 @@ static int two_pass(const void* rho, void* out, const void* ops, int K, const Ma
       // large operators: keep BOTH sides out of place (rho -> tmp -> out) so each side can
       // take the block-structured kernels (a beam splitter on rho: 2 x ~90 % passes)
       Scratch tmp2;
-      if (tmp2.alloc((size_t)(r.N * r.N) * es, s) == PW_OK) {
+      if (tmp2.alloc((size_t)r.total * es, s) == PW_OK) {
         // (with a skip flag the sides run the skippable kernels; in place would cost an
         // unconditional copy of rho)
         PW_TRY(apply_side(rho, tmp2.p, ops, r, false, false, dtype, s, skip));
@@ -777,7 +803,7 @@ static int two_pass(const void* rho, void* out, const void* ops, int K, const Ma
     return apply_side(out, out, ops, r, true, false, dtype, s, skip);
   }
   // out = sum_k (K_k rho) K_k^dagger; tmp holds K_k rho, the column pass accumulates
-  const size_t bytes = (size_t)(r.N * r.N) * es, op_bytes = (size_t)(r.t * r.t) * es;
+  const size_t bytes = (size_t)r.total * es, op_bytes = (size_t)(r.t * r.t) * es;
   Scratch tmp, src;
   PW_TRY(tmp.alloc(bytes, s));
   const void* in = rho;
@@ -794,10 +820,8 @@ static int two_pass(const void* rho, void* out, const void* ops, int K, const Ma
   return PW_OK;
 }
 
-static int matrix_dispatch(const void* rho, void* out, const void* ops, int K, const int64_t* dims,
-                           int n, const int32_t* targets, int nt, int dtype, cudaStream_t s) {
-  MatrixReq r;
-  PW_TRY(matrix_req(dims, n, targets, nt, &r));
+static int matrix_dispatch(const void* rho, void* out, const void* ops, int K, const MatrixReq& r,
+                           int dtype, cudaStream_t s) {
   const int mm = mat_mode();
   const size_t es = elem_size(dtype);
   Scratch super;
@@ -813,7 +837,7 @@ static int matrix_dispatch(const void* rho, void* out, const void* ops, int K, c
     if (rc == PW_OK && K > 1 && mm == 0 && !bd.staged && r.t * r.t <= 64 &&
         options().dense_mma.load(std::memory_order_relaxed)) {
       Plan pb;
-      PW_TRY(build_plan_axes(r.axes, 2 * r.n, r.both, 2 * r.nt, &pb));
+      PW_TRY(build_plan_axes(r.axes, r.naxes, r.both, r.ntr + r.ntc, &pb));
       const int rc2 = launch_dense_mma(rho, out, super.p, pb, dtype, false, s, skip);
       if (rc2 != PW_ERR_UNSUPPORTED) return rc2;
     }
@@ -821,15 +845,15 @@ static int matrix_dispatch(const void* rho, void* out, const void* ops, int K, c
   // single operator, untouched innermost axis: ONE pass through shared-memory tiles
   // (dense d <= 8 operators, beam-splitter-like block structure); decided on the device
   TwoSided ts;
-  if (K == 1 && mm == 0 && rho != out && r.t >= 2 && r.t <= kBlockMaxT && r.N * r.N >= matrix_min_elems(K, r.t) &&
+  if (K == 1 && mm == 0 && rho != out && r.t >= 2 && r.t <= kBlockMaxT && r.total >= matrix_min_elems(K, r.t) &&
       options().two_sided.load(std::memory_order_relaxed)) {
     Plan pb, pr, pc;
-    PW_TRY(build_plan_axes(r.axes, 2 * r.n, r.both, 2 * r.nt, &pb));
+    PW_TRY(build_plan_axes(r.axes, r.naxes, r.both, r.ntr + r.ntc, &pb));
     // (innermost axis a target: launch_two_sided takes the geometries it has a kernel for)
     const uint64_t r_in = inner_rest_run(pb);
     if (r_in >= 4 || r_in == 0) {
-      PW_TRY(build_plan_axes(r.axes, 2 * r.n, r.rows, r.nt, &pr));
-      PW_TRY(build_plan_axes(r.axes, 2 * r.n, r.cols, r.nt, &pc));
+      PW_TRY(build_plan_axes(r.axes, r.naxes, r.rows, r.ntr, &pr));
+      PW_TRY(build_plan_axes(r.axes, r.naxes, r.cols, r.ntc, &pc));
       const int rc = launch_two_sided(rho, out, ops, pb.fm, pr.tm, pc.tm, dtype, skip, &ts, s);
       if (rc == PW_OK) skip = ts.skip;
       else if (rc != PW_ERR_UNSUPPORTED) return rc;
@@ -847,9 +871,9 @@ static int matrix_dispatch(const void* rho, void* out, const void* ops, int K, c
     TiledGeom g;
     int rc = PW_ERR_UNSUPPORTED;
     if (super_mode) {
-      if (plan_tiled(r.axes, 2 * n, r.both, 2 * nt, nullptr, 0, -1, es, tile_elems(dtype), &g))
+      if (plan_tiled(r.axes, r.naxes, r.both, r.ntr + r.ntc, nullptr, 0, -1, es, tile_elems(dtype), &g))
         rc = launch_tiled(rho, out, ops, K, g, kModeMatrixSuper, dtype, s, skip);
-    } else if (plan_tiled(r.axes, 2 * n, r.rows, nt, r.cols, nt, -1, es, tile_elems(dtype), &g)) {
+    } else if (plan_tiled(r.axes, r.naxes, r.rows, r.ntr, r.cols, r.ntc, -1, es, tile_elems(dtype), &g)) {
       rc = launch_tiled(rho, out, ops, K, g, kModeMatrixTwoSided, dtype, s, skip);
     }
     if (rc != PW_ERR_UNSUPPORTED) return rc;
@@ -860,10 +884,10 @@ static int matrix_dispatch(const void* rho, void* out, const void* ops, int K, c
   // (measured: wins for d <= 4; for larger d the register tile limits occupancy and two
   //  register-kernel passes are faster -- profiles/r1_kbench_mat_v6.txt)
   const uint64_t pair_max_d = (uint64_t)options().mat_pair_max_d.load(std::memory_order_relaxed);
-  if (K == 1 && nt == 1 && rho != out && mm != 1 && r.t <= pair_max_d) {
+  if (K == 1 && r.ntr == 1 && r.ntc == 1 && rho != out && mm != 1 && r.t <= pair_max_d) {
     const int tg[2] = {r.rows[0], r.cols[0]};
     Plan p;
-    PW_TRY(build_plan_axes(r.axes, 2 * n, tg, 2, &p));
+    PW_TRY(build_plan_axes(r.axes, r.naxes, tg, 2, &p));
     int rc;
     if (dtype == PW_C128)
       rc = launch_pair_t<double2>((const double2*)rho, (double2*)out, (const double2*)ops,
@@ -880,7 +904,9 @@ extern "C" int pw_apply_mat(const void* rho, void* out, const void* op, const in
                             int n, const int32_t* targets, int nt, int dtype, void* stream) {
   if (!rho || !out || !op) return PW_ERR_INVALID;
   if (dtype != PW_C64 && dtype != PW_C128) return PW_ERR_INVALID;
-  return matrix_dispatch(rho, out, op, 1, dims, n, targets, nt, dtype, (cudaStream_t)stream);
+  MatrixReq r;
+  PW_TRY(matrix_req(dims, n, targets, nt, &r));
+  return matrix_dispatch(rho, out, op, 1, r, dtype, (cudaStream_t)stream);
 }
 
 extern "C" int pw_kraus_mat(const void* rho, void* out, const void* ops, int K,
@@ -888,7 +914,19 @@ extern "C" int pw_kraus_mat(const void* rho, void* out, const void* ops, int K,
                             int dtype, void* stream) {
   if (!rho || !out || !ops || K < 1) return PW_ERR_INVALID;
   if (dtype != PW_C64 && dtype != PW_C128) return PW_ERR_INVALID;
-  return matrix_dispatch(rho, out, ops, K, dims, n, targets, nt, dtype, (cudaStream_t)stream);
+  MatrixReq r;
+  PW_TRY(matrix_req(dims, n, targets, nt, &r));
+  return matrix_dispatch(rho, out, ops, K, r, dtype, (cudaStream_t)stream);
+}
+
+extern "C" int pw_kraus_axes(const void* x, void* out, const void* ops, int K, const int64_t* axes,
+                             int naxes, const int32_t* row_targets, int ntr,
+                             const int32_t* col_targets, int ntc, int dtype, void* stream) {
+  if (!x || !out || !ops || K < 1) return PW_ERR_INVALID;
+  if (dtype != PW_C64 && dtype != PW_C128) return PW_ERR_INVALID;
+  MatrixReq r;
+  PW_TRY(matrix_req_axes(axes, naxes, row_targets, ntr, col_targets, ntc, &r));
+  return matrix_dispatch(x, out, ops, K, r, dtype, (cudaStream_t)stream);
 }
 
 extern "C" int pw_apply_vec_pair(const void* psi, void* out, const void* op_a, const void* op_b,

@@ -97,6 +97,73 @@ k_probs_partial_wide(const V* __restrict__ x, const FiberMap fm, const TargetMap
   if (threadIdx.x == 0) partial[(size_t)c * tm.t + j] = r;
 }
 
+__global__ void __launch_bounds__(256)
+k_sums_finalize(const double* __restrict__ partial, const int nblocks, const uint32_t t,
+                double* __restrict__ sums) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= t) return;
+  double p = 0;
+  for (int b = 0; b < nblocks; ++b) p += partial[(size_t)b * t + j];
+  sums[j] = p;
+}
+
+// probs[j] = sums[j] / sum(sums), divided in the state's real dtype like k_probs_finalize
+template <typename R>
+__global__ void __launch_bounds__(256)
+k_probs_from_sums(const double* __restrict__ sums, const uint32_t t, R* __restrict__ probs) {
+  __shared__ double s_scratch[8];
+  __shared__ double s_total;
+  double local = 0;
+  for (uint32_t j = threadIdx.x; j < t; j += blockDim.x) local += sums[j];
+  const double tot = block_sum(local, s_scratch);
+  if (threadIdx.x == 0) s_total = tot;
+  __syncthreads();
+  for (uint32_t j = threadIdx.x; j < t; j += blockDim.x) probs[j] = (R)((R)sums[j] / (R)s_total);
+}
+
+// ---- strided views (multi-GPU layer) ----------------------------------------------------
+// out[j * tc + j'] = sum_f x[base(f) + row(j) + col(j')]: the partial trace of a block of rho
+// whose rows / columns / traced pairs are arbitrary strided axes
+template <typename V>
+__global__ void __launch_bounds__(kRedBlock)
+k_trace_strided(const V* __restrict__ x, const FiberMap fm, const TargetMap rows, const TargetMap cols,
+                V* __restrict__ out) {
+  __shared__ double s_scratch[4];
+  const uint64_t nout = (uint64_t)rows.t * cols.t;
+  for (uint64_t o = blockIdx.x; o < nout; o += gridDim.x) {
+    const int64_t off = rows.offset((uint32_t)(o / cols.t)) + cols.offset((uint32_t)(o % cols.t));
+    double re = 0, im = 0;
+    for (uint64_t f = threadIdx.x; f < fm.nfib; f += blockDim.x) {
+      const V v = x[off + fm.base(f)];
+      re += v.x; im += v.y;
+    }
+    re = block_sum(re, s_scratch);
+    im = block_sum(im, s_scratch);
+    if (threadIdx.x == 0) { V v; v.x = re; v.y = im; out[o] = v; }
+  }
+}
+
+// out[f] = x[base(f)] / den,  den = 1 | sqrt(probs[o] + 1e-18) | probs[o] + 1e-18 (the collapse
+// rescaling of core/kernels.py:205,225 on a strided slice)
+template <typename V>
+__global__ void k_gather_strided(const V* __restrict__ x, V* __restrict__ out, const FiberMap fm,
+                                 const typename RealOf<V>::type* __restrict__ probs,
+                                 const int64_t* __restrict__ outcome, const int mode) {
+  using R = typename RealOf<V>::type;
+  R den = (R)1;
+  if (mode && probs) {
+    const R p = probs[*outcome] + (R)1e-18;
+    den = mode == 1 ? sqrt(p) : p;
+  }
+  for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < fm.nfib;
+       f += (uint64_t)gridDim.x * blockDim.x) {
+    V v = x[fm.base(f)];
+    v.x = v.x / den;
+    v.y = v.y / den;
+    out[f] = v;
+  }
+}
+
 template <typename R>
 __global__ void __launch_bounds__(256)
 k_probs_finalize(const double* __restrict__ partial, const int nblocks, const uint32_t t,
@@ -158,7 +225,7 @@ static void launch_probs_small(const V* x, const Plan& p, int64_t mult, bool dia
 
 template <typename V>
 static int probs_impl(const V* x, void* probs, const Plan& p, int64_t mult, bool diag,
-                      cudaStream_t s) {
+                      cudaStream_t s, bool raw = false) {
   using R = typename RealOf<V>::type;
   const uint32_t t = p.tm.t;
   const size_t smem = ((size_t)t * kRedBlock + 4) * sizeof(double) + (size_t)t * sizeof(int64_t);
@@ -201,7 +268,10 @@ static int probs_impl(const V* x, void* probs, const Plan& p, int64_t mult, bool
       k_probs_partial_wide<V, false><<<nblocks * t, kRedBlock, 0, s>>>(x, p.fm, p.tm, mult, nblocks, (double*)partial.p);
     PW_LAUNCHED();
   }
-  k_probs_finalize<R><<<1, 256, 0, s>>>((const double*)partial.p, nblocks, t, (R*)probs);
+  if (raw)  // un-normalised double sums: the multi-GPU layer adds them across ranks first
+    k_sums_finalize<<<(t + 255) / 256, 256, 0, s>>>((const double*)partial.p, nblocks, t, (double*)probs);
+  else
+    k_probs_finalize<R><<<1, 256, 0, s>>>((const double*)partial.p, nblocks, t, (R*)probs);
   PW_LAUNCHED();
   return PW_OK;
 }
@@ -898,6 +968,114 @@ extern "C" int pw_probs_mat(const void* rho, void* probs, const int64_t* dims, i
   Plan p;  // plan over the n-axis index; offsets are scaled by N+1 to walk the diagonal
   PW_TRY(build_plan(dims, n, targets, nt, &p));
   return PW_DISPATCH(dtype, probs_mat_t, rho, probs, p, (cudaStream_t)stream);
+}
+
+// ---- strided views: maps straight from (extent, stride) lists -----------------------------
+static int strided_fibers(const int64_t* extent, const int64_t* stride, int n, FiberMap* fm) {
+  if (n < 0 || (n && (!extent || !stride))) return PW_ERR_INVALID;
+  fm->ng = 0;
+  fm->nfib = 1;
+  for (int i = 0; i < n; ++i) {
+    if (extent[i] < 1) return PW_ERR_INVALID;
+    if (extent[i] == 1) continue;
+    if (fm->nfib > (1ull << 62) / (uint64_t)extent[i]) return PW_ERR_INVALID;
+    fm->nfib *= (uint64_t)extent[i];
+    // merge with the previous group when the two walk one contiguous run
+    if (fm->ng > 0 && fm->gstride[fm->ng - 1] == stride[i] * extent[i]) {
+      fm->gsize[fm->ng - 1] *= (uint64_t)extent[i];
+      fm->gstride[fm->ng - 1] = stride[i];
+      continue;
+    }
+    if (fm->ng >= kMaxGroups) return PW_ERR_UNSUPPORTED;
+    fm->gsize[fm->ng] = (uint64_t)extent[i];
+    fm->gstride[fm->ng] = stride[i];
+    ++fm->ng;
+  }
+  return PW_OK;
+}
+
+static int strided_targets(const int64_t* extent, const int64_t* stride, int n, TargetMap* tm) {
+  if (n < 0 || n > kMaxTargets || (n && (!extent || !stride))) return PW_ERR_INVALID;
+  tm->nt = n;
+  uint64_t t = 1;
+  for (int i = 0; i < n; ++i) {
+    if (extent[i] < 1) return PW_ERR_INVALID;
+    tm->tdim[i] = (uint32_t)extent[i];
+    tm->tstride[i] = stride[i];
+    t *= (uint64_t)extent[i];
+    if (t > 0xffffffffull) return PW_ERR_UNSUPPORTED;
+  }
+  tm->t = (uint32_t)t;
+  return PW_OK;
+}
+
+template <typename V>
+static int sums_strided_t(const void* x, double* sums, const Plan& p, int real_part, cudaStream_t s) {
+  return probs_impl<V>((const V*)x, sums, p, 1, real_part != 0, s, true);
+}
+
+extern "C" int pw_sums_strided(const void* x, const int64_t* rest_extent, const int64_t* rest_stride,
+                               int nrest, const int64_t* tgt_extent, const int64_t* tgt_stride,
+                               int ntgt, int real_part, double* sums, int dtype, void* stream) {
+  if (!x || !sums) return PW_ERR_INVALID;
+  Plan p;
+  PW_TRY(strided_fibers(rest_extent, rest_stride, nrest, &p.fm));
+  PW_TRY(strided_targets(tgt_extent, tgt_stride, ntgt, &p.tm));
+  p.N = p.fm.nfib * p.tm.t;
+  return PW_DISPATCH(dtype, sums_strided_t, x, sums, p, real_part, (cudaStream_t)stream);
+}
+
+extern "C" int pw_probs_from_sums(const double* sums, int64_t t, void* probs, int dtype, void* stream) {
+  if (!sums || !probs || t < 1 || t > 0xffffffffll) return PW_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == PW_C128) k_probs_from_sums<double><<<1, 256, 0, s>>>(sums, (uint32_t)t, (double*)probs);
+  else if (dtype == PW_C64) k_probs_from_sums<float><<<1, 256, 0, s>>>(sums, (uint32_t)t, (float*)probs);
+  else return PW_ERR_INVALID;
+  PW_LAUNCHED();
+  return PW_OK;
+}
+
+template <typename V>
+static int trace_strided_t(const void* x, void* out, const FiberMap& fm, const TargetMap& rows,
+                           const TargetMap& cols, cudaStream_t s) {
+  const uint64_t nout = (uint64_t)rows.t * cols.t;
+  const int grid = (int)(nout < (uint64_t)kNumSMs * 16 ? nout : (uint64_t)kNumSMs * 16);
+  k_trace_strided<V><<<grid, kRedBlock, 0, s>>>((const V*)x, fm, rows, cols, (V*)out);
+  PW_LAUNCHED();
+  return PW_OK;
+}
+
+extern "C" int pw_trace_strided(const void* x, const int64_t* rest_extent, const int64_t* rest_stride,
+                                int nrest, const int64_t* row_extent, const int64_t* row_stride, int nrow,
+                                const int64_t* col_extent, const int64_t* col_stride, int ncol, void* out,
+                                int dtype, void* stream) {
+  if (!x || !out) return PW_ERR_INVALID;
+  FiberMap fm;
+  TargetMap rows, cols;
+  PW_TRY(strided_fibers(rest_extent, rest_stride, nrest, &fm));
+  PW_TRY(strided_targets(row_extent, row_stride, nrow, &rows));
+  PW_TRY(strided_targets(col_extent, col_stride, ncol, &cols));
+  if ((uint64_t)rows.t * cols.t > 0xffffffffull) return PW_ERR_UNSUPPORTED;
+  return PW_DISPATCH(dtype, trace_strided_t, x, out, fm, rows, cols, (cudaStream_t)stream);
+}
+
+template <typename V>
+static int gather_strided_t(const void* x, void* out, const FiberMap& fm, const void* probs,
+                            const int64_t* outcome, int mode, cudaStream_t s) {
+  using R = typename RealOf<V>::type;
+  k_gather_strided<V><<<grid_for(fm.nfib, 256, 8), 256, 0, s>>>((const V*)x, (V*)out, fm, (const R*)probs,
+                                                              outcome, mode);
+  PW_LAUNCHED();
+  return PW_OK;
+}
+
+extern "C" int pw_gather_strided(const void* x, const int64_t* extent, const int64_t* stride, int naxes,
+                                 void* out, const void* probs, const int64_t* outcome, int mode,
+                                 int dtype, void* stream) {
+  if (!x || !out || mode < 0 || mode > 2 || (mode && (!probs || !outcome))) return PW_ERR_INVALID;
+  FiberMap fm;
+  PW_TRY(strided_fibers(extent, stride, naxes, &fm));
+  return PW_DISPATCH(dtype, gather_strided_t, x, out, fm, probs, outcome, mode, (cudaStream_t)stream);
 }
 
 template <typename V>

@@ -1,10 +1,12 @@
 """
-Multi-GPU state vectors: one process per GPU, the state block-sharded over its
-leading subsystem axes, operators on local axes applied without communication, and
-an all-to-all AXIS SWAP (NCCL over NVLink) when an operator touches a sharded axis.
+Multi-GPU states: one process per GPU, the state block-sharded over its leading subsystem
+axes, operators on local axes applied without communication, and an all-to-all AXIS SWAP
+(peer reads over NVLink, or NCCL) when an operator touches a sharded axis.
 
-The reference has no distributed code at all; this is the
-B200-native design of BASELINE.json's north_star.
+The reference has no distributed code at all; this is the B200-native
+design of BASELINE.json's north_star.  Per block the arithmetic is the
+reference's: apply ``core/kernels.py:62-98``, U rho U^dagger / Kraus ``:101-186``, measurement
+probabilities ``:28-59``, collapse ``:189-227``, partial trace ``:301-319``.
 
 Layout bookkeeping
 ------------------
@@ -14,24 +16,34 @@ The local buffer is a row-major tensor over *virtual axes*.  A virtual axis
     index_g = sum over local virtual axes of g (coordinate * weight)
             + sum over sharded parts of g     (rank digit  * weight)
 
-``sparts`` lists the parts that are sharded (their coordinate is a digit of the
-rank, most significant first).  An operator on subsystem ``g`` is applied to all
-local virtual axes of ``g`` at once (ordered by weight, descending), which is exactly
-the multi-target strided kernel of libpwb200 -- no local transpose is ever needed.
+``sparts`` lists the parts that are sharded (their coordinate is a digit of the rank, most
+significant first).  An operator on subsystem ``g`` is applied to all local virtual axes of
+``g`` at once (ordered by weight, descending), which is exactly the multi-target strided
+kernel of libpwb200 -- no local transpose is ever needed.
 
-Axis swap (``relayout``): pick virtual axes whose extents multiply to the world
-size, bring them to the front of the buffer (a pack pass, skipped when they already
-lead -- the steady state when two layouts alternate), run ONE all_to_all_single over
-all ranks, and relabel: the received leading axes are the previously sharded parts
-(now local), the picked axes become the rank digits.
+Axis swap (``relayout``): pick virtual axes whose extents multiply to the world size, bring
+them to the front of the buffer (a pack pass, skipped when they already lead -- the steady
+state when two layouts alternate), run ONE all-to-all over all ranks, and relabel: the
+received leading axes are the previously sharded parts (now local), the picked axes become
+the rank digits.
+
+A density matrix is the same machinery over the ``2n`` subsystems ``dims ++ dims`` (rows, then
+columns) with only ROW subsystems ever sharded: the column side of every block is complete, so
+``U rho U^dagger`` / Kraus need the swap for the row side only.
+
+Reductions never move the state: each rank reduces its block (``pw_sums_strided`` /
+``pw_trace_strided`` / ``pw_reduced_from_vec``), ONE all-reduce of ``t`` or ``t^2`` numbers
+combines them.  A measurement of a sharded axis collapses on the OWNING ranks (the others
+drop their block) and the post state, ``t`` times smaller, is spread over all ranks again.
 """
 
 from __future__ import annotations
 
 import math
 from dataclasses import dataclass
-from typing import Any, List, Optional, Sequence, Tuple
+from typing import Any, Dict, List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 
@@ -40,6 +52,10 @@ class VAxis:
     g: int        # global subsystem index
     extent: int
     weight: int   # multiplier of this coordinate inside subsystem g's index
+
+
+class PeerUnavailable(RuntimeError):
+    """CUDA IPC peer memory could not be set up on EVERY rank (decided collectively)."""
 
 
 class _RawCuda:
@@ -55,6 +71,12 @@ class PeerBuffers:
     """
     Ping-pong shard buffers allocated by libpwb200 (cudaMalloc) and exported with CUDA IPC,
     so every rank can read every other rank's shard directly over NVLink.
+
+    Construction is COLLECTIVE and all-or-nothing: every rank takes part in both exchanges
+    whatever happened locally (a failed allocation travels as a sentinel), the outcome is agreed
+    on, and either every rank gets working peer buffers or every rank raises PeerUnavailable
+    with its own allocations released -- no rank is left waiting in a collective the others
+    skipped, and no rank runs the NCCL swap while its peers run the peer-memory one.
     """
 
     def __init__(self, numel: int, dtype: torch.dtype, nbuf: int, rank: int, world: int, dist: Any,
@@ -68,29 +90,44 @@ class PeerBuffers:
         self.esize = 16 if dtype == torch.complex128 else 8
         self._lib = lib
         self.local_ptrs: List[int] = []
-        handles = []
-        for _ in range(nbuf):
-            ptr = C.c_void_p()
-            h = (C.c_ubyte * 64)()
-            _lib.check(lib.pw_peer_alloc(numel * self.esize, C.byref(ptr), h), "pw_peer_alloc")
-            self.local_ptrs.append(int(ptr.value))
-            handles.append(bytes(h))
-        gathered: List[Any] = [None] * world
-        dist.all_gather_object(gathered, handles)
-        self.ptrs: List[List[int]] = []  # [buffer][rank]
         self._opened: List[int] = []
-        for b in range(nbuf):
-            row = []
-            for r in range(world):
-                if r == rank:
-                    row.append(self.local_ptrs[b])
-                else:
-                    ptr = C.c_void_p()
-                    h = (C.c_ubyte * 64).from_buffer_copy(gathered[r][b])
-                    _lib.check(lib.pw_peer_open(h, C.byref(ptr)), "pw_peer_open")
-                    row.append(int(ptr.value))
-                    self._opened.append(int(ptr.value))
-            self.ptrs.append(row)
+        handles: Optional[List[bytes]] = []
+        error = None
+        try:
+            for _ in range(nbuf):
+                ptr = C.c_void_p()
+                h = (C.c_ubyte * 64)()
+                _lib.check(lib.pw_peer_alloc(numel * self.esize, C.byref(ptr), h), "pw_peer_alloc")
+                self.local_ptrs.append(int(ptr.value))
+                handles.append(bytes(h))
+        except Exception as exc:  # noqa: BLE001 -- reported collectively below
+            error, handles = f"rank {rank}: {exc}", None
+        gathered: List[Any] = [None] * world
+        dist.all_gather_object(gathered, handles)          # unconditional: sentinel None on failure
+        if any(g is None for g in gathered):
+            self.close()
+            raise PeerUnavailable(error or "a peer rank could not allocate / export its shard buffers")
+        self.ptrs: List[List[int]] = []  # [buffer][rank]
+        try:
+            for b in range(nbuf):
+                row = []
+                for r in range(world):
+                    if r == rank:
+                        row.append(self.local_ptrs[b])
+                    else:
+                        ptr = C.c_void_p()
+                        h = (C.c_ubyte * 64).from_buffer_copy(gathered[r][b])
+                        _lib.check(lib.pw_peer_open(h, C.byref(ptr)), "pw_peer_open")
+                        row.append(int(ptr.value))
+                        self._opened.append(int(ptr.value))
+                self.ptrs.append(row)
+        except Exception as exc:  # noqa: BLE001
+            error = f"rank {rank}: {exc}"
+        flags: List[Any] = [None] * world
+        dist.all_gather_object(flags, error)                # agree on the outcome of the mapping
+        if any(f is not None for f in flags):
+            self.close()
+            raise PeerUnavailable(next(f for f in flags if f is not None))
         typestr = "<c16" if dtype == torch.complex128 else "<c8"
         self.tensors = [
             torch.as_tensor(_RawCuda(p, numel, typestr), device=torch.device("cuda", device))
@@ -117,6 +154,7 @@ class PeerBuffers:
 class CudaBackend:
     """Local arithmetic through libpwb200 (the product path)."""
 
+    # ---- peer memory ------------------------------------------------------------------
     def gather_chunks(self, srcs: List[int], chunk_elems: int, out: torch.Tensor, rank: int = 0) -> None:
         import ctypes as C
 
@@ -130,7 +168,7 @@ class CudaBackend:
 
     def apply_vec_gather(self, srcs: List[int], chunk_elems: int, out: torch.Tensor, op: torch.Tensor,
                          dims, targets, rank: int = 0) -> bool:
-        """Fused swap + apply; False when the shape is outside the fused kernel (t > 8)."""
+        """Fused swap + apply; False when the shape is outside the fused kernels."""
         import ctypes as C
 
         from . import _lib
@@ -146,20 +184,57 @@ class CudaBackend:
         _lib.check(rc, "pw_apply_vec_gather")
         return True
 
+    # ---- apply ------------------------------------------------------------------------
     def apply_vec(self, local: torch.Tensor, op: torch.Tensor, dims, targets, out=None):
         from .core import ffi
 
         return ffi.apply_vec(local, op, dims, targets, out=out)
+
+    def kraus_axes(self, local: torch.Tensor, ops: torch.Tensor, axes, row_targets, col_targets, out=None):
+        from .core import ffi
+
+        return ffi.kraus_axes(local, ops, axes, row_targets, col_targets, out=out)
 
     def permute(self, local: torch.Tensor, dims, perm, out=None):
         from .core import ffi
 
         return ffi.permute(local, dims, perm, out=out)
 
+    # ---- reductions -------------------------------------------------------------------
     def norm2(self, local: torch.Tensor) -> torch.Tensor:
         from .core import ffi
 
         return ffi.norm_stats(local)[:1].clone()
+
+    def sums_strided(self, local, offset, rest, tgt, real_part: bool) -> torch.Tensor:
+        from .core import ffi
+
+        return ffi.sums_strided(local, offset, rest, tgt, real_part)
+
+    def probs_from_sums(self, sums: torch.Tensor, cdtype: torch.dtype) -> torch.Tensor:
+        from .core import ffi
+
+        return ffi.probs_from_sums(sums, cdtype)
+
+    def draw(self, probs: torch.Tensor, key, cdtype: torch.dtype) -> torch.Tensor:
+        from .core import ffi
+
+        return ffi.draw(probs, key, cdtype)
+
+    def trace_strided(self, local, offset, rest, rows, cols) -> torch.Tensor:
+        from .core import ffi
+
+        return ffi.trace_strided(local, offset, rest, rows, cols)
+
+    def gather_strided(self, local, offset, axes, probs, outcome, mode: int) -> torch.Tensor:
+        from .core import ffi
+
+        return ffi.gather_strided(local, offset, axes, probs, outcome, mode)
+
+    def reduced_from_vec(self, local, dims, keep) -> torch.Tensor:
+        from .core import ffi
+
+        return ffi.reduced_from_vec(local, dims, keep)
 
 
 def rank_digits(rank: int, extents: Sequence[int]) -> List[int]:
@@ -170,8 +245,31 @@ def rank_digits(rank: int, extents: Sequence[int]) -> List[int]:
     return list(reversed(digits))
 
 
-class ShardedStateVector:
-    """A state vector of ``global_dims`` block-sharded over ``world`` ranks."""
+def digits_rank(digits: Sequence[int], extents: Sequence[int]) -> int:
+    r = 0
+    for d, e in zip(digits, extents):
+        r = r * e + d
+    return r
+
+
+def _strides(extents: Sequence[int]) -> List[int]:
+    out, acc = [], 1
+    for e in reversed(extents):
+        out.append(acc)
+        acc *= e
+    return list(reversed(out))
+
+
+# ======================================================================================
+# common machinery
+# ======================================================================================
+
+
+class ShardedTensor:
+    """A tensor over ``global_dims`` block-sharded over ``world`` ranks (virtual-axis layout)."""
+
+    #: subsystems that may be sharded / swapped out (None = all)
+    _shardable: Optional[range] = None
 
     def __init__(self, global_dims: Sequence[int], local: torch.Tensor, vaxes: List[VAxis],
                  sparts: List[VAxis], rank: int, world: int, dist: Any, backend: Any,
@@ -210,8 +308,7 @@ class ShardedStateVector:
         return plan
 
     @classmethod
-    def initial_layout(cls, global_dims: Sequence[int], world: int):
-        plan = dict(cls.shard_plan(global_dims, world))
+    def _layout(cls, global_dims: Sequence[int], plan: Dict[int, int]):
         vaxes, sparts = [], []
         for g, d in enumerate(global_dims):
             f = plan.get(g, 1)
@@ -221,17 +318,18 @@ class ShardedStateVector:
         return vaxes, sparts
 
     @classmethod
-    def from_full(cls, global_dims, full: torch.Tensor, rank: int, world: int, dist, backend):
-        """Every rank holds the full vector (tests / small cases): keep only the own block."""
-        vaxes, sparts = cls.initial_layout(global_dims, world)
+    def initial_layout(cls, global_dims: Sequence[int], world: int):
+        return cls._layout(global_dims, dict(cls.shard_plan(global_dims, world)))
+
+    @staticmethod
+    def _own_block(global_dims, full: torch.Tensor, sparts, rank: int) -> torch.Tensor:
         t = full.reshape(tuple(global_dims))
         digits = rank_digits(rank, [s.extent for s in sparts])
         index = [slice(None)] * len(global_dims)
         for s, b in zip(sparts, digits):
             blk = global_dims[s.g] // s.extent
             index[s.g] = slice(b * blk, (b + 1) * blk)
-        local = t[tuple(index)].clone().reshape(-1)  # never alias the caller's buffer
-        return cls(global_dims, local, vaxes, sparts, rank, world, dist, backend)
+        return t[tuple(index)].clone().reshape(-1)  # never alias the caller's buffer
 
     # ---- helpers ----------------------------------------------------------------------
 
@@ -239,23 +337,36 @@ class ShardedStateVector:
     def local_dims(self) -> Tuple[int, ...]:
         return tuple(v.extent for v in self.vaxes)
 
+    def local_strides(self) -> List[int]:
+        return _strides(self.local_dims)
+
+    def my_digits(self) -> List[int]:
+        return rank_digits(self.rank, [s.extent for s in self.sparts])
+
     def sharded_axes(self) -> List[int]:
         return sorted({s.g for s in self.sparts})
+
+    def _parts_of(self, g: int) -> List[int]:
+        """Positions of subsystem g's local virtual axes, most significant (largest weight) first."""
+        parts = [(v.weight, i) for i, v in enumerate(self.vaxes) if v.g == g and v.extent > 1]
+        if not parts:  # a subsystem of dimension 1, or one whose whole index is sharded
+            parts = [(v.weight, i) for i, v in enumerate(self.vaxes) if v.g == g][:1]
+        parts.sort(reverse=True)
+        return [i for _, i in parts]
 
     def _targets_for(self, axes: Sequence[int]) -> List[int]:
         targets: List[int] = []
         for g in axes:
-            parts = [(v.weight, i) for i, v in enumerate(self.vaxes) if v.g == g]
-            parts.sort(reverse=True)
+            pos = self._parts_of(g)
             # the local parts must tile subsystem g's index as a mixed radix number
             expect = 1
-            for w, i in sorted(parts):
-                if w != expect:
+            for i in reversed(pos):
+                if self.vaxes[i].weight != expect and self.vaxes[i].extent > 1:
                     raise RuntimeError(f"subsystem {g} is not fully local (layout {self.vaxes})")
                 expect *= self.vaxes[i].extent
             if expect != self.global_dims[g]:
                 raise RuntimeError(f"subsystem {g} is not fully local")
-            targets += [i for _, i in parts]
+            targets += pos
         return targets
 
     def _buffers(self) -> torch.Tensor:
@@ -263,129 +374,291 @@ class ShardedStateVector:
             self.spare = torch.empty_like(self.local)
         return self.spare
 
-    # ---- operations -------------------------------------------------------------------
-
     def _barrier(self) -> None:
         """Stream-ordered cross-rank barrier (a one-element all-reduce; no host sync)."""
         if self._flag is None:
             self._flag = torch.zeros(1, dtype=torch.float32, device=self.local.device)
         self.dist.all_reduce(self._flag)
 
-    def apply_operation(self, operator: torch.Tensor, axes: Sequence[int],
-                        prefer_shard: Optional[Sequence[int]] = None) -> None:
-        """psi <- (operator on global subsystems ``axes``) psi; swaps axes in if needed."""
-        if self.peers is not None and any(s.g in axes for s in self.sparts):
-            t = math.prod(self.global_dims[a] for a in axes)
-            if t <= 8:
-                # fused: the operator is applied while the swapped data streams in over NVLink
-                self.relayout(self._choose_parts(set(axes), prefer_shard), fused=(operator, axes))
-                return
-        self.ensure_local(axes, prefer_shard)
-        targets = self._targets_for(axes)
-        out = self._buffers()
-        self.backend.apply_vec(self.local, operator, self.local_dims, targets, out=out)
-        self.local, self.spare = out, self.local
+    def _all_reduce(self, t: torch.Tensor) -> torch.Tensor:
+        if self.world > 1:
+            self.dist.all_reduce(torch.view_as_real(t) if t.is_complex() else t)
+        return t
+
+    # ---- axis swap ----------------------------------------------------------------------
 
     def ensure_local(self, axes: Sequence[int], prefer_shard: Optional[Sequence[int]] = None) -> None:
         if any(s.g in axes for s in self.sparts):
-            self.relayout(self._choose_parts(set(axes), prefer_shard))
+            self.relayout(*self._plan_swap(set(axes), prefer_shard))
 
-    def _choose_parts(self, needed: set, prefer: Optional[Sequence[int]]) -> List[int]:
-        """
-        Choose virtual axes (splitting when necessary) whose extents multiply to the
-        world size; returns their positions.  Candidates: axes of the preferred
-        subsystems first, then front to back; never a needed subsystem.
-        """
-        order = list(range(len(self.vaxes)))
-        if prefer:
-            pref = [i for i in order if self.vaxes[i].g in prefer]
-            order = pref + [i for i in order if i not in pref]
-        rem = self.world
+    @staticmethod
+    def _prime_factors(n: int) -> List[int]:
+        out, p = [], 2
+        while n > 1:
+            while n % p == 0:
+                out.append(p)
+                n //= p
+            p += 1
+        return out
+
+    def _choose_parts(self, factors: Sequence[int], needed: set, prefer: Optional[Sequence[int]]) -> List[int]:
+        """For every factor (in order) pick a local virtual axis of exactly that extent, splitting
+        the top factor off a larger axis when necessary; returns their positions (aligned with
+        ``factors``).  Candidates: axes of the preferred subsystems first, then front to back;
+        never a needed subsystem, never one outside ``_shardable``."""
         chosen: List[int] = []
-        splits: List[Tuple[int, int]] = []  # (position, factor to split off the top)
-        for i in order:
-            if rem == 1:
+        for p in factors:
+            order = list(range(len(self.vaxes)))
+            if prefer:
+                pref = [i for i in order if self.vaxes[i].g in prefer]
+                order = pref + [i for i in order if i not in pref]
+            pick = None
+            for i in order:
+                v = self.vaxes[i]
+                if i in chosen or v.g in needed or v.extent % p != 0 or v.extent < p:
+                    continue
+                if self._shardable is not None and v.g not in self._shardable:
+                    continue
+                pick = i
                 break
-            v = self.vaxes[i]
-            if v.g in needed:
-                continue
-            f = math.gcd(v.extent, rem)
-            if f == 1:
-                continue
-            if f == v.extent:
-                chosen.append(i)
-            else:
-                splits.append((i, f))
-            rem //= f
-        if rem != 1:
-            raise RuntimeError("no admissible axis swap for this operator / world size")
-        # materialise splits (block split: (e) -> (f, e/f), weights (w*e/f, w)); positions shift
-        for i, f in sorted(splits, reverse=True):
-            v = self.vaxes[i]
-            hi = VAxis(v.g, f, v.weight * (v.extent // f))
-            lo = VAxis(v.g, v.extent // f, v.weight)
-            self.vaxes[i:i + 1] = [hi, lo]
-            chosen = [c + 1 if c > i else c for c in chosen]
-            chosen.append(i)
-        return sorted(chosen)
+            if pick is None:
+                raise RuntimeError("no admissible axis swap for this operator / world size "
+                                   f"(need a local factor {p}; layout {self.vaxes})")
+            v = self.vaxes[pick]
+            if v.extent != p:  # block split: (e) -> (p, e/p), weights (w*e/p, w)
+                hi = VAxis(v.g, p, v.weight * (v.extent // p))
+                lo = VAxis(v.g, v.extent // p, v.weight)
+                self.vaxes[pick:pick + 1] = [hi, lo]
+                chosen = [c + 1 if c > pick else c for c in chosen]
+            chosen.append(pick)
+        return chosen
 
-    def relayout(self, positions: Sequence[int], fused=None) -> None:
-        """All-to-all axis swap: the virtual axes at ``positions`` become the rank digits.
+    def _plan_swap(self, needed: set, prefer: Optional[Sequence[int]]) -> Tuple[List[int], List[int]]:
+        """Which sharded parts become local and which local parts take over their rank-digit
+        slots.  First choice: ALL sharded parts (one all-to-all over all ranks; nothing stays
+        sharded that a later operator of the layer might need -- the two-layout steady state).
+        When the local axes cannot supply the whole world size, only the parts of the needed
+        subsystems are localised and the others STAY sharded (an all-to-all inside groups).
+        Slots are refined to prime extents first (a pure relabelling), so that a slot can be
+        matched factor by factor."""
+        saved = (list(self.vaxes), list(self.sparts))
+        for everything in (True, False):
+            refined: List[VAxis] = []
+            slots: List[int] = []
+            for s in saved[1]:
+                if (everything or s.g in needed) and s.extent > 1:
+                    w = s.weight * s.extent
+                    for p in self._prime_factors(s.extent):
+                        w //= p
+                        slots.append(len(refined))
+                        refined.append(VAxis(s.g, p, w))
+                else:
+                    refined.append(s)
+            self.vaxes, self.sparts = list(saved[0]), refined
+            try:
+                positions = self._choose_parts([refined[k].extent for k in slots], needed, prefer)
+                return positions, slots
+            except RuntimeError:
+                if not everything:
+                    self.vaxes, self.sparts = saved
+                    raise
+        raise AssertionError("unreachable")
+
+    def _pack_front(self, positions: List[int]) -> None:
+        """Bring the virtual axes at ``positions`` to the front of the buffer (one local pass)."""
+        k = len(positions)
+        if positions == list(range(k)):
+            return
+        perm = positions + [i for i in range(len(self.vaxes)) if i not in positions]
+        out = self._buffers()
+        self.backend.permute(self.local, self.local_dims, perm, out=out)
+        self.local, self.spare = out, self.local
+        self.vaxes = [self.vaxes[i] for i in perm]
+        self.packs += 1
+
+    def relayout(self, positions: Sequence[int], slots: Optional[Sequence[int]] = None, fused=None) -> None:
+        """Axis swap: the virtual axes at ``positions`` take over the rank-digit ``slots`` (default:
+        all of them), whose sharded parts arrive as the new leading local axes.  Ranks that share
+        the digits of the OTHER slots form a group of f = prod(slot extents) members; the swap is
+        an all-to-all inside each group (f = world: one all-to-all over all ranks).
         ``fused=(operator, axes)``: apply that operator while gathering (peer mode only)."""
         positions = list(positions)
+        slots = list(range(len(self.sparts))) if slots is None else list(slots)
         k = len(positions)
-        assert math.prod(self.vaxes[p].extent for p in positions) == self.world
-        if positions != list(range(k)):
-            # pack: bring the outgoing parts to the front (one local pass)
-            perm = positions + [i for i in range(len(self.vaxes)) if i not in positions]
-            out = self._buffers()
-            self.backend.permute(self.local, self.local_dims, perm, out=out)
-            self.local, self.spare = out, self.local
-            self.vaxes = [self.vaxes[i] for i in perm]
-            self.packs += 1
+        assert k == len(slots)
+        assert [self.vaxes[p].extent for p in positions] == [self.sparts[q].extent for q in slots]
+        f = math.prod(self.sparts[q].extent for q in slots)
+        self._pack_front(positions)
         recv = self._buffers()
-        new_sparts = self.vaxes[:k]
-        new_vaxes = [VAxis(s.g, s.extent, s.weight) for s in self.sparts] + self.vaxes[k:]
+        new_sparts = list(self.sparts)
+        for j, q in enumerate(slots):
+            new_sparts[q] = self.vaxes[j]
+        new_vaxes = [self.sparts[q] for q in slots] + self.vaxes[k:]
+        # my group: same digits on the other slots; member c carries digits(c) on `slots`
+        ext = [s.extent for s in self.sparts]
+        mine = self.my_digits()
+        slot_ext = [ext[q] for q in slots]
+        members = []
+        for c in range(f):
+            d = list(mine)
+            for q, dq in zip(slots, rank_digits(c, slot_ext)):
+                d[q] = dq
+            members.append(digits_rank(d, ext))
+        c_me = digits_rank([mine[q] for q in slots], slot_ext)
+        chunk = self.local.numel() // f
         if self.peers is not None:
-            chunk = self.local.numel() // self.world
             self._barrier()  # every rank has finished writing the buffer we are about to read
-            srcs = self.peers.chunk_ptrs(self.peers.index_of(self.local), chunk)
+            buf = self.peers.index_of(self.local)
+            off = c_me * chunk * self.peers.esize
+            srcs = [self.peers.ptrs[buf][r] + off for r in members]
             done = False
             if fused is not None:
                 op, axes = fused
                 self.vaxes, self.sparts = new_vaxes, new_sparts
                 done = self.backend.apply_vec_gather(srcs, chunk, recv, op, self.local_dims,
-                                                     self._targets_for(axes), rank=self.rank)
+                                                     self._targets_for(axes), rank=c_me)
                 if done:
                     self.fused_swaps += 1
             if not done:
-                self.backend.gather_chunks(srcs, chunk, recv, rank=self.rank)
+                self.backend.gather_chunks(srcs, chunk, recv, rank=c_me)
             self._barrier()  # peers are done reading before anyone overwrites the old buffer
             self.local, self.spare = recv, self.local
             self.vaxes, self.sparts = new_vaxes, new_sparts
             self.swaps += 1
             if fused is not None and not done:
-                self.apply_operation(fused[0], fused[1])
+                self._apply_local(fused[0], fused[1])
             return
-        # complex buffers travel as (n, 2) reals: equal row splits, one piece per rank
-        self.dist.all_to_all_single(torch.view_as_real(recv), torch.view_as_real(self.local))
+        # complex buffers travel as (n, 2) reals: one equal piece per group member
+        if f == self.world:
+            self.dist.all_to_all_single(torch.view_as_real(recv), torch.view_as_real(self.local))
+        else:
+            splits = [chunk if r in members else 0 for r in range(self.world)]
+            self.dist.all_to_all_single(torch.view_as_real(recv), torch.view_as_real(self.local),
+                                        output_split_sizes=splits, input_split_sizes=splits)
         self.local, self.spare = recv, self.local
         self.vaxes, self.sparts = new_vaxes, new_sparts
         self.swaps += 1
         if fused is not None:
-            self.apply_operation(fused[0], fused[1])
+            self._apply_local(fused[0], fused[1])
 
-    def norm2(self) -> torch.Tensor:
-        """sum |psi|^2 over all ranks (device tensor)."""
-        n = self.backend.norm2(self.local)
-        self.dist.all_reduce(n)
-        return n
+    def _apply_local(self, operator, axes) -> None:  # pragma: no cover -- overridden
+        raise NotImplementedError
+
+    # ---- measurement plumbing shared by psi and rho ----------------------------------------
+
+    def _global_positions(self, axes: Sequence[int], parts: List[int]) -> np.ndarray:
+        """For every LOCAL joint index over the virtual axes ``parts`` (row-major, in that order):
+        the position in the global joint outcome (mixed radix over ``axes`` in the given order,
+        core/kernels.py:28-41), with this rank's digits filled in for the sharded parts."""
+        mult, acc = {}, 1
+        for g in reversed(list(axes)):
+            mult[g] = acc
+            acc *= self.global_dims[g]
+        pos = np.zeros((1,), dtype=np.int64)
+        for i in parts:
+            v = self.vaxes[i]
+            pos = (pos[:, None] + (np.arange(v.extent, dtype=np.int64) * v.weight * mult[v.g])[None, :]).reshape(-1)
+        const = 0
+        for s, b in zip(self.sparts, self.my_digits()):
+            if s.g in mult:
+                const += b * s.weight * mult[s.g]
+        return pos + const
+
+    def _combine_probs(self, local_sums: torch.Tensor, axes, parts: List[int]) -> torch.Tensor:
+        """Scatter this rank's partial sums into the global outcome vector, ONE all-reduce,
+        normalise (core/kernels.py:40, :58)."""
+        t = math.prod(self.global_dims[g] for g in axes)
+        full = torch.zeros(t, dtype=torch.float64, device=local_sums.device)
+        pos = torch.as_tensor(self._global_positions(axes, parts), device=local_sums.device)
+        full.index_copy_(0, pos, local_sums.reshape(-1))
+        self._all_reduce(full)
+        return self.backend.probs_from_sums(full, self.local.dtype)
+
+    def _outcome_digits(self, outcome: int, axes: Sequence[int]) -> Dict[int, int]:
+        idx, rem = {}, int(outcome)
+        for g in reversed(list(axes)):
+            idx[g] = rem % self.global_dims[g]
+            rem //= self.global_dims[g]
+        return idx
+
+    def _owner_and_offset(self, idx: Dict[int, int], strides: Dict[int, int]) -> Tuple[bool, int]:
+        """Does this rank hold outcome ``idx`` (its digits on the sharded measured parts match),
+        and the element offset of that outcome inside the local block."""
+        own = True
+        for s, b in zip(self.sparts, self.my_digits()):
+            if s.g in idx and (idx[s.g] // s.weight) % s.extent != b:
+                own = False
+        off = 0
+        for i, v in enumerate(self.vaxes):
+            if v.g in idx and i in strides:
+                off += ((idx[v.g] // v.weight) % v.extent) * strides[i]
+        return own, off
+
+    def _respread(self, post: Optional[torch.Tensor], post_vaxes: List[VAxis], measured: Sequence[int],
+                  idx: Dict[int, int]) -> Tuple[torch.Tensor, List[VAxis], List[VAxis]]:
+        """After a collapse on the owning ranks: spread the post state over ALL ranks again.
+
+        The measured sharded parts (factor f of the world size) no longer exist; the owners cut
+        their block along f fresh leading parts and send one piece to each rank of their group.
+        The post state is t times smaller than the state, so this moves little data.
+        Returns (local, vaxes, sparts) of the new layout."""
+        dtype, device = self.local.dtype, self.local.device
+        old_ext = [s.extent for s in self.sparts]
+        mine = self.my_digits()
+        kept = [k for k, s in enumerate(self.sparts) if s.g not in measured]
+        f = math.prod(s.extent for s in self.sparts if s.g in measured)
+        if f == 1:
+            return post, post_vaxes, [self.sparts[k] for k in kept]
+        # fresh parts: computed identically on every rank from the layout alone
+        probe = ShardedTensor.__new__(type(self))
+        probe.vaxes, probe._shardable = list(post_vaxes), self._shardable
+        positions = ShardedTensor._choose_parts(probe, self._prime_factors(f), set(), None)
+        new_vaxes = probe.vaxes
+        perm = positions + [i for i in range(len(new_vaxes)) if i not in positions]
+        fresh = [new_vaxes[i] for i in positions]
+        local_vaxes = [new_vaxes[i] for i in perm[len(positions):]]
+        n_piece = math.prod(v.extent for v in local_vaxes)
+        recv = torch.empty(n_piece, dtype=dtype, device=device)
+        new_sparts = [self.sparts[k] for k in kept] + fresh
+        new_ext = [s.extent for s in new_sparts]
+        fresh_ext = [v.extent for v in fresh]
+        ops = []
+        pieces = None
+        if post is not None:  # owner: cut the block along the fresh parts (front of the buffer)
+            dims = [v.extent for v in new_vaxes]
+            pieces = self.backend.permute(post.reshape(-1), dims, perm).reshape(f, n_piece)
+            for c in range(f):
+                dst = digits_rank([mine[k] for k in kept] + rank_digits(c, fresh_ext), new_ext)
+                if dst == self.rank:
+                    recv.copy_(pieces[c])
+                else:
+                    ops.append(self.dist.P2POp(self.dist.isend, torch.view_as_real(pieces[c]), dst))
+        # every rank receives exactly one piece, from the owner of its group
+        my_new = rank_digits(self.rank, new_ext)
+        src_digits = list(mine)
+        for j, k in enumerate(kept):
+            src_digits[k] = my_new[j]
+        for k, s in enumerate(self.sparts):
+            if s.g in measured:
+                src_digits[k] = (idx[s.g] // s.weight) % s.extent  # the owner's digit on that part
+        src = digits_rank(src_digits, old_ext)
+        if src != self.rank:
+            ops.append(self.dist.P2POp(self.dist.irecv, torch.view_as_real(recv), src))
+        if ops:
+            for req in self.dist.batch_isend_irecv(ops):
+                req.wait()
+        return recv, local_vaxes, new_sparts
+
+    # ---- reassembly (tests / preflight) -----------------------------------------------------
 
     def gather_full(self) -> torch.Tensor:
-        """Reassemble the full vector in canonical subsystem order on every rank (tests)."""
+        """Reassemble the full tensor in canonical subsystem order on every rank (tests)."""
         pieces = [torch.empty_like(self.local) for _ in range(self.world)]
-        self.dist.all_gather([torch.view_as_real(p) for p in pieces],
-                             torch.view_as_real(self.local.contiguous()))
+        if self.world > 1:
+            self.dist.all_gather([torch.view_as_real(p) for p in pieces],
+                                 torch.view_as_real(self.local.contiguous()))
+        else:
+            pieces = [self.local]
         n = len(self.global_dims)
         full = torch.empty(self.global_dims, dtype=self.local.dtype, device=self.local.device)
         sp_ext = [s.extent for s in self.sparts]
@@ -407,175 +680,240 @@ class ShardedStateVector:
         return full.reshape(-1)
 
 
-# --------------------------------------------------------------------------------------
-# bench.py --gpus N driver (strong scaling of the 12-mode layer)
-# --------------------------------------------------------------------------------------
+# ======================================================================================
+# state vector
+# ======================================================================================
 
 
-def bench_sharded(args, dist, rank, world, local_rank, make_layer, workload_config, peaks,
-                  ClockSampler, METRIC, UNIT):
-    import json
+class ShardedStateVector(ShardedTensor):
+    """A state vector of ``global_dims`` block-sharded over ``world`` ranks."""
 
-    from . import _lib
-    from .core import ffi
+    @classmethod
+    def from_full(cls, global_dims, full: torch.Tensor, rank: int, world: int, dist, backend):
+        """Every rank holds the full vector (tests / small cases): keep only the own block."""
+        vaxes, sparts = cls.initial_layout(global_dims, world)
+        local = cls._own_block(global_dims, full, sparts, rank)
+        return cls(global_dims, local, vaxes, sparts, rank, world, dist, backend)
 
-    lib = _lib.load()
-    modes, cutoff = args.modes, args.cutoff
-    dims = (cutoff,) * modes
-    N = cutoff**modes
-    layer = make_layer(modes, cutoff)
-    d_ops = [torch.as_tensor(o).cuda() for _, o, _ in layer]
-    nops = len(layer)
+    # ---- apply (core/kernels.py:62-98) ------------------------------------------------------
 
-    vaxes, sparts = ShardedStateVector.initial_layout(dims, world)
-    n_local = N // world
-    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
-    peers = None
-    swap_impl = "torch.distributed.all_to_all_single (NCCL)"
-    if not getattr(args, "nccl_swap", False):
-        try:
-            peers = PeerBuffers(n_local, torch.complex128, 2, rank, world, dist, local_rank)
-            swap_impl = ("libpwb200 peer reads over NVLink (CUDA IPC): pw_apply_vec_gather fused "
-                         "swap+apply, pw_gather_chunks otherwise")
-        except Exception as exc:  # IPC unavailable: fall back to the NCCL collective
-            peers = None
-            swap_impl += f" [peer memory unavailable: {exc}]"
-    if peers is not None:
-        local, spare = peers.tensors[0], peers.tensors[1]
-        torch.view_as_real(local).normal_(generator=gen)
-    else:
-        local = torch.view_as_complex(
-            torch.randn(n_local, 2, generator=gen, device="cuda", dtype=torch.float64))
-        spare = None
-    st = ShardedStateVector(dims, local, vaxes, sparts, rank, world, dist, CudaBackend(),
-                            spare=spare, peers=peers)
-    nrm = st.norm2()
-    ffi.scale_(st.local, (1.0 / torch.sqrt(nrm)).contiguous())
+    def apply_operation(self, operator: torch.Tensor, axes: Sequence[int],
+                        prefer_shard: Optional[Sequence[int]] = None) -> None:
+        """psi <- (operator on global subsystems ``axes``) psi; swaps axes in if needed."""
+        if self.peers is not None and any(s.g in axes for s in self.sparts):
+            # fused: the operator is applied while the swapped data streams in over NVLink
+            positions, slots = self._plan_swap(set(axes), prefer_shard)
+            self.relayout(positions, slots, fused=(operator, axes))
+            return
+        self.ensure_local(axes, prefer_shard)
+        self._apply_local(operator, axes)
 
-    # Two layouts alternate: A shards the leading axes, B shards axes in the middle, so
-    # every brick of the layer is local in one of them and each layer costs ONE swap.
-    k = len(st.sparts)
-    shard_a = [s.g for s in st.sparts]
-    mid = modes // 2
-    shard_b = list(range(mid, mid + k))
-    ops_a = [i for i, (t, _, _) in enumerate(layer) if not set(t) & set(shard_a)]
-    ops_b = [i for i in range(nops) if i not in ops_a]
-    assert all(not set(layer[i][0]) & set(shard_b) for i in ops_b)
+    def _apply_local(self, operator, axes) -> None:
+        targets = self._targets_for(axes)
+        out = self._buffers()
+        self.backend.apply_vec(self.local, operator, self.local_dims, targets, out=out)
+        self.local, self.spare = out, self.local
 
-    def run_layer(events=None):
-        # phase 1: everything local under the current layout; then swap; then the rest
-        cur_sharded = set(st.sharded_axes())
-        first = [i for i in range(nops) if not set(layer[i][0]) & cur_sharded]
-        second = [i for i in range(nops) if i not in first]
-        other = shard_b if cur_sharded == set(shard_a) else shard_a
-        slot = 0
-        for i in first:
-            if events is not None:
-                events[slot].record(); slot += 1
-            st.apply_operation(d_ops[i], layer[i][0])
-        if events is not None:
-            events[slot].record(); slot += 1
-        if second and st.peers is None:
-            st.ensure_local(layer[second[0]][0] + tuple(a for i in second for a in layer[i][0]),
-                            prefer_shard=other)
-        for i in second:
-            if events is not None:
-                events[slot].record(); slot += 1
-            # peer mode: the first of these ops carries the swap (fused gather + apply)
-            st.apply_operation(d_ops[i], layer[i][0], prefer_shard=other)
-        if events is not None:
-            events[slot].record()
-        return len(first)
+    # ---- reductions ---------------------------------------------------------------------------
 
-    for _ in range(args.warmup):
-        run_layer()
-    torch.cuda.synchronize()
-    dist.barrier()
+    def norm2(self) -> torch.Tensor:
+        """sum |psi|^2 over all ranks (device tensor)."""
+        return self._all_reduce(self.backend.norm2(self.local))
 
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(nops + 2)] for _ in range(args.steps)]
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    n0 = lib.pw_launch_count()
-    swaps0, packs0, fused0 = st.swaps, st.packs, st.fused_swaps
-    torch.cuda.synchronize()
-    dist.barrier()
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
-    t0.record()
-    nfirst = []
-    for s in range(args.steps):
-        nfirst.append(run_layer(ev[s]))
-    t1.record()
-    torch.cuda.synchronize()
-    dist.barrier()
-    launches = int(lib.pw_launch_count() - n0)
-    clocks = sampler.stop() if rank == 0 else None
-    ms = torch.tensor([t0.elapsed_time(t1)], device="cuda", dtype=torch.float64)
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    total_ms = float(ms.item())
+    def _split(self, axes: Sequence[int]):
+        parts = [i for g in axes for i in self._parts_of(g)]
+        rest = [i for i, v in enumerate(self.vaxes) if v.g not in axes]
+        return parts, rest
 
-    # swap time = the slot between the two phases
-    swap_ms = 0.0
-    op_ms = 0.0
-    fused_op_ms = 0.0
-    for s in range(args.steps):
-        nf = nfirst[s]
-        for j in range(nops + 1):
-            dt = ev[s][j].elapsed_time(ev[s][j + 1])
-            if j == nf:
-                swap_ms += dt
-            else:
-                op_ms += dt
-            if j == nf + 1:
-                fused_op_ms += dt  # first op after the swap slot (carries the fused swap)
-    fused_op_ms /= args.steps
-    swap_ms /= args.steps
-    op_ms /= args.steps
-    tm = torch.tensor([swap_ms, op_ms], device="cuda", dtype=torch.float64)
-    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    swap_ms, op_ms = float(tm[0]), float(tm[1])
-    norm_after = float(st.norm2().item())
-    swaps = (st.swaps - swaps0) / args.steps
-    packs = (st.packs - packs0) / args.steps
+    def probs(self, axes: Sequence[int]) -> torch.Tensor:
+        """Joint outcome probabilities of subsystems ``axes`` (given order), identical on every
+        rank; no data movement whether or not the axes are sharded (core/kernels.py:28-41)."""
+        parts, rest = self._split(axes)
+        st, ext = self.local_strides(), self.local_dims
+        sums = self.backend.sums_strided(self.local, 0, [(ext[i], st[i]) for i in rest],
+                                         [(ext[i], st[i]) for i in parts], False)
+        return self._combine_probs(sums, axes, parts)
 
-    if rank == 0:
-        peak, peak_src = peaks()
-        alg_bytes = 2 * n_local * 16
-        avg_op_ms = op_ms / nops
-        achieved = alg_bytes / (avg_op_ms * 1e-3) / 1e9
-        swap_bytes = n_local * 16 * (world - 1) / world
-        fused_per_step = (st.fused_swaps - fused0) / args.steps
-        line = {
-            "metric": METRIC, "value": nops * N * args.steps / (total_ms * 1e-3), "unit": UNIT,
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "c128", "data": "synthetic",
-            "config": workload_config(args, world), "clocks": clocks,
-            "e2e": {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                    "skipped": "end-to-end host-buffer path is measured at N=1 only"},
-            "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "apply_vec (per-rank shard, all ops of the layer)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_op_ms},
-            "cpu_baseline": None,
-            "axis_swap": {"swaps_per_step": swaps, "packs_per_step": packs, "ms_per_step": swap_ms,
-                          "bytes_sent_per_rank": swap_bytes,
-                          # stand-alone swaps only: a swap fused into the apply kernel has no
-                          # duration of its own (fused_swap_plus_apply_ms is the fused kernel)
-                          "gbs_per_rank_per_direction": swap_bytes * (swaps - fused_per_step) / (swap_ms * 1e-3) / 1e9
-                          if swap_ms > 0 and swaps - fused_per_step > 0 else None,
-                          "nvlink_reference_gbs": 770.0,
-                          "fused_swaps_per_step": fused_per_step,
-                          "fused_swap_plus_apply_ms": fused_op_ms if peers is not None else None,
-                          "implementation": swap_impl},
-            "compute_ms_per_step": op_ms, "norm_after": norm_after,
-        }
-        print(json.dumps(line), flush=True)
-    dist.barrier()
-    if peers is not None:
-        del st, local, spare
-        torch.cuda.synchronize()
-        peers.close()
-    dist.destroy_process_group()
+    def reduced(self, keep: Sequence[int], prefer_shard: Optional[Sequence[int]] = None) -> torch.Tensor:
+        """Tr_rest |psi><psi| for the subsystems ``keep`` (given order), on every rank
+        (state/utils/trace_out.py:17-25): local partial + one all-reduce of t^2 numbers."""
+        self.ensure_local(keep, prefer_shard)
+        part = self.backend.reduced_from_vec(self.local, self.local_dims, self._targets_for(keep))
+        return self._all_reduce(part)
+
+    def measure(self, axes: Sequence[int], key) -> Tuple[int, "ShardedStateVector", torch.Tensor]:
+        """Projective measurement of ``axes`` (core/kernels.py:189-206): returns (outcome, post
+        state over the remaining subsystems, probabilities).  Every rank draws from the same
+        all-reduced probabilities with the same key, so the outcome is identical everywhere;
+        the collapse happens on the ranks that own the outcome's sharded digits."""
+        axes = list(axes)
+        probs = self.probs(axes)
+        outcome_t = self.backend.draw(probs, key, self.local.dtype)
+        outcome = int(outcome_t.item())
+        idx = self._outcome_digits(outcome, axes)
+        parts, rest = self._split(axes)
+        st, ext = self.local_strides(), self.local_dims
+        own, off = self._owner_and_offset(idx, {i: st[i] for i in parts})
+        post = None
+        if own:
+            post = self.backend.gather_strided(self.local, off, [(ext[i], st[i]) for i in rest],
+                                               probs, outcome_t, 1)
+        post_vaxes = [self.vaxes[i] for i in rest]
+        local, vaxes, sparts = self._respread(post, post_vaxes, axes, idx)
+        # renumber the remaining subsystems
+        remaining = [g for g in range(len(self.global_dims)) if g not in axes]
+        new_id = {g: k for k, g in enumerate(remaining)}
+        vaxes = [VAxis(new_id[v.g], v.extent, v.weight) for v in vaxes]
+        sparts = [VAxis(new_id[s.g], s.extent, s.weight) for s in sparts]
+        dims = [self.global_dims[g] for g in remaining]
+        out = ShardedStateVector(dims, local, vaxes, sparts, self.rank, self.world, self.dist, self.backend)
+        return outcome, out, probs
+
+
+# ======================================================================================
+# density matrix
+# ======================================================================================
+
+
+class ShardedDensityMatrix(ShardedTensor):
+    """A density matrix over subsystems ``dims``, its ROW side block-sharded over ``world`` ranks.
+
+    Internally a tensor over the 2n subsystems ``dims ++ dims`` (row g = subsystem g, column g =
+    subsystem n + g) in which only row subsystems are ever sharded or swapped, so every block is
+    a set of complete rows: ``local`` is a row-major (local rows x N) matrix."""
+
+    def __init__(self, dims: Sequence[int], local, vaxes, sparts, rank, world, dist, backend,
+                 spare=None, peers=None):
+        self.dims = tuple(int(d) for d in dims)
+        self.n = len(self.dims)
+        self._shardable = range(self.n)
+        super().__init__(self.dims + self.dims, local, vaxes, sparts, rank, world, dist, backend,
+                         spare=spare, peers=peers)
+
+    @classmethod
+    def initial_layout(cls, dims: Sequence[int], world: int):
+        dims = tuple(dims)
+        plan = dict(cls.shard_plan(dims, world))  # row subsystems only
+        return cls._layout(dims + dims, plan)
+
+    @classmethod
+    def from_full(cls, dims, full: torch.Tensor, rank: int, world: int, dist, backend):
+        dims = tuple(dims)
+        vaxes, sparts = cls.initial_layout(dims, world)
+        local = cls._own_block(dims + dims, full, sparts, rank)
+        return cls(dims, local, vaxes, sparts, rank, world, dist, backend)
+
+    # ---- geometry -----------------------------------------------------------------------------
+
+    def _col_stride(self) -> Dict[int, int]:
+        """Element stride of column subsystem g (columns are whole, unsplit axes)."""
+        st = self.local_strides()
+        out = {}
+        for i, v in enumerate(self.vaxes):
+            if v.g >= self.n:
+                assert v.weight == 1 and v.extent == self.dims[v.g - self.n]
+                out[v.g - self.n] = st[i]
+        return out
+
+    def _diag(self):
+        """(diag stride of every row virtual axis, constant offset): walking a row part by one
+        step also moves the matching column subsystem by ``weight``, which stays on the diagonal
+        of rho; the rank's digits fix the column offset of the sharded parts."""
+        st, cs = self.local_strides(), self._col_stride()
+        dstride = {i: st[i] + v.weight * cs[v.g] for i, v in enumerate(self.vaxes) if v.g < self.n}
+        const = sum(b * s.weight * cs[s.g] for s, b in zip(self.sparts, self.my_digits()))
+        return dstride, const
+
+    # ---- apply / Kraus (core/kernels.py:101-186) ---------------------------------------------------
+
+    def apply_kraus(self, operators: torch.Tensor, axes: Sequence[int],
+                    prefer_shard: Optional[Sequence[int]] = None) -> None:
+        """rho <- sum_k K_k rho K_k^dagger on subsystems ``axes``; ONE HBM pass per block.  Only
+        the row side can be sharded, so at most one axis swap (of rows) precedes it."""
+        self.ensure_local(axes, prefer_shard)
+        self._apply_local(operators, axes)
+
+    def apply_operation(self, operator: torch.Tensor, axes: Sequence[int],
+                        prefer_shard: Optional[Sequence[int]] = None) -> None:
+        """rho <- U rho U^dagger."""
+        self.apply_kraus(operator.reshape((1,) + tuple(operator.shape[-2:])), axes, prefer_shard)
+
+    def _apply_local(self, operators, axes) -> None:
+        if operators.dim() == 2:
+            operators = operators.reshape((1,) + tuple(operators.shape))
+        rows = self._targets_for(axes)
+        cols = self._targets_for([self.n + a for a in axes])
+        out = self._buffers()
+        self.backend.kraus_axes(self.local, operators, self.local_dims, rows, cols, out=out)
+        self.local, self.spare = out, self.local
+
+    # ---- reductions -----------------------------------------------------------------------------
+
+    def _row_split(self, axes: Sequence[int]):
+        parts = [i for g in axes for i in self._parts_of(g)]
+        rest = [i for i, v in enumerate(self.vaxes) if v.g < self.n and v.g not in axes]
+        return parts, rest
+
+    def trace(self) -> torch.Tensor:
+        """Tr rho (device float64 tensor[1]) over all ranks."""
+        ds, const = self._diag()
+        ext = self.local_dims
+        rows = [i for i, v in enumerate(self.vaxes) if v.g < self.n]
+        sums = self.backend.sums_strided(self.local, const, [(ext[i], ds[i]) for i in rows], [], True)
+        return self._all_reduce(sums)
+
+    def probs(self, axes: Sequence[int]) -> torch.Tensor:
+        """Joint outcome probabilities (core/kernels.py:44-59): each rank sums the diagonal
+        entries of its own rows, ONE all-reduce of t numbers."""
+        ds, const = self._diag()
+        ext = self.local_dims
+        parts, rest = self._row_split(axes)
+        sums = self.backend.sums_strided(self.local, const, [(ext[i], ds[i]) for i in rest],
+                                         [(ext[i], ds[i]) for i in parts], True)
+        return self._combine_probs(sums, axes, parts)
+
+    def trace_out(self, keep: Sequence[int], prefer_shard: Optional[Sequence[int]] = None) -> torch.Tensor:
+        """Tr_rest rho for the subsystems ``keep`` (given order) on every rank
+        (core/kernels.py:301-319): local partial over the block's rows + one all-reduce of t^2."""
+        self.ensure_local(keep, prefer_shard)
+        ds, const = self._diag()
+        st, ext, cs = self.local_strides(), self.local_dims, self._col_stride()
+        parts, rest = self._row_split(keep)
+        part = self.backend.trace_strided(
+            self.local, const, [(ext[i], ds[i]) for i in rest], [(ext[i], st[i]) for i in parts],
+            [(self.dims[g], cs[g]) for g in keep])
+        return self._all_reduce(part)
+
+    def measure(self, axes: Sequence[int], key) -> Tuple[int, "ShardedDensityMatrix", torch.Tensor]:
+        """Projective measurement (core/kernels.py:209-227): post = rho[o,:,o,:] / (p_o + 1e-18)
+        taken on the ranks that own outcome o's rows, then spread over all ranks again."""
+        axes = list(axes)
+        probs = self.probs(axes)
+        outcome_t = self.backend.draw(probs, key, self.local.dtype)
+        outcome = int(outcome_t.item())
+        idx = self._outcome_digits(outcome, axes)
+        st, ext, cs = self.local_strides(), self.local_dims, self._col_stride()
+        parts, rest = self._row_split(axes)
+        own, off = self._owner_and_offset(idx, {i: st[i] for i in parts})
+        off += sum(idx[g] * cs[g] for g in axes)
+        rest_cols = [g for g in range(self.n) if g not in axes]
+        post = None
+        if own:
+            view = [(ext[i], st[i]) for i in rest] + [(self.dims[g], cs[g]) for g in rest_cols]
+            post = self.backend.gather_strided(self.local, off, view, probs, outcome_t, 2)
+        new_id = {g: k for k, g in enumerate(rest_cols)}
+        m = len(rest_cols)
+        post_vaxes = [self.vaxes[i] for i in rest] + [VAxis(self.n + g, self.dims[g], 1) for g in rest_cols]
+        local, vaxes, sparts = self._respread(post, post_vaxes, axes, idx)
+
+        def ren(v: VAxis) -> VAxis:
+            return VAxis(new_id[v.g] if v.g < self.n else m + new_id[v.g - self.n], v.extent, v.weight)
+
+        dims = [self.dims[g] for g in rest_cols]
+        out = ShardedDensityMatrix(dims, local, [ren(v) for v in vaxes], [ren(s) for s in sparts],
+                                   self.rank, self.world, self.dist, self.backend)
+        return outcome, out, probs
+
+    def gather_full(self) -> torch.Tensor:
+        n_tot = math.prod(self.dims)
+        return super().gather_full().reshape(n_tot, n_tot)

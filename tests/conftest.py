@@ -10,3 +10,6 @@ def pytest_configure(config):
     config.addinivalue_line(
         "markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)"
     )
+    config.addinivalue_line(
+        "markers", "gpu_multi: needs >= 2 CUDA devices of one node (gpurun --gpus N); skipped otherwise"
+    )

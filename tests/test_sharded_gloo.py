@@ -17,10 +17,66 @@ import torch.multiprocessing as mp
 
 from oracle import adapters_np as oad
 from oracle import operators as ops
-from photon_weave_b200.sharded import ShardedStateVector
+from oracle import rng_threefry as orng
+from photon_weave_b200.sharded import ShardedDensityMatrix, ShardedStateVector
+
+
+def _strided(local, offset, pairs):
+    a = local.numpy()
+    ext = tuple(int(e) for e, _ in pairs)
+    st = tuple(int(s) * a.itemsize for _, s in pairs)
+    return np.lib.stride_tricks.as_strided(a[offset:], shape=ext, strides=st, writeable=False)
 
 
 class NumpyBackend:
+    """The libpwb200 entry points the multi-GPU layer calls, restated with the NumPy oracle."""
+
+    def kraus_axes(self, local, ops, axes, row_targets, col_targets, out=None):
+        x = local.numpy().reshape(-1, 1)
+        acc = 0
+        for k in ops.numpy():
+            y = oad.apply_operation_vector(tuple(axes), tuple(row_targets), x, k, True)
+            acc = acc + oad.apply_operation_vector(tuple(axes), tuple(col_targets), y, k.conj(), True)
+        res = torch.from_numpy(np.ascontiguousarray(acc.reshape(-1)))
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+
+    def sums_strided(self, local, offset, rest, tgt, real_part):
+        v = _strided(local, offset, list(tgt) + list(rest))
+        w = v.real if real_part else np.abs(v) ** 2
+        t = math.prod(e for e, _ in tgt) if tgt else 1
+        return torch.from_numpy(np.ascontiguousarray(w.reshape(t, -1).sum(axis=1)).astype(np.float64))
+
+    def probs_from_sums(self, sums, cdtype):
+        s = sums.numpy()
+        return torch.from_numpy(s / s.sum())
+
+    def draw(self, probs, key, cdtype):
+        p = probs.numpy()
+        return torch.tensor(min(orng.choice(key, p.shape[0], p), p.shape[0] - 1), dtype=torch.int64)
+
+    def trace_strided(self, local, offset, rest, rows, cols):
+        v = _strided(local, offset, list(rows) + list(cols) + list(rest))
+        tr = math.prod(e for e, _ in rows) if rows else 1
+        tc = math.prod(e for e, _ in cols) if cols else 1
+        return torch.from_numpy(np.ascontiguousarray(v.reshape(tr, tc, -1).sum(axis=2)))
+
+    def gather_strided(self, local, offset, view, probs, outcome, mode):
+        v = np.ascontiguousarray(_strided(local, offset, view)).reshape(-1)
+        if mode:
+            p = probs.numpy()[int(outcome)] + 1e-18
+            v = v / (np.sqrt(p) if mode == 1 else p)
+        return torch.from_numpy(v)
+
+    def reduced_from_vec(self, local, dims, keep):
+        n = len(dims)
+        rest = [i for i in range(n) if i not in keep]
+        a = local.numpy().reshape(dims).transpose(list(keep) + rest)
+        a = a.reshape(math.prod(dims[i] for i in keep), -1)
+        return torch.from_numpy(np.ascontiguousarray(a @ a.conj().T))
+
     def apply_vec(self, local, op, dims, targets, out=None):
         res = oad.apply_operation_vector(tuple(dims), tuple(targets), local.numpy().reshape(-1, 1),
                                          op.numpy(), True)
@@ -128,3 +184,122 @@ def test_bench_layer_schedule_world2():
     program += [((0, 1), 7, (2,)), ((2, 3), 8, (0,))]
     err, nrm, swaps, packs = _run(2, dims, program)
     assert err < 1e-13 and abs(nrm - 1) < 1e-12
+
+
+# ---- reductions / measurement of a sharded state vector ---------------------------------------
+
+
+def _vec_reductions_worker(rank, world, port, dims, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        N = math.prod(dims)
+        psi = ops.random_state(N, 11)
+        st = ShardedStateVector.from_full(dims, torch.from_numpy(psi.reshape(-1)), rank, world, dist,
+                                          NumpyBackend())
+        # one swap first so that split virtual axes and non-leading shards are exercised too
+        u = ops.random_unitary(dims[0], 3)
+        st.apply_operation(torch.from_numpy(u), (0,))
+        ref = oad.apply_operation_vector(dims, (0,), psi, u, True)
+        errs = []
+        n = len(dims)
+        for axes in [(0,), (1,), (n - 1, 0), (1, 2, 0), tuple(range(n))]:
+            p = st.probs(axes).numpy()
+            _, _, p_ref, _ = oad.measure_vector_with_probs(dims, axes, ref, orng.PRNGKey(0))
+            errs.append(np.abs(p - p_ref).max())
+        for keep in [(1,), (0, n - 1), (2, 0)]:
+            r = st.reduced(keep).numpy()
+            errs.append(np.abs(r - oad.trace_out_vector(dims, keep, ref, False)).max())
+        for seed, axes in enumerate([(0,), (n - 1, 1), (1, 0), (2,)]):
+            key = orng.PRNGKey(20 + seed)
+            o, post, probs = st.measure(axes, key)
+            o_ref, post_ref, _ = oad.measure_vector(dims, axes, ref, key)
+            assert o == int(o_ref), (axes, o, int(o_ref))
+            got = post.gather_full().numpy()
+            errs.append(np.abs(got - post_ref.reshape(-1)).max())
+            assert abs(float(post.norm2().item()) - 1.0) < 1e-9
+            # the post state is spread over ALL ranks again
+            assert post.local.numel() * world == got.size
+        if rank == 0:
+            results.put(max(errs))
+    finally:
+        dist.destroy_process_group()
+
+
+def _spawn(world, worker, *args):
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=worker, args=(r, world, port) + args + (q,)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+        assert p.exitcode == 0
+    return q.get()
+
+
+@pytest.mark.parametrize("world,dims", [(2, (4, 3, 2, 6)), (4, (6, 6, 2, 4, 2)), (4, (6, 6, 2, 4))])
+def test_sharded_vector_probs_reduced_measure(world, dims):
+    assert _spawn(world, _vec_reductions_worker, dims) < 1e-12
+
+
+# ---- sharded density matrix: apply, Kraus, probs, partial trace, measurement -----------------
+
+
+def _rho_worker(rank, world, port, dims, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = len(dims)
+        N = math.prod(dims)
+        rho = ops.random_density(N, 5)
+        sd = ShardedDensityMatrix.from_full(dims, torch.from_numpy(rho.reshape(-1)), rank, world, dist,
+                                            NumpyBackend())
+        assert sd.local.numel() * world == N * N
+        ref = rho
+        errs = []
+        program = [("u", (1,), 1), ("k", (0,), 2), ("u", (0, n - 1), 3), ("k", (2,), 4), ("u", (1, 0), 5),
+                   ("k", (n - 1,), 6)]
+        for kind, axes, seed in program:
+            t = math.prod(dims[a] for a in axes)
+            if kind == "u":
+                op = ops.random_unitary(t, seed)
+                sd.apply_operation(torch.from_numpy(op), axes)
+                ref = oad.apply_operation_matrix(dims, axes, ref, op, True)
+            else:
+                ks = ops.loss_channel(t, 0.15)
+                sd.apply_kraus(torch.from_numpy(ks), axes)
+                ref = oad.apply_kraus_matrix(dims, axes, ref, ks, True)
+            errs.append(np.abs(sd.gather_full().numpy() - ref).max())
+            # only row subsystems are ever sharded
+            assert all(s.g < n for s in sd.sparts)
+        errs.append(abs(float(sd.trace().item()) - np.trace(ref).real))
+        for axes in [(0,), (1,), (n - 1, 0), tuple(range(n))]:
+            p = sd.probs(axes).numpy()
+            _, _, p_ref, _ = oad.measure_matrix_with_probs(dims, axes, ref, orng.PRNGKey(0))
+            errs.append(np.abs(p - p_ref).max())
+        for keep in [(1,), (0,), (n - 1, 0)]:
+            r = sd.trace_out(keep).numpy()
+            errs.append(np.abs(r - oad.trace_out_matrix(dims, keep, ref, False)).max())
+        for seed, axes in enumerate([(0,), (n - 1, 1), (1, 0)]):
+            key = orng.PRNGKey(40 + seed)
+            o, post, probs = sd.measure(axes, key)
+            o_ref, post_ref, _ = oad.measure_matrix(dims, axes, ref, key)
+            assert o == int(o_ref)
+            got = post.gather_full().numpy()
+            errs.append(np.abs(got - post_ref).max())
+            assert post.local.numel() * world == got.size
+            assert abs(float(post.trace().item()) - 1.0) < 1e-9
+        if rank == 0:
+            results.put((max(errs), sd.swaps))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,dims", [(2, (4, 2, 6)), (4, (4, 4, 2, 4)), (4, (2, 6, 4, 2)), (4, (2, 6, 2, 2))])
+def test_sharded_density_matrix_against_oracle(world, dims):
+    err, swaps = _spawn(world, _rho_worker, dims)
+    assert err < 1e-12 and swaps >= 1
