@@ -337,13 +337,13 @@ def run_gpu_arm(args):
     if world > 1 or args.workload == "rho":
         from photon_weave_b200 import bench_sharded as bs  # noqa: WPS433
 
-        def preflight(kind, want_peers):
+        def preflight(kind, want_peers, mode):
             # N>1 only: a small state through the same schedule on the same ranks vs the oracle
             if world == 1 or args.no_preflight:
                 return None
             return bs.parity_preflight(dist, rank, world, local_rank, kind,
                                        make_layer if kind == "vec" else make_rho_layer,
-                                       oracle_apply, preflight_input, want_peers)
+                                       oracle_apply, preflight_input, want_peers, mode=mode)
 
         if args.workload == "rho":
             return bs.bench_sharded_rho(args, dist, rank, world, local_rank, make_rho_layer, peaks,
@@ -768,6 +768,9 @@ def main():
     ap.add_argument("--rho-modes", type=int, default=5)
     ap.add_argument("--rho-cutoff", type=int, default=8)
     ap.add_argument("--no-preflight", action="store_true", help="N>1: skip the parity preflight")
+    ap.add_argument("--swap", default="pipelined", choices=["pipelined", "fused", "plain"],
+                    help="N>1 layer schedule: swap hidden behind chunk-wise local operations (default); "
+                         "fused gather+apply kernel; stand-alone swap")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

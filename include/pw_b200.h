@@ -244,6 +244,10 @@ int pw_peer_open(const unsigned char handle[64], void** ptr);
 int pw_peer_close(void* ptr);
 int pw_peer_free(void* ptr);
 
+/* dst (local) <- src (local or IPC-mapped peer memory), `bytes` bytes, on a COPY ENGINE
+ * (cudaMemcpyAsync): one piece of the pipelined axis swap, overlapping the apply kernels. */
+int pw_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
+
 /* Axis swap as a direct peer read: out[p * chunk + x] = srcs[p][x] for p < W.
  * `srcs` is a HOST array of W device pointers (local or IPC-mapped peer memory), each
  * already offset to the chunk this rank needs.  `rank` rotates the traversal so the W

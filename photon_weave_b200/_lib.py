@@ -81,6 +81,7 @@ SIGNATURES = {
     "pw_peer_open": (C.c_int, [C.POINTER(C.c_ubyte), C.POINTER(_vp)]),
     "pw_peer_close": (C.c_int, [_vp]),
     "pw_peer_free": (C.c_int, [_vp]),
+    "pw_peer_copy": (C.c_int, [_vp, _vp, C.c_size_t, _vp]),
     "pw_gather_chunks": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int64, C.c_int, _vp, C.c_int, _vp]),
     "pw_apply_vec_gather": (
         C.c_int,

@@ -32,39 +32,60 @@ def make_peers(numel: int, nbuf: int, rank: int, world: int, dist, local_rank: i
 
 
 class LayerRunner:
-    """One circuit layer on a sharded state with TWO alternating layouts: everything local under
-    the current layout first, ONE axis swap (to the other layout), then the rest."""
+    """One circuit layer on a sharded state with TWO alternating layouts.
+
+    mode "pipelined" (default): ``run_layer`` -- local operations that touch the outgoing axes,
+    then the other local operations chunk by chunk with the axis swap hidden behind them (each
+    finished chunk travels to its destination rank while the next one is computed), then the
+    operations that needed the swap.
+    mode "fused": everything local first, then the first operation that needs the swap carries
+    it (fused gather + apply over peer memory, state vectors), then the rest.
+    mode "plain": everything local, a stand-alone swap, the rest."""
 
     def __init__(self, st, layer: Sequence, d_ops: List[torch.Tensor], shard_a: Sequence[int],
-                 shard_b: Sequence[int], apply: Callable):
+                 shard_b: Sequence[int], apply: Callable, mode: str = "pipelined"):
         self.st, self.layer, self.d_ops = st, layer, d_ops
         self.shard_a, self.shard_b = list(shard_a), list(shard_b)
-        self.apply = apply  # (st, op tensor, targets, prefer_shard, kind)
+        self.apply = apply  # (st, op tensor, layer entry, prefer_shard)
         self.nops = len(layer)
+        self.mode = mode
+        self.last_info = None
 
-    def run(self, events=None) -> int:
+    def order(self) -> List[int]:
+        """Indices in the order the NEXT run applies them (for the oracle of the preflight the
+        program order is used instead: regrouping must not change the result)."""
+        return list(range(self.nops))
+
+    def run(self, marks=None) -> int:
         st, layer, nops = self.st, self.layer, self.nops
         cur = set(st.sharded_axes())
+        other = self.shard_b if cur == set(self.shard_a) else self.shard_a
+        if self.mode in ("pipelined", "plain"):
+            self.last_info = st.run_layer([(self.d_ops[i], layer[i][0]) for i in range(nops)],
+                                          next_shard=other, pipeline=self.mode == "pipelined", marks=marks)
+            return self.last_info["s0"] + self.last_info["s1"]
+
+        def mark(label):
+            if marks is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((label, ev))
+
         first = [i for i in range(nops) if not set(layer[i][0]) & cur]
         second = [i for i in range(nops) if i not in first]
-        other = self.shard_b if cur == set(self.shard_a) else self.shard_a
-        slot = 0
+        mark("begin")
         for i in first:
-            if events is not None:
-                events[slot].record(); slot += 1
             self.apply(st, self.d_ops[i], layer[i], None)
-        if events is not None:
-            events[slot].record(); slot += 1
+        mark("local_done")
         if second and (st.peers is None or not isinstance(st, ShardedStateVector)):
-            # stand-alone swap (NCCL, or a plain peer gather for rho)
             st.ensure_local(tuple(a for i in second for a in layer[i][0]), prefer_shard=other)
-        for i in second:
-            if events is not None:
-                events[slot].record(); slot += 1
+        for n, i in enumerate(second):
             # peer mode (state vector): the first of these ops carries the swap (fused gather + apply)
             self.apply(st, self.d_ops[i], layer[i], other)
-        if events is not None:
-            events[slot].record()
+            if n == 0:
+                mark("swap_done")
+        mark("end")
+        self.last_info = {"pipelined": False, "s0": 0, "s1": len(first), "s2": len(second)}
         return len(first)
 
 
@@ -89,16 +110,16 @@ def _layouts(cls, dims, world, modes):
 
 def parity_preflight(dist, rank: int, world: int, local_rank: int, kind: str, make_layer: Callable,
                      oracle_apply: Callable, random_input: Callable, want_peers: bool,
-                     layers: int = 2) -> dict:
+                     layers: int = 3, mode: str = "pipelined") -> dict:
     """A small state through the SAME LayerRunner schedule and swap implementation as the timed
     run, reassembled with gather_full() and compared with the oracle on rank 0.
-    kind 'vec': 6^8 amplitudes; kind 'rho': an (8,8,8) density matrix (512 x 512)."""
+    kind 'vec': 6^8 amplitudes; kind 'rho': a (4,4,4,4) density matrix (256 x 256)."""
     if kind == "vec":
         modes, cutoff = 8, 6
         dims = (cutoff,) * modes
         cls, apply = ShardedStateVector, _apply_vec
     else:
-        modes, cutoff = 3, 8
+        modes, cutoff = 4, 4
         dims = (cutoff,) * modes
         cls, apply = ShardedDensityMatrix, _apply_rho
     layer = make_layer(modes, cutoff)
@@ -106,28 +127,25 @@ def parity_preflight(dist, rank: int, world: int, local_rank: int, kind: str, ma
     vaxes, sparts, shard_a, shard_b = _layouts(cls, dims, world, modes)
     own = cls._own_block(dims if kind == "vec" else dims + dims, torch.as_tensor(full).reshape(-1),
                          sparts, rank).cuda()
-    peers, impl = make_peers(own.numel(), 2, rank, world, dist, local_rank, want_peers)
+    peers, impl = make_peers(own.numel(), 3, rank, world, dist, local_rank, want_peers)
     spare = None
     if peers is not None:
         peers.tensors[0].copy_(own)
         own, spare = peers.tensors[0], peers.tensors[1]
     st = cls(dims, own, vaxes, sparts, rank, world, dist, CudaBackend(), spare=spare, peers=peers)
     d_ops = [torch.as_tensor(o).cuda() for _, o, _ in layer]
-    runner = LayerRunner(st, layer, d_ops, shard_a, shard_b, apply)
-    order: List[int] = []
+    runner = LayerRunner(st, layer, d_ops, shard_a, shard_b, apply, mode)
     for _ in range(layers):
-        cur = set(st.sharded_axes())
-        first = [i for i in range(len(layer)) if not set(layer[i][0]) & cur]
-        order += first + [i for i in range(len(layer)) if i not in first]
         runner.run()
     got = st.gather_full().cpu().numpy()
-    swaps, fused = st.swaps, st.fused_swaps
-    res = {"kind": kind, "dims": list(dims), "layers": layers, "ops": len(order), "swaps": swaps,
-           "fused_swaps": fused, "swap": impl.split(":")[0], "tolerance": 1e-12}
+    res = {"kind": kind, "dims": list(dims), "layers": layers, "ops": layers * len(layer),
+           "swaps": st.swaps, "fused_swaps": st.fused_swaps, "pipelined_swaps": st.pipelined_swaps,
+           "schedule": mode, "swap": impl.split(":")[0], "tolerance": 1e-12}
     if rank == 0:
         ref = full
-        for i in order:                                   # the order the schedule applied them in
-            ref = oracle_apply(kind, dims, layer[i][0], ref, layer[i][1])
+        for _ in range(layers):                           # the oracle applies the PROGRAM order
+            for tg, op, _ in layer:
+                ref = oracle_apply(kind, dims, tg, ref, op)
         import numpy as np
 
         err = float(np.abs(got.reshape(ref.shape) - ref).max() / np.abs(ref).max())
@@ -145,25 +163,30 @@ def parity_preflight(dist, rank: int, world: int, local_rank: int, kind: str, ma
     return res
 
 
-def _time_layers(args, dist, rank, world, local_rank, runner, st, nops, lib, ClockSampler):
+def _time_layers(args, dist, rank, world, local_rank, runner, st, lib, ClockSampler):
+    """W warm-up layers, then exactly `steps` timed layers between barriers; returns the total
+    (max over ranks) and the stage durations from the CUDA events run_layer recorded."""
     for _ in range(args.warmup):
         runner.run()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(nops + 2)] for _ in range(args.steps)]
+    marks = [[] for _ in range(args.steps)]
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     n0 = lib.pw_launch_count()
-    c0 = (st.swaps, st.packs, st.fused_swaps)
+    c0 = (st.swaps, st.packs, st.fused_swaps, st.pipelined_swaps)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
-    nfirst = [runner.run(ev[s]) for s in range(args.steps)]
+    infos = []
+    for s in range(args.steps):
+        runner.run(marks[s])
+        infos.append(dict(runner.last_info))
     t1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -174,41 +197,78 @@ def _time_layers(args, dist, rank, world, local_rank, runner, st, nops, lib, Clo
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
-    swap_ms = op_ms = fused_op_ms = 0.0
-    for s in range(args.steps):
-        nf = nfirst[s]
-        for j in range(nops + 1):
-            dt = ev[s][j].elapsed_time(ev[s][j + 1])
-            if j == nf:
-                swap_ms += dt
-            else:
-                op_ms += dt
-            if j == nf + 1:
-                fused_op_ms += dt  # first op after the swap slot (carries the fused swap)
-    tm = torch.tensor([swap_ms / args.steps, op_ms / args.steps, fused_op_ms / args.steps],
-                      device="cuda", dtype=torch.float64)
+    # stage durations: label -> ms per step (averaged over steps, max over ranks)
+    names = ["s0", "s1", "swap_tail", "s2", "local", "swap"]
+    acc = dict.fromkeys(names, 0.0)
+    for m in marks:
+        d = {lbl: ev for lbl, ev in m}
+
+        def span(a, b):
+            return d[a].elapsed_time(d[b]) if a in d and b in d else 0.0
+
+        if "s1_done" in d:       # pipelined layer
+            acc["s0"] += span("begin", "s0_done")
+            acc["s1"] += span("s0_done", "s1_done")
+            acc["swap_tail"] += span("s1_done", "swap_done")
+            acc["s2"] += span("swap_done", "end")
+        elif "swap_done" in d:   # plain / fused layer
+            acc["local"] += span("begin", "local_done")
+            acc["swap"] += span("local_done", "swap_done")
+            acc["s2"] += span("swap_done", "end")
+        else:
+            acc["local"] += span("begin", "end")
+    tm = torch.tensor([acc[n] / args.steps for n in names], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    counts = ((st.swaps - c0[0]) / args.steps, (st.packs - c0[1]) / args.steps,
-              (st.fused_swaps - c0[2]) / args.steps)
-    return total_ms, float(tm[0]), float(tm[1]), float(tm[2]), launches, clocks, counts
+    stages = {n: float(v) for n, v in zip(names, tm)}
+    counts = {"swaps": (st.swaps - c0[0]) / args.steps, "packs": (st.packs - c0[1]) / args.steps,
+              "fused": (st.fused_swaps - c0[2]) / args.steps,
+              "pipelined": (st.pipelined_swaps - c0[3]) / args.steps}
+    return total_ms, stages, infos[-1], launches, clocks, counts
 
 
-def _swap_record(world, n_local, swap_ms, fused_op_ms, avg_op_ms, counts, impl, peers):
-    swaps, packs, fused = counts
+def _records(world, n_local, nops, stages, info, counts, impl, mode, peak, peak_src):
+    """roofline + axis_swap objects of the JSON line from the stage timings."""
+    alg_bytes = 2 * n_local * 16
     swap_bytes = n_local * 16 * (world - 1) / world
-    rec = {"swaps_per_step": swaps, "packs_per_step": packs, "ms_per_step": swap_ms,
-           "bytes_received_per_rank": swap_bytes, "nvlink_reference_gbs": 770.0,
-           "fused_swaps_per_step": fused, "implementation": impl,
-           "gbs_per_rank_per_direction": None, "fused_swap_plus_apply_ms": None}
-    if swaps - fused > 0 and swap_ms > 0:        # stand-alone swaps have a duration of their own
-        rec["gbs_per_rank_per_direction"] = swap_bytes * (swaps - fused) / (swap_ms * 1e-3) / 1e9
-    if fused > 0 and peers is not None:
-        # the fused kernel streams (W-1)/W of the shard in over NVLink while it applies the operator
-        rec["fused_swap_plus_apply_ms"] = fused_op_ms
-        rec["fused_gbs_per_rank_inbound"] = swap_bytes / (fused_op_ms * 1e-3) / 1e9
-        rec["fused_overhead_vs_local_op_ms"] = fused_op_ms - avg_op_ms
-    return rec
+    swap = {"swaps_per_step": counts["swaps"], "packs_per_step": counts["packs"],
+            "fused_swaps_per_step": counts["fused"], "pipelined_swaps_per_step": counts["pipelined"],
+            "schedule": mode, "bytes_received_per_rank": swap_bytes, "nvlink_reference_gbs": 770.0,
+            "implementation": impl, "stage_ms": stages,
+            "layer_split": {"s0_ops": info["s0"], "s1_ops": info["s1"], "s2_ops": info["s2"]}}
+    if counts["pipelined"] > 0:
+        # full-shard operations (S0 and S2) give the local kernel rate; S1 runs chunk by chunk
+        # with the transfers behind it; what is left of the swap is swap_tail
+        n_full = info["s0"] + info["s2"]
+        avg_op_ms = (stages["s0"] + stages["s2"]) / max(n_full, 1)
+        swap["exposed_swap_ms"] = stages["swap_tail"] + max(stages["s1"] - info["s1"] * avg_op_ms, 0.0)
+        swap["s1_ms_per_op"] = stages["s1"] / max(info["s1"], 1)
+        # the pieces move during S1: average inbound rate over that window
+        swap["gbs_per_rank_inbound_during_s1"] = swap_bytes / ((stages["s1"] + stages["swap_tail"]) * 1e-3) / 1e9
+        kernel = "apply (per-rank shard): full-shard operations of the layer (stages S0, S2)"
+    elif counts["fused"] > 0:
+        n_full = nops - 1
+        avg_op_ms = (stages["local"] + stages["s2"]) / max(n_full, 1) if stages["swap"] > 0 else \
+            (stages["local"] + stages["s2"]) / nops
+        swap["fused_swap_plus_apply_ms"] = stages["swap"]
+        swap["fused_gbs_per_rank_inbound"] = swap_bytes / (stages["swap"] * 1e-3) / 1e9 if stages["swap"] > 0 else None
+        swap["exposed_swap_ms"] = stages["swap"] - avg_op_ms
+        kernel = "apply (per-rank shard): local operations of the layer"
+    else:
+        avg_op_ms = (stages["local"] + stages["s2"]) / nops
+        if counts["swaps"] > 0 and stages["swap"] > 0:
+            swap["gbs_per_rank_per_direction"] = swap_bytes * counts["swaps"] / (stages["swap"] * 1e-3) / 1e9
+        swap["exposed_swap_ms"] = stages["swap"]
+        kernel = "apply (per-rank shard): all operations of the layer"
+    achieved = alg_bytes / (avg_op_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_op_ms}
+    return roofline, swap
+
+
+def _schedule_mode(args) -> str:
+    return getattr(args, "swap", None) or "pipelined"
 
 
 def bench_sharded(args, dist, rank, world, local_rank, make_layer, workload_config, peaks,
@@ -219,7 +279,8 @@ def bench_sharded(args, dist, rank, world, local_rank, make_layer, workload_conf
 
     lib = _lib.load()
     want_peers = not getattr(args, "nccl_swap", False)
-    parity = preflight("vec", want_peers) if preflight is not None else None
+    mode = _schedule_mode(args)
+    parity = preflight("vec", want_peers, mode) if preflight is not None else None
     modes, cutoff = args.modes, args.cutoff
     dims = (cutoff,) * modes
     N = cutoff**modes
@@ -229,7 +290,8 @@ def bench_sharded(args, dist, rank, world, local_rank, make_layer, workload_conf
     vaxes, sparts, shard_a, shard_b = _layouts(ShardedStateVector, dims, world, modes)
     n_local = N // world
     gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
-    peers, swap_impl = make_peers(n_local, 2, rank, world, dist, local_rank, want_peers)
+    peers, swap_impl = make_peers(n_local, 3 if mode == "pipelined" else 2, rank, world, dist,
+                                  local_rank, want_peers)
     if peers is not None:
         local, spare = peers.tensors[0], peers.tensors[1]
         torch.view_as_real(local).normal_(generator=gen)
@@ -241,17 +303,13 @@ def bench_sharded(args, dist, rank, world, local_rank, make_layer, workload_conf
                             spare=spare, peers=peers)
     nrm = st.norm2()
     ffi.scale_(st.local, (1.0 / torch.sqrt(nrm)).contiguous())
-    runner = LayerRunner(st, layer, d_ops, shard_a, shard_b, _apply_vec)
-    total_ms, swap_ms, op_ms, fused_op_ms, launches, clocks, counts = _time_layers(
-        args, dist, rank, world, local_rank, runner, st, nops, lib, ClockSampler)
+    runner = LayerRunner(st, layer, d_ops, shard_a, shard_b, _apply_vec, mode)
+    total_ms, stages, info, launches, clocks, counts = _time_layers(
+        args, dist, rank, world, local_rank, runner, st, lib, ClockSampler)
     norm_after = float(st.norm2().item())
     if rank == 0:
         peak, peak_src = peaks()
-        alg_bytes = 2 * n_local * 16
-        # local operators only: the op that carries a fused swap is NVLink-bound and reported apart
-        n_local_ops = nops - (1 if counts[2] > 0 else 0)
-        avg_op_ms = (op_ms - (fused_op_ms if counts[2] > 0 else 0.0)) / n_local_ops
-        achieved = alg_bytes / (avg_op_ms * 1e-3) / 1e9
+        roofline, swap = _records(world, n_local, nops, stages, info, counts, swap_impl, mode, peak, peak_src)
         line = {
             "metric": METRIC, "value": nops * N * args.steps / (total_ms * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -260,14 +318,8 @@ def bench_sharded(args, dist, rank, world, local_rank, make_layer, workload_conf
             "config": workload_config(args, world), "clocks": clocks,
             "e2e": {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                     "skipped": "end-to-end host-buffer path is measured at N=1 only"},
-            "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "apply_vec (per-rank shard, local ops of the layer)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_op_ms},
-            "cpu_baseline": None,
-            "axis_swap": _swap_record(world, n_local, swap_ms, fused_op_ms, avg_op_ms, counts, swap_impl, peers),
-            "compute_ms_per_step": op_ms, "norm_after": norm_after, "parity_n": parity,
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": None, "axis_swap": swap,
+            "norm_after": norm_after, "parity_n": parity,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -292,7 +344,10 @@ def bench_sharded_rho(args, dist, rank, world, local_rank, make_rho_layer, peaks
 
     lib = _lib.load()
     want_peers = not getattr(args, "nccl_swap", False)
-    parity = preflight("rho", want_peers) if preflight is not None else None
+    mode = _schedule_mode(args)
+    if mode == "fused":
+        mode = "plain"   # there is no fused gather for the two-sided kernels
+    parity = preflight("rho", want_peers, mode) if preflight is not None else None
     modes, cutoff = args.rho_modes, args.rho_cutoff
     dims = (cutoff,) * modes
     D = cutoff**modes
@@ -301,7 +356,8 @@ def bench_sharded_rho(args, dist, rank, world, local_rank, make_rho_layer, peaks
     nops = len(layer)
     vaxes, sparts, shard_a, shard_b = _layouts(ShardedDensityMatrix, dims, world, modes)
     n_local = D * D // world
-    peers, swap_impl = make_peers(n_local, 2, rank, world, dist, local_rank, want_peers)
+    peers, swap_impl = make_peers(n_local, 3 if mode == "pipelined" else 2, rank, world, dist,
+                                  local_rank, want_peers)
     # rho = A A^dagger / Tr with a (D, 4) Gaussian factor: PSD, built block by block
     gen = torch.Generator(device="cuda").manual_seed(4321)
     A = torch.view_as_complex(torch.randn(D, 4, 2, generator=gen, device="cuda", dtype=torch.float64))
@@ -318,15 +374,14 @@ def bench_sharded_rho(args, dist, rank, world, local_rank, make_rho_layer, peaks
     st = ShardedDensityMatrix(dims, local, vaxes, sparts, rank, world, dist, CudaBackend(),
                               spare=spare, peers=peers)
     tr0 = float(st.trace().item())
-    runner = LayerRunner(st, layer, d_ops, shard_a, shard_b, _apply_rho)
-    total_ms, swap_ms, op_ms, fused_op_ms, launches, clocks, counts = _time_layers(
-        args, dist, rank, world, local_rank, runner, st, nops, lib, ClockSampler)
+    runner = LayerRunner(st, layer, d_ops, shard_a, shard_b, _apply_rho, mode)
+    total_ms, stages, info, launches, clocks, counts = _time_layers(
+        args, dist, rank, world, local_rank, runner, st, lib, ClockSampler)
     tr1 = float(st.trace().item())
     if rank == 0:
         peak, peak_src = peaks()
-        alg_bytes = 2 * n_local * 16
-        avg_op_ms = op_ms / nops
-        achieved = alg_bytes / (avg_op_ms * 1e-3) / 1e9
+        roofline, swap = _records(world, n_local, nops, stages, info, counts, swap_impl, mode, peak, peak_src)
+        roofline["kernel"] = "Kraus / U rho U^dagger on a row block (one pass per op): " + roofline["kernel"]
         line = {
             "metric": RHO_METRIC, "value": nops * D * D * args.steps / (total_ms * 1e-3), "unit": RHO_UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -341,14 +396,8 @@ def bench_sharded_rho(args, dist, rank, world, local_rank, make_rho_layer, peaks
             "clocks": clocks,
             "e2e": {"value": None, "unit": RHO_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                     "skipped": "device-resident workload (the host-buffer path is measured on the headline workload)"},
-            "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "Kraus / U rho U^dagger on a row block (one pass per op)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_op_ms},
-            "cpu_baseline": None,
-            "axis_swap": _swap_record(world, n_local, swap_ms, fused_op_ms, avg_op_ms, counts, swap_impl, peers),
-            "compute_ms_per_step": op_ms, "trace_before": tr0, "trace_after": tr1, "parity_n": parity,
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": None, "axis_swap": swap,
+            "trace_before": tr0, "trace_after": tr1, "parity_n": parity,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

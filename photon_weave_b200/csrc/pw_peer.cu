@@ -136,6 +136,14 @@ extern "C" int pw_peer_free(void* ptr) {
   return PW_OK;
 }
 
+extern "C" int pw_peer_copy(void* dst, const void* src, size_t bytes, void* stream) {
+  if (!dst || !src) return PW_ERR_INVALID;
+  // unified addressing: src may be an IPC-mapped peer buffer; the copy runs on a copy engine
+  // (no SM), so it overlaps the apply kernels of the pipelined axis swap
+  PW_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+  return PW_OK;
+}
+
 static int make_seg(const void* const* srcs, int W, int64_t chunk, SegIn* s) {
   if (!srcs || W < 1 || W > kMaxPeers || chunk < 1) return PW_ERR_INVALID;
   for (int p = 0; p < W; ++p) {

@@ -184,6 +184,12 @@ class CudaBackend:
         _lib.check(rc, "pw_apply_vec_gather")
         return True
 
+    def peer_copy(self, dst: torch.Tensor, src_ptr: int, nbytes: int) -> None:
+        from . import _lib
+        from .core import _arrays as A
+
+        _lib.check(_lib.load().pw_peer_copy(dst.data_ptr(), src_ptr, nbytes, A.stream_ptr()), "pw_peer_copy")
+
     # ---- apply ------------------------------------------------------------------------
     def apply_vec(self, local: torch.Tensor, op: torch.Tensor, dims, targets, out=None):
         from .core import ffi
@@ -273,7 +279,8 @@ class ShardedTensor:
 
     def __init__(self, global_dims: Sequence[int], local: torch.Tensor, vaxes: List[VAxis],
                  sparts: List[VAxis], rank: int, world: int, dist: Any, backend: Any,
-                 spare: Optional[torch.Tensor] = None, peers: Optional[PeerBuffers] = None):
+                 spare: Optional[torch.Tensor] = None, peers: Optional[PeerBuffers] = None,
+                 third: Optional[torch.Tensor] = None):
         self.global_dims = tuple(int(d) for d in global_dims)
         self.local = local.reshape(-1)
         self.vaxes = list(vaxes)
@@ -283,6 +290,10 @@ class ShardedTensor:
         self.backend = backend
         self.spare = spare  # second buffer for out-of-place apply / all-to-all
         self.peers = peers  # IPC-mapped shard buffers: swap = direct NVLink reads, no NCCL
+        self.third = third  # receive buffer of the pipelined swap (run_layer)
+        self.pipelined_swaps = 0
+        self._side = None
+        self._flag_side = None
         self.swaps = 0
         self.packs = 0
         self.fused_swaps = 0
@@ -541,6 +552,195 @@ class ShardedTensor:
         if fused is not None:
             self._apply_local(fused[0], fused[1])
 
+    # ---- a whole circuit layer with a PIPELINED axis swap ------------------------------------
+
+    def _apply_on(self, x, out, operator, axes, skip: int) -> None:  # pragma: no cover -- overridden
+        raise NotImplementedError
+
+    def _third_buffer(self) -> torch.Tensor:
+        if self.third is None or self.third.numel() != self.local.numel():
+            self.third = torch.empty_like(self.local)
+        return self.third
+
+    @staticmethod
+    def _stages_keep_program_order(ops, stage: List[int]) -> bool:
+        """Reordering by stage is valid iff every pair of operations that share a subsystem keeps
+        its program order (operations on disjoint subsystems commute)."""
+        for i in range(len(ops)):
+            for j in range(i + 1, len(ops)):
+                if stage[i] > stage[j] and set(ops[i][1]) & set(ops[j][1]):
+                    return False
+        return True
+
+    def run_layer(self, ops: Sequence[Tuple[torch.Tensor, Sequence[int]]],
+                  next_shard: Optional[Sequence[int]] = None, pipeline: bool = True,
+                  marks: Optional[list] = None) -> Dict[str, Any]:
+        """Apply ``ops`` = [(operator, subsystems)] (program order) with at most ONE axis swap.
+
+        Operations on disjoint subsystems commute, so the layer is regrouped into
+          S0  local operations that touch the OUTGOING subsystems (those about to be sharded),
+          S1  the other local operations,
+          S2  the operations that need a currently sharded subsystem (after the swap),
+        and the swap is hidden behind S1: the outgoing axes lead the buffer, so the piece
+        destined to rank c is the contiguous chunk c, itself a dense tensor S1 can be applied to
+        on its own.  Rank r works through the chunks in the order r+1, r+2, ..., r; as soon as
+        chunk c is final it travels to rank c (a copy-engine pull over NVLink from peer memory
+        behind a stream-ordered barrier, or an NCCL send/recv pair) on a side stream while the
+        next chunk is being computed.  Every step moves W pieces between W disjoint pairs.
+        Falls back to the plain schedule (S0+S1, swap, S2) when the swap needs a pack pass or is
+        group-wise, and to operation-by-operation application when the regrouping would break
+        the program order.  ``marks``: optional list that receives (label, cuda event) pairs."""
+        ops = [(o, tuple(a)) for o, a in ops]
+        info: Dict[str, Any] = {"pipelined": False, "s0": 0, "s1": 0, "s2": 0}
+        cuda = self.local.is_cuda
+
+        def mark(label):
+            if marks is not None and cuda:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((label, ev))
+
+        mark("begin")
+        cur = set(self.sharded_axes())
+        s2 = [i for i, (_, a) in enumerate(ops) if set(a) & cur]
+        if not s2:
+            for o, a in ops:
+                self._apply_local(o, a)
+            info["s1"] = len(ops)
+            mark("end")
+            return info
+        needed = {g for i in s2 for g in ops[i][1]}
+        positions, slots = self._plan_swap(needed, next_shard)
+        k = len(positions)
+        out_g = {self.vaxes[p].g for p in positions}
+        stage = [2 if i in s2 else (0 if set(a) & out_g else 1) for i, (_, a) in enumerate(ops)]
+        # dependency closure: whatever follows a post-swap operation on a shared subsystem also
+        # runs after the swap; whatever precedes an S0 operation on a shared subsystem joins S0
+        for i in range(len(ops)):
+            for j in range(i + 1, len(ops)):
+                if stage[i] == 2 and stage[j] != 2 and set(ops[i][1]) & set(ops[j][1]):
+                    stage[j] = 2
+        for j in reversed(range(len(ops))):
+            for i in range(j):
+                if stage[j] == 0 and stage[i] == 1 and set(ops[i][1]) & set(ops[j][1]):
+                    stage[i] = 0
+        ok = all(not (stage[i] == 2 and set(a) & out_g) for i, (_, a) in enumerate(ops))
+        s2 = [i for i in range(len(ops)) if stage[i] == 2]
+        if not ok or not self._stages_keep_program_order(ops, stage):
+            for o, a in ops:            # no regrouping possible: every operation on its own
+                self.ensure_local(a, next_shard)
+                self._apply_local(o, a)
+            mark("end")
+            return info
+        st0 = [ops[i] for i in range(len(ops)) if stage[i] == 0]
+        st1 = [ops[i] for i in range(len(ops)) if stage[i] == 1]
+        st2 = [ops[i] for i in range(len(ops)) if stage[i] == 2]
+        info.update(s0=len(st0), s1=len(st1), s2=len(st2))
+        W = self.world
+        full = len(slots) == len(self.sparts) and math.prod(self.sparts[q].extent for q in slots) == W
+        can_pipe = (pipeline and W > 1 and full and positions == list(range(k)) and len(st1) > 0
+                    and (self.peers is None or len(self.peers.local_ptrs) >= 3))
+        if not can_pipe:
+            for o, a in st0 + st1:
+                self._apply_local(o, a)
+            mark("local_done")
+            self.relayout(positions, slots)
+            mark("swap_done")
+            for o, a in st2:
+                self._apply_local(o, a)
+            mark("end")
+            return info
+
+        for o, a in st0:
+            self._apply_local(o, a)
+        mark("s0_done")
+        X, Y = self.local, self._buffers()
+        if self.peers is not None:
+            others = [t for t in self.peers.tensors if t.data_ptr() not in (X.data_ptr(), Y.data_ptr())]
+            Z = others[0]
+        else:
+            Z = self._third_buffer()
+        chunk = X.numel() // W
+        src_buf = X if len(st1) % 2 == 0 else Y
+        side = None
+        if cuda:
+            if self._side is None:
+                self._side = torch.cuda.Stream(priority=-1)
+            side = self._side
+            side.wait_stream(torch.cuda.current_stream())
+        r = self.rank
+        ranks_by_digit = list(range(W))  # full swap: group member c is rank c
+        for step in range(W):
+            c = (r + 1 + step) % W
+            a, b = X[c * chunk:(c + 1) * chunk], Y[c * chunk:(c + 1) * chunk]
+            for o, ax in st1:
+                self._apply_on(a, b, o, ax, k)
+                a, b = b, a
+            p = (r - step - 1) % W
+            dst = Z[p * chunk:(p + 1) * chunk]
+            self._move_piece(a, ranks_by_digit[c], dst, ranks_by_digit[p], src_buf, chunk, side)
+        mark("s1_done")
+        if cuda:
+            torch.cuda.current_stream().wait_stream(side)
+        if self.peers is not None:
+            self._barrier()  # every rank has pulled its pieces before anyone overwrites the source
+        mark("swap_done")
+        new_sparts = list(self.sparts)
+        for j, q in enumerate(slots):
+            new_sparts[q] = self.vaxes[j]
+        self.vaxes = [self.sparts[q] for q in slots] + self.vaxes[k:]
+        self.sparts = new_sparts
+        keep = X if src_buf is Y else Y
+        self.local, self.spare = Z, keep
+        if self.peers is None:
+            self.third = src_buf
+        self.swaps += 1
+        self.pipelined_swaps += 1
+        info["pipelined"] = True
+        for o, a in st2:
+            self._apply_local(o, a)
+        mark("end")
+        return info
+
+    def _move_piece(self, piece, dst_rank: int, dst, src_rank: int, src_buf, chunk: int, side) -> None:
+        """One step of the pipelined swap: `piece` (a finished chunk of this rank) goes to
+        ``dst_rank``; ``dst`` receives the chunk this rank needs from ``src_rank``."""
+        cuda = piece.is_cuda
+        if self.peers is not None:
+            ev = torch.cuda.Event()
+            ev.record()
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                if self._flag_side is None:
+                    self._flag_side = torch.zeros(1, dtype=torch.float32, device=piece.device)
+                self.dist.all_reduce(self._flag_side)   # every rank has finished this step's chunk
+                buf = self.peers.index_of(src_buf)
+                src = self.peers.ptrs[buf][src_rank] + self.rank * chunk * self.peers.esize
+                self.backend.peer_copy(dst, src, chunk * self.peers.esize)
+            return
+        if dst_rank == self.rank:        # last step: the own chunk stays
+            if cuda:
+                ev = torch.cuda.Event()
+                ev.record()
+                with torch.cuda.stream(side):
+                    side.wait_event(ev)
+                    dst.copy_(piece)
+            else:
+                dst.copy_(piece)
+            return
+        reqs = [self.dist.P2POp(self.dist.isend, torch.view_as_real(piece), dst_rank),
+                self.dist.P2POp(self.dist.irecv, torch.view_as_real(dst), src_rank)]
+        if cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                for req in self.dist.batch_isend_irecv(reqs):
+                    req.wait()
+        else:
+            for req in self.dist.batch_isend_irecv(reqs):
+                req.wait()
+
     def _apply_local(self, operator, axes) -> None:  # pragma: no cover -- overridden
         raise NotImplementedError
 
@@ -709,10 +909,14 @@ class ShardedStateVector(ShardedTensor):
         self._apply_local(operator, axes)
 
     def _apply_local(self, operator, axes) -> None:
-        targets = self._targets_for(axes)
         out = self._buffers()
-        self.backend.apply_vec(self.local, operator, self.local_dims, targets, out=out)
+        self._apply_on(self.local, out, operator, axes, 0)
         self.local, self.spare = out, self.local
+
+    def _apply_on(self, x, out, operator, axes, skip: int) -> None:
+        targets = [t - skip for t in self._targets_for(axes)]
+        assert min(targets) >= 0
+        self.backend.apply_vec(x, operator, self.local_dims[skip:], targets, out=out)
 
     # ---- reductions ---------------------------------------------------------------------------
 
@@ -783,12 +987,12 @@ class ShardedDensityMatrix(ShardedTensor):
     a set of complete rows: ``local`` is a row-major (local rows x N) matrix."""
 
     def __init__(self, dims: Sequence[int], local, vaxes, sparts, rank, world, dist, backend,
-                 spare=None, peers=None):
+                 spare=None, peers=None, third=None):
         self.dims = tuple(int(d) for d in dims)
         self.n = len(self.dims)
         self._shardable = range(self.n)
         super().__init__(self.dims + self.dims, local, vaxes, sparts, rank, world, dist, backend,
-                         spare=spare, peers=peers)
+                         spare=spare, peers=peers, third=third)
 
     @classmethod
     def initial_layout(cls, dims: Sequence[int], world: int):
@@ -839,13 +1043,17 @@ class ShardedDensityMatrix(ShardedTensor):
         self.apply_kraus(operator.reshape((1,) + tuple(operator.shape[-2:])), axes, prefer_shard)
 
     def _apply_local(self, operators, axes) -> None:
+        out = self._buffers()
+        self._apply_on(self.local, out, operators, axes, 0)
+        self.local, self.spare = out, self.local
+
+    def _apply_on(self, x, out, operators, axes, skip: int) -> None:
         if operators.dim() == 2:
             operators = operators.reshape((1,) + tuple(operators.shape))
-        rows = self._targets_for(axes)
-        cols = self._targets_for([self.n + a for a in axes])
-        out = self._buffers()
-        self.backend.kraus_axes(self.local, operators, self.local_dims, rows, cols, out=out)
-        self.local, self.spare = out, self.local
+        rows = [t - skip for t in self._targets_for(axes)]
+        cols = [t - skip for t in self._targets_for([self.n + a for a in axes])]
+        assert min(rows) >= 0
+        self.backend.kraus_axes(x, operators, self.local_dims[skip:], rows, cols, out=out)
 
     # ---- reductions -----------------------------------------------------------------------------
 

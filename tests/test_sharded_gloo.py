@@ -303,3 +303,67 @@ def _rho_worker(rank, world, port, dims, results):
 def test_sharded_density_matrix_against_oracle(world, dims):
     err, swaps = _spawn(world, _rho_worker, dims)
     assert err < 1e-12 and swaps >= 1
+
+
+# ---- whole layers with the pipelined axis swap (run_layer) ------------------------------------------
+
+
+def _layer_worker(rank, world, port, kind, dims, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = len(dims)
+        N = math.prod(dims)
+        if kind == "vec":
+            ref = ops.random_state(N, 8)
+            st = ShardedStateVector.from_full(dims, torch.from_numpy(ref.reshape(-1)), rank, world, dist,
+                                              NumpyBackend())
+        else:
+            ref = ops.random_density(N, 8)
+            st = ShardedDensityMatrix.from_full(dims, torch.from_numpy(ref.reshape(-1)), rank, world, dist,
+                                                NumpyBackend())
+        shard_a = sorted({s.g for s in st.sparts})
+        shard_b = list(range(n // 2, n // 2 + len(shard_a)))
+        pipelined = 0
+        for rep in range(4):
+            layer = []
+            for m in range(n):
+                if kind == "vec":
+                    layer.append((ops.random_unitary(dims[m], 10 * rep + m), (m,)))
+                else:
+                    layer.append((ops.loss_channel(dims[m], 0.1 + 0.05 * m), (m,)))
+            for m in range(0, n - 1, 2):
+                layer.append((ops.random_unitary(dims[m] * dims[m + 1], 100 + 10 * rep + m), (m, m + 1)))
+            cur = set(st.sharded_axes())
+            other = shard_b if cur == set(shard_a) else shard_a
+            info = st.run_layer([(torch.from_numpy(o), a) for o, a in layer], next_shard=other)
+            pipelined += int(info["pipelined"])
+            for o, a in layer:                       # the oracle applies the PROGRAM order
+                if kind == "vec":
+                    ref = oad.apply_operation_vector(dims, a, ref, o, True)
+                elif o.ndim == 3:
+                    ref = oad.apply_kraus_matrix(dims, a, ref, o, True)
+                else:
+                    ref = oad.apply_operation_matrix(dims, a, ref, o, True)
+            got = st.gather_full().numpy()
+            err = float(np.abs(got.reshape(ref.shape) - ref).max())
+            assert err < 1e-12, (rep, err)
+        # a layer whose regrouping would break the program order falls back to op-by-op
+        o1, o2 = ops.random_unitary(dims[0] * dims[1], 7), ops.random_unitary(dims[1], 9)
+        if kind == "vec":
+            st.run_layer([(torch.from_numpy(o1), (0, 1)), (torch.from_numpy(o2), (1,))], next_shard=None)
+            ref = oad.apply_operation_vector(dims, (1,), oad.apply_operation_vector(dims, (0, 1), ref, o1, True), o2, True)
+            assert np.abs(st.gather_full().numpy().reshape(ref.shape) - ref).max() < 1e-12
+        if rank == 0:
+            results.put((pipelined, st.swaps, st.packs))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind,world,dims", [("vec", 2, (4, 3, 2, 6)), ("vec", 4, (6, 6, 2, 6, 6)),
+                                             ("rho", 2, (4, 2, 6, 2)), ("rho", 4, (4, 2, 4, 2))])
+def test_run_layer_pipelined_swap_matches_program_order(kind, world, dims):
+    pipelined, swaps, packs = _spawn(world, _layer_worker, kind, dims)
+    assert swaps >= 3
+    assert pipelined >= 2      # steady state: the outgoing axes lead, the swap hides behind S1
