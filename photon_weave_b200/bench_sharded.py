@@ -113,13 +113,13 @@ def parity_preflight(dist, rank: int, world: int, local_rank: int, kind: str, ma
                      layers: int = 3, mode: str = "pipelined") -> dict:
     """A small state through the SAME LayerRunner schedule and swap implementation as the timed
     run, reassembled with gather_full() and compared with the oracle on rank 0.
-    kind 'vec': 6^8 amplitudes; kind 'rho': a (4,4,4,4) density matrix (256 x 256)."""
+    kind 'vec': 6^8 amplitudes; kind 'rho': a (4,4,4,4,4) density matrix (1024 x 1024)."""
     if kind == "vec":
         modes, cutoff = 8, 6
         dims = (cutoff,) * modes
         cls, apply = ShardedStateVector, _apply_vec
     else:
-        modes, cutoff = 4, 4
+        modes, cutoff = 5, 4
         dims = (cutoff,) * modes
         cls, apply = ShardedDensityMatrix, _apply_rho
     layer = make_layer(modes, cutoff)

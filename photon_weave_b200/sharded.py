@@ -673,12 +673,15 @@ class ShardedTensor:
         for step in range(W):
             c = (r + 1 + step) % W
             a, b = X[c * chunk:(c + 1) * chunk], Y[c * chunk:(c + 1) * chunk]
-            for o, ax in st1:
-                self._apply_on(a, b, o, ax, k)
-                a, b = b, a
             p = (r - step - 1) % W
             dst = Z[p * chunk:(p + 1) * chunk]
-            self._move_piece(a, ranks_by_digit[c], dst, ranks_by_digit[p], src_buf, chunk, side)
+            for j, (o, ax) in enumerate(st1):
+                # the own chunk (last step) never travels: its last operation writes it in place
+                out = dst if (c == r and j == len(st1) - 1) else b
+                self._apply_on(a, out, o, ax, k)
+                a, b = b, a
+            if c != r:
+                self._move_piece(a, ranks_by_digit[c], dst, ranks_by_digit[p], src_buf, chunk, side)
         mark("s1_done")
         if cuda:
             torch.cuda.current_stream().wait_stream(side)
