@@ -128,6 +128,14 @@ int pw_trace_out_mat(const void* rho, void* out, const int64_t* dims, int n,
 int pw_reduced_from_vec(const void* psi, void* out, const int64_t* dims, int n,
                         const int32_t* keep, int nkeep, int dtype, void* stream);
 
+/* out (t x t)[a, b] = sum_rest x[(a, rest)] conj(y[(b, rest)]) over a tensor of `naxes` axes (up
+ * to 64: pass dims ++ dims for density matrices), kept axes in the given order.  With x = the
+ * cotangent of the output and y = the input state this is the OPERATOR cotangent of the linear
+ * maps above: the transform rule the reference gets from jax.grad through its einsum
+ * (core/kernels.py:87-98; tests/state/test_envelope.py:846-870) -- SURVEY.md section 8f.4. */
+int pw_cross_reduced(const void* x, const void* y, void* out, const int64_t* axes, int naxes,
+                     const int32_t* keep, int nkeep, int dtype, void* stream);
+
 /* probs[j] = sum_rest |psi[j,rest]|^2 / sum_all.
  * Replaces kernels._measurement_probs_vector (core/kernels.py:28-41). */
 int pw_probs_vec(const void* psi, void* probs, const int64_t* dims, int n,

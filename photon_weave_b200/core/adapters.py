@@ -15,6 +15,9 @@ Differences a maintainer should know:
   tensor) unless the inputs were host arrays.
 * The ``*_jit`` / ``*_jit_meta`` variants exist for API compatibility; there is
   nothing to trace -- launches are already asynchronous on the current stream.
+* Transform rules (core/transforms.py): when an input tensor requires a gradient the call is
+  recorded for reverse-mode differentiation (the derivative of an apply is another apply);
+  under ``transforms.vmap`` a leading batch axis of the state is served by one launch.
 """
 
 from __future__ import annotations
@@ -26,6 +29,7 @@ import torch
 
 from . import _arrays as A
 from . import ffi
+from . import transforms as T
 from .meta import DimsMeta
 
 
@@ -67,7 +71,8 @@ def apply_operation_vector(
     target_indices = tuple(target_indices)
     state_dims = tuple(state_dims)
     expected = int(math.prod(state_dims))
-    if _size_of(product_state) != expected:
+    batch = T.current_batch()
+    if _size_of(product_state) != expected * (batch or 1):
         raise ValueError(
             f"product_state has size {_size_of(product_state)}, expected {expected} "
             f"for dims {state_dims}"
@@ -79,8 +84,34 @@ def apply_operation_vector(
             f"{(target_dim, target_dim)}"
         )
     host, ps, (op,) = _prep(product_state, operator)
-    out = ffi.apply_vec(ps, op, state_dims, target_indices)
-    return A.back(out.reshape(expected, 1), host)
+    dims, tgt, shape = state_dims, target_indices, (expected, 1)
+    if batch:  # the batch axis is one more untouched subsystem: one launch for the whole batch
+        dims, tgt, shape = (batch,) + state_dims, tuple(t + 1 for t in target_indices), (batch, expected, 1)
+    if T.needs_grad(ps, op):
+        out = T.ApplyVec.apply(ps, op, dims, tgt)
+    else:
+        out = ffi.apply_vec(ps, op, dims, tgt)
+    return A.back(out.reshape(shape), host)
+
+
+def _two_sided(ps, ops, state_dims, target_indices, single: bool):
+    """sum_k K rho K^H on the device: plain, differentiable, or batched (leading batch axis)."""
+    expected = int(math.prod(state_dims))
+    n = len(state_dims)
+    batch = T.current_batch()
+    if batch:
+        if T.needs_grad(ps, ops):
+            raise T.NotBatchable("differentiating a batched two-sided apply")
+        axes = (batch,) + state_dims + state_dims
+        rows = [1 + t for t in target_indices]
+        cols = [1 + n + t for t in target_indices]
+        out = ffi.kraus_axes(ps.reshape(-1), ops, axes, rows, cols)
+        return out.reshape(batch, expected, expected)
+    if T.needs_grad(ps, ops):
+        return T.KrausMat.apply(ps, ops, state_dims, target_indices).reshape(expected, expected)
+    if single:
+        return ffi.apply_mat(ps, ops.reshape(ops.shape[-2:]), state_dims, target_indices).reshape(expected, expected)
+    return ffi.kraus_mat(ps, ops, state_dims, target_indices).reshape(expected, expected)
 
 
 def apply_operation_matrix(
@@ -94,7 +125,7 @@ def apply_operation_matrix(
     target_indices = tuple(target_indices)
     state_dims = tuple(state_dims)
     expected = int(math.prod(state_dims))
-    if _size_of(product_state) != expected * expected:
+    if _size_of(product_state) != expected * expected * (T.current_batch() or 1):
         raise ValueError(
             f"product_state has size {_size_of(product_state)}, expected {expected**2} "
             f"for dims {state_dims}"
@@ -106,8 +137,8 @@ def apply_operation_matrix(
             f"{(target_dim, target_dim)}"
         )
     host, ps, (op,) = _prep(product_state, operator)
-    out = ffi.apply_mat(ps, op, state_dims, target_indices)
-    return A.back(out.reshape(expected, expected), host)
+    out = _two_sided(ps, op.reshape(1, target_dim, target_dim), state_dims, target_indices, single=True)
+    return A.back(out, host)
 
 
 def apply_kraus_matrix(
@@ -127,12 +158,11 @@ def apply_kraus_matrix(
     host, ps, (ops,) = _prep(product_state, operators)
     # the reference reshapes (-1, *target_dims, *target_dims) (core/adapters.py:443)
     ops = ops.reshape(-1, target_dim, target_dim)
-    if ps.numel() != expected * expected:
+    if ps.numel() != expected * expected * (T.current_batch() or 1):
         raise ValueError(
             f"product_state has size {ps.numel()}, expected {expected**2} for dims {state_dims}"
         )
-    out = ffi.kraus_mat(ps, ops, state_dims, target_indices)
-    return A.back(out.reshape(expected, expected), host)
+    return A.back(_two_sided(ps, ops, state_dims, target_indices, single=False), host)
 
 
 # --------------------------------------------------------------------------------
@@ -141,6 +171,8 @@ def apply_kraus_matrix(
 
 
 def _measure(state_dims, target_indices, product_state, key, is_matrix: bool, rescale: bool = True):
+    if T.current_batch():
+        raise T.NotBatchable("sampling has no batching rule: one call per batch element")
     target_indices = tuple(target_indices)
     state_dims = tuple(state_dims)
     host, ps, _ = _prep(product_state)
@@ -184,9 +216,14 @@ def measure_vector_expectation(state_dims, target_indices, product_state):
     """
     target_indices = tuple(target_indices)
     state_dims = tuple(state_dims)
+    if T.current_batch():
+        raise T.NotBatchable("expectation of a batch: one call per batch element")
     host, ps, _ = _prep(product_state)
+    rest = _rest(state_dims, target_indices)
+    if T.needs_grad(ps):  # differentiable (tests/state/utils/test_measurements.py:337-353)
+        return T.ProbsVec.apply(ps, state_dims, target_indices), T.ReducedFromVec.apply(ps, state_dims, tuple(rest))
     probs = ffi.probs(ps, state_dims, target_indices, False)
-    post = ffi.reduced_from_vec(ps, state_dims, _rest(state_dims, target_indices))
+    post = ffi.reduced_from_vec(ps, state_dims, rest)
     return A.back(probs, host), A.back(post, host)
 
 
@@ -194,9 +231,13 @@ def measure_matrix_expectation(state_dims, target_indices, product_state):
     """core/adapters.py:646-673 -> (probs, Tr_targets rho)."""
     target_indices = tuple(target_indices)
     state_dims = tuple(state_dims)
+    if T.current_batch():
+        raise T.NotBatchable("expectation of a batch: one call per batch element")
     host, ps, _ = _prep(product_state)
-    probs = ffi.probs(ps, state_dims, target_indices, True)
     rest = _rest(state_dims, target_indices)
+    if T.needs_grad(ps):  # differentiable (tests/state/utils/test_measurements.py:356-371)
+        return T.ProbsMat.apply(ps, state_dims, target_indices), T.TraceOutMat.apply(ps, state_dims, tuple(rest))
+    probs = ffi.probs(ps, state_dims, target_indices, True)
     post = ffi.trace_out_mat(ps, state_dims, rest)
     return A.back(probs, host), A.back(post, host)
 
@@ -247,7 +288,11 @@ def trace_out_matrix(state_dims, target_indices, product_state, use_contraction:
             f"for dims {state_dims}"
         )
     keep = sorted(target_indices) if use_contraction else list(target_indices)
+    if T.current_batch():
+        raise T.NotBatchable("partial trace of a batch: one call per batch element")
     host, ps, _ = _prep(product_state)
+    if T.needs_grad(ps):
+        return T.TraceOutMat.apply(ps, state_dims, tuple(keep))
     return A.back(ffi.trace_out_mat(ps, state_dims, keep), host)
 
 
@@ -259,7 +304,11 @@ def trace_out_vector(state_dims, target_indices, product_state, use_contraction:
     state_dims = tuple(state_dims)
     target_indices = tuple(target_indices)
     keep = sorted(target_indices) if use_contraction else list(target_indices)
+    if T.current_batch():
+        raise T.NotBatchable("partial trace of a batch: one call per batch element")
     host, ps, _ = _prep(product_state)
+    if T.needs_grad(ps):
+        return T.ReducedFromVec.apply(ps, state_dims, tuple(keep))
     return A.back(ffi.reduced_from_vec(ps, state_dims, keep), host)
 
 

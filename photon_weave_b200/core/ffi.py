@@ -83,6 +83,19 @@ def reduced_from_vec(psi: torch.Tensor, dims, keep):
     return out
 
 
+def cross_reduced(x: torch.Tensor, y: torch.Tensor, axes, keep):
+    """out[a, b] = sum_rest x[(a, rest)] conj(y[(b, rest)]) (operator cotangent of a linear apply)."""
+    lib = _lib.load()
+    t = math.prod(axes[i] for i in keep)
+    out = torch.empty((t, t), dtype=x.dtype, device=x.device)
+    _lib.check(
+        lib.pw_cross_reduced(x.data_ptr(), y.data_ptr(), out.data_ptr(), _lib.i64_array(axes), len(axes),
+                             _lib.i32_array(keep), len(keep), A.code(x.dtype), A.stream_ptr()),
+        "pw_cross_reduced",
+    )
+    return out
+
+
 def probs(state: torch.Tensor, dims, targets, is_matrix: bool):
     lib = _lib.load()
     t = math.prod(dims[i] for i in targets)

@@ -143,6 +143,29 @@ k_trace_strided(const V* __restrict__ x, const FiberMap fm, const TargetMap rows
   }
 }
 
+// out[a, b] = sum_f x[f, a] conj(y[f, b]): the operator cotangent of a linear apply (the VJP of
+// y = O psi with respect to O pairs the output cotangent with the input state)
+template <typename V>
+__global__ void __launch_bounds__(kRedBlock)
+k_cross_reduced(const V* __restrict__ x, const V* __restrict__ y, const FiberMap fm, const TargetMap tm,
+                V* __restrict__ out) {
+  __shared__ double s_scratch[4];
+  const uint64_t t = tm.t, nout = t * t;
+  for (uint64_t o = blockIdx.x; o < nout; o += gridDim.x) {
+    const int64_t oa = tm.offset((uint32_t)(o / t)), ob = tm.offset((uint32_t)(o % t));
+    double re = 0, im = 0;
+    for (uint64_t f = threadIdx.x; f < fm.nfib; f += blockDim.x) {
+      const int64_t base = fm.base(f);
+      const V u = x[base + oa], v = y[base + ob];
+      re += (double)u.x * v.x + (double)u.y * v.y;   // u * conj(v)
+      im += (double)u.y * v.x - (double)u.x * v.y;
+    }
+    re = block_sum(re, s_scratch);
+    im = block_sum(im, s_scratch);
+    if (threadIdx.x == 0) { V r; r.x = re; r.y = im; out[o] = r; }
+  }
+}
+
 // out[f] = x[base(f)] / den,  den = 1 | sqrt(probs[o] + 1e-18) | probs[o] + 1e-18 (the collapse
 // rescaling of core/kernels.py:205,225 on a strided slice)
 template <typename V>
@@ -1076,6 +1099,27 @@ extern "C" int pw_gather_strided(const void* x, const int64_t* extent, const int
   FiberMap fm;
   PW_TRY(strided_fibers(extent, stride, naxes, &fm));
   return PW_DISPATCH(dtype, gather_strided_t, x, out, fm, probs, outcome, mode, (cudaStream_t)stream);
+}
+
+template <typename V>
+static int cross_reduced_t(const void* x, const void* y, void* out, const Plan& p, cudaStream_t s) {
+  const uint64_t nout = (uint64_t)p.tm.t * p.tm.t;
+  const int grid = (int)(nout < (uint64_t)kNumSMs * 16 ? nout : (uint64_t)kNumSMs * 16);
+  k_cross_reduced<V><<<grid, kRedBlock, 0, s>>>((const V*)x, (const V*)y, p.fm, p.tm, (V*)out);
+  PW_LAUNCHED();
+  return PW_OK;
+}
+
+extern "C" int pw_cross_reduced(const void* x, const void* y, void* out, const int64_t* axes, int naxes,
+                                const int32_t* keep, int nkeep, int dtype, void* stream) {
+  if (!x || !y || !out) return PW_ERR_INVALID;
+  Plan p;
+  int tg[kMaxTargets];
+  if (nkeep < 1 || nkeep > kMaxTargets || !keep) return PW_ERR_INVALID;
+  for (int i = 0; i < nkeep; ++i) tg[i] = keep[i];
+  PW_TRY(build_plan_axes(axes, naxes, tg, nkeep, &p));
+  if ((uint64_t)p.tm.t * p.tm.t > 0xffffffffull) return PW_ERR_UNSUPPORTED;
+  return PW_DISPATCH(dtype, cross_reduced_t, x, y, out, p, (cudaStream_t)stream);
 }
 
 template <typename V>
