@@ -154,6 +154,11 @@ int pw_probs_mat(const void* rho, void* probs, const int64_t* dims, int n,
 int pw_draw(const void* probs, int64_t t, uint32_t key0, uint32_t key1, int dtype,
             int64_t* outcome, void* stream);
 
+/* Same draw with the key's two uint32 words in DEVICE memory (a traced jax.random key inside a
+ * jitted computation: the XLA FFI handler cannot read it on the host without a sync). */
+int pw_draw_devkey(const void* probs, int64_t t, const uint32_t* key_dev, int dtype,
+                   int64_t* outcome, void* stream);
+
 /* post (r) = psi[outcome, :] / sqrt(probs[outcome] + 1e-18); rest in tensor order.
  * `outcome` and `probs` are device pointers (outputs of pw_draw / pw_probs_vec).
  * probs == NULL: plain gather without rescaling (jnp.take of the legacy sequential path,

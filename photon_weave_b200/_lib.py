@@ -58,6 +58,7 @@ SIGNATURES = {
     "pw_probs_vec": (C.c_int, [_vp, _vp, _i64p, C.c_int, _i32p, C.c_int, C.c_int, _vp]),
     "pw_probs_mat": (C.c_int, [_vp, _vp, _i64p, C.c_int, _i32p, C.c_int, C.c_int, _vp]),
     "pw_draw": (C.c_int, [_vp, C.c_int64, C.c_uint32, C.c_uint32, C.c_int, _vp, _vp]),
+    "pw_draw_devkey": (C.c_int, [_vp, C.c_int64, _vp, C.c_int, _vp, _vp]),
     "pw_collapse_vec": (
         C.c_int,
         [_vp, _vp, _vp, _vp, _i64p, C.c_int, _i32p, C.c_int, C.c_int, _vp],

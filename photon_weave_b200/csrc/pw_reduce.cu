@@ -624,13 +624,14 @@ k_draw_chunks(const R* __restrict__ probs, const int64_t t, double* __restrict__
 template <typename R>
 __global__ void __launch_bounds__(kDrawBlock)
 k_draw(const R* __restrict__ probs, const int64_t t, const double* __restrict__ chunk_sum,
-       const int64_t nchunks, const uint32_t k0, const uint32_t k1, const int exact,
-       int64_t* __restrict__ outcome) {
+       const int64_t nchunks, uint32_t k0, uint32_t k1, const uint32_t* __restrict__ key_dev,
+       const int exact, int64_t* __restrict__ outcome) {
   __shared__ double s_part[kDrawBlock];
   __shared__ double s_total, s_before;
   __shared__ int64_t s_chunk;
   __shared__ int s_clear;
   const int tid = threadIdx.x;
+  if (key_dev) { k0 = key_dev[0]; k1 = key_dev[1]; }  // key produced on the device (XLA FFI path)
   const R u = draw_uniform<R>(k0, k1);
   const double eps = sizeof(R) == 8 ? 1.1102230246251565e-16 : 5.9604644775390625e-8;
 
@@ -1159,12 +1160,12 @@ extern "C" int pw_trace_out_mat(const void* rho, void* out, const int64_t* dims,
 }
 
 template <typename V>
-static int draw_t(const void* probs, int64_t t, uint32_t k0, uint32_t k1, int64_t* outcome,
-                  cudaStream_t s) {
+static int draw_t(const void* probs, int64_t t, uint32_t k0, uint32_t k1, const uint32_t* key_dev,
+                  int64_t* outcome, cudaStream_t s) {
   using R = typename RealOf<V>::type;
   const int exact = options().draw_exact.load();
   if (t <= kDrawChunk) {
-    k_draw<R><<<1, kDrawBlock, 0, s>>>((const R*)probs, t, nullptr, 1, k0, k1, exact, outcome);
+    k_draw<R><<<1, kDrawBlock, 0, s>>>((const R*)probs, t, nullptr, 1, k0, k1, key_dev, exact, outcome);
     PW_LAUNCHED();
     return PW_OK;
   }
@@ -1173,8 +1174,8 @@ static int draw_t(const void* probs, int64_t t, uint32_t k0, uint32_t k1, int64_
   PW_TRY(cs.alloc(sizeof(double) * nchunks, s));
   k_draw_chunks<R><<<(unsigned)nchunks, kDrawBlock, 0, s>>>((const R*)probs, t, (double*)cs.p);
   PW_LAUNCHED();
-  k_draw<R><<<1, kDrawBlock, 0, s>>>((const R*)probs, t, (const double*)cs.p, nchunks, k0, k1, exact,
-                                    outcome);
+  k_draw<R><<<1, kDrawBlock, 0, s>>>((const R*)probs, t, (const double*)cs.p, nchunks, k0, k1, key_dev,
+                                    exact, outcome);
   PW_LAUNCHED();
   return PW_OK;
 }
@@ -1182,7 +1183,13 @@ static int draw_t(const void* probs, int64_t t, uint32_t k0, uint32_t k1, int64_
 extern "C" int pw_draw(const void* probs, int64_t t, uint32_t key0, uint32_t key1, int dtype,
                        int64_t* outcome, void* stream) {
   if (!probs || !outcome || t < 1) return PW_ERR_INVALID;
-  return PW_DISPATCH(dtype, draw_t, probs, t, key0, key1, outcome, (cudaStream_t)stream);
+  return PW_DISPATCH(dtype, draw_t, probs, t, key0, key1, nullptr, outcome, (cudaStream_t)stream);
+}
+
+extern "C" int pw_draw_devkey(const void* probs, int64_t t, const uint32_t* key_dev, int dtype,
+                              int64_t* outcome, void* stream) {
+  if (!probs || !outcome || !key_dev || t < 1) return PW_ERR_INVALID;
+  return PW_DISPATCH(dtype, draw_t, probs, t, 0u, 0u, key_dev, outcome, (cudaStream_t)stream);
 }
 
 template <typename V>
