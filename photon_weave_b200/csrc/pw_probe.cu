@@ -1,0 +1,86 @@
+// Arithmetic-peak probes: the SECOND roof of the dense-operator kernels (SURVEY.md section 8d;
+// BASELINE.md section 2 left the FP64 peak "unmeasured").  Register-only kernels with long chains
+// of independent FP64 FMAs / mma.sync.m8n8k4.f64 (DMMA) / FP32 FMAs; the caller times them with
+// CUDA events (tools/fp64_peak.py) and the flop count is returned, so that dense 36x36 / 64x64
+// operators can be quoted against a MEASURED compute roof as well as against HBM.
+#include "pw_internal.cuh"
+
+namespace pw {
+
+constexpr int kProbeBlock = 256;
+constexpr int kProbeCtas = 8;  // per SM
+
+__global__ void __launch_bounds__(kProbeBlock)
+k_probe_dfma(const int iters, double* __restrict__ sink) {
+  double a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = 1e-3 * (threadIdx.x + i);
+  const double m = 1.0000001, c = 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = fma(a[i], m, c);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 12345.678) sink[0] = s;  // keeps the chains alive, never true
+}
+
+__global__ void __launch_bounds__(kProbeBlock)
+k_probe_sfma(const int iters, double* __restrict__ sink) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = 1e-3f * (threadIdx.x + i);
+  const float m = 1.00001f, c = 1e-6f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], m, c);
+  }
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 12345.678f) sink[0] = s;
+}
+
+__global__ void __launch_bounds__(kProbeBlock)
+k_probe_dmma(const int iters, double* __restrict__ sink) {
+  double c0[8], c1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { c0[i] = 0; c1[i] = 0; }
+  const double a = 1e-3 * (threadIdx.x & 31), b = 1.0 + 1e-6 * (threadIdx.x >> 5);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c0[i]), "+d"(c1[i]) : "d"(a), "d"(b));
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c0[i] + c1[i];
+  if (s == 12345.678) sink[0] = s;
+}
+
+}  // namespace pw
+
+using namespace pw;
+
+// kind 0: FP64 FMA, 1: FP64 mma.sync m8n8k4 (DMMA), 2: FP32 FMA.  Enqueues ONE kernel of `iters`
+// iterations on `stream`; *flops receives the real flops it executes.  `sink` is one device double.
+extern "C" int pw_probe_arith(int kind, int iters, double* sink, double* flops, void* stream) {
+  if (!sink || !flops || iters < 1 || kind < 0 || kind > 2) return PW_ERR_INVALID;
+  const int grid = kNumSMs * kProbeCtas;
+  cudaStream_t s = (cudaStream_t)stream;
+  const double threads = (double)grid * kProbeBlock;
+  if (kind == 0) {
+    k_probe_dfma<<<grid, kProbeBlock, 0, s>>>(iters, sink);
+    *flops = threads * 16.0 * 2.0 * iters;
+  } else if (kind == 2) {
+    k_probe_sfma<<<grid, kProbeBlock, 0, s>>>(iters, sink);
+    *flops = threads * 16.0 * 2.0 * iters;
+  } else {
+    k_probe_dmma<<<grid, kProbeBlock, 0, s>>>(iters, sink);
+    *flops = (threads / 32.0) * 8.0 * 512.0 * iters;  // 8 MMAs of 2*8*8*4 flops per warp iteration
+  }
+  PW_LAUNCHED();
+  return PW_OK;
+}
