@@ -107,6 +107,15 @@ int pw_kraus_mat(const void* rho, void* out, const void* ops, int K, const int64
 int pw_apply_vec_pair(const void* psi, void* out, const void* op_a, const void* op_b,
                       const int64_t* dims, int n, int axis_a, int axis_b, int dtype, void* stream);
 
+/* `nops` (2..4) single-subsystem operators on DIFFERENT axes of one common dimension D (2..8) in
+ * ONE HBM pass: psi' = prod_i (ops[i] on axes[i]) psi (they commute).  `ops` is a HOST array of
+ * device pointers.  The sub-tensor spanned by the axes stays resident in shared memory while the
+ * operators are applied one after the other, so a layer of single-mode operators
+ * (fock.py:427 -> composite_envelope.py:587 once per mode) crosses HBM once per nops operators.
+ * `out` may alias `psi`.  PW_ERR_UNSUPPORTED outside that shape (apply them one by one). */
+int pw_apply_vec_multi(const void* psi, void* out, const void* const* ops, const int64_t* dims, int n,
+                       const int32_t* axes, int nops, int dtype, void* stream);
+
 /* Fused multi-step evolution of a small state (prod(dims) <= 128) under ONE dense operator
  * acting on ALL subsystems (op is N x N, indices in tensor order): psi <- op^nsteps psi in a
  * single kernel.  If reduced_out != NULL it receives, for every step s, the reduced density

@@ -109,6 +109,7 @@ SIGNATURES = {
     ),
     "pw_rng_split": (C.c_int, [C.POINTER(C.c_uint32), C.c_int, C.POINTER(C.c_uint32)]),
     "pw_apply_vec_pair": (C.c_int, [_vp, _vp, _vp, _vp, _i64p, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    "pw_apply_vec_multi": (C.c_int, [_vp, _vp, C.POINTER(_vp), _i64p, C.c_int, _i32p, C.c_int, C.c_int, _vp]),
     "pw_evolve_vec": (
         C.c_int,
         [_vp, _vp, _vp, _i64p, C.c_int, _i32p, C.c_int, C.c_int, _vp, C.c_int, _vp],

@@ -250,6 +250,20 @@ def apply_vec_pair(psi: torch.Tensor, op_a: torch.Tensor, op_b: torch.Tensor, di
     return out
 
 
+def apply_vec_multi(psi: torch.Tensor, ops, dims, axes, out: Optional[torch.Tensor] = None):
+    """prod_i (ops[i] on axes[i]) psi in ONE pass (2..4 operators of one dimension on different
+    axes); returns None when the shape is unsupported."""
+    lib = _lib.load()
+    out = torch.empty_like(psi) if out is None else out
+    arr = (C.c_void_p * len(ops))(*[o.data_ptr() for o in ops])
+    rc = lib.pw_apply_vec_multi(psi.data_ptr(), out.data_ptr(), arr, _lib.i64_array(dims), len(dims),
+                                _lib.i32_array(axes), len(axes), A.code(psi.dtype), A.stream_ptr())
+    if rc == 2:
+        return None
+    _lib.check(rc, "pw_apply_vec_multi")
+    return out
+
+
 def circuit_device(state: torch.Tensor, scratch: Optional[torch.Tensor], is_matrix: bool, dims,
                    ops_list, fuse: bool = True):
     """Device-resident op list (pw_circuit_device): ops_list = [(kind, targets, device tensor)].

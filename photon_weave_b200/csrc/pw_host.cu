@@ -29,8 +29,29 @@ static int run_ops(void** cur, void** other, int is_matrix, const int64_t* dims,
     void* dst = *other ? *other : *cur;
     int rc = PW_ERR_UNSUPPORTED;
     int used = 1;
-    if (fuse && *other && o.kind == 0 && o.nt == 1 && i + 1 < nops && ops[i + 1].kind == 0 &&
-        ops[i + 1].nt == 1 && ops[i + 1].targets[0] != o.targets[0]) {
+    if (fuse && o.kind == 0 && o.nt == 1) {
+      // consecutive single-subsystem operators on DIFFERENT axes commute: up to `fuse_group` of
+      // one common dimension go through the resident-tile kernel in ONE pass
+      const int gmax = pw::options().fuse_group.load(std::memory_order_relaxed);
+      int cnt = 1;
+      int32_t axes[4] = {o.targets[0], 0, 0, 0};
+      const void* gops[4] = {dev_ops[i], nullptr, nullptr, nullptr};
+      while (cnt < gmax && cnt < 4 && i + cnt < nops && ops[i + cnt].kind == 0 && ops[i + cnt].nt == 1 &&
+             dims[ops[i + cnt].targets[0]] == dims[o.targets[0]]) {
+        bool dup = false;
+        for (int k = 0; k < cnt; ++k) dup = dup || axes[k] == ops[i + cnt].targets[0];
+        if (dup) break;
+        axes[cnt] = ops[i + cnt].targets[0];
+        gops[cnt] = dev_ops[i + cnt];
+        ++cnt;
+      }
+      while (cnt >= 2 && rc == PW_ERR_UNSUPPORTED) {
+        rc = pw_apply_vec_multi(*cur, dst, gops, dims, n, axes, cnt, dtype, s);
+        if (rc == PW_OK) used = cnt; else if (rc == PW_ERR_UNSUPPORTED) --cnt;
+      }
+    }
+    if (rc == PW_ERR_UNSUPPORTED && fuse && *other && o.kind == 0 && o.nt == 1 && i + 1 < nops &&
+        ops[i + 1].kind == 0 && ops[i + 1].nt == 1 && ops[i + 1].targets[0] != o.targets[0]) {
       rc = pw_apply_vec_pair(*cur, dst, dev_ops[i], dev_ops[i + 1], dims, n, o.targets[0],
                              ops[i + 1].targets[0], dtype, s);
       if (rc == PW_OK) used = 2;

@@ -179,7 +179,8 @@ struct Options {
   std::atomic<int> contig_kernel{1};           // warp-transposing kernel for contiguous fibers
   std::atomic<int> diag_kernel{1};             // diagonal t <= 8 operators on large vectors: one streaming pass
   std::atomic<int> contig_mma{1};              // ... on the FP64 tensor cores (complex128, one 5..8-level target)
-  std::atomic<int> fuse_pairs{0};              // circuit entry points fuse adjacent single-axis ops
+  std::atomic<int> fuse_pairs{1};              // circuit entry points fuse adjacent single-axis ops
+  std::atomic<int> fuse_group{3};              // ... up to this many per HBM pass (resident-tile kernel, 2..4)
   std::atomic<int> mat_pair_max_d{4};          // single-pass U rho U^dagger register tile up to this d
   std::atomic<int> seg_kernel{1};              // warp-staged block kernel for innermost-target layouts
   std::atomic<int> nstage{0};                  // tiled kernel pipeline depth (0 = auto)

@@ -804,3 +804,67 @@ def test_diagonal_operator_streaming_kernel(ad, cdtype):
         ref = oad.apply_operation_vector(dims, tg, psi.astype(np.complex128), op, True)
         out = host(ad.apply_operation_vector(dims, tg, dev(psi), dev(op.astype(cdtype))))
         assert rel_err(out, ref) < tol, tg
+
+
+@pytest.mark.parametrize("cdtype", [np.complex128, np.complex64])
+@pytest.mark.parametrize("dims,axes", [
+    ((6, 6, 6, 6, 6, 6), (0, 1, 2)), ((6, 6, 6, 6, 6, 6), (3, 4, 5)), ((6, 6, 6, 6, 6, 6), (4, 1, 5)),
+    ((6, 6, 6, 6, 6, 6), (2, 0)), ((6, 6, 6, 6, 6), (0, 1, 2, 3)), ((6, 6, 6, 6, 6), (1, 2, 3, 4)),
+    ((4, 3, 4, 5, 4, 8), (2, 0, 4)), ((2,) * 10, (9, 3, 0, 5)), ((8, 8, 8, 4), (1, 0, 2)), ((3, 3, 3), (0, 1, 2)),
+    ((5, 7, 5, 16), (0, 2)), ((6, 6, 36), (1, 0)),
+])
+def test_fused_multi_operator_tile_kernel(ad, dims, axes, cdtype):
+    """pw_apply_vec_multi: k single-subsystem operators on different axes in ONE pass equal their
+    one-by-one application (core/kernels.py:62-98 applied k times); in place too."""
+    from photon_weave_b200.core import ffi
+
+    N = math.prod(dims)
+    psi = ops.random_state(N, 61, cdtype)
+    us = [ops.random_unitary(dims[a], 70 + i).astype(cdtype) for i, a in enumerate(axes)]
+    ref = psi.astype(np.complex128)
+    for a, u in zip(axes, us):
+        ref = oad.apply_operation_vector(dims, (a,), ref, u.astype(np.complex128))
+    d_psi = dev(psi).reshape(-1)
+    out = ffi.apply_vec_multi(d_psi, [dev(u) for u in us], dims, axes)
+    assert out is not None, "shape should be supported"
+    assert rel_err(host(out).reshape(-1, 1), ref) < TOL[cdtype]
+    same = ffi.apply_vec_multi(d_psi, [dev(u) for u in us], dims, axes, out=d_psi)
+    assert rel_err(host(same).reshape(-1, 1), ref) < TOL[cdtype]
+
+
+def test_fused_multi_operator_rejects_what_it_cannot_tile(ad):
+    from photon_weave_b200.core import ffi
+
+    psi = dev(ops.random_state(4 * 3 * 4, 1)).reshape(-1)
+    u4, u3 = dev(ops.random_unitary(4, 1)), dev(ops.random_unitary(3, 2))
+    assert ffi.apply_vec_multi(psi, [u4, u3], (4, 3, 4), (0, 1)) is None          # mixed dimensions
+    with pytest.raises(Exception):
+        ffi.apply_vec_multi(psi, [u4, u4], (4, 3, 4), (0, 0))                       # duplicate axis
+
+
+def test_device_circuit_groups_commuting_operators(ad):
+    """pw_circuit_device with fuse: a layer of single-mode operators + beam splitters equals the
+    op-by-op result (the program order is kept wherever operators share a subsystem)."""
+    from photon_weave_b200 import _lib
+    from photon_weave_b200.core import ffi
+
+    dims = (6,) * 7
+    N = math.prod(dims)
+    psi = ops.random_state(N, 5)
+    layer = [((m,), ops.random_unitary(6, 10 + m)) for m in range(7)]
+    layer += [((0, 1), ops.beam_splitter(6, 6, 0.7)), ((3,), ops.random_unitary(6, 30)), ((4,), ops.random_unitary(6, 31)),
+              ((3,), ops.random_unitary(6, 32)), ((5, 6), ops.beam_splitter(6, 6, 0.2)), ((2,), ops.random_unitary(6, 33))]
+    ref = psi
+    for tg, op in layer:
+        ref = oad.apply_operation_vector(dims, tg, ref, op)
+    for group in (2, 3, 4):
+        _lib.set_option("fuse_group", group)
+        try:
+            n0 = _lib.load().pw_launch_count()
+            a, b = dev(psi).reshape(-1), torch.empty(N, dtype=torch.complex128, device="cuda")
+            res, _ = ffi.circuit_device(a, b, False, dims, [(0, tg, dev(op)) for tg, op in layer], fuse=True)
+            fused_launches = _lib.load().pw_launch_count() - n0
+        finally:
+            _lib.set_option("fuse_group", 3)
+        assert rel_err(host(res).reshape(-1, 1), ref) < 1e-12, group
+        assert fused_launches < len(layer) + 6
