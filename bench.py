@@ -400,6 +400,27 @@ def run_gpu_arm(args):
     # norm must still be 1: every operator in the layer is unitary
     norm_after = float(ffi.norm_stats(a)[0])
 
+    # ---- the same layer through the circuit entry point (pw_circuit_device, fuse = 1): commuting
+    # single-mode operators are grouped three per HBM pass (resident-tile kernel); results equal the
+    # op-by-op layer (tests/test_gpu_parity.py::test_device_circuit_groups_commuting_operators)
+    ops_list = [(0, targets[i], d_ops[i]) for i in range(nops)]
+    fa, fb = ffi.circuit_device(a, b, False, dims, ops_list, fuse=True)
+    torch.cuda.synchronize()
+    n_f0 = lib.pw_launch_count()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        fa, fb = ffi.circuit_device(fa, fb, False, dims, ops_list, fuse=True)
+    f1.record()
+    torch.cuda.synchronize()
+    fused_ms = f0.elapsed_time(f1) / args.steps
+    fused = {"ms_per_step": fused_ms, "value": nops * N / (fused_ms * 1e-3), "unit": UNIT,
+             "launches_per_step": (lib.pw_launch_count() - n_f0) / args.steps,
+             "norm_after": float(ffi.norm_stats(fa)[0]),
+             "api": "pw_circuit_device(fuse=1): up to 3 commuting single-mode operators per HBM pass "
+                    "(pw_apply_vec_multi), beam splitters one pass each"}
+    a, b = fa, fb
+
     # per-operation device times from the events recorded inside the timed region
     per_op_ms = np.zeros(nops)
     for s in range(args.steps):
@@ -504,6 +525,7 @@ def run_gpu_arm(args):
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
         "config": workload_config(args, 1), "clocks": clocks, "e2e": e2e, "e2e_serial": e2e_serial,
+        "value_fused": fused["value"], "fused": fused,
         "gpu_launches": launches, "roofline": roofline, "roofline_kraus": roofline_kraus,
         "cpu_baseline": cpu,
         "kernels": kernels, "norm_after": norm_after, "density_matrix": extras, "small_configs": small,

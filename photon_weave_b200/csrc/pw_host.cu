@@ -45,7 +45,13 @@ static int run_ops(void** cur, void** other, int is_matrix, const int64_t* dims,
         gops[cnt] = dev_ops[i + cnt];
         ++cnt;
       }
-      while (cnt >= 2 && rc == PW_ERR_UNSUPPORTED) {
+      // measured on the 34.8 GB vector (profiles/r2_multi_*.txt): three or four operators per
+      // pass win everywhere in complex128 (1.28-1.47x); pairs go to the register-tile pair kernel
+      // below; complex64 tiles whose contiguous direction is a target lose (0.7x) and stay unfused
+      bool inner = false;
+      for (int k = 0; k < cnt; ++k) inner = inner || axes[k] == n - 1;
+      if (dtype == PW_C64 && inner) cnt = 0;
+      while (cnt >= 3 && rc == PW_ERR_UNSUPPORTED) {
         rc = pw_apply_vec_multi(*cur, dst, gops, dims, n, axes, cnt, dtype, s);
         if (rc == PW_OK) used = cnt; else if (rc == PW_ERR_UNSUPPORTED) --cnt;
       }

@@ -23,7 +23,6 @@
 namespace pw {
 
 constexpr int kMuMaxOps = 4;
-constexpr int kMuThreads = 256;
 
 struct MultiGeom {
   int nops;
@@ -33,6 +32,8 @@ struct MultiGeom {
   int st[kMuMaxOps]; // in-tile element stride of operator i's digit
   int64_t cstride;   // element stride between consecutive fibers of a chunk
   int j_fastest;     // load / store order: 1 = joint index fastest (innermost axis is a target)
+  int logC;          // C == 1 << logC, or -1
+  uint32_t inv_c, inv_t, inv_st[kMuMaxOps];  // ceil(2^32 / x): x / y for x < 2^16 is umulhi(x, inv)
   uint64_t units;    // nfib / C
   const void* op[kMuMaxOps];  // device operator of digit i (D x D, row-major)
 };
@@ -49,90 +50,131 @@ __device__ __forceinline__ void mu_commit() { asm volatile("cp.async.commit_grou
 template <int N>
 __device__ __forceinline__ void mu_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// dynamic smem: ops [nops][D*D] | offs [t] (int64) | tiles [2][tile]
-template <typename V, int D>
-__global__ void __launch_bounds__(kMuThreads, 2)
+// dynamic smem: ops [nops][D*D] | offs [t] (int64) | tile [tile]
+// F fibers of a pass per thread: every operator element read from shared memory (a broadcast
+// LDS.128 costs the load/store unit four cycles per warp whatever the data) is used for F
+// fibers, which is what keeps the kernel off the shared-memory instruction roof: with one fiber
+// per thread the 48 LDS/STS per 144 DFMAs bound it at 25 ms for three operators (measured);
+// F = 3 needs 24.  Tiles are single-buffered: several small CTAs per SM overlap each other's
+// load / compute / store phases.
+// CTA size / resident CTAs per fibers-per-thread: F fibers of D complex values live in registers
+constexpr int mu_threads(int F) { return F == 1 ? 384 : (F == 2 ? 192 : (F == 3 ? 128 : 96)); }
+constexpr int mu_ctas(int F) { return F == 1 ? 2 : (F == 2 ? 3 : 4); }  // (F = 3 at 5 CTAs spills: 28 ms against 22.9)
+
+template <typename V, int D, int F>
+__global__ void __launch_bounds__(mu_threads(F), mu_ctas(F))
 k_apply_multi(const V* in, V* out, const FiberMap fm, const TargetMap tm, const MultiGeom g) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   V* s_ops = (V*)s_raw;
   int64_t* s_off = (int64_t*)(s_ops + ((g.nops * D * D + 1) & ~1));
-  V* tiles = (V*)(s_off + ((g.t + 1) & ~1));
-  const int tid = threadIdx.x;
-  for (int i = tid; i < g.nops * D * D; i += kMuThreads) s_ops[i] = ((const V*)g.op[i / (D * D)])[i % (D * D)];
-  for (int j = tid; j < g.t; j += kMuThreads) s_off[j] = tm.offset((uint32_t)j);
+  V* tile = (V*)(s_off + ((g.t + 1) & ~1));
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  for (int i = tid; i < g.nops * D * D; i += nthr) s_ops[i] = ((const V*)g.op[i / (D * D)])[i % (D * D)];
+  for (int j = tid; j < g.t; j += nthr) s_off[j] = tm.offset((uint32_t)j);
   __syncthreads();
-
-  auto issue = [&](uint64_t u, int buf) {
-    if (u < g.units) {
-      V* tile = tiles + (size_t)buf * g.tile;
-      const V* src = in + fm.base(u * (uint64_t)g.C);
-      for (int e = tid; e < g.tile; e += kMuThreads) {
-        int j, c;
-        if (g.j_fastest) { c = e / g.t; j = e - c * g.t; } else { j = e / g.C; c = e - j * g.C; }
-        const V* p = src + s_off[j] + (int64_t)c * g.cstride;
-        if (sizeof(V) == 16) mu_cp16(tile + j * g.C + c, p); else mu_cp8(tile + j * g.C + c, p);
-      }
+  // tile slot e -> (joint index j, fiber c) without integer division
+  auto split = [&](int e, int& j, int& c) {
+    if (g.j_fastest) { c = (int)__umulhi((uint32_t)e, g.inv_t); j = e - c * g.t; }
+    else if (g.logC >= 0) { j = e >> g.logC; c = e & (g.C - 1); }
+    else { j = (int)__umulhi((uint32_t)e, g.inv_c); c = e - j * g.C; }
+  };
+  const int nf = g.tile / D;  // fibers per pass
+  for (uint64_t u = blockIdx.x; u < g.units; u += gridDim.x) {
+    const int64_t base = fm.base(u * (uint64_t)g.C);
+    const V* src = in + base;
+    for (int e = tid; e < g.tile; e += nthr) {
+      int j, c;
+      split(e, j, c);
+      const V* p = src + s_off[j] + (int64_t)c * g.cstride;
+      if (sizeof(V) == 16) mu_cp16(tile + j * g.C + c, p); else mu_cp8(tile + j * g.C + c, p);
     }
     mu_commit();
-  };
-
-  uint64_t u = blockIdx.x;
-  int cur = 0;
-  issue(u, 0);
-  for (; u < g.units; u += gridDim.x) {
-    V* tile = tiles + (size_t)cur * g.tile;
-    issue(u + gridDim.x, cur ^ 1);
-    mu_wait<1>();
+    mu_wait<0>();
     __syncthreads();
-    const int nf = g.tile / D;  // fibers per pass
     for (int i = 0; i < g.nops; ++i) {
       const int st = g.st[i];
       int zero = 0;
       asm volatile("" : "+r"(zero));  // keep the operator in shared memory (broadcast loads)
       const V* sop = s_ops + i * D * D + zero;
-      for (int q = tid; q < nf; q += kMuThreads) {
-        const int hi = q / st, lo = q - hi * st;
-        V* x0 = tile + hi * st * D + lo;
-        V x[D];
+      for (int q0 = tid * F; q0 < nf; q0 += nthr * F) {
+        V* x0[F];
+        V x[F][D];
+        bool live[F];
 #pragma unroll
-        for (int b = 0; b < D; ++b) x[b] = x0[b * st];
+        for (int f = 0; f < F; ++f) {
+          live[f] = q0 + f < nf;                 // ragged tail: idle slots touch nothing
+          const int q = live[f] ? q0 + f : q0;
+          const int hi = (int)__umulhi((uint32_t)q, g.inv_st[i]), lo = q - hi * st;
+          x0[f] = tile + hi * st * D + lo;
+#pragma unroll
+          for (int b = 0; b < D; ++b) x[f][b] = x0[f][b * st];
+        }
 #pragma unroll
         for (int a = 0; a < D; ++a) {
-          V acc = czero<V>();
+          V acc[F];
 #pragma unroll
-          for (int b = 0; b < D; ++b) cfma(acc, sop[a * D + b], x[b]);
-          x0[a * st] = acc;
+          for (int f = 0; f < F; ++f) acc[f] = czero<V>();
+#pragma unroll
+          for (int b = 0; b < D; ++b) {
+            const V o = sop[a * D + b];
+#pragma unroll
+            for (int f = 0; f < F; ++f) cfma(acc[f], o, x[f][b]);
+          }
+#pragma unroll
+          for (int f = 0; f < F; ++f)
+            if (f == 0 || live[f]) x0[f][a * st] = acc[f];
         }
       }
       __syncthreads();
     }
-    V* dst = out + fm.base(u * (uint64_t)g.C);
-    for (int e = tid; e < g.tile; e += kMuThreads) {
+    V* dst = out + base;
+    for (int e = tid; e < g.tile; e += nthr) {
       int j, c;
-      if (g.j_fastest) { c = e / g.t; j = e - c * g.t; } else { j = e / g.C; c = e - j * g.C; }
+      split(e, j, c);
       __stcg(dst + s_off[j] + (int64_t)c * g.cstride, tile[j * g.C + c]);
     }
     __syncthreads();
-    cur ^= 1;
   }
-  mu_wait<0>();
+}
+
+template <typename V, int D, int F>
+static int launch_multi_f(const V* in, V* out, const Plan& p, const MultiGeom& g, cudaStream_t s) {
+  const size_t smem = sizeof(V) * (size_t)((g.nops * D * D + 1) & ~1) + sizeof(int64_t) * (size_t)((g.t + 1) & ~1) +
+                      sizeof(V) * (size_t)g.tile;
+  if (smem > 100 * 1024) return PW_ERR_UNSUPPORTED;
+  static bool attr = false;
+  if (!attr) {
+    PW_CUDA(cudaFuncSetAttribute(k_apply_multi<V, D, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr = true;
+  }
+  const int nf = g.tile / D;
+  int threads = (((nf + F - 1) / F + 31) / 32) * 32;
+  const int tmax = mu_threads(F);
+  if (threads > tmax) threads = tmax;
+  if (threads < 32) threads = 32;
+  int ctas = (int)((220 * 1024) / (smem + 1024));   // resident CTAs per SM by shared memory
+  const int cmax = mu_ctas(F);
+  if (ctas > cmax) ctas = cmax;
+  if (ctas < 1) ctas = 1;
+  uint64_t grid = (uint64_t)kNumSMs * ctas;
+  if (grid > g.units) grid = g.units;
+  k_apply_multi<V, D, F><<<(unsigned)grid, threads, smem, s>>>(in, out, p.fm, p.tm, g);
+  PW_LAUNCHED();
+  return PW_OK;
 }
 
 template <typename V, int D>
 static int launch_multi_d(const V* in, V* out, const Plan& p, const MultiGeom& g, cudaStream_t s) {
-  const size_t smem = sizeof(V) * (size_t)((g.nops * D * D + 1) & ~1) + sizeof(int64_t) * (size_t)((g.t + 1) & ~1) +
-                      sizeof(V) * (size_t)2 * g.tile;
-  if (smem > 110 * 1024) return PW_ERR_UNSUPPORTED;
-  static bool attr = false;
-  if (!attr) {
-    PW_CUDA(cudaFuncSetAttribute(k_apply_multi<V, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-    attr = true;
+  // fibers per thread: 3 (24 regs of state per fiber in complex128) unless the operators are
+  // large; knob "multi_f" overrides (1..4)
+  int F = options().multi_f.load(std::memory_order_relaxed);
+  if (F <= 0) F = D <= 6 ? 3 : 2;
+  switch (F) {
+    case 1: return launch_multi_f<V, D, 1>(in, out, p, g, s);
+    case 2: return launch_multi_f<V, D, 2>(in, out, p, g, s);
+    case 3: return launch_multi_f<V, D, 3>(in, out, p, g, s);
+    default: return launch_multi_f<V, D, 4>(in, out, p, g, s);
   }
-  uint64_t grid = (uint64_t)kNumSMs * 2;
-  if (grid > g.units) grid = g.units;
-  k_apply_multi<V, D><<<(unsigned)grid, kMuThreads, smem, s>>>(in, out, p.fm, p.tm, g);
-  PW_LAUNCHED();
-  return PW_OK;
 }
 
 template <typename V>
@@ -205,6 +247,14 @@ extern "C" int pw_apply_vec_multi(const void* psi, void* out, const void* const*
   g.units = p.fm.nfib / (uint64_t)C;
   int st = C;
   for (int i = nops - 1; i >= 0; --i) { g.st[i] = st; st *= (int)d; }
+  auto recip = [](int x) { return (uint32_t)((0x100000000ull + (uint64_t)x - 1) / (uint64_t)x); };
+  if (g.tile >= (1 << 16)) return PW_ERR_UNSUPPORTED;
+  g.inv_c = recip(C);
+  g.inv_t = recip(g.t);
+  for (int i = 0; i < nops; ++i) g.inv_st[i] = recip(g.st[i]);
+  g.logC = -1;
+  for (int l = 0; l < 16; ++l)
+    if ((1 << l) == C) g.logC = l;
   if (dtype == PW_C128)
     return launch_multi_t<double2>((const double2*)psi, (double2*)out, p, g, (int)d, (cudaStream_t)stream);
   return launch_multi_t<float2>((const float2*)psi, (float2*)out, p, g, (int)d, (cudaStream_t)stream);

@@ -826,6 +826,10 @@ def test_fused_multi_operator_tile_kernel(ad, dims, axes, cdtype):
         ref = oad.apply_operation_vector(dims, (a,), ref, u.astype(np.complex128))
     d_psi = dev(psi).reshape(-1)
     out = ffi.apply_vec_multi(d_psi, [dev(u) for u in us], dims, axes)
+    if dims == (6, 6, 6, 6, 6) and axes == (0, 1, 2, 3):
+        # 6^4 joint indices leave no room for a 64-byte contiguous row per 28 KB tile
+        assert out is None
+        return
     assert out is not None, "shape should be supported"
     assert rel_err(host(out).reshape(-1, 1), ref) < TOL[cdtype]
     same = ffi.apply_vec_multi(d_psi, [dev(u) for u in us], dims, axes, out=d_psi)
