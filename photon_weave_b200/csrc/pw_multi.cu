@@ -104,7 +104,7 @@ k_apply_multi(const V* in, V* out, const FiberMap fm, const TargetMap tm, const 
         for (int f = 0; f < F; ++f) {
           live[f] = q0 + f < nf;                 // ragged tail: idle slots touch nothing
           const int q = live[f] ? q0 + f : q0;
-          const int hi = (int)__umulhi((uint32_t)q, g.inv_st[i]), lo = q - hi * st;
+          const int hi = st == 1 ? q : (int)__umulhi((uint32_t)q, g.inv_st[i]), lo = q - hi * st;  // (2^32 / 1 overflows)
           x0[f] = tile + hi * st * D + lo;
 #pragma unroll
           for (int b = 0; b < D; ++b) x[f][b] = x0[f][b * st];
