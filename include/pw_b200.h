@@ -286,7 +286,10 @@ int pw_gather_chunks(const void* const* srcs, int W, int64_t chunk_elems, int ra
 /* The same swap FUSED with the operator application that follows it: the input of
  * pw_apply_vec is the virtual concatenation of the W peer chunks (dims describe that
  * concatenated tensor, prod(dims) = W * chunk_elems), loads go over NVLink, the result
- * is written once to local memory.  Covers t <= 8 (PW_ERR_UNSUPPORTED otherwise). */
+ * is written once to local memory.  Covers t <= 8 and, for 8 < t <= 128, BLOCK-STRUCTURED
+ * operators (beam splitters, two-mode phases: the device-side structure analysis of
+ * pw_apply_vec; its verdict is read back, so this one entry point synchronises the stream);
+ * PW_ERR_UNSUPPORTED otherwise (dense t > 8: gather, then pw_apply_vec). */
 int pw_apply_vec_gather(const void* const* srcs, int W, int64_t chunk_elems, int rank, void* out,
                         const void* op, const int64_t* dims, int n, const int32_t* targets,
                         int nt, int dtype, void* stream);

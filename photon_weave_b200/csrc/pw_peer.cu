@@ -9,6 +9,7 @@
 #include <cstring>
 
 #include "pw_internal.cuh"
+#include "pw_blocks.cuh"
 
 namespace pw {
 
@@ -103,6 +104,52 @@ static int apply_gather_t(const SegIn& s, V* out, const V* op, const Plan& p, in
   return PW_OK;
 }
 
+// Block-structured operators (8 < t <= 128: beam splitters, two-mode phases) with the same
+// gathered input: k_apply_blocks whose loads go through the peer pointers.  One fiber per thread,
+// every block gathered into registers, the result written once to local memory.
+template <typename V>
+__global__ void __launch_bounds__(256, 3)
+k_apply_blocks_gather(const SegIn s, V* __restrict__ out, const FiberMap fm, const BlockArrays A,
+                      const bool small, const uint64_t rot) {
+  extern __shared__ __align__(16) unsigned char s_desc[];
+  const DescView<V> dv = desc_view<V>(A, s_desc, 24 * 1024);
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < fm.nfib; i += stride) {
+    uint64_t f = i + rot;
+    if (f >= fm.nfib) f -= fm.nfib;
+    const int64_t base = fm.base(f);
+    V* dst = out + base;
+    for (int b = 0; b < dv.nblocks; ++b) {
+      const int4 h = dv.blocks[b];
+      const int64_t* bo = dv.offs + h.z;
+      block_product<V>(dv.vals + h.w, h.x, h.y,
+                       [&](int j) { return *seg_addr<V>(s, (uint64_t)(base + bo[j]), small); },
+                       [&](int a, V v) { __stcg(dst + bo[h.y + a], v); });
+    }
+    for (int z = 0; z < dv.nzero; ++z) __stcg(dst + dv.zero_offs[z], czero<V>());
+  }
+}
+
+template <typename V>
+static int apply_gather_blocks_t(const SegIn& s, V* out, const void* op, const Plan& p, int dtype, int rank,
+                                 int W, cudaStream_t st) {
+  Scratch mem;
+  BlockArrays arr;
+  PW_TRY(build_block_desc(op, p.tm.t, false, p.tm, dtype, &mem, &arr, st));
+  // the structure analysis runs on the device; this entry point reads its verdict back (one
+  // 32-byte copy + stream synchronisation) because the caller needs to know whether to fall
+  // back to gather + apply -- the only libpwb200 device entry point that synchronises
+  BlockDescHeader h;
+  PW_CUDA(cudaMemcpyAsync(&h, arr.hdr, sizeof(h), cudaMemcpyDeviceToHost, st));
+  PW_CUDA(cudaStreamSynchronize(st));
+  if (!h.usable) return PW_ERR_UNSUPPORTED;
+  const uint64_t rot = (p.fm.nfib / (uint64_t)W) * (uint64_t)(rank % W);
+  k_apply_blocks_gather<V><<<grid_for(p.fm.nfib, 256, 3), 256, 24 * 1024, st>>>(s, out, p.fm, arr,
+                                                                              p.N <= 0xffffffffull, rot);
+  PW_LAUNCHED();
+  return PW_OK;
+}
+
 }  // namespace pw
 
 using namespace pw;
@@ -178,7 +225,15 @@ extern "C" int pw_apply_vec_gather(const void* const* srcs, int W, int64_t chunk
   Plan p;
   PW_TRY(build_plan(dims, n, targets, nt, &p));
   if (p.N != (uint64_t)chunk_elems * (uint64_t)W) return PW_ERR_INVALID;
-  if (dtype == PW_C128) return apply_gather_t<double2>(s, (double2*)out, (const double2*)op, p, rank < 0 ? 0 : rank, W, (cudaStream_t)stream);
-  if (dtype == PW_C64) return apply_gather_t<float2>(s, (float2*)out, (const float2*)op, p, rank < 0 ? 0 : rank, W, (cudaStream_t)stream);
+  const int r = rank < 0 ? 0 : rank;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p.tm.t > 8) {  // block-structured operators up to 128 x 128 (dense ones: PW_ERR_UNSUPPORTED)
+    if (p.tm.t > kBlockMaxT) return PW_ERR_UNSUPPORTED;
+    if (dtype == PW_C128) return apply_gather_blocks_t<double2>(s, (double2*)out, op, p, dtype, r, W, st);
+    if (dtype == PW_C64) return apply_gather_blocks_t<float2>(s, (float2*)out, op, p, dtype, r, W, st);
+    return PW_ERR_INVALID;
+  }
+  if (dtype == PW_C128) return apply_gather_t<double2>(s, (double2*)out, (const double2*)op, p, r, W, st);
+  if (dtype == PW_C64) return apply_gather_t<float2>(s, (float2*)out, (const float2*)op, p, r, W, st);
   return PW_ERR_INVALID;
 }

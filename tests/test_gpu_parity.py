@@ -404,7 +404,14 @@ def test_gather_kernels_single_process_emulation(ad):
         assert ok
         ref = oad.apply_operation_vector(dims, targets, psi.reshape(-1, 1), op)
         assert rel_err(host(out).reshape(-1, 1), ref) < 1e-12
+    # dense t > 8: not covered (gather, then apply); block-structured t > 8: fused
     assert be.apply_vec_gather(srcs, chunk, out, dev(ops.random_unitary(12, 1)), dims, (0, 1)) is False
+    for targets, op in [((2, 3), ops.beam_splitter(6, 5, 0.7)), ((3, 2), ops.beam_splitter(5, 6, 0.3)),
+                        ((0, 2), np.kron(ops.phase_operator(4, 0.3), ops.phase_operator(6, 1.1))),
+                        ((0, 3), ops.beam_splitter(4, 5, 0.9))]:
+        assert be.apply_vec_gather(srcs, chunk, out, dev(op), dims, targets, rank=1)
+        ref = oad.apply_operation_vector(dims, targets, psi.reshape(-1, 1), op)
+        assert rel_err(host(out).reshape(-1, 1), ref) < 1e-12, targets
 
 
 @pytest.mark.parametrize("cdtype", [np.complex128, np.complex64])
