@@ -62,6 +62,7 @@ Options& options() {
     env("PW_TWO_SIDED", p->two_sided);
     env("PW_TS_CTAS", p->ts_ctas);
     env("PW_TS_MMA", p->ts_mma);
+    env("PW_TS_MMA_C64", p->ts_mma_c64);
     env("PW_DRAW_EXACT", p->draw_exact);
     env("PW_FUSE_GROUP", p->fuse_group);
     env("PW_MULTI_F", p->multi_f);
@@ -96,6 +97,7 @@ extern "C" int pw_set_option(const char* name, int value) {
   else if (!std::strcmp(name, "two_sided")) o.two_sided.store(value);
   else if (!std::strcmp(name, "ts_ctas")) o.ts_ctas.store(value);
   else if (!std::strcmp(name, "ts_mma")) o.ts_mma.store(value);
+  else if (!std::strcmp(name, "ts_mma_c64")) o.ts_mma_c64.store(value);
   else if (!std::strcmp(name, "draw_exact")) o.draw_exact.store(value);
   else if (!std::strcmp(name, "fuse_group")) o.fuse_group.store(value);
   else if (!std::strcmp(name, "multi_f")) o.multi_f.store(value);

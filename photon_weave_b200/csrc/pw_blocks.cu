@@ -633,7 +633,7 @@ k_ts_build(const BlockArrays L, const BlockArrays R, const int* __restrict__ oth
     //  5..8-level column target with whole chunks of 32 fibers next to it -> 32-fiber tiles)
     if (inner) {
       if (mma && hl->nblocks == 1 && (inner & 2)) mma = 1;
-      else if (mma && nsb <= kTwMaxSb && hr->inplace_safe) mma = 2;
+      else if (mma && mma_ok >= 2 && nsb <= kTwMaxSb && hr->inplace_safe) mma = 2;  // (row tiles: complex128 only)
       else h = 0;
     }
     if (!h) mma = 0;
@@ -894,13 +894,37 @@ __device__ __forceinline__ int ts_sigma(const int f, const int a) {
   return ((f & 1) << 2) ^ (f & 6) ^ (a & 3);
 }
 
-template <bool MULTI, bool INNER>
-__device__ __forceinline__ void two_sided_mma_body(const double2* __restrict__ in, double2* __restrict__ out,
+// Storage type S of the state (double2, or float2 for complex64): the arithmetic is always the FP64
+// tensor-core product; complex64 values are widened when a fragment is read from the tile and
+// rounded when a result is written back (the tile and the intermediate U rho live in float2, like
+// every intermediate of the reference's complex64 path), so the kernel moves half the bytes with
+// the same DMMA count -- complex64 leaves the FMA pipe (33-42 % of the HBM roof) for this path.
+__device__ __forceinline__ double2 ts_ld(const double2* p) { return *p; }
+__device__ __forceinline__ double2 ts_ld(const float2* p) { const float2 v = *p; return make_double2((double)v.x, (double)v.y); }
+__device__ __forceinline__ double2 ts_ldg(const double2* p) { return __ldg(p); }
+__device__ __forceinline__ double2 ts_ldg(const float2* p) { const float2 v = __ldg(p); return make_double2((double)v.x, (double)v.y); }
+__device__ __forceinline__ void ts_st(double2* p, const double2 v) { *p = v; }
+__device__ __forceinline__ void ts_st(float2* p, const double2 v) { *p = make_float2((float)v.x, (float)v.y); }
+__device__ __forceinline__ void ts_cp(double2* smem_dst, const double2* gsrc) { cp_async16(smem_dst, gsrc); }
+__device__ __forceinline__ void ts_cp(float2* smem_dst, const float2* gsrc) { cp_async8(smem_dst, gsrc); }
+__device__ __forceinline__ void st_pair(float2* p0, float2* p1, const double2 v0, const double2 v1,
+                                        const bool ok0, const bool ok1) {
+  const float2 f0 = make_float2((float)v0.x, (float)v0.y), f1 = make_float2((float)v1.x, (float)v1.y);
+  if (ok0 && ok1 && p1 == p0 + 1 && (reinterpret_cast<uintptr_t>(p0) & 15) == 0) {
+    __stcg(reinterpret_cast<float4*>(p0), make_float4(f0.x, f0.y, f1.x, f1.y));
+  } else {
+    if (ok0) __stcg(p0, f0);
+    if (ok1) __stcg(p1, f1);
+  }
+}
+
+template <bool MULTI, bool INNER, typename S>
+__device__ __forceinline__ void two_sided_mma_body(const S* __restrict__ in, S* __restrict__ out,
                                                    const FiberMap& fm, const TsTables& T,
                                                    unsigned char* s_raw, const int order) {
   using V = double2;
   constexpr bool inner = INNER;
-  V* tile0 = (V*)s_raw;                                          // [3][kTsSlots][32], swizzled
+  S* tile0 = (S*)s_raw;                                          // [3][kTsSlots][32], swizzled
   int64_t* s_base = (int64_t*)(tile0 + 3 * kTsSlots * 32);       // [3][32] fiber bases (-1: past the end)
   int64_t* s_off = s_base + 3 * 32;                              // [4][kTsMaxSb][8]
   int* s_n = (int*)(s_off + 4 * kTsMaxSb * 8);                   // [kTsMaxSb]
@@ -916,7 +940,7 @@ __device__ __forceinline__ void two_sided_mma_body(const double2* __restrict__ i
   const int gid = lane >> 2, tig = lane & 3;
   const uint64_t chunks = (fm.nfib + 31) / 32;
   const uint64_t units = chunks * nsb * nsb;
-  const V* wtab = (const V*)T.sb_w;
+  const S* wtab = (const S*)T.sb_w;
 
   // chunk index fastest: CTAs that run side by side work on adjacent memory
   // (32-bit arithmetic: the host guarantees units < 2^32)
@@ -943,7 +967,7 @@ __device__ __forceinline__ void two_sided_mma_body(const double2* __restrict__ i
       uint64_t c;
       decode(u, K, L, c);
       const int nK = s_n[K], nL = s_n[L];
-      V* tile = tile0 + (size_t)buf * kTsSlots * 32;
+      S* tile = tile0 + (size_t)buf * kTsSlots * 32;
       if (!inner) {
         const uint64_t f = c * 32 + lane;
         const int64_t base = f < fm.nfib ? fm.base(f) : -1;
@@ -953,15 +977,15 @@ __device__ __forceinline__ void two_sided_mma_body(const double2* __restrict__ i
           const int64_t* co = cin + L * 8;
           if (nL == kTsWarps) {
             // full super-block: warp w copies column w of every row
-            const V* src = in + base + co[warp];
-            V* dst = tile + warp * 32;
+            const S* src = in + base + co[warp];
+            S* dst = tile + warp * 32;
             for (int a = 0; a < nK; ++a)
-              cp_async16(dst + a * (kTsWarps * 32) + (lane ^ (2 * (a & 3))), src + ro[a]);
+              ts_cp(dst + a * (kTsWarps * 32) + (lane ^ (2 * (a & 3))), src + ro[a]);
           } else {
             int a = 0, b = warp;
             while (b >= nL) { b -= nL; ++a; }
             for (; a < nK;) {
-              cp_async16(tile + (a * nL + b) * 32 + (lane ^ (2 * (a & 3))), in + base + ro[a] + co[b]);
+              ts_cp(tile + (a * nL + b) * 32 + (lane ^ (2 * (a & 3))), in + base + ro[a] + co[b]);
               b += kTsWarps;
               while (b >= nL) { b -= nL; ++a; }
             }
@@ -974,12 +998,12 @@ __device__ __forceinline__ void two_sided_mma_body(const double2* __restrict__ i
         const int nvalid = left < 32 ? (int)left : 32;
         if (warp == 0) s_base[buf * 32 + lane] = lane < nvalid ? base0 + (int64_t)lane * nL : -1;
         for (int a = warp; a < nK; a += kTsWarps) {
-          const V* src = in + base0 + rin[a];
-          V* dst = tile + a * 256;
+          const S* src = in + base0 + rin[a];
+          S* dst = tile + a * 256;
           int f = lane / nL, b = lane - f * nL;
           const int qa = 32 / nL, rb = 32 - qa * nL;
           for (int e = lane; e < nvalid * nL; e += 32) {
-            cp_async16(dst + f * 8 + (b ^ ts_sigma(f, a)), src + e);
+            ts_cp(dst + f * 8 + (b ^ ts_sigma(f, a)), src + e);
             f += qa; b += rb;
             if (b >= nL) { b -= nL; ++f; }
           }
@@ -1019,31 +1043,31 @@ __device__ __forceinline__ void two_sided_mma_body(const double2* __restrict__ i
   issue(u, 0);
   issue(u + gridDim.x, 1);
   // operand fragments (zero padded to 8 x 8): per unit, or once for a single super-block
-  V l0 = __ldg(wtab + gid * 8 + tig), l1 = __ldg(wtab + gid * 8 + 4 + tig);
-  V r0 = __ldg(wtab + kTsMaxSb * 64 + gid * 8 + tig), r1 = __ldg(wtab + kTsMaxSb * 64 + gid * 8 + 4 + tig);
+  V l0 = ts_ldg(wtab + gid * 8 + tig), l1 = ts_ldg(wtab + gid * 8 + 4 + tig);
+  V r0 = ts_ldg(wtab + kTsMaxSb * 64 + gid * 8 + tig), r1 = ts_ldg(wtab + kTsMaxSb * 64 + gid * 8 + 4 + tig);
   for (; u < units; u += gridDim.x) {
-    V* tile = tile0 + (size_t)cur * kTsSlots * 32;
+    S* tile = tile0 + (size_t)cur * kTsSlots * 32;
     uint32_t K, L;
     uint64_t c;
     decode(u, K, L, c);
     const int nK = s_n[K], nL = s_n[L];
     if (MULTI) {
-      const V* wl = wtab + (size_t)K * 64 + gid * 8 + tig;
-      const V* wr = wtab + (size_t)(kTsMaxSb + L) * 64 + gid * 8 + tig;
-      l0 = __ldg(wl); l1 = __ldg(wl + 4); r0 = __ldg(wr); r1 = __ldg(wr + 4);
+      const S* wl = wtab + (size_t)K * 64 + gid * 8 + tig;
+      const S* wr = wtab + (size_t)(kTsMaxSb + L) * 64 + gid * 8 + tig;
+      l0 = ts_ldg(wl); l1 = ts_ldg(wl + 4); r0 = ts_ldg(wr); r1 = ts_ldg(wr + 4);
     }
     cp_async_wait<1>();
     __syncthreads();
     issue(u + 2 * (uint64_t)gridDim.x, cur == 0 ? 2 : cur - 1);  // the buffer of the previous tile
     // stage 1: column j of the tile, in place
     for (int j = warp; j < nL; j += kTsWarps) {
-      V* col = tile + j * 32;
+      S* col = tile + j * 32;
       V y0[4], y1[4];
       if (inner)
-        product(l0, l1, nK, [&](int a, int f) { return tile[a * 256 + f * 8 + (j ^ ts_sigma(f, a))]; },
+        product(l0, l1, nK, [&](int a, int f) { return ts_ld(tile + a * 256 + f * 8 + (j ^ ts_sigma(f, a))); },
                 [&](int nt, int f, V v0, V v1) { y0[nt] = v0; y1[nt] = v1; (void)f; });
       else
-        product(l0, l1, nK, [&](int a, int f) { return col[a * nL * 32 + (f ^ (2 * (a & 3)))]; },
+        product(l0, l1, nK, [&](int a, int f) { return ts_ld(col + a * nL * 32 + (f ^ (2 * (a & 3)))); },
                 [&](int nt, int f, V v0, V v1) { y0[nt] = v0; y1[nt] = v1; (void)f; });
       __syncwarp();  // every lane has read its inputs before the column is overwritten
       if (inner) {
@@ -1051,18 +1075,18 @@ __device__ __forceinline__ void two_sided_mma_body(const double2* __restrict__ i
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt) {
             const int f = 8 * nt + 2 * tig;
-            tile[gid * 256 + f * 8 + (j ^ ts_sigma(f, gid))] = y0[nt];
-            tile[gid * 256 + (f + 1) * 8 + (j ^ ts_sigma(f + 1, gid))] = y1[nt];
+            ts_st(tile + gid * 256 + f * 8 + (j ^ ts_sigma(f, gid)), y0[nt]);
+            ts_st(tile + gid * 256 + (f + 1) * 8 + (j ^ ts_sigma(f + 1, gid)), y1[nt]);
           }
         }
       } else if (gid < nK) {
-        V* dst = col + gid * nL * 32;
+        S* dst = col + gid * nL * 32;
         const int sw = (2 * (j & 3)) ^ (gid & 1);
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           const int f = 8 * nt + 2 * tig;
-          dst[f ^ sw] = y0[nt];
-          dst[(f + 1) ^ sw] = y1[nt];
+          ts_st(dst + (f ^ sw), y0[nt]);
+          ts_st(dst + ((f + 1) ^ sw), y1[nt]);
         }
       }
     }
@@ -1079,8 +1103,8 @@ __device__ __forceinline__ void two_sided_mma_body(const double2* __restrict__ i
         for (int nt = 0; nt < 4; ++nt) {
           const int f = 8 * nt + gid;
           V x0 = make_double2(0.0, 0.0), x1 = x0;
-          if (tig < nL) x0 = tile[i * 256 + f * 8 + (tig ^ ts_sigma(f, i))];
-          if (4 + tig < nL) x1 = tile[i * 256 + f * 8 + ((4 + tig) ^ ts_sigma(f, i))];
+          if (tig < nL) x0 = ts_ld(tile + i * 256 + f * 8 + (tig ^ ts_sigma(f, i)));
+          if (4 + tig < nL) x1 = ts_ld(tile + i * 256 + f * 8 + ((4 + tig) ^ ts_sigma(f, i)));
           double re0 = 0.0, re1 = 0.0, im0 = 0.0, im1 = 0.0;
           dmma8x8x4(re0, re1, x0.x, r0.x);
           dmma8x8x4(im0, im1, x0.x, r0.y);
@@ -1091,19 +1115,19 @@ __device__ __forceinline__ void two_sided_mma_body(const double2* __restrict__ i
           dmma8x8x4(re0, re1, -x1.y, r1.y);
           dmma8x8x4(im0, im1, x1.y, r1.x);
           const int64_t b0 = sb[f];
-          V* dst = out + b0 + ro;
+          S* dst = out + b0 + ro;
           st_pair(dst, dst + 1, make_double2(re0, im0), make_double2(re1, im1), b0 >= 0 && 2 * tig < nL,
                   b0 >= 0 && 2 * tig + 1 < nL);
         }
       }
     } else
     for (int i = warp; i < nK; i += kTsWarps) {
-      const V* row = tile + i * nL * 32;
+      const S* row = tile + i * nL * 32;
       const int64_t ro = rout[K * 8 + i] + cout[L * 8 + gid];
       product(r0, r1, nL,
               [&](int b, int f) {
-                return inner ? tile[i * 256 + f * 8 + (b ^ ts_sigma(f, i))]
-                             : row[b * 32 + (f ^ (2 * (b & 3)) ^ (i & 1))];
+                return inner ? ts_ld(tile + i * 256 + f * 8 + (b ^ ts_sigma(f, i)))
+                             : ts_ld(row + b * 32 + (f ^ (2 * (b & 3)) ^ (i & 1)));
               },
               [&](int nt, int f, V v0, V v1) {
                 (void)nt;
@@ -1118,14 +1142,15 @@ __device__ __forceinline__ void two_sided_mma_body(const double2* __restrict__ i
   cp_async_wait<0>();
 }
 
+template <typename S>
 __global__ void __launch_bounds__(kTsWarps * 32, 2)
-k_two_sided_mma(const double2* __restrict__ in, double2* __restrict__ out, const FiberMap fm,
+k_two_sided_mma(const S* __restrict__ in, S* __restrict__ out, const FiberMap fm,
                 const TsTables T, const int inner, const int order) {
   if (!T.flags->handled || T.flags->use_mma != 1) return;
   extern __shared__ __align__(16) unsigned char s_raw[];
-  if (inner) two_sided_mma_body<false, true>(in, out, fm, T, s_raw, 0);
-  else if (T.flags->nsb == 1) two_sided_mma_body<false, false>(in, out, fm, T, s_raw, 0);
-  else two_sided_mma_body<true, false>(in, out, fm, T, s_raw, order);
+  if (inner) two_sided_mma_body<false, true, S>(in, out, fm, T, s_raw, 0);
+  else if (T.flags->nsb == 1) two_sided_mma_body<false, false, S>(in, out, fm, T, s_raw, 0);
+  else two_sided_mma_body<true, false, S>(in, out, fm, T, s_raw, order);
 }
 
 
@@ -1368,9 +1393,13 @@ static int launch_two_sided_t(const V* rho, V* out, const V* op, const FiberMap&
   T.sb_off = (int64_t*)(sbb + b_sbn + b_sbblk);
   T.sb_w = sbb + b_sbn + b_sbblk + b_sboff;
   // (the tensor-core kernels index their units with 32 bits)
-  const bool mma_ok = sizeof(V) == 16 && options().ts_mma.load(std::memory_order_relaxed) && fm.nfib < (1ull << 28);
+  // complex64: the same FP64 tensor-core kernel with float2 storage (values widened per fragment);
+  // the row-tile variant exists for complex128 only
+  const bool c128 = sizeof(V) == 16;
+  const bool mma_ok = options().ts_mma.load(std::memory_order_relaxed) && fm.nfib < (1ull << 28) &&
+                      (c128 || options().ts_mma_c64.load(std::memory_order_relaxed));
   if (inner && !mma_ok) return PW_ERR_UNSUPPORTED;
-  k_ts_build<V><<<1, 256, 0, s>>>(ts->L, ts->R, other, T, kTsValCap, mma_ok ? 1 : 0, inner);
+  k_ts_build<V><<<1, 256, 0, s>>>(ts->L, ts->R, other, T, kTsValCap, mma_ok ? (c128 ? 2 : 1) : 0, inner);
   PW_LAUNCHED();
   const size_t smem = 2 * kTsValCap + sizeof(V) * 2 * kTsSlots * 32;
   static bool attr_set = false;
@@ -1383,19 +1412,24 @@ static int launch_two_sided_t(const V* rho, V* out, const V* op, const FiberMap&
   }
   const int per_sm = options().ts_ctas.load(std::memory_order_relaxed);
   const int grid = kNumSMs * (per_sm > 0 ? per_sm : 2);
-  k_two_sided<V><<<grid, kTsWarps * 32, smem, s>>>(rho, out, fm, ts->L, ts->R, T);
+  if (!inner) k_two_sided<V><<<grid, kTsWarps * 32, smem, s>>>(rho, out, fm, ts->L, ts->R, T);
   if (mma_ok) {
-    PW_LAUNCHED();
+    if (!inner) PW_LAUNCHED();
     static bool attr_mma = false;
-    const size_t smem_mma = sizeof(double2) * 3 * kTsSlots * 32 + (3 * 32 + 4 * kTsMaxSb * 8) * sizeof(int64_t) +
+    const size_t smem_mma = sizeof(V) * 3 * kTsSlots * 32 + (3 * 32 + 4 * kTsMaxSb * 8) * sizeof(int64_t) +
                             kTsMaxSb * sizeof(int);
     if (!attr_mma) {
-      PW_CUDA(cudaFuncSetAttribute(k_two_sided_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma));
+      PW_CUDA(cudaFuncSetAttribute(k_two_sided_mma<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(sizeof(double2) * 3 * kTsSlots * 32 + (3 * 32 + 4 * kTsMaxSb * 8) * sizeof(int64_t) +
+                                         kTsMaxSb * sizeof(int))));
+      PW_CUDA(cudaFuncSetAttribute(k_two_sided_mma<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(sizeof(float2) * 3 * kTsSlots * 32 + (3 * 32 + 4 * kTsMaxSb * 8) * sizeof(int64_t) +
+                                         kTsMaxSb * sizeof(int))));
       attr_mma = true;
     }
-    k_two_sided_mma<<<grid, kTsWarps * 32, smem_mma, s>>>((const double2*)rho, (double2*)out, fm, T, inner ? 1 : 0,
-                                                            options().ts_order.load(std::memory_order_relaxed));
-    if (inner) {
+    k_two_sided_mma<V><<<grid, kTsWarps * 32, smem_mma, s>>>(rho, out, fm, T, inner ? 1 : 0,
+                                                          options().ts_order.load(std::memory_order_relaxed));
+    if (inner && c128) {
       PW_LAUNCHED();
       static bool attr_rows = false;
       const size_t smem_rows = sizeof(double2) * (kTnBufs * 8 * kTnRow + kTwMaxSb * 64) +

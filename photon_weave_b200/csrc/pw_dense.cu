@@ -49,16 +49,38 @@ __device__ __forceinline__ void st_pair(double2* p0, double2* p1, const double2 
     if (ok1) __stcg(p1, v1);
   }
 }
+__device__ __forceinline__ void cp8(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+// storage type S (double2 | float2 for complex64): the tile keeps S, fragments are widened to FP64
+// when read, accumulators rounded when stored -- same DMMA count, half the bytes
+__device__ __forceinline__ void cp_elem(double2* d, const double2* g) { cp16(d, g); }
+__device__ __forceinline__ void cp_elem(float2* d, const float2* g) { cp8(d, g); }
+__device__ __forceinline__ double2 wide(const double2 v) { return v; }
+__device__ __forceinline__ double2 wide(const float2 v) { return make_double2((double)v.x, (double)v.y); }
+__device__ __forceinline__ void st_pair(float2* p0, float2* p1, const double2 v0, const double2 v1,
+                                        const bool ok0, const bool ok1) {
+  const float2 f0 = make_float2((float)v0.x, (float)v0.y), f1 = make_float2((float)v1.x, (float)v1.y);
+  if (ok0 && ok1 && p1 == p0 + 1 && (reinterpret_cast<uintptr_t>(p0) & 15) == 0) {
+    __stcg(reinterpret_cast<float4*>(p0), make_float4(f0.x, f0.y, f1.x, f1.y));
+  } else {
+    if (ok0) __stcg(p0, f0);
+    if (ok1) __stcg(p1, f1);
+  }
+}
+__device__ __forceinline__ void st_one(double2* p, const double2 v) { __stcg(p, v); }
+__device__ __forceinline__ void st_one(float2* p, const double2 v) { __stcg(p, make_float2((float)v.x, (float)v.y)); }
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // blockDim = 32 * nwarps; dynamic smem: W [8 nm][wp] | offs [t] | base [2][64] | tiles [2][t][64]
 // (INNER: tiles [2][64][tp]; base[buf][0..1] = first element of the tile, valid fibers)
-template <bool INNER>
+template <bool INNER, typename S>
 __global__ void __launch_bounds__(512, 1)
-k_apply_dense_mma(const double2* __restrict__ in, double2* __restrict__ out,
-                  const double2* __restrict__ op, const int conj_op, const FiberMap fm,
+k_apply_dense_mma(const S* __restrict__ in, S* __restrict__ out,
+                  const S* __restrict__ op, const int conj_op, const FiberMap fm,
                   const TargetMap tm, const int* __restrict__ skip) {
   using V = double2;
   if (skip != nullptr && *skip != 0) return;
@@ -70,7 +92,7 @@ k_apply_dense_mma(const double2* __restrict__ in, double2* __restrict__ out,
   V* s_w = (V*)s_raw;                                        // [8 nm][wp], column c at (c ^ 4 (row & 1))
   int64_t* s_off = (int64_t*)(s_w + 8 * nm * wp);            // [t]
   int64_t* s_base = s_off + ((t + 1) & ~1);                  // [2][kDmFib]
-  V* tile0 = (V*)(s_base + 2 * kDmFib);                      // [2][t][kDmFib], fiber f of row j at (f ^ 2 (j & 3))
+  S* tile0 = (S*)(s_base + 2 * kDmFib);                      // [2][t][kDmFib], fiber f of row j at (f ^ 2 (j & 3))
   int tp = t;                                                // INNER: fiber pitch, 4 mod 8
   while ((tp & 7) != 4) ++tp;
   const size_t tile_elems = INNER ? (size_t)kDmFib * tp : (size_t)t * kDmFib;
@@ -83,7 +105,7 @@ k_apply_dense_mma(const double2* __restrict__ in, double2* __restrict__ out,
     const int r = i / wp, c = i - r * wp;
     V v = make_double2(0.0, 0.0);
     if (r < t && c < t) {
-      v = op[(size_t)r * t + c];
+      v = wide(op[(size_t)r * t + c]);
       if (conj_op) v.y = -v.y;
     }
     s_w[r * wp + (c ^ ((r & 1) << 2))] = v;
@@ -95,31 +117,31 @@ k_apply_dense_mma(const double2* __restrict__ in, double2* __restrict__ out,
   auto issue = [&](uint64_t u, int buf) {
     if (INNER) {
       if (u < units) {
-        V* tile = tile0 + (size_t)buf * tile_elems;
+        S* tile = tile0 + (size_t)buf * tile_elems;
         const uint64_t o = u / cpr, w = u - o * cpr;
         const uint64_t f0 = w * kDmFib;
         const int nvalid = (gl - f0) < (uint64_t)kDmFib ? (int)(gl - f0) : kDmFib;
         const int64_t base0 = fm.base(o * gl + f0);
         if (threadIdx.x == 0) { s_base[buf * kDmFib] = base0; s_base[buf * kDmFib + 1] = nvalid; }
-        const V* src = in + base0;
+        const S* src = in + base0;
         for (int e = threadIdx.x; e < nvalid * t; e += blockDim.x) {
           const int f = (int)__umulhi((uint32_t)e, inv_t);
-          cp16(tile + f * tp + (e - f * t), src + e);
+          cp_elem(tile + f * tp + (e - f * t), src + e);
         }
       }
       cp_commit();
       return;
     }
     if (u < units) {
-      V* tile = tile0 + (size_t)buf * tile_elems;
+      S* tile = tile0 + (size_t)buf * tile_elems;
       const uint64_t fa = u * kDmFib + lane, fb = fa + 32;
       const int64_t ba = fa < fm.nfib ? fm.base(fa) : -1, bb = fb < fm.nfib ? fm.base(fb) : -1;
       if (warp == 0) { s_base[buf * kDmFib + lane] = ba; s_base[buf * kDmFib + 32 + lane] = bb; }
       for (int j = warp; j < t; j += nwarps) {
         const int sw = 2 * (j & 3);
         const int64_t o = s_off[j];
-        if (ba >= 0) cp16(tile + j * kDmFib + (lane ^ sw), in + ba + o);
-        if (bb >= 0) cp16(tile + j * kDmFib + 32 + (lane ^ sw), in + bb + o);
+        if (ba >= 0) cp_elem(tile + j * kDmFib + (lane ^ sw), in + ba + o);
+        if (bb >= 0) cp_elem(tile + j * kDmFib + 32 + (lane ^ sw), in + bb + o);
       }
     }
     cp_commit();
@@ -131,7 +153,7 @@ k_apply_dense_mma(const double2* __restrict__ in, double2* __restrict__ out,
   int cur = 0;
   issue(u, 0);
   for (; u < units; u += gridDim.x) {
-    const V* tile = tile0 + (size_t)cur * tile_elems;
+    const S* tile = tile0 + (size_t)cur * tile_elems;
     issue(u + gridDim.x, cur ^ 1);
     cp_wait<1>();
     __syncthreads();
@@ -145,7 +167,7 @@ k_apply_dense_mma(const double2* __restrict__ in, double2* __restrict__ out,
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[n][q] = 0.0;
       const V* wrow = s_w + row * wp;
-      const V* xcol = INNER ? tile + (32 * h + gid) * tp                 // + 8 n tp + position of j
+      const S* xcol = INNER ? tile + (32 * h + gid) * tp                 // + 8 n tp + position of j
                             : tile + 32 * h + (gid ^ (2 * tig));        // + j * 64 + 8 n   (j & 3 == tig)
 #pragma unroll 2
       for (int k = 0; k < ks; ++k) {
@@ -155,10 +177,10 @@ k_apply_dense_mma(const double2* __restrict__ in, double2* __restrict__ out,
         if (INNER) {
           const int pj = j < t ? (int)s_off[j] : 0;
 #pragma unroll
-          for (int n = 0; n < 4; ++n) x[n] = j < t ? xcol[8 * n * tp + pj] : make_double2(0.0, 0.0);
+          for (int n = 0; n < 4; ++n) x[n] = j < t ? wide(xcol[8 * n * tp + pj]) : make_double2(0.0, 0.0);
         } else {
 #pragma unroll
-          for (int n = 0; n < 4; ++n) x[n] = j < t ? xcol[j * kDmFib + 8 * n] : make_double2(0.0, 0.0);
+          for (int n = 0; n < 4; ++n) x[n] = j < t ? wide(xcol[j * kDmFib + 8 * n]) : make_double2(0.0, 0.0);
         }
         // step-major issue order: the eight accumulator chains advance together (a warp issues
         // in order; consecutive DMMAs must be independent to keep the tensor pipe busy)
@@ -174,12 +196,12 @@ k_apply_dense_mma(const double2* __restrict__ in, double2* __restrict__ out,
       if (INNER) {
         if (row < t) {
           const int nvalid = (int)sb[1];
-          V* dst = out + sb[0] + s_off[row];
+          S* dst = out + sb[0] + s_off[row];
 #pragma unroll
           for (int n = 0; n < 4; ++n) {
             const int f = 32 * h + 8 * n + 2 * tig;
-            if (f < nvalid) __stcg(dst + (int64_t)f * t, make_double2(acc[n][0], acc[n][2]));
-            if (f + 1 < nvalid) __stcg(dst + (int64_t)(f + 1) * t, make_double2(acc[n][1], acc[n][3]));
+            if (f < nvalid) st_one(dst + (int64_t)f * t, make_double2(acc[n][0], acc[n][2]));
+            if (f + 1 < nvalid) st_one(dst + (int64_t)(f + 1) * t, make_double2(acc[n][1], acc[n][3]));
           }
         }
       } else if (row < t) {
@@ -201,29 +223,20 @@ k_apply_dense_mma(const double2* __restrict__ in, double2* __restrict__ out,
 
 }  // namespace
 
-int launch_dense_mma(const void* in, void* out, const void* op, const Plan& p, int dtype, bool conj_op,
-                     cudaStream_t s, const int* skip) {
+template <typename S>
+static int launch_dense_mma_s(const S* in, S* out, const S* op, const Plan& p, bool conj_op, bool inner,
+                              cudaStream_t s, const int* skip) {
   const int t = (int)p.tm.t;
-  if (dtype != PW_C128 || in == out || t <= 8 || t > kDmMaxT || p.fm.ng == 0) return PW_ERR_UNSUPPORTED;
-  // fibers adjacent in memory (untouched innermost run), or the targets are the innermost run
-  bool inner = false;
-  if (p.fm.gstride[p.fm.ng - 1] != 1) {
-    inner = p.fm.gstride[p.fm.ng - 1] == (int64_t)t;
-    for (int k = 0; k < p.tm.nt && inner; ++k) inner = p.tm.tdim[k] == 1 || p.tm.tstride[k] < (int64_t)t;
-    if (!inner) return PW_ERR_UNSUPPORTED;
-  } else if (p.fm.gsize[p.fm.ng - 1] < 16) {
-    return PW_ERR_UNSUPPORTED;
-  }
   const int nm = (t + 7) >> 3, ks = (t + 3) >> 2, wp = (4 * ks + 7) & ~7;
   int tp = t;
   while ((tp & 7) != 4) ++tp;
   const size_t smem = sizeof(double2) * (size_t)(8 * nm * wp) + sizeof(int64_t) * (size_t)(((t + 1) & ~1) + 2 * kDmFib) +
-                      sizeof(double2) * (size_t)2 * (inner ? tp : t) * kDmFib;
+                      sizeof(S) * (size_t)2 * (inner ? tp : t) * kDmFib;
   if (smem > 220 * 1024) return PW_ERR_UNSUPPORTED;
   static bool attr_set = false;
   if (!attr_set) {
-    PW_CUDA(cudaFuncSetAttribute(k_apply_dense_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
-    PW_CUDA(cudaFuncSetAttribute(k_apply_dense_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+    PW_CUDA(cudaFuncSetAttribute(k_apply_dense_mma<false, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+    PW_CUDA(cudaFuncSetAttribute(k_apply_dense_mma<true, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
     attr_set = true;
   }
   // one warp per item (8 rows x 32 fibers); two CTAs per SM when the tiles allow it
@@ -235,13 +248,32 @@ int launch_dense_mma(const void* in, void* out, const void* op, const Plan& p, i
   uint64_t grid = (uint64_t)kNumSMs * ctas;
   if (grid > units) grid = units;
   if (inner)
-    k_apply_dense_mma<true><<<(unsigned)grid, nwarps * 32, smem, s>>>((const double2*)in, (double2*)out, (const double2*)op,
-                                                                      conj_op ? 1 : 0, p.fm, p.tm, skip);
+    k_apply_dense_mma<true, S><<<(unsigned)grid, nwarps * 32, smem, s>>>(in, out, op, conj_op ? 1 : 0, p.fm, p.tm, skip);
   else
-    k_apply_dense_mma<false><<<(unsigned)grid, nwarps * 32, smem, s>>>((const double2*)in, (double2*)out, (const double2*)op,
-                                                                       conj_op ? 1 : 0, p.fm, p.tm, skip);
+    k_apply_dense_mma<false, S><<<(unsigned)grid, nwarps * 32, smem, s>>>(in, out, op, conj_op ? 1 : 0, p.fm, p.tm, skip);
   PW_LAUNCHED();
   return PW_OK;
+}
+
+int launch_dense_mma(const void* in, void* out, const void* op, const Plan& p, int dtype, bool conj_op,
+                     cudaStream_t s, const int* skip) {
+  const int t = (int)p.tm.t;
+  if (in == out || t <= 8 || t > kDmMaxT || p.fm.ng == 0) return PW_ERR_UNSUPPORTED;
+  if (dtype == PW_C64 && !options().ts_mma_c64.load(std::memory_order_relaxed)) return PW_ERR_UNSUPPORTED;
+  // fibers adjacent in memory (untouched innermost run), or the targets are the innermost run
+  bool inner = false;
+  if (p.fm.gstride[p.fm.ng - 1] != 1) {
+    inner = p.fm.gstride[p.fm.ng - 1] == (int64_t)t;
+    for (int k = 0; k < p.tm.nt && inner; ++k) inner = p.tm.tdim[k] == 1 || p.tm.tstride[k] < (int64_t)t;
+    if (!inner) return PW_ERR_UNSUPPORTED;
+  } else if (p.fm.gsize[p.fm.ng - 1] < 16) {
+    return PW_ERR_UNSUPPORTED;
+  }
+  if (dtype == PW_C128)
+    return launch_dense_mma_s<double2>((const double2*)in, (double2*)out, (const double2*)op, p, conj_op, inner, s, skip);
+  if (dtype == PW_C64)
+    return launch_dense_mma_s<float2>((const float2*)in, (float2*)out, (const float2*)op, p, conj_op, inner, s, skip);
+  return PW_ERR_UNSUPPORTED;
 }
 
 }  // namespace pw

@@ -194,6 +194,7 @@ struct Options {
   std::atomic<int> dense_mma{1};               // dense complex128 operators, 8 < t <= 64: FP64 tensor-core kernel
   std::atomic<int> ts_order{0};                // tensor-core kernel, several super-blocks: 0 chunk-fastest, 1 pair-fastest unit order
   std::atomic<int> draw_exact{1};              // pw_draw: re-run the sequential cumsum when the draw is within rounding distance of a bin edge
+  std::atomic<int> ts_mma_c64{1};              // complex64: the same FP64 tensor-core kernels with float2 storage
   std::atomic<int> ts_mma{1};                  // complex128: FP64 tensor cores (mma.sync m8n8k4) in that kernel
 };
 Options& options();
