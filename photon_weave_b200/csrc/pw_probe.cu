@@ -60,14 +60,38 @@ k_probe_dmma(const int iters, double* __restrict__ sink) {
   if (s == 12345.678) sink[0] = s;
 }
 
+// legacy warp-level TF32 tensor path (mma.sync m16n8k8): what an error-compensated 3 x TF32
+// complex64 kernel would run on without tcgen05 / TMEM plumbing
+__global__ void __launch_bounds__(kProbeBlock)
+k_probe_tf32(const int iters, double* __restrict__ sink) {
+  float c[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) c[i][q] = 0.f;
+  const uint32_t a0 = __float_as_uint(1e-3f * (threadIdx.x & 31)), a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+  const uint32_t b0 = __float_as_uint(1.0f + 1e-3f * (threadIdx.x >> 5)), b1 = b0 + 1;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                   : "+f"(c[i][0]), "+f"(c[i][1]), "+f"(c[i][2]), "+f"(c[i][3])
+                   : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  }
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1] + c[i][2] + c[i][3];
+  if (s == 12345.678f) sink[0] = s;
+}
+
 }  // namespace pw
 
 using namespace pw;
 
-// kind 0: FP64 FMA, 1: FP64 mma.sync m8n8k4 (DMMA), 2: FP32 FMA.  Enqueues ONE kernel of `iters`
+// kind 0: FP64 FMA, 1: FP64 mma.sync m8n8k4 (DMMA), 2: FP32 FMA, 3: TF32 mma.sync m16n8k8.  Enqueues ONE kernel of `iters`
 // iterations on `stream`; *flops receives the real flops it executes.  `sink` is one device double.
 extern "C" int pw_probe_arith(int kind, int iters, double* sink, double* flops, void* stream) {
-  if (!sink || !flops || iters < 1 || kind < 0 || kind > 2) return PW_ERR_INVALID;
+  if (!sink || !flops || iters < 1 || kind < 0 || kind > 3) return PW_ERR_INVALID;
   const int grid = kNumSMs * kProbeCtas;
   cudaStream_t s = (cudaStream_t)stream;
   const double threads = (double)grid * kProbeBlock;
@@ -77,6 +101,9 @@ extern "C" int pw_probe_arith(int kind, int iters, double* sink, double* flops, 
   } else if (kind == 2) {
     k_probe_sfma<<<grid, kProbeBlock, 0, s>>>(iters, sink);
     *flops = threads * 16.0 * 2.0 * iters;
+  } else if (kind == 3) {
+    k_probe_tf32<<<grid, kProbeBlock, 0, s>>>(iters, sink);
+    *flops = (threads / 32.0) * 8.0 * 2048.0 * iters;  // 8 MMAs of 2*16*8*8 flops per warp iteration
   } else {
     k_probe_dmma<<<grid, kProbeBlock, 0, s>>>(iters, sink);
     *flops = (threads / 32.0) * 8.0 * 512.0 * iters;  // 8 MMAs of 2*8*8*4 flops per warp iteration
