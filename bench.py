@@ -93,8 +93,8 @@ def preflight_input(kind, dims):
 
 def ncu_traffic(kernel_key: str):
     """dram__bytes_read+write per launch from the committed `ncu --set full` capture
-    (profiles/r1_traffic.json, produced by tools/ncu_summary.py); None if absent."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    (profiles/r2_traffic.json, from tools/ncu_summary.py --by-kernel); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     try:
         return json.load(open(path)).get(kernel_key, {}).get("dram_bytes_per_launch")
     except Exception:

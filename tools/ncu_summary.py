@@ -39,7 +39,30 @@ def summarize(rep):
     return launches
 
 
+def by_kernel(rep, min_ms=0.5):
+    """Per kernel name: launches captured and the AVERAGE of every metric over them (only
+    launches longer than min_ms: the analysis / skipped-fallback launches are not the point)."""
+    import re
+
+    agg = {}
+    for d in summarize(rep):
+        if d.get("duration", 0) * 1e3 < min_ms:
+            continue
+        name = re.sub(r"\(.*", "", d["kernel"]).replace("void ", "").strip()
+        agg.setdefault(name, []).append(d)
+    out = {}
+    for name, ls in agg.items():
+        keys = [k for k in ls[0] if k != "kernel"]
+        out[name] = {k: sum(x.get(k, 0.0) for x in ls) / len(ls) for k in keys}
+        out[name]["launches_captured"] = len(ls)
+        out[name]["duration_ms_each"] = [round(x["duration"] * 1e3, 3) for x in ls]
+    return out
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "--by-kernel":
+        print(json.dumps(by_kernel(sys.argv[2]), indent=1))
+        sys.exit(0)
     res = {}
     args = sys.argv[1:]
     for rep, key in zip(args[0::2], args[1::2]):
