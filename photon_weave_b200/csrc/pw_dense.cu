@@ -27,8 +27,7 @@ namespace pw {
 
 namespace {
 
-constexpr int kDmFib = 64;       // fibers per tile
-constexpr int kDmMaxT = 64;
+constexpr int kDmMaxT = 128;     // 64 < t <= 128: 32-fiber tiles, operator fragments from global memory
 
 __device__ __forceinline__ void dmma(double& d0, double& d1, const double a, const double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -77,7 +76,11 @@ __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0
 
 // blockDim = 32 * nwarps; dynamic smem: W [8 nm][wp] | offs [t] | base [2][64] | tiles [2][t][64]
 // (INNER: tiles [2][64][tp]; base[buf][0..1] = first element of the tile, valid fibers)
-template <bool INNER, typename S>
+// FIB: fibers per tile (64; 32 for 64 < t <= 128 so that two tiles still fit).  WG: the operator
+// fragments come from global memory (L1 / L2 resident) instead of a shared-memory copy -- a
+// 128 x 128 complex128 operator (the Jaynes-Cummings propagator, cutoff 64 (x) qubit, applied to a
+// BATCH of trajectories) is 256 KB and does not fit next to the tiles.
+template <bool INNER, typename S, int FIB, bool WG>
 __global__ void __launch_bounds__(512, 1)
 k_apply_dense_mma(const S* __restrict__ in, S* __restrict__ out,
                   const S* __restrict__ op, const int conj_op, const FiberMap fm,
@@ -90,18 +93,18 @@ k_apply_dense_mma(const S* __restrict__ in, S* __restrict__ out,
   const int ks = (t + 3) >> 2;             // steps of 4 complex inputs
   const int wp = (4 * ks + 7) & ~7;        // operand row pitch (multiple of 8: bank analysis)
   V* s_w = (V*)s_raw;                                        // [8 nm][wp], column c at (c ^ 4 (row & 1))
-  int64_t* s_off = (int64_t*)(s_w + 8 * nm * wp);            // [t]
-  int64_t* s_base = s_off + ((t + 1) & ~1);                  // [2][kDmFib]
-  S* tile0 = (S*)(s_base + 2 * kDmFib);                      // [2][t][kDmFib], fiber f of row j at (f ^ 2 (j & 3))
+  int64_t* s_off = (int64_t*)(s_w + (WG ? 0 : 8 * nm * wp)); // [t]
+  int64_t* s_base = s_off + ((t + 1) & ~1);                  // [2][FIB]
+  S* tile0 = (S*)(s_base + 2 * FIB);                      // [2][t][FIB], fiber f of row j at (f ^ 2 (j & 3))
   int tp = t;                                                // INNER: fiber pitch, 4 mod 8
   while ((tp & 7) != 4) ++tp;
-  const size_t tile_elems = INNER ? (size_t)kDmFib * tp : (size_t)t * kDmFib;
+  const size_t tile_elems = INNER ? (size_t)FIB * tp : (size_t)t * FIB;
   const uint32_t inv_t = 0xffffffffu / (uint32_t)t + 1;      // e / t for e < 2^16
   const uint64_t gl = INNER ? fm.gsize[fm.ng - 1] : 1;       // INNER: fibers per contiguous run
-  const uint64_t cpr = (gl + kDmFib - 1) / kDmFib;
+  const uint64_t cpr = (gl + FIB - 1) / FIB;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int gid = lane >> 2, tig = lane & 3;
-  for (int i = threadIdx.x; i < 8 * nm * wp; i += blockDim.x) {
+  for (int i = threadIdx.x; i < (WG ? 0 : 8 * nm * wp); i += blockDim.x) {
     const int r = i / wp, c = i - r * wp;
     V v = make_double2(0.0, 0.0);
     if (r < t && c < t) {
@@ -112,17 +115,17 @@ k_apply_dense_mma(const S* __restrict__ in, S* __restrict__ out,
   }
   for (int j = threadIdx.x; j < t; j += blockDim.x) s_off[j] = tm.offset((uint32_t)j);
   __syncthreads();
-  const uint64_t units = INNER ? (fm.nfib / gl) * cpr : (fm.nfib + kDmFib - 1) / kDmFib;
+  const uint64_t units = INNER ? (fm.nfib / gl) * cpr : (fm.nfib + FIB - 1) / FIB;
 
   auto issue = [&](uint64_t u, int buf) {
     if (INNER) {
       if (u < units) {
         S* tile = tile0 + (size_t)buf * tile_elems;
         const uint64_t o = u / cpr, w = u - o * cpr;
-        const uint64_t f0 = w * kDmFib;
-        const int nvalid = (gl - f0) < (uint64_t)kDmFib ? (int)(gl - f0) : kDmFib;
+        const uint64_t f0 = w * FIB;
+        const int nvalid = (gl - f0) < (uint64_t)FIB ? (int)(gl - f0) : FIB;
         const int64_t base0 = fm.base(o * gl + f0);
-        if (threadIdx.x == 0) { s_base[buf * kDmFib] = base0; s_base[buf * kDmFib + 1] = nvalid; }
+        if (threadIdx.x == 0) { s_base[buf * FIB] = base0; s_base[buf * FIB + 1] = nvalid; }
         const S* src = in + base0;
         for (int e = threadIdx.x; e < nvalid * t; e += blockDim.x) {
           const int f = (int)__umulhi((uint32_t)e, inv_t);
@@ -134,20 +137,32 @@ k_apply_dense_mma(const S* __restrict__ in, S* __restrict__ out,
     }
     if (u < units) {
       S* tile = tile0 + (size_t)buf * tile_elems;
-      const uint64_t fa = u * kDmFib + lane, fb = fa + 32;
-      const int64_t ba = fa < fm.nfib ? fm.base(fa) : -1, bb = fb < fm.nfib ? fm.base(fb) : -1;
-      if (warp == 0) { s_base[buf * kDmFib + lane] = ba; s_base[buf * kDmFib + 32 + lane] = bb; }
+      const uint64_t fa = u * FIB + lane, fb = fa + 32;
+      const int64_t ba = fa < fm.nfib ? fm.base(fa) : -1, bb = (FIB == 64 && fb < fm.nfib) ? fm.base(fb) : -1;
+      if (warp == 0) {
+        s_base[buf * FIB + lane] = ba;
+        if (FIB == 64) s_base[buf * FIB + 32 + lane] = bb;
+      }
       for (int j = warp; j < t; j += nwarps) {
         const int sw = 2 * (j & 3);
         const int64_t o = s_off[j];
-        if (ba >= 0) cp_elem(tile + j * kDmFib + (lane ^ sw), in + ba + o);
-        if (bb >= 0) cp_elem(tile + j * kDmFib + 32 + (lane ^ sw), in + bb + o);
+        if (ba >= 0) cp_elem(tile + j * FIB + (lane ^ sw), in + ba + o);
+        if (FIB == 64 && bb >= 0) cp_elem(tile + j * FIB + 32 + (lane ^ sw), in + bb + o);
       }
     }
     cp_commit();
   };
 
-  const int nitems = nm * (kDmFib / 32);
+  const int nitems = nm * (FIB / 32);
+  // WG: fragment W[row][j] straight from global memory
+  auto wglob = [&](int row, int j) {
+    V v = make_double2(0.0, 0.0);
+    if (row < t && j < t) {
+      v = wide(__ldg(op + (size_t)row * t + j));
+      if (conj_op) v.y = -v.y;
+    }
+    return v;
+  };
   const int fsw = (gid & 1) << 2;
   uint64_t u = blockIdx.x;
   int cur = 0;
@@ -157,9 +172,9 @@ k_apply_dense_mma(const S* __restrict__ in, S* __restrict__ out,
     issue(u + gridDim.x, cur ^ 1);
     cp_wait<1>();
     __syncthreads();
-    const int64_t* sb = s_base + cur * kDmFib;
+    const int64_t* sb = s_base + cur * FIB;
     for (int it = warp; it < nitems; it += nwarps) {
-      const int m = it >> 1, h = it & 1;
+      const int m = FIB == 64 ? it >> 1 : it, h = FIB == 64 ? it & 1 : 0;
       const int row = 8 * m + gid;
       double acc[4][4];
 #pragma unroll
@@ -169,10 +184,12 @@ k_apply_dense_mma(const S* __restrict__ in, S* __restrict__ out,
       const V* wrow = s_w + row * wp;
       const S* xcol = INNER ? tile + (32 * h + gid) * tp                 // + 8 n tp + position of j
                             : tile + 32 * h + (gid ^ (2 * tig));        // + j * 64 + 8 n   (j & 3 == tig)
+      V wnext = WG ? wglob(row, tig) : make_double2(0.0, 0.0);
 #pragma unroll 2
       for (int k = 0; k < ks; ++k) {
         const int j = 4 * k + tig;
-        const V w = wrow[(4 * k + tig) ^ fsw];
+        const V w = WG ? wnext : wrow[(4 * k + tig) ^ fsw];
+        if (WG && k + 1 < ks) wnext = wglob(row, j + 4);   // next step's fragment: hides the L1 / L2 latency
         V x[4];
         if (INNER) {
           const int pj = j < t ? (int)s_off[j] : 0;
@@ -180,7 +197,7 @@ k_apply_dense_mma(const S* __restrict__ in, S* __restrict__ out,
           for (int n = 0; n < 4; ++n) x[n] = j < t ? wide(xcol[8 * n * tp + pj]) : make_double2(0.0, 0.0);
         } else {
 #pragma unroll
-          for (int n = 0; n < 4; ++n) x[n] = j < t ? wide(xcol[j * kDmFib + 8 * n]) : make_double2(0.0, 0.0);
+          for (int n = 0; n < 4; ++n) x[n] = j < t ? wide(xcol[j * FIB + 8 * n]) : make_double2(0.0, 0.0);
         }
         // step-major issue order: the eight accumulator chains advance together (a warp issues
         // in order; consecutive DMMAs must be independent to keep the tensor pipe busy)
@@ -223,34 +240,35 @@ k_apply_dense_mma(const S* __restrict__ in, S* __restrict__ out,
 
 }  // namespace
 
-template <typename S>
+template <typename S, int FIB, bool WG>
 static int launch_dense_mma_s(const S* in, S* out, const S* op, const Plan& p, bool conj_op, bool inner,
                               cudaStream_t s, const int* skip) {
   const int t = (int)p.tm.t;
   const int nm = (t + 7) >> 3, ks = (t + 3) >> 2, wp = (4 * ks + 7) & ~7;
   int tp = t;
   while ((tp & 7) != 4) ++tp;
-  const size_t smem = sizeof(double2) * (size_t)(8 * nm * wp) + sizeof(int64_t) * (size_t)(((t + 1) & ~1) + 2 * kDmFib) +
-                      sizeof(S) * (size_t)2 * (inner ? tp : t) * kDmFib;
+  const size_t smem = (WG ? 0 : sizeof(double2) * (size_t)(8 * nm * wp)) +
+                      sizeof(int64_t) * (size_t)(((t + 1) & ~1) + 2 * FIB) +
+                      sizeof(S) * (size_t)2 * (inner ? tp : t) * FIB;
   if (smem > 220 * 1024) return PW_ERR_UNSUPPORTED;
   static bool attr_set = false;
   if (!attr_set) {
-    PW_CUDA(cudaFuncSetAttribute(k_apply_dense_mma<false, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
-    PW_CUDA(cudaFuncSetAttribute(k_apply_dense_mma<true, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+    PW_CUDA(cudaFuncSetAttribute(k_apply_dense_mma<false, S, FIB, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+    PW_CUDA(cudaFuncSetAttribute(k_apply_dense_mma<true, S, FIB, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
     attr_set = true;
   }
   // one warp per item (8 rows x 32 fibers); two CTAs per SM when the tiles allow it
-  int nwarps = 2 * nm;
+  int nwarps = nm * (FIB / 32);
   if (nwarps > 16) nwarps = 16;
   const int ctas = (smem + 1024) * 2 <= 227 * 1024 ? 2 : 1;
   const uint64_t gl = inner ? p.fm.gsize[p.fm.ng - 1] : 1;
-  const uint64_t units = inner ? (p.fm.nfib / gl) * ((gl + kDmFib - 1) / kDmFib) : (p.fm.nfib + kDmFib - 1) / kDmFib;
+  const uint64_t units = inner ? (p.fm.nfib / gl) * ((gl + FIB - 1) / FIB) : (p.fm.nfib + FIB - 1) / FIB;
   uint64_t grid = (uint64_t)kNumSMs * ctas;
   if (grid > units) grid = units;
   if (inner)
-    k_apply_dense_mma<true, S><<<(unsigned)grid, nwarps * 32, smem, s>>>(in, out, op, conj_op ? 1 : 0, p.fm, p.tm, skip);
+    k_apply_dense_mma<true, S, FIB, WG><<<(unsigned)grid, nwarps * 32, smem, s>>>(in, out, op, conj_op ? 1 : 0, p.fm, p.tm, skip);
   else
-    k_apply_dense_mma<false, S><<<(unsigned)grid, nwarps * 32, smem, s>>>(in, out, op, conj_op ? 1 : 0, p.fm, p.tm, skip);
+    k_apply_dense_mma<false, S, FIB, WG><<<(unsigned)grid, nwarps * 32, smem, s>>>(in, out, op, conj_op ? 1 : 0, p.fm, p.tm, skip);
   PW_LAUNCHED();
   return PW_OK;
 }
@@ -269,10 +287,17 @@ int launch_dense_mma(const void* in, void* out, const void* op, const Plan& p, i
   } else if (p.fm.gsize[p.fm.ng - 1] < 16) {
     return PW_ERR_UNSUPPORTED;
   }
+  if (t > 64) {
+    if (dtype == PW_C128)
+      return launch_dense_mma_s<double2, 32, true>((const double2*)in, (double2*)out, (const double2*)op, p, conj_op, inner, s, skip);
+    if (dtype == PW_C64)
+      return launch_dense_mma_s<float2, 32, true>((const float2*)in, (float2*)out, (const float2*)op, p, conj_op, inner, s, skip);
+    return PW_ERR_UNSUPPORTED;
+  }
   if (dtype == PW_C128)
-    return launch_dense_mma_s<double2>((const double2*)in, (double2*)out, (const double2*)op, p, conj_op, inner, s, skip);
+    return launch_dense_mma_s<double2, 64, false>((const double2*)in, (double2*)out, (const double2*)op, p, conj_op, inner, s, skip);
   if (dtype == PW_C64)
-    return launch_dense_mma_s<float2>((const float2*)in, (float2*)out, (const float2*)op, p, conj_op, inner, s, skip);
+    return launch_dense_mma_s<float2, 64, false>((const float2*)in, (float2*)out, (const float2*)op, p, conj_op, inner, s, skip);
   return PW_ERR_UNSUPPORTED;
 }
 

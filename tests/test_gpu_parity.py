@@ -889,3 +889,52 @@ def test_device_circuit_groups_commuting_operators(ad):
             _lib.set_option("fuse_group", 3)
         assert rel_err(host(res).reshape(-1, 1), ref) < 1e-12, group
         assert fused_launches < len(layer) + 6
+
+
+@pytest.mark.parametrize("cdtype", [np.complex128, np.complex64])
+def test_dense_tensor_core_kernel_up_to_128_and_complex64(ad, cdtype):
+    """64 < t <= 128 (32-fiber tiles, operator fragments from global memory) and the float2-storage
+    instantiation of the dense FP64 tensor-core kernel; both fiber layouts, ragged tails."""
+    from photon_weave_b200 import _lib
+
+    tol = TOL[cdtype]
+    _lib.set_option("blocks_min_elems", 0)
+    try:
+        for dims, tg, seed in [((64, 2, 70), (0, 1), 1), ((3, 128, 40), (1,), 2), ((77, 64, 2), (1, 2), 3),
+                               ((5, 9, 11, 37), (1, 2), 4), ((33, 100), (1,), 5), ((6, 6, 50), (0, 1), 6),
+                               ((50, 6, 6), (2, 1), 7), ((2, 8, 16, 19), (2, 1), 8)]:
+            N = math.prod(dims)
+            t = math.prod(dims[i] for i in tg)
+            psi = ops.random_state(N, seed, cdtype)
+            op = ops.random_unitary(t, 10 + seed).astype(cdtype)
+            ref = oad.apply_operation_vector(dims, tg, psi.astype(np.complex128), op.astype(np.complex128), True)
+            out = host(ad.apply_operation_vector(dims, tg, dev(psi), dev(op)))
+            assert rel_err(out, ref) < tol, (dims, tg)
+    finally:
+        _lib.set_option("blocks_min_elems", 1 << 18)
+
+
+def test_batched_jaynes_cummings_propagator_on_tensor_cores(ad):
+    """examples/jaynes_cummings_model.py:130-141 for a BATCH of trajectories (the jax.vmap use of
+    tests/state/test_shape_planning.py:104-121): B states of the cutoff-64 (x) qubit system under
+    one 128 x 128 propagator = ONE launch of the dense tensor-core kernel (a GEMM 128x128 . 128xB)."""
+    from photon_weave_b200 import _lib
+    from photon_weave_b200.core import transforms as T
+
+    dims, B = (64, 2), 3000
+    U = ops.random_unitary(128, 5)
+    states = np.stack([ops.random_state(128, 100 + i) for i in range(8)])
+    batch = np.concatenate([states] * (B // 8))                       # (B, 128, 1)
+    fn = lambda s, o: ad.apply_operation_vector(dims, (0, 1), s, o)
+    _lib.set_option("blocks_min_elems", 0)
+    try:
+        n0 = _lib.load().pw_launch_count()
+        out = T.vmap(fn, in_axes=(0, None))(dev(batch), dev(U))
+        launches = _lib.load().pw_launch_count() - n0
+    finally:
+        _lib.set_option("blocks_min_elems", 1 << 18)
+    want = np.stack([U @ s for s in states])
+    got = host(out)
+    assert got.shape == (B, 128, 1)
+    assert rel_err(got[:8], want) < 1e-12 and rel_err(got[-8:], want) < 1e-12
+    assert launches <= 4
