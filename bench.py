@@ -761,6 +761,28 @@ def run_small_configs(torch, ffi):
         x = U @ psi
         return oad.trace_out_vector(dims, (1,), x, True)
 
+    # a BATCH of trajectories under the same propagator (vmap): one dense tensor-core launch per step
+    from photon_weave_b200.core import transforms as T
+
+    Bt = 1 << 18
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    batch = torch.view_as_complex(torch.randn(Bt, 128, 1, 2, generator=gen, device="cuda", dtype=torch.float64))
+    step = T.vmap(lambda s, o: ad.apply_operation_vector(dims, (0, 1), s, o), in_axes=(0, None))
+    step(batch, d_U)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        batch = step(batch, d_U)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_b = e0.elapsed_time(e1) / 5
+    res["jaynes_cummings_batched"] = {
+        "trajectories": Bt, "ms_per_step": ms_b, "trajectory_steps_per_s": Bt / (ms_b * 1e-3),
+        "fp64_tflops": 8.0 * 128 * 128 * Bt / (ms_b * 1e-3) / 1e12,
+        "note": "128x128 propagator on 2^18 states = GEMM on the FP64 tensor cores (k_apply_dense_mma, t = 128); "
+                "measured DMMA roof 37.1 TFLOP/s (profiles/r2_arith_peaks.json)"}
+    del batch
     res["jaynes_cummings_10k_steps"] = {
         "fused_kernel_total_ms": fused_s * 1e3, "fused_us_per_step": fused_s / nsteps * 1e6,
         "per_call_api_us_per_step": gpu_us(jc_step_gpu, 200),

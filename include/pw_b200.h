@@ -79,6 +79,19 @@ int pw_set_option(const char* name, int value);
  * the real flops it performs; time it with CUDA events.  `sink` is one device double. */
 int pw_probe_arith(int kind, int iters, double* sink, double* flops, void* stream);
 
+/* ---- analysed-plan cache ----------------------------------------------------------
+ * pw_apply_vec / pw_apply_mat / pw_kraus_mat / pw_kraus_axes analyse their operator on the device
+ * before the kernel that does the work (block structure, super-block packing, superoperator).
+ * pw_op_pin(op) is the caller's promise that the device memory at `op` stays alive and UNCHANGED
+ * until pw_op_unpin(op): the library then keeps the analysis per (operator, dims, targets, dtype,
+ * aliasing) and later calls skip it (the container layer pins the cached device operator of an
+ * Operation -- photon_weave/operation/operation.py:292-294 recomputes it on every access).
+ * Results are identical with and without pinning.  pw_op_unpin releases the cached buffers (it
+ * waits for the device).  pw_plan_cache_size: entries alive (tests). */
+int pw_op_pin(const void* op);
+int pw_op_unpin(const void* op);
+int pw_plan_cache_size(void);
+
 /* ---- apply ------------------------------------------------------------------ */
 
 /* psi' = (O on targets) psi.

@@ -47,6 +47,9 @@ SIGNATURES = {
     "pw_path_counters": (None, [C.POINTER(C.c_uint64)]),
     "pw_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "pw_probe_arith": (C.c_int, [C.c_int, C.c_int, _vp, C.POINTER(C.c_double), _vp]),
+    "pw_op_pin": (C.c_int, [_vp]),
+    "pw_op_unpin": (C.c_int, [_vp]),
+    "pw_plan_cache_size": (C.c_int, []),
     "pw_apply_vec": (C.c_int, [_vp, _vp, _vp, _i64p, C.c_int, _i32p, C.c_int, C.c_int, _vp]),
     "pw_apply_mat": (C.c_int, [_vp, _vp, _vp, _i64p, C.c_int, _i32p, C.c_int, C.c_int, _vp]),
     "pw_kraus_mat": (

@@ -17,6 +17,14 @@ import torch
 from .sharded import CudaBackend, PeerBuffers, PeerUnavailable, ShardedDensityMatrix, ShardedStateVector
 
 
+def _device_ops(layer) -> List[torch.Tensor]:
+    """Operators of a layer in HBM, pinned: they never change, so libpwb200 keeps their structure
+    analysis across the many (chunk-wise) applications of the pipelined schedule."""
+    from .core import ffi
+
+    return [ffi.pin_operator(torch.as_tensor(o).cuda()) for _, o, _ in layer]
+
+
 def make_peers(numel: int, nbuf: int, rank: int, world: int, dist, local_rank: int, want: bool):
     """(peers | None, description).  The decision is collective (PeerBuffers raises on EVERY rank
     or on none), so all ranks run the same swap implementation."""
@@ -133,7 +141,7 @@ def parity_preflight(dist, rank: int, world: int, local_rank: int, kind: str, ma
         peers.tensors[0].copy_(own)
         own, spare = peers.tensors[0], peers.tensors[1]
     st = cls(dims, own, vaxes, sparts, rank, world, dist, CudaBackend(), spare=spare, peers=peers)
-    d_ops = [torch.as_tensor(o).cuda() for _, o, _ in layer]
+    d_ops = _device_ops(layer)
     runner = LayerRunner(st, layer, d_ops, shard_a, shard_b, apply, mode)
     for _ in range(layers):
         runner.run()
@@ -285,7 +293,7 @@ def bench_sharded(args, dist, rank, world, local_rank, make_layer, workload_conf
     dims = (cutoff,) * modes
     N = cutoff**modes
     layer = make_layer(modes, cutoff)
-    d_ops = [torch.as_tensor(o).cuda() for _, o, _ in layer]
+    d_ops = _device_ops(layer)
     nops = len(layer)
     vaxes, sparts, shard_a, shard_b = _layouts(ShardedStateVector, dims, world, modes)
     n_local = N // world
@@ -352,7 +360,7 @@ def bench_sharded_rho(args, dist, rank, world, local_rank, make_rho_layer, peaks
     dims = (cutoff,) * modes
     D = cutoff**modes
     layer = make_rho_layer(modes, cutoff)
-    d_ops = [torch.as_tensor(o).cuda() for _, o, _ in layer]
+    d_ops = _device_ops(layer)
     nops = len(layer)
     vaxes, sparts, shard_a, shard_b = _layouts(ShardedDensityMatrix, dims, world, modes)
     n_local = D * D // world

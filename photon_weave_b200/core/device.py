@@ -34,6 +34,14 @@ def asarray(x: Any) -> torch.Tensor:
     return A.as_complex(t, DTYPE)
 
 
+def pin_operator(op: torch.Tensor) -> torch.Tensor:
+    """Tell libpwb200 that a cached device operator never changes (pw_op_pin): its structure
+    analysis is then kept across applies.  No-op for host tensors (the oracle-backed test shim)."""
+    if isinstance(op, torch.Tensor) and op.is_cuda:
+        ffi.pin_operator(op)
+    return op
+
+
 def adopt(value: Any) -> Any:
     """What a container stores when the user assigns ``.state``: labels pass through, host
     arrays (NumPy / JAX / lists of rows) move into HBM as complex128."""

@@ -17,6 +17,19 @@ from .. import _lib
 from . import _arrays as A
 
 
+def pin_operator(op: torch.Tensor) -> torch.Tensor:
+    """Promise that ``op`` (a device operator) stays alive and unchanged: the library keeps its
+    structure analysis per (operator, dims, targets) and later applies skip it.  The pin is released
+    when the tensor is garbage collected.  Returns ``op``."""
+    import weakref
+
+    lib = _lib.load()
+    ptr = op.data_ptr()
+    _lib.check(lib.pw_op_pin(ptr), "pw_op_pin")
+    weakref.finalize(op, lib.pw_op_unpin, ptr)
+    return op
+
+
 def _common(dims: Sequence[int], idx: Sequence[int]):
     return _lib.i64_array(dims), len(dims), _lib.i32_array(idx), len(idx)
 

@@ -79,6 +79,7 @@ Options& options() {
 extern "C" int pw_set_option(const char* name, int value) {
   if (!name) return PW_ERR_INVALID;
   pw::Options& o = pw::options();
+  pw::g_options_epoch.fetch_add(1);   // dispatch may change: cached plans of older epochs are not reused
   if (!std::strcmp(name, "vec_path")) o.vec_path.store(value);
   else if (!std::strcmp(name, "mat_mode")) o.mat_mode.store(value);
   else if (!std::strcmp(name, "tile_elems")) o.tile_elems.store(value);

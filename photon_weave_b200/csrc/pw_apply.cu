@@ -440,11 +440,13 @@ static int launch_apply_t(const V* in, V* out, const V* op, const Plan& p, bool 
   // generic: needs a non-aliased source and the offset table in global memory
   Scratch toff, tmp;
   PW_TRY(toff.alloc(sizeof(int64_t) * p.tm.t, s));
-  k_target_offsets<<<(p.tm.t + 127) / 128, 128, 0, s>>>(p.tm, (int64_t*)toff.p);
-  PW_LAUNCHED();
+  if (!plan_replay()) {
+    k_target_offsets<<<(p.tm.t + 127) / 128, 128, 0, s>>>(p.tm, (int64_t*)toff.p);
+    PW_LAUNCHED();
+  }
   const V* src = in;
   if ((const void*)in == (const void*)out) {
-    PW_TRY(tmp.alloc(sizeof(V) * p.N, s));
+    PW_TRY(tmp.alloc_temp(sizeof(V) * p.N, s));
     PW_CUDA(cudaMemcpyAsync(tmp.p, in, sizeof(V) * p.N, cudaMemcpyDeviceToDevice, s));
     src = (const V*)tmp.p;
   }
@@ -596,8 +598,10 @@ static int try_diag(const V* in, V* out, const V* op, const Plan& p, bool conj_o
     if (tm.tstride[k] & 1) even = false;
   }
   PW_TRY(flag_mem->alloc(sizeof(int), s));
-  k_diag_check<V><<<1, 32, 0, s>>>(op, p.tm.t, (int*)flag_mem->p);
-  PW_LAUNCHED();
+  if (!plan_replay()) {
+    k_diag_check<V><<<1, 32, 0, s>>>(op, p.tm.t, (int*)flag_mem->p);
+    PW_LAUNCHED();
+  }
   const int* fl = (const int*)flag_mem->p;
   const int grid = grid_for(even ? p.N / 2 : p.N, 256, 8);
   if (even) {
@@ -697,7 +701,8 @@ extern "C" int pw_apply_vec(const void* psi, void* out, const void* op, const in
   if (!psi || !out || !op || nt < 1 || !dims || !targets) return PW_ERR_INVALID;
   if (dtype != PW_C64 && dtype != PW_C128) return PW_ERR_INVALID;
   if (n > PW_MAX_SUBSYSTEMS || nt > PW_MAX_TARGETS) return PW_ERR_INVALID;
-  return apply_axes(psi, out, op, dims, n, targets, nt, false, dtype, (cudaStream_t)stream);
+  PlanScope scope(op, 0, dtype, 1, dims, n, targets, nt, nullptr, 0, psi == out, (cudaStream_t)stream);
+  return scope.finish(apply_axes(psi, out, op, dims, n, targets, nt, false, dtype, (cudaStream_t)stream));
 }
 
 // A (possibly rectangular) block of a density matrix as a tensor over `naxes` axes with the
@@ -792,7 +797,7 @@ static int two_pass(const void* rho, void* out, const void* ops, int K, const Ma
       // large operators: keep BOTH sides out of place (rho -> tmp -> out) so each side can
       // take the block-structured kernels (a beam splitter on rho: 2 x ~90 % passes)
       Scratch tmp2;
-      if (tmp2.alloc((size_t)r.total * es, s) == PW_OK) {
+      if (tmp2.alloc_temp((size_t)r.total * es, s) == PW_OK) {
         // (with a skip flag the sides run the skippable kernels; in place would cost an
         // unconditional copy of rho)
         PW_TRY(apply_side(rho, tmp2.p, ops, r, false, false, dtype, s, skip));
@@ -805,10 +810,10 @@ static int two_pass(const void* rho, void* out, const void* ops, int K, const Ma
   // out = sum_k (K_k rho) K_k^dagger; tmp holds K_k rho, the column pass accumulates
   const size_t bytes = (size_t)r.total * es, op_bytes = (size_t)(r.t * r.t) * es;
   Scratch tmp, src;
-  PW_TRY(tmp.alloc(bytes, s));
+  PW_TRY(tmp.alloc_temp(bytes, s));
   const void* in = rho;
   if (rho == out) {
-    PW_TRY(src.alloc(bytes, s));
+    PW_TRY(src.alloc_temp(bytes, s));
     PW_CUDA(cudaMemcpyAsync(src.p, rho, bytes, cudaMemcpyDeviceToDevice, s));
     in = src.p;
   }
@@ -906,7 +911,8 @@ extern "C" int pw_apply_mat(const void* rho, void* out, const void* op, const in
   if (dtype != PW_C64 && dtype != PW_C128) return PW_ERR_INVALID;
   MatrixReq r;
   PW_TRY(matrix_req(dims, n, targets, nt, &r));
-  return matrix_dispatch(rho, out, op, 1, r, dtype, (cudaStream_t)stream);
+  PlanScope scope(op, 1, dtype, 1, dims, n, targets, nt, nullptr, 0, rho == out, (cudaStream_t)stream);
+  return scope.finish(matrix_dispatch(rho, out, op, 1, r, dtype, (cudaStream_t)stream));
 }
 
 extern "C" int pw_kraus_mat(const void* rho, void* out, const void* ops, int K,
@@ -916,7 +922,8 @@ extern "C" int pw_kraus_mat(const void* rho, void* out, const void* ops, int K,
   if (dtype != PW_C64 && dtype != PW_C128) return PW_ERR_INVALID;
   MatrixReq r;
   PW_TRY(matrix_req(dims, n, targets, nt, &r));
-  return matrix_dispatch(rho, out, ops, K, r, dtype, (cudaStream_t)stream);
+  PlanScope scope(ops, 2, dtype, K, dims, n, targets, nt, nullptr, 0, rho == out, (cudaStream_t)stream);
+  return scope.finish(matrix_dispatch(rho, out, ops, K, r, dtype, (cudaStream_t)stream));
 }
 
 extern "C" int pw_kraus_axes(const void* x, void* out, const void* ops, int K, const int64_t* axes,
@@ -926,7 +933,8 @@ extern "C" int pw_kraus_axes(const void* x, void* out, const void* ops, int K, c
   if (dtype != PW_C64 && dtype != PW_C128) return PW_ERR_INVALID;
   MatrixReq r;
   PW_TRY(matrix_req_axes(axes, naxes, row_targets, ntr, col_targets, ntc, &r));
-  return matrix_dispatch(x, out, ops, K, r, dtype, (cudaStream_t)stream);
+  PlanScope scope(ops, 3, dtype, K, axes, naxes, row_targets, ntr, col_targets, ntc, x == out, (cudaStream_t)stream);
+  return scope.finish(matrix_dispatch(x, out, ops, K, r, dtype, (cudaStream_t)stream));
 }
 
 extern "C" int pw_apply_vec_pair(const void* psi, void* out, const void* op_a, const void* op_b,

@@ -343,6 +343,7 @@ template <typename V>
 static int build_block_desc_t(const V* op, uint32_t t, bool conj_op, const TargetMap& tm,
                               Scratch* mem, BlockArrays* arr, cudaStream_t s, const int* skip = nullptr) {
   PW_TRY(alloc_block_desc<V>(t, mem, arr, s));
+  if (plan_replay()) return PW_OK;   // cached plan: the descriptor is already built
   k_build_blocks<V><<<1, 256, sizeof(int32_t) * 20 * t, s>>>(op, t, conj_op, tm, *arr, conj_op, tm, *arr, skip);
   PW_LAUNCHED();
   return PW_OK;
@@ -355,6 +356,7 @@ static int build_block_desc_pair_t(const V* op, uint32_t t, bool conj0, const Ta
                                    BlockArrays* arr1, cudaStream_t s) {
   PW_TRY(alloc_block_desc<V>(t, mem0, arr0, s));
   PW_TRY(alloc_block_desc<V>(t, mem1, arr1, s));
+  if (plan_replay()) return PW_OK;
   k_build_blocks<V><<<2, 256, sizeof(int32_t) * 20 * t, s>>>(op, t, conj0, tm0, *arr0, conj1, tm1, *arr1, nullptr);
   PW_LAUNCHED();
   return PW_OK;
@@ -1399,8 +1401,10 @@ static int launch_two_sided_t(const V* rho, V* out, const V* op, const FiberMap&
   const bool mma_ok = options().ts_mma.load(std::memory_order_relaxed) && fm.nfib < (1ull << 28) &&
                       (c128 || options().ts_mma_c64.load(std::memory_order_relaxed));
   if (inner && !mma_ok) return PW_ERR_UNSUPPORTED;
-  k_ts_build<V><<<1, 256, 0, s>>>(ts->L, ts->R, other, T, kTsValCap, mma_ok ? (c128 ? 2 : 1) : 0, inner);
-  PW_LAUNCHED();
+  if (!plan_replay()) {
+    k_ts_build<V><<<1, 256, 0, s>>>(ts->L, ts->R, other, T, kTsValCap, mma_ok ? (c128 ? 2 : 1) : 0, inner);
+    PW_LAUNCHED();
+  }
   const size_t smem = 2 * kTsValCap + sizeof(V) * 2 * kTsSlots * 32;
   static bool attr_set = false;
   if (!attr_set) {
@@ -1753,8 +1757,10 @@ static int enqueue_seg_mma(const void* in, void* out, const SegGeom& g, BlockDes
   S.sb_blk = (int2*)(base + b_flags + b_n);
   S.pos = (int*)(base + b_flags + b_n + b_blk);
   S.w = (double2*)(base + b_flags + b_n + b_blk + b_pos);
-  k_seg_sb_build<<<1, 128, 0, s>>>(d->arr, S);
-  PW_LAUNCHED();
+  if (!plan_replay()) {
+    k_seg_sb_build<<<1, 128, 0, s>>>(d->arr, S);
+    PW_LAUNCHED();
+  }
   const int tp = ((int)g.t + 7) & ~7;
   const int kSgFib = seg_mma_fibers((int)g.t);
   const size_t smem = sizeof(double2) * (size_t)(kSgMaxSb * 64 + 2 * kSgFib * tp) + sizeof(SgMeta) * 2 +

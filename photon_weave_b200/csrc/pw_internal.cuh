@@ -152,12 +152,65 @@ inline int grid_for(uint64_t work_items, int block, int max_ctas_per_sm) {
 // threshold of 0 hands multi-GB scratch back to the driver at every synchronisation).
 void keep_pool_memory();
 
-// Stream-ordered scratch buffer (freed on the same stream when it goes out of scope).
+// ---- analysed-plan cache ------------------------------------------------------------------
+// An apply / Kraus call analyses its operator on the device (block structure, super-blocks,
+// superoperator, CSR, diagonal test) into scratch buffers before the kernel that does the work.
+// For an operator the caller has PINNED (pw_op_pin: "this device memory stays alive and
+// unchanged") those buffers are kept: the first call with a given (operator, dims, targets,
+// dtype, aliasing, options) records them, later calls REPLAY -- Scratch::alloc hands the recorded
+// buffers back in the same order and the analysis kernels (guarded by plan_replay()) are not
+// launched again.  Descriptors are read-only once built, so replays on other streams only wait
+// for the event recorded after the build.
+struct PlanCacheEntry {
+  void* bufs[24];
+  size_t sizes[24];
+  int nbufs = 0;
+  cudaEvent_t ready = nullptr;
+  cudaStream_t fill_stream = nullptr;
+  bool filled = false;
+};
+struct PlanCacheCtx {
+  PlanCacheEntry* e = nullptr;
+  int cursor = 0;
+  bool replay = false;
+  bool broken = false;   // replay did not match the recording (never expected): the call fails
+};
+extern thread_local PlanCacheCtx* g_plan_ctx;
+inline bool plan_replay() { return g_plan_ctx != nullptr && g_plan_ctx->replay; }
+
+// Stream-ordered scratch buffer (freed on the same stream when it goes out of scope); inside a
+// cached call: a persistent buffer owned by the plan cache.
 struct Scratch {
   void* p = nullptr;
   cudaStream_t s = nullptr;
+  bool cached = false;
   int alloc(size_t bytes, cudaStream_t stream) {
     s = stream;
+    if (bytes == 0) bytes = 16;
+    if (PlanCacheCtx* c = g_plan_ctx) {
+      PlanCacheEntry* e = c->e;
+      cached = true;
+      if (c->replay) {
+        if (c->cursor >= e->nbufs || e->sizes[c->cursor] != bytes) { c->broken = true; p = nullptr; return PW_ERR_WORKSPACE; }
+        p = e->bufs[c->cursor++];
+        return PW_OK;
+      }
+      if (e->nbufs >= 24 || cudaMalloc(&p, bytes) != cudaSuccess) {
+        p = nullptr;
+        (void)cudaGetLastError();
+        c->broken = true;
+        return PW_ERR_WORKSPACE;
+      }
+      e->bufs[e->nbufs] = p;
+      e->sizes[e->nbufs++] = bytes;
+      return PW_OK;
+    }
+    return alloc_temp(bytes, stream);
+  }
+  // state-sized temporaries: never cached
+  int alloc_temp(size_t bytes, cudaStream_t stream) {
+    s = stream;
+    cached = false;
     keep_pool_memory();
     if (cudaMallocAsync(&p, bytes ? bytes : 16, stream) != cudaSuccess) {
       p = nullptr;
@@ -167,11 +220,23 @@ struct Scratch {
     return PW_OK;
   }
   ~Scratch() {
-    if (p) cudaFreeAsync(p, s);
+    if (p && !cached) cudaFreeAsync(p, s);
   }
 };
 
+// RAII around one C-ABI apply call: activates the plan cache when `op` is pinned.
+struct PlanScope {
+  PlanCacheCtx ctx;
+  bool active = false;
+  PlanScope(const void* op, int tag, int dtype, int K, const int64_t* dims, int n, const int32_t* t1, int nt1,
+            const int32_t* t2, int nt2, bool aliased, cudaStream_t stream);
+  int finish(int rc);   // call with the dispatch's status; returns the status to hand to the caller
+  ~PlanScope();
+  cudaStream_t stream_ = nullptr;
+};
+
 // ---- tuning knobs (pw_set_option / PW_* environment) -------------------------
+extern std::atomic<uint64_t> g_options_epoch;  // bumped by pw_set_option: cached plans of older epochs are not reused
 struct Options {
   std::atomic<int> vec_path{0}, mat_mode{0}, tile_elems{0}, ctas_per_sm{0};
   std::atomic<int> small_r{16};                // inner untouched run below this -> tiled staging

@@ -1,7 +1,86 @@
 // Host-side index planning: validates (dims, targets) and builds the fiber/target maps.
 #include "pw_internal.cuh"
 
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <set>
+#include <string>
+
 namespace pw {
+
+thread_local PlanCacheCtx* g_plan_ctx = nullptr;
+std::atomic<uint64_t> g_options_epoch{0};
+
+namespace {
+std::mutex g_plan_mu;
+std::set<const void*> g_pinned;
+std::map<std::string, PlanCacheEntry*> g_plans;   // key bytes start with the operator pointer
+
+void free_entry(PlanCacheEntry* e) {
+  for (int i = 0; i < e->nbufs; ++i) cudaFree(e->bufs[i]);
+  if (e->ready) cudaEventDestroy(e->ready);
+  delete e;
+}
+}  // namespace
+
+PlanScope::PlanScope(const void* op, int tag, int dtype, int K, const int64_t* dims, int n, const int32_t* t1,
+                     int nt1, const int32_t* t2, int nt2, bool aliased, cudaStream_t stream) {
+  stream_ = stream;
+  if (!op || !dims || n < 1 || n > kMaxAxes || nt1 < 0 || nt1 > kMaxTargets || nt2 < 0 || nt2 > kMaxTargets) return;
+  std::lock_guard<std::mutex> lock(g_plan_mu);
+  if (g_pinned.find(op) == g_pinned.end()) return;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::string key((const char*)&op, sizeof(op));
+  const int64_t head[8] = {tag, dtype, K, n, nt1, nt2, aliased ? 1 : 0, dev};
+  key.append((const char*)head, sizeof(head));
+  const uint64_t epoch = g_options_epoch.load();
+  key.append((const char*)&epoch, sizeof(epoch));
+  key.append((const char*)dims, sizeof(int64_t) * n);
+  if (nt1) key.append((const char*)t1, sizeof(int32_t) * nt1);
+  if (nt2) key.append((const char*)t2, sizeof(int32_t) * nt2);
+  auto it = g_plans.find(key);
+  PlanCacheEntry* e;
+  if (it == g_plans.end()) {
+    e = new PlanCacheEntry();
+    e->fill_stream = stream;
+    g_plans[key] = e;
+  } else {
+    e = it->second;
+    if (!e->filled) return;   // another thread is recording it right now: run uncached
+  }
+  ctx.e = e;
+  ctx.replay = e->filled;
+  if (ctx.replay && stream != e->fill_stream && e->ready) cudaStreamWaitEvent(stream, e->ready, 0);
+  g_plan_ctx = &ctx;
+  active = true;
+}
+
+int PlanScope::finish(int rc) {
+  if (!active) return rc;
+  g_plan_ctx = nullptr;
+  active = false;
+  std::lock_guard<std::mutex> lock(g_plan_mu);
+  PlanCacheEntry* e = ctx.e;
+  if (!ctx.replay) {
+    if (rc == PW_OK && !ctx.broken) {
+      if (cudaEventCreateWithFlags(&e->ready, cudaEventDisableTiming) == cudaSuccess) cudaEventRecord(e->ready, stream_);
+      e->filled = true;
+    } else {
+      // a failed or unsupported recording is dropped (its buffers may still be in use by kernels
+      // already enqueued: cudaFree waits for them)
+      for (auto it = g_plans.begin(); it != g_plans.end(); ++it)
+        if (it->second == e) { g_plans.erase(it); break; }
+      free_entry(e);
+    }
+  }
+  return rc;
+}
+
+PlanScope::~PlanScope() {
+  if (active) finish(PW_ERR_INVALID);
+}
 
 std::atomic<uint64_t> g_launches{0};
 std::atomic<uint64_t> g_paths[5];
@@ -90,3 +169,29 @@ int build_plan_matrix(const int64_t* dims, int n, const int32_t* targets, int nt
 }
 
 }  // namespace pw
+
+using namespace pw;
+
+extern "C" int pw_op_pin(const void* op) {
+  if (!op) return PW_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(g_plan_mu);
+  g_pinned.insert(op);
+  return PW_OK;
+}
+
+extern "C" int pw_op_unpin(const void* op) {
+  if (!op) return PW_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(g_plan_mu);
+  g_pinned.erase(op);
+  for (auto it = g_plans.begin(); it != g_plans.end();) {
+    const void* k;
+    std::memcpy(&k, it->first.data(), sizeof(k));
+    if (k == op) { free_entry(it->second); it = g_plans.erase(it); } else ++it;
+  }
+  return PW_OK;
+}
+
+extern "C" int pw_plan_cache_size(void) {
+  std::lock_guard<std::mutex> lock(g_plan_mu);
+  return (int)g_plans.size();
+}

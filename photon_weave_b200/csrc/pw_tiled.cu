@@ -609,10 +609,12 @@ static int launch_tiled_t(const V* in, V* out, const V* ops, int K, const TiledG
   Scratch rowptr, ents, bmem0, bmem1;
   PW_TRY(rowptr.alloc(sizeof(int32_t) * (size_t)csrK * (t + 1), s));
   PW_TRY(ents.alloc(sizeof(Entry<V>) * (size_t)csrK * cap, s));
-  k_build_csr<V><<<csrK, 256, sizeof(int32_t) * (t + 1), s>>>(
-      csr_src, t, cap, g.kind[0], g.kind[g.nkinds > 1 ? 1 : 0], g.nkinds, (int32_t*)rowptr.p,
-      (Entry<V>*)ents.p, skip);
-  PW_LAUNCHED();
+  if (!plan_replay()) {
+    k_build_csr<V><<<csrK, 256, sizeof(int32_t) * (t + 1), s>>>(
+        csr_src, t, cap, g.kind[0], g.kind[g.nkinds > 1 ? 1 : 0], g.nkinds, (int32_t*)rowptr.p,
+        (Entry<V>*)ents.p, skip);
+    PW_LAUNCHED();
+  }
 
   TiledParams P;
   P.g = g;
@@ -679,6 +681,7 @@ int launch_tiled(const void* in, void* out, const void* ops, int K, const TiledG
 }
 
 int build_superoperator(const void* ops, int K, uint32_t t, void* S, int dtype, cudaStream_t s) {
+  if (plan_replay()) return PW_OK;   // cached plan: S is already built
   const uint64_t total = (uint64_t)t * t * t * t;
   if (dtype == PW_C128)
     k_build_super<double2><<<grid_for(total, 256, 8), 256, 0, s>>>((const double2*)ops, K, t, (double2*)S);

@@ -122,6 +122,9 @@ class Operation:
                 return _CACHE[key]
         pair = (host, dev.asarray(host))
         if key is not None:
+            # the cached device operator is immutable for as long as it lives: let libpwb200 keep
+            # its structure analysis (block structure, super-blocks, superoperator) across applies
+            dev.pin_operator(pair[1])
             if len(_CACHE) >= _CACHE_LIMIT:
                 _CACHE.pop(next(iter(_CACHE)))
             _CACHE[key] = pair

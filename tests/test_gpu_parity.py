@@ -938,3 +938,65 @@ def test_batched_jaynes_cummings_propagator_on_tensor_cores(ad):
     assert got.shape == (B, 128, 1)
     assert rel_err(got[:8], want) < 1e-12 and rel_err(got[-8:], want) < 1e-12
     assert launches <= 4
+
+
+def test_pinned_operator_plan_cache(ad):
+    """pw_op_pin: the device-side analysis of a pinned operator is recorded once per (operator,
+    dims, targets, dtype, aliasing) and replayed; results are bit-identical to the unpinned call
+    on every structured path (blocks, staged blocks, two-sided, super-blocks, superoperator, dense,
+    diagonal), across repeated calls, other streams, changed options and after unpinning."""
+    from photon_weave_b200 import _lib
+    from photon_weave_b200.core import ffi
+
+    lib = _lib.load()
+    _lib.set_option("blocks_min_elems", 0)
+    _lib.set_option("blocks_min_elems_small_t", 0)
+    try:
+        cases = [("vec", (6, 6, 50), (0, 1), ops.beam_splitter(6, 6, 0.7)),
+                 ("vec", (50, 6, 6), (1, 2), ops.beam_splitter(6, 6, 0.3)),
+                 ("vec", (6, 6, 50), (0, 1), ops.random_unitary(36, 3)),
+                 ("vec", (4, 6, 40), (1,), ops.phase_operator(6, 0.4)),
+                 ("mat", (8, 4, 10), (0,), ops.random_unitary(8, 5)),
+                 ("mat", (8, 8, 6), (0, 1), ops.beam_splitter(8, 8, 0.6)),
+                 ("mat", (6, 8, 8), (1, 2), ops.beam_splitter(8, 8, 0.2)),
+                 ("kraus", (5, 5, 12), (1,), ops.loss_channel(5, 0.1)),
+                 ("kraus", (12, 5), (1,), ops.loss_channel(5, 0.2)),
+                 ("kraus", (8, 10), (0,), np.stack([ops.random_unitary(8, 7 + k) for k in range(3)]) / np.sqrt(3))]
+        skipped = 0
+        for kind, dims, tg, op in cases:
+            N = math.prod(dims)
+            x = dev(ops.random_state(N, 1)).reshape(-1) if kind == "vec" else dev(ops.random_density(N, 2)).reshape(-1)
+            fn = {"vec": ffi.apply_vec, "mat": ffi.apply_mat, "kraus": ffi.kraus_mat}[kind]
+            plain = fn(x, dev(op), dims, tg)
+            d_op = dev(op)
+            before = lib.pw_plan_cache_size()
+            ffi.pin_operator(d_op)
+            first = fn(x, d_op, dims, tg)                       # records
+            assert lib.pw_plan_cache_size() == before + 1
+            n0 = lib.pw_launch_count()
+            again = fn(x, d_op, dims, tg)                       # replays
+            replay_launches = lib.pw_launch_count() - n0
+            n0 = lib.pw_launch_count()
+            fn(x, dev(op), dims, tg)
+            plain_launches = lib.pw_launch_count() - n0
+            assert replay_launches <= plain_launches, (kind, dims, tg)
+            skipped += plain_launches - replay_launches                             # analysis kernels
+            with torch.cuda.stream(torch.cuda.Stream()):
+                other_stream = fn(x, d_op, dims, tg)
+            torch.cuda.synchronize()
+            x2 = x * (0.5 + 0.25j)                               # other data, same plan
+            scaled = fn(x2, d_op, dims, tg)
+            for got in (first, again, other_stream):
+                assert torch.equal(got, plain), (kind, dims, tg)
+            assert torch.equal(scaled, fn(x2, dev(op), dims, tg))
+            _lib.set_option("seg_fpw", 0)                        # any option change: new epoch, re-recorded
+            assert torch.equal(fn(x, d_op, dims, tg), plain)
+            del d_op                                             # garbage collection unpins and frees
+            import gc
+
+            gc.collect()
+            assert lib.pw_plan_cache_size() == before
+        assert skipped >= 12
+    finally:
+        _lib.set_option("blocks_min_elems", 1 << 18)
+        _lib.set_option("blocks_min_elems_small_t", 1 << 22)

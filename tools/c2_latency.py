@@ -23,12 +23,19 @@ def bench(fn, n=500):
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
     return (time.perf_counter() - t0) / n * 1e6, e0.elapsed_time(e1) / n * 1e3
-for thr in (1 << 18, 1 << 20):
+for pin in (False, True):
+  if pin:
+    for t_ in (bs, loss, u):
+        ffi.pin_operator(t_)
+  print("pinned operators (analysis cached)" if pin else "unpinned operators", flush=True)
+  for thr in (1 << 18,):
     _lib.set_option("blocks_min_elems", thr)
-    for name, fn in [("bs(1,2)", lambda: ffi.apply_mat(rho, bs, dims, (1, 2), out=out)),
+    if True:
+     for name, fn in [("bs(1,2)", lambda: ffi.apply_mat(rho, bs, dims, (1, 2), out=out)),
                      ("bs(2,3)", lambda: ffi.apply_mat(rho, bs, dims, (2, 3), out=out)),
                      ("kraus K5 (2)", lambda: ffi.kraus_mat(rho, loss, dims, (2,), out=out)),
                      ("kraus K5 (3)", lambda: ffi.kraus_mat(rho, loss, dims, (3,), out=out)),
                      ("dense 5x5 (1)", lambda: ffi.apply_mat(rho, u, dims, (1,), out=out))]:
-        w, dv = bench(fn)
-        print(f"thr=2^{int(math.log2(thr))} {name:14s} wall {w:7.1f} us  device {dv:7.1f} us", flush=True)
+         pass
+         w, dv = bench(fn)
+         print(f"thr=2^{int(math.log2(thr))} {name:14s} wall {w:7.1f} us  device {dv:7.1f} us", flush=True)
