@@ -165,12 +165,30 @@ def check(status: int, what: str) -> None:
         raise PwError(f"{what}: {msg}{extra}")
 
 
+_I64_CACHE: dict = {}
+_I32_CACHE: dict = {}
+
+
 def i64_array(vals: Sequence[int]):
-    return (C.c_int64 * max(len(vals), 1))(*[int(v) for v in vals])
+    """ctypes int64 array of ``vals`` (read-only to the library: cached per value tuple -- the
+    per-call latency of the small configs is host-bound)."""
+    key = vals if type(vals) is tuple else tuple(int(v) for v in vals)
+    arr = _I64_CACHE.get(key)
+    if arr is None:
+        arr = (C.c_int64 * max(len(key), 1))(*[int(v) for v in key])
+        if len(_I64_CACHE) < 4096:
+            _I64_CACHE[key] = arr
+    return arr
 
 
 def i32_array(vals: Sequence[int]):
-    return (C.c_int32 * max(len(vals), 1))(*[int(v) for v in vals])
+    key = vals if type(vals) is tuple else tuple(int(v) for v in vals)
+    arr = _I32_CACHE.get(key)
+    if arr is None:
+        arr = (C.c_int32 * max(len(key), 1))(*[int(v) for v in key])
+        if len(_I32_CACHE) < 4096:
+            _I32_CACHE[key] = arr
+    return arr
 
 
 def path_counters() -> dict:

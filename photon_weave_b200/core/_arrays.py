@@ -35,7 +35,15 @@ def device() -> str:
     return "cuda"
 
 
+try:  # the raw handle of the current stream without building a torch.cuda.Stream object (~1 us)
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+except AttributeError:  # pragma: no cover
+    _raw_stream = None
+
+
 def stream_ptr() -> int:
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 

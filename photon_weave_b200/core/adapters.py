@@ -33,6 +33,15 @@ from . import transforms as T
 from .meta import DimsMeta
 
 
+from functools import lru_cache
+
+
+@lru_cache(maxsize=4096)
+def _geom(state_dims: Tuple[int, ...], target_indices: Tuple[int, ...]) -> Tuple[int, int]:
+    """(prod(dims), prod(target dims)) -- cached: the small configs are host-latency bound."""
+    return (int(math.prod(state_dims)), int(math.prod([state_dims[i] for i in target_indices])))
+
+
 def _rest(state_dims: Sequence[int], target_indices: Sequence[int]) -> List[int]:
     return [i for i in range(len(state_dims)) if i not in target_indices]
 
@@ -42,11 +51,16 @@ def _shape_of(x: Any) -> Tuple[int, ...]:
 
 
 def _size_of(x: Any) -> int:
+    if type(x) is torch.Tensor:
+        return x.numel()
     return int(math.prod(_shape_of(x)))
 
 
 def _prep(state: Any, *others: Any):
     """Move everything to the device in one common complex dtype."""
+    if type(state) is torch.Tensor and state.is_cuda and state.is_complex() and state.is_contiguous() and \
+            all(type(o) is torch.Tensor and o.is_cuda and o.dtype == state.dtype and o.is_contiguous() for o in others):
+        return False, state, list(others)   # the common case: nothing to move or promote
     A.require_cuda()
     host = A.is_host(state)
     st = A.to_device(state)
@@ -70,14 +84,13 @@ def apply_operation_vector(
     """core/adapters.py:299-345 -> (N, 1)."""
     target_indices = tuple(target_indices)
     state_dims = tuple(state_dims)
-    expected = int(math.prod(state_dims))
+    expected, target_dim = _geom(state_dims, target_indices)
     batch = T.current_batch()
     if _size_of(product_state) != expected * (batch or 1):
         raise ValueError(
             f"product_state has size {_size_of(product_state)}, expected {expected} "
             f"for dims {state_dims}"
         )
-    target_dim = int(math.prod([state_dims[i] for i in target_indices]))
     if _shape_of(operator) != (target_dim, target_dim):
         raise AssertionError(
             f"Operator shape {_shape_of(operator)} does not match expected "
