@@ -108,12 +108,37 @@ def _apply_rho(st, op, entry, prefer):
         st.apply_operation(op, entry[0], prefer_shard=prefer)
 
 
-def _layouts(cls, dims, world, modes):
+def _layouts(cls, dims, world, modes, layer=None):
+    """Layout A = the initial sharding (leading subsystems); layout B = the window of as many
+    subsystems that (i) shares no operation with A's and (ii) is touched by the FEWEST operations
+    of the layer, dependency closure included: those operations (stage S0 of run_layer) cannot
+    hide the swap, everything else local can."""
     vaxes, sparts = cls.initial_layout(dims, world)
     shard_a = sorted({s.g for s in sparts})
     k = max(len(shard_a), 1)
     mid = modes // 2
-    return vaxes, sparts, shard_a, list(range(mid, mid + k))
+    best = list(range(mid, mid + k))
+    if layer:
+        targets = [set(t) for t, _, _ in layer]
+
+        def cost(window):
+            w = set(window)
+            if w & set(shard_a) or any(t & w and t & set(shard_a) for t in targets):
+                return None
+            s0 = [bool(t & w) for t in targets]
+            for j in reversed(range(len(targets))):          # operations that must precede an S0 one
+                for i in range(j):
+                    if s0[j] and not s0[i] and targets[i] & targets[j] and not targets[i] & set(shard_a):
+                        s0[i] = True
+            return sum(s0)
+
+        # ties: the window nearest the front (sharding the innermost subsystems would shorten the
+        # contiguous runs every local kernel streams)
+        scored = [(cost(range(s, s + k)), s, list(range(s, s + k))) for s in range(k, modes - k + 1)]
+        scored = [x for x in scored if x[0] is not None]
+        if scored:
+            best = min(scored)[2]
+    return vaxes, sparts, shard_a, best
 
 
 def parity_preflight(dist, rank: int, world: int, local_rank: int, kind: str, make_layer: Callable,
@@ -132,7 +157,7 @@ def parity_preflight(dist, rank: int, world: int, local_rank: int, kind: str, ma
         cls, apply = ShardedDensityMatrix, _apply_rho
     layer = make_layer(modes, cutoff)
     full = random_input(kind, dims)                       # identical on every rank (seeded NumPy)
-    vaxes, sparts, shard_a, shard_b = _layouts(cls, dims, world, modes)
+    vaxes, sparts, shard_a, shard_b = _layouts(cls, dims, world, modes, layer)
     own = cls._own_block(dims if kind == "vec" else dims + dims, torch.as_tensor(full).reshape(-1),
                          sparts, rank).cuda()
     peers, impl = make_peers(own.numel(), 3, rank, world, dist, local_rank, want_peers)
@@ -295,7 +320,7 @@ def bench_sharded(args, dist, rank, world, local_rank, make_layer, workload_conf
     layer = make_layer(modes, cutoff)
     d_ops = _device_ops(layer)
     nops = len(layer)
-    vaxes, sparts, shard_a, shard_b = _layouts(ShardedStateVector, dims, world, modes)
+    vaxes, sparts, shard_a, shard_b = _layouts(ShardedStateVector, dims, world, modes, layer)
     n_local = N // world
     gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
     peers, swap_impl = make_peers(n_local, 3 if mode == "pipelined" else 2, rank, world, dist,
@@ -362,7 +387,7 @@ def bench_sharded_rho(args, dist, rank, world, local_rank, make_rho_layer, peaks
     layer = make_rho_layer(modes, cutoff)
     d_ops = _device_ops(layer)
     nops = len(layer)
-    vaxes, sparts, shard_a, shard_b = _layouts(ShardedDensityMatrix, dims, world, modes)
+    vaxes, sparts, shard_a, shard_b = _layouts(ShardedDensityMatrix, dims, world, modes, layer)
     n_local = D * D // world
     peers, swap_impl = make_peers(n_local, 3 if mode == "pipelined" else 2, rank, world, dist,
                                   local_rank, want_peers)
