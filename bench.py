@@ -803,8 +803,10 @@ def main():
     ap.add_argument("--modes", type=int, default=12)
     ap.add_argument("--cutoff", type=int, default=6)
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--e2e-pipeline-steps", type=int, default=6,
-                    help="steps of the streaming (pipelined) end-to-end measurement")
+    ap.add_argument("--e2e-pipeline-steps", type=int, default=16,
+                    help="steps (independent jobs) of the streaming end-to-end measurement; pipeline fill "
+                         "and drain (one upload + one download that overlap nothing) are inside the timed "
+                         "region, so fewer steps quote more of them per step")
     ap.add_argument("--no-pipeline", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")

@@ -26,7 +26,8 @@ def pin_operator(op: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     ptr = op.data_ptr()
     _lib.check(lib.pw_op_pin(ptr), "pw_op_pin")
-    weakref.finalize(op, lib.pw_op_unpin, ptr)
+    fin = weakref.finalize(op, lib.pw_op_unpin, ptr)
+    fin.atexit = False   # at interpreter exit the CUDA context may be gone already: nothing to free
     return op
 
 

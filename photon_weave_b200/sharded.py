@@ -382,7 +382,11 @@ class ShardedTensor:
 
     def _buffers(self) -> torch.Tensor:
         if self.spare is None or self.spare.numel() != self.local.numel():
-            self.spare = torch.empty_like(self.local)
+            if self.peers is not None and self.local.numel() == self.peers.numel:
+                # peer mode: every buffer a swap may read must be one of the IPC-exported ones
+                self.spare = next(t for t in self.peers.tensors if t.data_ptr() != self.local.data_ptr())
+            else:
+                self.spare = torch.empty_like(self.local)
         return self.spare
 
     def _barrier(self) -> None:
