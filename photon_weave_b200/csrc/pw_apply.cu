@@ -338,9 +338,15 @@ __global__ void k_target_offsets(const TargetMap tm, int64_t* toff) {
 // loads per fiber and is sensitive to the SM clock: 11.7 ms alone, 14.1 ms inside the
 // power-capped bench layer on the 34.8 GB vector.)
 // ---------------------------------------------------------------------------------
-template <bool CONJ>
+// S = float2 (complex64): same FP64 tensor-core product, values widened as they are loaded and
+// rounded as they are stored (half the bytes per DMMA: the kernel that is HBM-bound at 49 % DMMA
+// utilisation in complex128 becomes DMMA-bound near the complex64 HBM roof)
+__device__ __forceinline__ double2 cm_wide(const double2 v) { return v; }
+__device__ __forceinline__ double2 cm_wide(const float2 v) { return make_double2((double)v.x, (double)v.y); }
+
+template <bool CONJ, typename S>
 __global__ void __launch_bounds__(256)
-k_apply_contig_mma(const double2* __restrict__ in, double2* __restrict__ out, const double2* __restrict__ op,
+k_apply_contig_mma(const S* __restrict__ in, S* __restrict__ out, const S* __restrict__ op,
                    const int t, const uint64_t nfib, const int* __restrict__ skip) {
   using V = double2;
   if (skip && *skip) return;
@@ -349,8 +355,8 @@ k_apply_contig_mma(const double2* __restrict__ in, double2* __restrict__ out, co
   // B = W^T fragments: lane (k = tig, n = gid) holds W[gid][tig] and W[gid][4 + tig]
   V w0 = zero, w1 = zero;
   if (gid < t) {
-    if (tig < t) w0 = op[gid * t + tig];
-    if (4 + tig < t) w1 = op[gid * t + 4 + tig];
+    if (tig < t) w0 = cm_wide(op[gid * t + tig]);
+    if (4 + tig < t) w1 = cm_wide(op[gid * t + 4 + tig]);
     if (CONJ) { w0.y = -w0.y; w1.y = -w1.y; }
   }
   const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
@@ -360,9 +366,9 @@ k_apply_contig_mma(const double2* __restrict__ in, double2* __restrict__ out, co
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
       const uint64_t f = g * 32 + 8 * m + gid;
-      const V* src = in + f * t;
-      x0[m] = (f < nfib && tig < t) ? __ldcg(src + tig) : zero;
-      x1[m] = (f < nfib && 4 + tig < t) ? __ldcg(src + 4 + tig) : zero;
+      const S* src = in + f * t;
+      x0[m] = (f < nfib && tig < t) ? cm_wide(__ldcg(src + tig)) : zero;
+      x1[m] = (f < nfib && 4 + tig < t) ? cm_wide(__ldcg(src + 4 + tig)) : zero;
     }
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
@@ -376,13 +382,22 @@ k_apply_contig_mma(const double2* __restrict__ in, double2* __restrict__ out, co
       asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(re0), "+d"(re1) : "d"(-x1[m].y), "d"(w1.y));
       asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(im0), "+d"(im1) : "d"(x1[m].y), "d"(w1.x));
       const uint64_t f = g * 32 + 8 * m + gid;
-      V* dst = out + f * t + 2 * tig;
+      S* dst = out + f * t + 2 * tig;
       const bool ok0 = f < nfib && 2 * tig < t, ok1 = f < nfib && 2 * tig + 1 < t;
-      if (ok0 && ok1 && (reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
-        asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(dst), "d"(re0), "d"(im0), "d"(re1), "d"(im1) : "memory");
+      if constexpr (sizeof(S) == 16) {
+        if (ok0 && ok1 && (reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
+          asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(dst), "d"(re0), "d"(im0), "d"(re1), "d"(im1) : "memory");
+        } else {
+          if (ok0) __stcg((double2*)dst, make_double2(re0, im0));
+          if (ok1) __stcg((double2*)dst + 1, make_double2(re1, im1));
+        }
       } else {
-        if (ok0) __stcg(dst, make_double2(re0, im0));
-        if (ok1) __stcg(dst + 1, make_double2(re1, im1));
+        if (ok0 && ok1 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+          __stcg(reinterpret_cast<float4*>(dst), make_float4((float)re0, (float)im0, (float)re1, (float)im1));
+        } else {
+          if (ok0) __stcg((float2*)dst, make_float2((float)re0, (float)im0));
+          if (ok1) __stcg((float2*)dst + 1, make_float2((float)re1, (float)im1));
+        }
       }
     }
   }
@@ -397,11 +412,11 @@ static int launch_small(const V* in, V* out, const V* op, const Plan& p, bool co
   // array-of-contiguous-fibers layout: the warp-transposing variant keeps loads coalesced
   if (!acc && T >= 2 && p.fm.ng == 1 && p.fm.gstride[0] == (int64_t)T && p.N == p.fm.nfib * T &&
       p.fm.nfib >= 4096 && options().contig_kernel.load(std::memory_order_relaxed)) {
-    if (sizeof(V) == 16 && T >= 5 && p.tm.nt == 1 && in != out &&
-        options().contig_mma.load(std::memory_order_relaxed)) {
+    if (T >= 5 && p.tm.nt == 1 && in != out && options().contig_mma.load(std::memory_order_relaxed) &&
+        (sizeof(V) == 16 || options().ts_mma_c64.load(std::memory_order_relaxed))) {
       const int g3 = grid_for((p.fm.nfib + 31) / 32 * 32, block, 8);
-      if (conj_op) k_apply_contig_mma<true><<<g3, block, 0, s>>>((const double2*)in, (double2*)out, (const double2*)op, T, p.fm.nfib, skip);
-      else         k_apply_contig_mma<false><<<g3, block, 0, s>>>((const double2*)in, (double2*)out, (const double2*)op, T, p.fm.nfib, skip);
+      if (conj_op) k_apply_contig_mma<true, V><<<g3, block, 0, s>>>(in, out, op, T, p.fm.nfib, skip);
+      else         k_apply_contig_mma<false, V><<<g3, block, 0, s>>>(in, out, op, T, p.fm.nfib, skip);
       PW_LAUNCHED();
       return PW_OK;
     }

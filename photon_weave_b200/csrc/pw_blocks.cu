@@ -635,7 +635,7 @@ k_ts_build(const BlockArrays L, const BlockArrays R, const int* __restrict__ oth
     //  5..8-level column target with whole chunks of 32 fibers next to it -> 32-fiber tiles)
     if (inner) {
       if (mma && hl->nblocks == 1 && (inner & 2)) mma = 1;
-      else if (mma && mma_ok >= 2 && nsb <= kTwMaxSb && hr->inplace_safe) mma = 2;  // (row tiles: complex128 only)
+      else if (mma && nsb <= kTwMaxSb && hr->inplace_safe) mma = 2;
       else h = 0;
     }
     if (!h) mma = 0;
@@ -1187,16 +1187,17 @@ constexpr int kTnBufs = 3;
 // the last two modes is one segment (lseg = t); on modes (4, 0) it is eight segments of eight.
 struct TnSeg { int lseg, nseg; int64_t seg_off[64]; };
 
+template <typename S>
 __global__ void __launch_bounds__(kTnWarps * 32, 2)
-k_two_sided_mma_rows(const double2* __restrict__ in, double2* __restrict__ out, const FiberMap fm,
+k_two_sided_mma_rows(const S* __restrict__ in, S* __restrict__ out, const FiberMap fm,
                      const TsTables T, const int t, const int order, const TnSeg seg) {
   using V = double2;
   if (!T.flags->handled || T.flags->use_mma != 2) return;
   extern __shared__ __align__(16) unsigned char s_raw[];
   __shared__ int64_t s_seg[64];
   if (threadIdx.x < 64) s_seg[threadIdx.x] = threadIdx.x < seg.nseg ? seg.seg_off[threadIdx.x] : 0;
-  V* tile0 = (V*)s_raw;                                       // [kTnBufs][8][kTnRow]
-  V* s_w = tile0 + kTnBufs * 8 * kTnRow;                      // [kTwMaxSb][64] column-side operands (swizzled)
+  S* tile0 = (S*)s_raw;                                       // [kTnBufs][8][kTnRow]
+  V* s_w = (V*)(tile0 + kTnBufs * 8 * kTnRow);                // [kTwMaxSb][64] column-side operands (swizzled)
   int64_t* s_roff = (int64_t*)(s_w + kTwMaxSb * 64);          // [2][kTwMaxSb][8] row offsets: in, out
   TwMeta* s_meta = (TwMeta*)(s_roff + 2 * kTwMaxSb * 8);      // [kTnBufs]
   int* s_cpos = (int*)(s_meta + kTnBufs);                     // [2][kTwMaxSb][8] column positions: in, out
@@ -1205,7 +1206,7 @@ k_two_sided_mma_rows(const double2* __restrict__ in, double2* __restrict__ out, 
   const int gid = lane >> 2, tig = lane & 3;
   const int nsb = T.flags->nsb;
   for (int i = threadIdx.x; i < kTwMaxSb * 64; i += blockDim.x)
-    s_w[i ^ (((i >> 3) & 1) << 2)] = ((const V*)T.sb_w)[kTsMaxSb * 64 + i];
+    s_w[i ^ (((i >> 3) & 1) << 2)] = ts_ld((const S*)T.sb_w + kTsMaxSb * 64 + i);
   for (int i = threadIdx.x; i < 2 * kTwMaxSb * 8; i += blockDim.x) {
     const int which = i / (kTwMaxSb * 8), r = i - which * (kTwMaxSb * 8);
     s_roff[i] = T.sb_off[(2 * which) * kTsMaxSb * 8 + r];
@@ -1227,7 +1228,7 @@ k_two_sided_mma_rows(const double2* __restrict__ in, double2* __restrict__ out, 
   const uint32_t cpr = (gl + F - 1) / F;
   const uint32_t chunks = (uint32_t)(fm.nfib / gl) * cpr;
   const uint32_t units = chunks * (uint32_t)nsb;
-  const V* wl_tab = (const V*)T.sb_w;          // row-side operands (global, L1 resident)
+  const S* wl_tab = (const S*)T.sb_w;          // row-side operands (global, L1 resident)
 
   auto sig = [](int a) { return (2 * (a & 3)) ^ (a & 4); };
 
@@ -1242,7 +1243,7 @@ k_two_sided_mma_rows(const double2* __restrict__ in, double2* __restrict__ out, 
       const int64_t base0 = fm.base((uint64_t)o * gl + f0);
       if (threadIdx.x == 0) { s_meta[buf].base0 = base0; s_meta[buf].K = (int)K; s_meta[buf].nvalid = nvalid; }
       const int nK = s_n[K];
-      V* tile = tile0 + (size_t)buf * 8 * kTnRow;
+      S* tile = tile0 + (size_t)buf * 8 * kTnRow;
       const int64_t* ro = rin + K * 8;
       // per segment the F fibers x lseg positions are one contiguous piece
       const int rowlen = nvalid * lseg;
@@ -1250,9 +1251,9 @@ k_two_sided_mma_rows(const double2* __restrict__ in, double2* __restrict__ out, 
         const int sg = nseg == 1 ? 0 : idx / rowlen;
         const int e = idx - sg * rowlen;
         const int f = (int)__umulhi((uint32_t)e, inv_l), j = sg * lseg + (e - f * lseg);
-        V* dst = tile + f * tp;
-        const V* src = in + base0 + s_seg[sg] + e;
-        for (int a = 0; a < nK; ++a) cp_async16(dst + a * kTnRow + (j ^ sig(a)), src + ro[a]);
+        S* dst = tile + f * tp;
+        const S* src = in + base0 + s_seg[sg] + e;
+        for (int a = 0; a < nK; ++a) ts_cp(dst + a * kTnRow + (j ^ sig(a)), src + ro[a]);
       }
     }
     cp_async_commit();
@@ -1274,13 +1275,13 @@ k_two_sided_mma_rows(const double2* __restrict__ in, double2* __restrict__ out, 
   issue(u, 0);
   issue(u + g, 1);
   for (; u < units; u += g) {
-    V* tile = tile0 + (size_t)cur * 8 * kTnRow;
+    S* tile = tile0 + (size_t)cur * 8 * kTnRow;
     cp_async_wait<1>();
     __syncthreads();  // A: tile `cur` is resident; the previous tile has been copied out
     issue(u + 2 * g, cur == 0 ? kTnBufs - 1 : cur - 1);
     const TwMeta meta = s_meta[cur];
     const int K = meta.K, nK = s_n[K];
-    const V l0 = __ldg(wl_tab + K * 64 + gid * 8 + tig), l1 = __ldg(wl_tab + K * 64 + gid * 8 + 4 + tig);
+    const V l0 = ts_ldg(wl_tab + K * 64 + gid * 8 + tig), l1 = ts_ldg(wl_tab + K * 64 + gid * 8 + 4 + tig);
     // The two sides commute: the COLUMN side runs first, in place, so that the row side can
     // stream its accumulators straight to HBM -- a lane owns positions 8 q + 2 tig and + 1 of one
     // output row (one full 32-byte sector, a quarter warp one full 128-byte line).  Four items per
@@ -1305,9 +1306,9 @@ k_two_sided_mma_rows(const double2* __restrict__ in, double2* __restrict__ out, 
       V x0[kB], x1[kB], y0[kB], y1[kB];
 #pragma unroll
       for (int b = 0; b < kB; ++b) {
-        const V* fib = tile + (f0 + b) * tp;
-        x0[b] = (tig < nL && f0 + b < F) ? fib[c0] : zero;
-        x1[b] = (4 + tig < nL && f0 + b < F) ? fib[c1] : zero;
+        const S* fib = tile + (f0 + b) * tp;
+        x0[b] = (tig < nL && f0 + b < F) ? ts_ld(fib + c0) : zero;
+        x1[b] = (4 + tig < nL && f0 + b < F) ? ts_ld(fib + c1) : zero;
       }
       cmma_batch<kB, true>(&r0, &r1, x0, x1, y0, y1);
       __syncwarp();
@@ -1315,16 +1316,16 @@ k_two_sided_mma_rows(const double2* __restrict__ in, double2* __restrict__ out, 
 #pragma unroll
         for (int b = 0; b < kB; ++b)
           if (f0 + b < F) {
-            V* fib = tile + (f0 + b) * tp;
-            fib[wa] = y0[b];
-            fib[wb] = y1[b];
+            S* fib = tile + (f0 + b) * tp;
+            ts_st(fib + wa, y0[b]);
+            ts_st(fib + wb, y1[b]);
           }
       }
     }
     __syncthreads();  // B
     // stage 2 (row side): (fiber f, position octet q), rows mixed, streamed to HBM
     const int n1 = F * nq;
-    V* orow = out + meta.base0 + rout[K * 8 + (gid < nK ? gid : 0)];
+    S* orow = out + meta.base0 + rout[K * 8 + (gid < nK ? gid : 0)];
     for (int it0 = warp; it0 < n1; it0 += kB * kTnWarps) {
       int fq[kB];
       V x0[kB], x1[kB], y0[kB], y1[kB];
@@ -1333,10 +1334,10 @@ k_two_sided_mma_rows(const double2* __restrict__ in, double2* __restrict__ out, 
         const int it = it0 + b * kTnWarps;
         const int itc = it < n1 ? it : it0;
         const int f = (int)(((uint32_t)itc * inv_nq) >> 16), q = itc - f * nq;
-        const V* col = tile + f * tp + 8 * q;
+        const S* col = tile + f * tp + 8 * q;
         fq[b] = it < n1 ? (f << 8) | q : -1;
-        x0[b] = (tig < nK && it < n1) ? col[rd1a] : zero;
-        x1[b] = (4 + tig < nK && it < n1) ? col[rd1b] : zero;
+        x0[b] = (tig < nK && it < n1) ? ts_ld(col + rd1a) : zero;
+        x1[b] = (4 + tig < nK && it < n1) ? ts_ld(col + rd1b) : zero;
       }
 #ifdef PW_TS_ABLATE  // ts_order bit 4 = no row-side arithmetic (copies the inputs)
       if (order & 4) {
@@ -1352,7 +1353,7 @@ k_two_sided_mma_rows(const double2* __restrict__ in, double2* __restrict__ out, 
           const int f = fq[b] >> 8, j = 8 * (fq[b] & 255) + 2 * tig;
           if (f >= meta.nvalid) continue;
           const int sg0 = (int)__umulhi((uint32_t)j, inv_l), sg1 = (int)__umulhi((uint32_t)(j + 1), inv_l);
-          V* dst = orow + (int64_t)f * lseg;
+          S* dst = orow + (int64_t)f * lseg;
           st_pair(dst + s_seg[sg0] + (j - sg0 * lseg), dst + s_seg[sg1] + (j + 1 - sg1 * lseg), y0[b], y1[b],
                   j < t, j + 1 < t);
         }
@@ -1396,13 +1397,12 @@ static int launch_two_sided_t(const V* rho, V* out, const V* op, const FiberMap&
   T.sb_w = sbb + b_sbn + b_sbblk + b_sboff;
   // (the tensor-core kernels index their units with 32 bits)
   // complex64: the same FP64 tensor-core kernel with float2 storage (values widened per fragment);
-  // the row-tile variant exists for complex128 only
   const bool c128 = sizeof(V) == 16;
   const bool mma_ok = options().ts_mma.load(std::memory_order_relaxed) && fm.nfib < (1ull << 28) &&
                       (c128 || options().ts_mma_c64.load(std::memory_order_relaxed));
   if (inner && !mma_ok) return PW_ERR_UNSUPPORTED;
   if (!plan_replay()) {
-    k_ts_build<V><<<1, 256, 0, s>>>(ts->L, ts->R, other, T, kTsValCap, mma_ok ? (c128 ? 2 : 1) : 0, inner);
+    k_ts_build<V><<<1, 256, 0, s>>>(ts->L, ts->R, other, T, kTsValCap, mma_ok ? 1 : 0, inner);
     PW_LAUNCHED();
   }
   const size_t smem = 2 * kTsValCap + sizeof(V) * 2 * kTsSlots * 32;
@@ -1433,18 +1433,20 @@ static int launch_two_sided_t(const V* rho, V* out, const V* op, const FiberMap&
     }
     k_two_sided_mma<V><<<grid, kTsWarps * 32, smem_mma, s>>>(rho, out, fm, T, inner ? 1 : 0,
                                                           options().ts_order.load(std::memory_order_relaxed));
-    if (inner && c128) {
+    if (inner) {
       PW_LAUNCHED();
       static bool attr_rows = false;
-      const size_t smem_rows = sizeof(double2) * (kTnBufs * 8 * kTnRow + kTwMaxSb * 64) +
-                               sizeof(int64_t) * 2 * kTwMaxSb * 8 + sizeof(TwMeta) * kTnBufs +
-                               sizeof(int) * (2 * kTwMaxSb * 8 + kTwMaxSb);
+      auto rows_smem = [](size_t es) {
+        return es * (size_t)(kTnBufs * 8 * kTnRow) + sizeof(double2) * (size_t)(kTwMaxSb * 64) +
+               sizeof(int64_t) * 2 * kTwMaxSb * 8 + sizeof(TwMeta) * kTnBufs + sizeof(int) * (2 * kTwMaxSb * 8 + kTwMaxSb);
+      };
       if (!attr_rows) {
-        PW_CUDA(cudaFuncSetAttribute(k_two_sided_mma_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+        PW_CUDA(cudaFuncSetAttribute(k_two_sided_mma_rows<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem(16)));
+        PW_CUDA(cudaFuncSetAttribute(k_two_sided_mma_rows<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem(8)));
         attr_rows = true;
       }
-      k_two_sided_mma_rows<<<2 * kNumSMs, kTnWarps * 32, smem_rows, s>>>((const double2*)rho, (double2*)out, fm, T, (int)cols.t,
-                                                                      options().ts_order.load(std::memory_order_relaxed), seg);
+      k_two_sided_mma_rows<V><<<2 * kNumSMs, kTnWarps * 32, rows_smem(sizeof(V)), s>>>(rho, out, fm, T, (int)cols.t,
+                                                                                   options().ts_order.load(std::memory_order_relaxed), seg);
     }
   }
   PW_LAUNCHED();
