@@ -412,8 +412,10 @@ static int launch_small(const V* in, V* out, const V* op, const Plan& p, bool co
   // array-of-contiguous-fibers layout: the warp-transposing variant keeps loads coalesced
   if (!acc && T >= 2 && p.fm.ng == 1 && p.fm.gstride[0] == (int64_t)T && p.N == p.fm.nfib * T &&
       p.fm.nfib >= 4096 && options().contig_kernel.load(std::memory_order_relaxed)) {
+    // (complex64 through this kernel measured SLOWER than the warp-transposing register kernel:
+    //  8.46 against 7.85 ms on the 17.4 GB vector; it stays available as contig_mma = 2)
     if (T >= 5 && p.tm.nt == 1 && in != out && options().contig_mma.load(std::memory_order_relaxed) &&
-        (sizeof(V) == 16 || options().ts_mma_c64.load(std::memory_order_relaxed))) {
+        (sizeof(V) == 16 || options().contig_mma.load(std::memory_order_relaxed) >= 2)) {
       const int g3 = grid_for((p.fm.nfib + 31) / 32 * 32, block, 8);
       if (conj_op) k_apply_contig_mma<true, V><<<g3, block, 0, s>>>(in, out, op, T, p.fm.nfib, skip);
       else         k_apply_contig_mma<false, V><<<g3, block, 0, s>>>(in, out, op, T, p.fm.nfib, skip);

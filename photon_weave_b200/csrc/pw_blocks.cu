@@ -1473,7 +1473,9 @@ int launch_two_sided(const void* rho, void* out, const void* op, const FiberMap&
     // must fill the innermost run exactly (lseg positions); the other column targets enumerate
     // segments (tensor order, last fastest)
     const int64_t L = fm.gstride[fm.ng - 1];
-    if (dtype != PW_C128 || cols.t < 5 || cols.t > 64 || fm.nfib >= (1ull << 28)) return PW_ERR_UNSUPPORTED;
+    if ((dtype != PW_C128 && !options().ts_mma_c64.load(std::memory_order_relaxed)) || cols.t < 5 || cols.t > 64 ||
+        fm.nfib >= (1ull << 28))
+      return PW_ERR_UNSUPPORTED;
     int64_t prod_in = 1;
     int outer[kMaxTargets], n_out = 0;
     for (int k = 0; k < cols.nt; ++k) {
