@@ -19,6 +19,8 @@
 #include "pw_internal.cuh"
 #include "pw_blocks.cuh"
 
+#include <type_traits>
+
 namespace pw {
 
 // ---- preparation ---------------------------------------------------------------------
@@ -901,6 +903,92 @@ __device__ __forceinline__ int ts_sigma(const int f, const int a) {
 // rounded when a result is written back (the tile and the intermediate U rho live in float2, like
 // every intermediate of the reference's complex64 path), so the kernel moves half the bytes with
 // the same DMMA count -- complex64 leaves the FMA pipe (33-42 % of the HBM roof) for this path.
+// ---- complex64 on the TF32 tensor cores, error-compensated (3 x TF32) ---------------------------
+// The FP64 tensor-core path gives complex64 the complex128 TIMES (it is DMMA-bound: 37 TFLOP/s
+// measured), i.e. 35-46 % of the complex64 HBM roof.  mma.sync.m16n8k8 TF32 runs at 279 TFLOP/s
+// (measured); splitting every operand into hi + lo TF32 parts and accumulating
+// a_lo b_hi + a_hi b_lo + a_hi b_hi in FP32 keeps ~2^-21 relative accuracy (complex64 tolerance:
+// 1e-5) at a third of that rate -- still 2.5x the FP64 tensor cores.  The fragment conventions
+// coincide with the complex FP64 product: with A = [Wr; Wi] (16 x 8) the registers a0..a3 of
+// lane (gid, tig) are exactly (w0.x, w0.y, w1.x, w1.y), B = Xr is (x0.x, x1.x), and the
+// accumulators c0..c3 are (Yr[gid][2 tig], Yr[gid][2 tig + 1], Yi[..], Yi[..]): a second MMA with
+// A = [-Wi; Wr], B = Xi completes the complex product -- 2 MMAs instead of 8 DMMAs.
+__device__ __forceinline__ uint32_t tf32_of(const float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+struct Tf2 { uint32_t hi, lo; };
+__device__ __forceinline__ Tf2 tf_split(const float x) {
+  Tf2 r;
+  r.hi = tf32_of(x);
+  r.lo = tf32_of(x - __uint_as_float(r.hi));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float& c0, float& c1, float& c2, float& c3, const uint32_t a0,
+                                         const uint32_t a1, const uint32_t a2, const uint32_t a3,
+                                         const uint32_t b0, const uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// operand fragment of a complex 8 x 8 matrix, pre-split: [re; im] rows and [-im; re] rows
+struct TfW {
+  Tf2 re0, im0, re1, im1, nim0, nim1;   // w0.x, w0.y, w1.x, w1.y, -w0.y, -w1.y
+};
+__device__ __forceinline__ TfW tf_w(const float2 w0, const float2 w1) {
+  TfW r;
+  r.re0 = tf_split(w0.x); r.im0 = tf_split(w0.y); r.re1 = tf_split(w1.x); r.im1 = tf_split(w1.y);
+  r.nim0 = tf_split(-w0.y); r.nim1 = tf_split(-w1.y);
+  return r;
+}
+// Y = W X (complex 8 x 8 times 8 x 8): lane (gid, tig) holds W[gid][tig], W[gid][4 + tig] (in w),
+// x0 = X[tig][n = gid], x1 = X[4 + tig][gid]; y0 = Y[gid][2 tig], y1 = Y[gid][2 tig + 1]
+__device__ __forceinline__ void cprod_tf32(const TfW& w, const float2 x0, const float2 x1, float2& y0, float2& y1) {
+  const Tf2 xr0 = tf_split(x0.x), xr1 = tf_split(x1.x), xi0 = tf_split(x0.y), xi1 = tf_split(x1.y);
+  float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+  // small terms first
+  mma_tf32(c0, c1, c2, c3, w.re0.lo, w.im0.lo, w.re1.lo, w.im1.lo, xr0.hi, xr1.hi);
+  mma_tf32(c0, c1, c2, c3, w.nim0.lo, w.re0.lo, w.nim1.lo, w.re1.lo, xi0.hi, xi1.hi);
+  mma_tf32(c0, c1, c2, c3, w.re0.hi, w.im0.hi, w.re1.hi, w.im1.hi, xr0.lo, xr1.lo);
+  mma_tf32(c0, c1, c2, c3, w.nim0.hi, w.re0.hi, w.nim1.hi, w.re1.hi, xi0.lo, xi1.lo);
+  mma_tf32(c0, c1, c2, c3, w.re0.hi, w.im0.hi, w.re1.hi, w.im1.hi, xr0.hi, xr1.hi);
+  mma_tf32(c0, c1, c2, c3, w.nim0.hi, w.re0.hi, w.nim1.hi, w.re1.hi, xi0.hi, xi1.hi);
+  y0 = make_float2(c0, c2);
+  y1 = make_float2(c1, c3);
+}
+// the TRANSPOSED product Y^T = X^T W^T: A = [Xr^T; Xi^T] (fibers x inputs, real rows then
+// imaginary rows), B = Wr^T, then B = Wi^T.  Lane (gid, tig): x0 = X^T[fiber gid][tig],
+// x1 = X^T[gid][4 + tig]; w0 = W[gid][tig] = W^T[tig][gid], w1 = W[gid][4 + tig];
+// y0 = Y^T[fiber gid][2 tig], y1 = Y^T[gid][2 tig + 1].
+__device__ __forceinline__ void cprod_tf32_t(const TfW& w, const float2 x0, const float2 x1, float2& y0, float2& y1) {
+  const Tf2 xr0 = tf_split(x0.x), xr1 = tf_split(x1.x), xi0 = tf_split(x0.y), xi1 = tf_split(x1.y);
+  float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;   // [Xr Wr^T; Xi Wr^T]
+  float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;   // [Xr Wi^T; Xi Wi^T]
+  mma_tf32(p0, p1, p2, p3, xr0.lo, xi0.lo, xr1.lo, xi1.lo, w.re0.hi, w.re1.hi);
+  mma_tf32(q0, q1, q2, q3, xr0.lo, xi0.lo, xr1.lo, xi1.lo, w.im0.hi, w.im1.hi);
+  mma_tf32(p0, p1, p2, p3, xr0.hi, xi0.hi, xr1.hi, xi1.hi, w.re0.lo, w.re1.lo);
+  mma_tf32(q0, q1, q2, q3, xr0.hi, xi0.hi, xr1.hi, xi1.hi, w.im0.lo, w.im1.lo);
+  mma_tf32(p0, p1, p2, p3, xr0.hi, xi0.hi, xr1.hi, xi1.hi, w.re0.hi, w.re1.hi);
+  mma_tf32(q0, q1, q2, q3, xr0.hi, xi0.hi, xr1.hi, xi1.hi, w.im0.hi, w.im1.hi);
+  y0 = make_float2(p0 - q2, q0 + p2);   // Yr = Xr Wr^T - Xi Wi^T, Yi = Xr Wi^T + Xi Wr^T
+  y1 = make_float2(p1 - q3, q1 + p3);
+}
+
+// compute type of a storage type: complex64 tiles are multiplied in TF32 x 3 (TF) or widened to FP64
+template <typename S, bool TF> struct TsCompute { using V = double2; };
+template <> struct TsCompute<float2, true> { using V = float2; };
+template <typename V> __device__ __forceinline__ V ts_ldv(const double2* p);
+template <> __device__ __forceinline__ double2 ts_ldv<double2>(const double2* p) { return *p; }
+template <typename V> __device__ __forceinline__ V ts_ldv(const float2* p);
+template <> __device__ __forceinline__ double2 ts_ldv<double2>(const float2* p) { const float2 v = *p; return make_double2((double)v.x, (double)v.y); }
+template <> __device__ __forceinline__ float2 ts_ldv<float2>(const float2* p) { return *p; }
+template <typename V> __device__ __forceinline__ V ts_ldgv(const double2* p);
+template <> __device__ __forceinline__ double2 ts_ldgv<double2>(const double2* p) { return __ldg(p); }
+template <typename V> __device__ __forceinline__ V ts_ldgv(const float2* p);
+template <> __device__ __forceinline__ double2 ts_ldgv<double2>(const float2* p) { const float2 v = __ldg(p); return make_double2((double)v.x, (double)v.y); }
+template <> __device__ __forceinline__ float2 ts_ldgv<float2>(const float2* p) { return __ldg(p); }
+__device__ __forceinline__ void ts_st(float2* p, const float2 v) { *p = v; }
+
 __device__ __forceinline__ double2 ts_ld(const double2* p) { return *p; }
 __device__ __forceinline__ double2 ts_ld(const float2* p) { const float2 v = *p; return make_double2((double)v.x, (double)v.y); }
 __device__ __forceinline__ double2 ts_ldg(const double2* p) { return __ldg(p); }
@@ -909,9 +997,8 @@ __device__ __forceinline__ void ts_st(double2* p, const double2 v) { *p = v; }
 __device__ __forceinline__ void ts_st(float2* p, const double2 v) { *p = make_float2((float)v.x, (float)v.y); }
 __device__ __forceinline__ void ts_cp(double2* smem_dst, const double2* gsrc) { cp_async16(smem_dst, gsrc); }
 __device__ __forceinline__ void ts_cp(float2* smem_dst, const float2* gsrc) { cp_async8(smem_dst, gsrc); }
-__device__ __forceinline__ void st_pair(float2* p0, float2* p1, const double2 v0, const double2 v1,
+__device__ __forceinline__ void st_pair(float2* p0, float2* p1, const float2 f0, const float2 f1,
                                         const bool ok0, const bool ok1) {
-  const float2 f0 = make_float2((float)v0.x, (float)v0.y), f1 = make_float2((float)v1.x, (float)v1.y);
   if (ok0 && ok1 && p1 == p0 + 1 && (reinterpret_cast<uintptr_t>(p0) & 15) == 0) {
     __stcg(reinterpret_cast<float4*>(p0), make_float4(f0.x, f0.y, f1.x, f1.y));
   } else {
@@ -919,12 +1006,17 @@ __device__ __forceinline__ void st_pair(float2* p0, float2* p1, const double2 v0
     if (ok1) __stcg(p1, f1);
   }
 }
+__device__ __forceinline__ void st_pair(float2* p0, float2* p1, const double2 v0, const double2 v1,
+                                        const bool ok0, const bool ok1) {
+  st_pair(p0, p1, make_float2((float)v0.x, (float)v0.y), make_float2((float)v1.x, (float)v1.y), ok0, ok1);
+}
 
-template <bool MULTI, bool INNER, typename S>
+template <bool MULTI, bool INNER, typename S, bool TF>
 __device__ __forceinline__ void two_sided_mma_body(const S* __restrict__ in, S* __restrict__ out,
                                                    const FiberMap& fm, const TsTables& T,
                                                    unsigned char* s_raw, const int order) {
-  using V = double2;
+  using V = typename TsCompute<S, TF>::V;   // float2: TF32 x 3 products; double2: FP64 tensor cores
+  constexpr bool kTf = sizeof(V) == 8;
   constexpr bool inner = INNER;
   S* tile0 = (S*)s_raw;                                          // [3][kTsSlots][32], swizzled
   int64_t* s_base = (int64_t*)(tile0 + 3 * kTsSlots * 32);       // [3][32] fiber bases (-1: past the end)
@@ -1021,22 +1113,37 @@ __device__ __forceinline__ void two_sided_mma_body(const S* __restrict__ in, S* 
   //  octet nt; the step-major batch of cmma_batch measured 20 % slower HERE, 6 % faster in the
   //  row-tile kernel)
   auto product = [&](const V w0, const V w1, const int nx, auto ldx, auto sty) {
+    if constexpr (kTf) {
+      const TfW w = tf_w(w0, w1);
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const int f = 8 * nt + gid;
-      V x0 = make_double2(0.0, 0.0), x1 = x0;
-      if (tig < nx) x0 = ldx(tig, f);
-      if (4 + tig < nx) x1 = ldx(4 + tig, f);
-      double re0 = 0.0, re1 = 0.0, im0 = 0.0, im1 = 0.0;
-      dmma8x8x4(re0, re1, w0.x, x0.x);
-      dmma8x8x4(im0, im1, w0.y, x0.x);
-      dmma8x8x4(re0, re1, -w0.y, x0.y);
-      dmma8x8x4(im0, im1, w0.x, x0.y);
-      dmma8x8x4(re0, re1, w1.x, x1.x);
-      dmma8x8x4(im0, im1, w1.y, x1.x);
-      dmma8x8x4(re0, re1, -w1.y, x1.y);
-      dmma8x8x4(im0, im1, w1.x, x1.y);
-      sty(nt, 8 * nt + 2 * tig, make_double2(re0, im0), make_double2(re1, im1));
+      for (int nt = 0; nt < 4; ++nt) {
+        const int f = 8 * nt + gid;
+        V x0 = czero<V>(), x1 = x0, y0, y1;
+        if (tig < nx) x0 = ldx(tig, f);
+        if (4 + tig < nx) x1 = ldx(4 + tig, f);
+        cprod_tf32(w, x0, x1, y0, y1);
+        sty(nt, 8 * nt + 2 * tig, y0, y1);
+      }
+    } else {
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int f = 8 * nt + gid;
+        V x0 = czero<V>(), x1 = x0;
+        if (tig < nx) x0 = ldx(tig, f);
+        if (4 + tig < nx) x1 = ldx(4 + tig, f);
+        double re0 = 0.0, re1 = 0.0, im0 = 0.0, im1 = 0.0;
+        dmma8x8x4(re0, re1, w0.x, x0.x);
+        dmma8x8x4(im0, im1, w0.y, x0.x);
+        dmma8x8x4(re0, re1, -w0.y, x0.y);
+        dmma8x8x4(im0, im1, w0.x, x0.y);
+        dmma8x8x4(re0, re1, w1.x, x1.x);
+        dmma8x8x4(im0, im1, w1.y, x1.x);
+        dmma8x8x4(re0, re1, -w1.y, x1.y);
+        dmma8x8x4(im0, im1, w1.x, x1.y);
+        V v0, v1;
+        v0.x = re0; v0.y = im0; v1.x = re1; v1.y = im1;
+        sty(nt, 8 * nt + 2 * tig, v0, v1);
+      }
     }
   };
 
@@ -1045,8 +1152,8 @@ __device__ __forceinline__ void two_sided_mma_body(const S* __restrict__ in, S* 
   issue(u, 0);
   issue(u + gridDim.x, 1);
   // operand fragments (zero padded to 8 x 8): per unit, or once for a single super-block
-  V l0 = ts_ldg(wtab + gid * 8 + tig), l1 = ts_ldg(wtab + gid * 8 + 4 + tig);
-  V r0 = ts_ldg(wtab + kTsMaxSb * 64 + gid * 8 + tig), r1 = ts_ldg(wtab + kTsMaxSb * 64 + gid * 8 + 4 + tig);
+  V l0 = ts_ldgv<V>(wtab + gid * 8 + tig), l1 = ts_ldgv<V>(wtab + gid * 8 + 4 + tig);
+  V r0 = ts_ldgv<V>(wtab + kTsMaxSb * 64 + gid * 8 + tig), r1 = ts_ldgv<V>(wtab + kTsMaxSb * 64 + gid * 8 + 4 + tig);
   for (; u < units; u += gridDim.x) {
     S* tile = tile0 + (size_t)cur * kTsSlots * 32;
     uint32_t K, L;
@@ -1056,7 +1163,7 @@ __device__ __forceinline__ void two_sided_mma_body(const S* __restrict__ in, S* 
     if (MULTI) {
       const S* wl = wtab + (size_t)K * 64 + gid * 8 + tig;
       const S* wr = wtab + (size_t)(kTsMaxSb + L) * 64 + gid * 8 + tig;
-      l0 = ts_ldg(wl); l1 = ts_ldg(wl + 4); r0 = ts_ldg(wr); r1 = ts_ldg(wr + 4);
+      l0 = ts_ldgv<V>(wl); l1 = ts_ldgv<V>(wl + 4); r0 = ts_ldgv<V>(wr); r1 = ts_ldgv<V>(wr + 4);
     }
     cp_async_wait<1>();
     __syncthreads();
@@ -1066,10 +1173,10 @@ __device__ __forceinline__ void two_sided_mma_body(const S* __restrict__ in, S* 
       S* col = tile + j * 32;
       V y0[4], y1[4];
       if (inner)
-        product(l0, l1, nK, [&](int a, int f) { return ts_ld(tile + a * 256 + f * 8 + (j ^ ts_sigma(f, a))); },
+        product(l0, l1, nK, [&](int a, int f) { return ts_ldv<V>(tile + a * 256 + f * 8 + (j ^ ts_sigma(f, a))); },
                 [&](int nt, int f, V v0, V v1) { y0[nt] = v0; y1[nt] = v1; (void)f; });
       else
-        product(l0, l1, nK, [&](int a, int f) { return ts_ld(col + a * nL * 32 + (f ^ (2 * (a & 3)))); },
+        product(l0, l1, nK, [&](int a, int f) { return ts_ldv<V>(col + a * nL * 32 + (f ^ (2 * (a & 3)))); },
                 [&](int nt, int f, V v0, V v1) { y0[nt] = v0; y1[nt] = v1; (void)f; });
       __syncwarp();  // every lane has read its inputs before the column is overwritten
       if (inner) {
@@ -1104,22 +1211,26 @@ __device__ __forceinline__ void two_sided_mma_body(const S* __restrict__ in, S* 
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           const int f = 8 * nt + gid;
-          V x0 = make_double2(0.0, 0.0), x1 = x0;
-          if (tig < nL) x0 = ts_ld(tile + i * 256 + f * 8 + (tig ^ ts_sigma(f, i)));
-          if (4 + tig < nL) x1 = ts_ld(tile + i * 256 + f * 8 + ((4 + tig) ^ ts_sigma(f, i)));
-          double re0 = 0.0, re1 = 0.0, im0 = 0.0, im1 = 0.0;
-          dmma8x8x4(re0, re1, x0.x, r0.x);
-          dmma8x8x4(im0, im1, x0.x, r0.y);
-          dmma8x8x4(re0, re1, -x0.y, r0.y);
-          dmma8x8x4(im0, im1, x0.y, r0.x);
-          dmma8x8x4(re0, re1, x1.x, r1.x);
-          dmma8x8x4(im0, im1, x1.x, r1.y);
-          dmma8x8x4(re0, re1, -x1.y, r1.y);
-          dmma8x8x4(im0, im1, x1.y, r1.x);
+          V x0 = czero<V>(), x1 = x0, v0, v1;
+          if (tig < nL) x0 = ts_ldv<V>(tile + i * 256 + f * 8 + (tig ^ ts_sigma(f, i)));
+          if (4 + tig < nL) x1 = ts_ldv<V>(tile + i * 256 + f * 8 + ((4 + tig) ^ ts_sigma(f, i)));
+          if constexpr (kTf) {
+            cprod_tf32_t(tf_w(r0, r1), x0, x1, v0, v1);
+          } else {
+            double re0 = 0.0, re1 = 0.0, im0 = 0.0, im1 = 0.0;
+            dmma8x8x4(re0, re1, x0.x, r0.x);
+            dmma8x8x4(im0, im1, x0.x, r0.y);
+            dmma8x8x4(re0, re1, -x0.y, r0.y);
+            dmma8x8x4(im0, im1, x0.y, r0.x);
+            dmma8x8x4(re0, re1, x1.x, r1.x);
+            dmma8x8x4(im0, im1, x1.x, r1.y);
+            dmma8x8x4(re0, re1, -x1.y, r1.y);
+            dmma8x8x4(im0, im1, x1.y, r1.x);
+            v0.x = re0; v0.y = im0; v1.x = re1; v1.y = im1;
+          }
           const int64_t b0 = sb[f];
           S* dst = out + b0 + ro;
-          st_pair(dst, dst + 1, make_double2(re0, im0), make_double2(re1, im1), b0 >= 0 && 2 * tig < nL,
-                  b0 >= 0 && 2 * tig + 1 < nL);
+          st_pair(dst, dst + 1, v0, v1, b0 >= 0 && 2 * tig < nL, b0 >= 0 && 2 * tig + 1 < nL);
         }
       }
     } else
@@ -1128,8 +1239,8 @@ __device__ __forceinline__ void two_sided_mma_body(const S* __restrict__ in, S* 
       const int64_t ro = rout[K * 8 + i] + cout[L * 8 + gid];
       product(r0, r1, nL,
               [&](int b, int f) {
-                return inner ? ts_ld(tile + i * 256 + f * 8 + (b ^ ts_sigma(f, i)))
-                             : ts_ld(row + b * 32 + (f ^ (2 * (b & 3)) ^ (i & 1)));
+                return inner ? ts_ldv<V>(tile + i * 256 + f * 8 + (b ^ ts_sigma(f, i)))
+                             : ts_ldv<V>(row + b * 32 + (f ^ (2 * (b & 3)) ^ (i & 1)));
               },
               [&](int nt, int f, V v0, V v1) {
                 (void)nt;
@@ -1144,15 +1255,15 @@ __device__ __forceinline__ void two_sided_mma_body(const S* __restrict__ in, S* 
   cp_async_wait<0>();
 }
 
-template <typename S>
+template <typename S, bool TF>
 __global__ void __launch_bounds__(kTsWarps * 32, 2)
 k_two_sided_mma(const S* __restrict__ in, S* __restrict__ out, const FiberMap fm,
                 const TsTables T, const int inner, const int order) {
   if (!T.flags->handled || T.flags->use_mma != 1) return;
   extern __shared__ __align__(16) unsigned char s_raw[];
-  if (inner) two_sided_mma_body<false, true, S>(in, out, fm, T, s_raw, 0);
-  else if (T.flags->nsb == 1) two_sided_mma_body<false, false, S>(in, out, fm, T, s_raw, 0);
-  else two_sided_mma_body<true, false, S>(in, out, fm, T, s_raw, order);
+  if (inner) two_sided_mma_body<false, true, S, TF>(in, out, fm, T, s_raw, 0);
+  else if (T.flags->nsb == 1) two_sided_mma_body<false, false, S, TF>(in, out, fm, T, s_raw, 0);
+  else two_sided_mma_body<true, false, S, TF>(in, out, fm, T, s_raw, order);
 }
 
 
@@ -1187,11 +1298,21 @@ constexpr int kTnBufs = 3;
 // the last two modes is one segment (lseg = t); on modes (4, 0) it is eight segments of eight.
 struct TnSeg { int lseg, nseg; int64_t seg_off[64]; };
 
-template <typename S>
+// float2 items: TF32 x 3 products (the operand fragments are split once per batch)
+template <int NB, bool SAMEW>
+__device__ __forceinline__ void cmma_batch(const float2* w0, const float2* w1, const float2* x0,
+                                           const float2* x1, float2* y0, float2* y1) {
+  static_assert(SAMEW, "float2 batches share their operand");
+  const TfW w = tf_w(w0[0], w1[0]);
+#pragma unroll
+  for (int b = 0; b < NB; ++b) cprod_tf32(w, x0[b], x1[b], y0[b], y1[b]);
+}
+
+template <typename S, bool TF>
 __global__ void __launch_bounds__(kTnWarps * 32, 2)
 k_two_sided_mma_rows(const S* __restrict__ in, S* __restrict__ out, const FiberMap fm,
                      const TsTables T, const int t, const int order, const TnSeg seg) {
-  using V = double2;
+  using V = typename TsCompute<S, TF>::V;
   if (!T.flags->handled || T.flags->use_mma != 2) return;
   extern __shared__ __align__(16) unsigned char s_raw[];
   __shared__ int64_t s_seg[64];
@@ -1206,7 +1327,7 @@ k_two_sided_mma_rows(const S* __restrict__ in, S* __restrict__ out, const FiberM
   const int gid = lane >> 2, tig = lane & 3;
   const int nsb = T.flags->nsb;
   for (int i = threadIdx.x; i < kTwMaxSb * 64; i += blockDim.x)
-    s_w[i ^ (((i >> 3) & 1) << 2)] = ts_ld((const S*)T.sb_w + kTsMaxSb * 64 + i);
+    s_w[i ^ (((i >> 3) & 1) << 2)] = ts_ldv<V>((const S*)T.sb_w + kTsMaxSb * 64 + i);
   for (int i = threadIdx.x; i < 2 * kTwMaxSb * 8; i += blockDim.x) {
     const int which = i / (kTwMaxSb * 8), r = i - which * (kTwMaxSb * 8);
     s_roff[i] = T.sb_off[(2 * which) * kTsMaxSb * 8 + r];
@@ -1261,7 +1382,7 @@ k_two_sided_mma_rows(const S* __restrict__ in, S* __restrict__ out, const FiberM
 
 
   const int fsw = (gid & 1) << 2;
-  const V zero = make_double2(0.0, 0.0);
+  const V zero = czero<V>();
   // row-side lane constants: read rows tig / 4 + tig at position octet + gid
   const int rd1a = tig * kTnRow + (gid ^ sig(tig)), rd1b = (4 + tig) * kTnRow + (gid ^ sig(4 + tig));
   // column-side lane constants: read row pi(gid), write rows tig and tig + 4
@@ -1281,7 +1402,7 @@ k_two_sided_mma_rows(const S* __restrict__ in, S* __restrict__ out, const FiberM
     issue(u + 2 * g, cur == 0 ? kTnBufs - 1 : cur - 1);
     const TwMeta meta = s_meta[cur];
     const int K = meta.K, nK = s_n[K];
-    const V l0 = ts_ldg(wl_tab + K * 64 + gid * 8 + tig), l1 = ts_ldg(wl_tab + K * 64 + gid * 8 + 4 + tig);
+    const V l0 = ts_ldgv<V>(wl_tab + K * 64 + gid * 8 + tig), l1 = ts_ldgv<V>(wl_tab + K * 64 + gid * 8 + 4 + tig);
     // The two sides commute: the COLUMN side runs first, in place, so that the row side can
     // stream its accumulators straight to HBM -- a lane owns positions 8 q + 2 tig and + 1 of one
     // output row (one full 32-byte sector, a quarter warp one full 128-byte line).  Four items per
@@ -1307,8 +1428,8 @@ k_two_sided_mma_rows(const S* __restrict__ in, S* __restrict__ out, const FiberM
 #pragma unroll
       for (int b = 0; b < kB; ++b) {
         const S* fib = tile + (f0 + b) * tp;
-        x0[b] = (tig < nL && f0 + b < F) ? ts_ld(fib + c0) : zero;
-        x1[b] = (4 + tig < nL && f0 + b < F) ? ts_ld(fib + c1) : zero;
+        x0[b] = (tig < nL && f0 + b < F) ? ts_ldv<V>(fib + c0) : zero;
+        x1[b] = (4 + tig < nL && f0 + b < F) ? ts_ldv<V>(fib + c1) : zero;
       }
       cmma_batch<kB, true>(&r0, &r1, x0, x1, y0, y1);
       __syncwarp();
@@ -1336,8 +1457,8 @@ k_two_sided_mma_rows(const S* __restrict__ in, S* __restrict__ out, const FiberM
         const int f = (int)(((uint32_t)itc * inv_nq) >> 16), q = itc - f * nq;
         const S* col = tile + f * tp + 8 * q;
         fq[b] = it < n1 ? (f << 8) | q : -1;
-        x0[b] = (tig < nK && it < n1) ? ts_ld(col + rd1a) : zero;
-        x1[b] = (4 + tig < nK && it < n1) ? ts_ld(col + rd1b) : zero;
+        x0[b] = (tig < nK && it < n1) ? ts_ldv<V>(col + rd1a) : zero;
+        x1[b] = (4 + tig < nK && it < n1) ? ts_ldv<V>(col + rd1b) : zero;
       }
 #ifdef PW_TS_ABLATE  // ts_order bit 4 = no row-side arithmetic (copies the inputs)
       if (order & 4) {
@@ -1423,16 +1544,20 @@ static int launch_two_sided_t(const V* rho, V* out, const V* op, const FiberMap&
     const size_t smem_mma = sizeof(V) * 3 * kTsSlots * 32 + (3 * 32 + 4 * kTsMaxSb * 8) * sizeof(int64_t) +
                             kTsMaxSb * sizeof(int);
     if (!attr_mma) {
-      PW_CUDA(cudaFuncSetAttribute(k_two_sided_mma<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      PW_CUDA(cudaFuncSetAttribute(k_two_sided_mma<double2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)(sizeof(double2) * 3 * kTsSlots * 32 + (3 * 32 + 4 * kTsMaxSb * 8) * sizeof(int64_t) +
                                          kTsMaxSb * sizeof(int))));
-      PW_CUDA(cudaFuncSetAttribute(k_two_sided_mma<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)(sizeof(float2) * 3 * kTsSlots * 32 + (3 * 32 + 4 * kTsMaxSb * 8) * sizeof(int64_t) +
-                                         kTsMaxSb * sizeof(int))));
+      const int sm_f = (int)(sizeof(float2) * 3 * kTsSlots * 32 + (3 * 32 + 4 * kTsMaxSb * 8) * sizeof(int64_t) +
+                             kTsMaxSb * sizeof(int));
+      PW_CUDA(cudaFuncSetAttribute(k_two_sided_mma<float2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_f));
+      PW_CUDA(cudaFuncSetAttribute(k_two_sided_mma<float2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_f));
       attr_mma = true;
     }
-    k_two_sided_mma<V><<<grid, kTsWarps * 32, smem_mma, s>>>(rho, out, fm, T, inner ? 1 : 0,
-                                                          options().ts_order.load(std::memory_order_relaxed));
+    // complex64: TF32 x 3 (default) or widened FP64 products (ts_mma_c64 = 2)
+    const bool tf = !c128 && options().ts_mma_c64.load(std::memory_order_relaxed) == 1;
+    const int ord = options().ts_order.load(std::memory_order_relaxed);
+    if (tf) k_two_sided_mma<V, !std::is_same<V, double2>::value><<<grid, kTsWarps * 32, smem_mma, s>>>(rho, out, fm, T, inner ? 1 : 0, ord);
+    else k_two_sided_mma<V, false><<<grid, kTsWarps * 32, smem_mma, s>>>(rho, out, fm, T, inner ? 1 : 0, ord);
     if (inner) {
       PW_LAUNCHED();
       static bool attr_rows = false;
@@ -1441,12 +1566,13 @@ static int launch_two_sided_t(const V* rho, V* out, const V* op, const FiberMap&
                sizeof(int64_t) * 2 * kTwMaxSb * 8 + sizeof(TwMeta) * kTnBufs + sizeof(int) * (2 * kTwMaxSb * 8 + kTwMaxSb);
       };
       if (!attr_rows) {
-        PW_CUDA(cudaFuncSetAttribute(k_two_sided_mma_rows<double2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem(16)));
-        PW_CUDA(cudaFuncSetAttribute(k_two_sided_mma_rows<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem(8)));
+        PW_CUDA(cudaFuncSetAttribute(k_two_sided_mma_rows<double2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem(16)));
+        PW_CUDA(cudaFuncSetAttribute(k_two_sided_mma_rows<float2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem(8)));
+        PW_CUDA(cudaFuncSetAttribute(k_two_sided_mma_rows<float2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem(8)));
         attr_rows = true;
       }
-      k_two_sided_mma_rows<V><<<2 * kNumSMs, kTnWarps * 32, rows_smem(sizeof(V)), s>>>(rho, out, fm, T, (int)cols.t,
-                                                                                   options().ts_order.load(std::memory_order_relaxed), seg);
+      if (tf) k_two_sided_mma_rows<V, !std::is_same<V, double2>::value><<<2 * kNumSMs, kTnWarps * 32, rows_smem(sizeof(V)), s>>>(rho, out, fm, T, (int)cols.t, ord, seg);
+      else k_two_sided_mma_rows<V, false><<<2 * kNumSMs, kTnWarps * 32, rows_smem(sizeof(V)), s>>>(rho, out, fm, T, (int)cols.t, ord, seg);
     }
   }
   PW_LAUNCHED();
