@@ -22,6 +22,7 @@
 // a store instruction writes four full 128-byte lines (eight adjacent output rows per fiber).
 #include "pw_internal.cuh"
 #include "pw_dense.cuh"
+#include "pw_tf32.cuh"
 
 namespace pw {
 
@@ -80,7 +81,9 @@ __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0
 // fragments come from global memory (L1 / L2 resident) instead of a shared-memory copy -- a
 // 128 x 128 complex128 operator (the Jaynes-Cummings propagator, cutoff 64 (x) qubit, applied to a
 // BATCH of trajectories) is 256 KB and does not fit next to the tiles.
-template <bool INNER, typename S, int FIB, bool WG>
+// TF (complex64 only): the products run on the TF32 tensor cores, error-compensated (3 x TF32,
+// pw_tf32.cuh) -- the FP64 path is DMMA-bound for complex64 (same DMMA count, half the bytes).
+template <bool INNER, typename S, int FIB, bool WG, bool TF>
 __global__ void __launch_bounds__(512, 1)
 k_apply_dense_mma(const S* __restrict__ in, S* __restrict__ out,
                   const S* __restrict__ op, const int conj_op, const FiberMap fm,
@@ -184,9 +187,46 @@ k_apply_dense_mma(const S* __restrict__ in, S* __restrict__ out,
       const V* wrow = s_w + row * wp;
       const S* xcol = INNER ? tile + (32 * h + gid) * tp                 // + 8 n tp + position of j
                             : tile + 32 * h + (gid ^ (2 * tig));        // + j * 64 + 8 n   (j & 3 == tig)
-      V wnext = WG ? wglob(row, tig) : make_double2(0.0, 0.0);
+      if constexpr (TF) {
+        // two k4 steps per m16n8k8 MMA: inputs 8 k2 + tig and 8 k2 + 4 + tig
+        float c[4][4];
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) c[n][q] = 0.f;
+        const int ks2 = (ks + 1) >> 1;
 #pragma unroll 2
-      for (int k = 0; k < ks; ++k) {
+        for (int k2 = 0; k2 < ks2; ++k2) {
+          const int ja = 8 * k2 + tig, jb = ja + 4;
+          const V wa = WG ? wglob(row, ja) : wrow[(8 * k2 + tig) ^ fsw];
+          const V wb = WG ? wglob(row, jb) : ((8 * k2 + 4) < wp ? wrow[(8 * k2 + 4 + tig) ^ fsw] : make_double2(0.0, 0.0));
+          const TfW w = tf_w(make_float2((float)wa.x, (float)wa.y), make_float2((float)wb.x, (float)wb.y));
+          float2 xa[4], xb[4];
+          if (INNER) {
+            const int pa = ja < t ? (int)s_off[ja] : 0, pb = jb < t ? (int)s_off[jb] : 0;
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+              xa[n] = ja < t ? xcol[8 * n * tp + pa] : make_float2(0.f, 0.f);
+              xb[n] = jb < t ? xcol[8 * n * tp + pb] : make_float2(0.f, 0.f);
+            }
+          } else {
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+              xa[n] = ja < t ? xcol[ja * FIB + 8 * n] : make_float2(0.f, 0.f);
+              xb[n] = jb < t ? xcol[jb * FIB + 8 * n] : make_float2(0.f, 0.f);
+            }
+          }
+#pragma unroll
+          for (int n = 0; n < 4; ++n) cprod_tf32_acc(w, xa[n], xb[n], c[n]);
+        }
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[n][q] = (double)c[n][q];
+      }
+      V wnext = (WG && !TF) ? wglob(row, tig) : make_double2(0.0, 0.0);
+#pragma unroll 2
+      for (int k = 0; k < (TF ? 0 : ks); ++k) {
         const int j = 4 * k + tig;
         const V w = WG ? wnext : wrow[(4 * k + tig) ^ fsw];
         if (WG && k + 1 < ks) wnext = wglob(row, j + 4);   // next step's fragment: hides the L1 / L2 latency
@@ -240,7 +280,7 @@ k_apply_dense_mma(const S* __restrict__ in, S* __restrict__ out,
 
 }  // namespace
 
-template <typename S, int FIB, bool WG>
+template <typename S, int FIB, bool WG, bool TF>
 static int launch_dense_mma_s(const S* in, S* out, const S* op, const Plan& p, bool conj_op, bool inner,
                               cudaStream_t s, const int* skip) {
   const int t = (int)p.tm.t;
@@ -253,8 +293,8 @@ static int launch_dense_mma_s(const S* in, S* out, const S* op, const Plan& p, b
   if (smem > 220 * 1024) return PW_ERR_UNSUPPORTED;
   static bool attr_set = false;
   if (!attr_set) {
-    PW_CUDA(cudaFuncSetAttribute(k_apply_dense_mma<false, S, FIB, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
-    PW_CUDA(cudaFuncSetAttribute(k_apply_dense_mma<true, S, FIB, WG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+    PW_CUDA(cudaFuncSetAttribute(k_apply_dense_mma<false, S, FIB, WG, TF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
+    PW_CUDA(cudaFuncSetAttribute(k_apply_dense_mma<true, S, FIB, WG, TF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)));
     attr_set = true;
   }
   // one warp per item (8 rows x 32 fibers); two CTAs per SM when the tiles allow it
@@ -266,9 +306,9 @@ static int launch_dense_mma_s(const S* in, S* out, const S* op, const Plan& p, b
   uint64_t grid = (uint64_t)kNumSMs * ctas;
   if (grid > units) grid = units;
   if (inner)
-    k_apply_dense_mma<true, S, FIB, WG><<<(unsigned)grid, nwarps * 32, smem, s>>>(in, out, op, conj_op ? 1 : 0, p.fm, p.tm, skip);
+    k_apply_dense_mma<true, S, FIB, WG, TF><<<(unsigned)grid, nwarps * 32, smem, s>>>(in, out, op, conj_op ? 1 : 0, p.fm, p.tm, skip);
   else
-    k_apply_dense_mma<false, S, FIB, WG><<<(unsigned)grid, nwarps * 32, smem, s>>>(in, out, op, conj_op ? 1 : 0, p.fm, p.tm, skip);
+    k_apply_dense_mma<false, S, FIB, WG, TF><<<(unsigned)grid, nwarps * 32, smem, s>>>(in, out, op, conj_op ? 1 : 0, p.fm, p.tm, skip);
   PW_LAUNCHED();
   return PW_OK;
 }
@@ -287,17 +327,22 @@ int launch_dense_mma(const void* in, void* out, const void* op, const Plan& p, i
   } else if (p.fm.gsize[p.fm.ng - 1] < 16) {
     return PW_ERR_UNSUPPORTED;
   }
+  const bool tf = options().ts_mma_c64.load(std::memory_order_relaxed) == 1;  // complex64: 3 x TF32 (2 = widened FP64)
   if (t > 64) {
     if (dtype == PW_C128)
-      return launch_dense_mma_s<double2, 32, true>((const double2*)in, (double2*)out, (const double2*)op, p, conj_op, inner, s, skip);
+      return launch_dense_mma_s<double2, 32, true, false>((const double2*)in, (double2*)out, (const double2*)op, p, conj_op, inner, s, skip);
+    if (dtype == PW_C64 && tf)
+      return launch_dense_mma_s<float2, 32, true, true>((const float2*)in, (float2*)out, (const float2*)op, p, conj_op, inner, s, skip);
     if (dtype == PW_C64)
-      return launch_dense_mma_s<float2, 32, true>((const float2*)in, (float2*)out, (const float2*)op, p, conj_op, inner, s, skip);
+      return launch_dense_mma_s<float2, 32, true, false>((const float2*)in, (float2*)out, (const float2*)op, p, conj_op, inner, s, skip);
     return PW_ERR_UNSUPPORTED;
   }
   if (dtype == PW_C128)
-    return launch_dense_mma_s<double2, 64, false>((const double2*)in, (double2*)out, (const double2*)op, p, conj_op, inner, s, skip);
+    return launch_dense_mma_s<double2, 64, false, false>((const double2*)in, (double2*)out, (const double2*)op, p, conj_op, inner, s, skip);
+  if (dtype == PW_C64 && tf)
+    return launch_dense_mma_s<float2, 64, false, true>((const float2*)in, (float2*)out, (const float2*)op, p, conj_op, inner, s, skip);
   if (dtype == PW_C64)
-    return launch_dense_mma_s<float2, 64, false>((const float2*)in, (float2*)out, (const float2*)op, p, conj_op, inner, s, skip);
+    return launch_dense_mma_s<float2, 64, false, false>((const float2*)in, (float2*)out, (const float2*)op, p, conj_op, inner, s, skip);
   return PW_ERR_UNSUPPORTED;
 }
 
