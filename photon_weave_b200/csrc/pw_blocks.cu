@@ -1045,15 +1045,19 @@ __device__ __forceinline__ void two_sided_mma_body(const S* __restrict__ in, S* 
   auto product = [&](const V w0, const V w1, const int nx, auto ldx, auto sty) {
     if constexpr (kTf) {
       const TfW w = tf_w(w0, w1);
+      V x0[4], x1[4];
+      float c[4][4];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const int f = 8 * nt + gid;
-        V x0 = czero<V>(), x1 = x0, y0, y1;
-        if (tig < nx) x0 = ldx(tig, f);
-        if (4 + tig < nx) x1 = ldx(4 + tig, f);
-        cprod_tf32(w, x0, x1, y0, y1);
-        sty(nt, 8 * nt + 2 * tig, y0, y1);
+        x0[nt] = czero<V>(); x1[nt] = x0[nt];
+        if (tig < nx) x0[nt] = ldx(tig, f);
+        if (4 + tig < nx) x1[nt] = ldx(4 + tig, f);
       }
+      cprod_tf32_batch<4, false>(w, x0, x1, c);   // term-major: four independent accumulators
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+        sty(nt, 8 * nt + 2 * tig, make_float2(c[nt][0], c[nt][2]), make_float2(c[nt][1], c[nt][3]));
     } else {
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
@@ -1234,8 +1238,13 @@ __device__ __forceinline__ void cmma_batch(const float2* w0, const float2* w1, c
                                            const float2* x1, float2* y0, float2* y1) {
   static_assert(SAMEW, "float2 batches share their operand");
   const TfW w = tf_w(w0[0], w1[0]);
+  float c[NB][4];
+  cprod_tf32_batch<NB, false>(w, x0, x1, c);
 #pragma unroll
-  for (int b = 0; b < NB; ++b) cprod_tf32(w, x0[b], x1[b], y0[b], y1[b]);
+  for (int b = 0; b < NB; ++b) {
+    y0[b] = make_float2(c[b][0], c[b][2]);
+    y1[b] = make_float2(c[b][1], c[b][3]);
+  }
 }
 
 template <typename S, bool TF>

@@ -216,8 +216,7 @@ k_apply_dense_mma(const S* __restrict__ in, S* __restrict__ out,
               xb[n] = jb < t ? xcol[jb * FIB + 8 * n] : make_float2(0.f, 0.f);
             }
           }
-#pragma unroll
-          for (int n = 0; n < 4; ++n) cprod_tf32_acc(w, xa[n], xb[n], c[n]);
+          cprod_tf32_batch<4, true>(w, xa, xb, c);
         }
 #pragma unroll
         for (int n = 0; n < 4; ++n)

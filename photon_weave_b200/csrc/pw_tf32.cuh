@@ -88,4 +88,30 @@ __device__ __forceinline__ void cprod_tf32_acc(const TfW& w, const float2 x0, co
   mma_tf32(c[0], c[1], c[2], c[3], w.nim0.hi, w.re0.hi, w.nim1.hi, w.re1.hi, xi0.hi, xi1.hi);
 }
 
+// NB independent items that share the operand fragment w, issued TERM-major: consecutive MMAs in
+// program order belong to different accumulators (a warp issues in order; six dependent MMAs per
+// item back to back would serialise on the tensor-pipe latency).  ACC: add to c instead of
+// starting from zero.
+template <int NB, bool ACC>
+__device__ __forceinline__ void cprod_tf32_batch(const TfW& w, const float2* x0, const float2* x1, float (*c)[4]) {
+  Tf2 xr0[NB], xr1[NB], xi0[NB], xi1[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    xr0[b] = tf_split(x0[b].x); xr1[b] = tf_split(x1[b].x); xi0[b] = tf_split(x0[b].y); xi1[b] = tf_split(x1[b].y);
+    if (!ACC) { c[b][0] = 0.f; c[b][1] = 0.f; c[b][2] = 0.f; c[b][3] = 0.f; }
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) mma_tf32(c[b][0], c[b][1], c[b][2], c[b][3], w.re0.lo, w.im0.lo, w.re1.lo, w.im1.lo, xr0[b].hi, xr1[b].hi);
+#pragma unroll
+  for (int b = 0; b < NB; ++b) mma_tf32(c[b][0], c[b][1], c[b][2], c[b][3], w.nim0.lo, w.re0.lo, w.nim1.lo, w.re1.lo, xi0[b].hi, xi1[b].hi);
+#pragma unroll
+  for (int b = 0; b < NB; ++b) mma_tf32(c[b][0], c[b][1], c[b][2], c[b][3], w.re0.hi, w.im0.hi, w.re1.hi, w.im1.hi, xr0[b].lo, xr1[b].lo);
+#pragma unroll
+  for (int b = 0; b < NB; ++b) mma_tf32(c[b][0], c[b][1], c[b][2], c[b][3], w.nim0.hi, w.re0.hi, w.nim1.hi, w.re1.hi, xi0[b].lo, xi1[b].lo);
+#pragma unroll
+  for (int b = 0; b < NB; ++b) mma_tf32(c[b][0], c[b][1], c[b][2], c[b][3], w.re0.hi, w.im0.hi, w.re1.hi, w.im1.hi, xr0[b].hi, xr1[b].hi);
+#pragma unroll
+  for (int b = 0; b < NB; ++b) mma_tf32(c[b][0], c[b][1], c[b][2], c[b][3], w.nim0.hi, w.re0.hi, w.nim1.hi, w.re1.hi, xi0[b].hi, xi1[b].hi);
+}
+
 }  // namespace pw
