@@ -16,6 +16,7 @@ ap.add_argument("what"); ap.add_argument("modes", type=int); ap.add_argument("cu
 ap.add_argument("op"); ap.add_argument("targets", type=int, nargs="+")
 ap.add_argument("--path", type=int, default=0); ap.add_argument("--tile", type=int, default=0)
 ap.add_argument("--ctas", type=int, default=0); ap.add_argument("--reps", type=int, default=4)
+ap.add_argument("--c64", action="store_true", help="complex64 state and operator")
 ap.add_argument("--trace", action="store_true", help="print per-kernel device times (torch.profiler)")
 ap.add_argument("--set", nargs="*", default=[], help="pw_set_option name=value ...")
 a = ap.parse_args()
@@ -29,7 +30,8 @@ dims = (d,) * m
 N = d**m
 n = N * N if a.what == "mat" else N
 gen = torch.Generator(device="cuda").manual_seed(0)
-x = torch.view_as_complex(torch.randn(n, 2, generator=gen, device="cuda", dtype=torch.float64))
+x = torch.view_as_complex(torch.randn(n, 2, generator=gen, device="cuda",
+                                      dtype=torch.float32 if a.c64 else torch.float64))
 y = torch.empty_like(x)
 t = d ** len(a.targets)
 op = {"u": lambda: ops.random_unitary(t, 1), "bs": lambda: ops.beam_splitter(d, d, math.pi / 4),
@@ -37,6 +39,8 @@ op = {"u": lambda: ops.random_unitary(t, 1), "bs": lambda: ops.beam_splitter(d, 
       "dense2": lambda: ops.random_unitary(t, 2),
       "krausd": lambda: np.stack([ops.random_unitary(t, 10 + k) / 2.0 for k in range(4)])}[a.op]()
 op = torch.as_tensor(np.ascontiguousarray(op)).cuda()
+if a.c64:
+    op = op.to(torch.complex64)
 def run():
     for _ in range(a.reps):
         if a.what == "vec":
