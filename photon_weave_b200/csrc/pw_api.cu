@@ -66,6 +66,7 @@ Options& options() {
     env("PW_DRAW_EXACT", p->draw_exact);
     env("PW_FUSE_GROUP", p->fuse_group);
     env("PW_MULTI_F", p->multi_f);
+    env("PW_HOST_OVERLAP", p->host_overlap);
     env("PW_TS_ORDER", p->ts_order);
     env("PW_DENSE_MMA", p->dense_mma);
     env("PW_SEG_FPW", p->seg_fpw);
@@ -102,6 +103,7 @@ extern "C" int pw_set_option(const char* name, int value) {
   else if (!std::strcmp(name, "draw_exact")) o.draw_exact.store(value);
   else if (!std::strcmp(name, "fuse_group")) o.fuse_group.store(value);
   else if (!std::strcmp(name, "multi_f")) o.multi_f.store(value);
+  else if (!std::strcmp(name, "host_overlap")) o.host_overlap.store(value);
   else if (!std::strcmp(name, "ts_order")) o.ts_order.store(value);
   else if (!std::strcmp(name, "dense_mma")) o.dense_mma.store(value);
   else if (!std::strcmp(name, "seg_fpw")) o.seg_fpw.store(value);

@@ -165,11 +165,83 @@ extern "C" int pw_circuit_host(const void* h_state, void* h_out, int is_matrix,
     PW_CUDA(cudaMalloc(&dops[i].p, ob));
     PW_CUDA(cudaMemcpyAsync(dops[i].p, o.op, ob, cudaMemcpyHostToDevice, st.s));
   }
+  std::vector<void*> dev_ops(nops);
+  for (int i = 0; i < nops; ++i) dev_ops[i] = dops[i].p;
+  const int fuse = pw::options().fuse_pairs.load(std::memory_order_relaxed);
+  // ---- upload overlapped with compute ------------------------------------------------------
+  // Operations on disjoint subsystems commute.  Those that do not touch subsystem 0 (nor follow,
+  // on a shared subsystem, one that does) act independently on every slab of the leading axis, so
+  // they run slab by slab BEHIND the upload (a second stream, one event per slab) instead of
+  // waiting for the whole 34.8 GB state; the rest runs on the complete state afterwards.
+  std::vector<int> late(nops, 0);
+  int n_early = 0;
+  const int64_t slabs = dims[0];
+  const int overlap_mib = pw::options().host_overlap.load(std::memory_order_relaxed);  // 0 = off, else minimum state size
+  if (!is_matrix && n >= 2 && slabs >= 2 && slabs <= 64 && overlap_mib > 0 && bytes >= ((size_t)overlap_mib << 20)) {
+    for (int i = 0; i < nops; ++i) {
+      for (int k = 0; k < ops[i].nt; ++k) late[i] |= ops[i].targets[k] == 0;
+      for (int j = 0; j < i && !late[i]; ++j) {
+        if (!late[j]) continue;
+        for (int a = 0; a < ops[i].nt && !late[i]; ++a)
+          for (int b = 0; b < ops[j].nt; ++b)
+            if (ops[i].targets[a] == ops[j].targets[b]) { late[i] = 1; break; }
+      }
+      n_early += !late[i];
+    }
+  }
+  if (n_early > 0) {
+    Stream up;
+    PW_CUDA(cudaStreamCreateWithFlags(&up.s, cudaStreamNonBlocking));
+    std::vector<pw_host_op> early, rest;
+    std::vector<void*> early_dev, rest_dev;
+    for (int i = 0; i < nops; ++i) {
+      if (late[i]) { rest.push_back(ops[i]); rest_dev.push_back(dev_ops[i]); continue; }
+      pw_host_op o = ops[i];
+      for (int k = 0; k < o.nt; ++k) o.targets[k] -= 1;   // the slab drops the leading axis
+      early.push_back(o);
+      early_dev.push_back(dev_ops[i]);
+    }
+    const size_t slab_bytes = bytes / (size_t)slabs;
+    void* cur0 = state.p;
+    void* oth0 = other.p;
+    void* res_cur = state.p;
+    void* res_oth = other.p;
+    std::vector<cudaEvent_t> evs((size_t)slabs, nullptr);
+    int rc = PW_OK;
+    for (int64_t k = 0; k < slabs && rc == PW_OK; ++k) {
+      const size_t off = (size_t)k * slab_bytes;
+      rc = cuda_status(cudaMemcpyAsync((char*)cur0 + off, (const char*)h_state + off, slab_bytes,
+                                       cudaMemcpyHostToDevice, up.s));
+      if (rc == PW_OK) rc = cuda_status(cudaEventCreateWithFlags(&evs[k], cudaEventDisableTiming));
+      if (rc == PW_OK) rc = cuda_status(cudaEventRecord(evs[k], up.s));
+      if (rc == PW_OK) rc = cuda_status(cudaStreamWaitEvent(st.s, evs[k], 0));
+      if (rc != PW_OK) break;
+      void* c = (char*)cur0 + off;
+      void* o = oth0 ? (char*)oth0 + off : nullptr;
+      rc = run_ops(&c, &o, 0, dims + 1, n - 1, early.data(), early_dev.data(), (int)early.size(), dtype, fuse, st.s);
+      // every slab takes the same passes: the result sits in the same buffer for all of them
+      res_cur = ((char*)c - off);
+      res_oth = o ? (void*)((char*)o - off) : nullptr;
+    }
+    if (rc == PW_OK) {
+      state.p = res_cur;
+      other.p = res_oth;
+      rc = run_ops(&state.p, &other.p, 0, dims, n, rest.data(), rest_dev.data(), (int)rest.size(), dtype, fuse, st.s);
+    }
+    if (rc != PW_OK) {
+      cudaStreamSynchronize(up.s);
+      cudaStreamSynchronize(st.s);
+      for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+      return rc;
+    }
+    PW_CUDA(cudaMemcpyAsync(h_out, state.p, bytes, cudaMemcpyDeviceToHost, st.s));
+    const int rs = cuda_status(cudaStreamSynchronize(st.s));
+    cudaStreamSynchronize(up.s);
+    for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+    return rs;
+  }
   PW_CUDA(cudaMemcpyAsync(state.p, h_state, bytes, cudaMemcpyHostToDevice, st.s));
   {
-    std::vector<void*> dev_ops(nops);
-    for (int i = 0; i < nops; ++i) dev_ops[i] = dops[i].p;
-    const int fuse = pw::options().fuse_pairs.load(std::memory_order_relaxed);
     const int rc = run_ops(&state.p, &other.p, is_matrix, dims, n, ops, dev_ops.data(), nops, dtype,
                            fuse, st.s);
     if (rc != PW_OK) {

@@ -245,6 +245,7 @@ struct Options {
   std::atomic<int> diag_kernel{1};             // diagonal t <= 8 operators on large vectors: one streaming pass
   std::atomic<int> contig_mma{1};              // ... on the FP64 tensor cores (complex128, one 5..8-level target)
   std::atomic<int> fuse_pairs{1};              // circuit entry points fuse adjacent single-axis ops
+  std::atomic<int> host_overlap{256};          // pw_circuit_host: states of at least this many MiB upload slab-wise, overlapped with the operations that allow it (0 = off)
   std::atomic<int> multi_f{0};                 // resident-tile kernel: fibers per thread (0 = auto)
   std::atomic<int> fuse_group{3};              // ... up to this many per HBM pass (resident-tile kernel, 2..4)
   std::atomic<int> mat_pair_max_d{4};          // single-pass U rho U^dagger register tile up to this d

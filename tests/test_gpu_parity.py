@@ -1000,3 +1000,38 @@ def test_pinned_operator_plan_cache(ad):
     finally:
         _lib.set_option("blocks_min_elems", 1 << 18)
         _lib.set_option("blocks_min_elems_small_t", 1 << 22)
+
+
+def test_circuit_host_overlaps_upload_with_slab_wise_operations(ad):
+    """pw_circuit_host on a state above the overlap threshold: operations that do not touch
+    subsystem 0 (nor follow one that does on a shared subsystem) run slab by slab behind the
+    upload; the result must equal the plain order on every kind of layer, including layers where
+    NOTHING or EVERYTHING can run early, and match the non-overlapped call bit for bit."""
+    from photon_weave_b200 import _lib
+    from photon_weave_b200.core import ffi
+
+    dims = (6,) * 7
+    N = 6**7
+    psi = ops.random_state(N, 71)
+    u = [ops.random_unitary(6, 80 + m) for m in range(7)]
+    bs = ops.beam_splitter(6, 6, 0.7)
+    layers = {
+        "bench_like": [((m,), u[m]) for m in range(7)] + [((0, 1), bs), ((2, 3), bs), ((4, 5), bs)],
+        "late_first": [((0,), u[0]), ((0, 1), bs), ((1,), u[1]), ((3,), u[3]), ((1, 2), bs), ((5, 6), bs)],
+        "all_early": [((m,), u[m]) for m in range(1, 7)] + [((3, 4), bs)],
+        "all_late": [((0,), u[0]), ((0, 1), bs), ((1, 0), bs)],
+    }
+    for name, layer in layers.items():
+        ref = psi
+        for tg, op in layer:
+            ref = oad.apply_operation_vector(dims, tg, ref, op)
+        ops_list = [(0, tg, op) for tg, op in layer]
+        outs = {}
+        for thr in (1, 0):                      # 1 MiB threshold: overlapped; 0: plain
+            _lib.set_option("host_overlap", thr)
+            try:
+                outs[thr] = ffi.circuit_host(psi.reshape(-1), False, dims, ops_list)
+            finally:
+                _lib.set_option("host_overlap", 256)
+        assert rel_err(outs[1].reshape(-1, 1), ref) < 1e-12, name
+        assert np.array_equal(outs[1], outs[0]), name
