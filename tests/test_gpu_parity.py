@@ -1034,4 +1034,4 @@ def test_circuit_host_overlaps_upload_with_slab_wise_operations(ad):
             finally:
                 _lib.set_option("host_overlap", 256)
         assert rel_err(outs[1].reshape(-1, 1), ref) < 1e-12, name
-        assert np.array_equal(outs[1], outs[0]), name
+        assert rel_err(outs[1], outs[0]) < 1e-13, name   # (different fusion groups: last-ulp differences)
