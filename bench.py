@@ -534,6 +534,21 @@ def run_gpu_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def pinned_near_gpu(torch, n):
+    """Pinned complex128 host buffer allocated while the process is bound to the CPUs of the
+    GPU's NUMA node (NVML affinity; the binding is dropped again right after)."""
+    from photon_weave_b200.bench_sharded import _gpu_local_cpus
+
+    before = os.sched_getaffinity(0)
+    near = _gpu_local_cpus(torch.cuda.current_device())
+    if near:
+        os.sched_setaffinity(0, near)
+    try:
+        return torch.empty(n, dtype=torch.complex128, pin_memory=True)
+    finally:
+        os.sched_setaffinity(0, before)
+
+
 def run_e2e_prepare(args, torch, dev_state, N):
     """Copy the evolved state into a pinned host buffer (outside any timed region)."""
     try:
@@ -547,7 +562,7 @@ def run_e2e_prepare(args, torch, dev_state, N):
         return ({"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                  "skipped": f"host has {avail / 1e9:.0f} GB available, needs {need * 1.5 / 1e9:.0f} GB"},
                 None)
-    h = torch.empty(N, dtype=torch.complex128, pin_memory=True)
+    h = pinned_near_gpu(torch, N)
     h.copy_(dev_state.reshape(-1))
     torch.cuda.synchronize()
     return None, h
@@ -592,7 +607,7 @@ def run_e2e(args, torch, ffi, layer, h, N, nops):
     if args.no_pipeline or avail < need + (16 << 30):
         out["serial"] = serial
         return out
-    h_out = torch.empty(N, dtype=torch.complex128, pin_memory=True)
+    h_out = pinned_near_gpu(torch, N)
     o_np = h_out.numpy()
     psteps = max(steps, args.e2e_pipeline_steps)
     with ffi.HostPipeline(dims, False, np.complex128, device=dev, buffers=4) as pl:

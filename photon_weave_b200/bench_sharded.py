@@ -9,6 +9,7 @@ this package never imports ``oracle/``).
 from __future__ import annotations
 
 import json
+import os
 import math
 from typing import Any, Callable, List, Optional, Sequence
 
@@ -260,6 +261,69 @@ def _time_layers(args, dist, rank, world, local_rank, runner, st, lib, ClockSamp
     return total_ms, stages, infos[-1], launches, clocks, counts
 
 
+def _gpu_local_cpus(index: int):
+    """CPUs on the NUMA node of GPU `index` (NVML), or None: pinned host memory is placed on the
+    node of the allocating thread, and a shard crossing the socket link halves the PCIe rate."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if word >> b & 1}
+        cpus &= os.sched_getaffinity(0)
+        return cpus or None
+    except Exception:
+        return None
+
+
+def _time_e2e(args, dist, rank, world, runner, st, units):
+    """The step END TO END at N ranks: every rank uploads its shard from pinned host memory over
+    its own PCIe link, runs the layer, and reads its shard back -- all inside the timed region
+    (barrier + synchronize on both sides, max over ranks)."""
+    steps = max(1, min(args.steps, 2 * getattr(args, "e2e_steps", 2)))
+    before = os.sched_getaffinity(0)
+    near = _gpu_local_cpus(torch.cuda.current_device())
+    if near:
+        os.sched_setaffinity(0, near)
+    host = torch.empty(st.local.numel(), dtype=st.local.dtype, pin_memory=True)
+    os.sched_setaffinity(0, before)
+    st.store_host(host)
+    torch.cuda.synchronize()
+
+    def step():
+        st.load_host(host)
+        runner.run()
+        st.store_host(host)
+
+    step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        step()
+    t1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([t0.elapsed_time(t1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = float(ms.item()) / steps
+    nbytes = host.numel() * host.element_size() * world
+    del host
+    return {"value": units / (ms_step * 1e-3), "ms_per_step": ms_step, "steps": steps,
+            "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+            "host_numa": "pinned shard allocated on the GPU's NUMA node (NVML cpu affinity)" if near
+            else "pinned shard allocated wherever the rank ran",
+            "path": "per rank: pinned host shard -> ShardedTensor.load_host -> run_layer (axis swap "
+                    "included) -> store_host; one PCIe link per rank, all ranks concurrently"}
+
+
 def _records(world, n_local, nops, stages, info, counts, impl, mode, peak, peak_src):
     """roofline + axis_swap objects of the JSON line from the stage timings."""
     alg_bytes = 2 * n_local * 16
@@ -340,6 +404,7 @@ def bench_sharded(args, dist, rank, world, local_rank, make_layer, workload_conf
     total_ms, stages, info, launches, clocks, counts = _time_layers(
         args, dist, rank, world, local_rank, runner, st, lib, ClockSampler)
     norm_after = float(st.norm2().item())
+    e2e = dict(_time_e2e(args, dist, rank, world, runner, st, nops * N), unit=UNIT)
     if rank == 0:
         peak, peak_src = peaks()
         roofline, swap = _records(world, n_local, nops, stages, info, counts, swap_impl, mode, peak, peak_src)
@@ -349,8 +414,7 @@ def bench_sharded(args, dist, rank, world, local_rank, make_layer, workload_conf
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "c128", "data": "synthetic",
             "config": workload_config(args, world), "clocks": clocks,
-            "e2e": {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                    "skipped": "end-to-end host-buffer path is measured at N=1 only"},
+            "e2e": e2e,
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": None, "axis_swap": swap,
             "norm_after": norm_after, "parity_n": parity,
         }
@@ -411,6 +475,7 @@ def bench_sharded_rho(args, dist, rank, world, local_rank, make_rho_layer, peaks
     total_ms, stages, info, launches, clocks, counts = _time_layers(
         args, dist, rank, world, local_rank, runner, st, lib, ClockSampler)
     tr1 = float(st.trace().item())
+    e2e = dict(_time_e2e(args, dist, rank, world, runner, st, nops * D * D), unit=RHO_UNIT)
     if rank == 0:
         peak, peak_src = peaks()
         roofline, swap = _records(world, n_local, nops, stages, info, counts, swap_impl, mode, peak, peak_src)
@@ -427,8 +492,7 @@ def bench_sharded_rho(args, dist, rank, world, local_rank, make_rho_layer, peaks
                        f"leading ROW axis block-sharded over {world} ranks (column side local)",
                        "l2": "block (>= 2 GB per rank) exceeds the 126 MB L2; no flush needed"},
             "clocks": clocks,
-            "e2e": {"value": None, "unit": RHO_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                    "skipped": "device-resident workload (the host-buffer path is measured on the headline workload)"},
+            "e2e": e2e,
             "gpu_launches": launches, "roofline": roofline, "cpu_baseline": None, "axis_swap": swap,
             "trace_before": tr0, "trace_after": tr1, "parity_n": parity,
         }

@@ -856,6 +856,21 @@ class ShardedTensor:
                 req.wait()
         return recv, local_vaxes, new_sparts
 
+    # ---- host buffers (one pinned shard per rank) --------------------------------------------
+
+    def load_host(self, host: torch.Tensor) -> None:
+        """Replace this rank's shard (current layout) with a pinned host shard, asynchronously on
+        the current stream: every rank uploads over its own PCIe link."""
+        if host.numel() != self.local.numel() or host.dtype != self.local.dtype:
+            raise ValueError("host shard must match the local shard's size and dtype")
+        self.local.reshape(-1).copy_(host.reshape(-1), non_blocking=True)
+
+    def store_host(self, host: torch.Tensor) -> None:
+        """Copy this rank's shard (current layout: `vaxes`, `sparts`) into a pinned host shard."""
+        if host.numel() != self.local.numel() or host.dtype != self.local.dtype:
+            raise ValueError("host shard must match the local shard's size and dtype")
+        host.reshape(-1).copy_(self.local.reshape(-1), non_blocking=True)
+
     # ---- reassembly (tests / preflight) -----------------------------------------------------
 
     def gather_full(self) -> torch.Tensor:

@@ -120,6 +120,13 @@ def _worker(rank, world, port, dims, program, results):
             op = ops.random_unitary(t, seed)
             st.apply_operation(torch.from_numpy(op), axes, prefer_shard=prefer)
             ref = oad.apply_operation_vector(dims, axes, ref, op, True)
+        # host round trip of the shard in its current layout (the e2e leg of bench.py --gpus N)
+        host = torch.empty(st.local.numel(), dtype=st.local.dtype)
+        st.store_host(host)
+        st.local.zero_()
+        st.load_host(host)
+        with pytest.raises(ValueError):
+            st.load_host(host[:-1])
         got = st.gather_full().numpy()
         err = float(np.abs(got - ref.reshape(-1)).max())
         nrm = float(st.norm2().item())
