@@ -67,6 +67,7 @@ Options& options() {
     env("PW_FUSE_GROUP", p->fuse_group);
     env("PW_MULTI_F", p->multi_f);
     env("PW_HOST_OVERLAP", p->host_overlap);
+    env("PW_C64_PAIRS", p->c64_pairs);
     env("PW_TS_ORDER", p->ts_order);
     env("PW_DENSE_MMA", p->dense_mma);
     env("PW_SEG_FPW", p->seg_fpw);
@@ -104,6 +105,7 @@ extern "C" int pw_set_option(const char* name, int value) {
   else if (!std::strcmp(name, "fuse_group")) o.fuse_group.store(value);
   else if (!std::strcmp(name, "multi_f")) o.multi_f.store(value);
   else if (!std::strcmp(name, "host_overlap")) o.host_overlap.store(value);
+  else if (!std::strcmp(name, "c64_pairs")) o.c64_pairs.store(value);
   else if (!std::strcmp(name, "ts_order")) o.ts_order.store(value);
   else if (!std::strcmp(name, "dense_mma")) o.dense_mma.store(value);
   else if (!std::strcmp(name, "seg_fpw")) o.seg_fpw.store(value);

@@ -65,6 +65,42 @@ k_apply_small(const V* in, V* out, const V* __restrict__ op, const FiberMap fm,
   }
 }
 
+// complex64 with an even contiguous untouched run: two adjacent fibers per thread, every access
+// 128 bits wide (the complex128 kernel's bytes per thread and per instruction).  `fm` counts
+// fiber PAIRS (pair_fiber_map).
+template <int T, bool CONJ>
+__global__ void __launch_bounds__(256, T <= 4 ? 4 : (T <= 6 ? 3 : 2))
+k_apply_small_c64x2(const float2* in, float2* out, const float2* __restrict__ op, const FiberMap fm,
+                    const TargetMap tm, const int* __restrict__ skip) {
+  if (skip && *skip) return;
+  __shared__ float2 s_op[T * T];
+  __shared__ int64_t s_off[T];
+  for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
+    float2 o = op[i];
+    if (CONJ) o.y = -o.y;
+    s_op[i] = o;
+  }
+  if (threadIdx.x < T) s_off[threadIdx.x] = tm.offset(threadIdx.x);
+  __syncthreads();
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < fm.nfib; f += stride) {
+    const int64_t base = fm.base(f);
+    int zero = 0;
+    asm volatile("" : "+r"(zero));
+    const float2* sop = s_op + zero;
+    C64x2 x[T];
+#pragma unroll
+    for (int j = 0; j < T; ++j) x[j] = ld_c64x2(in + base + s_off[j]);
+#pragma unroll
+    for (int a = 0; a < T; ++a) {
+      C64x2 acc = czero<C64x2>();
+#pragma unroll
+      for (int b = 0; b < T; ++b) cfma(acc, sop[a * T + b], x[b]);
+      st_c64x2(out + base + s_off[a], acc);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // Register path, CONTIGUOUS fibers (the targets are the innermost axes, so the tensor is
 // an array of t-element fibers).  Thread-per-fiber loads would touch 32 different lines
@@ -425,6 +461,15 @@ static int launch_small(const V* in, V* out, const V* op, const Plan& p, bool co
     const int g2 = grid_for((p.fm.nfib + 31) / 32 * 32, block, 3);
     if (conj_op) k_apply_small_contig<V, T, true><<<g2, block, 0, s>>>(in, out, op, p.fm.nfib, p.tm, skip);
     else         k_apply_small_contig<V, T, false><<<g2, block, 0, s>>>(in, out, op, p.fm.nfib, p.tm, skip);
+    PW_LAUNCHED();
+    return PW_OK;
+  }
+  FiberMap pm;
+  if (sizeof(V) == 8 && !acc && T >= 2 && options().c64_pairs.load(std::memory_order_relaxed) &&
+      pair_fiber_map(p.fm, in, out, &pm)) {
+    const int gp = grid_for(pm.nfib, block, 8);
+    if (conj_op) k_apply_small_c64x2<T, true><<<gp, block, 0, s>>>((const float2*)in, (float2*)out, (const float2*)op, pm, p.tm, skip);
+    else         k_apply_small_c64x2<T, false><<<gp, block, 0, s>>>((const float2*)in, (float2*)out, (const float2*)op, pm, p.tm, skip);
     PW_LAUNCHED();
     return PW_OK;
   }

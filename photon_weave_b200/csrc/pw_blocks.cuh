@@ -89,7 +89,8 @@ __device__ __forceinline__ DescView<V> desc_view(const BlockArrays& A, unsigned 
 // land on positions another lane of the same warp reads)
 template <typename V, int NC, int UR, bool SYNCW, typename LoadX, typename StoreY>
 __device__ __forceinline__ void block_product_nc(const V* __restrict__ bv, const int nr, LoadX ldx, StoreY sty) {
-  V x[NC];
+  using X = decltype(ldx(0));  // V, or C64x2: two adjacent complex64 fibers per thread
+  X x[NC];
 #pragma unroll
   for (int j = 0; j < NC; ++j) x[j] = ldx(j);
   if (SYNCW) __syncwarp();
@@ -98,7 +99,7 @@ __device__ __forceinline__ void block_product_nc(const V* __restrict__ bv, const
   int a = 0;
   if (UR >= 4)
   for (; a + 4 <= nr; a += 4) {
-    V acc0 = czero<V>(), acc1 = czero<V>(), acc2 = czero<V>(), acc3 = czero<V>();
+    X acc0 = czero<X>(), acc1 = czero<X>(), acc2 = czero<X>(), acc3 = czero<X>();
 #pragma unroll
     for (int j = 0; j < NC; ++j) {
       cfma(acc0, bv[a * NC + j], x[j]);
@@ -109,7 +110,7 @@ __device__ __forceinline__ void block_product_nc(const V* __restrict__ bv, const
     sty(a, acc0); sty(a + 1, acc1); sty(a + 2, acc2); sty(a + 3, acc3);
   }
   for (; a < nr; ++a) {
-    V acc = czero<V>();
+    X acc = czero<X>();
 #pragma unroll
     for (int j = 0; j < NC; ++j) cfma(acc, bv[a * NC + j], x[j]);
     sty(a, acc);

@@ -39,6 +39,25 @@ __device__ __forceinline__ void cfma_conja(V& acc, const V a, const V b) {
   acc.x = fma(a.x, b.x, acc.x); acc.x = fma(a.y, b.y, acc.x);
   acc.y = fma(a.x, b.y, acc.y); acc.y = fma(-a.y, b.x, acc.y);
 }
+// two adjacent complex64 values moved as ONE 128-bit access (fiber pairs of the complex64
+// register kernels: the same bytes per thread and per instruction as complex128)
+struct __align__(16) C64x2 { float2 a, b; };
+template <>
+__host__ __device__ __forceinline__ C64x2 czero<C64x2>() {
+  C64x2 z; z.a = czero<float2>(); z.b = czero<float2>(); return z;
+}
+__device__ __forceinline__ void cfma(C64x2& acc, const float2 o, const C64x2 x) {
+  cfma(acc.a, o, x.a);
+  cfma(acc.b, o, x.b);
+}
+__device__ __forceinline__ C64x2 ld_c64x2(const float2* p) {
+  const float4 v = __ldcg(reinterpret_cast<const float4*>(p));
+  C64x2 r; r.a = make_float2(v.x, v.y); r.b = make_float2(v.z, v.w); return r;
+}
+__device__ __forceinline__ void st_c64x2(float2* p, const C64x2 v) {
+  __stcg(reinterpret_cast<float4*>(p), make_float4(v.a.x, v.a.y, v.b.x, v.b.y));
+}
+
 template <typename V>
 __device__ __forceinline__ typename RealOf<V>::type cabs2(const V a) {
   return fma(a.x, a.x, a.y * a.y);
@@ -98,6 +117,19 @@ struct TargetMap {
     return off;
   }
 };
+
+// fiber-pair map of `fm`, or false: the innermost group must be the contiguous direction with an
+// even extent (then every other stride and every target offset is even: 16-byte aligned pairs)
+inline bool pair_fiber_map(const FiberMap& fm, const void* in, const void* out, FiberMap* pm) {
+  if (fm.ng < 1 || fm.gstride[fm.ng - 1] != 1 || (fm.gsize[fm.ng - 1] & 1) != 0) return false;
+  if ((((uintptr_t)in | (uintptr_t)out) & 15) != 0) return false;
+  *pm = fm;
+  pm->gsize[fm.ng - 1] = fm.gsize[fm.ng - 1] / 2;
+  pm->gstride[fm.ng - 1] = 2;
+  pm->nfib = fm.nfib / 2;
+  return true;
+}
+
 
 struct Plan {
   uint64_t N;  // total elements of the tensor the maps index
@@ -246,6 +278,7 @@ struct Options {
   std::atomic<int> contig_mma{1};              // ... on the FP64 tensor cores (complex128, one 5..8-level target)
   std::atomic<int> fuse_pairs{1};              // circuit entry points fuse adjacent single-axis ops
   std::atomic<int> host_overlap{256};          // pw_circuit_host: states of at least this many MiB upload slab-wise, overlapped with the operations that allow it (0 = off)
+  std::atomic<int> c64_pairs{1};              // complex64 register / block kernels: two adjacent fibers per thread (128-bit accesses) when the contiguous untouched run is even
   std::atomic<int> multi_f{0};                 // resident-tile kernel: fibers per thread (0 = auto)
   std::atomic<int> fuse_group{3};              // ... up to this many per HBM pass (resident-tile kernel, 2..4)
   std::atomic<int> mat_pair_max_d{4};          // single-pass U rho U^dagger register tile up to this d

@@ -1035,3 +1035,50 @@ def test_circuit_host_overlaps_upload_with_slab_wise_operations(ad):
                 _lib.set_option("host_overlap", 256)
         assert rel_err(outs[1].reshape(-1, 1), ref) < 1e-12, name
         assert rel_err(outs[1], outs[0]) < 1e-13, name   # (different fusion groups: last-ulp differences)
+
+
+def test_complex64_fiber_pairs_equal_single_fiber_kernels(ad):
+    """complex64 register / block kernels: two adjacent fibers per thread (128-bit accesses) when the
+    contiguous untouched run is even -- the same arithmetic in the same order, so results are
+    bitwise those of the one-fiber kernels; odd runs and unaligned views keep the one-fiber path."""
+    from photon_weave_b200 import _lib
+    from photon_weave_b200.core import ffi
+
+    cd = np.complex64
+    cases = [((6, 5, 4), (0,), "dense"), ((3, 6, 7, 2), (1,), "dense"), ((8, 3, 10), (0,), "dense"),
+             ((5, 5, 6), (0, 1), "bs"), ((4, 6, 6, 14), (1, 2), "bs"), ((6, 6, 9, 2), (0, 1), "bs"),
+             ((7, 3, 4, 4), (0,), "phase"), ((6, 6, 5), (0, 1), "bs"), ((4, 7), (0,), "dense")]
+    _lib.set_option("blocks_min_elems", 0)
+    try:
+        for dims, tg, kind in cases:
+            N = math.prod(dims)
+            t = math.prod(dims[i] for i in tg)
+            if kind == "bs":
+                op = ops.beam_splitter(dims[tg[0]], dims[tg[1]], 0.3 + 0.1 * len(dims))
+            elif kind == "phase":
+                op = ops.phase_operator(t, 0.7)
+            else:
+                op = ops.random_unitary(t, 3)
+            op = np.ascontiguousarray(op).astype(cd)
+            psi = ops.random_state(N, 7, cd)
+            ref = oad.apply_operation_vector(dims, tg, psi.astype(np.complex128), op.astype(np.complex128), True)
+            outs = []
+            for pairs in (1, 0):
+                _lib.set_option("c64_pairs", pairs)
+                outs.append(host(ad.apply_operation_vector(dims, tg, dev(psi), dev(op))))
+            assert np.array_equal(outs[0], outs[1]), (dims, tg, kind)
+            assert rel_err(outs[0], ref) < TOL[cd], (dims, tg, kind)
+        # a view that starts on an odd element: not 16-byte aligned -> one-fiber kernel, same result
+        _lib.set_option("c64_pairs", 1)
+        dims, tg = (6, 4, 6), (0,)
+        N = math.prod(dims)
+        op = np.ascontiguousarray(ops.random_unitary(6, 9)).astype(cd)
+        psi = ops.random_state(N, 11, cd)
+        buf = torch.zeros(N + 1, dtype=torch.complex64, device="cuda")
+        buf[1:] = dev(psi).reshape(-1)
+        res = ffi.apply_vec(buf[1:], dev(op), dims, tg)
+        ref = oad.apply_operation_vector(dims, tg, psi.astype(np.complex128), op.astype(np.complex128), True)
+        assert rel_err(host(res).reshape(-1, 1), ref) < TOL[cd]
+    finally:
+        _lib.set_option("c64_pairs", 1)
+        _lib.set_option("blocks_min_elems", 1 << 18)
