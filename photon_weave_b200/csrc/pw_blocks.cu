@@ -907,6 +907,41 @@ __device__ __forceinline__ void st_pair(double2* p0, double2* p1, const double2 
 template <int NB, bool SAMEW>
 __device__ __forceinline__ void cmma_batch(const double2* w0, const double2* w1, const double2* x0,
                                            const double2* x1, double2* y0, double2* y1) {
+#ifndef PW_CMMA_BATCH_4M
+  // Three real products per complex product (Gauss): with s = xr + xi,
+  //   k = wr s,  yr = k - (wr + wi) xi,  yi = k + (wi - wr) xr
+  // -- 6 DMMAs per item instead of 8 (the FP64 tensor pipe is where these kernels stall:
+  // profiles/r2_ncu_rows_lines.txt), paid with one DADD per state fragment; the operator-side
+  // combinations are formed once per call.  k is accumulated first and seeds both accumulators.
+  double re0[NB], re1[NB], im0[NB], im1[NB], s0[NB], s1[NB];
+  constexpr int NW = SAMEW ? 1 : NB;
+  double n0[NW], d0[NW], n1[NW], d1[NW];
+#pragma unroll
+  for (int b = 0; b < NW; ++b) {
+    n0[b] = -(w0[b].x + w0[b].y); d0[b] = w0[b].y - w0[b].x;
+    n1[b] = -(w1[b].x + w1[b].y); d1[b] = w1[b].y - w1[b].x;
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    re0[b] = re1[b] = 0.0;
+    s0[b] = x0[b].x + x0[b].y;
+    s1[b] = x1[b].x + x1[b].y;
+  }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) dmma8x8x4(re0[b], re1[b], w0[SAMEW ? 0 : b].x, s0[b]);
+#pragma unroll
+  for (int b = 0; b < NB; ++b) dmma8x8x4(re0[b], re1[b], w1[SAMEW ? 0 : b].x, s1[b]);
+#pragma unroll
+  for (int b = 0; b < NB; ++b) { im0[b] = re0[b]; im1[b] = re1[b]; }
+#pragma unroll
+  for (int b = 0; b < NB; ++b) dmma8x8x4(re0[b], re1[b], n0[SAMEW ? 0 : b], x0[b].y);
+#pragma unroll
+  for (int b = 0; b < NB; ++b) dmma8x8x4(im0[b], im1[b], d0[SAMEW ? 0 : b], x0[b].x);
+#pragma unroll
+  for (int b = 0; b < NB; ++b) dmma8x8x4(re0[b], re1[b], n1[SAMEW ? 0 : b], x1[b].y);
+#pragma unroll
+  for (int b = 0; b < NB; ++b) dmma8x8x4(im0[b], im1[b], d1[SAMEW ? 0 : b], x1[b].x);
+#else
   double re0[NB], re1[NB], im0[NB], im1[NB];
 #pragma unroll
   for (int b = 0; b < NB; ++b) re0[b] = re1[b] = im0[b] = im1[b] = 0.0;
@@ -926,6 +961,7 @@ __device__ __forceinline__ void cmma_batch(const double2* w0, const double2* w1,
   for (int b = 0; b < NB; ++b) dmma8x8x4(re0[b], re1[b], -w1[SAMEW ? 0 : b].y, x1[b].y);
 #pragma unroll
   for (int b = 0; b < NB; ++b) dmma8x8x4(im0[b], im1[b], w1[SAMEW ? 0 : b].x, x1[b].y);
+#endif
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
     y0[b] = make_double2(re0[b], im0[b]);
@@ -1117,7 +1153,18 @@ __device__ __forceinline__ void two_sided_mma_body(const S* __restrict__ in, S* 
         V x0 = czero<V>(), x1 = x0;
         if (tig < nx) x0 = ldx(tig, f);
         if (4 + tig < nx) x1 = ldx(4 + tig, f);
-        double re0 = 0.0, re1 = 0.0, im0 = 0.0, im1 = 0.0;
+        double re0 = 0.0, re1 = 0.0, im0, im1;
+#ifndef PW_CMMA_4M
+        // three real products per complex product (see cmma_batch)
+        dmma8x8x4(re0, re1, w0.x, x0.x + x0.y);
+        dmma8x8x4(re0, re1, w1.x, x1.x + x1.y);
+        im0 = re0; im1 = re1;
+        dmma8x8x4(re0, re1, -(w0.x + w0.y), x0.y);
+        dmma8x8x4(im0, im1, w0.y - w0.x, x0.x);
+        dmma8x8x4(re0, re1, -(w1.x + w1.y), x1.y);
+        dmma8x8x4(im0, im1, w1.y - w1.x, x1.x);
+#else
+        im0 = im1 = 0.0;
         dmma8x8x4(re0, re1, w0.x, x0.x);
         dmma8x8x4(im0, im1, w0.y, x0.x);
         dmma8x8x4(re0, re1, -w0.y, x0.y);
@@ -1126,6 +1173,7 @@ __device__ __forceinline__ void two_sided_mma_body(const S* __restrict__ in, S* 
         dmma8x8x4(im0, im1, w1.y, x1.x);
         dmma8x8x4(re0, re1, -w1.y, x1.y);
         dmma8x8x4(im0, im1, w1.x, x1.y);
+#endif
         V v0, v1;
         v0.x = re0; v0.y = im0; v1.x = re1; v1.y = im1;
         sty(nt, 8 * nt + 2 * tig, v0, v1);
@@ -1203,7 +1251,18 @@ __device__ __forceinline__ void two_sided_mma_body(const S* __restrict__ in, S* 
           if constexpr (kTf) {
             cprod_tf32_t(tf_w(r0, r1), x0, x1, v0, v1);
           } else {
-            double re0 = 0.0, re1 = 0.0, im0 = 0.0, im1 = 0.0;
+            double re0 = 0.0, re1 = 0.0, im0, im1;
+#ifndef PW_CMMA_4M
+            // three real products (operands swapped: the state fragment is A, the operator B)
+            dmma8x8x4(re0, re1, x0.x + x0.y, r0.x);
+            dmma8x8x4(re0, re1, x1.x + x1.y, r1.x);
+            im0 = re0; im1 = re1;
+            dmma8x8x4(re0, re1, x0.y, -(r0.x + r0.y));
+            dmma8x8x4(im0, im1, x0.x, r0.y - r0.x);
+            dmma8x8x4(re0, re1, x1.y, -(r1.x + r1.y));
+            dmma8x8x4(im0, im1, x1.x, r1.y - r1.x);
+#else
+            im0 = im1 = 0.0;
             dmma8x8x4(re0, re1, x0.x, r0.x);
             dmma8x8x4(im0, im1, x0.x, r0.y);
             dmma8x8x4(re0, re1, -x0.y, r0.y);
@@ -1212,6 +1271,7 @@ __device__ __forceinline__ void two_sided_mma_body(const S* __restrict__ in, S* 
             dmma8x8x4(im0, im1, x1.x, r1.y);
             dmma8x8x4(re0, re1, -x1.y, r1.y);
             dmma8x8x4(im0, im1, x1.y, r1.x);
+#endif
             v0.x = re0; v0.y = im0; v1.x = re1; v1.y = im1;
           }
           const int64_t b0 = sb[f];

@@ -238,6 +238,9 @@ k_apply_dense_mma(const S* __restrict__ in, S* __restrict__ out,
 #pragma unroll
           for (int n = 0; n < 4; ++n) x[n] = j < t ? wide(xcol[j * FIB + 8 * n]) : make_double2(0.0, 0.0);
         }
+        // (Gauss' three-product complex multiply -- 12 DMMAs per step instead of 16 -- measured SLOWER
+        //  here: 28.6-30.9 against 25.1 ms, also with the sums software-pipelined, although it gains
+        //  3-7 % in the two-sided and row-tile kernels: see cmma_batch in pw_blocks.cu)
         // step-major issue order: the eight accumulator chains advance together (a warp issues
         // in order; consecutive DMMAs must be independent to keep the tensor pipe busy)
 #pragma unroll

@@ -60,6 +60,38 @@ k_probe_dmma(const int iters, double* __restrict__ sink) {
   if (s == 12345.678) sink[0] = s;
 }
 
+// DMMA interleaved with scalar adds: 6 DMMAs + NADD independent adds per group (FP64 adds: the
+// price of Gauss' three-product complex multiply on the FP64 tensor cores; FP32 adds: control)
+template <int NADD, bool F64>
+__global__ void __launch_bounds__(kProbeBlock)
+k_probe_dmma_mix(const int iters, double* __restrict__ sink) {
+  double c0[6], c1[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { c0[i] = 0; c1[i] = 0; }
+  double ad[NADD];
+  float af[NADD];
+#pragma unroll
+  for (int i = 0; i < NADD; ++i) { ad[i] = 1e-3 * (threadIdx.x + i); af[i] = (float)ad[i]; }
+  const double a = 1e-3 * (threadIdx.x & 31), b = 1.0 + 1e-6 * (threadIdx.x >> 5);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c0[i]), "+d"(c1[i]) : "d"(a), "d"(b));
+      if (i < NADD) {
+        if (F64) asm volatile("add.f64 %0, %0, %1;" : "+d"(ad[i]) : "d"(b));
+        else     asm volatile("add.f32 %0, %0, %1;" : "+f"(af[i]) : "f"(1.5f));
+      }
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) s += c0[i] + c1[i];
+#pragma unroll
+  for (int i = 0; i < NADD; ++i) s += ad[i] + af[i];
+  if (s == 12345.678) sink[0] = s;
+}
+
 // legacy warp-level TF32 tensor path (mma.sync m16n8k8): what an error-compensated 3 x TF32
 // complex64 kernel would run on without tcgen05 / TMEM plumbing
 __global__ void __launch_bounds__(kProbeBlock)
@@ -88,10 +120,11 @@ k_probe_tf32(const int iters, double* __restrict__ sink) {
 
 using namespace pw;
 
-// kind 0: FP64 FMA, 1: FP64 mma.sync m8n8k4 (DMMA), 2: FP32 FMA, 3: TF32 mma.sync m16n8k8.  Enqueues ONE kernel of `iters`
+// kind 0: FP64 FMA, 1: FP64 mma.sync m8n8k4 (DMMA), 2: FP32 FMA, 3: TF32 mma.sync m16n8k8,
+// 4..7: DMMA interleaved with scalar adds (MMA flops only are counted).  Enqueues ONE kernel of `iters`
 // iterations on `stream`; *flops receives the real flops it executes.  `sink` is one device double.
 extern "C" int pw_probe_arith(int kind, int iters, double* sink, double* flops, void* stream) {
-  if (!sink || !flops || iters < 1 || kind < 0 || kind > 3) return PW_ERR_INVALID;
+  if (!sink || !flops || iters < 1 || kind < 0 || kind > 7) return PW_ERR_INVALID;
   const int grid = kNumSMs * kProbeCtas;
   cudaStream_t s = (cudaStream_t)stream;
   const double threads = (double)grid * kProbeBlock;
@@ -104,6 +137,13 @@ extern "C" int pw_probe_arith(int kind, int iters, double* sink, double* flops, 
   } else if (kind == 3) {
     k_probe_tf32<<<grid, kProbeBlock, 0, s>>>(iters, sink);
     *flops = (threads / 32.0) * 8.0 * 2048.0 * iters;  // 8 MMAs of 2*16*8*8 flops per warp iteration
+  } else if (kind >= 4) {
+    // 4: 6 DMMA + 1 FP64 add, 5: + 2 FP64 adds, 6: + 3 FP64 adds, 7: + 2 FP32 adds; MMA flops only
+    if (kind == 4) k_probe_dmma_mix<1, true><<<grid, kProbeBlock, 0, s>>>(iters, sink);
+    else if (kind == 5) k_probe_dmma_mix<2, true><<<grid, kProbeBlock, 0, s>>>(iters, sink);
+    else if (kind == 6) k_probe_dmma_mix<3, true><<<grid, kProbeBlock, 0, s>>>(iters, sink);
+    else k_probe_dmma_mix<2, false><<<grid, kProbeBlock, 0, s>>>(iters, sink);
+    *flops = (threads / 32.0) * 6.0 * 512.0 * iters;
   } else {
     k_probe_dmma<<<grid, kProbeBlock, 0, s>>>(iters, sink);
     *flops = (threads / 32.0) * 8.0 * 512.0 * iters;  // 8 MMAs of 2*8*8*4 flops per warp iteration

@@ -380,8 +380,10 @@ k_reduced_wide(const V* __restrict__ x, const FiberMap fm, const TargetMap tm, V
   if (threadIdx.x == 0) { V v; v.x = re; v.y = im; out[blockIdx.x] = v; }
 }
 
-// t <= 8: Hermitian accumulators in registers
-template <typename V, int T>
+// t <= 8: Hermitian accumulators in registers.  PAIR (complex64, even contiguous untouched run,
+// `fm` = fiber pairs): two adjacent fibers per thread from one 128-bit load each -- with 8-byte
+// loads the kernel sat at 52 % of the complex64 roof (latency-bound at ~100 registers).
+template <typename V, int T, bool PAIR>
 __global__ void __launch_bounds__(256)
 k_reduced_small(const V* __restrict__ x, const FiberMap fm, const TargetMap tm,
                 double2* __restrict__ partial) {
@@ -393,12 +395,7 @@ k_reduced_small(const V* __restrict__ x, const FiberMap fm, const TargetMap tm,
   double re[NP], im[NP];
 #pragma unroll
   for (int q = 0; q < NP; ++q) { re[q] = 0.0; im[q] = 0.0; }
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < fm.nfib; f += stride) {
-    const int64_t base = fm.base(f);
-    double vx[T], vy[T];
-#pragma unroll
-    for (int j = 0; j < T; ++j) { const V v = __ldcg(x + base + s_off[j]); vx[j] = v.x; vy[j] = v.y; }
+  auto accumulate = [&](const double (&vx)[T], const double (&vy)[T]) {
     int q = 0;
 #pragma unroll
     for (int a = 0; a < T; ++a)
@@ -407,6 +404,25 @@ k_reduced_small(const V* __restrict__ x, const FiberMap fm, const TargetMap tm,
         re[q] = fma(vx[a], vx[b], fma(vy[a], vy[b], re[q]));   // xa * conj(xb)
         if (b != a) im[q] = fma(vy[a], vx[b], fma(-vx[a], vy[b], im[q]));
       }
+  };
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < fm.nfib; f += stride) {
+    const int64_t base = fm.base(f);
+    double vx[T], vy[T];
+    if constexpr (PAIR) {
+      double wx[T], wy[T];
+#pragma unroll
+      for (int j = 0; j < T; ++j) {
+        const C64x2 v = ld_c64x2((const float2*)x + base + s_off[j]);
+        vx[j] = v.a.x; vy[j] = v.a.y; wx[j] = v.b.x; wy[j] = v.b.y;
+      }
+      accumulate(vx, vy);
+      accumulate(wx, wy);
+    } else {
+#pragma unroll
+      for (int j = 0; j < T; ++j) { const V v = __ldcg(x + base + s_off[j]); vx[j] = v.x; vy[j] = v.y; }
+      accumulate(vx, vy);
+    }
   }
 #pragma unroll
   for (int q = 0; q < NP; ++q) {
@@ -416,20 +432,31 @@ k_reduced_small(const V* __restrict__ x, const FiberMap fm, const TargetMap tm,
   }
 }
 
+template <typename V, bool PAIR>
+static bool launch_reduced_small_p(const V* x, const FiberMap& fm, const TargetMap& tm, int nblocks,
+                                   double2* partial, cudaStream_t s) {
+  switch (tm.t) {
+    case 1: k_reduced_small<V, 1, PAIR><<<nblocks, 256, 0, s>>>(x, fm, tm, partial); return true;
+    case 2: k_reduced_small<V, 2, PAIR><<<nblocks, 256, 0, s>>>(x, fm, tm, partial); return true;
+    case 3: k_reduced_small<V, 3, PAIR><<<nblocks, 256, 0, s>>>(x, fm, tm, partial); return true;
+    case 4: k_reduced_small<V, 4, PAIR><<<nblocks, 256, 0, s>>>(x, fm, tm, partial); return true;
+    case 5: k_reduced_small<V, 5, PAIR><<<nblocks, 256, 0, s>>>(x, fm, tm, partial); return true;
+    case 6: k_reduced_small<V, 6, PAIR><<<nblocks, 256, 0, s>>>(x, fm, tm, partial); return true;
+    case 7: k_reduced_small<V, 7, PAIR><<<nblocks, 256, 0, s>>>(x, fm, tm, partial); return true;
+    case 8: k_reduced_small<V, 8, PAIR><<<nblocks, 256, 0, s>>>(x, fm, tm, partial); return true;
+    default: return false;
+  }
+}
+
 template <typename V>
 static bool launch_reduced_small(const V* x, const Plan& p, int nblocks, double2* partial,
                                  cudaStream_t s) {
-  switch (p.tm.t) {
-    case 1: k_reduced_small<V, 1><<<nblocks, 256, 0, s>>>(x, p.fm, p.tm, partial); return true;
-    case 2: k_reduced_small<V, 2><<<nblocks, 256, 0, s>>>(x, p.fm, p.tm, partial); return true;
-    case 3: k_reduced_small<V, 3><<<nblocks, 256, 0, s>>>(x, p.fm, p.tm, partial); return true;
-    case 4: k_reduced_small<V, 4><<<nblocks, 256, 0, s>>>(x, p.fm, p.tm, partial); return true;
-    case 5: k_reduced_small<V, 5><<<nblocks, 256, 0, s>>>(x, p.fm, p.tm, partial); return true;
-    case 6: k_reduced_small<V, 6><<<nblocks, 256, 0, s>>>(x, p.fm, p.tm, partial); return true;
-    case 7: k_reduced_small<V, 7><<<nblocks, 256, 0, s>>>(x, p.fm, p.tm, partial); return true;
-    case 8: k_reduced_small<V, 8><<<nblocks, 256, 0, s>>>(x, p.fm, p.tm, partial); return true;
-    default: return false;
+  if constexpr (sizeof(V) == 8) {
+    FiberMap pm;
+    if (options().c64_pairs.load(std::memory_order_relaxed) && pair_fiber_map(p.fm, x, x, &pm))
+      return launch_reduced_small_p<V, true>(x, pm, p.tm, nblocks, partial, s);
   }
+  return launch_reduced_small_p<V, false>(x, p.fm, p.tm, nblocks, partial, s);
 }
 
 template <typename V>

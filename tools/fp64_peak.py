@@ -18,7 +18,10 @@ from photon_weave_b200 import _lib  # noqa: E402
 lib = _lib.load()
 sink = torch.zeros(1, dtype=torch.float64, device="cuda")
 out = {}
-for kind, name in ((0, "fp64_fma"), (1, "fp64_mma_m8n8k4"), (2, "fp32_fma"), (3, "tf32_mma_sync_m16n8k8")):
+KINDS = ((0, "fp64_fma"), (1, "fp64_mma_m8n8k4"), (2, "fp32_fma"), (3, "tf32_mma_sync_m16n8k8"),
+         (4, "fp64_mma_with_1_dadd_per_6"), (5, "fp64_mma_with_2_dadd_per_6"), (6, "fp64_mma_with_3_dadd_per_6"),
+         (7, "fp64_mma_with_2_fadd_per_6"))
+for kind, name in KINDS:
     flops = C.c_double(0)
     best = 0.0
     for iters in (2000, 20000):

@@ -20,18 +20,27 @@ for l in sass[start:end]:
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
     if m:
         seq.append((cur, m.group(2)))
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+# <rep> may also be the CSV already exported on the GPU box (`ncu -i x.ncu-rep --page source --csv`)
+out = open(rep).read() if rep.endswith(".csv") else \
+    subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-hdr, data = rows[1], rows[2:]
+h0 = next(i for i, r in enumerate(rows) if "Instructions Executed" in r)
+hdr, data = rows[h0], rows[h0 + 1:]
+reasons = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "(" not in h]
 ia, ist = hdr.index("Instructions Executed"), hdr.index("Warp Stall Sampling (All Samples)")
 assert len(seq) == len(data), (len(seq), len(data))
-agg, st = {}, {}
+agg, st, why = {}, {}, {}
 for (ln, _), r in zip(seq, data):
     agg[ln] = agg.get(ln, 0) + int(r[ia])
     st[ln] = st.get(ln, 0) + int(r[ist])
+    w = why.setdefault(ln, {})
+    for i in reasons:
+        if r[i] not in ("", "0"):
+            w[hdr[i]] = w.get(hdr[i], 0) + int(float(r[i]))
 tot, tst = sum(agg.values()), sum(st.values())
 lines = open(src).read().split("\n")
 print(f"instructions {tot}, stall samples {tst}")
 for ln, c in sorted(st.items(), key=lambda x: -x[1])[:top]:
     text = lines[ln - 1].strip()[:100] if ln and ln > 0 else "(other file)"
-    print(f"stall {c / tst:6.1%}  inst {agg[ln] / tot:6.1%}  L{ln}: {text}")
+    top3 = " ".join(f"{k[6:]}={v}" for k, v in sorted(why.get(ln, {}).items(), key=lambda x: -x[1])[:3])
+    print(f"stall {c / tst:6.1%}  inst {agg[ln] / tot:6.1%}  L{ln}: {text}  [{top3}]")
