@@ -725,16 +725,6 @@ class ShardedTensor:
                 src = self.peers.ptrs[buf][src_rank] + self.rank * chunk * self.peers.esize
                 self.backend.peer_copy(dst, src, chunk * self.peers.esize)
             return
-        if dst_rank == self.rank:        # last step: the own chunk stays
-            if cuda:
-                ev = torch.cuda.Event()
-                ev.record()
-                with torch.cuda.stream(side):
-                    side.wait_event(ev)
-                    dst.copy_(piece)
-            else:
-                dst.copy_(piece)
-            return
         reqs = [self.dist.P2POp(self.dist.isend, torch.view_as_real(piece), dst_rank),
                 self.dist.P2POp(self.dist.irecv, torch.view_as_real(dst), src_rank)]
         if cuda:
