@@ -25,6 +25,52 @@ def dev(x):
 
 REPS = 3
 HEADLINE = len(sys.argv) > 1 and sys.argv[1] == "headline"   # only the three classes bench.py quotes
+LATE = len(sys.argv) > 1 and sys.argv[1] == "late"           # the kernels added after r2_ncu_all_classes.json
+
+
+def late_round():
+    """complex64 fiber-pair kernels, complex64 TF32 x 3 and complex128 Gauss two-sided kernels."""
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    d, modes = 6, 12
+    dims = (d,) * modes
+    N = d**modes
+    a = torch.view_as_complex(torch.randn(N, 2, generator=gen, device="cuda", dtype=torch.float32))
+    b = torch.empty_like(a)
+    c64 = lambda x: dev(x).to(torch.complex64)
+    u, bs = c64(ops.random_unitary(d, 1)), c64(ops.beam_splitter(d, d, math.pi / 4))
+    for _ in range(2):
+        ffi.apply_vec(a, u, dims, (0,), out=b)          # k_apply_small_c64x2
+        ffi.apply_vec(a, bs, dims, (0, 1), out=b)       # k_apply_blocks_c64x2
+        ffi.reduced_from_vec(a, dims, (3,))             # k_reduced_small<.., PAIR>
+    torch.cuda.synchronize()
+    del a, b
+    torch.cuda.empty_cache()
+    d, modes = 8, 5
+    dims = (d,) * modes
+    D = d**modes
+    for dt in (torch.float32, torch.float64):
+        rho = torch.view_as_complex(torch.randn(D * D, 2, generator=gen, device="cuda", dtype=dt))
+        out = torch.empty_like(rho)
+        cast = (lambda x: dev(x).to(torch.complex64)) if dt == torch.float32 else dev
+        loss, u8 = cast(ops.loss_channel(d, 0.1)), cast(ops.random_unitary(d, 1))
+        bs8 = cast(ops.beam_splitter(d, d, math.pi / 4))
+        for _ in range(2):
+            if dt == torch.float32:
+                ffi.kraus_mat(rho, loss, dims, (2,), out=out)     # k_apply_blocks_c64x2 (superoperator)
+            ffi.apply_mat(rho, u8, dims, (2,), out=out)           # k_two_sided_mma (TF32 x 3 / Gauss DMMA)
+            ffi.apply_mat(rho, bs8, dims, (1, 2), out=out)        # k_two_sided_mma, super-blocks
+            ffi.apply_mat(rho, bs8, dims, (3, 4), out=out)        # k_two_sided_mma_rows
+            if dt == torch.float64:
+                ffi.kraus_mat(rho, loss, dims, (4,), out=out)     # k_apply_blocks_seg_mma
+        torch.cuda.synchronize()
+        del rho, out
+        torch.cuda.empty_cache()
+    print("ncu targets (late) done")
+
+
+if LATE:
+    late_round()
+    sys.exit(0)
 d, modes = 6, 12
 dims = (d,) * modes
 N = d**modes
