@@ -746,6 +746,17 @@ def run_small_configs(torch, ffi):
         return oad.trace_out_vector(dims, (0,), x, True), oad.trace_out_vector(dims, (1,), x, True)
 
     res["mach_zehnder_5_calls"] = {"gpu_us": gpu_us(mzi_gpu), "cpu_port_us": cpu_us(mzi_cpu)}
+    # the same five calls captured once and replayed as ONE CUDA graph launch (core/graphs.py)
+    from photon_weave_b200.core.graphs import GraphedCalls
+
+    def mzi_seq(x):
+        x = ad.apply_operation_vector(dims, (0, 1), x, d_bs)
+        x = ad.apply_operation_vector(dims, (0,), x, d_ph)
+        x = ad.apply_operation_vector(dims, (0, 1), x, d_bs)
+        return ad.trace_out_vector(dims, (0,), x), ad.trace_out_vector(dims, (1,), x)
+
+    mzi_graph = GraphedCalls(mzi_seq, d_psi)
+    res["mach_zehnder_5_calls"]["gpu_graph_replay_us"] = gpu_us(lambda: mzi_graph())
     # configs[1] lossy 4-mode circuit on a density matrix, cutoff 5 (6.25 MB): BS + loss channels
     dims = (5, 5, 5, 5)
     D = 625
@@ -801,9 +812,12 @@ def run_small_configs(torch, ffi):
         "note": "128x128 propagator on 2^18 states = GEMM on the FP64 tensor cores (k_apply_dense_mma, t = 128); "
                 "measured DMMA roof 37.1 TFLOP/s (profiles/r2_arith_peaks.json)"}
     del batch
+    jc_graph = GraphedCalls(lambda p: (lambda x: (x, ad.trace_out_vector(dims, (1,), x)))(
+        ad.apply_operation_vector(dims, (0, 1), p, d_U)), d_psi.reshape(-1, 1).clone())
     res["jaynes_cummings_10k_steps"] = {
         "fused_kernel_total_ms": fused_s * 1e3, "fused_us_per_step": fused_s / nsteps * 1e6,
         "per_call_api_us_per_step": gpu_us(jc_step_gpu, 200),
+        "graph_replay_us_per_step": gpu_us(lambda: jc_graph(), 200),
         "cpu_port_us_per_step": cpu_us(jc_step_cpu, 200),
         "norm_check": float(np.trace(red_host[-1].numpy()).real)}
     return res

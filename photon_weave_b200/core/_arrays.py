@@ -41,9 +41,12 @@ except AttributeError:  # pragma: no cover
     _raw_stream = None
 
 
+_get_device = getattr(torch._C, "_cuda_getDevice", None)   # torch.cuda.current_device() minus its lazy-init check
+
+
 def stream_ptr() -> int:
     if _raw_stream is not None:
-        return _raw_stream(torch.cuda.current_device())
+        return _raw_stream(_get_device() if _get_device is not None else torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -104,7 +104,9 @@ def apply_operation_vector(
         out = T.ApplyVec.apply(ps, op, dims, tgt)
     else:
         out = ffi.apply_vec(ps, op, dims, tgt)
-    return A.back(out.reshape(shape), host)
+    if out.shape != shape:   # (N, 1) in, (N, 1) out is the common case: no view to build
+        out = out.reshape(shape)
+    return A.back(out, host)
 
 
 def _two_sided(ps, ops, state_dims, target_indices, single: bool):
@@ -316,12 +318,12 @@ def trace_out_vector(state_dims, target_indices, product_state, use_contraction:
     """
     state_dims = tuple(state_dims)
     target_indices = tuple(target_indices)
-    keep = sorted(target_indices) if use_contraction else list(target_indices)
+    keep = tuple(sorted(target_indices)) if use_contraction else target_indices
     if T.current_batch():
         raise T.NotBatchable("partial trace of a batch: one call per batch element")
     host, ps, _ = _prep(product_state)
     if T.needs_grad(ps):
-        return T.ReducedFromVec.apply(ps, state_dims, tuple(keep))
+        return T.ReducedFromVec.apply(ps, state_dims, keep)
     return A.back(ffi.reduced_from_vec(ps, state_dims, keep), host)
 
 

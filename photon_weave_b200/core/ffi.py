@@ -31,7 +31,19 @@ def pin_operator(op: torch.Tensor) -> torch.Tensor:
     return op
 
 
+_COMMON_CACHE: dict = {}
+
+
 def _common(dims: Sequence[int], idx: Sequence[int]):
+    """(ctypes dims, n, ctypes indices, count); cached per (dims, indices) pair of tuples -- the
+    launch-bound configs spend their time on the host."""
+    if type(dims) is tuple and type(idx) is tuple:
+        hit = _COMMON_CACHE.get((dims, idx))
+        if hit is None:
+            hit = (_lib.i64_array(dims), len(dims), _lib.i32_array(idx), len(idx))
+            if len(_COMMON_CACHE) < 4096:
+                _COMMON_CACHE[(dims, idx)] = hit
+        return hit
     return _lib.i64_array(dims), len(dims), _lib.i32_array(idx), len(idx)
 
 

@@ -62,7 +62,10 @@ def _h(op: torch.Tensor) -> torch.Tensor:
 
 
 def needs_grad(*xs: Any) -> bool:
-    return torch.is_grad_enabled() and any(isinstance(x, torch.Tensor) and x.requires_grad for x in xs)
+    for x in xs:   # plain loop: this sits on the per-call path of the launch-bound configs
+        if isinstance(x, torch.Tensor) and x.requires_grad:
+            return torch.is_grad_enabled()
+    return False
 
 
 # --------------------------------------------------------------------------------------

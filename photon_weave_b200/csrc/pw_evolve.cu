@@ -124,11 +124,51 @@ k_apply_rows(const V* __restrict__ in, V* __restrict__ out, const V* __restrict_
   }
 }
 
+// The same for a HANDFUL of fibers (one Jaynes-Cummings state: a single fiber): one WARP per output
+// row -- coalesced operator rows, a shuffle reduction -- and 8 rows per block, so a 128 x 128
+// operator on one state runs on 16 blocks instead of on 128 threads of one (16 -> ~3 us).
+template <typename V>
+__global__ void __launch_bounds__(256)
+k_apply_rows_warp(const V* __restrict__ in, V* __restrict__ out, const V* __restrict__ op,
+                  const FiberMap fm, const TargetMap tm, const bool conj_op) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  V* sx = (V*)s_raw;
+  const uint32_t t = tm.t;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t base = fm.base(blockIdx.y);
+  for (uint32_t b = threadIdx.x; b < t; b += blockDim.x) sx[b] = in[base + tm.offset(b)];
+  __syncthreads();
+  const uint32_t a = blockIdx.x * 8 + warp;
+  if (a >= t) return;
+  V acc = czero<V>();
+  const V* row = op + (size_t)a * t;
+  for (uint32_t b = lane; b < t; b += 32) {
+    V o = row[b];
+    if (conj_op) o.y = -o.y;
+    cfma(acc, o, sx[b]);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    acc.x += __shfl_down_sync(0xffffffffu, acc.x, o);
+    acc.y += __shfl_down_sync(0xffffffffu, acc.y, o);
+  }
+  if (lane == 0) out[base + tm.offset(a)] = acc;
+}
+
 int launch_apply_rows(const void* in, void* out, const void* op, const Plan& p, int dtype,
                       bool conj_op, cudaStream_t s) {
   const size_t es = dtype == PW_C128 ? 16 : 8;
   const size_t smem = (size_t)p.tm.t * es;
   if (smem > 48 * 1024 || in == out) return PW_ERR_UNSUPPORTED;
+  if (p.fm.nfib <= 64 && p.tm.t >= 32) {
+    const dim3 grid2((p.tm.t + 7) / 8, (unsigned)p.fm.nfib);
+    if (dtype == PW_C128)
+      k_apply_rows_warp<double2><<<grid2, 256, smem, s>>>((const double2*)in, (double2*)out, (const double2*)op, p.fm, p.tm, conj_op);
+    else
+      k_apply_rows_warp<float2><<<grid2, 256, smem, s>>>((const float2*)in, (float2*)out, (const float2*)op, p.fm, p.tm, conj_op);
+    g_paths[1].fetch_add(1, std::memory_order_relaxed);
+    PW_LAUNCHED();
+    return PW_OK;
+  }
   const int grid = (int)(p.fm.nfib < (uint64_t)kNumSMs * 8 ? p.fm.nfib : (uint64_t)kNumSMs * 8);
   if (dtype == PW_C128)
     k_apply_rows<double2><<<grid, 256, smem, s>>>((const double2*)in, (double2*)out, (const double2*)op, p.fm, p.tm, conj_op);

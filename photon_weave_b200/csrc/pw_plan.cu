@@ -52,7 +52,13 @@ PlanScope::PlanScope(const void* op, int tag, int dtype, int K, const int64_t* d
   }
   ctx.e = e;
   ctx.replay = e->filled;
-  if (ctx.replay && stream != e->fill_stream && e->ready) cudaStreamWaitEvent(stream, e->ready, 0);
+  if (ctx.replay && stream != e->fill_stream && e->ready) {
+    // inside a CUDA-graph capture the recording finished long ago (the caller warmed up and
+    // synchronised before capturing): no cross-stream edge to an event from outside the capture
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap == cudaStreamCaptureStatusNone)
+      cudaStreamWaitEvent(stream, e->ready, 0);
+  }
   g_plan_ctx = &ctx;
   active = true;
 }

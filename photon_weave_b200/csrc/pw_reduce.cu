@@ -465,6 +465,13 @@ static int reduced_impl(const V* x, V* out, const Plan& p, cudaStream_t s) {
   const size_t npair = (size_t)t * (t + 1) / 2;
   const size_t smem = npair * kRedBlock * sizeof(double2) + 4 * sizeof(double) +
                       t * sizeof(int64_t) + (size_t)t * kRedBlock * sizeof(double2);
+  // launch-bound states (the Mach-Zehnder / Jaynes-Cummings configs): ONE launch, one block per
+  // output entry, no scratch allocation, instead of partial sums + finalize
+  if (t <= 8 && (uint64_t)p.fm.nfib * t <= 16384) {
+    k_reduced_wide<V><<<t * t, kRedBlock, 0, s>>>(x, p.fm, p.tm, out);
+    PW_LAUNCHED();
+    return PW_OK;
+  }
   if (t <= 8) {
     const int nblocks = grid_for(p.fm.nfib, 256, 2);
     Scratch partial;

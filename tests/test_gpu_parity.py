@@ -1082,3 +1082,20 @@ def test_complex64_fiber_pairs_equal_single_fiber_kernels(ad):
     finally:
         _lib.set_option("c64_pairs", 1)
         _lib.set_option("blocks_min_elems", 1 << 18)
+
+
+@pytest.mark.parametrize("cdtype", [np.complex128, np.complex64])
+def test_row_parallel_kernels_for_launch_bound_states(ad, cdtype):
+    """Dense operators on states below the analysis threshold: one block per fiber, or -- for a
+    handful of fibers, the Jaynes-Cummings shape -- one warp per output row (k_apply_rows_warp)."""
+    tol = TOL[cdtype]
+    for dims, tg, seed in [((64, 2), (0, 1), 1), ((64, 2), (1, 0), 2), ((100,), (0,), 3), ((2, 40, 3), (1,), 4),
+                           ((3, 33), (1,), 5), ((33, 3), (0,), 6), ((70, 9), (0,), 7), ((5, 12, 4, 3), (1, 3), 8),
+                           ((200, 11), (0,), 9), ((9, 32), (1,), 10)]:
+        N = math.prod(dims)
+        t = math.prod(dims[i] for i in tg)
+        psi = ops.random_state(N, seed, cdtype)
+        op = ops.random_unitary(t, 20 + seed).astype(cdtype)
+        ref = oad.apply_operation_vector(dims, tg, psi.astype(np.complex128), op.astype(np.complex128), True)
+        out = host(ad.apply_operation_vector(dims, tg, dev(psi), dev(op)))
+        assert rel_err(out, ref) < tol, (dims, tg)
