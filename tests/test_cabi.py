@@ -76,3 +76,23 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_no_cpu_fallback_without_a_cuda_device():
+    """The product path fails loudly where there is no GPU (this container): no silent CPU route."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from photon_weave_b200.core import _arrays as A
+    from photon_weave_b200.core.graphs import GraphedCalls
+
+    with pytest.raises(RuntimeError):
+        A.require_cuda()
+    with pytest.raises(RuntimeError):
+        GraphedCalls(lambda x: x, torch.zeros(2))
+    from photon_weave_b200.core import adapters as ad
+    import numpy as np
+
+    with pytest.raises(RuntimeError):
+        ad.apply_operation_vector((2,), (0,), np.array([[1.0], [0.0]]), np.eye(2))
