@@ -9,9 +9,10 @@
 //   innermost untouched run (so a row of the tile is a contiguous piece of >= 64 bytes of memory;
 //   when the innermost axis of the tensor is itself a target, j's last digit is the contiguous
 //   direction instead and the tile is loaded j-fastest).
-//   load (cp.async, double buffered) -> k in-place passes, one operator each, a thread owns whole
-//   fibers of that operator (D loads, D*D complex FMAs against the operator broadcast from shared
-//   memory, D stores; __syncthreads between passes) -> coalesced store.
+//   load (cp.async; tiles are single-buffered, several small CTAs per SM overlap each other's
+//   phases) -> k in-place passes, one operator each, a thread owns F whole fibers of that operator
+//   (D loads each, D*D complex FMAs against the operator broadcast from shared memory, D stores;
+//   __syncthreads between passes) -> coalesced store.
 //
 // Per amplitude and operator: 2 shared-memory accesses and D complex FMAs; the k = 3, d = 6 case
 // needs 144 real flops per 32 bytes of HBM traffic, i.e. it sits near the corner of the HBM and
