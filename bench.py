@@ -541,12 +541,16 @@ def pinned_near_gpu(torch, n):
 
     before = os.sched_getaffinity(0)
     near = _gpu_local_cpus(torch.cuda.current_device())
-    if near:
-        os.sched_setaffinity(0, near)
+    try:
+        if near:
+            os.sched_setaffinity(0, near)
+    except OSError:      # not allowed in this container: allocate wherever the process runs
+        near = None
     try:
         return torch.empty(n, dtype=torch.complex128, pin_memory=True)
     finally:
-        os.sched_setaffinity(0, before)
+        if near:
+            os.sched_setaffinity(0, before)
 
 
 def run_e2e_prepare(args, torch, dev_state, N):

@@ -285,10 +285,16 @@ def _time_e2e(args, dist, rank, world, runner, st, units):
     steps = max(1, min(args.steps, 2 * getattr(args, "e2e_steps", 2)))
     before = os.sched_getaffinity(0)
     near = _gpu_local_cpus(torch.cuda.current_device())
-    if near:
-        os.sched_setaffinity(0, near)
-    host = torch.empty(st.local.numel(), dtype=st.local.dtype, pin_memory=True)
-    os.sched_setaffinity(0, before)
+    try:
+        if near:
+            os.sched_setaffinity(0, near)
+    except OSError:      # not allowed in this container: allocate wherever the rank runs
+        near = None
+    try:
+        host = torch.empty(st.local.numel(), dtype=st.local.dtype, pin_memory=True)
+    finally:
+        if near:
+            os.sched_setaffinity(0, before)
     st.store_host(host)
     torch.cuda.synchronize()
 
