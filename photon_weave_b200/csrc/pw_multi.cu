@@ -57,7 +57,8 @@ __device__ __forceinline__ void mu_wait() { asm volatile("cp.async.wait_group %0
 // fibers, which is what keeps the kernel off the shared-memory instruction roof: with one fiber
 // per thread the 48 LDS/STS per 144 DFMAs bound it at 25 ms for three operators (measured);
 // F = 3 needs 24.  Tiles are single-buffered: several small CTAs per SM overlap each other's
-// load / compute / store phases.
+// load / compute / store phases (a second buffer per CTA with the next tile's cp.async in flight
+// during the passes measured SLOWER: 28.3 against 23.6 ms for three operators on the same box).
 // CTA size / resident CTAs per fibers-per-thread: F fibers of D complex values live in registers
 constexpr int mu_threads(int F) { return F == 1 ? 384 : (F == 2 ? 192 : (F == 3 ? 128 : 96)); }
 constexpr int mu_ctas(int F) { return F == 1 ? 2 : (F == 2 ? 3 : 4); }  // (F = 3 at 5 CTAs spills: 28 ms against 22.9)
