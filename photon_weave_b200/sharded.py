@@ -614,7 +614,16 @@ class ShardedTensor:
             mark("end")
             return info
         needed = {g for i in s2 for g in ops[i][1]}
-        positions, slots = self._plan_swap(needed, next_shard)
+        try:
+            positions, slots = self._plan_swap(needed, next_shard)
+        except RuntimeError:
+            # the post-swap operations together touch so many subsystems that ONE swap cannot make
+            # them all local: every operation on its own (each needs only its own subsystems local)
+            for o, a in ops:
+                self.ensure_local(a, next_shard)
+                self._apply_local(o, a)
+            mark("end")
+            return info
         k = len(positions)
         out_g = {self.vaxes[p].g for p in positions}
         stage = [2 if i in s2 else (0 if set(a) & out_g else 1) for i, (_, a) in enumerate(ops)]
@@ -791,6 +800,23 @@ class ShardedTensor:
                 off += ((idx[v.g] // v.weight) % v.extent) * strides[i]
         return own, off
 
+    def _check_respreadable(self, post_vaxes: List[VAxis], measured: Sequence[int]) -> None:
+        """Raise BEFORE any collective when the post-measurement state cannot be spread over all
+        ranks again (its remaining local axes cannot supply the factor the measured sharded parts
+        held) -- every rank sees the same layout, so every rank raises the same error."""
+        f = math.prod(s.extent for s in self.sparts if s.g in measured)
+        if f == 1:
+            return
+        probe = ShardedTensor.__new__(type(self))
+        probe.vaxes, probe._shardable = list(post_vaxes), self._shardable
+        try:
+            ShardedTensor._choose_parts(probe, self._prime_factors(f), set(), None)
+        except RuntimeError:
+            raise ValueError(
+                f"measuring subsystems {tuple(measured)} leaves a state whose local axes "
+                f"{[(v.g, v.extent) for v in post_vaxes]} cannot be spread over the {f} ranks that shared "
+                "the measured axes; measure on fewer ranks or gather the state first") from None
+
     def _respread(self, post: Optional[torch.Tensor], post_vaxes: List[VAxis], measured: Sequence[int],
                   idx: Dict[int, int]) -> Tuple[torch.Tensor, List[VAxis], List[VAxis]]:
         """After a collapse on the owning ranks: spread the post state over ALL ranks again.
@@ -963,11 +989,12 @@ class ShardedStateVector(ShardedTensor):
         all-reduced probabilities with the same key, so the outcome is identical everywhere;
         the collapse happens on the ranks that own the outcome's sharded digits."""
         axes = list(axes)
+        parts, rest = self._split(axes)
+        self._check_respreadable([self.vaxes[i] for i in rest], axes)
         probs = self.probs(axes)
         outcome_t = self.backend.draw(probs, key, self.local.dtype)
         outcome = int(outcome_t.item())
         idx = self._outcome_digits(outcome, axes)
-        parts, rest = self._split(axes)
         st, ext = self.local_strides(), self.local_dims
         own, off = self._owner_and_offset(idx, {i: st[i] for i in parts})
         post = None
@@ -1108,15 +1135,17 @@ class ShardedDensityMatrix(ShardedTensor):
         """Projective measurement (core/kernels.py:209-227): post = rho[o,:,o,:] / (p_o + 1e-18)
         taken on the ranks that own outcome o's rows, then spread over all ranks again."""
         axes = list(axes)
+        parts, rest = self._row_split(axes)
+        rest_cols = [g for g in range(self.n) if g not in axes]
+        self._check_respreadable([self.vaxes[i] for i in rest] +
+                                 [VAxis(self.n + g, self.dims[g], 1) for g in rest_cols], axes)
         probs = self.probs(axes)
         outcome_t = self.backend.draw(probs, key, self.local.dtype)
         outcome = int(outcome_t.item())
         idx = self._outcome_digits(outcome, axes)
         st, ext, cs = self.local_strides(), self.local_dims, self._col_stride()
-        parts, rest = self._row_split(axes)
         own, off = self._owner_and_offset(idx, {i: st[i] for i in parts})
         off += sum(idx[g] * cs[g] for g in axes)
-        rest_cols = [g for g in range(self.n) if g not in axes]
         post = None
         if own:
             view = [(ext[i], st[i]) for i in rest] + [(self.dims[g], cs[g]) for g in rest_cols]
