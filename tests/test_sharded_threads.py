@@ -209,3 +209,41 @@ def test_random_density_matrix_programs(world):
         assert max(res) < 1e-12, (dims, res)
         ran += 1
     assert ran >= 3
+
+
+# ---- the schedule bench.py --gpus N runs (layouts, LayerRunner, pipelined swap) on CPU ranks ----
+
+
+def _bench_schedule(rank, world, dist, kind, modes, cutoff):
+    import bench
+    from photon_weave_b200 import bench_sharded as bs
+
+    dims = (cutoff,) * modes
+    cls = ShardedStateVector if kind == "vec" else ShardedDensityMatrix
+    layer = bench.make_layer(modes, cutoff) if kind == "vec" else bench.make_rho_layer(modes, cutoff)
+    vaxes, sparts, shard_a, shard_b = bs._layouts(cls, dims, world, modes, layer)
+    ref = bench.preflight_input(kind, dims)
+    local = cls._own_block(dims if kind == "vec" else dims + dims, torch.from_numpy(ref.reshape(-1)), sparts, rank)
+    st = cls(dims, local, vaxes, sparts, rank, world, dist, NumpyBackend())
+    d_ops = [torch.from_numpy(np.ascontiguousarray(o)) for _, o, _ in layer]
+    runner = bs.LayerRunner(st, layer, d_ops, shard_a, shard_b, bs._apply_vec if kind == "vec" else bs._apply_rho,
+                            "pipelined")
+    piped = 0
+    for _ in range(3):
+        runner.run()
+        piped += int(runner.last_info["pipelined"])
+        for t, o, _ in layer:                      # the oracle applies the PROGRAM order
+            ref = bench.oracle_apply(kind, dims, t, ref, o)
+        err = float(np.abs(st.gather_full().numpy().reshape(ref.shape) - ref).max())
+        assert err < 1e-12, err
+    return piped, st.swaps, st.packs, tuple(shard_a), tuple(shard_b)
+
+
+@pytest.mark.parametrize("kind,world,modes,cutoff", [("vec", 2, 6, 6), ("vec", 4, 6, 6), ("vec", 8, 8, 4),
+                                                    ("rho", 2, 4, 4), ("rho", 4, 4, 4), ("rho", 8, 5, 4)])
+def test_bench_schedule_is_pipelined_and_exact(kind, world, modes, cutoff):
+    res = run_ranks(world, _bench_schedule, kind, modes, cutoff)
+    assert len(set(res)) == 1
+    piped, swaps, packs, shard_a, shard_b = res[0]
+    assert swaps == 3 and not set(shard_a) & set(shard_b)
+    assert piped >= 2          # steady state of the two alternating layouts: every swap is hidden
