@@ -276,6 +276,8 @@ class ShardedTensor:
 
     #: subsystems that may be sharded / swapped out (None = all)
     _shardable: Optional[range] = None
+    #: whether an operation may be a stack of Kraus operators (K, t, t)
+    _stacked_ok = False
 
     def __init__(self, global_dims: Sequence[int], local: torch.Tensor, vaxes: List[VAxis],
                  sparts: List[VAxis], rank: int, world: int, dist: Any, backend: Any,
@@ -399,6 +401,26 @@ class ShardedTensor:
         if self.world > 1:
             self.dist.all_reduce(torch.view_as_real(t) if t.is_complex() else t)
         return t
+
+    # ---- argument checks (the seam's error behaviour: core/adapters.py:317-327) -------------
+
+    def _n_subsystems(self) -> int:
+        return len(self.global_dims)
+
+    def _validated(self, operator: torch.Tensor, axes: Sequence[int], stacked: bool = False):
+        """(operator in the state's dtype, contiguous; axes as a tuple) or the reference's errors:
+        ValueError for bad targets, AssertionError for an operator of the wrong shape."""
+        axes = tuple(int(a) for a in axes)
+        nsub = self._n_subsystems()
+        if not axes or len(set(axes)) != len(axes) or any(a < 0 or a >= nsub for a in axes):
+            raise ValueError(f"target subsystems {axes} must be distinct indices below {nsub}")
+        t = math.prod(self.global_dims[a] for a in axes)
+        shape = tuple(operator.shape)
+        if not (shape == (t, t) or (stacked and len(shape) == 3 and shape[1:] == (t, t) and shape[0] >= 1)):
+            raise AssertionError(f"Operator shape {shape} does not match expected {(t, t)}")
+        if operator.dtype != self.local.dtype:
+            operator = operator.to(self.local.dtype)
+        return operator.contiguous(), axes
 
     # ---- axis swap ----------------------------------------------------------------------
 
@@ -594,7 +616,7 @@ class ShardedTensor:
         Falls back to the plain schedule (S0+S1, swap, S2) when the swap needs a pack pass or is
         group-wise, and to operation-by-operation application when the regrouping would break
         the program order.  ``marks``: optional list that receives (label, cuda event) pairs."""
-        ops = [(o, tuple(a)) for o, a in ops]
+        ops = [self._validated(o, a, stacked=self._stacked_ok) for o, a in ops]
         info: Dict[str, Any] = {"pipelined": False, "s0": 0, "s1": 0, "s2": 0}
         cuda = self.local.is_cuda
 
@@ -938,6 +960,7 @@ class ShardedStateVector(ShardedTensor):
     def apply_operation(self, operator: torch.Tensor, axes: Sequence[int],
                         prefer_shard: Optional[Sequence[int]] = None) -> None:
         """psi <- (operator on global subsystems ``axes``) psi; swaps axes in if needed."""
+        operator, axes = self._validated(operator, axes)
         if self.peers is not None and any(s.g in axes for s in self.sparts):
             # fused: the operator is applied while the swapped data streams in over NVLink
             positions, slots = self._plan_swap(set(axes), prefer_shard)
@@ -1033,6 +1056,11 @@ class ShardedDensityMatrix(ShardedTensor):
         super().__init__(self.dims + self.dims, local, vaxes, sparts, rank, world, dist, backend,
                          spare=spare, peers=peers, third=third)
 
+    _stacked_ok = True
+
+    def _n_subsystems(self) -> int:
+        return self.n
+
     @classmethod
     def initial_layout(cls, dims: Sequence[int], world: int):
         dims = tuple(dims)
@@ -1073,6 +1101,7 @@ class ShardedDensityMatrix(ShardedTensor):
                     prefer_shard: Optional[Sequence[int]] = None) -> None:
         """rho <- sum_k K_k rho K_k^dagger on subsystems ``axes``; ONE HBM pass per block.  Only
         the row side can be sharded, so at most one axis swap (of rows) precedes it."""
+        operators, axes = self._validated(operators, axes, stacked=True)
         self.ensure_local(axes, prefer_shard)
         self._apply_local(operators, axes)
 

@@ -247,3 +247,31 @@ def test_bench_schedule_is_pipelined_and_exact(kind, world, modes, cutoff):
     piped, swaps, packs, shard_a, shard_b = res[0]
     assert swaps == 3 and not set(shard_a) & set(shard_b)
     assert piped >= 2          # steady state of the two alternating layouts: every swap is hidden
+
+
+def _bad_arguments(rank, world, dist):
+    dims = (4, 3, 2)
+    psi = ops.random_state(24, 1)
+    st = ShardedStateVector.from_full(dims, torch.from_numpy(psi.reshape(-1)), rank, world, dist, NumpyBackend())
+    u3 = torch.from_numpy(ops.random_unitary(3, 1))
+    for bad_axes in [(), (3,), (-1,), (1, 1)]:
+        with pytest.raises(ValueError):
+            st.apply_operation(u3, bad_axes)
+    with pytest.raises(AssertionError):
+        st.apply_operation(u3, (0,))                       # 3 x 3 operator on a 4-level subsystem
+    with pytest.raises(AssertionError):
+        st.run_layer([(torch.from_numpy(ops.loss_channel(3, 0.1)), (1,))])   # Kraus stack on a vector
+    st.apply_operation(u3.to(torch.complex64), (1,))       # promoted to the state's dtype
+    ref = oad.apply_operation_vector(dims, (1,), psi, u3.numpy().astype(np.complex64).astype(np.complex128), True)
+    err = float(np.abs(st.gather_full().numpy().reshape(-1, 1) - ref).max())
+    rho = ops.random_density(24, 2)
+    sd = ShardedDensityMatrix.from_full(dims, torch.from_numpy(rho.reshape(-1)), rank, world, dist, NumpyBackend())
+    with pytest.raises(ValueError):
+        sd.apply_kraus(torch.from_numpy(ops.loss_channel(3, 0.1)), (3,))     # column subsystems are not addressable
+    with pytest.raises(AssertionError):
+        sd.apply_operation(u3, (2,))
+    return err
+
+
+def test_sharded_argument_errors_follow_the_seam():
+    assert max(run_ranks(2, _bad_arguments)) < 1e-6
