@@ -407,13 +407,17 @@ class ShardedTensor:
     def _n_subsystems(self) -> int:
         return len(self.global_dims)
 
-    def _validated(self, operator: torch.Tensor, axes: Sequence[int], stacked: bool = False):
-        """(operator in the state's dtype, contiguous; axes as a tuple) or the reference's errors:
-        ValueError for bad targets, AssertionError for an operator of the wrong shape."""
+    def _check_axes(self, axes: Sequence[int]) -> Tuple[int, ...]:
         axes = tuple(int(a) for a in axes)
         nsub = self._n_subsystems()
         if not axes or len(set(axes)) != len(axes) or any(a < 0 or a >= nsub for a in axes):
             raise ValueError(f"target subsystems {axes} must be distinct indices below {nsub}")
+        return axes
+
+    def _validated(self, operator: torch.Tensor, axes: Sequence[int], stacked: bool = False):
+        """(operator in the state's dtype, contiguous; axes as a tuple) or the reference's errors:
+        ValueError for bad targets, AssertionError for an operator of the wrong shape."""
+        axes = self._check_axes(axes)
         t = math.prod(self.global_dims[a] for a in axes)
         shape = tuple(operator.shape)
         if not (shape == (t, t) or (stacked and len(shape) == 3 and shape[1:] == (t, t) and shape[0] >= 1)):
@@ -993,6 +997,7 @@ class ShardedStateVector(ShardedTensor):
     def probs(self, axes: Sequence[int]) -> torch.Tensor:
         """Joint outcome probabilities of subsystems ``axes`` (given order), identical on every
         rank; no data movement whether or not the axes are sharded (core/kernels.py:28-41)."""
+        axes = self._check_axes(axes)
         parts, rest = self._split(axes)
         st, ext = self.local_strides(), self.local_dims
         sums = self.backend.sums_strided(self.local, 0, [(ext[i], st[i]) for i in rest],
@@ -1002,6 +1007,7 @@ class ShardedStateVector(ShardedTensor):
     def reduced(self, keep: Sequence[int], prefer_shard: Optional[Sequence[int]] = None) -> torch.Tensor:
         """Tr_rest |psi><psi| for the subsystems ``keep`` (given order), on every rank
         (state/utils/trace_out.py:17-25): local partial + one all-reduce of t^2 numbers."""
+        keep = self._check_axes(keep)
         self.ensure_local(keep, prefer_shard)
         part = self.backend.reduced_from_vec(self.local, self.local_dims, self._targets_for(keep))
         return self._all_reduce(part)
@@ -1011,6 +1017,7 @@ class ShardedStateVector(ShardedTensor):
         state over the remaining subsystems, probabilities).  Every rank draws from the same
         all-reduced probabilities with the same key, so the outcome is identical everywhere;
         the collapse happens on the ranks that own the outcome's sharded digits."""
+        axes = self._check_axes(axes)
         axes = list(axes)
         parts, rest = self._split(axes)
         self._check_respreadable([self.vaxes[i] for i in rest], axes)
@@ -1141,6 +1148,7 @@ class ShardedDensityMatrix(ShardedTensor):
     def probs(self, axes: Sequence[int]) -> torch.Tensor:
         """Joint outcome probabilities (core/kernels.py:44-59): each rank sums the diagonal
         entries of its own rows, ONE all-reduce of t numbers."""
+        axes = self._check_axes(axes)
         ds, const = self._diag()
         ext = self.local_dims
         parts, rest = self._row_split(axes)
@@ -1151,6 +1159,7 @@ class ShardedDensityMatrix(ShardedTensor):
     def trace_out(self, keep: Sequence[int], prefer_shard: Optional[Sequence[int]] = None) -> torch.Tensor:
         """Tr_rest rho for the subsystems ``keep`` (given order) on every rank
         (core/kernels.py:301-319): local partial over the block's rows + one all-reduce of t^2."""
+        keep = self._check_axes(keep)
         self.ensure_local(keep, prefer_shard)
         ds, const = self._diag()
         st, ext, cs = self.local_strides(), self.local_dims, self._col_stride()
@@ -1163,6 +1172,7 @@ class ShardedDensityMatrix(ShardedTensor):
     def measure(self, axes: Sequence[int], key) -> Tuple[int, "ShardedDensityMatrix", torch.Tensor]:
         """Projective measurement (core/kernels.py:209-227): post = rho[o,:,o,:] / (p_o + 1e-18)
         taken on the ranks that own outcome o's rows, then spread over all ranks again."""
+        axes = self._check_axes(axes)
         axes = list(axes)
         parts, rest = self._row_split(axes)
         rest_cols = [g for g in range(self.n) if g not in axes]
