@@ -75,7 +75,9 @@ int pw_set_option(const char* name, int value);
 
 /* Arithmetic-peak probe (measurement aid: the FP64 roof the dense-operator kernels are quoted
  * against).  kind 0: FP64 FMA, 1: FP64 tensor cores (mma.sync.m8n8k4),
- * 2: FP32 FMA, 3: TF32 mma.sync.m16n8k8.  Enqueues ONE register-only kernel of `iters` iterations; *flops (host) receives
+ * 2: FP32 FMA, 3: TF32 mma.sync.m16n8k8, 4..6: FP64 tensor cores with 1 / 2 / 3 FP64 adds interleaved per 6
+ * MMAs, 7: with 2 FP32 adds (the cost of the three-product complex multiply; MMA flops only are counted).
+ * Enqueues ONE register-only kernel of `iters` iterations; *flops (host) receives
  * the real flops it performs; time it with CUDA events.  `sink` is one device double. */
 int pw_probe_arith(int kind, int iters, double* sink, double* flops, void* stream);
 
