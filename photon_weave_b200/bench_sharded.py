@@ -10,8 +10,7 @@ from __future__ import annotations
 
 import json
 import os
-import math
-from typing import Any, Callable, List, Optional, Sequence
+from typing import Callable, List, Optional, Sequence
 
 import torch
 
